@@ -1,0 +1,167 @@
+"""ctypes loader for the CPU oracle (oracle/mpassit_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- may be imported from tests/, from
+__graft_entry__.smoke() and from bench.py's cpu_baseline / --impl reference legs.
+The product package (mpassit_b200/) never imports this module.
+
+PARITY UNPINNED: see the header of mpassit_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmpassit_oracle.so")
+_lib = None
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "mpassit_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_mesh_rad_to_deg.argtypes = [C.c_int64, _f64p, _f64p, _f64p, _f64p]
+        L.orc_sph_deg_to_cart.argtypes = [C.c_int64, _f64p, _f64p, _f64p]
+        L.orc_dual_triangles.argtypes = [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p]
+        L.orc_dual_triangles.restype = C.c_int
+        L.orc_nearest.argtypes = [C.c_int32, _f64p, C.c_int64, _f64p, _i32p, C.c_int]
+        L.orc_nearest.restype = C.c_int
+        L.orc_bilinear.argtypes = [C.c_int32, _f64p, C.c_int32, _i32p, C.c_int32, _i32p, C.c_int64, _f64p,
+                                   _i32p, _i32p, _f64p, C.c_int]
+        L.orc_bilinear.restype = C.c_int
+        for name, tin, tout in (("orc_apply_f32_f32", _f32p, _f32p), ("orc_apply_f32_f64", _f32p, _f64p),
+                                ("orc_apply_f64_f64", _f64p, _f64p), ("orc_apply_f64_f32", _f64p, _f32p),
+                                ("orc_apply_f32_f32_tiled", _f32p, _f32p)):
+            getattr(L, name).argtypes = [C.c_int64, _i32p, _i32p, _f64p, C.c_int32, tin, tout]
+        L.orc_rotate_winds.argtypes = [C.c_int64, C.c_int32, _f64p, _f64p, _f64p, _f64p]
+        L.orc_rotate_winds_f32.argtypes = [C.c_int64, C.c_int32, _f32p, _f32p, _f64p, _f64p]
+        for opt in ("orc_conserve_count", "orc_conserve_fill", "orc_bilinear_quadgrid", "orc_bilinear_polygon"):
+            if hasattr(L, opt):
+                pass
+        _lib = L
+    return _lib
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
+# ---------------------------------------------------------------- geometry
+def mesh_rad_to_deg(lon_rad, lat_rad):
+    lon_rad = np.ascontiguousarray(lon_rad, np.float64)
+    lat_rad = np.ascontiguousarray(lat_rad, np.float64)
+    lo = np.empty_like(lon_rad)
+    la = np.empty_like(lat_rad)
+    lib().orc_mesh_rad_to_deg(lon_rad.size, lon_rad, lat_rad, lo, la)
+    return lo, la
+
+
+def sph_deg_to_cart(lon_deg, lat_deg):
+    lon_deg = np.ascontiguousarray(lon_deg, np.float64).reshape(-1)
+    lat_deg = np.ascontiguousarray(lat_deg, np.float64).reshape(-1)
+    xyz = np.empty((lon_deg.size, 3), np.float64)
+    lib().orc_sph_deg_to_cart(lon_deg.size, lon_deg, lat_deg, xyz)
+    return xyz
+
+
+def dual_triangles(verticesOnCell, nVertices):
+    voc = np.ascontiguousarray(verticesOnCell, np.int32)
+    tri = np.empty((nVertices, 3), np.int32)
+    rc = lib().orc_dual_triangles(voc.shape[0], nVertices, voc.shape[1], voc, tri)
+    if rc != 0:
+        raise ValueError(f"orc_dual_triangles rc={rc}")
+    return tri
+
+
+# ---------------------------------------------------------------- weights
+def nearest(src_xyz, dst_xyz, brute=False):
+    src_xyz = np.ascontiguousarray(src_xyz, np.float64)
+    dst_xyz = np.ascontiguousarray(dst_xyz, np.float64)
+    idx = np.empty(dst_xyz.shape[0], np.int32)
+    rc = lib().orc_nearest(src_xyz.shape[0], src_xyz, dst_xyz.shape[0], dst_xyz, idx, int(brute))
+    if rc != 0:
+        raise ValueError(f"orc_nearest rc={rc}")
+    return idx
+
+
+def bilinear(cell_xyz, tri, verticesOnCell, dst_xyz, brute=False):
+    cell_xyz = np.ascontiguousarray(cell_xyz, np.float64)
+    tri = np.ascontiguousarray(tri, np.int32)
+    voc = np.ascontiguousarray(verticesOnCell, np.int32)
+    dst_xyz = np.ascontiguousarray(dst_xyz, np.float64)
+    n = dst_xyz.shape[0]
+    elem = np.empty(n, np.int32)
+    col = np.empty((n, 3), np.int32)
+    w = np.empty((n, 3), np.float64)
+    rc = lib().orc_bilinear(cell_xyz.shape[0], cell_xyz, tri.shape[0], tri, voc.shape[1], voc, n, dst_xyz,
+                            elem, col, w, int(brute))
+    if rc != 0:
+        raise ValueError(f"orc_bilinear rc={rc}")
+    return elem, col, w
+
+
+def ell_to_csr(mask, col, w):
+    """Fixed-width rows (col [n][k], w [n][k]) + mapped mask -> CSR (rowptr, col, w)."""
+    n, k = col.shape
+    cnt = np.where(mask, k, 0).astype(np.int64)
+    rowptr = np.zeros(n + 1, np.int32)
+    np.cumsum(cnt, out=rowptr[1:])
+    return rowptr, np.ascontiguousarray(col[mask].reshape(-1), np.int32), \
+        np.ascontiguousarray(w[mask].reshape(-1), np.float64)
+
+
+def nearest_to_csr(idx):
+    n = idx.shape[0]
+    return np.arange(n + 1, dtype=np.int32), np.ascontiguousarray(idx, np.int32), np.ones(n, np.float64)
+
+
+# ---------------------------------------------------------------- apply
+def apply(rowptr, col, w, src, out_dtype=np.float32, tiled=False):
+    """src [nSrc][nlev] (or [nSrc]) -> dst [nlev][nDst]."""
+    src = np.ascontiguousarray(src)
+    if src.ndim == 1:
+        src = src.reshape(-1, 1)
+    nlev = src.shape[1]
+    nDst = rowptr.shape[0] - 1
+    dst = np.empty((nlev, nDst), out_dtype)
+    key = ("f32" if src.dtype == np.float32 else "f64") + "_" + ("f32" if dst.dtype == np.float32 else "f64")
+    name = "orc_apply_" + key + ("_tiled" if tiled and key == "f32_f32" else "")
+    getattr(lib(), name)(nDst, np.ascontiguousarray(rowptr, np.int32), np.ascontiguousarray(col, np.int32),
+                         np.ascontiguousarray(w, np.float64), nlev, src, dst)
+    return dst
+
+
+def rotate_winds(u, v, cosa, sina):
+    """In place on [nlev][n] arrays (fp64 or fp32)."""
+    n = cosa.size
+    nlev = u.size // n
+    cosa = np.ascontiguousarray(cosa, np.float64).reshape(-1)
+    sina = np.ascontiguousarray(sina, np.float64).reshape(-1)
+    if u.dtype == np.float64:
+        lib().orc_rotate_winds(n, nlev, u, v, cosa, sina)
+    else:
+        lib().orc_rotate_winds_f32(n, nlev, u, v, cosa, sina)
+    return u, v
