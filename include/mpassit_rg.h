@@ -1,0 +1,156 @@
+/*
+ * mpassit_rg.h -- C ABI of libmpassit_rg.so, the B200 (sm_100a) regridding engine
+ * that stands in for the ESMF calls on MPASSIT's interpolation path.
+ *
+ * Plain C: pointers, sizes and opaque handles only.  Every entry point returns
+ * an int rc, 0 = success (mirrors ESMF_SUCCESS); nonzero = failure, message via
+ * mprg_last_error().  The library never aborts or throws; the Fortran host keeps
+ * its `if (rc /= 0) call error_handler(msg, rc)` pattern
+ * (/root/reference/utils.F90:16-33, e.g. interp.F90:130-131).
+ *
+ * All calls on one context are collective in the reference's sense: every rank
+ * (one process per GPU) makes the same calls in the same order
+ * (interp.F90 has no rank-conditional regrid call).  A context is not
+ * thread-safe; work is stream-ordered on the context's stream.
+ *
+ * Index conventions: MPAS ids are 1-based in verticesOnCell with 0 = unused
+ * slot (model_grid.F90:448,479); everything this library exports (CSR) is
+ * 0-based.  Target arrays are C order [nj][ni] == Fortran (i,j), i fastest.
+ *
+ * Each declaration names the reference interface it replaces (file:line under
+ * /root/reference).
+ */
+#ifndef MPASSIT_RG_H
+#define MPASSIT_RG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mprg_ctx mprg_ctx;     /* one per rank / GPU */
+typedef struct mprg_route mprg_route; /* weights + schedule == type(esmf_routehandle), interp.F90:86,192 */
+
+/* regridmethod, interp.F90:119,204 (BILINEAR) :370 (CONSERVE) :420 (NEAREST_STOD) */
+enum { MPRG_BILINEAR = 0, MPRG_CONSERVE = 1, MPRG_NEAREST_STOD = 2 };
+/* where the source field lives: ESMF_MESHLOC_ELEMENT (input_data.F90:970-1132),
+ * ESMF_MESHLOC_NODE (vorticity bundle, interp.F90:353), or the target grid's
+ * CENTER stagger (u/v_target_grid_nostag, interp.F90:298,316) */
+enum { MPRG_SRC_MESH_ELEMENT = 0, MPRG_SRC_MESH_NODE = 1, MPRG_SRC_GRID_CENTER = 2 };
+/* ESMF_STAGGERLOC_* of the destination, interp.F90:477-520, model_grid.F90:707-728 */
+enum { MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3 };
+enum { MPRG_F32 = 0, MPRG_F64 = 1 };
+enum { MPRG_HOST = 0, MPRG_DEVICE = 1 };
+/* per-field fused epilogues (WRF-compat post-ops the reference runs serially on
+ * PET 0, write_data.F90:1339-1345 and :1406-1425) */
+enum { MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2 };
+
+/* ---- lifetime: replaces ESMF_Initialize / ESMF_VMGet / ESMF_finalize
+ *      (mpassit.F90:84-94,140).  `device` is the CUDA ordinal; rank/nranks give
+ *      the target row-slab this context owns (para_range, model_grid.F90:2428). */
+int mprg_init(int device, int rank, int nranks, mprg_ctx **out);
+int mprg_finalize(mprg_ctx *ctx);
+const char *mprg_last_error(const mprg_ctx *ctx); /* ctx may be NULL: last init error */
+const char *mprg_version(void);
+/* run all work of this context on an existing CUDA stream (cudaStream_t passed
+ * as void*); NULL restores the context's own stream */
+int mprg_set_stream(mprg_ctx *ctx, void *cuda_stream);
+int mprg_synchronize(mprg_ctx *ctx);
+
+/* pinned host memory for callers that want full-speed H2D/D2H (optional) */
+int mprg_host_alloc(mprg_ctx *ctx, size_t bytes, void **ptr);
+int mprg_host_free(mprg_ctx *ctx, void *ptr);
+
+/* ---- source mesh: replaces ESMF_MeshCreate, model_grid.F90:488-497.
+ *      Takes the arrays exactly as read from the MPAS grid file
+ *      (model_grid.F90:354-417): radians, verticesOnCell [nCells][maxEdges]
+ *      (== Fortran (maxEdges,nCells)).  The engine applies the reference's
+ *      *180/PI and >180 -> -360 wrap (model_grid.F90:450-454,464-468) itself. */
+int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges,
+                  const double *lonCell_rad, const double *latCell_rad,
+                  const double *lonVertex_rad, const double *latVertex_rad,
+                  const int32_t *verticesOnCell);
+
+/* ---- target grid: replaces ESMF_GridCreate* + GridAddCoord/GetCoord fills,
+ *      model_grid.F90:684-728, 949-1038.  One call per stagger; lon/lat in
+ *      degrees, full grid [nj][ni] on every rank.  CENTER is ni x nj =
+ *      i_target x j_target, EDGE1 (ni+1) x nj, EDGE2 ni x (nj+1),
+ *      CORNER (ni+1) x (nj+1)  (interp.F90:477-520). */
+int mprg_set_target(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj,
+                    const double *lon_deg, const double *lat_deg);
+/* rows [j0, j1) of `stagger` owned by this rank (0-based; para_range) */
+int mprg_get_slab(const mprg_ctx *ctx, int stagger, int32_t *j0, int32_t *j1);
+
+/* ---- weights: replaces ESMF_FieldRegridStore / ESMF_FieldBundleRegridStore
+ *      (interp.F90:123,207,226,241,259,277,298,316,334,353,372,394,421,437)
+ *      with srcTermProcessing=1, unmappedaction=IGNORE, other arguments default.
+ *      Routes are memoised per (method, src_loc, dst_stagger): the reference's 12
+ *      Store calls hit 4-6 distinct matrices.  The returned handle is reference
+ *      counted; pair every store with one mprg_release. */
+int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_route **rh);
+/* replaces ESMF_FieldBundleRegridRelease, interp.F90:450-463 */
+int mprg_release(mprg_ctx *ctx, mprg_route *rh);
+/* drop every memoised route (forces the next store to rebuild) */
+int mprg_clear_routes(mprg_ctx *ctx);
+
+/* sizes of this rank's part of the route: destination points (slab), stored
+ * weights, unmapped destination points, source entities (cells/nodes/points) */
+int mprg_route_info(const mprg_route *rh, int64_t *nDst, int64_t *nnz, int64_t *nUnmapped, int64_t *nSrc);
+/* test / weight-cache hooks: CSR of this rank's slab, 0-based, host buffers
+ * rowptr[nDst+1], col[nnz], w[nnz] */
+int mprg_route_export_csr(mprg_ctx *ctx, const mprg_route *rh, int32_t *rowptr, int32_t *col, double *w);
+int mprg_route_import_csr(mprg_ctx *ctx, int64_t nSrc, int64_t nDst, const int32_t *rowptr,
+                          const int32_t *col, const double *w, mprg_route **rh);
+
+/* ---- apply: replaces ESMF_FieldRegrid / ESMF_FieldBundleRegrid
+ *      (interp.F90:134,219,236,251,268,286,307,325,344,363,382,404,431,443).
+ *      nfields stacked fields in ONE batched launch sequence.
+ *      src[f]: [nSrc][nlev[f]] level-fastest == MPAS file order
+ *              (input_data.F90:630,645); for MPRG_SRC_GRID_CENTER the source is a
+ *              previous output, [nlev[f]][nj][ni] (level-slowest).
+ *      dst[f]: this rank's slab [nlev[f]][nj_slab][ni] (the full grid on 1 rank).
+ *      Unmapped destination points are written 0 (zeroregion=TOTAL default).
+ *      src_mem / dst_mem: MPRG_HOST buffers are copied through the engine's
+ *      pipelined staging; MPRG_DEVICE pointers are used in place. */
+int mprg_apply(mprg_ctx *ctx, mprg_route *rh, int32_t nfields,
+               const void *const *src, const int32_t *nlev, int src_dtype, int src_mem,
+               void *const *dst, int dst_dtype, int dst_mem);
+/* same, with one fused epilogue per field: dst = op(dst, epi_arg[f])
+ * (T-300: write_data.F90:1339-1345; PHB=zgrid*9.81: write_data.F90:1417) */
+int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields,
+                  const void *const *src, const int32_t *nlev, int src_dtype, int src_mem,
+                  void *const *dst, int dst_dtype, int dst_mem,
+                  const int32_t *epi_op, const double *epi_arg);
+
+/* ---- wind rotation: replaces rotate_winds_cgrid, interp.F90:689-749.
+ *      cosa/sina: CENTER stagger, full grid [nj][ni], fp64 (cosa_target_grid /
+ *      sina_target_grid, model_grid.F90:1113-1185).  u, v: this rank's CENTER
+ *      slab [nlev][nj_slab][ni], rotated in place. */
+int mprg_set_rotation(mprg_ctx *ctx, const double *cosa, const double *sina);
+int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem);
+
+/* ---- gather: replaces ESMF_FieldGather(rootPet=0), write_data.F90:1006-1453.
+ *      Collects every rank's slab of a [nlev][nj][ni] field on `root`.
+ *      Device buffers; NCCL over NVLink.  With nranks == 1 it is a device copy.
+ *      mprg_comm_id / mprg_comm_init bootstrap the communicator: rank 0 calls
+ *      mprg_comm_id, the host program broadcasts the 128 bytes by whatever
+ *      transport it already has (MPI_Bcast in the Fortran host), then every
+ *      rank calls mprg_comm_init. */
+int mprg_comm_id(mprg_ctx *ctx, void *id128);
+int mprg_comm_init(mprg_ctx *ctx, const void *id128);
+int mprg_gather(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype,
+                const void *slab_dev, int root, void *full_dev);
+
+/* ---- instrumentation */
+/* number of engine kernels launched on this context since init */
+int64_t mprg_kernel_launches(const mprg_ctx *ctx);
+/* device milliseconds of the most recent store / apply (CUDA events on the
+ * context's stream) */
+double mprg_last_ms(const mprg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPASSIT_RG_H */

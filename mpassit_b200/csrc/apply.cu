@@ -1,0 +1,362 @@
+// apply.cu -- batched sparse-weight application ("FieldBundleRegrid"):
+//     dst[f][lev][t] = sum_k W[t][k] * src[f][col[t][k]][lev]      (0 for empty rows)
+// for every stacked field f and level lev, over this rank's destination slab.
+// Replaces ESMF_FieldRegrid / ESMF_FieldBundleRegrid, interp.F90:134,219,236,251,
+// 268,286,307,325,344,363,382,404,431,443.
+//
+// Memory-bound irregular SpMM (no tensor cores: < 1 flop/byte).  Three kernels:
+//   k_apply_cols    3-D fields, source level-fastest [cell][nlev] (MPAS file order):
+//                   lanes run along levels so every gathered source column is one
+//                   contiguous 128..256-byte request; the finished 32-target x
+//                   64-level tile is transposed through shared memory so each level
+//                   row leaves as one coalesced 128-byte store into [lev][j][i].
+//   k_apply_flat    2-D fields (nlev == 1): lanes run along targets, the row's
+//                   (col, w) stay in registers across the stacked fields.
+//   k_apply_planes  source is itself a [lev][j][i] grid field (centre -> edge
+//                   staggering, interp.F90:298,316): lanes along targets per level.
+// Grid order is (tiles fastest, field-chunks slowest) so one chunk's source
+// columns are swept once while they are L2-resident; outputs use streaming
+// stores so they do not evict them.
+#include "common.cuh"
+
+namespace mprg {
+
+constexpr int kTile = 32;        // targets per CTA tile
+constexpr int kLevChunk = 64;    // levels per pass through shared memory
+constexpr int kCsrCap = 512;     // CSR entries cached per tile (falls back to global beyond)
+constexpr int kFieldsPerCta = 4; // stacked fields handled by one CTA for one tile
+constexpr int kThreads = 256;
+
+struct FieldDev {
+    const void *src;
+    void *dst;
+    int32_t nlev;
+    int32_t epi_op;
+    double epi_arg;
+};
+
+template <typename TW>
+struct ApplyArgs {
+    const int32_t *rowptr;
+    const int32_t *col;
+    const TW *w;
+    int64_t nDst;
+    const FieldDev *fields;
+    int32_t nfields;
+    int64_t srcPlane;  // k_apply_planes only
+};
+
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
+
+template <typename TACC>
+__device__ __forceinline__ TACC epilogue(TACC v, int op, double arg) {
+    if (op == MPRG_EPI_ADD) return v + (TACC)arg;
+    if (op == MPRG_EPI_MUL) return v * (TACC)arg;
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// 3-D fields
+// ---------------------------------------------------------------------------
+template <typename TIN, typename TOUT, typename TACC, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+k_apply_cols(ApplyArgs<TACC> a) {
+    __shared__ int32_t s_rowptr[kTile + 1];
+    __shared__ int32_t s_col[kCsrCap];
+    __shared__ TACC s_w[kCsrCap];
+    __shared__ TOUT s_out[2][kLevChunk][kTile + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * kTile;
+    const int ntile = (int)min((int64_t)kTile, a.nDst - t0);
+
+    if (tid <= kTile) s_rowptr[tid] = a.rowptr[min(t0 + tid, a.nDst)];
+    __syncthreads();
+    const int base = s_rowptr[0];
+    const int cnt = s_rowptr[ntile] - base;
+    const bool cached = cnt <= kCsrCap;
+    if (cached) {
+        for (int k = tid; k < cnt; k += kThreads) {
+            s_col[k] = __ldg(a.col + base + k);
+            s_w[k] = __ldg(a.w + base + k);
+        }
+    }
+    __syncthreads();
+
+    const int f0 = blockIdx.y * kFieldsPerCta;
+    const int f1 = min(f0 + kFieldsPerCta, a.nfields);
+    int buf = 0;
+    for (int f = f0; f < f1; ++f) {
+        const FieldDev fd = a.fields[f];
+        const TIN *__restrict__ src = (const TIN *)fd.src;
+        TOUT *__restrict__ dst = (TOUT *)fd.dst;
+        const int nlev = fd.nlev;
+        for (int L0 = 0; L0 < nlev; L0 += kLevChunk, buf ^= 1) {
+            const int Ln = min(kLevChunk, nlev - L0);
+            // ---- phase A: gather + reduce, lanes along levels ----------------
+            if (VEC) {
+                // half-warp per target, 4 consecutive levels per lane (16-byte loads)
+                const int l16 = lane & 15, hw = lane >> 4;
+                const bool act = 4 * l16 < Ln;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int t = warp * 4 + it * 2 + hw;
+                    TACC acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+                    if (t < ntile && act) {
+                        const int b = s_rowptr[t] - base, e = s_rowptr[t + 1] - base;
+                        for (int k = b; k < e; ++k) {
+                            const int c = cached ? s_col[k] : __ldg(a.col + base + k);
+                            const TACC wt = cached ? s_w[k] : __ldg(a.w + base + k);
+                            const TIN *p = src + (size_t)c * nlev + L0 + 4 * l16;
+                            if (sizeof(TIN) == 4) {
+                                const float4 v = __ldg((const float4 *)p);
+                                acc0 += wt * (TACC)v.x; acc1 += wt * (TACC)v.y;
+                                acc2 += wt * (TACC)v.z; acc3 += wt * (TACC)v.w;
+                            } else {
+                                const double2 v0 = __ldg((const double2 *)p);
+                                const double2 v1 = __ldg((const double2 *)p + 1);
+                                acc0 += wt * (TACC)v0.x; acc1 += wt * (TACC)v0.y;
+                                acc2 += wt * (TACC)v1.x; acc3 += wt * (TACC)v1.y;
+                            }
+                        }
+                    }
+                    if (t < ntile && act) {
+                        s_out[buf][4 * l16 + 0][t] = (TOUT)epilogue(acc0, fd.epi_op, fd.epi_arg);
+                        s_out[buf][4 * l16 + 1][t] = (TOUT)epilogue(acc1, fd.epi_op, fd.epi_arg);
+                        s_out[buf][4 * l16 + 2][t] = (TOUT)epilogue(acc2, fd.epi_op, fd.epi_arg);
+                        s_out[buf][4 * l16 + 3][t] = (TOUT)epilogue(acc3, fd.epi_op, fd.epi_arg);
+                    }
+                }
+            } else {
+                // warp per target, levels lane and lane+32; two targets in flight
+                const bool a0 = lane < Ln, a1 = lane + 32 < Ln;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int tA = warp * 4 + it * 2, tB = tA + 1;
+                    TACC accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
+                    int bA = 0, eA = 0, bB = 0, eB = 0;
+                    if (tA < ntile) { bA = s_rowptr[tA] - base; eA = s_rowptr[tA + 1] - base; }
+                    if (tB < ntile) { bB = s_rowptr[tB] - base; eB = s_rowptr[tB + 1] - base; }
+                    const int nk = max(eA - bA, eB - bB);
+                    for (int k = 0; k < nk; ++k) {
+                        const bool hA = bA + k < eA, hB = bB + k < eB;
+                        int cA = 0, cB = 0;
+                        TACC wA = 0, wB = 0;
+                        if (hA) { cA = cached ? s_col[bA + k] : __ldg(a.col + base + bA + k);
+                                  wA = cached ? s_w[bA + k] : __ldg(a.w + base + bA + k); }
+                        if (hB) { cB = cached ? s_col[bB + k] : __ldg(a.col + base + bB + k);
+                                  wB = cached ? s_w[bB + k] : __ldg(a.w + base + bB + k); }
+                        const TIN *pA = src + (size_t)cA * nlev + L0 + lane;
+                        const TIN *pB = src + (size_t)cB * nlev + L0 + lane;
+                        TIN xA0 = 0, xA1 = 0, xB0 = 0, xB1 = 0;
+                        if (hA && a0) xA0 = __ldg(pA);
+                        if (hA && a1) xA1 = __ldg(pA + 32);
+                        if (hB && a0) xB0 = __ldg(pB);
+                        if (hB && a1) xB1 = __ldg(pB + 32);
+                        accA0 += wA * (TACC)xA0; accA1 += wA * (TACC)xA1;
+                        accB0 += wB * (TACC)xB0; accB1 += wB * (TACC)xB1;
+                    }
+                    if (tA < ntile) {
+                        if (a0) s_out[buf][lane][tA] = (TOUT)epilogue(accA0, fd.epi_op, fd.epi_arg);
+                        if (a1) s_out[buf][lane + 32][tA] = (TOUT)epilogue(accA1, fd.epi_op, fd.epi_arg);
+                    }
+                    if (tB < ntile) {
+                        if (a0) s_out[buf][lane][tB] = (TOUT)epilogue(accB0, fd.epi_op, fd.epi_arg);
+                        if (a1) s_out[buf][lane + 32][tB] = (TOUT)epilogue(accB1, fd.epi_op, fd.epi_arg);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase B: transposed, coalesced streaming store --------------
+            if (lane < ntile) {
+                for (int lev = warp; lev < Ln; lev += kThreads / 32)
+                    st_stream(dst + (size_t)(L0 + lev) * a.nDst + t0 + lane, s_out[buf][lev][lane]);
+            }
+            // s_out is double buffered: the next pass writes the other buffer, and the
+            // barrier of that pass orders this pass's reads before the buffer is reused.
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 2-D fields (nlev == 1): thread per target, row kept in registers
+// ---------------------------------------------------------------------------
+constexpr int kFlatRow = 4;  // row entries held in registers; longer rows stream from global
+
+template <typename TIN, typename TOUT, typename TACC>
+__global__ void __launch_bounds__(256)
+k_apply_flat(ApplyArgs<TACC> a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nDst) return;
+    const int b = __ldg(a.rowptr + t), e = __ldg(a.rowptr + t + 1);
+    int c[kFlatRow];
+    TACC w[kFlatRow];
+#pragma unroll
+    for (int k = 0; k < kFlatRow; ++k) {
+        const bool h = b + k < e;
+        c[k] = h ? __ldg(a.col + b + k) : 0;
+        w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
+    }
+    for (int f = 0; f < a.nfields; ++f) {
+        const FieldDev fd = a.fields[f];
+        const TIN *__restrict__ src = (const TIN *)fd.src;
+        TACC acc = 0;
+#pragma unroll
+        for (int k = 0; k < kFlatRow; ++k)
+            if (b + k < e) acc += w[k] * (TACC)__ldg(src + c[k]);
+        for (int k = b + kFlatRow; k < e; ++k) acc += __ldg(a.w + k) * (TACC)__ldg(src + __ldg(a.col + k));
+        st_stream((TOUT *)fd.dst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// source is a level-slowest grid field [lev][srcPlane] (centre -> edge stagger)
+// ---------------------------------------------------------------------------
+template <typename TIN, typename TOUT, typename TACC>
+__global__ void __launch_bounds__(256)
+k_apply_planes(ApplyArgs<TACC> a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nDst) return;
+    const int b = __ldg(a.rowptr + t), e = __ldg(a.rowptr + t + 1);
+    int c[kFlatRow];
+    TACC w[kFlatRow];
+#pragma unroll
+    for (int k = 0; k < kFlatRow; ++k) {
+        const bool h = b + k < e;
+        c[k] = h ? __ldg(a.col + b + k) : 0;
+        w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
+    }
+    const FieldDev fd = a.fields[blockIdx.y];
+    const TIN *__restrict__ src = (const TIN *)fd.src;
+    TOUT *__restrict__ dst = (TOUT *)fd.dst;
+    for (int lev = 0; lev < fd.nlev; ++lev) {
+        const TIN *pl = src + (size_t)lev * a.srcPlane;
+        TACC acc = 0;
+#pragma unroll
+        for (int k = 0; k < kFlatRow; ++k)
+            if (b + k < e) acc += w[k] * (TACC)__ldg(pl + c[k]);
+        for (int k = b + kFlatRow; k < e; ++k) acc += __ldg(a.w + k) * (TACC)__ldg(pl + __ldg(a.col + k));
+        st_stream(dst + (size_t)lev * a.nDst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------
+static bool acc_fp32_requested() {
+    const char *e = getenv("MPASSIT_GPU_ACC");
+    return e && (!strcmp(e, "f32") || !strcmp(e, "fp32"));
+}
+
+template <typename TIN, typename TOUT, typename TACC>
+static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols_vec,
+                       const std::vector<FieldDev> &cols_sca, const std::vector<FieldDev> &flat,
+                       const std::vector<FieldDev> &planes) {
+    const size_t total = cols_vec.size() + cols_sca.size() + flat.size() + planes.size();
+    if (total == 0 || r->nDst == 0) return;
+    ctx->scratch.ensure(total * sizeof(FieldDev));
+    std::vector<FieldDev> all;
+    all.reserve(total);
+    all.insert(all.end(), cols_vec.begin(), cols_vec.end());
+    all.insert(all.end(), cols_sca.begin(), cols_sca.end());
+    all.insert(all.end(), flat.begin(), flat.end());
+    all.insert(all.end(), planes.begin(), planes.end());
+    MPRG_CUDA(cudaMemcpyAsync(ctx->scratch.p, all.data(), total * sizeof(FieldDev), cudaMemcpyHostToDevice,
+                              ctx->stream));
+    const FieldDev *dev = (const FieldDev *)ctx->scratch.p;
+    ApplyArgs<TACC> a;
+    a.rowptr = r->rowptr.p;
+    a.col = r->col.p;
+    if (sizeof(TACC) == 8) a.w = (const TACC *)r->w.p; else a.w = (const TACC *)r->w32.p;
+    a.nDst = r->nDst;
+    a.srcPlane = r->srcPlane;
+    const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
+    if (!cols_vec.empty()) {
+        a.fields = dev; a.nfields = (int)cols_vec.size();
+        dim3 g(tiles, (unsigned)((cols_vec.size() + kFieldsPerCta - 1) / kFieldsPerCta));
+        k_apply_cols<TIN, TOUT, TACC, true><<<g, kThreads, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    if (!cols_sca.empty()) {
+        a.fields = dev + cols_vec.size(); a.nfields = (int)cols_sca.size();
+        dim3 g(tiles, (unsigned)((cols_sca.size() + kFieldsPerCta - 1) / kFieldsPerCta));
+        k_apply_cols<TIN, TOUT, TACC, false><<<g, kThreads, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    if (!flat.empty()) {
+        a.fields = dev + cols_vec.size() + cols_sca.size(); a.nfields = (int)flat.size();
+        k_apply_flat<TIN, TOUT, TACC><<<(unsigned)((r->nDst + 255) / 256), 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    if (!planes.empty()) {
+        a.fields = dev + cols_vec.size() + cols_sca.size() + flat.size(); a.nfields = (int)planes.size();
+        dim3 g((unsigned)((r->nDst + 255) / 256), (unsigned)planes.size());
+        k_apply_planes<TIN, TOUT, TACC><<<g, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    MPRG_CUDA(cudaGetLastError());
+}
+
+void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
+                  int dst_dtype) {
+    std::vector<FieldDev> cols_vec, cols_sca, flat, planes;
+    const size_t in_sz = src_dtype == MPRG_F32 ? 4 : 8;
+    for (int f = 0; f < nfields; ++f) {
+        if (fields[f].nlev <= 0) fail(31, "mprg_apply: field %d has nlev %d", f, fields[f].nlev);
+        if (!fields[f].src || !fields[f].dst) fail(32, "mprg_apply: field %d has a null buffer", f);
+        FieldDev d{fields[f].src, fields[f].dst, fields[f].nlev, fields[f].epi_op, fields[f].epi_arg};
+        if (r->srcLevelSlowest) planes.push_back(d);
+        else if (d.nlev == 1) flat.push_back(d);
+        else if ((d.nlev * in_sz) % 16 == 0 && ((uintptr_t)d.src % 16) == 0) cols_vec.push_back(d);
+        else cols_sca.push_back(d);
+    }
+    const bool f32acc = acc_fp32_requested() && src_dtype == MPRG_F32 && dst_dtype == MPRG_F32;
+    if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F32) {
+        if (f32acc) launch_all<float, float, float>(ctx, r, cols_vec, cols_sca, flat, planes);
+        else launch_all<float, float, double>(ctx, r, cols_vec, cols_sca, flat, planes);
+    } else if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F64) {
+        launch_all<float, double, double>(ctx, r, cols_vec, cols_sca, flat, planes);
+    } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F32) {
+        launch_all<double, float, double>(ctx, r, cols_vec, cols_sca, flat, planes);
+    } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F64) {
+        launch_all<double, double, double>(ctx, r, cols_vec, cols_sca, flat, planes);
+    } else {
+        fail(33, "mprg_apply: bad dtype %d/%d", src_dtype, dst_dtype);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// rotate_winds_cgrid, interp.F90:689-749 (v' uses the already rotated u')
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_rotate(T *__restrict__ u, T *__restrict__ v, const double *__restrict__ cosa,
+                         const double *__restrict__ sina, int64_t n, int32_t nlev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ca = cosa[i], sa = sina[i];
+    const double tana = sa / ca;
+    const double den = ca + sa * tana;
+    for (int l = blockIdx.y; l < nlev; l += gridDim.y) {
+        const size_t o = (size_t)l * n + i;
+        double uu = (double)u[o], vv = (double)v[o];
+        uu = (uu + vv * tana) / den;
+        vv = (vv - uu * sa) / ca;
+        u[o] = (T)uu;
+        v[o] = (T)vv;
+    }
+}
+
+void rotate_device(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype) {
+    if (!ctx->haveRot) fail(41, "mprg_rotate_winds: mprg_set_rotation was not called");
+    const Target &tg = ctx->target[MPRG_CENTER];
+    const int64_t n = tg.nSlab();
+    if (n == 0 || nlev <= 0) return;
+    dim3 g((unsigned)((n + 255) / 256), (unsigned)min(nlev, 64));
+    if (dtype == MPRG_F32) k_rotate<float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, ctx->cosa.p, ctx->sina.p, n, nlev);
+    else k_rotate<double><<<g, 256, 0, ctx->stream>>>((double *)u, (double *)v, ctx->cosa.p, ctx->sina.p, n, nlev);
+    ctx->launches++;
+    MPRG_CUDA(cudaGetLastError());
+}
+
+}  // namespace mprg

@@ -1,0 +1,434 @@
+// capi.cu -- extern "C" entry points declared in include/mpassit_rg.h.
+// No exception crosses the boundary: every entry returns an rc and records a
+// message retrievable with mprg_last_error().
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace mprg;
+
+static std::string g_init_error;
+
+#define MPRG_ENTER(ctx)                                     \
+    if (!(ctx)) return 1;                                   \
+    try {                                                   \
+        MPRG_CUDA(cudaSetDevice((ctx)->device));
+
+#define MPRG_LEAVE(ctx)                                     \
+        return 0;                                           \
+    } catch (const Error &e) {                              \
+        (ctx)->err = e.msg;                                 \
+        return e.rc ? e.rc : 1;                             \
+    } catch (const std::exception &e) {                     \
+        (ctx)->err = e.what();                              \
+        return 2;                                           \
+    } catch (...) {                                         \
+        (ctx)->err = "unknown error";                       \
+        return 3;                                           \
+    }
+
+extern "C" {
+
+const char *mprg_version(void) { return "mpassit-rg 0.1 (sm_100a)"; }
+
+int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
+    if (!out) return 1;
+    *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) { g_init_error = "mprg_init: bad rank/nranks"; return 4; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        // no CPU fallback: the engine is CUDA only
+        g_init_error = std::string("mprg_init: no CUDA device (") + cudaGetErrorString(e) + ")";
+        return 5;
+    }
+    if (device < 0 || device >= ndev) { g_init_error = "mprg_init: bad device ordinal"; return 6; }
+    mprg_ctx *c = new mprg_ctx();
+    c->device = device; c->rank = rank; c->nranks = nranks;
+    try {
+        MPRG_CUDA(cudaSetDevice(device));
+        MPRG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        MPRG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        MPRG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        MPRG_CUDA(cudaEventCreate(&c->ev0));
+        MPRG_CUDA(cudaEventCreate(&c->ev1));
+        for (int i = 0; i < 2; ++i) {
+            MPRG_CUDA(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
+            MPRG_CUDA(cudaEventCreateWithFlags(&c->evK[i], cudaEventDisableTiming));
+            MPRG_CUDA(cudaEventCreateWithFlags(&c->evOut[i], cudaEventDisableTiming));
+        }
+    } catch (const Error &er) {
+        g_init_error = er.msg;
+        delete c;
+        return er.rc;
+    }
+    *out = c;
+    return 0;
+}
+
+int mprg_finalize(mprg_ctx *ctx) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : ctx->routes) delete kv.second;
+    for (auto *r : ctx->imported) delete r;
+    ctx->routes.clear();
+    ctx->imported.clear();
+    mprg::comm_destroy(ctx);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->evIn[i]) cudaEventDestroy(ctx->evIn[i]);
+        if (ctx->evK[i]) cudaEventDestroy(ctx->evK[i]);
+        if (ctx->evOut[i]) cudaEventDestroy(ctx->evOut[i]);
+    }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    delete ctx;
+    return 0;
+}
+
+const char *mprg_last_error(const mprg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int mprg_set_stream(mprg_ctx *ctx, void *cuda_stream) {
+    MPRG_ENTER(ctx)
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_synchronize(mprg_ctx *ctx) {
+    MPRG_ENTER(ctx)
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_host_alloc(mprg_ctx *ctx, size_t bytes, void **ptr) {
+    MPRG_ENTER(ctx)
+    if (!ptr) fail(1, "mprg_host_alloc: null out pointer");
+    MPRG_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_host_free(mprg_ctx *ctx, void *ptr) {
+    MPRG_ENTER(ctx)
+    if (ptr) MPRG_CUDA(cudaFreeHost(ptr));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonCell_rad,
+                  const double *latCell_rad, const double *lonVertex_rad, const double *latVertex_rad,
+                  const int32_t *verticesOnCell) {
+    MPRG_ENTER(ctx)
+    mesh_set(ctx, nCells, nVertices, maxEdges, lonCell_rad, latCell_rad, lonVertex_rad, latVertex_rad,
+             verticesOnCell);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_set_target(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const double *lon_deg,
+                    const double *lat_deg) {
+    MPRG_ENTER(ctx)
+    target_set(ctx, stagger, ni, nj, lon_deg, lat_deg);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_get_slab(const mprg_ctx *ctx, int stagger, int32_t *j0, int32_t *j1) {
+    if (!ctx || stagger < 0 || stagger > 3 || !ctx->target[stagger].set) return 1;
+    if (j0) *j0 = ctx->target[stagger].j0;
+    if (j1) *j1 = ctx->target[stagger].j1;
+    return 0;
+}
+
+int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_route **rh) {
+    MPRG_ENTER(ctx)
+    if (!rh) fail(1, "mprg_store: null route pointer");
+    *rh = nullptr;
+    if (dst_stagger < 0 || dst_stagger > 3) fail(51, "mprg_store: bad destination stagger %d", dst_stagger);
+    if (!ctx->target[dst_stagger].set) fail(52, "mprg_store: target stagger %d not set", dst_stagger);
+    if (src_loc != MPRG_SRC_GRID_CENTER && ctx->mesh.nCells == 0) fail(53, "mprg_store: mesh not set");
+    auto key = std::make_tuple(method, src_loc, dst_stagger);
+    auto it = ctx->routes.find(key);
+    if (it != ctx->routes.end()) {
+        it->second->refcount++;
+        *rh = it->second;
+        ctx->last_ms = 0.0;
+        return 0;
+    }
+    std::unique_ptr<mprg_route> r(new mprg_route());
+    r->method = method; r->src_loc = src_loc; r->dst_stagger = dst_stagger;
+    MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_NEAREST_STOD) store_nearest(ctx, r.get());
+    else if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_BILINEAR) store_bilinear_element(ctx, r.get());
+    else if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_CONSERVE) store_conserve(ctx, r.get());
+    else if (src_loc == MPRG_SRC_MESH_NODE && method == MPRG_BILINEAR) store_bilinear_node(ctx, r.get());
+    else if (src_loc == MPRG_SRC_GRID_CENTER && method == MPRG_BILINEAR) store_bilinear_grid(ctx, r.get());
+    else fail(54, "mprg_store: unsupported (method %d, src_loc %d)", method, src_loc);
+    route_finish(ctx, r.get());
+    MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MPRG_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    MPRG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    r->refcount = 1;
+    r->memoised = true;
+    *rh = r.get();
+    ctx->routes[key] = r.release();
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_release(mprg_ctx *ctx, mprg_route *rh) {
+    MPRG_ENTER(ctx)
+    if (!rh) fail(1, "mprg_release: null route");
+    rh->refcount--;
+    if (rh->refcount <= 0 && !rh->memoised) {
+        auto it = std::find(ctx->imported.begin(), ctx->imported.end(), rh);
+        if (it != ctx->imported.end()) ctx->imported.erase(it);
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        delete rh;
+    }
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_clear_routes(mprg_ctx *ctx) {
+    MPRG_ENTER(ctx)
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &kv : ctx->routes) {
+        kv.second->memoised = false;
+        if (kv.second->refcount <= 0) delete kv.second;
+        else ctx->imported.push_back(kv.second);  // still held by a caller: freed on its release
+    }
+    ctx->routes.clear();
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_route_info(const mprg_route *rh, int64_t *nDst, int64_t *nnz, int64_t *nUnmapped, int64_t *nSrc) {
+    if (!rh) return 1;
+    if (nDst) *nDst = rh->nDst;
+    if (nnz) *nnz = rh->nnz;
+    if (nUnmapped) *nUnmapped = rh->nUnmapped;
+    if (nSrc) *nSrc = rh->nSrc;
+    return 0;
+}
+
+int mprg_route_export_csr(mprg_ctx *ctx, const mprg_route *rh, int32_t *rowptr, int32_t *col, double *w) {
+    MPRG_ENTER(ctx)
+    if (!rh) fail(1, "mprg_route_export_csr: null route");
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (rowptr) MPRG_CUDA(cudaMemcpy(rowptr, rh->rowptr.p, (rh->nDst + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (col && rh->nnz) MPRG_CUDA(cudaMemcpy(col, rh->col.p, rh->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (w && rh->nnz) MPRG_CUDA(cudaMemcpy(w, rh->w.p, rh->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_route_import_csr(mprg_ctx *ctx, int64_t nSrc, int64_t nDst, const int32_t *rowptr, const int32_t *col,
+                          const double *w, mprg_route **rh) {
+    MPRG_ENTER(ctx)
+    if (!rh || !rowptr || nDst < 0 || nSrc <= 0) fail(1, "mprg_route_import_csr: bad arguments");
+    *rh = nullptr;
+    if (rowptr[0] != 0) fail(61, "mprg_route_import_csr: rowptr[0] != 0");
+    for (int64_t t = 0; t < nDst; ++t)
+        if (rowptr[t + 1] < rowptr[t]) fail(62, "mprg_route_import_csr: rowptr not monotone at row %lld", (long long)t);
+    int64_t nnz = rowptr[nDst];
+    if (nnz > 0 && (!col || !w)) fail(1, "mprg_route_import_csr: null col/w");
+    for (int64_t k = 0; k < nnz; ++k)
+        if (col[k] < 0 || col[k] >= nSrc) fail(63, "mprg_route_import_csr: column %d out of range at %lld", col[k], (long long)k);
+    std::unique_ptr<mprg_route> r(new mprg_route());
+    r->method = -1; r->src_loc = MPRG_SRC_MESH_ELEMENT; r->dst_stagger = -1;
+    r->nDst = nDst; r->nnz = nnz; r->nSrc = nSrc;
+    r->rowptr.alloc(nDst + 1); r->col.alloc(nnz > 0 ? nnz : 1); r->w.alloc(nnz > 0 ? nnz : 1);
+    MPRG_CUDA(cudaMemcpyAsync(r->rowptr.p, rowptr, (nDst + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        MPRG_CUDA(cudaMemcpyAsync(r->col.p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        MPRG_CUDA(cudaMemcpyAsync(r->w.p, w, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    route_finish(ctx, r.get());
+    r->refcount = 1;
+    *rh = r.get();
+    ctx->imported.push_back(r.release());
+    MPRG_LEAVE(ctx)
+}
+
+// ---------------------------------------------------------------------------
+// apply
+// ---------------------------------------------------------------------------
+static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
+                       int src_dtype, int src_mem, void *const *dst, int dst_dtype, int dst_mem,
+                       const int32_t *epi_op, const double *epi_arg) {
+    if (!rh) fail(1, "mprg_apply: null route");
+    if (nfields <= 0) return;
+    if (!src || !dst || !nlev) fail(1, "mprg_apply: null argument");
+    const size_t isz = src_dtype == MPRG_F32 ? 4 : 8, osz = dst_dtype == MPRG_F32 ? 4 : 8;
+    const int64_t nSrcPts = rh->srcLevelSlowest ? rh->srcPlane : rh->nSrc;
+    MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (src_mem == MPRG_DEVICE && dst_mem == MPRG_DEVICE) {
+        std::vector<ApplyField> fl(nfields);
+        for (int f = 0; f < nfields; ++f)
+            fl[f] = ApplyField{src[f], dst[f], nlev[f], epi_op ? epi_op[f] : 0, epi_arg ? epi_arg[f] : 0.0};
+        apply_device(ctx, rh, fl.data(), nfields, src_dtype, dst_dtype);
+    } else {
+        // Pipelined staging: fields are cut into batches; batch b's H2D overlaps the
+        // kernels of batch b-1 and the D2H of batch b-2 (two staging slots each way).
+        const size_t budget = (size_t)768 << 20;
+        int f = 0, slot = 0, batch = 0;
+        while (f < nfields) {
+            int g = f;
+            size_t inB = 0, outB = 0;
+            while (g < nfields) {
+                size_t a = (size_t)nSrcPts * nlev[g] * isz, b = (size_t)rh->nDst * nlev[g] * osz;
+                a = (a + 255) & ~(size_t)255; b = (b + 255) & ~(size_t)255;
+                if (g > f && (inB + a > budget || outB + b > budget)) break;
+                inB += a; outB += b; ++g;
+            }
+            if (src_mem == MPRG_HOST) ctx->stageIn[slot].ensure(inB);
+            if (dst_mem == MPRG_HOST) ctx->stageOut[slot].ensure(outB);
+            // slot reuse: the kernel that last read stageIn[slot] / the D2H that last read stageOut[slot]
+            if (batch >= 2) {
+                MPRG_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->evK[slot], 0));
+                MPRG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evOut[slot], 0));
+            }
+            std::vector<ApplyField> fl;
+            size_t io = 0, oo = 0;
+            for (int k = f; k < g; ++k) {
+                size_t a = (size_t)nSrcPts * nlev[k] * isz, b = (size_t)rh->nDst * nlev[k] * osz;
+                const void *s = src[k];
+                void *d = dst[k];
+                if (src_mem == MPRG_HOST) {
+                    MPRG_CUDA(cudaMemcpyAsync(ctx->stageIn[slot].p + io, src[k], a, cudaMemcpyHostToDevice, ctx->h2d_stream));
+                    s = ctx->stageIn[slot].p + io;
+                }
+                if (dst_mem == MPRG_HOST) d = ctx->stageOut[slot].p + oo;
+                fl.push_back(ApplyField{s, d, nlev[k], epi_op ? epi_op[k] : 0, epi_arg ? epi_arg[k] : 0.0});
+                io += (a + 255) & ~(size_t)255;
+                oo += (b + 255) & ~(size_t)255;
+            }
+            if (src_mem == MPRG_HOST) {
+                MPRG_CUDA(cudaEventRecord(ctx->evIn[slot], ctx->h2d_stream));
+                MPRG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evIn[slot], 0));
+            }
+            apply_device(ctx, rh, fl.data(), (int)fl.size(), src_dtype, dst_dtype);
+            MPRG_CUDA(cudaEventRecord(ctx->evK[slot], ctx->stream));
+            if (dst_mem == MPRG_HOST) {
+                MPRG_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->evK[slot], 0));
+                oo = 0;
+                for (int k = f; k < g; ++k) {
+                    size_t b = (size_t)rh->nDst * nlev[k] * osz;
+                    MPRG_CUDA(cudaMemcpyAsync(dst[k], ctx->stageOut[slot].p + oo, b, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    oo += (b + 255) & ~(size_t)255;
+                }
+                MPRG_CUDA(cudaEventRecord(ctx->evOut[slot], ctx->d2h_stream));
+            }
+            f = g;
+            slot ^= 1;
+            ++batch;
+        }
+        // host-buffer applies complete before returning (reference semantics: Regrid is blocking)
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (dst_mem == MPRG_HOST) MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    }
+    MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+}
+
+int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
+                  int src_dtype, int src_mem, void *const *dst, int dst_dtype, int dst_mem, const int32_t *epi_op,
+                  const double *epi_arg) {
+    MPRG_ENTER(ctx)
+    apply_impl(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst, dst_dtype, dst_mem, epi_op, epi_arg);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_apply(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
+               int src_dtype, int src_mem, void *const *dst, int dst_dtype, int dst_mem) {
+    return mprg_apply_ex(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst, dst_dtype, dst_mem, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// wind rotation
+// ---------------------------------------------------------------------------
+int mprg_set_rotation(mprg_ctx *ctx, const double *cosa, const double *sina) {
+    MPRG_ENTER(ctx)
+    const Target &tg = ctx->target[MPRG_CENTER];
+    if (!tg.set) fail(42, "mprg_set_rotation: CENTER target not set");
+    if (!cosa || !sina) fail(1, "mprg_set_rotation: null argument");
+    int64_t n = tg.nSlab();
+    ctx->cosa.alloc(n > 0 ? n : 1);
+    ctx->sina.alloc(n > 0 ? n : 1);
+    if (n) {
+        MPRG_CUDA(cudaMemcpyAsync(ctx->cosa.p, cosa + tg.slabOffset(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MPRG_CUDA(cudaMemcpyAsync(ctx->sina.p, sina + tg.slabOffset(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->haveRot = true;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem) {
+    MPRG_ENTER(ctx)
+    if (!u || !v) fail(1, "mprg_rotate_winds: null argument");
+    const Target &tg = ctx->target[MPRG_CENTER];
+    const size_t bytes = (size_t)tg.nSlab() * nlev * (dtype == MPRG_F32 ? 4 : 8);
+    if (mem == MPRG_DEVICE) {
+        rotate_device(ctx, u, v, nlev, dtype);
+    } else {
+        ctx->stageIn[0].ensure(2 * bytes);
+        unsigned char *du = ctx->stageIn[0].p, *dv = du + bytes;
+        MPRG_CUDA(cudaMemcpyAsync(du, u, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        MPRG_CUDA(cudaMemcpyAsync(dv, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        rotate_device(ctx, du, dv, nlev, dtype);
+        MPRG_CUDA(cudaMemcpyAsync(u, du, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        MPRG_CUDA(cudaMemcpyAsync(v, dv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    MPRG_LEAVE(ctx)
+}
+
+// ---------------------------------------------------------------------------
+// gather (gather.cu)
+// ---------------------------------------------------------------------------
+int mprg_comm_id(mprg_ctx *ctx, void *id128) {
+    MPRG_ENTER(ctx)
+    if (!id128) fail(1, "mprg_comm_id: null buffer");
+    comm_id(ctx, id128);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_comm_init(mprg_ctx *ctx, const void *id128) {
+    MPRG_ENTER(ctx)
+    if (ctx->nranks > 1 && !id128) fail(1, "mprg_comm_init: null id");
+    comm_init(ctx, id128);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_gather(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void *slab_dev, int root, void *full_dev) {
+    MPRG_ENTER(ctx)
+    gather_slabs(ctx, stagger, nlev, dtype, slab_dev, root, full_dev);
+    MPRG_LEAVE(ctx)
+}
+
+int64_t mprg_kernel_launches(const mprg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+double mprg_last_ms(const mprg_ctx *ctx) {
+    if (!ctx) return 0.0;
+    if (cudaEventQuery(ctx->ev1) == cudaSuccess && cudaEventQuery(ctx->ev0) == cudaSuccess) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) return ms;
+    }
+    return ctx->last_ms;
+}
+
+}  // extern "C"
+
+// ---- not-yet-implemented stores (filled in by conserve.cu / stagger.cu) -------
+namespace mprg {
+#ifndef MPRG_HAVE_CONSERVE
+void store_conserve(mprg_ctx *, mprg_route *) { fail(91, "CONSERVE store not built into this library"); }
+#endif
+#ifndef MPRG_HAVE_STAGGER
+void store_bilinear_grid(mprg_ctx *, mprg_route *) { fail(92, "GRID_CENTER bilinear store not built into this library"); }
+#endif
+#ifndef MPRG_HAVE_NODE
+void store_bilinear_node(mprg_ctx *, mprg_route *) { fail(93, "MESH_NODE bilinear store not built into this library"); }
+#endif
+}  // namespace mprg

@@ -1,0 +1,210 @@
+// common.cuh -- context, device buffers and error plumbing of libmpassit_rg.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/mpassit_rg.h"
+
+namespace mprg {
+
+constexpr double kTol = 1e-10;  // ESMF parametric point-in-element tolerance
+constexpr int kNumSM = 148;     // B200
+
+struct Error {
+    int rc;
+    std::string msg;
+};
+
+[[noreturn]] inline void fail(int rc, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error{rc, buf};
+}
+
+#define MPRG_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            ::mprg::fail(700 + (int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                         __FILE__, __LINE__);                                                \
+    } while (0)
+
+// RAII device allocation
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) MPRG_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t n = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void ensure(size_t bytes) {
+        if (bytes <= n) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        MPRG_CUDA(cudaMallocHost(&p, bytes));
+        n = bytes;
+    }
+};
+
+// Implicit bounding-volume hierarchy over Morton-sorted primitives (bvh.cu)
+struct Bvh {
+    int32_t nPrim = 0;
+    int32_t nLeafNodes = 0;    // power of two
+    DevBuf<float4> nodes;      // [2*nLeafNodes-1][2]: (lox,loy,loz,hix) (hiy,hiz,-,-)
+    DevBuf<int32_t> primId;    // [nPrim] Morton order -> original id
+};
+
+struct Mesh {
+    int32_t nCells = 0, nVertices = 0, maxEdges = 0;
+    DevBuf<double> cellXyz;    // [nCells][3]   unit sphere
+    DevBuf<double> vertXyz;    // [nVertices][3]
+    DevBuf<int32_t> voc;       // [nCells][maxEdges] 1-based, 0 = pad (as given)
+    DevBuf<int32_t> tri;       // [nVertices][3] dual triangles, ascending cell ids, -1 = none
+    DevBuf<double> cellSorted; // [nCells][3] in cellBvh order (leaf-contiguous loads)
+    Bvh cellBvh;               // points: cell centres              (nearest)
+    Bvh triBvh;                // boxes: dual triangles              (bilinear, element)
+    Bvh polyBvh;               // boxes: Voronoi polygons            (conserve; bilinear, node)
+    bool haveCellBvh = false, haveTriBvh = false, havePolyBvh = false;
+    double maxTriEdge2 = 0.0;
+};
+
+struct Target {
+    int32_t ni = 0, nj = 0;    // full grid
+    int32_t j0 = 0, j1 = 0;    // slab rows owned by this rank
+    DevBuf<double> xyz;        // full grid [nj][ni][3]
+    bool set = false;
+    int64_t nSlab() const { return (int64_t)(j1 - j0) * ni; }
+    int64_t slabOffset() const { return (int64_t)j0 * ni; }
+};
+
+}  // namespace mprg
+
+// Route handle: CSR weights of this rank's destination slab.
+struct mprg_route {
+    int method = 0, src_loc = 0, dst_stagger = 0;
+    int64_t nDst = 0, nnz = 0, nUnmapped = 0, nSrc = 0;
+    int32_t maxRow = 0;        // longest row
+    bool uniform = false;      // every mapped row has exactly `maxRow` entries, stored ELL-like
+    mprg::DevBuf<int32_t> rowptr;  // [nDst+1]
+    mprg::DevBuf<int32_t> col;     // [nnz]
+    mprg::DevBuf<double> w;        // [nnz]
+    mprg::DevBuf<float> w32;       // [nnz] fp32 copy for the all-fp32 path
+    int refcount = 0;
+    bool memoised = false;
+    // source is a structured grid (MPRG_SRC_GRID_CENTER): level-slowest source layout
+    bool srcLevelSlowest = false;
+    int64_t srcPlane = 0;      // points per source level plane
+};
+
+struct mprg_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::string err;
+    mprg::Mesh mesh;
+    mprg::Target target[4];
+    std::map<std::tuple<int, int, int>, mprg_route *> routes;
+    std::vector<mprg_route *> imported;
+    mprg::DevBuf<double> cosa, sina;  // CENTER slab
+    bool haveRot = false;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // staging for host-buffer applies
+    mprg::DevBuf<unsigned char> stageIn[2], stageOut[2];
+    cudaEvent_t evIn[2] = {nullptr, nullptr}, evK[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    mprg::DevBuf<unsigned char> scratch;  // apply descriptors etc.
+    void *nccl = nullptr;                 // ncclComm_t
+    void *ncclLib = nullptr;
+};
+
+namespace mprg {
+
+// reference's balanced block splitter, model_grid.F90:2428-2441 (0-based, half-open)
+inline void para_range(int32_t n, int nprocs, int irank, int32_t *begin, int32_t *end) {
+    int32_t w1 = n / nprocs, w2 = n % nprocs;
+    int32_t ista = irank * w1 + (irank < w2 ? irank : w2);
+    int32_t iend = ista + w1 + (w2 > irank ? 1 : 0);
+    *begin = ista;
+    *end = iend;
+}
+
+// bvh.cu
+void bvh_build_points(mprg_ctx *ctx, const double *xyz_dev, int32_t n, Bvh &out, DevBuf<double> *sortedXyz);
+void bvh_build_boxes(mprg_ctx *ctx, const float *lo_dev, const float *hi_dev, int32_t n, Bvh &out);
+
+// mesh.cu
+void mesh_set(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonC,
+              const double *latC, const double *lonV, const double *latV, const int32_t *voc);
+void target_set(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const double *lon, const double *lat);
+void mesh_need_cell_bvh(mprg_ctx *ctx);
+void mesh_need_tri_bvh(mprg_ctx *ctx);
+void mesh_need_poly_bvh(mprg_ctx *ctx);
+
+// locate.cu
+void store_nearest(mprg_ctx *ctx, mprg_route *r);
+void store_bilinear_element(mprg_ctx *ctx, mprg_route *r);
+// conserve.cu / stagger.cu / polygon
+void store_conserve(mprg_ctx *ctx, mprg_route *r);
+void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r);
+void store_bilinear_node(mprg_ctx *ctx, mprg_route *r);
+void route_finish(mprg_ctx *ctx, mprg_route *r);  // stats + fp32 weight copy
+
+// apply.cu
+struct ApplyField {
+    const void *src;
+    void *dst;
+    int32_t nlev;
+    int32_t epi_op;
+    double epi_arg;
+};
+void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
+                  int dst_dtype);
+void rotate_device(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype);
+
+// gather.cu
+void comm_destroy(mprg_ctx *ctx);
+void comm_id(mprg_ctx *ctx, void *id128);
+void comm_init(mprg_ctx *ctx, const void *id128);
+void gather_slabs(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void *slab_dev, int root,
+                  void *full_dev);
+
+}  // namespace mprg

@@ -1,0 +1,95 @@
+"""ctypes binding of libmpassit_rg.so (include/mpassit_rg.h).
+
+Thin by design: every function maps 1:1 onto a C-ABI entry point, checks the rc
+and raises ``MprgError`` with ``mprg_last_error`` -- the Python analogue of the
+reference's ``if (rc /= 0) call error_handler(msg, rc)`` (utils.F90:16-33).
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible,
+calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpassit_rg.so")
+
+BILINEAR, CONSERVE, NEAREST_STOD = 0, 1, 2
+SRC_MESH_ELEMENT, SRC_MESH_NODE, SRC_GRID_CENTER = 0, 1, 2
+CENTER, EDGE1, EDGE2, CORNER = 0, 1, 2, 3
+F32, F64 = 0, 1
+HOST, DEVICE = 0, 1
+EPI_NONE, EPI_ADD, EPI_MUL = 0, 1, 2
+
+EXPORTS = [
+    "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize",
+    "mprg_host_alloc", "mprg_host_free", "mprg_set_mesh", "mprg_set_target", "mprg_get_slab", "mprg_store",
+    "mprg_release", "mprg_clear_routes", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
+    "mprg_apply", "mprg_apply_ex", "mprg_set_rotation", "mprg_rotate_winds", "mprg_comm_id", "mprg_comm_init",
+    "mprg_gather", "mprg_kernel_launches", "mprg_last_ms",
+]
+
+
+class MprgError(RuntimeError):
+    def __init__(self, rc: int, msg: str):
+        super().__init__(f"mprg rc={rc}: {msg}")
+        self.rc = rc
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the engine.  Raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MprgError(-1, f"{LIB_PATH} not built; run `python -m mpassit_b200.build` (or __graft_entry__.build())")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pp = C.POINTER(C.c_void_p)
+    L.mprg_version.restype = C.c_char_p
+    L.mprg_last_error.restype = C.c_char_p
+    L.mprg_last_error.argtypes = [vp]
+    L.mprg_init.argtypes = [C.c_int, C.c_int, C.c_int, pp]
+    L.mprg_finalize.argtypes = [vp]
+    L.mprg_set_stream.argtypes = [vp, vp]
+    L.mprg_synchronize.argtypes = [vp]
+    L.mprg_host_alloc.argtypes = [vp, C.c_size_t, pp]
+    L.mprg_host_free.argtypes = [vp, vp]
+    L.mprg_set_mesh.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.mprg_set_target.argtypes = [vp, C.c_int, i32, i32, vp, vp]
+    L.mprg_get_slab.argtypes = [vp, C.c_int, C.POINTER(i32), C.POINTER(i32)]
+    L.mprg_store.argtypes = [vp, C.c_int, C.c_int, C.c_int, pp]
+    L.mprg_release.argtypes = [vp, vp]
+    L.mprg_clear_routes.argtypes = [vp]
+    L.mprg_route_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.mprg_route_export_csr.argtypes = [vp, vp, vp, vp, vp]
+    L.mprg_route_import_csr.argtypes = [vp, i64, i64, vp, vp, vp, pp]
+    L.mprg_apply.argtypes = [vp, vp, i32, pp, C.POINTER(i32), C.c_int, C.c_int, pp, C.c_int, C.c_int]
+    L.mprg_apply_ex.argtypes = [vp, vp, i32, pp, C.POINTER(i32), C.c_int, C.c_int, pp, C.c_int, C.c_int,
+                                C.POINTER(i32), C.POINTER(dbl)]
+    L.mprg_set_rotation.argtypes = [vp, vp, vp]
+    L.mprg_rotate_winds.argtypes = [vp, vp, vp, i32, C.c_int, C.c_int]
+    L.mprg_comm_id.argtypes = [vp, vp]
+    L.mprg_comm_init.argtypes = [vp, vp]
+    L.mprg_gather.argtypes = [vp, C.c_int, i32, C.c_int, vp, C.c_int, vp]
+    L.mprg_kernel_launches.argtypes = [vp]
+    L.mprg_kernel_launches.restype = i64
+    L.mprg_last_ms.argtypes = [vp]
+    L.mprg_last_ms.restype = dbl
+    _lib = L
+    return L
+
+
+def check(ctx, rc: int) -> None:
+    if rc != 0:
+        msg = load().mprg_last_error(ctx)
+        raise MprgError(rc, msg.decode() if msg else "")
+
+
+def np_ptr(a: np.ndarray) -> int:
+    return a.ctypes.data

@@ -1,0 +1,235 @@
+"""Python host-side view of the engine: one ``Regridder`` per rank / GPU.
+
+Mirrors the ESMF object vocabulary the reference uses on this path
+(/root/reference/interp.F90): a *mesh* (ESMF_Mesh, model_grid.F90:488), a
+*target grid* with staggers (ESMF_Grid, model_grid.F90:684-728), ``store`` ->
+route handle (ESMF_FieldBundleRegridStore, interp.F90:123), ``apply``
+(ESMF_FieldBundleRegrid, interp.F90:134), ``release``
+(ESMF_FieldBundleRegridRelease, interp.F90:450) and ``gather``
+(ESMF_FieldGather, write_data.F90:1006).  All arithmetic happens in
+libmpassit_rg.so; this file only marshals pointers.
+
+Fields may be numpy arrays (host buffers, copied through the engine's pipelined
+staging) or torch CUDA tensors (used in place).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import lib as _l
+from .lib import (BILINEAR, CENTER, CONSERVE, CORNER, DEVICE, EDGE1, EDGE2, F32, F64, HOST,  # noqa: F401
+                  NEAREST_STOD, SRC_GRID_CENTER, SRC_MESH_ELEMENT, SRC_MESH_NODE, MprgError)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _dtype_code(x) -> int:
+    if _is_torch(x):
+        import torch
+
+        if x.dtype == torch.float32:
+            return F32
+        if x.dtype == torch.float64:
+            return F64
+    else:
+        if x.dtype == np.float32:
+            return F32
+        if x.dtype == np.float64:
+            return F64
+    raise TypeError(f"unsupported field dtype {x.dtype}")
+
+
+def _ptr(x) -> int:
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError("device fields must be contiguous")
+        return x.data_ptr()
+    if not x.flags["C_CONTIGUOUS"]:
+        raise ValueError("host fields must be C-contiguous")
+    return x.ctypes.data
+
+
+class Route:
+    """Opaque route handle (weights + schedule) == type(esmf_routehandle), interp.F90:86."""
+
+    def __init__(self, owner: "Regridder", handle: int, method: int, src_loc: int, dst_stagger: int):
+        self.owner, self.handle = owner, handle
+        self.method, self.src_loc, self.dst_stagger = method, src_loc, dst_stagger
+
+    def info(self) -> dict:
+        v = [C.c_int64() for _ in range(4)]
+        rc = _l.load().mprg_route_info(self.handle, *[C.byref(x) for x in v])
+        _l.check(self.owner.ctx, rc)
+        return dict(nDst=v[0].value, nnz=v[1].value, nUnmapped=v[2].value, nSrc=v[3].value)
+
+    def export_csr(self):
+        i = self.info()
+        rowptr = np.empty(i["nDst"] + 1, np.int32)
+        col = np.empty(max(i["nnz"], 1), np.int32)
+        w = np.empty(max(i["nnz"], 1), np.float64)
+        rc = _l.load().mprg_route_export_csr(self.owner.ctx, self.handle, rowptr.ctypes.data, col.ctypes.data,
+                                             w.ctypes.data)
+        _l.check(self.owner.ctx, rc)
+        return rowptr, col[: i["nnz"]], w[: i["nnz"]]
+
+    def release(self) -> None:
+        if self.handle:
+            _l.check(self.owner.ctx, _l.load().mprg_release(self.owner.ctx, self.handle))
+            self.handle = 0
+
+
+class Regridder:
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1):
+        L = _l.load()
+        ctx = C.c_void_p()
+        rc = L.mprg_init(device, rank, nranks, C.byref(ctx))
+        if rc != 0:
+            raise MprgError(rc, (L.mprg_last_error(None) or b"").decode())
+        self.ctx = ctx
+        self.L = L
+        self.device, self.rank, self.nranks = device, rank, nranks
+        self.shape = {}  # stagger -> (nj, ni) full grid
+        self.nSrc = {}
+
+    # ---- lifetime -------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "ctx", None):
+            self.L.mprg_finalize(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int) -> None:
+        _l.check(self.ctx, rc)
+
+    def use_torch_stream(self) -> None:
+        """Run engine work on torch's current CUDA stream (so torch events time it)."""
+        import torch
+
+        self._ck(self.L.mprg_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def synchronize(self) -> None:
+        self._ck(self.L.mprg_synchronize(self.ctx))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.L.mprg_kernel_launches(self.ctx))
+
+    @property
+    def last_ms(self) -> float:
+        return float(self.L.mprg_last_ms(self.ctx))
+
+    # ---- geometry -------------------------------------------------------
+    def set_mesh(self, lonCell, latCell, lonVertex, latVertex, verticesOnCell) -> None:
+        lonC = np.ascontiguousarray(lonCell, np.float64)
+        latC = np.ascontiguousarray(latCell, np.float64)
+        lonV = np.ascontiguousarray(lonVertex, np.float64)
+        latV = np.ascontiguousarray(latVertex, np.float64)
+        voc = np.ascontiguousarray(verticesOnCell, np.int32)
+        if voc.ndim != 2 or voc.shape[0] != lonC.size:
+            raise ValueError("verticesOnCell must be [nCells][maxEdges]")
+        self._ck(self.L.mprg_set_mesh(self.ctx, lonC.size, lonV.size, voc.shape[1], lonC.ctypes.data, latC.ctypes.data,
+                                      lonV.ctypes.data, latV.ctypes.data, voc.ctypes.data))
+        self.nSrc[SRC_MESH_ELEMENT] = lonC.size
+        self.nSrc[SRC_MESH_NODE] = lonV.size
+
+    def set_target(self, stagger: int, lon_deg, lat_deg) -> None:
+        lon = np.ascontiguousarray(lon_deg, np.float64)
+        lat = np.ascontiguousarray(lat_deg, np.float64)
+        if lon.ndim != 2 or lon.shape != lat.shape:
+            raise ValueError("target coordinates must be [nj][ni]")
+        nj, ni = lon.shape
+        self._ck(self.L.mprg_set_target(self.ctx, stagger, ni, nj, lon.ctypes.data, lat.ctypes.data))
+        self.shape[stagger] = (nj, ni)
+        if stagger == CENTER:
+            self.nSrc[SRC_GRID_CENTER] = nj * ni
+
+    def slab(self, stagger: int) -> tuple[int, int]:
+        j0, j1 = C.c_int32(), C.c_int32()
+        self._ck(self.L.mprg_get_slab(self.ctx, stagger, C.byref(j0), C.byref(j1)))
+        return j0.value, j1.value
+
+    # ---- weights --------------------------------------------------------
+    def store(self, method: int, src_loc: int = SRC_MESH_ELEMENT, dst_stagger: int = CENTER) -> Route:
+        h = C.c_void_p()
+        self._ck(self.L.mprg_store(self.ctx, method, src_loc, dst_stagger, C.byref(h)))
+        return Route(self, h.value, method, src_loc, dst_stagger)
+
+    def import_csr(self, nSrc: int, rowptr, col, w) -> Route:
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        col = np.ascontiguousarray(col, np.int32)
+        w = np.ascontiguousarray(w, np.float64)
+        h = C.c_void_p()
+        self._ck(self.L.mprg_route_import_csr(self.ctx, nSrc, rowptr.size - 1, rowptr.ctypes.data,
+                                              col.ctypes.data if col.size else None,
+                                              w.ctypes.data if w.size else None, C.byref(h)))
+        return Route(self, h.value, -1, SRC_MESH_ELEMENT, -1)
+
+    def clear_routes(self) -> None:
+        self._ck(self.L.mprg_clear_routes(self.ctx))
+
+    # ---- apply ----------------------------------------------------------
+    def apply(self, route: Route, srcs: Sequence, dsts: Sequence, nlev: Sequence[int] | None = None,
+              epi_op: Sequence[int] | None = None, epi_arg: Sequence[float] | None = None) -> None:
+        """dsts[f][lev][slab] = W . srcs[f]; buffers are numpy (host) or torch CUDA (device)."""
+        n = len(srcs)
+        if n == 0:
+            return
+        if len(dsts) != n:
+            raise ValueError("srcs/dsts length mismatch")
+        s_mem = DEVICE if _is_torch(srcs[0]) else HOST
+        d_mem = DEVICE if _is_torch(dsts[0]) else HOST
+        s_dt, d_dt = _dtype_code(srcs[0]), _dtype_code(dsts[0])
+        if nlev is None:
+            nlev = []
+            for s in srcs:
+                if route.src_loc == SRC_GRID_CENTER:
+                    nlev.append(1 if s.ndim == 2 else int(s.shape[0]))
+                else:
+                    nlev.append(1 if s.ndim == 1 else int(s.shape[1]))
+        sp = (C.c_void_p * n)(*[_ptr(s) for s in srcs])
+        dp = (C.c_void_p * n)(*[_ptr(d) for d in dsts])
+        nl = (C.c_int32 * n)(*[int(v) for v in nlev])
+        for s, d in zip(srcs, dsts):
+            if _dtype_code(s) != s_dt or _dtype_code(d) != d_dt:
+                raise TypeError("all stacked fields of one apply share a dtype")
+        if epi_op is None:
+            rc = self.L.mprg_apply(self.ctx, route.handle, n, sp, nl, s_dt, s_mem, dp, d_dt, d_mem)
+        else:
+            eo = (C.c_int32 * n)(*[int(v) for v in epi_op])
+            ea = (C.c_double * n)(*[float(v) for v in (epi_arg or [0.0] * n)])
+            rc = self.L.mprg_apply_ex(self.ctx, route.handle, n, sp, nl, s_dt, s_mem, dp, d_dt, d_mem, eo, ea)
+        self._ck(rc)
+
+    # ---- winds ----------------------------------------------------------
+    def set_rotation(self, cosa, sina) -> None:
+        ca = np.ascontiguousarray(cosa, np.float64)
+        sa = np.ascontiguousarray(sina, np.float64)
+        self._ck(self.L.mprg_set_rotation(self.ctx, ca.ctypes.data, sa.ctypes.data))
+
+    def rotate_winds(self, u, v, nlev: int) -> None:
+        mem = DEVICE if _is_torch(u) else HOST
+        self._ck(self.L.mprg_rotate_winds(self.ctx, _ptr(u), _ptr(v), int(nlev), _dtype_code(u), mem))
+
+    # ---- gather ---------------------------------------------------------
+    def comm_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.L.mprg_comm_id(self.ctx, buf))
+        return buf.raw
+
+    def comm_init(self, id128: bytes) -> None:
+        buf = C.create_string_buffer(id128, 128)
+        self._ck(self.L.mprg_comm_init(self.ctx, buf))
+
+    def gather(self, stagger: int, nlev: int, slab, root: int = 0, full=None) -> None:
+        self._ck(self.L.mprg_gather(self.ctx, stagger, int(nlev), _dtype_code(slab), _ptr(slab), int(root),
+                                    _ptr(full) if full is not None else None))

@@ -1,0 +1,196 @@
+"""GPU parity: CUDA engine (through the C ABI) vs the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): bit-exact for nearest-neighbour columns, masks and
+indices; weights <= 1e-12 abs; fp32 bilinear fields <= 1e-5 relative (here far tighter).
+"""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rg(engine_lib):
+    from mpassit_b200.regrid import Regridder
+
+    r = Regridder(device=0)
+    yield r
+    r.close()
+
+
+CASES = {
+    "global_icos_jit": lambda: (H.small_global(2562, 0.15), H.latlon_grid(144, 72)),
+    "global_c1": lambda: (H.synth.global_mesh(40962), H.latlon_grid(360, 180)),
+    "regional_ragged": lambda: (H.small_regional(3000), H.latlon_grid(150, 110, -102.0, -93.0, 36.0, 41.0)),
+}
+
+
+def _setup(rg, orc, name):
+    mesh, (lon, lat) = CASES[name]()
+    rg.set_mesh(mesh.lonCell, mesh.latCell, mesh.lonVertex, mesh.latVertex, mesh.verticesOnCell)
+    rg.set_target(0, lon, lat)
+    cxyz, vxyz, tri = H.oracle_geometry(orc, mesh)
+    dxyz = orc.sph_deg_to_cart(lon, lat)
+    return mesh, lon, lat, cxyz, vxyz, tri, dxyz
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_nearest_indices_bit_exact(rg, orc, name):
+    from mpassit_b200 import lib as l
+
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, name)
+    want = orc.nearest(cxyz, dxyz, brute=(name != "global_c1"))
+    r = rg.store(l.NEAREST_STOD, l.SRC_MESH_ELEMENT, l.CENTER)
+    rowptr, col, w = r.export_csr()
+    assert np.array_equal(rowptr, np.arange(lon.size + 1))
+    assert np.array_equal(col, want)
+    assert np.all(w == 1.0)
+    assert r.info()["nUnmapped"] == 0
+    r.release()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_bilinear_structure_and_weights(rg, orc, name):
+    from mpassit_b200 import lib as l
+
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, name)
+    elem, col, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz, brute=(name != "global_c1"))
+    mask = elem >= 0
+    rp_want, col_want, w_want = orc.ell_to_csr(mask, col, w)
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    rowptr, gcol, gw = r.export_csr()
+    assert np.array_equal(rowptr, rp_want)          # mapped / unmapped mask bit-exact
+    assert np.array_equal(gcol, col_want)           # indices bit-exact
+    assert np.abs(gw - w_want).max() <= 1e-12 if gw.size else True
+    assert r.info()["nUnmapped"] == int((~mask).sum())
+    if name == "regional_ragged":
+        assert 0 < (~mask).sum() < mask.size        # the case really exercises unmapped rows
+    r.release()
+
+
+@pytest.mark.parametrize("nlev", [1, 4, 55, 60, 61, 130])
+def test_apply_bilinear_levels(rg, orc, nlev):
+    from mpassit_b200 import lib as l
+
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "regional_ragged")
+    elem, col, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
+    rp, cc, ww = orc.ell_to_csr(elem >= 0, col, w)
+    src = H.synth.smooth_field(mesh.lonCell, mesh.latCell, nlev, seed=nlev)
+    want = orc.apply(rp, cc, ww, src, np.float32)
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    got = np.full((nlev, lon.size), np.nan, np.float32)
+    rg.apply(r, [src if nlev > 1 else src.reshape(-1)], [got], nlev=[nlev])
+    r.release()
+    unm = elem < 0
+    assert np.all(got[:, unm] == 0.0)                # zero fill of unmapped rows
+    # fp64 accumulation, one rounding: at most 1 ulp from the oracle's rounding of the same sum
+    np.testing.assert_allclose(got, want, rtol=2e-7, atol=0)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_apply_nearest_bit_exact_and_stacked(rg, orc):
+    from mpassit_b200 import lib as l
+
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "global_icos_jit")
+    idx = orc.nearest(cxyz, dxyz)
+    rp, cc, ww = orc.nearest_to_csr(idx)
+    r = rg.store(l.NEAREST_STOD, l.SRC_MESH_ELEMENT, l.CENTER)
+    xland = H.synth.integer_field(mesh.nCells, 2)
+    ivg = H.synth.integer_field(mesh.nCells, 20, seed=3)
+    soil = np.ascontiguousarray(np.stack([H.synth.integer_field(mesh.nCells, 9, seed=s) for s in range(4)], 1))
+    outs = [np.empty((1, lon.size), np.float32), np.empty((1, lon.size), np.float32), np.empty((4, lon.size), np.float32)]
+    rg.apply(r, [xland, ivg, soil], outs, nlev=[1, 1, 4])
+    r.release()
+    assert np.array_equal(outs[0][0], xland[idx])
+    assert np.array_equal(outs[1][0], ivg[idx])
+    assert np.array_equal(outs[2], soil[idx].T)
+    assert np.array_equal(outs[2], orc.apply(rp, cc, ww, soil, np.float32))
+
+
+@pytest.mark.parametrize("sdt,ddt", [(np.float32, np.float64), (np.float64, np.float64), (np.float64, np.float32)])
+def test_apply_dtype_combinations(rg, orc, sdt, ddt):
+    from mpassit_b200 import lib as l
+
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "global_icos_jit")
+    elem, col, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
+    rp, cc, ww = orc.ell_to_csr(elem >= 0, col, w)
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    for nlev in (8, 55):
+        src = H.synth.smooth_field(mesh.lonCell, mesh.latCell, nlev, dtype=sdt)
+        want = orc.apply(rp, cc, ww, src, ddt)
+        got = np.empty((nlev, lon.size), ddt)
+        rg.apply(r, [src], [got], nlev=[nlev])
+        np.testing.assert_allclose(got, want, rtol=(2e-7 if ddt == np.float32 else 1e-14))
+    r.release()
+
+
+def test_import_csr_ragged_rows_and_empty(rg, orc):
+    """Conservative-like ragged rows (0..20 entries) incl. rows longer than the register/smem fast paths."""
+    rng = np.random.default_rng(5)
+    nSrc, nDst = 5000, 3333
+    lens = rng.integers(0, 21, nDst)
+    lens[:40] = 0
+    lens[100] = 700   # longer than the per-tile CSR cache
+    rp = np.zeros(nDst + 1, np.int32)
+    np.cumsum(lens, out=rp[1:])
+    col = rng.integers(0, nSrc, rp[-1]).astype(np.int32)
+    w = rng.random(rp[-1])
+    r = rg.import_csr(nSrc, rp, col, w)
+    for nlev in (1, 7, 64, 65):
+        src = rng.standard_normal((nSrc, nlev)).astype(np.float32)
+        got = np.empty((nlev, nDst), np.float32)
+        rg.apply(r, [src if nlev > 1 else src.reshape(-1)], [got], nlev=[nlev])
+        want = orc.apply(rp, col, w, src, np.float32)
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+        assert np.all(got[:, lens == 0] == 0.0)
+    r.release()
+
+
+def test_device_buffers_and_memoised_store(rg, orc):
+    import torch
+
+    from mpassit_b200 import lib as l
+
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "global_icos_jit")
+    r1 = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    n0 = rg.kernel_launches
+    r2 = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)     # memoised: no new kernels
+    assert r2.handle == r1.handle and rg.kernel_launches == n0
+    src = H.synth.smooth_field(mesh.lonCell, mesh.latCell, 60)
+    host = np.empty((60, lon.size), np.float32)
+    rg.apply(r1, [src], [host])
+    dsrc = torch.from_numpy(src).cuda()
+    ddst = torch.empty((60, lon.size), dtype=torch.float32, device="cuda")
+    rg.apply(r1, [dsrc], [ddst])
+    rg.synchronize()
+    assert np.array_equal(ddst.cpu().numpy(), host)
+    assert rg.kernel_launches > n0
+    r1.release(); r2.release()
+
+
+def test_rotate_winds(rg, orc):
+    mesh, lon, lat, *_ = _setup(rg, orc, "global_icos_jit")
+    rng = np.random.default_rng(3)
+    n = lon.size
+    alpha = rng.uniform(-0.4, 0.4, n)
+    cosa, sina = np.cos(alpha), np.sin(alpha)
+    rg.set_rotation(cosa.reshape(lon.shape), sina.reshape(lon.shape))
+    for dt, tol in ((np.float64, 1e-13), (np.float32, 2e-6)):
+        u = rng.standard_normal((5, n)).astype(dt) * 10
+        v = rng.standard_normal((5, n)).astype(dt) * 10
+        wu, wv = orc.rotate_winds(u.copy(), v.copy(), cosa, sina)
+        rg.rotate_winds(u, v, 5)
+        np.testing.assert_allclose(u, wu, rtol=tol, atol=tol)
+        np.testing.assert_allclose(v, wv, rtol=tol, atol=tol)
+
+
+def test_errors_are_reported_not_fatal(rg):
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import MprgError
+
+    with pytest.raises(MprgError):
+        rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CORNER if l.CORNER not in rg.shape else 7)
+    with pytest.raises(MprgError):
+        rg.import_csr(10, np.array([0, 2], np.int32), np.array([1, 11], np.int32), np.ones(2))
