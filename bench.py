@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- interpolated target-point-levels/s of one MPASSIT interp_data pass.
+
+  python bench.py --gpus N --steps K --warmup W            # this engine (N = 1 default)
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference's ESMF path
+
+A *step* is one pass of the hot path (interp_data, /root/reference/interp.F90:92-465) over
+one synthetic MPAS output time: every field of diaglist + histlist_2d/3d/soil on the
+BASELINE.json configs[1] workload (3-km regional mesh -> Lambert 1801 x 1061, 60 levels).
+  value : device-resident pass (sources, weights and outputs in HBM), CUDA-event timed
+  e2e   : the same pass through the C ABI with HOST buffers, weights rebuilt every step
+          (what one `mpassit` run does), H2D + D2H inside the timed region
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "interpolated target-point-levels/s"
+UNIT = "point-levels/s"
+KIND_NAMES = {0: "k_apply_cols<vec16B>", 1: "k_apply_cols<scalar4B>", 2: "k_apply_flat", 3: "k_apply_planes"}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = samples in the upper half of the power range seen
+        thr = 0.5 * (min(pw) + max(pw))
+        load = [s for s, w in zip(sm, pw) if w >= thr] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_pass(wl, frac_rows: float, steps: int, warmup: int, threads: int | None = None):
+    """The reference's CPU path restated by oracle/ (ESMF cannot be built here): weight
+    generation (RegridStore) + application (Regrid) for a contiguous block of target rows,
+    every field class of the workload.  Returns (units per step, [seconds per step], detail)."""
+    from oracle import oracle as orc
+    from mpassit_b200 import synth
+
+    if threads:
+        orc.set_num_threads(threads)
+    m = wl.mesh
+    lo, la = orc.mesh_rad_to_deg(m.lonCell, m.latCell)
+    cxyz = orc.sph_deg_to_cart(lo, la)
+    lov, lav = orc.mesh_rad_to_deg(m.lonVertex, m.latVertex)
+    vxyz = orc.sph_deg_to_cart(lov, lav)
+    latM, lonM = wl.grids["M"]
+    nj, ni = latM.shape
+    nrows = max(2, int(round(nj * frac_rows)))
+    j0 = (nj - nrows) // 2
+    rows = slice(j0, j0 + nrows)
+    rng = np.random.default_rng(1)
+    # source fields (values do not affect timing; one array per distinct level count is reused)
+    src = {n: synth.smooth_field(m.lonCell, m.latCell, n, seed=n) for n in {1, wl.nz, wl.nz + 1, wl.nsoil}}
+    lists = wl.lists
+    wrf = bool(wl.cfg.wrf_mod_vars)
+    detail = {}
+
+    def one_pass():
+        t0 = time.perf_counter()
+        tri = orc.dual_triangles(m.verticesOnCell, m.nVertices)
+        dM = orc.sph_deg_to_cart(lonM[rows], latM[rows])
+        e, c, w = orc.bilinear(cxyz, tri, m.verticesOnCell, dM)
+        bil = orc.ell_to_csr(e >= 0, c, w)
+        nst = orc.nearest_to_csr(orc.nearest(cxyz, dM))
+        clat, clon = wl.grids["CORNER"]
+        cor = orc.sph_deg_to_cart(clon[j0:j0 + nrows + 1], clat[j0:j0 + nrows + 1]).reshape(nrows + 1, ni + 1, 3)
+        cons = orc.conserve(cxyz, vxyz, m.verticesOnCell, cor)
+        sx = dM.reshape(nrows, ni, 3)
+        ulat, ulon = wl.grids["U"]
+        vlat, vlon = wl.grids["V"]
+        eu, cu, wu = orc.bilinear_quadgrid(sx, orc.sph_deg_to_cart(ulon[rows], ulat[rows]))
+        ev, cv, wv = orc.bilinear_quadgrid(sx, orc.sph_deg_to_cart(vlon[j0:j0 + nrows + 1], vlat[j0:j0 + nrows + 1]))
+        ucsr, vcsr = orc.ell_to_csr(eu >= 0, cu, wu), orc.ell_to_csr(ev >= 0, cv, wv)
+        t1 = time.perf_counter()
+        units = 0
+        for nm, _ in lists["diag"]:
+            n = wl.levels_of("diag", nm)
+            orc.apply(*bil, src[n], np.float32, tiled=True); units += n * dM.shape[0]
+        for nm, _ in lists["hist_2d"]:
+            csr = cons if nm in ("snow", "snowh") else nst if nm in ("xland", "ivgtyp", "isltyp", "landmask") else bil
+            orc.apply(*csr, src[1], np.float32, tiled=True); units += dM.shape[0]
+        orc.apply(*bil, src[1], np.float32, tiled=True); units += dM.shape[0]     # HGT
+        winds = {}
+        for nm, _ in lists["hist_3d"]:
+            n = wl.levels_of("hist_3d", nm)
+            if wrf and nm in ("uReconstructZonal", "uReconstructMeridional"):
+                winds[nm] = orc.apply(*bil, src[n], np.float64); units += n * dM.shape[0]
+            else:
+                orc.apply(*bil, src[n], np.float32, tiled=True); units += n * dM.shape[0]
+        if len(winds) == 2 and wl.cosa is not None:
+            orc.rotate_winds(winds["uReconstructZonal"], winds["uReconstructMeridional"],
+                             wl.cosa[rows].reshape(-1), wl.sina[rows].reshape(-1))
+        for nm, csr in (("uReconstructZonal", ucsr), ("uReconstructMeridional", vcsr)):
+            if nm in winds:
+                orc.apply_planes(*csr, winds[nm]); units += wl.nz * (csr[0].size - 1)
+        for nm, _ in lists["soil"]:
+            orc.apply(*nst, src[wl.nsoil], np.float32, tiled=True); units += wl.nsoil * dM.shape[0]
+        t2 = time.perf_counter()
+        detail.update(weights_s=t1 - t0, apply_s=t2 - t1, rows=nrows, of_rows=nj)
+        return units, t2 - t0
+
+    times, units = [], 0
+    for k in range(warmup + steps):
+        units, dt = one_pass()
+        if k >= warmup:
+            times.append(dt)
+    return units, times, detail
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("MPASSIT_BENCH_CONFIG", "c2"))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from mpassit_b200 import build, workload
+    from mpassit_b200 import lib as L
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        build.build_all()
+        wl = workload.make(args.config)
+        from oracle import oracle as orc
+
+        orc.build()
+        frac = 1.0 / 16.0 if args.config == "c2" else 1.0
+        units, times, det = cpu_reference_pass(wl, frac, args.steps, max(args.warmup, 1))
+        t = sum(times) / len(times)
+        v = units / t
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{wl.name}: interp_data pass (weights + apply), CPU restatement of the ESMF path "
+                                   f"(not ESMF), {det['rows']} of {det['of_rows']} target rows per step"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                             "sample": f"{det['rows']}/{det['of_rows']} target rows x all fields; weights "
+                                       f"{det['weights_s']:.2f}s + apply {det['apply_s']:.2f}s per step"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------------------------------------------------------- this engine
+    import torch
+
+    if not torch.cuda.is_available():
+        log("bench.py: no CUDA device; the engine has no CPU fallback")
+        return 2
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        build.build_all()
+    if dist:
+        dist.barrier()
+    from mpassit_b200.regrid import Regridder
+
+    t_setup = time.perf_counter()
+    wl = workload.make(args.config)
+    rg = Regridder(device=local_rank, rank=rank, nranks=world)
+    rg.use_torch_stream()
+    workload.load_geometry(rg, wl)
+    if world > 1:
+        ids = [rg.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        rg.comm_init(ids[0])
+    want_e2e = not args.no_e2e
+    F = workload.make_fields(wl, device=f"cuda:{local_rank}", pinned_host=want_e2e, rg=rg)
+    log(f"[rank {rank}] setup {time.perf_counter() - t_setup:.1f}s: {wl.mesh.nCells} cells -> "
+        f"{wl.grids['M'][0].shape[::-1]} mass points, {wl.units_per_pass():.3e} units/pass")
+
+    # weights once (memoised for the device-resident steps); keep handles so they stay resident
+    t0 = time.perf_counter()
+    held = []
+    store_ms = {}
+    for tag, (m, s, d) in {"bilinear": (L.BILINEAR, L.SRC_MESH_ELEMENT, L.CENTER),
+                           "nearest": (L.NEAREST_STOD, L.SRC_MESH_ELEMENT, L.CENTER),
+                           "conserve": (L.CONSERVE, L.SRC_MESH_ELEMENT, L.CENTER),
+                           "stagger_u": (L.BILINEAR, L.SRC_GRID_CENTER, L.EDGE1),
+                           "stagger_v": (L.BILINEAR, L.SRC_GRID_CENTER, L.EDGE2)}.items():
+        held.append(rg.store(m, s, d))
+        store_ms[tag] = rg.last_ms
+    rg.synchronize()
+    store_wall = time.perf_counter() - t0
+    info = held[0].info()
+
+    def gather_outputs():
+        if world == 1:
+            return
+        # the path's only collective: slabs -> writing rank (write_data.F90:1006-1453)
+        for g in ("diag", "hist_2d", "hist_3d", "soil"):
+            for s in F["dev"][g]:
+                if g == "hist_3d" and s.name in ("uReconstructZonal", "uReconstructMeridional"):
+                    continue
+                rg.gather(L.CENTER, s.nlev, s.dst, 0, full_bufs[0][: s.nlev] if rank == 0 else None)
+        rg.gather(L.EDGE1, wl.nz, F["dev"]["u_stag"], 0, full_bufs[1] if rank == 0 else None)
+        rg.gather(L.EDGE2, wl.nz, F["dev"]["v_stag"], 0, full_bufs[2] if rank == 0 else None)
+
+    full_bufs = None
+    if world > 1 and rank == 0:
+        nzmax = wl.nz + 1
+        full_bufs = [torch.empty((nzmax, wl.n_mass), dtype=torch.float32, device="cuda"),
+                     torch.empty((wl.nz, wl.grids["U"][0].size), dtype=torch.float32, device="cuda"),
+                     torch.empty((wl.nz, wl.grids["V"][0].size), dtype=torch.float32, device="cuda")]
+
+    def device_step():
+        workload.run_interp(rg, wl, F["dev"], L.DEVICE)
+        gather_outputs()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    rg.profile(True)
+    n0 = rg.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = rg.kernel_launches - n0
+    prof = rg.profile_read()
+    rg.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    units = wl.units_per_pass()
+    value = units / (ms_step * 1e-3)
+
+    # roofline of the dominant kernel, from per-launch CUDA events inside the timed steps
+    by_kind = {}
+    for r in prof:
+        k = by_kind.setdefault(r["kind"], dict(ms=0.0, bytes=0.0, units=0.0, n=0))
+        k["ms"] += r["ms"]; k["bytes"] += r["alg_bytes"]; k["units"] += r["units"]; k["n"] += 1
+    dom = max(by_kind, key=lambda k: by_kind[k]["ms"]) if by_kind else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = None
+    if dom is not None:
+        d = by_kind[dom]
+        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "kernel": KIND_NAMES[dom], "launches": d["n"], "avg_launch_ms": d["ms"] / d["n"],
+                    "alg_bytes_per_launch": d["bytes"] / d["n"], "units_per_launch": d["units"] / d["n"],
+                    "share_of_step": d["ms"] / ms_total,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                    "kernels": {KIND_NAMES[k]: {"ms_per_step": v["ms"] / args.steps, "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
+                                for k, v in by_kind.items()}}
+
+    # end to end: host buffers through the C ABI, weights rebuilt each step
+    e2e = None
+    if want_e2e:
+        h2d, d2h = workload.io_bytes(wl, F["host"])
+        for r in held:
+            r.release()
+        held = []
+        ts = []
+        for k in range(1 + args.e2e_steps):
+            rg.clear_routes()
+            barrier()
+            t0 = time.perf_counter()
+            workload.run_interp(rg, wl, F["host"], L.HOST)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if k >= 1:
+                ts.append(dt)
+        t = sum(ts) / len(ts)
+        if dist:
+            tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        e2e = {"value": units / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * t, "includes": "weight generation + H2D + apply + D2H, pinned host buffers"}
+        # parity spot check of the two paths (device-resident vs host-buffer) on one field
+        a = F["dev"]["hist_3d"][2].dst.cpu()
+        b = F["host"]["hist_3d"][2].dst
+        if not torch.equal(a, b):
+            log("WARNING: device-resident and host-buffer results differ")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        orc.build()
+        frac = 1.0 / 16.0 if args.config == "c2" else 1.0
+        u, times, det = cpu_reference_pass(wl, frac, 1, 0)
+        cpu = {"value": u / times[0], "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+               "sample": f"{det['rows']}/{det['of_rows']} target rows x all fields (weights {det['weights_s']:.2f}s + "
+                         f"apply {det['apply_s']:.2f}s); CPU restatement of the ESMF path, not ESMF"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 accumulate, f32 in/out" if os.environ.get("MPASSIT_GPU_ACC", "") not in ("f32", "fp32") else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{wl.name}: 3-km regional MPAS ({wl.mesh.nCells} cells, {wl.nz} levels) -> Lambert "
+                                   f"{wl.cfg.nx}x{wl.cfg.ny} dx={wl.cfg.dxkm:.0f} m, diaglist+histlist_2d/3d/soil, "
+                                   f"one interp_data pass" if wl.name != "c1" else "c1: 120-km global -> 1 deg lat-lon",
+                       "units_per_step": units, "target_points": wl.n_mass, "l2_policy": "inputs (>9 GB) exceed L2; no flush",
+                       "parallelism": f"target row slabs x{world}", "weights": "resident (memoised) in `value`; rebuilt per step in `e2e`"},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "store_ms": store_ms, "store_wall_s": store_wall,
+            "route_bilinear": info,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    rg.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -62,6 +62,10 @@ int mprg_synchronize(mprg_ctx *ctx);
 /* pinned host memory for callers that want full-speed H2D/D2H (optional) */
 int mprg_host_alloc(mprg_ctx *ctx, size_t bytes, void **ptr);
 int mprg_host_free(mprg_ctx *ctx, void *ptr);
+/* device memory for hosts that keep intermediates on the GPU (the mass-point
+ * winds between interp.F90:268 and :307 never need to visit the host) */
+int mprg_device_alloc(mprg_ctx *ctx, size_t bytes, void **ptr);
+int mprg_device_free(mprg_ctx *ctx, void *ptr);
 
 /* ---- source mesh: replaces ESMF_MeshCreate, model_grid.F90:488-497.
  *      Takes the arrays exactly as read from the MPAS grid file
@@ -149,6 +153,19 @@ int64_t mprg_kernel_launches(const mprg_ctx *ctx);
 /* device milliseconds of the most recent store / apply (CUDA events on the
  * context's stream) */
 double mprg_last_ms(const mprg_ctx *ctx);
+
+/* per-launch timing of the apply kernels (CUDA events on the context's stream):
+ * enable, run applies, then read the records accumulated since the last reset.
+ * kind: 0 = columns kernel, 16-byte loads; 1 = columns kernel, 4-byte loads;
+ * 2 = flat (2-D fields); 3 = planes (grid source).  alg_bytes is the algorithmic
+ * traffic of that launch, units its target-point-levels.
+ * mprg_profile_read synchronises the stream; returns the number of records
+ * (arrays may be NULL to query the count). */
+int mprg_profile_enable(mprg_ctx *ctx, int on);
+int mprg_profile_read(mprg_ctx *ctx, int32_t max, int32_t *kind, double *ms, double *alg_bytes, double *units);
+int mprg_profile_reset(mprg_ctx *ctx);
+/* distinct source entities referenced by a route's weights (nSrcT of the roofline model) */
+int64_t mprg_route_src_referenced(const mprg_route *rh);
 
 #ifdef __cplusplus
 }

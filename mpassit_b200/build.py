@@ -89,5 +89,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libmpassit_host.so")
+HOST_SRC = ["setup.cpp", "target_grid.cpp", "interp.cpp"]
+
+
+def build_host(force: bool = False) -> str:
+    """libmpassit_host.so: C++ mirror of the reference's Fortran host stages (no CUDA code;
+    calls the engine through its C ABI, resolved from the same directory via rpath)."""
+    srcs = [os.path.join(HERE, "host", s) for s in HOST_SRC]
+    deps = srcs + [os.path.join(HERE, "..", "include", "mpassit_host.h"), os.path.join(HERE, "..", "include", "mpassit_rg.h"), LIB]
+    if force or _stale(HOST_LIB, deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOST_LIB, *srcs,
+               "-L" + HERE, "-lmpassit_rg", "-Wl,-rpath,$ORIGIN"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout + p.stderr)
+            raise RuntimeError("host library build failed")
+    return HOST_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build(force, verbose), build_host(force)
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

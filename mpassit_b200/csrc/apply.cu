@@ -249,6 +249,36 @@ static bool acc_fp32_requested() {
     return e && (!strcmp(e, "f32") || !strcmp(e, "fp32"));
 }
 
+// ---- per-launch profiling (bench.py's live roofline measurement) ---------------
+static cudaEvent_t prof_event(mprg_ctx *ctx) {
+    cudaEvent_t e;
+    if (!ctx->evPool.empty()) { e = ctx->evPool.back(); ctx->evPool.pop_back(); return e; }
+    MPRG_CUDA(cudaEventCreate(&e));
+    return e;
+}
+// Algorithmic bytes of one launch (SURVEY.md §8d / DESIGN.md):
+//   K nSrcRef b_in + K nDst b_out + nnz (4 + b_w) + (nDst + 1) 4
+static double alg_bytes(const mprg_route *r, double K, size_t bin, size_t bout, size_t bw) {
+    return K * (double)r->nSrcRef * bin + K * (double)r->nDst * bout + (double)r->nnz * (4.0 + bw) +
+           ((double)r->nDst + 1.0) * 4.0;
+}
+struct ProfScope {
+    mprg_ctx *ctx;
+    bool on;
+    mprg_ctx::ProfRec rec;
+    ProfScope(mprg_ctx *c, int kind, double bytes, double units) : ctx(c), on(c->profile) {
+        if (!on) return;
+        rec.kind = kind; rec.algBytes = bytes; rec.units = units;
+        rec.a = prof_event(c); rec.b = prof_event(c);
+        cudaEventRecord(rec.a, c->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(rec.b, ctx->stream);
+        ctx->prof.push_back(rec);
+    }
+};
+
 template <typename TIN, typename TOUT, typename TACC>
 static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols_vec,
                        const std::vector<FieldDev> &cols_sca, const std::vector<FieldDev> &flat,
@@ -272,24 +302,29 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     a.nDst = r->nDst;
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
+    auto ksum = [](const std::vector<FieldDev> &v) { double k = 0; for (auto &f : v) k += f.nlev; return k; };
     if (!cols_vec.empty()) {
+        ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
         a.fields = dev; a.nfields = (int)cols_vec.size();
         dim3 g(tiles, (unsigned)((cols_vec.size() + kFieldsPerCta - 1) / kFieldsPerCta));
         k_apply_cols<TIN, TOUT, TACC, true><<<g, kThreads, 0, ctx->stream>>>(a);
         ctx->launches++;
     }
     if (!cols_sca.empty()) {
+        ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
         a.fields = dev + cols_vec.size(); a.nfields = (int)cols_sca.size();
         dim3 g(tiles, (unsigned)((cols_sca.size() + kFieldsPerCta - 1) / kFieldsPerCta));
         k_apply_cols<TIN, TOUT, TACC, false><<<g, kThreads, 0, ctx->stream>>>(a);
         ctx->launches++;
     }
     if (!flat.empty()) {
+        ProfScope ps(ctx, 2, alg_bytes(r, ksum(flat), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(flat) * r->nDst);
         a.fields = dev + cols_vec.size() + cols_sca.size(); a.nfields = (int)flat.size();
         k_apply_flat<TIN, TOUT, TACC><<<(unsigned)((r->nDst + 255) / 256), 256, 0, ctx->stream>>>(a);
         ctx->launches++;
     }
     if (!planes.empty()) {
+        ProfScope ps(ctx, 3, alg_bytes(r, ksum(planes), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(planes) * r->nDst);
         a.fields = dev + cols_vec.size() + cols_sca.size() + flat.size(); a.nfields = (int)planes.size();
         dim3 g((unsigned)((r->nDst + 255) / 256), (unsigned)planes.size());
         k_apply_planes<TIN, TOUT, TACC><<<g, 256, 0, ctx->stream>>>(a);

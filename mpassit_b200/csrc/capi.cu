@@ -119,6 +119,19 @@ int mprg_host_free(mprg_ctx *ctx, void *ptr) {
     MPRG_LEAVE(ctx)
 }
 
+int mprg_device_alloc(mprg_ctx *ctx, size_t bytes, void **ptr) {
+    MPRG_ENTER(ctx)
+    if (!ptr) fail(1, "mprg_device_alloc: null out pointer");
+    MPRG_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_device_free(mprg_ctx *ctx, void *ptr) {
+    MPRG_ENTER(ctx)
+    if (ptr) MPRG_CUDA(cudaFree(ptr));
+    MPRG_LEAVE(ctx)
+}
+
 int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonCell_rad,
                   const double *latCell_rad, const double *lonVertex_rad, const double *latVertex_rad,
                   const int32_t *verticesOnCell) {
@@ -406,6 +419,38 @@ int mprg_gather(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void 
     gather_slabs(ctx, stagger, nlev, dtype, slab_dev, root, full_dev);
     MPRG_LEAVE(ctx)
 }
+
+int mprg_profile_enable(mprg_ctx *ctx, int on) {
+    MPRG_ENTER(ctx)
+    ctx->profile = on != 0;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_profile_reset(mprg_ctx *ctx) {
+    MPRG_ENTER(ctx)
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) { ctx->evPool.push_back(r.a); ctx->evPool.push_back(r.b); }
+    ctx->prof.clear();
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_profile_read(mprg_ctx *ctx, int32_t max, int32_t *kind, double *ms, double *alg_bytes, double *units) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    int32_t n = (int32_t)ctx->prof.size();
+    for (int32_t i = 0; i < n && i < max; ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->prof[i].a, ctx->prof[i].b);
+        if (kind) kind[i] = ctx->prof[i].kind;
+        if (ms) ms[i] = t;
+        if (alg_bytes) alg_bytes[i] = ctx->prof[i].algBytes;
+        if (units) units[i] = ctx->prof[i].units;
+    }
+    return n;
+}
+
+int64_t mprg_route_src_referenced(const mprg_route *rh) { return rh ? rh->nSrcRef : 0; }
 
 int64_t mprg_kernel_launches(const mprg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

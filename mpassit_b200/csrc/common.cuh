@@ -121,6 +121,7 @@ struct Target {
 struct mprg_route {
     int method = 0, src_loc = 0, dst_stagger = 0;
     int64_t nDst = 0, nnz = 0, nUnmapped = 0, nSrc = 0;
+    int64_t nSrcRef = 0;       // distinct source entities referenced by the weights
     int32_t maxRow = 0;        // longest row
     bool uniform = false;      // every mapped row has exactly `maxRow` entries, stored ELL-like
     mprg::DevBuf<int32_t> rowptr;  // [nDst+1]
@@ -154,6 +155,11 @@ struct mprg_ctx {
     mprg::DevBuf<unsigned char> scratch;  // apply descriptors etc.
     void *nccl = nullptr;                 // ncclComm_t
     void *ncclLib = nullptr;
+    // optional per-launch profiling of the apply kernels (mprg_profile_*)
+    struct ProfRec { int kind; double algBytes; double units; cudaEvent_t a, b; };
+    bool profile = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> evPool;
 };
 
 namespace mprg {

@@ -132,6 +132,17 @@ __global__ void k_route_stats(int64_t nDst, const int32_t *__restrict__ rowptr, 
     atomicMax(maxRow, len);
 }
 
+__global__ void k_mark_cols(int64_t nnz, const int32_t *__restrict__ col, unsigned char *__restrict__ mark) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) mark[col[i]] = 1;
+}
+__global__ void k_count_marks(int64_t n, const unsigned char *__restrict__ mark, unsigned long long *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v = (i < n && mark[i]) ? 1u : 0u;
+    unsigned b = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
+}
+
 __global__ void k_w32(int64_t nnz, const double *__restrict__ w, float *__restrict__ w32) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) w32[i] = (float)w[i];
@@ -153,12 +164,24 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
         k_w32<<<(unsigned)((r->nnz + 255) / 256), 256, 0, ctx->stream>>>(r->nnz, r->w.p, r->w32.p);
         ctx->launches++;
     }
-    unsigned long long hun = 0;
+    DevBuf<unsigned long long> nref(1);
+    MPRG_CUDA(cudaMemsetAsync(nref.p, 0, sizeof(unsigned long long), ctx->stream));
+    DevBuf<unsigned char> mark;
+    if (r->nnz > 0 && r->nSrc > 0) {
+        mark.alloc(r->nSrc);
+        MPRG_CUDA(cudaMemsetAsync(mark.p, 0, r->nSrc, ctx->stream));
+        k_mark_cols<<<(unsigned)((r->nnz + 255) / 256), 256, 0, ctx->stream>>>(r->nnz, r->col.p, mark.p);
+        k_count_marks<<<(unsigned)((r->nSrc + 255) / 256), 256, 0, ctx->stream>>>(r->nSrc, mark.p, nref.p);
+        ctx->launches += 2;
+    }
+    unsigned long long hun = 0, href = 0;
+    MPRG_CUDA(cudaMemcpyAsync(&href, nref.p, sizeof href, cudaMemcpyDeviceToHost, ctx->stream));
     int32_t hmm[2] = {0, 0};
     MPRG_CUDA(cudaMemcpyAsync(&hun, un.p, sizeof hun, cudaMemcpyDeviceToHost, ctx->stream));
     MPRG_CUDA(cudaMemcpyAsync(hmm, mm.p, sizeof hmm, cudaMemcpyDeviceToHost, ctx->stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     r->nUnmapped = (int64_t)hun;
+    r->nSrcRef = (int64_t)href;
     r->maxRow = hmm[0];
     r->uniform = (r->nnz > 0 && hmm[0] == hmm[1]);
 }

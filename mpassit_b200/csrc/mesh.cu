@@ -112,21 +112,22 @@ __global__ void k_poly_boxes(int32_t nCells, int32_t maxEdges, const int32_t *__
     double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
     double e2 = 0.0;
     int n = 0;
-    d3 first{0, 0, 0}, prev{0, 0, 0};
+    d3 first{0, 0, 0};
     for (int k = 0; k < maxEdges; ++k) {
         int32_t v = voc[(size_t)c * maxEdges + k];
         if (v <= 0) continue;
         d3 p = ld3(vxyz + 3 * (size_t)(v - 1));
         mn[0] = fmin(mn[0], p.x); mn[1] = fmin(mn[1], p.y); mn[2] = fmin(mn[2], p.z);
         mx[0] = fmax(mx[0], p.x); mx[1] = fmax(mx[1], p.y); mx[2] = fmax(mx[2], p.z);
-        if (n == 0) first = p; else e2 = fmax(e2, dist2(prev, p));
-        prev = p;
+        if (n == 0) first = p; else e2 = fmax(e2, dist2(first, p));
         ++n;
     }
     if (n < 3) { l[0] = l[1] = l[2] = INFINITY; h[0] = h[1] = h[2] = -INFINITY; return; }
-    e2 = fmax(e2, dist2(prev, first));
-    // great-circle edges bulge beyond their chord by at most 1 - sqrt(1 - c^2/4)
-    double m = (1.0 - sqrt(fmax(0.0, 1.0 - e2 / 4.0))) * 1.01 + 1e-12;
+    // The polygon's diameter D is at most twice the largest distance from its first vertex.
+    // Great-circle edges bulge beyond their chords by <= 1 - sqrt(1 - D^2/4) and the radial image of
+    // any flat fan triangle lies within 1 - sqrt(1 - D^2/3) of it; cover both.
+    double D2 = 4.0 * e2;
+    double m = (1.0 - sqrt(fmax(0.0, 1.0 - D2 / 3.0))) * 1.01 + sqrt(D2) * 1e-9 + 1e-12;
     for (int a = 0; a < 3; ++a) { l[a] = f_down(mn[a] - m); h[a] = f_up(mx[a] + m); }
 }
 

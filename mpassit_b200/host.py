@@ -1,0 +1,225 @@
+"""ctypes binding of libmpassit_host.so (include/mpassit_host.h): the C++ mirror of the
+reference's Fortran host stages -- ``read_setup_namelist`` (program_setup.F90:87),
+``read_varlist`` (input_data.F90:1146), the regrid-class tables
+(input_data.F90:840-911), ``define_target_grid_params`` coordinates
+(model_grid.F90:644-1201), ``get_rotang`` (model_grid.F90:2450) and ``interp_data``
+(interp.F90:92-465).  Python adds nothing but marshalling.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _l
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libmpassit_host.so")
+STRLEN, NAMELEN = 512, 64
+NAN = 1.0e20
+PROJ_LATLON, PROJ_LC, PROJ_PS, PROJ_MERC = 0, 1, 2, 3
+(CLASS_2D_PATCH, CLASS_2D_CONS, CLASS_2D_NSTD, CLASS_3D_NZ, CLASS_3D_NZP1, CLASS_3D_VERT, CLASS_U, CLASS_V,
+ CLASS_SOIL, CLASS_DIAG_2D, CLASS_DIAG_3D) = range(11)
+
+
+class HostError(RuntimeError):
+    """error_handler(msg, rc) of the reference (utils.F90:16-33), minus the mpi_abort."""
+
+    def __init__(self, rc, msg):
+        super().__init__(f"rc={rc}: {msg}")
+        self.rc, self.msg = rc, msg
+
+
+class Config(C.Structure):
+    _fields_ = ([(n, C.c_char * STRLEN) for n in
+                 ("grid_file_input_grid", "diag_file_input_grid", "hist_file_input_grid", "file_target_grid",
+                  "output_file", "block_decomp_file", "target_grid_type")] +
+                [(n, C.c_int32) for n in
+                 ("interp_diag", "interp_hist", "wrf_mod_vars", "esmf_log", "is_regional", "interp_as_bundle", "nx", "ny")] +
+                [(n, C.c_double) for n in
+                 ("dx", "dy", "ref_lat", "ref_lon", "ref_x", "ref_y", "truelat1", "truelat2", "stand_lon", "pole_lat",
+                  "pole_lon")] +
+                [(n, C.c_int32) for n in ("i_target", "j_target", "proj_code")] +
+                [(n, C.c_double) for n in
+                 ("dxkm", "dykm", "dlondeg", "dlatdeg", "known_lat", "known_lon", "known_x", "known_y")] +
+                [("map_proj_char", C.c_char * NAMELEN)])
+
+
+class Field(C.Structure):
+    _fields_ = [("name", C.c_char * NAMELEN), ("target_name", C.c_char * NAMELEN), ("nlev", C.c_int32),
+                ("klass", C.c_int32), ("src", C.c_void_p), ("dst", C.c_void_p)]
+
+
+class InterpIO(C.Structure):
+    _fields_ = [("src_dtype", C.c_int32), ("dst_dtype", C.c_int32), ("mem", C.c_int32), ("nz", C.c_int32),
+                ("n_diag", C.c_int32), ("diag", C.POINTER(Field)),
+                ("n_hist_2d", C.c_int32), ("hist_2d", C.POINTER(Field)),
+                ("n_hist_3d", C.c_int32), ("hist_3d", C.POINTER(Field)),
+                ("n_soil", C.c_int32), ("soil", C.POINTER(Field)),
+                ("ter", C.c_void_p), ("hgt", C.c_void_p), ("u_stag", C.c_void_p), ("v_stag", C.c_void_p),
+                ("cosa", C.c_void_p), ("sina", C.c_void_p)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(HOST_LIB_PATH):
+        raise HostError(-1, f"{HOST_LIB_PATH} not built; run `python -m mpassit_b200.build`")
+    _l.load()  # the engine first (resolved by rpath anyway)
+    L = C.CDLL(HOST_LIB_PATH)
+    cp, i32 = C.c_char_p, C.c_int32
+    L.mpassit_read_setup_namelist.argtypes = [cp, C.POINTER(Config), cp, C.c_size_t]
+    L.mpassit_read_varlist.argtypes = [cp, i32, C.POINTER(i32), cp, cp, cp, C.c_size_t]
+    L.mpassit_classify_hist_2d.argtypes = [cp]
+    L.mpassit_classify_hist_3d.argtypes = [cp, C.c_int]
+    L.mpassit_classify_diag.argtypes = [cp]
+    L.mpassit_para_range.argtypes = [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.mpassit_para_range.restype = None
+    L.mpassit_read_block_decomp_file.argtypes = [cp, i32, i32, C.c_void_p, cp, C.c_size_t]
+    L.mpassit_target_dims.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(i32), C.POINTER(i32)]
+    L.mpassit_target_coords.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_void_p, cp, C.c_size_t]
+    L.mpassit_get_rotang.argtypes = [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p]
+    L.mpassit_get_rotang.restype = None
+    L.mpassit_classify_fields.argtypes = [C.POINTER(Config), C.POINTER(InterpIO)] + [C.POINTER(i32)] * 4
+    L.mpassit_interp_data.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(InterpIO), cp, C.c_size_t]
+    _lib = L
+    return L
+
+
+def _err():
+    return C.create_string_buffer(2048)
+
+
+def read_setup_namelist(path: str) -> Config:
+    cfg, e = Config(), _err()
+    rc = load().mpassit_read_setup_namelist(path.encode(), C.byref(cfg), e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return cfg
+
+
+def read_varlist(path: str) -> list[tuple[str, str]]:
+    n, e = C.c_int32(), _err()
+    cap = 512
+    a = C.create_string_buffer(cap * NAMELEN)
+    b = C.create_string_buffer(cap * NAMELEN)
+    rc = load().mpassit_read_varlist(path.encode(), cap, C.byref(n), a, b, e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    out = []
+    for k in range(n.value):
+        out.append((a.raw[k * NAMELEN:(k + 1) * NAMELEN].split(b"\0")[0].decode(),
+                    b.raw[k * NAMELEN:(k + 1) * NAMELEN].split(b"\0")[0].decode()))
+    return out
+
+
+def classify_hist_2d(name: str) -> int:
+    return load().mpassit_classify_hist_2d(name.encode())
+
+
+def classify_hist_3d(name: str, wrf_mod_vars: bool) -> int:
+    return load().mpassit_classify_hist_3d(name.encode(), int(wrf_mod_vars))
+
+
+def classify_diag(name: str) -> int:
+    return load().mpassit_classify_diag(name.encode())
+
+
+def para_range(n1: int, n2: int, nprocs: int, irank: int) -> tuple[int, int]:
+    a, b = C.c_int32(), C.c_int32()
+    load().mpassit_para_range(n1, n2, nprocs, irank, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def read_block_decomp_file(path: str, ncells: int, npets: int) -> np.ndarray:
+    owner = np.empty(ncells, np.int32)
+    e = _err()
+    rc = load().mpassit_read_block_decomp_file(path.encode(), ncells, npets, owner.ctypes.data, e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return owner
+
+
+def target_dims(cfg: Config, stagger: int) -> tuple[int, int]:
+    ni, nj = C.c_int32(), C.c_int32()
+    load().mpassit_target_dims(C.byref(cfg), stagger, C.byref(ni), C.byref(nj))
+    return ni.value, nj.value
+
+
+def target_coords(cfg: Config, stagger: int) -> tuple[np.ndarray, np.ndarray]:
+    """(lat, lon) [nj][ni] degrees of one stagger of the projected target grid."""
+    ni, nj = target_dims(cfg, stagger)
+    lat = np.empty((nj, ni), np.float64)
+    lon = np.empty((nj, ni), np.float64)
+    e = _err()
+    rc = load().mpassit_target_coords(C.byref(cfg), stagger, lat.ctypes.data, lon.ctypes.data, e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return lat, lon
+
+
+def get_rotang(lat: np.ndarray, lon: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    lat = np.ascontiguousarray(lat, np.float64)
+    lon = np.ascontiguousarray(lon, np.float64)
+    nj, ni = lat.shape
+    cosa, sina = np.empty_like(lat), np.empty_like(lat)
+    load().mpassit_get_rotang(lat.ctypes.data, lon.ctypes.data, ni, nj, cosa.ctypes.data, sina.ctypes.data)
+    return cosa, sina
+
+
+@dataclass
+class FieldSpec:
+    name: str
+    target_name: str
+    nlev: int
+    src: object  # numpy array or torch CUDA tensor, [n][nlev] level-fastest (or [n] when nlev == 1)
+    dst: object  # [nlev][nj_slab][ni]
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if type(x).__module__.startswith("torch"):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+def _farr(specs):
+    arr = (Field * max(len(specs), 1))()
+    for k, s in enumerate(specs):
+        arr[k].name = s.name.encode()
+        arr[k].target_name = s.target_name.encode()
+        arr[k].nlev = int(s.nlev)
+        arr[k].src = _ptr(s.src)
+        arr[k].dst = _ptr(s.dst)
+    return arr
+
+
+def interp_data(rg, cfg: Config, *, diag=(), hist_2d=(), hist_3d=(), soil=(), ter=None, hgt=None, u_stag=None,
+                v_stag=None, cosa=None, sina=None, nz=0, src_dtype=_l.F32, dst_dtype=_l.F32, mem=_l.HOST) -> InterpIO:
+    """interp_data (interp.F90:92) on Regridder ``rg``; field lists are FieldSpec sequences in
+    var-list order.  Returns the InterpIO (with the regrid class of every field filled in)."""
+    io = InterpIO()
+    io.src_dtype, io.dst_dtype, io.mem, io.nz = src_dtype, dst_dtype, mem, nz
+    keep = [_farr(diag), _farr(hist_2d), _farr(hist_3d), _farr(soil)]
+    io.n_diag, io.diag = len(diag), keep[0]
+    io.n_hist_2d, io.hist_2d = len(hist_2d), keep[1]
+    io.n_hist_3d, io.hist_3d = len(hist_3d), keep[2]
+    io.n_soil, io.soil = len(soil), keep[3]
+    io.ter, io.hgt, io.u_stag, io.v_stag = _ptr(ter), _ptr(hgt), _ptr(u_stag), _ptr(v_stag)
+    if cosa is not None:
+        cosa = np.ascontiguousarray(cosa, np.float64)
+        sina = np.ascontiguousarray(sina, np.float64)
+        io.cosa, io.sina = cosa.ctypes.data, sina.ctypes.data
+    e = _err()
+    rc = load().mpassit_interp_data(rg.ctx, C.byref(cfg), C.byref(io), e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    io._keep = keep
+    return io

@@ -1,0 +1,220 @@
+// interp.cpp -- host mirror of the reference's hot path, interp.F90:92-465
+// (interp_data -> interp_diag_data / interp_hist_data) on top of the engine's
+// C ABI.  Same call order, same regrid classes, same quirks:
+//   * `method` is a carried variable: set to BILINEAR only when a 2-D patch
+//     variable exists (interp.F90:203-204), to CONSERVE by the cons bundle (:370)
+//     and NEAREST_STOD by the nstd bundle (:420); the soil bundle uses whatever
+//     it holds at that point (:436-443).
+//   * winds: cell-centre u,v -> mass points (:256-289), rotation at mass points
+//     (:291-293, LC only), then mass -> EDGE1 / EDGE2 by a grid-to-grid bilinear
+//     (:295-328).
+// What differs by design: fields that share a route are stacked into ONE batched
+// apply, and each distinct weight matrix is generated once (mprg_store memoises),
+// instead of the reference's 12 RegridStore calls.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpassit_host.h"
+
+namespace {
+
+struct Fail {
+    int rc;
+    std::string msg;
+};
+
+void ck(mprg_ctx *ctx, int rc, const char *where) {
+    // reference pattern: if (ESMF_logFoundError(rc)) call error_handler("IN <where>", rc)
+    if (rc != 0) throw Fail{rc, std::string("IN ") + where + ": " + mprg_last_error(ctx)};
+}
+
+struct Batch {
+    std::vector<const void *> src;
+    std::vector<void *> dst;
+    std::vector<int32_t> nlev;
+    void add(const void *s, void *d, int32_t n) { src.push_back(s); dst.push_back(d); nlev.push_back(n); }
+    bool empty() const { return src.empty(); }
+};
+
+void run(mprg_ctx *ctx, mprg_route *rh, Batch &b, int sdt, int smem, int ddt, int dmem, const char *where) {
+    if (b.empty()) return;
+    ck(ctx, mprg_apply(ctx, rh, (int32_t)b.src.size(), b.src.data(), b.nlev.data(), sdt, smem, b.dst.data(), ddt, dmem),
+       where);
+    b = Batch();
+}
+
+// ESMF_REGRIDMETHOD flags carried in `method`; -1 = never assigned (Fortran: undefined)
+constexpr int kUnset = -1;
+
+}  // namespace
+
+extern "C" {
+
+int mpassit_classify_fields(const mpassit_config *cfg, mpassit_interp_io *io, int32_t *do_u, int32_t *do_v,
+                            int32_t *u10_ind, int32_t *v10_ind) {
+    if (!cfg || !io) return 1;
+    int32_t du = 0, dv = 0, u10 = -1, v10 = -1;
+    for (int i = 0; i < io->n_diag; ++i) {
+        io->diag[i].klass = mpassit_classify_diag(io->diag[i].name);
+        if (!std::strcmp(io->diag[i].name, "u10")) u10 = i;  // input_data.F90:173-180
+        if (!std::strcmp(io->diag[i].name, "v10")) v10 = i;
+    }
+    for (int i = 0; i < io->n_hist_2d; ++i) io->hist_2d[i].klass = mpassit_classify_hist_2d(io->hist_2d[i].name);
+    for (int i = 0; i < io->n_hist_3d; ++i) {
+        io->hist_3d[i].klass = mpassit_classify_hist_3d(io->hist_3d[i].name, cfg->wrf_mod_vars);
+        if (io->hist_3d[i].klass == MPASSIT_CLASS_U) du = 1;
+        if (io->hist_3d[i].klass == MPASSIT_CLASS_V) dv = 1;
+    }
+    for (int i = 0; i < io->n_soil; ++i) io->soil[i].klass = MPASSIT_CLASS_SOIL;
+    if (do_u) *do_u = du;
+    if (do_v) *do_v = dv;
+    if (u10_ind) *u10_ind = u10;
+    if (v10_ind) *v10_ind = v10;
+    return 0;
+}
+
+int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp_io *io, char *err, size_t errlen) {
+    if (!ctx || !cfg || !io) return 1;
+    void *d_um = nullptr, *d_vm = nullptr;
+    std::vector<mprg_route *> held;
+    int rc_out = 0;
+    try {
+        int32_t do_u = 0, do_v = 0, u10 = -1, v10 = -1;
+        mpassit_classify_fields(cfg, io, &do_u, &do_v, &u10, &v10);
+        const int sdt = io->src_dtype, ddt = io->dst_dtype, mem = io->mem;
+        auto store = [&](int method, int src_loc, int stagger, const char *where) {
+            mprg_route *rh = nullptr;
+            ck(ctx, mprg_store(ctx, method, src_loc, stagger, &rh), where);
+            held.push_back(rh);
+            return rh;
+        };
+        const bool rotate = cfg->proj_code == MPASSIT_PROJ_LC && io->cosa && io->sina;
+        if (rotate) ck(ctx, mprg_set_rotation(ctx, io->cosa, io->sina), "set_rotation");
+
+        // ---------------- interp_diag_data, interp.F90:107-141 ----------------
+        if (cfg->interp_diag && io->n_diag > 0) {
+            mprg_route *rh = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
+            Batch b;
+            for (int i = 0; i < io->n_diag; ++i) b.add(io->diag[i].src, io->diag[i].dst, io->diag[i].nlev);
+            run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+            if (u10 >= 0 && v10 >= 0 && rotate)  // interp.F90:138-139
+                ck(ctx, mprg_rotate_winds(ctx, io->diag[u10].dst, io->diag[v10].dst, 1, ddt, mem), "rotate_winds_cgrid");
+        }
+
+        // ---------------- interp_hist_data, interp.F90:183-465 ----------------
+        if (cfg->interp_hist) {
+            int method = kUnset;
+            int n2p = 0, n2c = 0, n2n = 0, n3 = 0, n3p1 = 0, n3v = 0;
+            for (int i = 0; i < io->n_hist_2d; ++i) {
+                n2p += io->hist_2d[i].klass == MPASSIT_CLASS_2D_PATCH;
+                n2c += io->hist_2d[i].klass == MPASSIT_CLASS_2D_CONS;
+                n2n += io->hist_2d[i].klass == MPASSIT_CLASS_2D_NSTD;
+            }
+            for (int i = 0; i < io->n_hist_3d; ++i) {
+                n3 += io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZ;
+                n3p1 += io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZP1;
+                n3v += io->hist_3d[i].klass == MPASSIT_CLASS_3D_VERT;
+            }
+            if (n2p > 0) method = MPRG_BILINEAR;  // interp.F90:203-204
+            // interp.F90:226-358 use `method` unconditionally; Fortran leaves it undefined when no
+            // 2-D patch variable is listed.  ESMF_REGRIDMETHOD_BILINEAR is the zero flag, which is
+            // what zero-initialised storage yields, so that is what the mirror assumes.
+            const int m_bil = method == kUnset ? MPRG_BILINEAR : method;
+
+            // one stacked apply for everything on the bilinear element->CENTER route:
+            // 2d_patch (:207-221), hgt (:226-238), 3d_nz (:240-254), 3d_nzp1 (:331-347)
+            {
+                Batch b;
+                for (int i = 0; i < io->n_hist_2d; ++i)
+                    if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_PATCH) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
+                if (io->ter && io->hgt) b.add(io->ter, io->hgt, 1);
+                for (int i = 0; i < io->n_hist_3d; ++i)
+                    if (io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZ || io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZP1)
+                        b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
+                if (!b.empty()) {
+                    mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
+                    run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                }
+            }
+
+            // winds, interp.F90:256-328
+            if (do_u || do_v) {
+                const mpassit_field *fu = nullptr, *fv = nullptr;
+                for (int i = 0; i < io->n_hist_3d; ++i) {
+                    if (io->hist_3d[i].klass == MPASSIT_CLASS_U) fu = &io->hist_3d[i];
+                    if (io->hist_3d[i].klass == MPASSIT_CLASS_V) fv = &io->hist_3d[i];
+                }
+                int32_t j0 = 0, j1 = 0, ni = 0, nj = 0;
+                mpassit_target_dims(cfg, MPRG_CENTER, &ni, &nj);
+                ck(ctx, mprg_get_slab(ctx, MPRG_CENTER, &j0, &j1), "get_slab");
+                const size_t nslab = (size_t)(j1 - j0) * ni;
+                mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldRegridStore");
+                // mass-point winds stay on the device in fp64 (the reference's R8 fields)
+                Batch b;
+                if (fu) { ck(ctx, mprg_device_alloc(ctx, nslab * fu->nlev * 8, &d_um), "device_alloc"); b.add(fu->src, d_um, fu->nlev); }
+                if (fv) { ck(ctx, mprg_device_alloc(ctx, nslab * fv->nlev * 8, &d_vm), "device_alloc"); b.add(fv->src, d_vm, fv->nlev); }
+                run(ctx, rh, b, sdt, mem, MPRG_F64, MPRG_DEVICE, "FieldRegrid");
+                if (fu && fv && rotate)  // interp.F90:291-293
+                    ck(ctx, mprg_rotate_winds(ctx, d_um, d_vm, fu->nlev, MPRG_F64, MPRG_DEVICE), "rotate_winds_cgrid");
+                if (fu && io->u_stag) {  // interp.F90:295-311
+                    mprg_route *ru = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE1, "FieldRegridStore");
+                    const void *s = d_um; void *d = io->u_stag; int32_t nl = fu->nlev;
+                    ck(ctx, mprg_apply(ctx, ru, 1, &s, &nl, MPRG_F64, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                }
+                if (fv && io->v_stag) {  // interp.F90:313-328
+                    mprg_route *rv = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE2, "FieldRegridStore");
+                    const void *s = d_vm; void *d = io->v_stag; int32_t nl = fv->nlev;
+                    ck(ctx, mprg_apply(ctx, rv, 1, &s, &nl, MPRG_F64, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                }
+            }
+
+            // 3d_vert bundle (source on mesh nodes), interp.F90:350-366
+            if (n3v > 0) {
+                mprg_route *rh = store(m_bil, MPRG_SRC_MESH_NODE, MPRG_CENTER, "FieldBundleRegridStore");
+                Batch b;
+                for (int i = 0; i < io->n_hist_3d; ++i)
+                    if (io->hist_3d[i].klass == MPASSIT_CLASS_3D_VERT)
+                        b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+            }
+            // 2d_cons bundle, interp.F90:368-416 (bundle and per-field paths apply the same matrix)
+            if (n2c > 0) {
+                method = MPRG_CONSERVE;
+                mprg_route *rh = store(method, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
+                Batch b;
+                for (int i = 0; i < io->n_hist_2d; ++i)
+                    if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_CONS) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+            }
+            // 2d_nstd bundle, interp.F90:418-434
+            if (n2n > 0) {
+                method = MPRG_NEAREST_STOD;
+                mprg_route *rh = store(method, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
+                Batch b;
+                for (int i = 0; i < io->n_hist_2d; ++i)
+                    if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_NSTD) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+            }
+            // soil bundle: whatever `method` holds now, interp.F90:436-447
+            if (io->n_soil > 0) {
+                const int m_soil = method == kUnset ? MPRG_BILINEAR : method;
+                mprg_route *rh = store(m_soil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
+                Batch b;
+                for (int i = 0; i < io->n_soil; ++i) b.add(io->soil[i].src, io->soil[i].dst, io->soil[i].nlev);
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+            }
+        }
+    } catch (const Fail &f) {
+        if (err && errlen) std::snprintf(err, errlen, "%s", f.msg.c_str());
+        rc_out = f.rc ? f.rc : 1;
+    }
+    // interp.F90:449-464 FieldBundleRegridRelease (here: every handle taken above)
+    for (mprg_route *rh : held) mprg_release(ctx, rh);
+    if (d_um) mprg_device_free(ctx, d_um);
+    if (d_vm) mprg_device_free(ctx, d_vm);
+    return rc_out;
+}
+
+}  // extern "C"

@@ -65,7 +65,8 @@ class Route:
         v = [C.c_int64() for _ in range(4)]
         rc = _l.load().mprg_route_info(self.handle, *[C.byref(x) for x in v])
         _l.check(self.owner.ctx, rc)
-        return dict(nDst=v[0].value, nnz=v[1].value, nUnmapped=v[2].value, nSrc=v[3].value)
+        return dict(nDst=v[0].value, nnz=v[1].value, nUnmapped=v[2].value, nSrc=v[3].value,
+                    nSrcRef=int(_l.load().mprg_route_src_referenced(self.handle)))
 
     def export_csr(self):
         i = self.info()
@@ -127,6 +128,18 @@ class Regridder:
     @property
     def last_ms(self) -> float:
         return float(self.L.mprg_last_ms(self.ctx))
+
+    # ---- profiling ------------------------------------------------------
+    def profile(self, on: bool = True) -> None:
+        self._ck(self.L.mprg_profile_enable(self.ctx, int(on)))
+        self._ck(self.L.mprg_profile_reset(self.ctx))
+
+    def profile_read(self) -> list[dict]:
+        n = self.L.mprg_profile_read(self.ctx, 0, None, None, None, None)
+        kind = np.zeros(max(n, 1), np.int32)
+        ms, by, un = (np.zeros(max(n, 1), np.float64) for _ in range(3))
+        self.L.mprg_profile_read(self.ctx, n, kind.ctypes.data, ms.ctypes.data, by.ctypes.data, un.ctypes.data)
+        return [dict(kind=int(kind[i]), ms=float(ms[i]), alg_bytes=float(by[i]), units=float(un[i])) for i in range(n)]
 
     # ---- geometry -------------------------------------------------------
     def set_mesh(self, lonCell, latCell, lonVertex, latVertex, verticesOnCell) -> None:

@@ -459,3 +459,393 @@ void orc_rotate_winds_f32(int64_t n, int32_t nlev, float *u, float *v, const dou
         }
     }
 }
+
+/* ------------------------------------------------------------------------ */
+/* (7) BILINEAR, Grid(CENTER) -> Grid(EDGE1 / EDGE2)  (interp.F90:298,316)    */
+/* ------------------------------------------------------------------------ */
+/* Source elements are the quads of 4 adjacent centre points; element id =
+ * j*(ni-1)+i (grid sequence order, i fastest).  ESMF maps a point into a quad
+ * by Newton iteration on   q0 + u B + v C + u v A = t p   (B=q1-q0, C=q3-q0,
+ * A=q0-q1+q2-q3; start (0,0,0); stop when |F|^2 < 1e-20; at most 100 steps),
+ * accepts iff u,v in [-tol, 1+tol] and t > 0; weights
+ * ((1-u)(1-v), u(1-v), u v, (1-u) v) on (q0,q1,q2,q3) = (i,j),(i+1,j),(i+1,j+1),(i,j+1). */
+static int invert3(const double *J, double *inv) {
+    double c00 = J[4] * J[8] - J[5] * J[7];
+    double c01 = J[5] * J[6] - J[3] * J[8];
+    double c02 = J[3] * J[7] - J[4] * J[6];
+    double det = (J[0] * c00 + J[1] * c01) + J[2] * c02;
+    if (det == 0.0) return 0;
+    double id = 1.0 / det;
+    inv[0] = c00 * id;
+    inv[1] = (J[2] * J[7] - J[1] * J[8]) * id;
+    inv[2] = (J[1] * J[5] - J[2] * J[4]) * id;
+    inv[3] = c01 * id;
+    inv[4] = (J[0] * J[8] - J[2] * J[6]) * id;
+    inv[5] = (J[2] * J[3] - J[0] * J[5]) * id;
+    inv[6] = c02 * id;
+    inv[7] = (J[1] * J[6] - J[0] * J[7]) * id;
+    inv[8] = (J[0] * J[4] - J[1] * J[3]) * id;
+    return 1;
+}
+
+static int quad_locate(const double *q0, const double *q1, const double *q2, const double *q3, const double *p,
+                       double *w) {
+    double A[3], B[3], C[3], X[3] = {0.0, 0.0, 0.0}, F[3], J[9], inv[9];
+    for (int d = 0; d < 3; ++d) {
+        A[d] = ((q0[d] - q1[d]) + q2[d]) - q3[d];
+        B[d] = q1[d] - q0[d];
+        C[d] = q3[d] - q0[d];
+    }
+    for (int it = 0; it < 100; ++it) {
+        for (int d = 0; d < 3; ++d)
+            F[d] = (((X[0] * X[1]) * A[d] + X[0] * B[d]) + X[1] * C[d]) - X[2] * p[d] + q0[d];
+        if ((F[0] * F[0] + F[1] * F[1]) + F[2] * F[2] < 1.0e-20) break;
+        for (int d = 0; d < 3; ++d) {
+            J[3 * d + 0] = A[d] * X[1] + B[d];
+            J[3 * d + 1] = A[d] * X[0] + C[d];
+            J[3 * d + 2] = -p[d];
+        }
+        if (!invert3(J, inv)) return 0;
+        for (int r = 0; r < 3; ++r)
+            X[r] = X[r] - ((inv[3 * r] * F[0] + inv[3 * r + 1] * F[1]) + inv[3 * r + 2] * F[2]);
+    }
+    double u = X[0], v = X[1], t = X[2];
+    if (!(t > 0.0)) return 0;
+    if (!(u >= -ORC_TOL && u <= 1.0 + ORC_TOL && v >= -ORC_TOL && v <= 1.0 + ORC_TOL)) return 0;
+    w[0] = (1.0 - u) * (1.0 - v);
+    w[1] = u * (1.0 - v);
+    w[2] = u * v;
+    w[3] = (1.0 - u) * v;
+    return 1;
+}
+
+typedef struct {
+    const double *sxyz;
+    int32_t ni, nj;
+    const double *p;
+    int64_t best;
+    double w[4];
+} quad_ctx;
+
+static void quad_try(int32_t i, int32_t j, quad_ctx *c) {
+    if (i < 0 || j < 0 || i >= c->ni - 1 || j >= c->nj - 1) return;
+    int64_t id = (int64_t)j * (c->ni - 1) + i;
+    if (c->best >= 0 && id >= c->best) return;
+    const double *q0 = c->sxyz + 3 * ((int64_t)j * c->ni + i);
+    const double *q1 = q0 + 3, *q3 = q0 + 3 * (int64_t)c->ni, *q2 = q3 + 3;
+    double w[4];
+    if (quad_locate(q0, q1, q2, q3, c->p, w)) {
+        c->best = id;
+        for (int k = 0; k < 4; ++k) c->w[k] = w[k];
+    }
+}
+static void quad_visit_point(int32_t pt, void *vctx) {
+    quad_ctx *c = (quad_ctx *)vctx;
+    int32_t i = pt % c->ni, j = pt / c->ni;
+    quad_try(i - 1, j - 1, c);
+    quad_try(i, j - 1, c);
+    quad_try(i - 1, j, c);
+    quad_try(i, j, c);
+}
+
+/* elem = winning quad id or -1; col [nDst][4] = source point ids (j*ni+i) of
+ * (q0,q1,q2,q3); w [nDst][4]. */
+int orc_bilinear_quadgrid(int32_t ni, int32_t nj, const double *sxyz, int64_t nDst, const double *dxyz,
+                          int64_t *elem, int32_t *col, double *w, int brute) {
+    if (ni < 2 || nj < 2) return -1;
+    kdtree *t = NULL;
+    double r2 = 0.0;
+    if (!brute) {
+        double m2 = 0.0;
+        for (int32_t j = 0; j < nj - 1; ++j)
+            for (int32_t i = 0; i < ni - 1; ++i) {
+                const double *q0 = sxyz + 3 * ((int64_t)j * ni + i);
+                double d1 = dist2(q0, q0 + 3 * ((int64_t)ni + 1)), d2 = dist2(q0 + 3, q0 + 3 * (int64_t)ni);
+                if (d1 > m2) m2 = d1;
+                if (d2 > m2) m2 = d2;
+            }
+        double r = sqrt(m2) * 1.001 + 1e-9;
+        r2 = r * r;
+        t = kd_build(ni * nj, sxyz);
+    }
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t n = 0; n < nDst; ++n) {
+        quad_ctx c;
+        c.sxyz = sxyz; c.ni = ni; c.nj = nj; c.p = dxyz + 3 * n; c.best = -1;
+        c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.0;
+        if (brute) {
+            for (int32_t j = 0; j < nj - 1; ++j)
+                for (int32_t i = 0; i < ni - 1; ++i) quad_try(i, j, &c);
+        } else {
+            kd_radius_rec(t, 0, ni * nj, c.p, r2, quad_visit_point, &c);
+        }
+        elem[n] = c.best;
+        if (c.best >= 0) {
+            int32_t i = (int32_t)(c.best % (ni - 1)), j = (int32_t)(c.best / (ni - 1));
+            int32_t b = j * ni + i;
+            col[4 * n + 0] = b; col[4 * n + 1] = b + 1; col[4 * n + 2] = b + ni + 1; col[4 * n + 3] = b + ni;
+            for (int k = 0; k < 4; ++k) w[4 * n + k] = c.w[k];
+        } else {
+            for (int k = 0; k < 4; ++k) { col[4 * n + k] = -1; w[4 * n + k] = 0.0; }
+        }
+    }
+    if (t) kd_free(t);
+    return 0;
+}
+
+/* Level-slowest source variant of the apply (source is itself a [lev][plane]
+ * grid field: u/v_target_grid_nostag, interp.F90:307,325). */
+void orc_apply_planes_f64(int64_t nDst, const int32_t *rowptr, const int32_t *col, const double *w, int32_t nlev,
+                          int64_t srcPlane, const double *src, double *dst) {
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < nDst; ++t)
+        for (int32_t l = 0; l < nlev; ++l) {
+            double acc = 0.0;
+            for (int32_t k = rowptr[t]; k < rowptr[t + 1]; ++k) acc = acc + w[k] * src[(int64_t)l * srcPlane + col[k]];
+            dst[(int64_t)l * nDst + t] = acc;
+        }
+}
+
+/* ------------------------------------------------------------------------ */
+/* (8) CONSERVE, first order  (interp.F90:370-407; snow, snowh)              */
+/* ------------------------------------------------------------------------ */
+/* w_ij = area(S_j ^ D_i) / area(D_i)   (normType DSTAREA, no renormalisation
+ * of partially covered destination cells).  S_j = Voronoi polygon of source
+ * cell j (verticesOnCell order, model_grid.F90:446-486), D_i = quad of the 4
+ * CORNER-stagger points around centre i (model_grid.F90:962-980).  Edges are
+ * great circles (lineType GREAT_CIRCLE is ESMF's default for conservative).
+ * Intersection: Sutherland-Hodgman clip of S_j by the 4 great-circle planes of
+ * D_i; areas: fan of spherical triangles,
+ *   E = 2 atan2(|a.((b-a)x(c-a))|, 1 + a.b + b.c + c.a). */
+#define ORC_MAXPOLY 40
+
+static double sph_tri_area(const double *a, const double *b, const double *c) {
+    double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    double ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    double n[3];
+    cross3(ab, ac, n);
+    double num = fabs(dot3(a, n));
+    double den = ((1.0 + dot3(a, b)) + dot3(b, c)) + dot3(c, a);
+    return 2.0 * atan2(num, den);
+}
+
+static double sph_poly_area(const double *v, int n) {
+    double s = 0.0;
+    for (int k = 1; k + 1 < n; ++k) s = s + sph_tri_area(v, v + 3 * k, v + 3 * (k + 1));
+    return s;
+}
+
+/* make counter-clockwise seen from outside the sphere (reverse in place if not) */
+static void orient_ccw(double *v, int n) {
+    double s = 0.0, nrm[3], e1[3], e2[3];
+    for (int k = 1; k + 1 < n; ++k) {
+        for (int d = 0; d < 3; ++d) { e1[d] = v[3 * k + d] - v[d]; e2[d] = v[3 * (k + 1) + d] - v[d]; }
+        cross3(e1, e2, nrm);
+        s = s + dot3(v, nrm);
+    }
+    if (s < 0.0)
+        for (int a = 0, b = n - 1; a < b; ++a, --b)
+            for (int d = 0; d < 3; ++d) { double t = v[3 * a + d]; v[3 * a + d] = v[3 * b + d]; v[3 * b + d] = t; }
+}
+
+static int clip_by_plane(const double *in, int n, const double *nrm, double *out) {
+    int m = 0;
+    if (n == 0) return 0;
+    const double *s = in + 3 * (n - 1);
+    double ds = dot3(nrm, s);
+    for (int k = 0; k < n; ++k) {
+        const double *e = in + 3 * k;
+        double de = dot3(nrm, e);
+        if ((de >= 0.0) != (ds >= 0.0)) {
+            double tau = ds / (ds - de);
+            double x[3] = {s[0] + tau * (e[0] - s[0]), s[1] + tau * (e[1] - s[1]), s[2] + tau * (e[2] - s[2])};
+            double inv = 1.0 / sqrt(dot3(x, x));
+            if (m < ORC_MAXPOLY) { out[3 * m] = x[0] * inv; out[3 * m + 1] = x[1] * inv; out[3 * m + 2] = x[2] * inv; ++m; }
+        }
+        if (de >= 0.0 && m < ORC_MAXPOLY) { out[3 * m] = e[0]; out[3 * m + 1] = e[1]; out[3 * m + 2] = e[2]; ++m; }
+        s = e;
+        ds = de;
+    }
+    return m;
+}
+
+/* overlap area of source polygon sp (ns vertices, CCW) with destination quad dq (CCW) */
+static double overlap_area(const double *sp, int ns, const double *dq) {
+    double a[3 * ORC_MAXPOLY], b[3 * ORC_MAXPOLY];
+    memcpy(a, sp, sizeof(double) * 3 * (size_t)ns);
+    int n = ns;
+    double *cur = a, *nxt = b;
+    for (int e = 0; e < 4 && n > 0; ++e) {
+        double nrm[3];
+        cross3(dq + 3 * e, dq + 3 * ((e + 1) % 4), nrm);
+        n = clip_by_plane(cur, n, nrm, nxt);
+        double *t = cur; cur = nxt; nxt = t;
+    }
+    if (n < 3) return 0.0;
+    return sph_poly_area(cur, n);
+}
+
+typedef struct {
+    const double *vxyz;
+    const int32_t *voc;
+    int32_t maxEdges;
+    const double *dq;
+    double dstArea;
+    int32_t *col;   /* NULL in the counting pass */
+    double *w;
+    int32_t n, cap;
+} cons_ctx;
+
+static void cons_visit_cell(int32_t cell, void *vctx) {
+    cons_ctx *c = (cons_ctx *)vctx;
+    double sp[3 * ORC_MAXPOLY];
+    int ns = 0;
+    for (int32_t k = 0; k < c->maxEdges && ns < ORC_MAXPOLY - 8; ++k) {
+        int32_t v = c->voc[(int64_t)cell * c->maxEdges + k];
+        if (v <= 0) continue;
+        memcpy(sp + 3 * ns, c->vxyz + 3 * (int64_t)(v - 1), 3 * sizeof(double));
+        ++ns;
+    }
+    if (ns < 3) return;
+    orient_ccw(sp, ns);
+    double ar = overlap_area(sp, ns, c->dq);
+    if (!(ar > 0.0)) return;
+    if (c->col) {
+        /* insertion by ascending source id */
+        int32_t pos = c->n;
+        while (pos > 0 && c->col[pos - 1] > cell) { c->col[pos] = c->col[pos - 1]; c->w[pos] = c->w[pos - 1]; --pos; }
+        c->col[pos] = cell;
+        c->w[pos] = ar / c->dstArea;
+    }
+    c->n++;
+}
+
+/* Two-pass CSR: call with col == NULL to fill rowcount[nDst]; build rowptr; call
+ * again with col/w sized rowptr[nDst].  corner_xyz: [(nj+1)][(ni+1)][3];
+ * destination cell (i,j) (0-based, t = j*ni+i) uses corners (i,j),(i+1,j),
+ * (i+1,j+1),(i,j+1).  cxyz = source cell centres (search only). */
+int orc_conserve(int32_t nCells, const double *cxyz, const double *vxyz, int32_t maxEdges, const int32_t *voc,
+                 int32_t ni, int32_t nj, const double *corner_xyz, int32_t *rowcount, const int32_t *rowptr,
+                 int32_t *col, double *w, int brute) {
+    kdtree *t = NULL;
+    double rs = 0.0;
+    if (!brute) {
+        /* largest centre->vertex distance over all source cells */
+        for (int32_t c = 0; c < nCells; ++c)
+            for (int32_t k = 0; k < maxEdges; ++k) {
+                int32_t v = voc[(int64_t)c * maxEdges + k];
+                if (v <= 0) continue;
+                double d = dist2(cxyz + 3 * (int64_t)c, vxyz + 3 * (int64_t)(v - 1));
+                if (d > rs) rs = d;
+            }
+        rs = sqrt(rs);
+        t = kd_build(nCells, cxyz);
+    }
+    int64_t nDst = (int64_t)ni * nj;
+#pragma omp parallel for schedule(dynamic, 128)
+    for (int64_t n = 0; n < nDst; ++n) {
+        int32_t i = (int32_t)(n % ni), j = (int32_t)(n / ni);
+        double dq[12];
+        const double *c00 = corner_xyz + 3 * ((int64_t)j * (ni + 1) + i);
+        memcpy(dq, c00, 24);
+        memcpy(dq + 3, c00 + 3, 24);
+        memcpy(dq + 6, c00 + 3 * ((int64_t)ni + 2), 24);
+        memcpy(dq + 9, c00 + 3 * ((int64_t)ni + 1), 24);
+        orient_ccw(dq, 4);
+        cons_ctx c;
+        c.vxyz = vxyz; c.voc = voc; c.maxEdges = maxEdges; c.dq = dq;
+        c.dstArea = sph_poly_area(dq, 4);
+        c.n = 0; c.cap = 0;
+        c.col = col ? col + rowptr[n] : NULL;
+        c.w = w ? w + rowptr[n] : NULL;
+        if (c.dstArea > 0.0) {
+            if (brute) {
+                for (int32_t s = 0; s < nCells; ++s) cons_visit_cell(s, &c);
+            } else {
+                double cen[3] = {((dq[0] + dq[3]) + dq[6]) + dq[9], ((dq[1] + dq[4]) + dq[7]) + dq[10],
+                                 ((dq[2] + dq[5]) + dq[8]) + dq[11]};
+                double inv = 1.0 / sqrt(dot3(cen, cen));
+                cen[0] *= inv; cen[1] *= inv; cen[2] *= inv;
+                double rd = 0.0;
+                for (int k = 0; k < 4; ++k) { double d = dist2(cen, dq + 3 * k); if (d > rd) rd = d; }
+                double r = (sqrt(rd) + rs) * 1.001 + 1e-9;
+                kd_radius_rec(t, 0, nCells, cen, r * r, cons_visit_cell, &c);
+            }
+        }
+        if (rowcount) rowcount[n] = c.n;
+    }
+    if (t) kd_free(t);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* (9) BILINEAR, Mesh(node) -> Grid  (vorticity bundle, interp.F90:350-366)   */
+/* ------------------------------------------------------------------------ */
+/* Source values sit on the Voronoi vertices; source elements are the original
+ * polygons.  ESMF splits polygons with more than 4 corners into triangles
+ * before bilinear mapping; the exact split is an ESMF-internal choice that
+ * cannot be checked here, so this restatement (and the engine) use a fan from
+ * the polygon's first vertex in verticesOnCell order, for every polygon size.
+ * Element id = cell id: smallest accepting cell wins, then its first accepting
+ * fan triangle.  col [nDst][3] = vertex ids (0-based), w [nDst][3]. */
+typedef struct {
+    const double *vxyz;
+    const int32_t *voc;
+    int32_t maxEdges;
+    const double *p;
+    int32_t best;
+    int32_t c[3];
+    double w[3];
+} node_ctx;
+
+static void node_visit_cell(int32_t cell, void *vctx) {
+    node_ctx *c = (node_ctx *)vctx;
+    if (c->best >= 0 && cell >= c->best) return;
+    int32_t v0 = -1, vp = -1;
+    for (int32_t k = 0; k < c->maxEdges; ++k) {
+        int32_t v = c->voc[(int64_t)cell * c->maxEdges + k];
+        if (v <= 0) continue;
+        v -= 1;
+        if (v0 < 0) { v0 = v; continue; }
+        if (vp < 0) { vp = v; continue; }
+        double w[3];
+        if (tri_locate(c->vxyz + 3 * (int64_t)v0, c->vxyz + 3 * (int64_t)vp, c->vxyz + 3 * (int64_t)v, c->p, w)) {
+            c->best = cell;
+            c->c[0] = v0; c->c[1] = vp; c->c[2] = v;
+            c->w[0] = w[0]; c->w[1] = w[1]; c->w[2] = w[2];
+            return;
+        }
+        vp = v;
+    }
+}
+
+int orc_bilinear_node(int32_t nCells, const double *cxyz, const double *vxyz, int32_t maxEdges, const int32_t *voc,
+                      int64_t nDst, const double *dxyz, int32_t *elem, int32_t *col, double *w, int brute) {
+    kdtree *t = NULL;
+    double r2 = 0.0;
+    if (!brute) {
+        double rs = 0.0;
+        for (int32_t c = 0; c < nCells; ++c)
+            for (int32_t k = 0; k < maxEdges; ++k) {
+                int32_t v = voc[(int64_t)c * maxEdges + k];
+                if (v <= 0) continue;
+                double d = dist2(cxyz + 3 * (int64_t)c, vxyz + 3 * (int64_t)(v - 1));
+                if (d > rs) rs = d;
+            }
+        double r = sqrt(rs) * 1.01 + 1e-9;
+        r2 = r * r;
+        t = kd_build(nCells, cxyz);
+    }
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < nDst; ++i) {
+        node_ctx c;
+        c.vxyz = vxyz; c.voc = voc; c.maxEdges = maxEdges; c.p = dxyz + 3 * i; c.best = -1;
+        c.c[0] = c.c[1] = c.c[2] = -1; c.w[0] = c.w[1] = c.w[2] = 0.0;
+        if (brute) for (int32_t s = 0; s < nCells; ++s) node_visit_cell(s, &c);
+        else kd_radius_rec(t, 0, nCells, c.p, r2, node_visit_cell, &c);
+        elem[i] = c.best;
+        for (int k = 0; k < 3; ++k) { col[3 * i + k] = c.c[k]; w[3 * i + k] = c.w[k]; }
+    }
+    if (t) kd_free(t);
+    return 0;
+}

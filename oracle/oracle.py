@@ -54,9 +54,16 @@ def lib():
             getattr(L, name).argtypes = [C.c_int64, _i32p, _i32p, _f64p, C.c_int32, tin, tout]
         L.orc_rotate_winds.argtypes = [C.c_int64, C.c_int32, _f64p, _f64p, _f64p, _f64p]
         L.orc_rotate_winds_f32.argtypes = [C.c_int64, C.c_int32, _f32p, _f32p, _f64p, _f64p]
-        for opt in ("orc_conserve_count", "orc_conserve_fill", "orc_bilinear_quadgrid", "orc_bilinear_polygon"):
-            if hasattr(L, opt):
-                pass
+        _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        L.orc_bilinear_quadgrid.argtypes = [C.c_int32, C.c_int32, _f64p, C.c_int64, _f64p, _i64p, _i32p, _f64p, C.c_int]
+        L.orc_bilinear_quadgrid.restype = C.c_int
+        L.orc_apply_planes_f64.argtypes = [C.c_int64, _i32p, _i32p, _f64p, C.c_int32, C.c_int64, _f64p, _f64p]
+        L.orc_conserve.argtypes = [C.c_int32, _f64p, _f64p, C.c_int32, _i32p, C.c_int32, C.c_int32, _f64p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_conserve.restype = C.c_int
+        L.orc_bilinear_node.argtypes = [C.c_int32, _f64p, _f64p, C.c_int32, _i32p, C.c_int64, _f64p, _i32p, _i32p,
+                                        _f64p, C.c_int]
+        L.orc_bilinear_node.restype = C.c_int
         _lib = L
     return _lib
 
@@ -165,3 +172,72 @@ def rotate_winds(u, v, cosa, sina):
     else:
         lib().orc_rotate_winds_f32(n, nlev, u, v, cosa, sina)
     return u, v
+
+
+def bilinear_quadgrid(src_xyz_grid, dst_xyz, brute=False):
+    """src_xyz_grid [nj][ni][3] (CENTER points) -> (elem, col [n][4], w [n][4])."""
+    src = np.ascontiguousarray(src_xyz_grid, np.float64)
+    nj, ni = src.shape[0], src.shape[1]
+    dst = np.ascontiguousarray(dst_xyz, np.float64).reshape(-1, 3)
+    n = dst.shape[0]
+    elem = np.empty(n, np.int64)
+    col = np.empty((n, 4), np.int32)
+    w = np.empty((n, 4), np.float64)
+    rc = lib().orc_bilinear_quadgrid(ni, nj, src.reshape(-1, 3), n, dst, elem, col, w, int(brute))
+    if rc != 0:
+        raise ValueError(f"orc_bilinear_quadgrid rc={rc}")
+    return elem, col, w
+
+
+def apply_planes(rowptr, col, w, src_planes):
+    """src [nlev][plane] fp64 -> dst [nlev][nDst] fp64 (level-slowest source)."""
+    src = np.ascontiguousarray(src_planes, np.float64)
+    if src.ndim == 1:
+        src = src.reshape(1, -1)
+    nlev, plane = src.shape
+    nDst = rowptr.shape[0] - 1
+    dst = np.empty((nlev, nDst), np.float64)
+    lib().orc_apply_planes_f64(nDst, np.ascontiguousarray(rowptr, np.int32), np.ascontiguousarray(col, np.int32),
+                               np.ascontiguousarray(w, np.float64), nlev, plane, src, dst)
+    return dst
+
+
+def conserve(cell_xyz, vert_xyz, verticesOnCell, corner_xyz_grid, brute=False):
+    """corner_xyz_grid [(nj+1)][(ni+1)][3] -> CSR (rowptr, col, w) over the ni x nj destination cells."""
+    cxyz = np.ascontiguousarray(cell_xyz, np.float64)
+    vxyz = np.ascontiguousarray(vert_xyz, np.float64)
+    voc = np.ascontiguousarray(verticesOnCell, np.int32)
+    cor = np.ascontiguousarray(corner_xyz_grid, np.float64)
+    nj, ni = cor.shape[0] - 1, cor.shape[1] - 1
+    n = ni * nj
+    cnt = np.zeros(n, np.int32)
+    L = lib()
+    rc = L.orc_conserve(cxyz.shape[0], cxyz, vxyz, voc.shape[1], voc, ni, nj, cor.reshape(-1, 3),
+                        cnt.ctypes.data, None, None, None, int(brute))
+    if rc != 0:
+        raise ValueError(f"orc_conserve rc={rc}")
+    rowptr = np.zeros(n + 1, np.int32)
+    np.cumsum(cnt, out=rowptr[1:])
+    col = np.empty(max(int(rowptr[-1]), 1), np.int32)
+    w = np.empty(max(int(rowptr[-1]), 1), np.float64)
+    rc = L.orc_conserve(cxyz.shape[0], cxyz, vxyz, voc.shape[1], voc, ni, nj, cor.reshape(-1, 3),
+                        None, rowptr.ctypes.data, col.ctypes.data, w.ctypes.data, int(brute))
+    if rc != 0:
+        raise ValueError(f"orc_conserve rc={rc}")
+    return rowptr, col[: rowptr[-1]], w[: rowptr[-1]]
+
+
+def bilinear_node(cell_xyz, vert_xyz, verticesOnCell, dst_xyz, brute=False):
+    """Source on mesh nodes (Voronoi vertices): (elem=cell id or -1, col [n][3] vertex ids, w [n][3])."""
+    cxyz = np.ascontiguousarray(cell_xyz, np.float64)
+    vxyz = np.ascontiguousarray(vert_xyz, np.float64)
+    voc = np.ascontiguousarray(verticesOnCell, np.int32)
+    dst = np.ascontiguousarray(dst_xyz, np.float64).reshape(-1, 3)
+    n = dst.shape[0]
+    elem = np.empty(n, np.int32)
+    col = np.empty((n, 3), np.int32)
+    w = np.empty((n, 3), np.float64)
+    rc = lib().orc_bilinear_node(cxyz.shape[0], cxyz, vxyz, voc.shape[1], voc, n, dst, elem, col, w, int(brute))
+    if rc != 0:
+        raise ValueError(f"orc_bilinear_node rc={rc}")
+    return elem, col, w

@@ -1,0 +1,206 @@
+"""GPU parity for the remaining regrid classes and for the whole interp_data pass:
+grid->grid stagger bilinear, conservative, node-based bilinear, and the host mirror's
+call sequence (interp.F90:92-465) end to end, all through the C ABI."""
+import numpy as np
+import pytest
+
+from mpassit_b200 import defaults
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rg(engine_lib):
+    from mpassit_b200.regrid import Regridder
+
+    r = Regridder(device=0)
+    yield r
+    r.close()
+
+
+@pytest.fixture(scope="module")
+def host(engine_lib):
+    from mpassit_b200 import build, host
+
+    build.build_host()
+    host.load()
+    return host
+
+
+@pytest.fixture(scope="module")
+def lc_case(host, tmp_path_factory):
+    """30-km Lambert target (60 x 40 mass points) over an irregular regional mesh that does
+    not cover it completely (unmapped rows + extrapolating nearest rows both occur)."""
+    d = tmp_path_factory.mktemp("lc")
+    cfg = host.read_setup_namelist(defaults.write_namelist(str(d / "namelist.input"), nx=61, ny=41, dx=30000.0))
+    grids = {k: host.target_coords(cfg, s) for k, s in (("M", 0), ("U", 1), ("V", 2), ("CORNER", 3))}
+    mesh = H.synth.regional_delaunay_mesh(9000, extent_x_m=1700e3, extent_y_m=1150e3, seed=21, lloyd_iters=3)
+    cosa, sina = host.get_rotang(*grids["M"])
+    return cfg, grids, mesh, cosa, sina
+
+
+def _load(rg, grids, mesh):
+    rg.set_mesh(mesh.lonCell, mesh.latCell, mesh.lonVertex, mesh.latVertex, mesh.verticesOnCell)
+    for k, s in (("M", 0), ("U", 1), ("V", 2), ("CORNER", 3)):
+        lat, lon = grids[k]
+        rg.set_target(s, lon, lat)
+
+
+def test_stagger_routes_bit_exact(rg, orc, lc_case):
+    from mpassit_b200 import lib as l
+
+    cfg, grids, mesh, cosa, sina = lc_case
+    _load(rg, grids, mesh)
+    lat, lon = grids["M"]
+    sx = orc.sph_deg_to_cart(lon, lat).reshape(lat.shape[0], lat.shape[1], 3)
+    for key, stag in (("U", l.EDGE1), ("V", l.EDGE2)):
+        slat, slon = grids[key]
+        e, c, w = orc.bilinear_quadgrid(sx, orc.sph_deg_to_cart(slon, slat), brute=True)
+        rp, cc, ww = orc.ell_to_csr(e >= 0, c, w)
+        r = rg.store(l.BILINEAR, l.SRC_GRID_CENTER, stag)
+        grp, gc, gw = r.export_csr()
+        assert np.array_equal(grp, rp) and np.array_equal(gc, cc)
+        assert np.abs(gw - ww).max() <= 1e-12
+        un = (e < 0).reshape(slat.shape)
+        # edge points outside the hull of the centres are unmapped: first/last column of U, first/last row of V
+        if key == "U":
+            assert un[:, 0].all() and un[:, -1].all() and not un[1:-1, 1:-1].any()
+        else:
+            assert un[0, :].all() and un[-1, :].all() and not un[1:-1, 1:-1].any()
+        # apply: fp64 level-slowest source -> fp32
+        src = np.random.default_rng(1).standard_normal((5, lat.size))
+        got = np.empty((5, slat.size), np.float32)
+        import torch
+
+        dsrc = torch.from_numpy(src).cuda()
+        dgot = torch.empty((5, slat.size), dtype=torch.float32, device="cuda")
+        rg.apply(r, [dsrc], [dgot], nlev=[5])
+        rg.synchronize()
+        got = dgot.cpu().numpy()
+        want = orc.apply_planes(rp, cc, ww, src).astype(np.float32)
+        np.testing.assert_allclose(got, want, rtol=2e-7, atol=1e-7)
+        r.release()
+
+
+def test_conserve_structure_weights_and_conservation(rg, orc, lc_case):
+    from mpassit_b200 import lib as l
+
+    cfg, grids, mesh, cosa, sina = lc_case
+    _load(rg, grids, mesh)
+    cxyz, vxyz, tri = H.oracle_geometry(orc, mesh)
+    clat, clon = grids["CORNER"]
+    cor = orc.sph_deg_to_cart(clon, clat).reshape(clat.shape[0], clat.shape[1], 3)
+    rp, cc, ww = orc.conserve(cxyz, vxyz, mesh.verticesOnCell, cor)
+    r = rg.store(l.CONSERVE, l.SRC_MESH_ELEMENT, l.CENTER)
+    grp, gc, gw = r.export_csr()
+    assert np.array_equal(grp, rp)            # which destination cells are touched, and by how many sources
+    assert np.array_equal(gc, cc)             # which sources (ascending ids)
+    assert np.abs(gw - ww).max() <= 1e-12
+    frac = np.zeros(rp.size - 1)
+    np.add.at(frac, np.repeat(np.arange(rp.size - 1), np.diff(rp)), gw)
+    # (the planar-Delaunay synthetic mesh is not exactly Delaunay on the sphere, so neighbouring polygons can
+    #  overlap by slivers of ~1e-7 of a cell; a true Voronoi tiling would give <= 1 to rounding)
+    assert frac.max() <= 1 + 1e-6 and (frac < 0.5).any() and (np.abs(frac - 1) < 1e-6).any()
+    # constant field -> covered fraction; patchy snow field vs oracle
+    lo, la = mesh.lonCell, mesh.latCell
+    snow = H.synth.patchy_field(lo, la)
+    ones = np.ones(mesh.nCells, np.float32)
+    o1 = np.empty((1, frac.size), np.float32)
+    o2 = np.empty((1, frac.size), np.float32)
+    rg.apply(r, [ones, snow], [o1, o2], nlev=[1, 1])
+    np.testing.assert_allclose(o1[0], frac.astype(np.float32), rtol=3e-7, atol=1e-7)
+    np.testing.assert_allclose(o2, orc.apply(rp, cc, ww, snow, np.float32), rtol=1e-5, atol=1e-6)
+    r.release()
+
+
+def test_node_bilinear(rg, orc, lc_case):
+    from mpassit_b200 import lib as l
+
+    cfg, grids, mesh, cosa, sina = lc_case
+    _load(rg, grids, mesh)
+    cxyz, vxyz, tri = H.oracle_geometry(orc, mesh)
+    lat, lon = grids["M"]
+    e, c, w = orc.bilinear_node(cxyz, vxyz, mesh.verticesOnCell, orc.sph_deg_to_cart(lon, lat), brute=True)
+    rp, cc, ww = orc.ell_to_csr(e >= 0, c, w)
+    r = rg.store(l.BILINEAR, l.SRC_MESH_NODE, l.CENTER)
+    grp, gc, gw = r.export_csr()
+    assert np.array_equal(grp, rp) and np.array_equal(gc, cc) and np.abs(gw - ww).max() <= 1e-12
+    vort = H.synth.smooth_field(mesh.lonVertex, mesh.latVertex, 12, seed=4)
+    got = np.empty((12, lat.size), np.float32)
+    rg.apply(r, [vort], [got])
+    np.testing.assert_allclose(got, orc.apply(rp, cc, ww, vort, np.float32), rtol=2e-7)
+    r.release()
+
+
+def _fields(mesh, nz=8, nsoil=4):
+    lo, la = mesh.lonCell, mesh.latCell
+    S = H.synth
+    diag = []
+    for k, (nm, _) in enumerate(defaults.DIAGLIST):
+        diag.append((nm, S.smooth_field(lo, la, nz if nm == "refl10cm" else 1, seed=100 + k).reshape(mesh.nCells, -1)))
+    h2 = []
+    for k, (nm, _) in enumerate(defaults.HISTLIST_2D):
+        if nm in ("snow", "snowh"):
+            a = S.patchy_field(lo, la, seed=k)
+        elif nm == "xland":
+            a = S.integer_field(mesh.nCells, 2)
+        else:
+            a = S.smooth_field(lo, la, 1, seed=200 + k).reshape(-1)
+        h2.append((nm, a.reshape(mesh.nCells, 1)))
+    h3 = []
+    for k, (nm, _) in enumerate(defaults.HISTLIST_3D):
+        nl = nz + 1 if nm in ("zgrid", "w") else nz
+        a = S.moisture_field(lo, la, nl, seed=300 + k) if nm.startswith("q") else S.smooth_field(lo, la, nl, seed=300 + k)
+        h3.append((nm, a))
+    soil = [(nm, np.ascontiguousarray(np.stack([S.integer_field(mesh.nCells, 30, seed=400 + 7 * k + s) for s in range(nsoil)], 1)))
+            for k, (nm, _) in enumerate(defaults.HISTLIST_SOIL)]
+    ter = S.smooth_field(lo, la, 1, seed=9).reshape(mesh.nCells, 1)
+    return dict(diag=diag, hist_2d=h2, hist_3d=h3, soil=soil, ter=ter)
+
+
+def test_interp_data_end_to_end(rg, orc, host, lc_case):
+    """Default parm lists + wrf_mod_vars: diag bundle, 2d patch, hgt, 3d nz/nzp1, wind chain with rotation and
+    staggering, conservative snow, nearest xland, and the soil bundle inheriting NEAREST_STOD."""
+    cfg, grids, mesh, cosa, sina = lc_case
+    _load(rg, grids, mesh)
+    nz, nsoil = 8, 4
+    F = _fields(mesh, nz, nsoil)
+    want = H.oracle_interp(orc, mesh, grids, F, cosa, sina)
+    nM, nU, nV = grids["M"][0].size, grids["U"][0].size, grids["V"][0].size
+
+    def specs(items, table):
+        tn = dict(table)
+        return [host.FieldSpec(nm, tn.get(nm, nm), a.shape[1], a, np.full((a.shape[1], nM), np.nan, np.float32)) for nm, a in items]
+
+    diag, h2, h3, soil = (specs(F["diag"], defaults.DIAGLIST), specs(F["hist_2d"], defaults.HISTLIST_2D),
+                          specs(F["hist_3d"], defaults.HISTLIST_3D), specs(F["soil"], defaults.HISTLIST_SOIL))
+    hgt = np.full((1, nM), np.nan, np.float32)
+    ust = np.full((nz, nU), np.nan, np.float32)
+    vst = np.full((nz, nV), np.nan, np.float32)
+    n0 = rg.kernel_launches
+    io = host.interp_data(rg, cfg, diag=diag, hist_2d=h2, hist_3d=h3, soil=soil, ter=F["ter"], hgt=hgt, u_stag=ust,
+                          v_stag=vst, cosa=cosa, sina=sina, nz=nz)
+    assert rg.kernel_launches > n0
+    got = {s.name: s.dst for s in diag + h2 + h3 + soil}
+    got["HGT"], got["U"], got["V"] = hgt, ust, vst
+    # regrid classes the mirror assigned (input_data.F90:840-911)
+    k3 = {F["hist_3d"][i][0]: io.hist_3d[i].klass for i in range(len(h3))}
+    assert k3["uReconstructZonal"] == host.CLASS_U and k3["zgrid"] == host.CLASS_3D_NZP1 and k3["theta"] == host.CLASS_3D_NZ
+    exact = {"xland", "tslb", "smois", "sh2o"}            # nearest-neighbour classes: bit-exact
+    for nm, w in want.items():
+        if nm in ("uReconstructZonal", "uReconstructMeridional"):
+            continue
+        g = got[nm]
+        assert not np.isnan(g).any(), nm
+        if nm in exact:
+            assert np.array_equal(g, w), nm
+        else:
+            scale = max(np.abs(w).max(), 1e-30)
+            assert np.abs(g - w).max() <= 1e-5 * scale, (nm, np.abs(g - w).max(), scale)
+    # the wind inputs are peeled off into U/V (their own dst buffers stay untouched)
+    assert np.isnan(got["uReconstructZonal"]).all()
+    # soil really used nearest neighbour (values are integers from the source, never blended)
+    assert np.array_equal(got["tslb"], np.round(got["tslb"]))
+    # unmapped bilinear points are exactly zero, and some exist in this case
+    assert (got["theta"] == 0).any() and (got["xland"] != 0).all()
