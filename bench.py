@@ -236,6 +236,9 @@ def main():
     t_setup = time.perf_counter()
     wl = workload.make(args.config)
     rg = Regridder(device=local_rank, rank=rank, nranks=world)
+    # a dedicated (non-default) stream: engine kernels and the timing events share it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     rg.use_torch_stream()
     workload.load_geometry(rg, wl)
     if world > 1:

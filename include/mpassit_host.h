@@ -107,7 +107,8 @@ typedef struct mpassit_interp_io {
      * [nz][nj+1][ni]; the rotated mass-point winds (UMASS/VMASS, never written to the
      * output file) stay on the device */
     void *u_stag, *v_stag;
-    const double *cosa, *sina;                 /* CENTER [nj][ni]; NULL => no rotation */
+    /* wind rotation (interp.F90:138,291) uses the angles registered once with mprg_set_rotation,
+     * the analogue of cosa/sina_target_grid created in define_target_grid (model_grid.F90:1113-1185) */
 } mpassit_interp_io;
 
 /* fills klass for every field (input_data.F90:283,858-911) and returns the

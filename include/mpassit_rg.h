@@ -66,6 +66,9 @@ int mprg_host_free(mprg_ctx *ctx, void *ptr);
  * winds between interp.F90:268 and :307 never need to visit the host) */
 int mprg_device_alloc(mprg_ctx *ctx, size_t bytes, void **ptr);
 int mprg_device_free(mprg_ctx *ctx, void *ptr);
+/* engine-owned device scratch that persists across calls (slot 0..7, grown on demand,
+ * freed by mprg_finalize): lets a host run interp_data repeatedly without allocating */
+int mprg_scratch(mprg_ctx *ctx, int slot, size_t bytes, void **ptr);
 
 /* ---- source mesh: replaces ESMF_MeshCreate, model_grid.F90:488-497.
  *      Takes the arrays exactly as read from the MPAS grid file
@@ -133,6 +136,7 @@ int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields,
  *      sina_target_grid, model_grid.F90:1113-1185).  u, v: this rank's CENTER
  *      slab [nlev][nj_slab][ni], rotated in place. */
 int mprg_set_rotation(mprg_ctx *ctx, const double *cosa, const double *sina);
+int mprg_has_rotation(const mprg_ctx *ctx); /* 1 once mprg_set_rotation succeeded */
 int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem);
 
 /* ---- gather: replaces ESMF_FieldGather(rootPet=0), write_data.F90:1006-1453.

@@ -285,16 +285,24 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
                        const std::vector<FieldDev> &planes) {
     const size_t total = cols_vec.size() + cols_sca.size() + flat.size() + planes.size();
     if (total == 0 || r->nDst == 0) return;
-    ctx->scratch.ensure(total * sizeof(FieldDev));
-    std::vector<FieldDev> all;
-    all.reserve(total);
-    all.insert(all.end(), cols_vec.begin(), cols_vec.end());
-    all.insert(all.end(), cols_sca.begin(), cols_sca.end());
-    all.insert(all.end(), flat.begin(), flat.end());
-    all.insert(all.end(), planes.begin(), planes.end());
-    MPRG_CUDA(cudaMemcpyAsync(ctx->scratch.p, all.data(), total * sizeof(FieldDev), cudaMemcpyHostToDevice,
+    // Descriptors travel through a pinned host ring into a device ring (both 1 MiB): the copy is
+    // truly asynchronous and a slot is not reused until ~1e4 later applies have been enqueued.
+    constexpr size_t kRing = 1 << 20;
+    const size_t need = (total * sizeof(FieldDev) + 255) & ~(size_t)255;
+    if (need > kRing) fail(34, "mprg_apply: too many stacked fields (%zu)", total);
+    ctx->descHost.ensure(kRing);
+    ctx->scratch.ensure(kRing);
+    if (ctx->descCursor + need > kRing) ctx->descCursor = 0;
+    FieldDev *all = (FieldDev *)((unsigned char *)ctx->descHost.p + ctx->descCursor);
+    size_t n = 0;
+    for (auto &f : cols_vec) all[n++] = f;
+    for (auto &f : cols_sca) all[n++] = f;
+    for (auto &f : flat) all[n++] = f;
+    for (auto &f : planes) all[n++] = f;
+    MPRG_CUDA(cudaMemcpyAsync(ctx->scratch.p + ctx->descCursor, all, total * sizeof(FieldDev), cudaMemcpyHostToDevice,
                               ctx->stream));
-    const FieldDev *dev = (const FieldDev *)ctx->scratch.p;
+    const FieldDev *dev = (const FieldDev *)(ctx->scratch.p + ctx->descCursor);
+    ctx->descCursor += need;
     ApplyArgs<TACC> a;
     a.rowptr = r->rowptr.p;
     a.col = r->col.p;

@@ -132,6 +132,19 @@ int mprg_device_free(mprg_ctx *ctx, void *ptr) {
     MPRG_LEAVE(ctx)
 }
 
+int mprg_scratch(mprg_ctx *ctx, int slot, size_t bytes, void **ptr) {
+    MPRG_ENTER(ctx)
+    if (!ptr || slot < 0 || slot >= 8) fail(1, "mprg_scratch: bad slot/pointer");
+    if (bytes > ctx->userScratch[slot].n) {
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->userScratch[slot].alloc(bytes);
+    }
+    *ptr = ctx->userScratch[slot].p;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_has_rotation(const mprg_ctx *ctx) { return ctx && ctx->haveRot ? 1 : 0; }
+
 int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonCell_rad,
                   const double *latCell_rad, const double *lonVertex_rad, const double *latVertex_rad,
                   const int32_t *verticesOnCell) {

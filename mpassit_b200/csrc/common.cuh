@@ -152,7 +152,10 @@ struct mprg_ctx {
     // staging for host-buffer applies
     mprg::DevBuf<unsigned char> stageIn[2], stageOut[2];
     cudaEvent_t evIn[2] = {nullptr, nullptr}, evK[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
-    mprg::DevBuf<unsigned char> scratch;  // apply descriptors etc.
+    mprg::DevBuf<unsigned char> scratch;  // apply descriptors (device side)
+    mprg::PinnedBuf descHost;             // apply descriptors (pinned ring, host side)
+    size_t descCursor = 0;
+    mprg::DevBuf<unsigned char> userScratch[8];  // mprg_scratch slots
     void *nccl = nullptr;                 // ncclComm_t
     void *ncclLib = nullptr;
     // optional per-launch profiling of the apply kernels (mprg_profile_*)

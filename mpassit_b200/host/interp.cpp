@@ -90,8 +90,10 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             held.push_back(rh);
             return rh;
         };
-        const bool rotate = cfg->proj_code == MPASSIT_PROJ_LC && io->cosa && io->sina;
-        if (rotate) ck(ctx, mprg_set_rotation(ctx, io->cosa, io->sina), "set_rotation");
+        // rotation applies on Lambert targets only (interp.F90:138,291: proj_code==PROJ_LC)
+        const bool rotate = cfg->proj_code == MPASSIT_PROJ_LC;
+        if (rotate && !mprg_has_rotation(ctx))
+            throw Fail{41, "IN rotate_winds_cgrid: cosa/sina not registered (mprg_set_rotation)"};
 
         // ---------------- interp_diag_data, interp.F90:107-141 ----------------
         if (cfg->interp_diag && io->n_diag > 0) {
@@ -153,8 +155,8 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldRegridStore");
                 // mass-point winds stay on the device in fp64 (the reference's R8 fields)
                 Batch b;
-                if (fu) { ck(ctx, mprg_device_alloc(ctx, nslab * fu->nlev * 8, &d_um), "device_alloc"); b.add(fu->src, d_um, fu->nlev); }
-                if (fv) { ck(ctx, mprg_device_alloc(ctx, nslab * fv->nlev * 8, &d_vm), "device_alloc"); b.add(fv->src, d_vm, fv->nlev); }
+                if (fu) { ck(ctx, mprg_scratch(ctx, 0, nslab * fu->nlev * 8, &d_um), "scratch"); b.add(fu->src, d_um, fu->nlev); }
+                if (fv) { ck(ctx, mprg_scratch(ctx, 1, nslab * fv->nlev * 8, &d_vm), "scratch"); b.add(fv->src, d_vm, fv->nlev); }
                 run(ctx, rh, b, sdt, mem, MPRG_F64, MPRG_DEVICE, "FieldRegrid");
                 if (fu && fv && rotate)  // interp.F90:291-293
                     ck(ctx, mprg_rotate_winds(ctx, d_um, d_vm, fu->nlev, MPRG_F64, MPRG_DEVICE), "rotate_winds_cgrid");
@@ -212,8 +214,6 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
     }
     // interp.F90:449-464 FieldBundleRegridRelease (here: every handle taken above)
     for (mprg_route *rh : held) mprg_release(ctx, rh);
-    if (d_um) mprg_device_free(ctx, d_um);
-    if (d_vm) mprg_device_free(ctx, d_vm);
     return rc_out;
 }
 

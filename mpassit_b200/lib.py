@@ -25,7 +25,7 @@ EPI_NONE, EPI_ADD, EPI_MUL = 0, 1, 2
 
 EXPORTS = [
     "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize",
-    "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_set_mesh", "mprg_set_target", "mprg_get_slab", "mprg_store",
+    "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_get_slab", "mprg_store",
     "mprg_release", "mprg_clear_routes", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
     "mprg_apply", "mprg_apply_ex", "mprg_set_rotation", "mprg_rotate_winds", "mprg_comm_id", "mprg_comm_init",
     "mprg_gather", "mprg_kernel_launches", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
@@ -63,6 +63,8 @@ def load() -> C.CDLL:
     L.mprg_host_free.argtypes = [vp, vp]
     L.mprg_device_alloc.argtypes = [vp, C.c_size_t, pp]
     L.mprg_device_free.argtypes = [vp, vp]
+    L.mprg_scratch.argtypes = [vp, C.c_int, C.c_size_t, pp]
+    L.mprg_has_rotation.argtypes = [vp]
     L.mprg_set_mesh.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mprg_set_target.argtypes = [vp, C.c_int, i32, i32, vp, vp]
     L.mprg_get_slab.argtypes = [vp, C.c_int, C.POINTER(i32), C.POINTER(i32)]

@@ -104,6 +104,8 @@ def load_geometry(rg, wl: Workload) -> None:
     for k, s in (("M", L.CENTER), ("U", L.EDGE1), ("V", L.EDGE2), ("CORNER", L.CORNER)):
         lat, lon = wl.grids[k]
         rg.set_target(s, lon, lat)
+    if wl.cosa is not None:  # cosa/sina_target_grid, model_grid.F90:1113-1185
+        rg.set_rotation(wl.cosa, wl.sina)
 
 
 def _field_values_torch(wl: Workload, group: str, name: str, nlev: int, k: int, device):
@@ -192,7 +194,7 @@ def run_interp(rg, wl: Workload, F: dict, mem: int):
 
     return host.interp_data(rg, wl.cfg, diag=conv(F["diag"]), hist_2d=conv(F["hist_2d"]), hist_3d=conv(F["hist_3d"]),
                             soil=conv(F["soil"]), ter=_np(F["ter"]), hgt=_np(F["hgt"]), u_stag=_np(F["u_stag"]),
-                            v_stag=_np(F["v_stag"]), cosa=wl.cosa, sina=wl.sina, nz=wl.nz, mem=mem)
+                            v_stag=_np(F["v_stag"]), nz=wl.nz, mem=mem)
 
 
 def io_bytes(wl: Workload, F: dict) -> tuple[int, int]:

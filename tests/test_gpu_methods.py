@@ -45,6 +45,8 @@ def _load(rg, grids, mesh):
     for k, s in (("M", 0), ("U", 1), ("V", 2), ("CORNER", 3)):
         lat, lon = grids[k]
         rg.set_target(s, lon, lat)
+    cosa, sina = __import__("mpassit_b200.host", fromlist=["x"]).get_rotang(*grids["M"])
+    rg.set_rotation(cosa, sina)
 
 
 def test_stagger_routes_bit_exact(rg, orc, lc_case):
@@ -180,7 +182,7 @@ def test_interp_data_end_to_end(rg, orc, host, lc_case):
     vst = np.full((nz, nV), np.nan, np.float32)
     n0 = rg.kernel_launches
     io = host.interp_data(rg, cfg, diag=diag, hist_2d=h2, hist_3d=h3, soil=soil, ter=F["ter"], hgt=hgt, u_stag=ust,
-                          v_stag=vst, cosa=cosa, sina=sina, nz=nz)
+                          v_stag=vst, nz=nz)
     assert rg.kernel_launches > n0
     got = {s.name: s.dst for s in diag + h2 + h3 + soil}
     got["HGT"], got["U"], got["V"] = hgt, ust, vst
