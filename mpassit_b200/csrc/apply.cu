@@ -49,6 +49,27 @@ struct ApplyArgs {
 template <typename T>
 __device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
 
+constexpr int kRowChunk = 3;  // row entries gathered per batch of loads (bilinear rows are exactly 3)
+
+// four consecutive levels of one source column
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    float x, y, z, w;
+    __device__ __forceinline__ void zero() { x = y = z = w = 0.f; }
+    __device__ __forceinline__ void load(const float *p) {
+        const float4 v = __ldg((const float4 *)p);
+        x = v.x; y = v.y; z = v.z; w = v.w;
+    }
+};
+template <> struct Vec4<double> {
+    double x, y, z, w;
+    __device__ __forceinline__ void zero() { x = y = z = w = 0.0; }
+    __device__ __forceinline__ void load(const double *p) {
+        const double2 a = __ldg((const double2 *)p), b = __ldg((const double2 *)p + 1);
+        x = a.x; y = a.y; z = b.x; w = b.y;
+    }
+};
+
 template <typename TACC>
 __device__ __forceinline__ TACC epilogue(TACC v, int op, double arg) {
     if (op == MPRG_EPI_ADD) return v + (TACC)arg;
@@ -59,8 +80,8 @@ __device__ __forceinline__ TACC epilogue(TACC v, int op, double arg) {
 // ---------------------------------------------------------------------------
 // 3-D fields
 // ---------------------------------------------------------------------------
-template <typename TIN, typename TOUT, typename TACC, bool VEC>
-__global__ void __launch_bounds__(kThreads)
+template <typename TIN, typename TOUT, typename TACC, bool VEC, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_apply_cols(ApplyArgs<TACC> a) {
     __shared__ int32_t s_rowptr[kTile + 1];
     __shared__ int32_t s_col[kCsrCap];
@@ -95,76 +116,101 @@ k_apply_cols(ApplyArgs<TACC> a) {
         for (int L0 = 0; L0 < nlev; L0 += kLevChunk, buf ^= 1) {
             const int Ln = min(kLevChunk, nlev - L0);
             // ---- phase A: gather + reduce, lanes along levels ----------------
+            // Every load of a row chunk (kRowChunk entries x 2 targets) is issued before the
+            // first FMA that consumes one, so each lane keeps 6 (vector) / 12 (scalar) requests
+            // in flight: the kernel is latency-bound otherwise.
             if (VEC) {
-                // half-warp per target, 4 consecutive levels per lane (16-byte loads)
+                // half-warp per target, 4 consecutive levels per lane (16/32-byte loads)
                 const int l16 = lane & 15, hw = lane >> 4;
                 const bool act = 4 * l16 < Ln;
+                const TIN *sbase = src + L0 + 4 * l16;
+                int tt[2], rb[2], re[2];
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                    const int t = warp * 4 + it * 2 + hw;
-                    TACC acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-                    if (t < ntile && act) {
-                        const int b = s_rowptr[t] - base, e = s_rowptr[t + 1] - base;
-                        for (int k = b; k < e; ++k) {
-                            const int c = cached ? s_col[k] : __ldg(a.col + base + k);
-                            const TACC wt = cached ? s_w[k] : __ldg(a.w + base + k);
-                            const TIN *p = src + (size_t)c * nlev + L0 + 4 * l16;
-                            if (sizeof(TIN) == 4) {
-                                const float4 v = __ldg((const float4 *)p);
-                                acc0 += wt * (TACC)v.x; acc1 += wt * (TACC)v.y;
-                                acc2 += wt * (TACC)v.z; acc3 += wt * (TACC)v.w;
-                            } else {
-                                const double2 v0 = __ldg((const double2 *)p);
-                                const double2 v1 = __ldg((const double2 *)p + 1);
-                                acc0 += wt * (TACC)v0.x; acc1 += wt * (TACC)v0.y;
-                                acc2 += wt * (TACC)v1.x; acc3 += wt * (TACC)v1.y;
+                    tt[it] = warp * 4 + it * 2 + hw;
+                    rb[it] = re[it] = 0;
+                    if (tt[it] < ntile && act) { rb[it] = s_rowptr[tt[it]] - base; re[it] = s_rowptr[tt[it] + 1] - base; }
+                }
+                TACC acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+                const int nk = max(re[0] - rb[0], re[1] - rb[1]);
+                for (int k0 = 0; k0 < nk; k0 += kRowChunk) {
+                    Vec4<TIN> v[2][kRowChunk];
+                    TACC wt[2][kRowChunk];
+#pragma unroll
+                    for (int it = 0; it < 2; ++it)
+#pragma unroll
+                        for (int j = 0; j < kRowChunk; ++j) {
+                            const int k = rb[it] + k0 + j;
+                            wt[it][j] = 0;
+                            v[it][j].zero();
+                            if (k < re[it]) {
+                                const int c = cached ? s_col[k] : __ldg(a.col + base + k);
+                                wt[it][j] = cached ? s_w[k] : __ldg(a.w + base + k);
+                                v[it][j].load(sbase + (size_t)c * nlev);
                             }
                         }
-                    }
-                    if (t < ntile && act) {
-                        s_out[buf][4 * l16 + 0][t] = (TOUT)epilogue(acc0, fd.epi_op, fd.epi_arg);
-                        s_out[buf][4 * l16 + 1][t] = (TOUT)epilogue(acc1, fd.epi_op, fd.epi_arg);
-                        s_out[buf][4 * l16 + 2][t] = (TOUT)epilogue(acc2, fd.epi_op, fd.epi_arg);
-                        s_out[buf][4 * l16 + 3][t] = (TOUT)epilogue(acc3, fd.epi_op, fd.epi_arg);
-                    }
-                }
-            } else {
-                // warp per target, levels lane and lane+32; two targets in flight
-                const bool a0 = lane < Ln, a1 = lane + 32 < Ln;
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const int tA = warp * 4 + it * 2, tB = tA + 1;
-                    TACC accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
-                    int bA = 0, eA = 0, bB = 0, eB = 0;
-                    if (tA < ntile) { bA = s_rowptr[tA] - base; eA = s_rowptr[tA + 1] - base; }
-                    if (tB < ntile) { bB = s_rowptr[tB] - base; eB = s_rowptr[tB + 1] - base; }
-                    const int nk = max(eA - bA, eB - bB);
-                    for (int k = 0; k < nk; ++k) {
-                        const bool hA = bA + k < eA, hB = bB + k < eB;
-                        int cA = 0, cB = 0;
-                        TACC wA = 0, wB = 0;
-                        if (hA) { cA = cached ? s_col[bA + k] : __ldg(a.col + base + bA + k);
-                                  wA = cached ? s_w[bA + k] : __ldg(a.w + base + bA + k); }
-                        if (hB) { cB = cached ? s_col[bB + k] : __ldg(a.col + base + bB + k);
-                                  wB = cached ? s_w[bB + k] : __ldg(a.w + base + bB + k); }
-                        const TIN *pA = src + (size_t)cA * nlev + L0 + lane;
-                        const TIN *pB = src + (size_t)cB * nlev + L0 + lane;
-                        TIN xA0 = 0, xA1 = 0, xB0 = 0, xB1 = 0;
-                        if (hA && a0) xA0 = __ldg(pA);
-                        if (hA && a1) xA1 = __ldg(pA + 32);
-                        if (hB && a0) xB0 = __ldg(pB);
-                        if (hB && a1) xB1 = __ldg(pB + 32);
-                        accA0 += wA * (TACC)xA0; accA1 += wA * (TACC)xA1;
-                        accB0 += wB * (TACC)xB0; accB1 += wB * (TACC)xB1;
+                    for (int it = 0; it < 2; ++it)
+#pragma unroll
+                        for (int j = 0; j < kRowChunk; ++j) {
+                            acc[it][0] += wt[it][j] * (TACC)v[it][j].x; acc[it][1] += wt[it][j] * (TACC)v[it][j].y;
+                            acc[it][2] += wt[it][j] * (TACC)v[it][j].z; acc[it][3] += wt[it][j] * (TACC)v[it][j].w;
+                        }
+                }
+#pragma unroll
+                for (int it = 0; it < 2; ++it)
+                    if (tt[it] < ntile && act) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            s_out[buf][4 * l16 + q][tt[it]] = (TOUT)epilogue(acc[it][q], fd.epi_op, fd.epi_arg);
                     }
-                    if (tA < ntile) {
-                        if (a0) s_out[buf][lane][tA] = (TOUT)epilogue(accA0, fd.epi_op, fd.epi_arg);
-                        if (a1) s_out[buf][lane + 32][tA] = (TOUT)epilogue(accA1, fd.epi_op, fd.epi_arg);
+            } else {
+                // warp per target, levels lane and lane+32; two targets per step
+                const bool a0 = lane < Ln, a1 = lane + 32 < Ln;
+                const TIN *sbase = src + L0 + lane;
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    int tt[2], rb[2], re[2];
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        tt[it] = warp * 4 + pr * 2 + it;
+                        rb[it] = re[it] = 0;
+                        if (tt[it] < ntile) { rb[it] = s_rowptr[tt[it]] - base; re[it] = s_rowptr[tt[it] + 1] - base; }
                     }
-                    if (tB < ntile) {
-                        if (a0) s_out[buf][lane][tB] = (TOUT)epilogue(accB0, fd.epi_op, fd.epi_arg);
-                        if (a1) s_out[buf][lane + 32][tB] = (TOUT)epilogue(accB1, fd.epi_op, fd.epi_arg);
+                    TACC acc[2][2] = {{0, 0}, {0, 0}};
+                    const int nk = max(re[0] - rb[0], re[1] - rb[1]);
+                    for (int k0 = 0; k0 < nk; k0 += kRowChunk) {
+                        TIN x[2][kRowChunk][2];
+                        TACC wt[2][kRowChunk];
+#pragma unroll
+                        for (int it = 0; it < 2; ++it)
+#pragma unroll
+                            for (int j = 0; j < kRowChunk; ++j) {
+                                const int k = rb[it] + k0 + j;
+                                wt[it][j] = 0;
+                                x[it][j][0] = x[it][j][1] = 0;
+                                if (k < re[it]) {
+                                    const int c = cached ? s_col[k] : __ldg(a.col + base + k);
+                                    wt[it][j] = cached ? s_w[k] : __ldg(a.w + base + k);
+                                    const TIN *p = sbase + (size_t)c * nlev;
+                                    if (a0) x[it][j][0] = __ldg(p);
+                                    if (a1) x[it][j][1] = __ldg(p + 32);
+                                }
+                            }
+#pragma unroll
+                        for (int it = 0; it < 2; ++it)
+#pragma unroll
+                            for (int j = 0; j < kRowChunk; ++j) {
+                                acc[it][0] += wt[it][j] * (TACC)x[it][j][0];
+                                acc[it][1] += wt[it][j] * (TACC)x[it][j][1];
+                            }
                     }
+#pragma unroll
+                    for (int it = 0; it < 2; ++it)
+                        if (tt[it] < ntile) {
+                            if (a0) s_out[buf][lane][tt[it]] = (TOUT)epilogue(acc[it][0], fd.epi_op, fd.epi_arg);
+                            if (a1) s_out[buf][lane + 32][tt[it]] = (TOUT)epilogue(acc[it][1], fd.epi_op, fd.epi_arg);
+                        }
                 }
             }
             __syncthreads();
@@ -244,6 +290,11 @@ k_apply_planes(ApplyArgs<TACC> a) {
 // ---------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------
+static int tune_minb() {  // resident CTAs/SM the vector kernel is compiled for (register cap)
+    const char *e = getenv("MPASSIT_GPU_MINB");
+    return e ? atoi(e) : 3;
+}
+
 static bool acc_fp32_requested() {
     const char *e = getenv("MPASSIT_GPU_ACC");
     return e && (!strcmp(e, "f32") || !strcmp(e, "fp32"));
@@ -315,14 +366,17 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
         a.fields = dev; a.nfields = (int)cols_vec.size();
         dim3 g(tiles, (unsigned)((cols_vec.size() + kFieldsPerCta - 1) / kFieldsPerCta));
-        k_apply_cols<TIN, TOUT, TACC, true><<<g, kThreads, 0, ctx->stream>>>(a);
+        const int minb = tune_minb();
+        if (minb == 2) k_apply_cols<TIN, TOUT, TACC, true, 2><<<g, kThreads, 0, ctx->stream>>>(a);
+        else if (minb == 4) k_apply_cols<TIN, TOUT, TACC, true, 4><<<g, kThreads, 0, ctx->stream>>>(a);
+        else k_apply_cols<TIN, TOUT, TACC, true, 3><<<g, kThreads, 0, ctx->stream>>>(a);
         ctx->launches++;
     }
     if (!cols_sca.empty()) {
         ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
         a.fields = dev + cols_vec.size(); a.nfields = (int)cols_sca.size();
         dim3 g(tiles, (unsigned)((cols_sca.size() + kFieldsPerCta - 1) / kFieldsPerCta));
-        k_apply_cols<TIN, TOUT, TACC, false><<<g, kThreads, 0, ctx->stream>>>(a);
+        k_apply_cols<TIN, TOUT, TACC, false, 3><<<g, kThreads, 0, ctx->stream>>>(a);
         ctx->launches++;
     }
     if (!flat.empty()) {

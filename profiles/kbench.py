@@ -1,0 +1,77 @@
+"""Kernel-level benchmark of the batched apply on the C2 geometry (profiling aid).
+
+  python profiles/kbench.py [--config c2] [--variants f64:3,f64:2,f32:4] [--iters 5] [--only-3d]
+
+Builds the workload once, then for every variant (accumulate type : compiled CTAs/SM)
+runs the bilinear-route stacked apply over the 3-D fields and prints per-kernel GB/s
+from the engine's per-launch CUDA events.  Also used as the short command under ncu.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mpassit_b200 import lib as L  # noqa: E402
+from mpassit_b200 import workload  # noqa: E402
+from mpassit_b200.regrid import Regridder  # noqa: E402
+
+KIND = {0: "cols_vec", 1: "cols_scalar", 2: "flat", 3: "planes"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--variants", default="f64:3,f64:2,f64:4,f32:3,f32:4,f32:2")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--fields", type=int, default=12, help="number of stacked nz-level fields")
+    ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
+    args = ap.parse_args()
+    t0 = time.time()
+    wl = workload.make(args.config)
+    rg = Regridder(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    rg.use_torch_stream()
+    workload.load_geometry(rg, wl)
+    route = rg.store(L.BILINEAR, L.SRC_MESH_ELEMENT, L.CENTER)
+    info = route.info()
+    nlev = args.nlev or wl.nz
+    n = wl.mesh.nCells
+    srcs = [torch.randn((n, nlev), device="cuda", dtype=torch.float32) for _ in range(args.fields)]
+    dsts = [torch.empty((nlev, wl.n_mass), device="cuda", dtype=torch.float32) for _ in range(args.fields)]
+    print(f"setup {time.time() - t0:.1f}s  route {info}", file=sys.stderr)
+    peak = 6450.0
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    for var in args.variants.split(","):
+        acc, minb = var.split(":")
+        os.environ["MPASSIT_GPU_ACC"] = acc
+        os.environ["MPASSIT_GPU_MINB"] = minb
+        for _ in range(2):
+            rg.apply(route, srcs, dsts, nlev=[nlev] * args.fields)
+        rg.profile(True)
+        for _ in range(args.iters):
+            rg.apply(route, srcs, dsts, nlev=[nlev] * args.fields)
+        recs = rg.profile_read()
+        rg.profile(False)
+        out = {}
+        for r in recs:
+            k = out.setdefault(KIND[r["kind"]], [0.0, 0.0, 0])
+            k[0] += r["ms"]; k[1] += r["alg_bytes"]; k[2] += 1
+        for k, (ms, by, cnt) in out.items():
+            gbs = by / (ms * 1e-3) / 1e9
+            print(f"{var:8s} {k:12s} nlev={nlev:3d} x{args.fields}: {ms / cnt:8.3f} ms/launch  {gbs:8.1f} GB/s  "
+                  f"{100 * gbs / peak:5.1f}% of {peak:.0f}")
+    rg.close()
+
+
+if __name__ == "__main__":
+    main()
