@@ -17,6 +17,8 @@
 // Grid order is (tiles fastest, field-chunks slowest) so one chunk's source
 // columns are swept once while they are L2-resident; outputs use streaming
 // stores so they do not evict them.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mprg {
@@ -77,8 +79,12 @@ __device__ __forceinline__ TACC epilogue(TACC v, int op, double arg) {
     return v;
 }
 
+}  // namespace mprg
+#include "apply_pipe.cuh"
+namespace mprg {
+
 // ---------------------------------------------------------------------------
-// 3-D fields
+// 3-D fields, register-gather variant (fallback when a tile does not fit the pipeline)
 // ---------------------------------------------------------------------------
 template <typename TIN, typename TOUT, typename TACC, bool VEC, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
@@ -330,30 +336,129 @@ struct ProfScope {
     }
 };
 
+// ---- pipelined column kernel (apply_pipe.cuh) -------------------------------------
+static bool pipe_disabled() {
+    const char *e = getenv("MPASSIT_GPU_APPLY");
+    return e && !strcmp(e, "direct");
+}
+
+// descriptor ring shared by every apply kernel: returns the device address of `bytes` copied from `host`
+static const void *push_desc(mprg_ctx *ctx, const void *host, size_t bytes) {
+    constexpr size_t kRing = 1 << 20;
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (need > kRing) fail(34, "mprg_apply: too many stacked fields");
+    ctx->descHost.ensure(kRing);
+    ctx->scratch.ensure(kRing);
+    if (ctx->descCursor + need > kRing) ctx->descCursor = 0;
+    unsigned char *h = (unsigned char *)ctx->descHost.p + ctx->descCursor;
+    memcpy(h, host, bytes);
+    unsigned char *d = ctx->scratch.p + ctx->descCursor;
+    MPRG_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->descCursor += need;
+    return d;
+}
+
+static bool pipe_bulk() {  // TMA bulk-copy staging (default) vs per-thread cp.async
+    const char *e = getenv("MPASSIT_GPU_FILL");
+    return !(e && !strcmp(e, "ldgsts"));
+}
+
+template <typename TIN, typename TOUT, typename TACC, bool VEC, int STAGES>
+static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles) {
+    if (VEC && pipe_bulk()) {
+        auto kern = k_apply_pipe<TIN, TOUT, TACC, VEC, STAGES, VEC>;  // BULK only exists for VEC layouts
+        MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
+    } else {
+        auto kern = k_apply_pipe<TIN, TOUT, TACC, VEC, STAGES, false>;
+        MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
+    }
+    ctx->launches++;
+}
+
+// returns false if this route / field set does not fit the pipelined kernel
+template <typename TIN, typename TOUT, typename TACC, bool VEC>
+static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields) {
+    if (pipe_disabled() || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || r->tileUniqMax > kPipeCap) return false;
+    const int slotBytes = pipe_slot_bytes<TIN>();
+    const size_t stage = (size_t)r->tileUniqMax * slotBytes;
+    const size_t fixed = pipe_fixed_bytes<TOUT, TACC>();
+    // deepest pipeline that still leaves >= 3 CTAs per SM; fewer stages / CTAs for fat tiles
+    const size_t smMax = 227 * 1024;
+    int stages = 0;
+    for (int s : {4, 3, 2}) {
+        const size_t need = fixed + (size_t)s * stage + 1024;
+        const int ctas = (int)(smMax / need);
+        if ((s == 4 && ctas >= 3) || (s == 3 && ctas >= 2) || (s == 2 && ctas >= 1)) { stages = s; break; }
+    }
+    if (const char *e = getenv("MPASSIT_GPU_STAGES")) {
+        const int s = atoi(e);
+        if (s >= 2 && s <= 4 && fixed + (size_t)s * stage + 1024 <= smMax) stages = s;
+    }
+    if (!stages) return false;
+    std::vector<UnitDev> units;
+    for (auto &f : fields) {
+        for (int L0 = 0; L0 < f.nlev; L0 += kPipeLev) {
+            UnitDev u;
+            u.src = f.src; u.dst = f.dst; u.srcBytes = (size_t)r->nSrc * f.nlev * sizeof(TIN);
+            u.nlev = f.nlev; u.L0 = L0; u.Ln = std::min(kPipeLev, f.nlev - L0);
+            u.epi_op = f.epi_op; u.epi_arg = f.epi_arg;
+            units.push_back(u);
+        }
+    }
+    PipeArgs<TACC> pa;
+    pa.rowptr = r->rowptr.p; pa.col = r->col.p;
+    if (sizeof(TACC) == 8) pa.w = (const TACC *)r->w.p; else pa.w = (const TACC *)r->w32.p;
+    pa.nDst = r->nDst;
+    pa.maxU = r->tileUniqMax;
+    pa.ni = r->dstNi;
+    pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
+    const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
+    const size_t smemBytes = fixed + (size_t)stages * stage;
+    for (size_t u0 = 0; u0 < units.size(); u0 += kPipeMaxUnits) {
+        const size_t nu = std::min<size_t>(kPipeMaxUnits, units.size() - u0);
+        pa.units = (const UnitDev *)push_desc(ctx, units.data() + u0, nu * sizeof(UnitDev));
+        pa.nunits = (int)nu;
+        if (stages == 4) launch_pipe_s<TIN, TOUT, TACC, VEC, 4>(ctx, pa, smemBytes, tiles);
+        else if (stages == 3) launch_pipe_s<TIN, TOUT, TACC, VEC, 3>(ctx, pa, smemBytes, tiles);
+        else launch_pipe_s<TIN, TOUT, TACC, VEC, 2>(ctx, pa, smemBytes, tiles);
+    }
+    MPRG_CUDA(cudaGetLastError());
+    return true;
+}
+
+void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
+    r->tileEntriesMax = r->tileUniqMax = 0;
+    if (r->nDst <= 0 || r->nnz <= 0) return;
+    DevBuf<int32_t> mm(2);
+    MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    if (r->dstNi <= 0) r->dstNi = (int32_t)std::min<int64_t>(r->nDst, 0x7fffffff);
+    const int tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
+    const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * tilesPerRow);
+    k_tile_stats<<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow, mm.p, mm.p + 1);
+    ctx->launches++;
+    int32_t h[2] = {0, 0};
+    MPRG_CUDA(cudaMemcpyAsync(h, mm.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    r->tileEntriesMax = h[0];
+    r->tileUniqMax = h[1];
+}
+
 template <typename TIN, typename TOUT, typename TACC>
 static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols_vec,
                        const std::vector<FieldDev> &cols_sca, const std::vector<FieldDev> &flat,
                        const std::vector<FieldDev> &planes) {
     const size_t total = cols_vec.size() + cols_sca.size() + flat.size() + planes.size();
     if (total == 0 || r->nDst == 0) return;
-    // Descriptors travel through a pinned host ring into a device ring (both 1 MiB): the copy is
-    // truly asynchronous and a slot is not reused until ~1e4 later applies have been enqueued.
-    constexpr size_t kRing = 1 << 20;
-    const size_t need = (total * sizeof(FieldDev) + 255) & ~(size_t)255;
-    if (need > kRing) fail(34, "mprg_apply: too many stacked fields (%zu)", total);
-    ctx->descHost.ensure(kRing);
-    ctx->scratch.ensure(kRing);
-    if (ctx->descCursor + need > kRing) ctx->descCursor = 0;
-    FieldDev *all = (FieldDev *)((unsigned char *)ctx->descHost.p + ctx->descCursor);
-    size_t n = 0;
-    for (auto &f : cols_vec) all[n++] = f;
-    for (auto &f : cols_sca) all[n++] = f;
-    for (auto &f : flat) all[n++] = f;
-    for (auto &f : planes) all[n++] = f;
-    MPRG_CUDA(cudaMemcpyAsync(ctx->scratch.p + ctx->descCursor, all, total * sizeof(FieldDev), cudaMemcpyHostToDevice,
-                              ctx->stream));
-    const FieldDev *dev = (const FieldDev *)(ctx->scratch.p + ctx->descCursor);
-    ctx->descCursor += need;
+    std::vector<FieldDev> all;
+    all.reserve(total);
+    all.insert(all.end(), cols_vec.begin(), cols_vec.end());
+    all.insert(all.end(), cols_sca.begin(), cols_sca.end());
+    all.insert(all.end(), flat.begin(), flat.end());
+    all.insert(all.end(), planes.begin(), planes.end());
+    // descriptors travel through a pinned host ring into a device ring: the copy is truly asynchronous
+    const FieldDev *dev = (const FieldDev *)push_desc(ctx, all.data(), total * sizeof(FieldDev));
     ApplyArgs<TACC> a;
     a.rowptr = r->rowptr.p;
     a.col = r->col.p;
@@ -362,7 +467,18 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
     auto ksum = [](const std::vector<FieldDev> &v) { double k = 0; for (auto &f : v) k += f.nlev; return k; };
+    bool piped_vec = false, piped_sca = false;
     if (!cols_vec.empty()) {
+        ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
+        piped_vec = launch_pipe<TIN, TOUT, TACC, true>(ctx, r, cols_vec);
+        if (!piped_vec && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+    }
+    if (!cols_sca.empty()) {
+        ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
+        piped_sca = launch_pipe<TIN, TOUT, TACC, false>(ctx, r, cols_sca);
+        if (!piped_sca && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+    }
+    if (!cols_vec.empty() && !piped_vec) {
         ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
         a.fields = dev; a.nfields = (int)cols_vec.size();
         dim3 g(tiles, (unsigned)((cols_vec.size() + kFieldsPerCta - 1) / kFieldsPerCta));
@@ -372,7 +488,7 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         else k_apply_cols<TIN, TOUT, TACC, true, 3><<<g, kThreads, 0, ctx->stream>>>(a);
         ctx->launches++;
     }
-    if (!cols_sca.empty()) {
+    if (!cols_sca.empty() && !piped_sca) {
         ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
         a.fields = dev + cols_vec.size(); a.nfields = (int)cols_sca.size();
         dim3 g(tiles, (unsigned)((cols_sca.size() + kFieldsPerCta - 1) / kFieldsPerCta));

@@ -192,6 +192,7 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
     else if (src_loc == MPRG_SRC_MESH_NODE && method == MPRG_BILINEAR) store_bilinear_node(ctx, r.get());
     else if (src_loc == MPRG_SRC_GRID_CENTER && method == MPRG_BILINEAR) store_bilinear_grid(ctx, r.get());
     else fail(54, "mprg_store: unsupported (method %d, src_loc %d)", method, src_loc);
+    r->dstNi = ctx->target[dst_stagger].ni;
     route_finish(ctx, r.get());
     MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MPRG_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -490,3 +491,12 @@ void store_bilinear_grid(mprg_ctx *, mprg_route *) { fail(92, "GRID_CENTER bilin
 void store_bilinear_node(mprg_ctx *, mprg_route *) { fail(93, "MESH_NODE bilinear store not built into this library"); }
 #endif
 }  // namespace mprg
+
+// test / tuning hook (not part of the reference-facing surface): per-tile maxima that size the
+// pipelined apply kernel's staging
+extern "C" int mprg_debug_route_tiles(const mprg_route *rh, int32_t *entriesMax, int32_t *uniqMax) {
+    if (!rh) return 1;
+    if (entriesMax) *entriesMax = rh->tileEntriesMax;
+    if (uniqMax) *uniqMax = rh->tileUniqMax;
+    return 0;
+}

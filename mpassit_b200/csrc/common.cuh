@@ -122,6 +122,8 @@ struct mprg_route {
     int method = 0, src_loc = 0, dst_stagger = 0;
     int64_t nDst = 0, nnz = 0, nUnmapped = 0, nSrc = 0;
     int64_t nSrcRef = 0;       // distinct source entities referenced by the weights
+    int32_t tileEntriesMax = 0, tileUniqMax = 0;  // per 32-target tile: CSR entries / distinct columns
+    int32_t dstNi = 0;         // destination row length (tiles of the apply kernel never straddle rows)
     int32_t maxRow = 0;        // longest row
     bool uniform = false;      // every mapped row has exactly `maxRow` entries, stored ELL-like
     mprg::DevBuf<int32_t> rowptr;  // [nDst+1]
@@ -196,6 +198,7 @@ void store_conserve(mprg_ctx *ctx, mprg_route *r);
 void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r);
 void store_bilinear_node(mprg_ctx *ctx, mprg_route *r);
 void route_finish(mprg_ctx *ctx, mprg_route *r);  // stats + fp32 weight copy
+void route_tile_stats(mprg_ctx *ctx, mprg_route *r);  // apply.cu
 
 // apply.cu
 struct ApplyField {

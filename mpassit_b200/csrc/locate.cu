@@ -182,6 +182,7 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     r->nUnmapped = (int64_t)hun;
     r->nSrcRef = (int64_t)href;
+    if (!r->srcLevelSlowest) route_tile_stats(ctx, r);
     r->maxRow = hmm[0];
     r->uniform = (r->nnz > 0 && hmm[0] == hmm[1]);
 }

@@ -27,7 +27,7 @@ KIND = {0: "cols_vec", 1: "cols_scalar", 2: "flat", 3: "planes"}
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--variants", default="f64:3,f64:2,f64:4,f32:3,f32:4,f32:2")
+    ap.add_argument("--variants", default="f64:p4,f64:p3,f64:p2,f32:p4,f32:p3,f32:d4,f64:d3")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--fields", type=int, default=12, help="number of stacked nz-level fields")
     ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
@@ -45,16 +45,25 @@ def main():
     n = wl.mesh.nCells
     srcs = [torch.randn((n, nlev), device="cuda", dtype=torch.float32) for _ in range(args.fields)]
     dsts = [torch.empty((nlev, wl.n_mass), device="cuda", dtype=torch.float32) for _ in range(args.fields)]
-    print(f"setup {time.time() - t0:.1f}s  route {info}", file=sys.stderr)
+    import ctypes
+    em, um = ctypes.c_int32(), ctypes.c_int32()
+    rg.L.mprg_debug_route_tiles(ctypes.c_void_p(route.handle), ctypes.byref(em), ctypes.byref(um))
+    print(f"setup {time.time() - t0:.1f}s  route {info} tile entries max {em.value} uniq max {um.value}", file=sys.stderr)
     peak = 6450.0
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
     for var in args.variants.split(","):
-        acc, minb = var.split(":")
+        acc, mode = var.split(":")          # f64:p4 (TMA-bulk pipeline, 4 stages) f64:l4 (cp.async pipeline) f32:d3 (direct)
         os.environ["MPASSIT_GPU_ACC"] = acc
-        os.environ["MPASSIT_GPU_MINB"] = minb
+        os.environ["MPASSIT_GPU_FILL"] = "ldgsts" if mode[0] == "l" else "bulk"
+        if mode[0] in "pl":
+            os.environ["MPASSIT_GPU_APPLY"] = "pipe"
+            os.environ["MPASSIT_GPU_STAGES"] = mode[1:] or "0"
+        else:
+            os.environ["MPASSIT_GPU_APPLY"] = "direct"
+            os.environ["MPASSIT_GPU_MINB"] = mode[1:] or "3"
         for _ in range(2):
             rg.apply(route, srcs, dsts, nlev=[nlev] * args.fields)
         rg.profile(True)
