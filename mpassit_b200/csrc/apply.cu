@@ -363,14 +363,18 @@ static bool pipe_bulk() {  // TMA bulk-copy staging (default) vs per-thread cp.a
     return !(e && !strcmp(e, "ldgsts"));
 }
 
-template <typename TIN, typename TOUT, typename TACC, bool VEC, int STAGES>
-static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles) {
-    if (VEC && pipe_bulk()) {
-        auto kern = k_apply_pipe<TIN, TOUT, TACC, VEC, STAGES, VEC>;  // BULK only exists for VEC layouts
+template <typename TIN, typename TOUT, typename TACC, int STAGES>
+static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles, bool allvec) {
+    if (pipe_bulk() && allvec) {
+        auto kern = k_apply_pipe<TIN, TOUT, TACC, STAGES, true, true>;
+        MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
+    } else if (pipe_bulk()) {
+        auto kern = k_apply_pipe<TIN, TOUT, TACC, STAGES, true, false>;
         MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
         kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
     } else {
-        auto kern = k_apply_pipe<TIN, TOUT, TACC, VEC, STAGES, false>;
+        auto kern = k_apply_pipe<TIN, TOUT, TACC, STAGES, false, false>;
         MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
         kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
     }
@@ -378,9 +382,9 @@ static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBy
 }
 
 // returns false if this route / field set does not fit the pipelined kernel
-template <typename TIN, typename TOUT, typename TACC, bool VEC>
+template <typename TIN, typename TOUT, typename TACC>
 static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields) {
-    if (pipe_disabled() || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || r->tileUniqMax > kPipeCap) return false;
+    if (pipe_disabled() || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
     const int slotBytes = pipe_slot_bytes<TIN>();
     const size_t stage = (size_t)r->tileUniqMax * slotBytes;
     const size_t fixed = pipe_fixed_bytes<TOUT, TACC>();
@@ -403,13 +407,16 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             UnitDev u;
             u.src = f.src; u.dst = f.dst; u.srcBytes = (size_t)r->nSrc * f.nlev * sizeof(TIN);
             u.nlev = f.nlev; u.L0 = L0; u.Ln = std::min(kPipeLev, f.nlev - L0);
-            u.epi_op = f.epi_op; u.epi_arg = f.epi_arg;
+            const bool aligned = ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0;
+            u.epi_op = (f.epi_op & 0xff) | (aligned ? kUnitAligned : 0);
+            u.epi_arg = f.epi_arg;
             units.push_back(u);
         }
     }
     PipeArgs<TACC> pa;
     pa.rowptr = r->rowptr.p; pa.col = r->col.p;
     if (sizeof(TACC) == 8) pa.w = (const TACC *)r->w.p; else pa.w = (const TACC *)r->w32.p;
+    pa.tileUPtr = r->tileUPtr.p; pa.tileUCols = r->tileUCols.p; pa.entrySlot = r->entrySlot.p;
     pa.nDst = r->nDst;
     pa.maxU = r->tileUniqMax;
     pa.ni = r->dstNi;
@@ -420,29 +427,48 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         const size_t nu = std::min<size_t>(kPipeMaxUnits, units.size() - u0);
         pa.units = (const UnitDev *)push_desc(ctx, units.data() + u0, nu * sizeof(UnitDev));
         pa.nunits = (int)nu;
-        if (stages == 4) launch_pipe_s<TIN, TOUT, TACC, VEC, 4>(ctx, pa, smemBytes, tiles);
-        else if (stages == 3) launch_pipe_s<TIN, TOUT, TACC, VEC, 3>(ctx, pa, smemBytes, tiles);
-        else launch_pipe_s<TIN, TOUT, TACC, VEC, 2>(ctx, pa, smemBytes, tiles);
+        bool allvec = true;
+        for (size_t k = 0; k < nu; ++k) allvec = allvec && (units[u0 + k].epi_op & kUnitAligned);
+        if (stages == 4) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, smemBytes, tiles, allvec);
+        else if (stages == 3) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, smemBytes, tiles, allvec);
+        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, smemBytes, tiles, allvec);
     }
     MPRG_CUDA(cudaGetLastError());
     return true;
 }
 
+void scan_counts(mprg_ctx *ctx, const int32_t *cnt, int32_t *rowptr, int64_t nPlus1);  // locate.cu
+
+// builds the route's tile schedule (the "communication schedule" half of an ESMF route handle)
 void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
     r->tileEntriesMax = r->tileUniqMax = 0;
     if (r->nDst <= 0 || r->nnz <= 0) return;
-    DevBuf<int32_t> mm(2);
-    MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 2 * sizeof(int32_t), ctx->stream));
     if (r->dstNi <= 0) r->dstNi = (int32_t)std::min<int64_t>(r->nDst, 0x7fffffff);
     const int tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * tilesPerRow);
-    k_tile_stats<<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow, mm.p, mm.p + 1);
+    DevBuf<int32_t> mm(2), cnt(tiles + 1);
+    MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    MPRG_CUDA(cudaMemsetAsync(cnt.p, 0, (tiles + 1) * sizeof(int32_t), ctx->stream));
+    k_tile_schedule<false><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
+                                                                   mm.p, mm.p + 1, cnt.p, nullptr, nullptr, nullptr);
     ctx->launches++;
     int32_t h[2] = {0, 0};
     MPRG_CUDA(cudaMemcpyAsync(h, mm.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     r->tileEntriesMax = h[0];
     r->tileUniqMax = h[1];
+    if (h[0] > kPipeCap) return;  // no schedule: register-gather kernels only
+    r->tileUPtr.alloc(tiles + 1);
+    scan_counts(ctx, cnt.p, r->tileUPtr.p, (int64_t)tiles + 1);
+    int32_t total = 0;
+    MPRG_CUDA(cudaMemcpy(&total, r->tileUPtr.p + tiles, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    r->tileUCols.alloc(total > 0 ? total : 1);
+    r->entrySlot.alloc(r->nnz);
+    k_tile_schedule<true><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
+                                                                  nullptr, nullptr, nullptr, r->tileUPtr.p, r->tileUCols.p,
+                                                                  r->entrySlot.p);
+    ctx->launches++;
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 template <typename TIN, typename TOUT, typename TACC>
@@ -467,16 +493,20 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
     auto ksum = [](const std::vector<FieldDev> &v) { double k = 0; for (auto &f : v) k += f.nlev; return k; };
+    // every 3-D field of the apply goes through ONE pipelined launch (aligned and unaligned level
+    // counts are told apart per unit); the register-gather kernels below are the fallback
     bool piped_vec = false, piped_sca = false;
-    if (!cols_vec.empty()) {
-        ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
-        piped_vec = launch_pipe<TIN, TOUT, TACC, true>(ctx, r, cols_vec);
-        if (!piped_vec && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
-    }
-    if (!cols_sca.empty()) {
-        ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
-        piped_sca = launch_pipe<TIN, TOUT, TACC, false>(ctx, r, cols_sca);
-        if (!piped_sca && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+    if (!cols_vec.empty() || !cols_sca.empty()) {
+        if (!cols_vec.empty()) {
+            ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
+            piped_vec = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_vec);
+            if (!piped_vec && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+        }
+        if (!cols_sca.empty()) {
+            ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
+            piped_sca = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_sca);
+            if (!piped_sca && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+        }
     }
     if (!cols_vec.empty() && !piped_vec) {
         ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);

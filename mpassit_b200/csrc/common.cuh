@@ -124,6 +124,9 @@ struct mprg_route {
     int64_t nSrcRef = 0;       // distinct source entities referenced by the weights
     int32_t tileEntriesMax = 0, tileUniqMax = 0;  // per 32-target tile: CSR entries / distinct columns
     int32_t dstNi = 0;         // destination row length (tiles of the apply kernel never straddle rows)
+    // tile schedule for the pipelined apply kernel (apply_pipe.cuh)
+    mprg::DevBuf<int32_t> tileUPtr, tileUCols;
+    mprg::DevBuf<unsigned char> entrySlot;
     int32_t maxRow = 0;        // longest row
     bool uniform = false;      // every mapped row has exactly `maxRow` entries, stored ELL-like
     mprg::DevBuf<int32_t> rowptr;  // [nDst+1]

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--fields", type=int, default=12, help="number of stacked nz-level fields")
     ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
+    ap.add_argument("--stack", default="", help="explicit stack, e.g. 60x12,61x2 (levels x fields)")
     args = ap.parse_args()
     t0 = time.time()
     wl = workload.make(args.config)
@@ -43,8 +44,11 @@ def main():
     info = route.info()
     nlev = args.nlev or wl.nz
     n = wl.mesh.nCells
-    srcs = [torch.randn((n, nlev), device="cuda", dtype=torch.float32) for _ in range(args.fields)]
-    dsts = [torch.empty((nlev, wl.n_mass), device="cuda", dtype=torch.float32) for _ in range(args.fields)]
+    levs = [nlev] * args.fields
+    if args.stack:
+        levs = [int(a.split("x")[0]) for a in args.stack.split(",") for _ in range(int(a.split("x")[1]))]
+    srcs = [torch.randn((n, L), device="cuda", dtype=torch.float32) for L in levs]
+    dsts = [torch.empty((L, wl.n_mass), device="cuda", dtype=torch.float32) for L in levs]
     import ctypes
     em, um = ctypes.c_int32(), ctypes.c_int32()
     rg.L.mprg_debug_route_tiles(ctypes.c_void_p(route.handle), ctypes.byref(em), ctypes.byref(um))
@@ -65,10 +69,10 @@ def main():
             os.environ["MPASSIT_GPU_APPLY"] = "direct"
             os.environ["MPASSIT_GPU_MINB"] = mode[1:] or "3"
         for _ in range(2):
-            rg.apply(route, srcs, dsts, nlev=[nlev] * args.fields)
+            rg.apply(route, srcs, dsts, nlev=levs)
         rg.profile(True)
         for _ in range(args.iters):
-            rg.apply(route, srcs, dsts, nlev=[nlev] * args.fields)
+            rg.apply(route, srcs, dsts, nlev=levs)
         recs = rg.profile_read()
         rg.profile(False)
         out = {}
@@ -77,7 +81,7 @@ def main():
             k[0] += r["ms"]; k[1] += r["alg_bytes"]; k[2] += 1
         for k, (ms, by, cnt) in out.items():
             gbs = by / (ms * 1e-3) / 1e9
-            print(f"{var:8s} {k:12s} nlev={nlev:3d} x{args.fields}: {ms / cnt:8.3f} ms/launch  {gbs:8.1f} GB/s  "
+            print(f"{var:8s} {k:12s} {args.stack or f'{nlev}x{args.fields}':>14s}: {ms / cnt:8.3f} ms/launch  {gbs:8.1f} GB/s  "
                   f"{100 * gbs / peak:5.1f}% of {peak:.0f}")
     rg.close()
 
