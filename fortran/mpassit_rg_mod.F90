@@ -1,0 +1,208 @@
+!> mpassit_rg_mod -- ISO_C_BINDING interfaces to libmpassit_rg.so (include/mpassit_rg.h).
+!!
+!! This is the thin layer BASELINE.json's north_star asks for: the Fortran host code of
+!! MPASSIT (interp.F90, model_grid.F90, input_data.F90, write_data.F90) keeps its structure
+!! and calls CUDA through these bind(C) interfaces instead of ESMF.  Each interface names
+!! the ESMF call it replaces.  NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler
+!! is installed there); the C ABI itself is exercised from C++/Python (tests/, bench.py) and
+!! the call sites a maintainer would change are listed in INTEGRATION.md.
+!!
+!! Conventions: every function returns integer(c_int) rc, 0 = success (== ESMF_SUCCESS), so
+!! the reference's pattern is kept verbatim:
+!!     rc = mprg_store(ctx, MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, rh_patch)
+!!     if (rc /= 0) call error_handler("IN FieldBundleRegridStore", rc)
+!! Fortran arrays map without copies: a (nz, nCells) file-order variable is the C
+!! [nCells][nz] the engine wants (the reference's transpose at input_data.F90:653-655
+!! disappears); a target (i, j, lev) array is the C [lev][j][i] the engine writes.
+module mpassit_rg_mod
+  use iso_c_binding
+  implicit none
+  private
+
+  ! enum values of include/mpassit_rg.h
+  integer(c_int), parameter, public :: MPRG_BILINEAR = 0, MPRG_CONSERVE = 1, MPRG_NEAREST_STOD = 2
+  integer(c_int), parameter, public :: MPRG_SRC_MESH_ELEMENT = 0, MPRG_SRC_MESH_NODE = 1, MPRG_SRC_GRID_CENTER = 2
+  integer(c_int), parameter, public :: MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3
+  integer(c_int), parameter, public :: MPRG_F32 = 0, MPRG_F64 = 1
+  integer(c_int), parameter, public :: MPRG_HOST = 0, MPRG_DEVICE = 1
+  integer(c_int), parameter, public :: MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2
+
+  public :: mprg_init, mprg_finalize, mprg_last_error, mprg_error_message
+  public :: mprg_set_mesh, mprg_set_target, mprg_get_slab
+  public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
+  public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds
+  public :: mprg_comm_id, mprg_comm_init, mprg_gather
+  public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
+
+  interface
+     !> replaces ESMF_Initialize + ESMF_VMGet (mpassit.F90:84-94)
+     integer(c_int) function mprg_init(device, rank, nranks, ctx) bind(C, name="mprg_init")
+       import :: c_int, c_ptr
+       integer(c_int), value :: device, rank, nranks
+       type(c_ptr), intent(out) :: ctx
+     end function
+     !> replaces ESMF_finalize (mpassit.F90:140)
+     integer(c_int) function mprg_finalize(ctx) bind(C, name="mprg_finalize")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     type(c_ptr) function mprg_last_error(ctx) bind(C, name="mprg_last_error")
+       import :: c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function mprg_synchronize(ctx) bind(C, name="mprg_synchronize")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function mprg_host_alloc(ctx, bytes, ptr) bind(C, name="mprg_host_alloc")
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value :: ctx
+       integer(c_size_t), value :: bytes
+       type(c_ptr), intent(out) :: ptr
+     end function
+     integer(c_int) function mprg_host_free(ctx, ptr) bind(C, name="mprg_host_free")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, ptr
+     end function
+     integer(c_int) function mprg_scratch(ctx, slot, bytes, ptr) bind(C, name="mprg_scratch")
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: slot
+       integer(c_size_t), value :: bytes
+       type(c_ptr), intent(out) :: ptr
+     end function
+
+     !> replaces ESMF_MeshCreate (model_grid.F90:488-497).  Pass lonCell, latCell, lonVert,
+     !! latVert (radians, as read at model_grid.F90:354-384) and vertOnCell(maxEdges,nCells)
+     !! (model_grid.F90:416) unchanged; no unique_sort / FINDLOC connectivity build is needed.
+     integer(c_int) function mprg_set_mesh(ctx, nCells, nVertices, maxEdges, lonCell, latCell, lonVertex, &
+                                           latVertex, verticesOnCell) bind(C, name="mprg_set_mesh")
+       import :: c_int, c_ptr, c_int32_t, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int32_t), value :: nCells, nVertices, maxEdges
+       real(c_double), intent(in) :: lonCell(*), latCell(*), lonVertex(*), latVertex(*)
+       integer(c_int32_t), intent(in) :: verticesOnCell(*)
+     end function
+     !> replaces ESMF_GridAddCoord / GridGetCoord fills (model_grid.F90:707-728, 949-1038):
+     !! one call per stagger with the (i,j) lon/lat arrays in degrees
+     !! (longitude_one / latitude_one etc. from get_lat_lon_fields, model_grid.F90:747-794)
+     integer(c_int) function mprg_set_target(ctx, stagger, ni, nj, lon_deg, lat_deg) bind(C, name="mprg_set_target")
+       import :: c_int, c_ptr, c_int32_t, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: stagger
+       integer(c_int32_t), value :: ni, nj
+       real(c_double), intent(in) :: lon_deg(*), lat_deg(*)
+     end function
+     !> rows [j0, j1) (0-based) of a stagger owned by this rank == ESMF_GridGet bounds (clb/cub)
+     integer(c_int) function mprg_get_slab(ctx, stagger, j0, j1) bind(C, name="mprg_get_slab")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: stagger
+       integer(c_int32_t), intent(out) :: j0, j1
+     end function
+
+     !> replaces ESMF_FieldRegridStore / ESMF_FieldBundleRegridStore
+     !! (interp.F90:123,207,226,241,259,277,298,316,334,353,372,394,421,437)
+     integer(c_int) function mprg_store(ctx, method, src_loc, dst_stagger, rh) bind(C, name="mprg_store")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: method, src_loc, dst_stagger
+       type(c_ptr), intent(out) :: rh
+     end function
+     !> replaces ESMF_FieldBundleRegridRelease (interp.F90:450-463)
+     integer(c_int) function mprg_release(ctx, rh) bind(C, name="mprg_release")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, rh
+     end function
+     integer(c_int) function mprg_clear_routes(ctx) bind(C, name="mprg_clear_routes")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function mprg_route_info(rh, nDst, nnz, nUnmapped, nSrc) bind(C, name="mprg_route_info")
+       import :: c_int, c_ptr, c_int64_t
+       type(c_ptr), value :: rh
+       integer(c_int64_t), intent(out) :: nDst, nnz, nUnmapped, nSrc
+     end function
+
+     !> replaces ESMF_FieldRegrid / ESMF_FieldBundleRegrid
+     !! (interp.F90:134,219,236,251,268,286,307,325,344,363,382,404,431,443).
+     !! src / dst are arrays of c_loc() addresses, one per field of the bundle.
+     integer(c_int) function mprg_apply(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst, dst_dtype, dst_mem) &
+          bind(C, name="mprg_apply")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, rh
+       integer(c_int32_t), value :: nfields
+       type(c_ptr), intent(in) :: src(*), dst(*)
+       integer(c_int32_t), intent(in) :: nlev(*)
+       integer(c_int), value :: src_dtype, src_mem, dst_dtype, dst_mem
+     end function
+     !> same with a fused per-field epilogue (T-300, PHB = zgrid*9.81: write_data.F90:1339-1345, 1417)
+     integer(c_int) function mprg_apply_ex(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst, dst_dtype, dst_mem, &
+                                           epi_op, epi_arg) bind(C, name="mprg_apply_ex")
+       import :: c_int, c_ptr, c_int32_t, c_double
+       type(c_ptr), value :: ctx, rh
+       integer(c_int32_t), value :: nfields
+       type(c_ptr), intent(in) :: src(*), dst(*)
+       integer(c_int32_t), intent(in) :: nlev(*), epi_op(*)
+       integer(c_int), value :: src_dtype, src_mem, dst_dtype, dst_mem
+       real(c_double), intent(in) :: epi_arg(*)
+     end function
+
+     !> cosa_target_grid / sina_target_grid (model_grid.F90:1113-1185) registered once
+     integer(c_int) function mprg_set_rotation(ctx, cosa, sina) bind(C, name="mprg_set_rotation")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double), intent(in) :: cosa(*), sina(*)
+     end function
+     !> replaces rotate_winds_cgrid (interp.F90:689-749)
+     integer(c_int) function mprg_rotate_winds(ctx, u, v, nlev, dtype, mem) bind(C, name="mprg_rotate_winds")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, u, v
+       integer(c_int32_t), value :: nlev
+       integer(c_int), value :: dtype, mem
+     end function
+
+     !> NCCL bootstrap: rank 0 calls mprg_comm_id, the 128 bytes are MPI_Bcast'ed by the host
+     !! (mpi_comm_world is already up, mpassit.F90:71), every rank calls mprg_comm_init
+     integer(c_int) function mprg_comm_id(ctx, id128) bind(C, name="mprg_comm_id")
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(out) :: id128(128)
+     end function
+     integer(c_int) function mprg_comm_init(ctx, id128) bind(C, name="mprg_comm_init")
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(in) :: id128(128)
+     end function
+     !> replaces ESMF_FieldGather(rootPet=0) (write_data.F90:1006-1453); device buffers
+     integer(c_int) function mprg_gather(ctx, stagger, nlev, dtype, slab_dev, root, full_dev) bind(C, name="mprg_gather")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, slab_dev, full_dev
+       integer(c_int), value :: stagger, dtype, root
+       integer(c_int32_t), value :: nlev
+     end function
+  end interface
+
+contains
+
+  !> mprg_last_error as a Fortran string, for error_handler(trim(msg), rc) (utils.F90:16-33)
+  function mprg_error_message(ctx) result(msg)
+    type(c_ptr), intent(in) :: ctx
+    character(len=:), allocatable :: msg
+    character(kind=c_char), pointer :: p(:)
+    type(c_ptr) :: cp
+    integer :: n
+    cp = mprg_last_error(ctx)
+    msg = ""
+    if (.not. c_associated(cp)) return
+    call c_f_pointer(cp, p, [1024])
+    n = 0
+    do while (n < 1024)
+       if (p(n + 1) == c_null_char) exit
+       n = n + 1
+    end do
+    allocate (character(len=n) :: msg)
+    if (n > 0) msg = transfer(p(1:n), msg)
+  end function mprg_error_message
+
+end module mpassit_rg_mod

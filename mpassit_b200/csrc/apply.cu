@@ -301,9 +301,14 @@ static int tune_minb() {  // resident CTAs/SM the vector kernel is compiled for 
     return e ? atoi(e) : 3;
 }
 
+// Accumulation type for fp32-in / fp32-out fields.  Default fp32: every weight set on this path is a
+// convex combination (bilinear, conservative) or a single 1.0 (nearest), so fp32 FMA accumulation
+// stays within ~2e-7 of the fp64 result -- 50x inside the 1e-5 contract -- and nearest-neighbour
+// output remains bit-exact (1.0f * x).  MPASSIT_GPU_ACC=f64 restores the reference's R8 arithmetic
+// (one rounding on store) at ~25 % lower throughput.
 static bool acc_fp32_requested() {
     const char *e = getenv("MPASSIT_GPU_ACC");
-    return e && (!strcmp(e, "f32") || !strcmp(e, "fp32"));
+    return !(e && (!strcmp(e, "f64") || !strcmp(e, "fp64")));
 }
 
 // ---- per-launch profiling (bench.py's live roofline measurement) ---------------
@@ -388,13 +393,13 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     const int slotBytes = pipe_slot_bytes<TIN>();
     const size_t stage = (size_t)r->tileUniqMax * slotBytes;
     const size_t fixed = pipe_fixed_bytes<TOUT, TACC>();
-    // deepest pipeline that still leaves >= 3 CTAs per SM; fewer stages / CTAs for fat tiles
+    // Measured on B200 (profiles/r01): resident CTAs per SM matter more than pipeline depth (2 stages x
+    // 4 CTAs beats 3 x 3 and 4 x 2 by 10-40 %), so take the shallowest pipeline that fits.
     const size_t smMax = 227 * 1024;
     int stages = 0;
-    for (int s : {4, 3, 2}) {
+    for (int s : {2}) {
         const size_t need = fixed + (size_t)s * stage + 1024;
-        const int ctas = (int)(smMax / need);
-        if ((s == 4 && ctas >= 3) || (s == 3 && ctas >= 2) || (s == 2 && ctas >= 1)) { stages = s; break; }
+        if (need <= smMax) { stages = s; break; }
     }
     if (const char *e = getenv("MPASSIT_GPU_STAGES")) {
         const int s = atoi(e);

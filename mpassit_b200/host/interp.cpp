@@ -12,6 +12,7 @@
 // apply, and each distinct weight matrix is generated once (mprg_store memoises),
 // instead of the reference's 12 RegridStore calls.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -96,13 +97,21 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             throw Fail{41, "IN rotate_winds_cgrid: cosa/sina not registered (mprg_set_rotation)"};
 
         // ---------------- interp_diag_data, interp.F90:107-141 ----------------
-        if (cfg->interp_diag && io->n_diag > 0) {
-            mprg_route *rh = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
-            Batch b;
-            for (int i = 0; i < io->n_diag; ++i) b.add(io->diag[i].src, io->diag[i].dst, io->diag[i].nlev);
-            run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
-            if (u10 >= 0 && v10 >= 0 && rotate)  // interp.F90:138-139
+        // The diag bundle uses the same bilinear element->CENTER matrix as the hist 2d_patch / hgt /
+        // 3d bundles.  When both stages run and the hist stage's `method` is BILINEAR, their fields are
+        // stacked into ONE apply (independent fields: order of evaluation does not change any value).
+        Batch diagBatch;
+        const bool have_diag = cfg->interp_diag && io->n_diag > 0;
+        if (have_diag)
+            for (int i = 0; i < io->n_diag; ++i) diagBatch.add(io->diag[i].src, io->diag[i].dst, io->diag[i].nlev);
+        auto finish_diag = [&]() {
+            if (have_diag && u10 >= 0 && v10 >= 0 && rotate)  // interp.F90:138-139
                 ck(ctx, mprg_rotate_winds(ctx, io->diag[u10].dst, io->diag[v10].dst, 1, ddt, mem), "rotate_winds_cgrid");
+        };
+        if (have_diag && !cfg->interp_hist) {
+            mprg_route *rh = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
+            run(ctx, rh, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid");
+            finish_diag();
         }
 
         // ---------------- interp_hist_data, interp.F90:183-465 ----------------
@@ -125,13 +134,47 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             // what zero-initialised storage yields, so that is what the mirror assumes.
             const int m_bil = method == kUnset ? MPRG_BILINEAR : method;
 
+            // mass-point winds (UMASS / VMASS, interp.F90:256-289) are intermediates that never leave the
+            // device.  Default: kept in the output precision (the rotation itself runs in fp64 registers);
+            // MPASSIT_GPU_ACC=f64 keeps them as the reference's R8 fields.  Either is far inside the 1e-5
+            // contract; the fp32 chain moves half the bytes.
+            const mpassit_field *fu = nullptr, *fv = nullptr;
+            for (int i = 0; i < io->n_hist_3d; ++i) {
+                if (io->hist_3d[i].klass == MPASSIT_CLASS_U) fu = &io->hist_3d[i];
+                if (io->hist_3d[i].klass == MPASSIT_CLASS_V) fv = &io->hist_3d[i];
+            }
+            const char *acc_env = std::getenv("MPASSIT_GPU_ACC");
+            const bool chain64 = acc_env && (!std::strcmp(acc_env, "f64") || !std::strcmp(acc_env, "fp64"));
+            const int chain_dt = chain64 ? MPRG_F64 : ddt;
+            const size_t chain_sz = chain_dt == MPRG_F64 ? 8 : 4;
+            if (fu || fv) {
+                int32_t j0 = 0, j1 = 0, ni = 0, nj = 0;
+                mpassit_target_dims(cfg, MPRG_CENTER, &ni, &nj);
+                ck(ctx, mprg_get_slab(ctx, MPRG_CENTER, &j0, &j1), "get_slab");
+                const size_t nslab = (size_t)(j1 - j0) * ni;
+                if (fu) ck(ctx, mprg_scratch(ctx, 0, nslab * fu->nlev * chain_sz, &d_um), "scratch");
+                if (fv) ck(ctx, mprg_scratch(ctx, 1, nslab * fv->nlev * chain_sz, &d_vm), "scratch");
+            }
+            // the winds join the main stacked apply when its destinations are device buffers of the same type
+            const bool winds_in_batch = (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR;
+
             // one stacked apply for everything on the bilinear element->CENTER route:
             // 2d_patch (:207-221), hgt (:226-238), 3d_nz (:240-254), 3d_nzp1 (:331-347)
             {
                 Batch b;
+                if (have_diag && m_bil == MPRG_BILINEAR) {
+                    b = diagBatch;
+                } else if (have_diag) {  // cannot happen with the reference's method sequence; kept for safety
+                    mprg_route *rd = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
+                    run(ctx, rd, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                }
                 for (int i = 0; i < io->n_hist_2d; ++i)
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_PATCH) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
                 if (io->ter && io->hgt) b.add(io->ter, io->hgt, 1);
+                if (winds_in_batch) {
+                    if (fu) b.add(fu->src, d_um, fu->nlev);
+                    if (fv) b.add(fv->src, d_vm, fv->nlev);
+                }
                 for (int i = 0; i < io->n_hist_3d; ++i)
                     if (io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZ || io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZP1)
                         b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
@@ -139,36 +182,29 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                     mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
                     run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
                 }
+                finish_diag();
             }
 
             // winds, interp.F90:256-328
             if (do_u || do_v) {
-                const mpassit_field *fu = nullptr, *fv = nullptr;
-                for (int i = 0; i < io->n_hist_3d; ++i) {
-                    if (io->hist_3d[i].klass == MPASSIT_CLASS_U) fu = &io->hist_3d[i];
-                    if (io->hist_3d[i].klass == MPASSIT_CLASS_V) fv = &io->hist_3d[i];
+                if (!winds_in_batch) {
+                    mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldRegridStore");
+                    Batch b;
+                    if (fu) b.add(fu->src, d_um, fu->nlev);
+                    if (fv) b.add(fv->src, d_vm, fv->nlev);
+                    run(ctx, rh, b, sdt, mem, chain_dt, MPRG_DEVICE, "FieldRegrid");
                 }
-                int32_t j0 = 0, j1 = 0, ni = 0, nj = 0;
-                mpassit_target_dims(cfg, MPRG_CENTER, &ni, &nj);
-                ck(ctx, mprg_get_slab(ctx, MPRG_CENTER, &j0, &j1), "get_slab");
-                const size_t nslab = (size_t)(j1 - j0) * ni;
-                mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldRegridStore");
-                // mass-point winds stay on the device in fp64 (the reference's R8 fields)
-                Batch b;
-                if (fu) { ck(ctx, mprg_scratch(ctx, 0, nslab * fu->nlev * 8, &d_um), "scratch"); b.add(fu->src, d_um, fu->nlev); }
-                if (fv) { ck(ctx, mprg_scratch(ctx, 1, nslab * fv->nlev * 8, &d_vm), "scratch"); b.add(fv->src, d_vm, fv->nlev); }
-                run(ctx, rh, b, sdt, mem, MPRG_F64, MPRG_DEVICE, "FieldRegrid");
                 if (fu && fv && rotate)  // interp.F90:291-293
-                    ck(ctx, mprg_rotate_winds(ctx, d_um, d_vm, fu->nlev, MPRG_F64, MPRG_DEVICE), "rotate_winds_cgrid");
+                    ck(ctx, mprg_rotate_winds(ctx, d_um, d_vm, fu->nlev, chain_dt, MPRG_DEVICE), "rotate_winds_cgrid");
                 if (fu && io->u_stag) {  // interp.F90:295-311
                     mprg_route *ru = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE1, "FieldRegridStore");
                     const void *s = d_um; void *d = io->u_stag; int32_t nl = fu->nlev;
-                    ck(ctx, mprg_apply(ctx, ru, 1, &s, &nl, MPRG_F64, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                    ck(ctx, mprg_apply(ctx, ru, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
                 }
                 if (fv && io->v_stag) {  // interp.F90:313-328
                     mprg_route *rv = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE2, "FieldRegridStore");
                     const void *s = d_vm; void *d = io->v_stag; int32_t nl = fv->nlev;
-                    ck(ctx, mprg_apply(ctx, rv, 1, &s, &nl, MPRG_F64, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                    ck(ctx, mprg_apply(ctx, rv, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
                 }
             }
 

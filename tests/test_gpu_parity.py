@@ -70,9 +70,12 @@ def test_bilinear_structure_and_weights(rg, orc, name):
     r.release()
 
 
+@pytest.mark.parametrize("acc", ["f32", "f64"])
 @pytest.mark.parametrize("nlev", [1, 4, 55, 60, 61, 130])
-def test_apply_bilinear_levels(rg, orc, nlev):
+def test_apply_bilinear_levels(rg, orc, nlev, acc, monkeypatch):
     from mpassit_b200 import lib as l
+
+    monkeypatch.setenv("MPASSIT_GPU_ACC", acc)   # default is f32 accumulation; f64 = the reference's R8 arithmetic
 
     mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "regional_ragged")
     elem, col, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
@@ -85,9 +88,14 @@ def test_apply_bilinear_levels(rg, orc, nlev):
     r.release()
     unm = elem < 0
     assert np.all(got[:, unm] == 0.0)                # zero fill of unmapped rows
-    # fp64 accumulation, one rounding: at most 1 ulp from the oracle's rounding of the same sum
-    np.testing.assert_allclose(got, want, rtol=2e-7, atol=0)
+    # contract (BASELINE.json north_star): <= 1e-5 relative for fp32 bilinear fields
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    if acc == "f64":
+        # fp64 accumulation, one rounding: at most 1 ulp from the oracle's rounding of the same sum
+        np.testing.assert_allclose(got, want, rtol=2e-7, atol=0)
+    else:
+        # fp32 FMA accumulation of a convex combination: a few ulp
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
 
 
 def test_apply_nearest_bit_exact_and_stacked(rg, orc):
@@ -143,7 +151,7 @@ def test_import_csr_ragged_rows_and_empty(rg, orc):
         got = np.empty((nlev, nDst), np.float32)
         rg.apply(r, [src if nlev > 1 else src.reshape(-1)], [got], nlev=[nlev])
         want = orc.apply(rp, col, w, src, np.float32)
-        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)   # up to 700 random-sign terms per row
         assert np.all(got[:, lens == 0] == 0.0)
     r.release()
 
