@@ -18,9 +18,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -39,55 +37,65 @@ def log(*a):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~5 ms by an NVML thread while the timed region runs
+    (the region lasts well under a second, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, gpu_index: int = 0):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        self.proc = None
         self.idx = gpu_index
+        self.samples = []       # (sm_mhz, power_w, reasons bitmask)
+        self._stop = False
+        self._thr = None
+        self.err = None
 
     def start(self):
+        import threading
+
         try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it holds plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",") if x.strip().isdigit()]
+            phys = ids[self.idx] if self.idx < len(ids) else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = f"nvml unavailable: {e}"
+            return
+
+        def loop():
+            while not self._stop:
+                try:
+                    self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                         nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                         int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.005)
+
+        self._nv = nv
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.fh.close()
-        sm, mx, pw, reasons = [], [], [], set()
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.path)
-        except OSError:
-            pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # under load = samples in the upper half of the power range seen
-        thr = 0.5 * (min(pw) + max(pw))
-        load = [s for s, w in zip(sm, pw) if w >= thr] or sm
-        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw)}
+        if self._thr is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not started"]}
+        self._stop = True
+        self._thr.join(timeout=2)
+        nv = self._nv
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        mask = 0
+        for _, _, r in self.samples:
+            mask |= r
+        pw = [p for _, p, _ in self.samples]
+        thr = 0.5 * (min(pw) + max(pw))     # under load = samples in the upper half of the power range seen
+        load = [c for c, p, _ in self.samples if p >= thr] or [c for c, _, _ in self.samples]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, bit in names if mask & bit], "samples": len(self.samples), "power_w_max": max(pw)}
 
 
 # --------------------------------------------------------------------------- CPU reference arm
@@ -173,7 +181,7 @@ def cpu_reference_pass(wl, frac_rows: float, steps: int, warmup: int, threads: i
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=os.environ.get("MPASSIT_BENCH_CONFIG", "c2"))
@@ -397,7 +405,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64 accumulate, f32 in/out" if os.environ.get("MPASSIT_GPU_ACC", "") not in ("f32", "fp32") else "f32",
+            "dtype": "f32" if os.environ.get("MPASSIT_GPU_ACC", "") not in ("f64", "fp64") else "f64 accumulate, f32 in/out",
             "data": "synthetic",
             "config": {"workload": f"{wl.name}: 3-km regional MPAS ({wl.mesh.nCells} cells, {wl.nz} levels) -> Lambert "
                                    f"{wl.cfg.nx}x{wl.cfg.ny} dx={wl.cfg.dxkm:.0f} m, diaglist+histlist_2d/3d/soil, "

@@ -363,27 +363,19 @@ static const void *push_desc(mprg_ctx *ctx, const void *host, size_t bytes) {
     return d;
 }
 
-static bool pipe_bulk() {  // TMA bulk-copy staging (default) vs per-thread cp.async
-    const char *e = getenv("MPASSIT_GPU_FILL");
-    return !(e && !strcmp(e, "ldgsts"));
+template <typename KERN, typename TACC>
+static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles) {
+    MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
+    ctx->launches++;
 }
 
 template <typename TIN, typename TOUT, typename TACC, int STAGES>
-static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles, bool allvec) {
-    if (pipe_bulk() && allvec) {
-        auto kern = k_apply_pipe<TIN, TOUT, TACC, STAGES, true, true>;
-        MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
-    } else if (pipe_bulk()) {
-        auto kern = k_apply_pipe<TIN, TOUT, TACC, STAGES, true, false>;
-        MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
-    } else {
-        auto kern = k_apply_pipe<TIN, TOUT, TACC, STAGES, false, false>;
-        MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
-    }
-    ctx->launches++;
+static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles, bool allvec, int minb) {
+    if (allvec && minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 5>, pa, smemBytes, tiles);
+    else if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 4>, pa, smemBytes, tiles);
+    else if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 5>, pa, smemBytes, tiles);
+    else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 4>, pa, smemBytes, tiles);
 }
 
 // returns false if this route / field set does not fit the pipelined kernel
@@ -392,7 +384,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     if (pipe_disabled() || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
     const int slotBytes = pipe_slot_bytes<TIN>();
     const size_t stage = (size_t)r->tileUniqMax * slotBytes;
-    const size_t fixed = pipe_fixed_bytes<TOUT, TACC>();
+    const size_t fixed = pipe_fixed_bytes<TACC>();
     // Measured on B200 (profiles/r01): resident CTAs per SM matter more than pipeline depth (2 stages x
     // 4 CTAs beats 3 x 3 and 4 x 2 by 10-40 %), so take the shallowest pipeline that fits.
     const size_t smMax = 227 * 1024;
@@ -406,6 +398,9 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         if (s >= 2 && s <= 4 && fixed + (size_t)s * stage + 1024 <= smMax) stages = s;
     }
     if (!stages) return false;
+    // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
+    int minb = (fixed + (size_t)stages * stage + 1024) * 5 <= smMax ? 5 : 4;
+    if (const char *e = getenv("MPASSIT_GPU_PIPE_MINB")) minb = atoi(e) >= 5 ? 5 : 4;
     std::vector<UnitDev> units;
     for (auto &f : fields) {
         for (int L0 = 0; L0 < f.nlev; L0 += kPipeLev) {
@@ -434,9 +429,9 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         pa.nunits = (int)nu;
         bool allvec = true;
         for (size_t k = 0; k < nu; ++k) allvec = allvec && (units[u0 + k].epi_op & kUnitAligned);
-        if (stages == 4) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, smemBytes, tiles, allvec);
-        else if (stages == 3) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, smemBytes, tiles, allvec);
-        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, smemBytes, tiles, allvec);
+        if (stages == 4) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, smemBytes, tiles, allvec, minb);
+        else if (stages == 3) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, smemBytes, tiles, allvec, minb);
+        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, smemBytes, tiles, allvec, minb);
     }
     MPRG_CUDA(cudaGetLastError());
     return true;

@@ -12,7 +12,8 @@ static std::string g_init_error;
 #define MPRG_ENTER(ctx)                                     \
     if (!(ctx)) return 1;                                   \
     try {                                                   \
-        MPRG_CUDA(cudaSetDevice((ctx)->device));
+        MPRG_CUDA(cudaSetDevice((ctx)->device));           \
+        ::mprg::tl_stream = (ctx)->stream;
 
 #define MPRG_LEAVE(ctx)                                     \
         return 0;                                           \
@@ -47,6 +48,11 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
     c->device = device; c->rank = rank; c->nranks = nranks;
     try {
         MPRG_CUDA(cudaSetDevice(device));
+        // engine temporaries come from the stream-ordered pool and stay cached in it (common.cuh: DevBuf)
+        cudaMemPool_t pool;
+        MPRG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ULL;
+        MPRG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         MPRG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         MPRG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
         MPRG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
@@ -71,6 +77,7 @@ int mprg_finalize(mprg_ctx *ctx) {
     if (!ctx) return 1;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    mprg::tl_stream = nullptr;  // frees below are ordered on the default stream: the context's streams are going away
     for (auto &kv : ctx->routes) delete kv.second;
     for (auto *r : ctx->imported) delete r;
     ctx->routes.clear();
@@ -94,7 +101,10 @@ const char *mprg_last_error(const mprg_ctx *ctx) { return ctx ? ctx->err.c_str()
 
 int mprg_set_stream(mprg_ctx *ctx, void *cuda_stream) {
     MPRG_ENTER(ctx)
+    // pool allocations made so far become valid on any stream once the old one has drained
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    mprg::tl_stream = ctx->stream;
     MPRG_LEAVE(ctx)
 }
 
@@ -138,6 +148,7 @@ int mprg_scratch(mprg_ctx *ctx, int slot, size_t bytes, void **ptr) {
     if (bytes > ctx->userScratch[slot].n) {
         MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->userScratch[slot].alloc(bytes);
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));  // callers may use the block on their own streams
     }
     *ptr = ctx->userScratch[slot].p;
     MPRG_LEAVE(ctx)
@@ -309,8 +320,8 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                 if (g > f && (inB + a > budget || outB + b > budget)) break;
                 inB += a; outB += b; ++g;
             }
-            if (src_mem == MPRG_HOST) ctx->stageIn[slot].ensure(inB);
-            if (dst_mem == MPRG_HOST) ctx->stageOut[slot].ensure(outB);
+            if (src_mem == MPRG_HOST) ctx->stageIn[slot].ensure_shared(inB);
+            if (dst_mem == MPRG_HOST) ctx->stageOut[slot].ensure_shared(outB);
             // slot reuse: the kernel that last read stageIn[slot] / the D2H that last read stageOut[slot]
             if (batch >= 2) {
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->evK[slot], 0));

@@ -41,7 +41,16 @@ struct Error {
                          __FILE__, __LINE__);                                                \
     } while (0)
 
-// RAII device allocation
+// Stream on which this thread's DevBuf allocations and frees are ordered: every C-ABI entry sets
+// it to the context's stream (MPRG_ENTER in capi.cu).
+inline thread_local cudaStream_t tl_stream = nullptr;
+
+// RAII device allocation from the device's stream-ordered memory pool (cudaMallocAsync, release
+// threshold = keep everything: mprg_init).  Weight generation allocates ~15 temporaries per route;
+// with plain cudaMalloc/cudaFree each of those is a driver call behind a host-wide lock shared with
+// every other tenant of the machine (measured: 30 ms .. 1.3 s per store on a shared B200 host for
+// 10-20 ms of kernels).  Pool allocations are valid for work ordered after them on tl_stream; buffers
+// that other streams touch are allocated with ensure_shared().
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -59,11 +68,19 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) MPRG_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        if (count) MPRG_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), tl_stream));
     }
     void ensure(size_t count) { if (count > n) alloc(count); }
+    // for buffers used on more than one stream (staging): the old block may still be in flight on
+    // another stream and the new one must be visible to all of them
+    void ensure_shared(size_t count) {
+        if (count <= n) return;
+        MPRG_CUDA(cudaDeviceSynchronize());
+        alloc(count);
+        MPRG_CUDA(cudaStreamSynchronize(tl_stream));
+    }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, tl_stream);
         p = nullptr;
         n = 0;
     }

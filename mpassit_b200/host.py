@@ -136,6 +136,24 @@ def para_range(n1: int, n2: int, nprocs: int, irank: int) -> tuple[int, int]:
     return a.value, b.value
 
 
+def slab_rows(nj: int, nranks: int, rank: int) -> tuple[int, int]:
+    """Target rows [j0, j1) (0-based) owned by `rank`: para_range over 1..nj, model_grid.F90:2428."""
+    a, b = para_range(1, nj, nranks, rank)
+    return a - 1, b
+
+
+def gather_runs(ni: int, nj: int, nlev: int, nranks: int, rank: int) -> list[tuple[int, int, int]]:
+    """Placement of one rank's slab [nlev][j1-j0][ni] inside the gathered field [nlev][nj][ni]
+    (what ESMF_FieldGather does for the reference, write_data.F90:1006-1453): one contiguous
+    run per level, as (offset in the slab, offset in the full field, element count).  The
+    engine's mprg_gather posts exactly these runs as grouped ncclSend/ncclRecv pairs."""
+    j0, j1 = slab_rows(nj, nranks, rank)
+    n = (j1 - j0) * ni
+    if n <= 0:
+        return []
+    return [(l * n, l * nj * ni + j0 * ni, n) for l in range(nlev)]
+
+
 def read_block_decomp_file(path: str, ncells: int, npets: int) -> np.ndarray:
     owner = np.empty(ncells, np.int32)
     e = _err()

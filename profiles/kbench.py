@@ -27,7 +27,7 @@ KIND = {0: "cols_vec", 1: "cols_scalar", 2: "flat", 3: "planes"}
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--variants", default="f64:p4,f64:p3,f64:p2,f32:p4,f32:p3,f32:d4,f64:d3")
+    ap.add_argument("--variants", default="f32:p2b4,f32:p2b5,f32:p3b4,f64:p2")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--fields", type=int, default=12, help="number of stacked nz-level fields")
     ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
@@ -59,12 +59,16 @@ def main():
     except Exception:
         pass
     for var in args.variants.split(","):
-        acc, mode = var.split(":")          # f64:p4 (TMA-bulk pipeline, 4 stages) f64:l4 (cp.async pipeline) f32:d3 (direct)
+        acc, mode = var.split(":")          # f32:p2 / f32:p2b5 (TMA-bulk pipeline, 2 stages[, 5 CTAs/SM]) f32:d3 (register gathers)
         os.environ["MPASSIT_GPU_ACC"] = acc
-        os.environ["MPASSIT_GPU_FILL"] = "ldgsts" if mode[0] == "l" else "bulk"
-        if mode[0] in "pl":
+        if mode[0] == "p":
             os.environ["MPASSIT_GPU_APPLY"] = "pipe"
-            os.environ["MPASSIT_GPU_STAGES"] = mode[1:] or "0"
+            st, _, mb = mode[1:].partition("b")
+            os.environ["MPASSIT_GPU_STAGES"] = st or "0"
+            if mb:
+                os.environ["MPASSIT_GPU_PIPE_MINB"] = mb
+            else:
+                os.environ.pop("MPASSIT_GPU_PIPE_MINB", None)
         else:
             os.environ["MPASSIT_GPU_APPLY"] = "direct"
             os.environ["MPASSIT_GPU_MINB"] = mode[1:] or "3"
