@@ -22,7 +22,8 @@ module mpassit_rg_mod
   ! enum values of include/mpassit_rg.h
   integer(c_int), parameter, public :: MPRG_BILINEAR = 0, MPRG_CONSERVE = 1, MPRG_NEAREST_STOD = 2
   integer(c_int), parameter, public :: MPRG_SRC_MESH_ELEMENT = 0, MPRG_SRC_MESH_NODE = 1, MPRG_SRC_GRID_CENTER = 2
-  integer(c_int), parameter, public :: MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3
+  integer(c_int), parameter, public :: MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3, &
+                                        MPRG_CENTER_HALO = 4
   integer(c_int), parameter, public :: MPRG_F32 = 0, MPRG_F64 = 1
   integer(c_int), parameter, public :: MPRG_HOST = 0, MPRG_DEVICE = 1
   integer(c_int), parameter, public :: MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2
@@ -30,7 +31,7 @@ module mpassit_rg_mod
   public :: mprg_init, mprg_finalize, mprg_last_error, mprg_error_message
   public :: mprg_set_mesh, mprg_set_target, mprg_get_slab
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
-  public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds
+  public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
   public :: mprg_comm_id, mprg_comm_init, mprg_gather
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
@@ -158,6 +159,15 @@ module mpassit_rg_mod
      integer(c_int) function mprg_rotate_winds(ctx, u, v, nlev, dtype, mem) bind(C, name="mprg_rotate_winds")
        import :: c_int, c_ptr, c_int32_t
        type(c_ptr), value :: ctx, u, v
+       integer(c_int32_t), value :: nlev
+       integer(c_int), value :: dtype, mem
+     end function
+     !> same on the rows of MPRG_CENTER or MPRG_CENTER_HALO (the mass-point winds of the U/V chain)
+     integer(c_int) function mprg_rotate_winds_on(ctx, stagger, u, v, nlev, dtype, mem) &
+         bind(C, name="mprg_rotate_winds_on")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, u, v
+       integer(c_int), value :: stagger
        integer(c_int32_t), value :: nlev
        integer(c_int), value :: dtype, mem
      end function

@@ -40,7 +40,13 @@ enum { MPRG_BILINEAR = 0, MPRG_CONSERVE = 1, MPRG_NEAREST_STOD = 2 };
  * CENTER stagger (u/v_target_grid_nostag, interp.F90:298,316) */
 enum { MPRG_SRC_MESH_ELEMENT = 0, MPRG_SRC_MESH_NODE = 1, MPRG_SRC_GRID_CENTER = 2 };
 /* ESMF_STAGGERLOC_* of the destination, interp.F90:477-520, model_grid.F90:707-728 */
-enum { MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3 };
+enum { MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3,
+       /* CENTER rows of this rank widened by one halo row on each side (clipped to the grid): the
+        * mass-point rows that this rank's EDGE1 / EDGE2 points interpolate from.  The reference gets
+        * them through ESMF's halo exchange inside the Grid->Grid regrid (interp.F90:298,316); here the
+        * wind chain recomputes them from the replicated source mesh instead, so no rank waits on a
+        * neighbour.  Defined as soon as CENTER is set; equals CENTER on one rank. */
+       MPRG_CENTER_HALO = 4 };
 enum { MPRG_F32 = 0, MPRG_F64 = 1 };
 enum { MPRG_HOST = 0, MPRG_DEVICE = 1 };
 /* per-field fused epilogues (WRF-compat post-ops the reference runs serially on
@@ -116,7 +122,8 @@ int mprg_route_import_csr(mprg_ctx *ctx, int64_t nSrc, int64_t nDst, const int32
  *      nfields stacked fields in ONE batched launch sequence.
  *      src[f]: [nSrc][nlev[f]] level-fastest == MPAS file order
  *              (input_data.F90:630,645); for MPRG_SRC_GRID_CENTER the source is a
- *              previous output, [nlev[f]][nj][ni] (level-slowest).
+ *              previous output on this rank's MPRG_CENTER_HALO rows,
+ *              [nlev[f]][rows][ni] (level-slowest; the whole grid on one rank).
  *      dst[f]: this rank's slab [nlev[f]][nj_slab][ni] (the full grid on 1 rank).
  *      Unmapped destination points are written 0 (zeroregion=TOTAL default).
  *      src_mem / dst_mem: MPRG_HOST buffers are copied through the engine's
@@ -138,6 +145,8 @@ int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields,
 int mprg_set_rotation(mprg_ctx *ctx, const double *cosa, const double *sina);
 int mprg_has_rotation(const mprg_ctx *ctx); /* 1 once mprg_set_rotation succeeded */
 int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem);
+/* same on the rows of `stagger` = MPRG_CENTER or MPRG_CENTER_HALO (u, v: [nlev][rows][ni]) */
+int mprg_rotate_winds_on(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype, int mem);
 
 /* ---- gather: replaces ESMF_FieldGather(rootPet=0), write_data.F90:1006-1453.
  *      Collects every rank's slab of a [nlev][nj][ni] field on `root`.

@@ -10,7 +10,7 @@
 //                   contiguous 128..256-byte request; the finished 32-target x
 //                   64-level tile is transposed through shared memory so each level
 //                   row leaves as one coalesced 128-byte store into [lev][j][i].
-//   k_apply_flat    2-D fields (nlev == 1): lanes run along targets, the row's
+//   k_apply_flat    2-D fields and short columns (nlev <= 8: soil): lanes run along targets, the row's
 //                   (col, w) stay in registers across the stacked fields.
 //   k_apply_planes  source is itself a [lev][j][i] grid field (centre -> edge
 //                   staggering, interp.F90:298,316): lanes along targets per level.
@@ -236,6 +236,8 @@ k_apply_cols(ApplyArgs<TACC> a) {
 // ---------------------------------------------------------------------------
 constexpr int kFlatRow = 4;  // row entries held in registers; longer rows stream from global
 
+constexpr int kShortLev = 8;  // fields with at most this many levels (2-D fields, soil) take the flat kernel
+
 template <typename TIN, typename TOUT, typename TACC>
 __global__ void __launch_bounds__(256)
 k_apply_flat(ApplyArgs<TACC> a) {
@@ -253,12 +255,36 @@ k_apply_flat(ApplyArgs<TACC> a) {
     for (int f = 0; f < a.nfields; ++f) {
         const FieldDev fd = a.fields[f];
         const TIN *__restrict__ src = (const TIN *)fd.src;
-        TACC acc = 0;
+        const int nlev = fd.nlev;
+        if (nlev == 1) {
+            TACC acc = 0;
 #pragma unroll
-        for (int k = 0; k < kFlatRow; ++k)
-            if (b + k < e) acc += w[k] * (TACC)__ldg(src + c[k]);
-        for (int k = b + kFlatRow; k < e; ++k) acc += __ldg(a.w + k) * (TACC)__ldg(src + __ldg(a.col + k));
-        st_stream((TOUT *)fd.dst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+            for (int k = 0; k < kFlatRow; ++k)
+                if (b + k < e) acc += w[k] * (TACC)__ldg(src + c[k]);
+            for (int k = b + kFlatRow; k < e; ++k) acc += __ldg(a.w + k) * (TACC)__ldg(src + __ldg(a.col + k));
+            st_stream((TOUT *)fd.dst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+        } else {
+            // short columns (soil layers): the whole column of every row entry, one coalesced store per level
+            TACC acc[kShortLev];
+#pragma unroll
+            for (int l = 0; l < kShortLev; ++l) acc[l] = 0;
+            for (int k = b; k < e; ++k) {
+                const bool inreg = k - b < kFlatRow;
+                TACC wk = (TACC)0;
+                int ck = 0;
+#pragma unroll
+                for (int q = 0; q < kFlatRow; ++q)
+                    if (k - b == q) { wk = w[q]; ck = c[q]; }
+                if (!inreg) { wk = __ldg(a.w + k); ck = __ldg(a.col + k); }
+                const TIN *p = src + (size_t)ck * nlev;
+#pragma unroll
+                for (int l = 0; l < kShortLev; ++l)
+                    if (l < nlev) acc[l] += wk * (TACC)__ldg(p + l);
+            }
+#pragma unroll
+            for (int l = 0; l < kShortLev; ++l)
+                if (l < nlev) st_stream((TOUT *)fd.dst + (size_t)l * a.nDst + t, (TOUT)epilogue(acc[l], fd.epi_op, fd.epi_arg));
+        }
     }
 }
 
@@ -550,7 +576,7 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
         if (!fields[f].src || !fields[f].dst) fail(32, "mprg_apply: field %d has a null buffer", f);
         FieldDev d{fields[f].src, fields[f].dst, fields[f].nlev, fields[f].epi_op, fields[f].epi_arg};
         if (r->srcLevelSlowest) planes.push_back(d);
-        else if (d.nlev == 1) flat.push_back(d);
+        else if (d.nlev <= kShortLev) flat.push_back(d);
         else if ((d.nlev * in_sz) % 16 == 0 && ((uintptr_t)d.src % 16) == 0) cols_vec.push_back(d);
         else cols_sca.push_back(d);
     }
@@ -590,14 +616,15 @@ __global__ void k_rotate(T *__restrict__ u, T *__restrict__ v, const double *__r
     }
 }
 
-void rotate_device(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype) {
+void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype) {
     if (!ctx->haveRot) fail(41, "mprg_rotate_winds: mprg_set_rotation was not called");
-    const Target &tg = ctx->target[MPRG_CENTER];
+    const Target &tg = ctx->target[stagger];
     const int64_t n = tg.nSlab();
     if (n == 0 || nlev <= 0) return;
-    dim3 g((unsigned)((n + 255) / 256), (unsigned)min(nlev, 64));
-    if (dtype == MPRG_F32) k_rotate<float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, ctx->cosa.p, ctx->sina.p, n, nlev);
-    else k_rotate<double><<<g, 256, 0, ctx->stream>>>((double *)u, (double *)v, ctx->cosa.p, ctx->sina.p, n, nlev);
+    const double *cosa = ctx->cosa.p + tg.slabOffset(), *sina = ctx->sina.p + tg.slabOffset();
+    dim3 g((unsigned)((n + 255) / 256), (unsigned)min(nlev, 4));  // >= 15 levels per thread: tana, den once per point
+    if (dtype == MPRG_F32) k_rotate<float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, cosa, sina, n, nlev);
+    else k_rotate<double><<<g, 256, 0, ctx->stream>>>((double *)u, (double *)v, cosa, sina, n, nlev);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
 }

@@ -243,12 +243,21 @@ k_apply_pipe(PipeArgs<TACC> a) {
         const TACC earg = (TACC)ud.epi_arg;
         const int ngroups = (Ln + 3) >> 2;
         if (!live) continue;
+        // unaligned units: byte offset of each register-held entry's first wanted level inside its staged
+        // 16-byte-aligned window, (c * nlev + L0) mod EPV = ((c mod EPV) * (nlev mod EPV) + L0 mod EPV) mod EPV
+        const int nm = ud.nlev & (EPV - 1), lm = ud.L0 & (EPV - 1);
+        auto win_off = [&](int so) { return (so & ~15) + ((((so & 15) * nm + lm) & (EPV - 1)) * (int)sizeof(TIN)); };
+        int po[3] = {0, 0, 0};
+        if (!aligned) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) po[j] = win_off(ro[j]);
+        }
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
         TOUT *d = (TOUT *)ud.dst + ((size_t)(ud.L0 + 4 * warp) * a.nDst + t0 + lane);
         for (int g = warp; g < ngroups; g += kPipeWarps, d += grp8) {
             TACC acc[4] = {0, 0, 0, 0};
+            const unsigned lp = st + g * GB;
             if (aligned) {
-                const unsigned lp = st + g * GB;
                 if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
                     fma4<TIN, TACC>(acc, rw[0], lp + (ro[0] & ~15));
                     fma4<TIN, TACC>(acc, rw[1], lp + (ro[1] & ~15));
@@ -261,22 +270,18 @@ k_apply_pipe(PipeArgs<TACC> a) {
                     for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (s_off[k] & ~15));
                 }
             } else {
-                // element offset of a column's first wanted level inside its staged window:
-                //   (c * nlev + L0) mod EPV = ((c mod EPV) * (nlev mod EPV) + L0 mod EPV) mod EPV
-                const int nm = ud.nlev & (EPV - 1), lm = ud.L0 & (EPV - 1);
-                auto entry = [&](TACC wt, int so) {
-                    const int eo = ((so & 15) * nm + lm) & (EPV - 1);
-                    // the staged window holds EPV-1 elements of slack after the chunk: reads past Ln stay inside the slot
-                    const unsigned p = st + (so & ~15) + (eo + 4 * g) * (int)sizeof(TIN);
+                // 4-byte loads; the staged window holds EPV-1 elements of slack after the chunk, so reads
+                // past Ln stay inside the slot (their results are never stored)
+                auto entry = [&](TACC wt, unsigned p) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc[k] += wt * (TACC)lds1<TIN>(p + k * (int)sizeof(TIN));
                 };
                 if (fast) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
-                        if (all3 || j < rlen) entry(rw[j], ro[j]);
+                        if (all3 || j < rlen) entry(rw[j], lp + po[j]);
                 } else {
-                    for (int k = rbeg; k < rbeg + rlen; ++k) entry(s_w[k], s_off[k]);
+                    for (int k = rbeg; k < rbeg + rlen; ++k) entry(s_w[k], lp + win_off(s_off[k]));
                 }
             }
             if (eop != MPRG_EPI_NONE) {

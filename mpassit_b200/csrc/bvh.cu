@@ -93,6 +93,17 @@ __global__ void k_leaf_boxes(const float *__restrict__ lo, const float *__restri
     nodes[2 * node + 1] = make_float4(hy, hz, 0.f, 0.f);
 }
 
+// per-primitive boxes in Morton order (lets a leaf visitor reject a primitive without touching its geometry)
+__global__ void k_prim_boxes(const float *__restrict__ lo, const float *__restrict__ hi,
+                             const int32_t *__restrict__ primId, int32_t n, float4 *__restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int id = primId[s];
+    const float *l = lo + 3 * (size_t)id, *h = hi + 3 * (size_t)id;
+    out[2 * (size_t)s] = make_float4(l[0], l[1], l[2], h[0]);
+    out[2 * (size_t)s + 1] = make_float4(h[1], h[2], 0.f, 0.f);
+}
+
 __global__ void k_inner_level(float4 *nodes, int32_t first, int32_t count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -151,7 +162,8 @@ void bvh_build_points(mprg_ctx *ctx, const double *xyz_dev, int32_t n, Bvh &out,
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-void bvh_build_boxes(mprg_ctx *ctx, const float *lo_dev, const float *hi_dev, int32_t n, Bvh &out) {
+void bvh_build_boxes(mprg_ctx *ctx, const float *lo_dev, const float *hi_dev, int32_t n, Bvh &out,
+                     bool keepPrimBoxes) {
     if (n <= 0) fail(21, "bvh_build_boxes: no primitives");
     DevBuf<uint64_t> keys(n);
     DevBuf<int32_t> ids(n);
@@ -164,6 +176,11 @@ void bvh_build_boxes(mprg_ctx *ctx, const float *lo_dev, const float *hi_dev, in
     k_leaf_boxes<<<(out.nLeafNodes + 255) / 256, 256, 0, ctx->stream>>>(lo_dev, hi_dev, out.primId.p, n,
                                                                          out.nLeafNodes, out.nodes.p);
     ctx->launches++;
+    if (keepPrimBoxes) {
+        out.primBox.alloc(2 * (size_t)n);
+        k_prim_boxes<<<(n + 255) / 256, 256, 0, ctx->stream>>>(lo_dev, hi_dev, out.primId.p, n, out.primBox.p);
+        ctx->launches++;
+    }
     build_inner(ctx, out);
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
 }

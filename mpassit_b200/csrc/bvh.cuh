@@ -19,7 +19,16 @@ struct BvhView {
     const int32_t *primId;
     int32_t nLeafNodes;
     int32_t nPrim;
+    const float4 *primBox = nullptr;  // optional per-primitive boxes, Morton order
 };
+
+// does primitive s (Morton order) overlap the query box?  true when no per-primitive boxes are kept
+__device__ __forceinline__ bool prim_hit(const BvhView &t, int s, d3 qlo, d3 qhi) {
+    if (!t.primBox) return true;
+    const float4 a = __ldg(t.primBox + 2 * (size_t)s), b = __ldg(t.primBox + 2 * (size_t)s + 1);
+    return (double)a.x <= qhi.x && (double)a.w >= qlo.x && (double)a.y <= qhi.y && (double)b.x >= qlo.y &&
+           (double)a.z <= qhi.z && (double)b.y >= qlo.z;
+}
 
 __device__ __forceinline__ void node_box(const float4 *nodes, int i, float &lx, float &ly, float &lz,
                                          float &hx, float &hy, float &hz) {

@@ -2,12 +2,31 @@
 // No exception crosses the boundary: every entry returns an rc and records a
 // message retrievable with mprg_last_error().
 #include <algorithm>
+#include <chrono>
 
 #include "common.cuh"
 
 using namespace mprg;
 
 static std::string g_init_error;
+
+// MPASSIT_TRACE=1: host wall time of every store / apply call on stderr (where an end-to-end pass goes)
+struct Trace {
+    const char *what;
+    int a, b;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    Trace(const char *w, int a_ = 0, int b_ = 0) : what(w), a(a_), b(b_) {
+        static const bool enabled = getenv("MPASSIT_TRACE") != nullptr;
+        on = enabled;
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    ~Trace() {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[mprg] %-14s %3d %3d  %9.3f ms\n", what, a, b, ms);
+    }
+};
 
 #define MPRG_ENTER(ctx)                                     \
     if (!(ctx)) return 1;                                   \
@@ -173,17 +192,19 @@ int mprg_set_target(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const do
 }
 
 int mprg_get_slab(const mprg_ctx *ctx, int stagger, int32_t *j0, int32_t *j1) {
-    if (!ctx || stagger < 0 || stagger > 3 || !ctx->target[stagger].set) return 1;
+    if (!ctx || stagger < 0 || stagger > MPRG_CENTER_HALO || !ctx->target[stagger].set) return 1;
     if (j0) *j0 = ctx->target[stagger].j0;
     if (j1) *j1 = ctx->target[stagger].j1;
     return 0;
 }
 
 int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_route **rh) {
+    Trace tr("store", method, dst_stagger);
     MPRG_ENTER(ctx)
     if (!rh) fail(1, "mprg_store: null route pointer");
     *rh = nullptr;
-    if (dst_stagger < 0 || dst_stagger > 3) fail(51, "mprg_store: bad destination stagger %d", dst_stagger);
+    if (dst_stagger < 0 || dst_stagger > MPRG_CENTER_HALO) fail(51, "mprg_store: bad destination stagger %d", dst_stagger);
+    if (dst_stagger == MPRG_CENTER_HALO && ctx->nranks == 1) dst_stagger = MPRG_CENTER;  // same rows: share the route
     if (!ctx->target[dst_stagger].set) fail(52, "mprg_store: target stagger %d not set", dst_stagger);
     if (src_loc != MPRG_SRC_GRID_CENTER && ctx->mesh.nCells == 0) fail(53, "mprg_store: mesh not set");
     auto key = std::make_tuple(method, src_loc, dst_stagger);
@@ -231,6 +252,7 @@ int mprg_release(mprg_ctx *ctx, mprg_route *rh) {
 }
 
 int mprg_clear_routes(mprg_ctx *ctx) {
+    Trace tr("clear_routes");
     MPRG_ENTER(ctx)
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     for (auto &kv : ctx->routes) {
@@ -372,6 +394,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
 int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
                   int src_dtype, int src_mem, void *const *dst, int dst_dtype, int dst_mem, const int32_t *epi_op,
                   const double *epi_arg) {
+    Trace tr("apply", nfields, src_mem * 2 + dst_mem);
     MPRG_ENTER(ctx)
     apply_impl(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst, dst_dtype, dst_mem, epi_op, epi_arg);
     MPRG_LEAVE(ctx)
@@ -390,36 +413,40 @@ int mprg_set_rotation(mprg_ctx *ctx, const double *cosa, const double *sina) {
     const Target &tg = ctx->target[MPRG_CENTER];
     if (!tg.set) fail(42, "mprg_set_rotation: CENTER target not set");
     if (!cosa || !sina) fail(1, "mprg_set_rotation: null argument");
-    int64_t n = tg.nSlab();
-    ctx->cosa.alloc(n > 0 ? n : 1);
-    ctx->sina.alloc(n > 0 ? n : 1);
-    if (n) {
-        MPRG_CUDA(cudaMemcpyAsync(ctx->cosa.p, cosa + tg.slabOffset(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        MPRG_CUDA(cudaMemcpyAsync(ctx->sina.p, sina + tg.slabOffset(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
+    const int64_t n = (int64_t)tg.ni * tg.nj;  // full grid: both CENTER and CENTER_HALO rows index into it
+    ctx->cosa.alloc(n);
+    ctx->sina.alloc(n);
+    MPRG_CUDA(cudaMemcpyAsync(ctx->cosa.p, cosa, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MPRG_CUDA(cudaMemcpyAsync(ctx->sina.p, sina, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->haveRot = true;
     MPRG_LEAVE(ctx)
 }
 
-int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem) {
+int mprg_rotate_winds_on(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype, int mem) {
     MPRG_ENTER(ctx)
     if (!u || !v) fail(1, "mprg_rotate_winds: null argument");
-    const Target &tg = ctx->target[MPRG_CENTER];
+    if (stagger != MPRG_CENTER && stagger != MPRG_CENTER_HALO) fail(43, "mprg_rotate_winds: winds live on CENTER rows");
+    const Target &tg = ctx->target[stagger];
+    if (!tg.set) fail(42, "mprg_rotate_winds: CENTER target not set");
     const size_t bytes = (size_t)tg.nSlab() * nlev * (dtype == MPRG_F32 ? 4 : 8);
     if (mem == MPRG_DEVICE) {
-        rotate_device(ctx, u, v, nlev, dtype);
+        rotate_device(ctx, stagger, u, v, nlev, dtype);
     } else {
-        ctx->stageIn[0].ensure(2 * bytes);
+        ctx->stageIn[0].ensure_shared(2 * bytes);
         unsigned char *du = ctx->stageIn[0].p, *dv = du + bytes;
         MPRG_CUDA(cudaMemcpyAsync(du, u, bytes, cudaMemcpyHostToDevice, ctx->stream));
         MPRG_CUDA(cudaMemcpyAsync(dv, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        rotate_device(ctx, du, dv, nlev, dtype);
+        rotate_device(ctx, stagger, du, dv, nlev, dtype);
         MPRG_CUDA(cudaMemcpyAsync(u, du, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         MPRG_CUDA(cudaMemcpyAsync(v, dv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     MPRG_LEAVE(ctx)
+}
+
+int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem) {
+    return mprg_rotate_winds_on(ctx, MPRG_CENTER, u, v, nlev, dtype, mem);
 }
 
 // ---------------------------------------------------------------------------

@@ -107,6 +107,7 @@ struct Bvh {
     int32_t nLeafNodes = 0;    // power of two
     DevBuf<float4> nodes;      // [2*nLeafNodes-1][2]: (lox,loy,loz,hix) (hiy,hiz,-,-)
     DevBuf<int32_t> primId;    // [nPrim] Morton order -> original id
+    DevBuf<float4> primBox;    // optional [nPrim][2], Morton order: per-primitive boxes (same packing as nodes)
 };
 
 struct Mesh {
@@ -127,6 +128,8 @@ struct Target {
     int32_t ni = 0, nj = 0;    // full grid
     int32_t j0 = 0, j1 = 0;    // slab rows owned by this rank
     DevBuf<double> xyz;        // full grid [nj][ni][3]
+    const double *xyzRef = nullptr;  // MPRG_CENTER_HALO shares CENTER's coordinates
+    const double *x() const { return xyzRef ? xyzRef : xyz.p; }
     bool set = false;
     int64_t nSlab() const { return (int64_t)(j1 - j0) * ni; }
     int64_t slabOffset() const { return (int64_t)j0 * ni; }
@@ -163,10 +166,10 @@ struct mprg_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::string err;
     mprg::Mesh mesh;
-    mprg::Target target[4];
+    mprg::Target target[5];           // + MPRG_CENTER_HALO (derived from CENTER)
     std::map<std::tuple<int, int, int>, mprg_route *> routes;
     std::vector<mprg_route *> imported;
-    mprg::DevBuf<double> cosa, sina;  // CENTER slab
+    mprg::DevBuf<double> cosa, sina;  // CENTER, full grid
     bool haveRot = false;
     int64_t launches = 0;
     double last_ms = 0.0;
@@ -200,7 +203,8 @@ inline void para_range(int32_t n, int nprocs, int irank, int32_t *begin, int32_t
 
 // bvh.cu
 void bvh_build_points(mprg_ctx *ctx, const double *xyz_dev, int32_t n, Bvh &out, DevBuf<double> *sortedXyz);
-void bvh_build_boxes(mprg_ctx *ctx, const float *lo_dev, const float *hi_dev, int32_t n, Bvh &out);
+void bvh_build_boxes(mprg_ctx *ctx, const float *lo_dev, const float *hi_dev, int32_t n, Bvh &out,
+                     bool keepPrimBoxes = false);
 
 // mesh.cu
 void mesh_set(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonC,
@@ -230,7 +234,7 @@ struct ApplyField {
 };
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
                   int dst_dtype);
-void rotate_device(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype);
+void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype);
 
 // gather.cu
 void comm_destroy(mprg_ctx *ctx);

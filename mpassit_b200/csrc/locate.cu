@@ -36,7 +36,7 @@ void store_nearest(mprg_ctx *ctx, mprg_route *r) {
     r->rowptr.alloc(n + 1); r->col.alloc(n); r->w.alloc(n);
     BvhView v{m.cellBvh.nodes.p, m.cellBvh.primId.p, m.cellBvh.nLeafNodes, m.cellBvh.nPrim};
     k_nearest<<<(unsigned)((n + 1 + 127) / 128), 128, 0, ctx->stream>>>(
-        v, m.cellSorted.p, tg.xyz.p + 3 * tg.slabOffset(), n, r->rowptr.p, r->col.p, r->w.p);
+        v, m.cellSorted.p, tg.x() + 3 * tg.slabOffset(), n, r->rowptr.p, r->col.p, r->w.p);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
 }
@@ -106,7 +106,7 @@ void store_bilinear_element(mprg_ctx *ctx, mprg_route *r) {
     DevBuf<double> ew(3 * n);
     BvhView v{m.triBvh.nodes.p, m.triBvh.primId.p, m.triBvh.nLeafNodes, m.triBvh.nPrim};
     k_bilinear_tri<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
-        v, m.tri.p, m.cellXyz.p, tg.xyz.p + 3 * tg.slabOffset(), n, elem.p, ecol.p, ew.p, cnt.p);
+        v, m.tri.p, m.cellXyz.p, tg.x() + 3 * tg.slabOffset(), n, elem.p, ecol.p, ew.p, cnt.p);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
     r->rowptr.alloc(n + 1);

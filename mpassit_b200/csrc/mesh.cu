@@ -5,6 +5,7 @@
 // unit-sphere Cartesian fp64, the dual (Delaunay) triangles are derived by
 // inverting verticesOnCell on the device, and search structures are built
 // lazily the first time a regrid method needs them.
+#include <algorithm>
 #include <cmath>
 #include <thread>
 
@@ -192,7 +193,7 @@ void mesh_need_poly_bvh(mprg_ctx *ctx) {
     k_poly_boxes<<<(m.nCells + 255) / 256, 256, 0, ctx->stream>>>(m.nCells, m.maxEdges, m.voc.p, m.vertXyz.p,
                                                                   lo.p, hi.p);
     ctx->launches++;
-    bvh_build_boxes(ctx, lo.p, hi.p, m.nCells, m.polyBvh);
+    bvh_build_boxes(ctx, lo.p, hi.p, m.nCells, m.polyBvh, /*keepPrimBoxes=*/true);
     m.havePolyBvh = true;
 }
 
@@ -212,10 +213,22 @@ void target_set(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const double
     MPRG_CUDA(cudaMemcpyAsync(t.xyz.p, x.data(), t.xyz.bytes(), cudaMemcpyHostToDevice, ctx->stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     t.set = true;
+    t.xyzRef = nullptr;
+    if (stagger == MPRG_CENTER) {
+        // CENTER rows +- one halo row: what this rank's EDGE1 / EDGE2 rows read (para_range over nj and
+        // nj + 1 differ by at most one row at each slab boundary)
+        Target &h = ctx->target[MPRG_CENTER_HALO];
+        h.ni = ni; h.nj = nj;
+        h.j0 = ctx->nranks > 1 ? std::max(0, t.j0 - 1) : t.j0;
+        h.j1 = ctx->nranks > 1 ? std::min(nj, t.j1 + 1) : t.j1;
+        h.xyzRef = t.xyz.p;
+        h.set = true;
+        ctx->haveRot = false;  // angles belong to the previous grid
+    }
     // routes into this stagger (or out of CENTER) are stale
     for (auto it = ctx->routes.begin(); it != ctx->routes.end();) {
         int dst = std::get<2>(it->first), srcloc = std::get<1>(it->first);
-        if (dst == stagger || (srcloc == MPRG_SRC_GRID_CENTER && stagger == MPRG_CENTER)) {
+        if (dst == stagger || (stagger == MPRG_CENTER && (srcloc == MPRG_SRC_GRID_CENTER || dst == MPRG_CENTER_HALO))) {
             it->second->memoised = false;
             if (it->second->refcount <= 0) delete it->second;
             it = ctx->routes.erase(it);

@@ -124,27 +124,41 @@ __global__ void k_compact4(int64_t nDst, const int32_t *__restrict__ rowptr, con
 }
 
 void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r) {
-    Target &src = ctx->target[MPRG_CENTER];
+    // Source = the CENTER rows this rank holds mass-point values for (MPRG_CENTER_HALO: its own slab
+    // +- one row; the whole grid on one rank).  Quads, their ids (tie rule: smallest id wins) and the
+    // emitted columns are all relative to that row block, which preserves the global order.
+    Target &src = ctx->target[MPRG_CENTER_HALO];
     Target &tg = ctx->target[r->dst_stagger];
     if (!src.set) fail(55, "mprg_store: GRID_CENTER source needs the CENTER stagger");
-    if (ctx->nranks > 1) fail(56, "mprg_store: GRID_CENTER source is single-rank in this build (needs a halo row)");
-    if (src.ni < 2 || src.nj < 2) fail(57, "mprg_store: CENTER grid too small for quads");
-    int64_t nq = (int64_t)(src.ni - 1) * (src.nj - 1);
+    if (r->dst_stagger != MPRG_EDGE1 && r->dst_stagger != MPRG_EDGE2)
+        fail(56, "mprg_store: GRID_CENTER source feeds the EDGE1 / EDGE2 staggers only");
+    const int32_t srows = src.j1 - src.j0;
+    int64_t n = tg.nSlab();
+    r->nDst = n;
+    r->nSrc = (int64_t)src.ni * srows;
+    r->srcLevelSlowest = true;
+    r->srcPlane = r->nSrc;
+    if (src.ni < 2 || srows < 2) {
+        if (ctx->nranks == 1) fail(57, "mprg_store: CENTER grid too small for quads");
+        // a rank with fewer than two source rows owns no mappable edge point: all rows empty
+        r->nnz = 0;
+        r->rowptr.alloc(n + 1); r->col.alloc(1); r->w.alloc(1);
+        MPRG_CUDA(cudaMemsetAsync(r->rowptr.p, 0, (n + 1) * sizeof(int32_t), ctx->stream));
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        return;
+    }
+    const double *sxyz = src.x() + 3 * src.slabOffset();
+    int64_t nq = (int64_t)(src.ni - 1) * (srows - 1);
     DevBuf<float> lo(3 * nq), hi(3 * nq);
-    k_quad_boxes<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(src.ni, src.nj, src.xyz.p, lo.p, hi.p);
+    k_quad_boxes<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(src.ni, srows, sxyz, lo.p, hi.p);
     ctx->launches++;
     Bvh bvh;
     bvh_build_boxes(ctx, lo.p, hi.p, (int32_t)nq, bvh);
-    int64_t n = tg.nSlab();
-    r->nDst = n;
-    r->nSrc = (int64_t)src.ni * src.nj;
-    r->srcLevelSlowest = true;
-    r->srcPlane = r->nSrc;
     DevBuf<int32_t> ecol(4 * n), cnt(n + 1);
     DevBuf<double> ew(4 * n);
     BvhView v{bvh.nodes.p, bvh.primId.p, bvh.nLeafNodes, bvh.nPrim};
-    k_bilinear_quad<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(v, src.ni, src.xyz.p,
-                                                                          tg.xyz.p + 3 * tg.slabOffset(), n, ecol.p,
+    k_bilinear_quad<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(v, src.ni, sxyz,
+                                                                          tg.x() + 3 * tg.slabOffset(), n, ecol.p,
                                                                           ew.p, cnt.p);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
@@ -226,7 +240,7 @@ void store_bilinear_node(mprg_ctx *ctx, mprg_route *r) {
     DevBuf<double> ew(3 * n);
     BvhView v{m.polyBvh.nodes.p, m.polyBvh.primId.p, m.polyBvh.nLeafNodes, m.polyBvh.nPrim};
     k_bilinear_node<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
-        v, m.maxEdges, m.voc.p, m.vertXyz.p, tg.xyz.p + 3 * tg.slabOffset(), n, ecol.p, ew.p, cnt.p);
+        v, m.maxEdges, m.voc.p, m.vertXyz.p, tg.x() + 3 * tg.slabOffset(), n, ecol.p, ew.p, cnt.p);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
     r->rowptr.alloc(n + 1);

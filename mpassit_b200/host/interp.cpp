@@ -147,16 +147,22 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             const bool chain64 = acc_env && (!std::strcmp(acc_env, "f64") || !std::strcmp(acc_env, "fp64"));
             const int chain_dt = chain64 ? MPRG_F64 : ddt;
             const size_t chain_sz = chain_dt == MPRG_F64 ? 8 : 4;
+            // Mass-point winds live on MPRG_CENTER_HALO rows: this rank's CENTER slab plus the one row
+            // either side that its EDGE1 / EDGE2 points interpolate from (the reference gets those rows
+            // through ESMF's halo exchange; recomputing them from the replicated mesh needs no exchange).
+            bool halo_is_center = true;
             if (fu || fv) {
-                int32_t j0 = 0, j1 = 0, ni = 0, nj = 0;
+                int32_t j0 = 0, j1 = 0, c0 = 0, c1 = 0, ni = 0, nj = 0;
                 mpassit_target_dims(cfg, MPRG_CENTER, &ni, &nj);
-                ck(ctx, mprg_get_slab(ctx, MPRG_CENTER, &j0, &j1), "get_slab");
+                ck(ctx, mprg_get_slab(ctx, MPRG_CENTER_HALO, &j0, &j1), "get_slab");
+                ck(ctx, mprg_get_slab(ctx, MPRG_CENTER, &c0, &c1), "get_slab");
+                halo_is_center = (j0 == c0 && j1 == c1);
                 const size_t nslab = (size_t)(j1 - j0) * ni;
                 if (fu) ck(ctx, mprg_scratch(ctx, 0, nslab * fu->nlev * chain_sz, &d_um), "scratch");
                 if (fv) ck(ctx, mprg_scratch(ctx, 1, nslab * fv->nlev * chain_sz, &d_vm), "scratch");
             }
             // the winds join the main stacked apply when its destinations are device buffers of the same type
-            const bool winds_in_batch = (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR;
+            const bool winds_in_batch = (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR && halo_is_center;
 
             // one stacked apply for everything on the bilinear element->CENTER route:
             // 2d_patch (:207-221), hgt (:226-238), 3d_nz (:240-254), 3d_nzp1 (:331-347)
@@ -188,14 +194,14 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             // winds, interp.F90:256-328
             if (do_u || do_v) {
                 if (!winds_in_batch) {
-                    mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldRegridStore");
+                    mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER_HALO, "FieldRegridStore");
                     Batch b;
                     if (fu) b.add(fu->src, d_um, fu->nlev);
                     if (fv) b.add(fv->src, d_vm, fv->nlev);
                     run(ctx, rh, b, sdt, mem, chain_dt, MPRG_DEVICE, "FieldRegrid");
                 }
                 if (fu && fv && rotate)  // interp.F90:291-293
-                    ck(ctx, mprg_rotate_winds(ctx, d_um, d_vm, fu->nlev, chain_dt, MPRG_DEVICE), "rotate_winds_cgrid");
+                    ck(ctx, mprg_rotate_winds_on(ctx, MPRG_CENTER_HALO, d_um, d_vm, fu->nlev, chain_dt, MPRG_DEVICE), "rotate_winds_cgrid");
                 if (fu && io->u_stag) {  // interp.F90:295-311
                     mprg_route *ru = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE1, "FieldRegridStore");
                     const void *s = d_um; void *d = io->u_stag; int32_t nl = fu->nlev;

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libmpassit_rg.so")
 
 BILINEAR, CONSERVE, NEAREST_STOD = 0, 1, 2
 SRC_MESH_ELEMENT, SRC_MESH_NODE, SRC_GRID_CENTER = 0, 1, 2
-CENTER, EDGE1, EDGE2, CORNER = 0, 1, 2, 3
+CENTER, EDGE1, EDGE2, CORNER, CENTER_HALO = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
 EPI_NONE, EPI_ADD, EPI_MUL = 0, 1, 2
@@ -27,7 +27,7 @@ EXPORTS = [
     "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize",
     "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_get_slab", "mprg_store",
     "mprg_release", "mprg_clear_routes", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
-    "mprg_apply", "mprg_apply_ex", "mprg_set_rotation", "mprg_rotate_winds", "mprg_comm_id", "mprg_comm_init",
+    "mprg_apply", "mprg_apply_ex", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
     "mprg_gather", "mprg_kernel_launches", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
     "mprg_profile_reset", "mprg_route_src_referenced",
 ]
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
                                 C.POINTER(i32), C.POINTER(dbl)]
     L.mprg_set_rotation.argtypes = [vp, vp, vp]
     L.mprg_rotate_winds.argtypes = [vp, vp, vp, i32, C.c_int, C.c_int]
+    L.mprg_rotate_winds_on.argtypes = [vp, C.c_int, vp, vp, i32, C.c_int, C.c_int]
     L.mprg_comm_id.argtypes = [vp, vp]
     L.mprg_comm_init.argtypes = [vp, vp]
     L.mprg_gather.argtypes = [vp, C.c_int, i32, C.c_int, vp, C.c_int, vp]

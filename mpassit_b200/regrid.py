@@ -20,7 +20,7 @@ from typing import Sequence
 import numpy as np
 
 from . import lib as _l
-from .lib import (BILINEAR, CENTER, CONSERVE, CORNER, DEVICE, EDGE1, EDGE2, F32, F64, HOST,  # noqa: F401
+from .lib import (BILINEAR, CENTER, CENTER_HALO, CONSERVE, CORNER, DEVICE, EDGE1, EDGE2, F32, F64, HOST,  # noqa: F401
                   NEAREST_STOD, SRC_GRID_CENTER, SRC_MESH_ELEMENT, SRC_MESH_NODE, MprgError)
 
 
@@ -229,9 +229,9 @@ class Regridder:
         sa = np.ascontiguousarray(sina, np.float64)
         self._ck(self.L.mprg_set_rotation(self.ctx, ca.ctypes.data, sa.ctypes.data))
 
-    def rotate_winds(self, u, v, nlev: int) -> None:
+    def rotate_winds(self, u, v, nlev: int, stagger: int = CENTER) -> None:
         mem = DEVICE if _is_torch(u) else HOST
-        self._ck(self.L.mprg_rotate_winds(self.ctx, _ptr(u), _ptr(v), int(nlev), _dtype_code(u), mem))
+        self._ck(self.L.mprg_rotate_winds_on(self.ctx, int(stagger), _ptr(u), _ptr(v), int(nlev), _dtype_code(u), mem))
 
     # ---- gather ---------------------------------------------------------
     def comm_id(self) -> bytes:

@@ -206,3 +206,57 @@ def test_interp_data_end_to_end(rg, orc, host, lc_case):
     assert np.array_equal(got["tslb"], np.round(got["tslb"]))
     # unmapped bilinear points are exactly zero, and some exist in this case
     assert (got["theta"] == 0).any() and (got["xland"] != 0).all()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_interp_data_rank_slabs_equal_single_rank(engine_lib, host, lc_case, nranks):
+    """The whole pass on `nranks` row slabs (ranks emulated one after another on one device; the regrid
+    itself needs no collective) reproduces the single-rank output bit-for-bit for every field, including
+    the staggered winds whose mass-point halo rows are recomputed locally (MPRG_CENTER_HALO)."""
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import Regridder
+
+    cfg, grids, mesh, cosa, sina = lc_case
+    nz, nsoil = 8, 4
+    F = _fields(mesh, nz, nsoil)
+    shapes = {k: grids[k][0].shape for k in ("M", "U", "V")}
+
+    def run(rank, n):
+        r = Regridder(device=0, rank=rank, nranks=n)
+        _load(r, grids, mesh)
+        rows = {k: r.slab(s) for k, s in (("M", l.CENTER), ("U", l.EDGE1), ("V", l.EDGE2))}
+        nM = (rows["M"][1] - rows["M"][0]) * shapes["M"][1]
+        nU = (rows["U"][1] - rows["U"][0]) * shapes["U"][1]
+        nV = (rows["V"][1] - rows["V"][0]) * shapes["V"][1]
+
+        def specs(items, table):
+            tn = dict(table)
+            return [host.FieldSpec(nm, tn.get(nm, nm), a.shape[1], a, np.full((a.shape[1], nM), np.nan, np.float32))
+                    for nm, a in items]
+
+        diag, h2, h3, soil = (specs(F["diag"], defaults.DIAGLIST), specs(F["hist_2d"], defaults.HISTLIST_2D),
+                              specs(F["hist_3d"], defaults.HISTLIST_3D), specs(F["soil"], defaults.HISTLIST_SOIL))
+        hgt = np.full((1, nM), np.nan, np.float32)
+        ust = np.full((nz, nU), np.nan, np.float32)
+        vst = np.full((nz, nV), np.nan, np.float32)
+        host.interp_data(r, cfg, diag=diag, hist_2d=h2, hist_3d=h3, soil=soil, ter=F["ter"], hgt=hgt, u_stag=ust,
+                         v_stag=vst, nz=nz)
+        out = {s.name: (s.dst, "M") for s in diag + h2 + h3 + soil if not s.name.startswith("uReconstruct")}
+        out["HGT"], out["U"], out["V"] = (hgt, "M"), (ust, "U"), (vst, "V")
+        r.close()
+        return out, rows
+
+    single, _ = run(0, 1)
+    parts = [run(k, nranks) for k in range(nranks)]
+    for name, (full, stag) in single.items():
+        ni = shapes[stag][1]
+        pieces = [p[0][name][0].reshape(full.shape[0], -1, ni) for p in parts]
+        got = np.concatenate(pieces, axis=1).reshape(full.shape[0], -1)
+        assert got.shape == full.shape, name
+        assert not np.isnan(got).any(), name
+        assert np.array_equal(got, full), name
+    # slabs tile each stagger's rows exactly once
+    for k in ("M", "U", "V"):
+        spans = [p[1][k] for p in parts]
+        assert spans[0][0] == 0 and spans[-1][1] == shapes[k][0]
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

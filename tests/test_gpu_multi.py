@@ -1,0 +1,94 @@
+"""Two real GPUs (skipped on a one-GPU box): every rank regrids its own target-row slab, the slabs
+are gathered to rank 0 with mprg_gather (grouped ncclSend/ncclRecv over NVLink: the path's only
+collective, replacing ESMF_FieldGather, write_data.F90:1006-1453) and must equal the single-rank
+result bit-for-bit, for a CENTER field, the staggered winds (EDGE1 / EDGE2) and a nearest field."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from mpassit_b200 import lib as l
+    from mpassit_b200 import workload
+    from mpassit_b200.regrid import Regridder
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wl = workload.make("mini")
+        rg = Regridder(device=rank, rank=rank, nranks=world)
+        workload.load_geometry(rg, wl)
+        ids = [rg.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        rg.comm_init(ids[0])
+        F = workload.make_fields(wl, device=f"cuda:{rank}", rg=rg)
+        workload.run_interp(rg, wl, F["dev"], l.DEVICE)
+        names = {"theta": ("hist_3d", l.CENTER), "tslb": ("soil", l.CENTER)}
+        got = {}
+        for nm, (grp, stag) in names.items():
+            s = next(x for x in F["dev"][grp] if x.name == nm)
+            full = torch.full((s.nlev, wl.n_mass), float("nan"), device="cuda") if rank == 0 else None
+            rg.gather(stag, s.nlev, s.dst, 0, full)
+            got[nm] = full
+        for nm, stag, key in (("U", l.EDGE1, "u_stag"), ("V", l.EDGE2, "v_stag")):
+            n = wl.grids[nm][0].size
+            full = torch.full((wl.nz, n), float("nan"), device="cuda") if rank == 0 else None
+            rg.gather(stag, wl.nz, F["dev"][key], 0, full)
+            got[nm] = full
+        rg.synchronize()
+        dist.barrier()
+        if rank == 0:
+            # the same pass on one rank, same device, same synthetic inputs (seeded per field)
+            r1 = Regridder(device=0)
+            workload.load_geometry(r1, wl)
+            F1 = workload.make_fields(wl, device="cuda:0")
+            workload.run_interp(r1, wl, F1["dev"], l.DEVICE)
+            r1.synchronize()
+            want = {nm: next(x for x in F1["dev"][grp] if x.name == nm).dst for nm, (grp, _) in names.items()}
+            want["U"], want["V"] = F1["dev"]["u_stag"], F1["dev"]["v_stag"]
+            res = {nm: bool(torch.equal(got[nm], want[nm])) and not bool(torch.isnan(got[nm]).any()) for nm in want}
+            q.put(res)
+            r1.close()
+        dist.barrier()
+        rg.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_slabs_gather_equals_single_rank(engine_lib):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from mpassit_b200 import build
+
+    build.build_host()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res and all(res.values()), res
