@@ -275,28 +275,25 @@ def main():
     store_wall = time.perf_counter() - t0
     info = held[0].info()
 
-    def gather_outputs():
-        if world == 1:
-            return
-        # the path's only collective: slabs -> writing rank (write_data.F90:1006-1453)
+    # The path's only collective -- output slabs -> the writing rank (ESMF_FieldGather in write_to_file,
+    # write_data.F90:1006-1453) -- is not part of interp_data: it is timed on its own below and
+    # reported under "gather", all fields of the pass in one NCCL group.
+    gather_items = []
+    if world > 1:
+        def full(nlev, n):
+            return torch.empty((nlev, n), dtype=torch.float32, device="cuda") if rank == 0 else None
+
         for g in ("diag", "hist_2d", "hist_3d", "soil"):
             for s in F["dev"][g]:
                 if g == "hist_3d" and s.name in ("uReconstructZonal", "uReconstructMeridional"):
                     continue
-                rg.gather(L.CENTER, s.nlev, s.dst, 0, full_bufs[0][: s.nlev] if rank == 0 else None)
-        rg.gather(L.EDGE1, wl.nz, F["dev"]["u_stag"], 0, full_bufs[1] if rank == 0 else None)
-        rg.gather(L.EDGE2, wl.nz, F["dev"]["v_stag"], 0, full_bufs[2] if rank == 0 else None)
-
-    full_bufs = None
-    if world > 1 and rank == 0:
-        nzmax = wl.nz + 1
-        full_bufs = [torch.empty((nzmax, wl.n_mass), dtype=torch.float32, device="cuda"),
-                     torch.empty((wl.nz, wl.grids["U"][0].size), dtype=torch.float32, device="cuda"),
-                     torch.empty((wl.nz, wl.grids["V"][0].size), dtype=torch.float32, device="cuda")]
+                gather_items.append((L.CENTER, s.nlev, s.dst, full(s.nlev, wl.n_mass)))
+        gather_items.append((L.CENTER, 1, F["dev"]["hgt"], full(1, wl.n_mass)))
+        gather_items.append((L.EDGE1, wl.nz, F["dev"]["u_stag"], full(wl.nz, wl.grids["U"][0].size)))
+        gather_items.append((L.EDGE2, wl.nz, F["dev"]["v_stag"], full(wl.nz, wl.grids["V"][0].size)))
 
     def device_step():
         workload.run_interp(rg, wl, F["dev"], L.DEVICE)
-        gather_outputs()
 
     def barrier():
         torch.cuda.synchronize()
@@ -331,6 +328,28 @@ def main():
     ms_step = ms_total / args.steps
     units = wl.units_per_pass()
     value = units / (ms_step * 1e-3)
+
+    gather = None
+    if world > 1:
+        rg.gather_many(gather_items, 0)      # warm-up (NCCL channel setup)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = 5
+        g0.record()
+        for _ in range(nrep):
+            rg.gather_many(gather_items, 0)
+        g1.record()
+        barrier()
+        tt = torch.tensor([g0.elapsed_time(g1) / nrep], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        gms = float(tt.item())
+        total = sum(int(it[1]) * (wl.n_mass if it[0] == L.CENTER else wl.grids["U" if it[0] == L.EDGE1 else "V"][0].size) * 4
+                    for it in gather_items)
+        to_root = total * (world - 1) / world
+        gather = {"ms_per_pass": gms, "bytes_into_root": to_root, "GBps_into_root": to_root / (gms * 1e-3) / 1e9,
+                  "nvlink_peak_GBps": 770.0, "peak_source": "B200_PROFILING.md measured peer copy, per direction",
+                  "fields": len(gather_items), "note": "slabs of every output field -> rank 0, one NCCL group; not part of "
+                  "interp_data (the reference gathers in write_to_file), so not inside `value`"}
 
     # roofline of the dominant kernel, from per-launch CUDA events inside the timed steps.  A launch
     # class = (kernel, units per launch): the same kernel also runs a few small launches per step
@@ -413,6 +432,7 @@ def main():
                        "units_per_step": units, "target_points": wl.n_mass, "l2_policy": "inputs (>9 GB) exceed L2; no flush",
                        "parallelism": f"target row slabs x{world}", "weights": "resident (memoised) in `value`; rebuilt per step in `e2e`"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gather": gather,
             "store_ms": store_ms, "store_wall_s": store_wall,
             "route_bilinear": info,
         }

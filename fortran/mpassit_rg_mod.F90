@@ -32,7 +32,8 @@ module mpassit_rg_mod
   public :: mprg_set_mesh, mprg_set_target, mprg_get_slab
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
   public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
-  public :: mprg_comm_id, mprg_comm_init, mprg_gather
+  public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
+  public :: mprg_set_async, mprg_get_async, mprg_download
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
   interface
@@ -190,6 +191,32 @@ module mpassit_rg_mod
        type(c_ptr), value :: ctx, slab_dev, full_dev
        integer(c_int), value :: stagger, dtype, root
        integer(c_int32_t), value :: nlev
+     end function
+     !> asynchronous host-buffer applies (see mpassit_rg.h); synchronise with mprg_synchronize
+     integer(c_int) function mprg_set_async(ctx, on) bind(C, name="mprg_set_async")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: on
+     end function
+     integer(c_int) function mprg_get_async(ctx) bind(C, name="mprg_get_async")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function mprg_download(ctx, dev, host, bytes) bind(C, name="mprg_download")
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value :: ctx, dev, host
+       integer(c_size_t), value :: bytes
+     end function
+     !> nfields fields in one NCCL group (the ~20 back-to-back FieldGather calls of write_to_file)
+     integer(c_int) function mprg_gather_v(ctx, nfields, stagger, nlev, dtype, slab_dev, root, full_dev) &
+         bind(C, name="mprg_gather_v")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx
+       integer(c_int32_t), value :: nfields
+       integer(c_int), intent(in) :: stagger(*)
+       integer(c_int32_t), intent(in) :: nlev(*)
+       integer(c_int), value :: dtype, root
+       type(c_ptr), intent(in) :: slab_dev(*), full_dev(*)
      end function
   end interface
 

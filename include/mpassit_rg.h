@@ -64,6 +64,15 @@ const char *mprg_version(void);
  * as void*); NULL restores the context's own stream */
 int mprg_set_stream(mprg_ctx *ctx, void *cuda_stream);
 int mprg_synchronize(mprg_ctx *ctx);
+/* Host-buffer applies are blocking by default, like ESMF_FieldRegrid.  With async on they return once
+ * their copies and kernels are queued (the H2D / kernel / D2H pipeline then runs across consecutive
+ * applies, and beside weight generation, which has its own stream); the caller must not touch the host
+ * buffers of queued applies until mprg_synchronize returns.  Environment MPASSIT_GPU_ASYNC=1 sets the
+ * initial mode. */
+int mprg_set_async(mprg_ctx *ctx, int on);
+int mprg_get_async(const mprg_ctx *ctx);
+/* device -> host copy ordered after everything queued on the context so far (blocking unless async) */
+int mprg_download(mprg_ctx *ctx, const void *dev, void *host, size_t bytes);
 
 /* pinned host memory for callers that want full-speed H2D/D2H (optional) */
 int mprg_host_alloc(mprg_ctx *ctx, size_t bytes, void **ptr);
@@ -159,6 +168,10 @@ int mprg_comm_id(mprg_ctx *ctx, void *id128);
 int mprg_comm_init(mprg_ctx *ctx, const void *id128);
 int mprg_gather(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype,
                 const void *slab_dev, int root, void *full_dev);
+/* the same for nfields fields in ONE NCCL group (one launch, all peers and fields in flight together:
+ * what write_to_file's ~20 back-to-back FieldGather calls amount to).  full_dev[] is read on root only. */
+int mprg_gather_v(mprg_ctx *ctx, int32_t nfields, const int *stagger, const int32_t *nlev, int dtype,
+                  const void *const *slab_dev, int root, void *const *full_dev);
 
 /* ---- instrumentation */
 /* number of engine kernels launched on this context since init */

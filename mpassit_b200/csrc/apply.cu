@@ -380,7 +380,11 @@ static const void *push_desc(mprg_ctx *ctx, const void *host, size_t bytes) {
     if (need > kRing) fail(34, "mprg_apply: too many stacked fields");
     ctx->descHost.ensure(kRing);
     ctx->scratch.ensure(kRing);
-    if (ctx->descCursor + need > kRing) ctx->descCursor = 0;
+    if (ctx->descCursor + need > kRing) {
+        // wrapping: descriptors of launches still queued (asynchronous applies) must not be overwritten
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->descCursor = 0;
+    }
     unsigned char *h = (unsigned char *)ctx->descHost.p + ctx->descCursor;
     memcpy(h, host, bytes);
     unsigned char *d = ctx->scratch.p + ctx->descCursor;

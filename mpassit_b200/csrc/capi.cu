@@ -75,10 +75,13 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
         MPRG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         MPRG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
         MPRG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        MPRG_CUDA(cudaStreamCreateWithFlags(&c->store_stream, cudaStreamNonBlocking));
         c->stream = c->own_stream;
         MPRG_CUDA(cudaEventCreate(&c->ev0));
         MPRG_CUDA(cudaEventCreate(&c->ev1));
-        for (int i = 0; i < 2; ++i) {
+        MPRG_CUDA(cudaEventCreateWithFlags(&c->evDl, cudaEventDisableTiming));
+        if (const char *e = getenv("MPASSIT_GPU_ASYNC")) c->async = atoi(e) != 0;
+        for (int i = 0; i < mprg_ctx::kSlots; ++i) {
             MPRG_CUDA(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
             MPRG_CUDA(cudaEventCreateWithFlags(&c->evK[i], cudaEventDisableTiming));
             MPRG_CUDA(cudaEventCreateWithFlags(&c->evOut[i], cudaEventDisableTiming));
@@ -102,7 +105,9 @@ int mprg_finalize(mprg_ctx *ctx) {
     ctx->routes.clear();
     ctx->imported.clear();
     mprg::comm_destroy(ctx);
-    for (int i = 0; i < 2; ++i) {
+    if (ctx->evDl) cudaEventDestroy(ctx->evDl);
+    if (ctx->store_stream) cudaStreamDestroy(ctx->store_stream);
+    for (int i = 0; i < mprg_ctx::kSlots; ++i) {
         if (ctx->evIn[i]) cudaEventDestroy(ctx->evIn[i]);
         if (ctx->evK[i]) cudaEventDestroy(ctx->evK[i]);
         if (ctx->evOut[i]) cudaEventDestroy(ctx->evOut[i]);
@@ -132,6 +137,7 @@ int mprg_synchronize(mprg_ctx *ctx) {
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->store_stream));
     MPRG_LEAVE(ctx)
 }
 
@@ -175,6 +181,30 @@ int mprg_scratch(mprg_ctx *ctx, int slot, size_t bytes, void **ptr) {
 
 int mprg_has_rotation(const mprg_ctx *ctx) { return ctx && ctx->haveRot ? 1 : 0; }
 
+int mprg_set_async(mprg_ctx *ctx, int on) {
+    MPRG_ENTER(ctx)
+    if (ctx->async && !on) {  // leaving asynchronous mode: drain what is in flight
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        MPRG_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+        MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    }
+    ctx->async = on != 0;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_get_async(const mprg_ctx *ctx) { return ctx && ctx->async ? 1 : 0; }
+
+int mprg_download(mprg_ctx *ctx, const void *dev, void *host, size_t bytes) {
+    MPRG_ENTER(ctx)
+    if (!dev || !host) fail(1, "mprg_download: null argument");
+    // after everything queued so far on the context's stream; on the D2H stream so that it overlaps later kernels
+    MPRG_CUDA(cudaEventRecord(ctx->evDl, ctx->stream));
+    MPRG_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->evDl, 0));
+    MPRG_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (!ctx->async) MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    MPRG_LEAVE(ctx)
+}
+
 int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonCell_rad,
                   const double *latCell_rad, const double *lonVertex_rad, const double *latVertex_rad,
                   const int32_t *verticesOnCell) {
@@ -215,7 +245,14 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
         ctx->last_ms = 0.0;
         return 0;
     }
-    std::unique_ptr<mprg_route> r(new mprg_route());
+    // Weights depend on geometry only, so they are generated on their own stream: queued (asynchronous)
+    // applies keep streaming while the host waits here.  The call returns with the route complete.
+    struct StreamSwap {
+        mprg_ctx *c; cudaStream_t saved;
+        StreamSwap(mprg_ctx *c_) : c(c_), saved(c_->stream) { c->stream = c->store_stream; mprg::tl_stream = c->stream; }
+        ~StreamSwap() { c->stream = saved; mprg::tl_stream = saved; }
+    } swap(ctx);
+    std::unique_ptr<mprg_route> r(new mprg_route());  // after `swap`: on failure its buffers are freed on the store stream
     r->method = method; r->src_loc = src_loc; r->dst_stagger = dst_stagger;
     MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_NEAREST_STOD) store_nearest(ctx, r.get());
@@ -227,7 +264,7 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
     r->dstNi = ctx->target[dst_stagger].ni;
     route_finish(ctx, r.get());
     MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    MPRG_CUDA(cudaEventSynchronize(ctx->ev1));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));  // every allocation and kernel of the route is complete
     float ms = 0.f;
     MPRG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
@@ -329,10 +366,11 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
             fl[f] = ApplyField{src[f], dst[f], nlev[f], epi_op ? epi_op[f] : 0, epi_arg ? epi_arg[f] : 0.0};
         apply_device(ctx, rh, fl.data(), nfields, src_dtype, dst_dtype);
     } else {
-        // Pipelined staging: fields are cut into batches; batch b's H2D overlaps the
-        // kernels of batch b-1 and the D2H of batch b-2 (two staging slots each way).
+        // Pipelined staging: fields are cut into batches; a batch's H2D overlaps the kernels of the batch
+        // before it and the D2H of the ones before that.  The slot ring persists across calls, so with
+        // mprg_set_async(1) consecutive applies overlap the same way.
         const size_t budget = (size_t)768 << 20;
-        int f = 0, slot = 0, batch = 0;
+        int f = 0;
         while (f < nfields) {
             int g = f;
             size_t inB = 0, outB = 0;
@@ -342,10 +380,11 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                 if (g > f && (inB + a > budget || outB + b > budget)) break;
                 inB += a; outB += b; ++g;
             }
+            const int slot = (int)(ctx->slotCursor++ % mprg_ctx::kSlots);
             if (src_mem == MPRG_HOST) ctx->stageIn[slot].ensure_shared(inB);
             if (dst_mem == MPRG_HOST) ctx->stageOut[slot].ensure_shared(outB);
             // slot reuse: the kernel that last read stageIn[slot] / the D2H that last read stageOut[slot]
-            if (batch >= 2) {
+            if (ctx->slotUsed[slot]) {
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->evK[slot], 0));
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evOut[slot], 0));
             }
@@ -378,15 +417,17 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                     MPRG_CUDA(cudaMemcpyAsync(dst[k], ctx->stageOut[slot].p + oo, b, cudaMemcpyDeviceToHost, ctx->d2h_stream));
                     oo += (b + 255) & ~(size_t)255;
                 }
-                MPRG_CUDA(cudaEventRecord(ctx->evOut[slot], ctx->d2h_stream));
             }
+            MPRG_CUDA(cudaEventRecord(ctx->evOut[slot], ctx->d2h_stream));
+            ctx->slotUsed[slot] = true;
             f = g;
-            slot ^= 1;
-            ++batch;
         }
-        // host-buffer applies complete before returning (reference semantics: Regrid is blocking)
-        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (dst_mem == MPRG_HOST) MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+        // host-buffer applies complete before returning (reference semantics: Regrid is blocking) unless
+        // the caller asked for asynchronous applies and synchronises itself (mprg_synchronize)
+        if (!ctx->async) {
+            MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (dst_mem == MPRG_HOST) MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+        }
     }
     MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
 }
@@ -468,7 +509,14 @@ int mprg_comm_init(mprg_ctx *ctx, const void *id128) {
 
 int mprg_gather(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void *slab_dev, int root, void *full_dev) {
     MPRG_ENTER(ctx)
-    gather_slabs(ctx, stagger, nlev, dtype, slab_dev, root, full_dev);
+    gather_slabs(ctx, 1, &stagger, &nlev, dtype, &slab_dev, root, &full_dev);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_gather_v(mprg_ctx *ctx, int32_t nfields, const int *stagger, const int32_t *nlev, int dtype,
+                  const void *const *slab_dev, int root, void *const *full_dev) {
+    MPRG_ENTER(ctx)
+    gather_slabs(ctx, nfields, stagger, nlev, dtype, slab_dev, root, full_dev);
     MPRG_LEAVE(ctx)
 }
 

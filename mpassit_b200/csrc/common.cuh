@@ -164,6 +164,8 @@ struct mprg_ctx {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t store_stream = nullptr;  // weight generation runs here, beside the copy-bound apply pipeline
+    bool async = false;                   // host-buffer applies return once enqueued (mprg_set_async)
     std::string err;
     mprg::Mesh mesh;
     mprg::Target target[5];           // + MPRG_CENTER_HALO (derived from CENTER)
@@ -174,9 +176,14 @@ struct mprg_ctx {
     int64_t launches = 0;
     double last_ms = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // staging for host-buffer applies
-    mprg::DevBuf<unsigned char> stageIn[2], stageOut[2];
-    cudaEvent_t evIn[2] = {nullptr, nullptr}, evK[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    // staging for host-buffer applies: a ring of slots that persists across calls, so consecutive
+    // (asynchronous) applies keep H2D, kernels and D2H of different batches in flight together
+    static constexpr int kSlots = 4;
+    mprg::DevBuf<unsigned char> stageIn[kSlots], stageOut[kSlots];
+    cudaEvent_t evIn[kSlots] = {}, evK[kSlots] = {}, evOut[kSlots] = {};
+    bool slotUsed[kSlots] = {};
+    unsigned slotCursor = 0;
+    cudaEvent_t evDl = nullptr;           // mprg_download ordering
     mprg::DevBuf<unsigned char> scratch;  // apply descriptors (device side)
     mprg::PinnedBuf descHost;             // apply descriptors (pinned ring, host side)
     size_t descCursor = 0;
@@ -240,7 +247,7 @@ void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, i
 void comm_destroy(mprg_ctx *ctx);
 void comm_id(mprg_ctx *ctx, void *id128);
 void comm_init(mprg_ctx *ctx, const void *id128);
-void gather_slabs(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void *slab_dev, int root,
-                  void *full_dev);
+void gather_slabs(mprg_ctx *ctx, int nfields, const int *stagger, const int32_t *nlev, int dtype,
+                  const void *const *slab_dev, int root, void *const *full_dev);
 
 }  // namespace mprg

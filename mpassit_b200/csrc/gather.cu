@@ -66,43 +66,54 @@ void comm_init(mprg_ctx *ctx, const void *id128) {
     check(ctx, sym<fn_init>(ctx, "ncclCommInitRank")(&ctx->nccl, ctx->nranks, id, ctx->rank), "ncclCommInitRank");
 }
 
-void gather_slabs(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void *slab_dev, int root,
-                  void *full_dev) {
-    if (stagger < 0 || stagger > 3 || !ctx->target[stagger].set) fail(83, "mprg_gather: stagger %d not set", stagger);
+void gather_slabs(mprg_ctx *ctx, int nfields, const int *stagger, const int32_t *nlev, int dtype,
+                  const void *const *slab_dev, int root, void *const *full_dev) {
     if (root < 0 || root >= ctx->nranks) fail(86, "mprg_gather: bad root %d", root);
-    if (nlev <= 0) return;
-    const Target &tg = ctx->target[stagger];
+    if (nfields <= 0) return;
+    if (!stagger || !nlev || !slab_dev) fail(1, "mprg_gather: null argument");
     const size_t esz = dtype == MPRG_F32 ? 4 : 8;
-    const int64_t nFull = (int64_t)tg.ni * tg.nj;
-    const int64_t nMine = tg.nSlab();
-    if (ctx->rank == root && !full_dev) fail(1, "mprg_gather: root needs a destination buffer");
-    if (nMine > 0 && !slab_dev) fail(1, "mprg_gather: null slab");
+    for (int f = 0; f < nfields; ++f) {
+        if (stagger[f] < 0 || stagger[f] > 3 || !ctx->target[stagger[f]].set)
+            fail(83, "mprg_gather: stagger %d not set", stagger[f]);
+        const Target &tg = ctx->target[stagger[f]];
+        if (ctx->rank == root && nlev[f] > 0 && (!full_dev || !full_dev[f])) fail(1, "mprg_gather: root needs a destination buffer");
+        if (tg.nSlab() > 0 && nlev[f] > 0 && !slab_dev[f]) fail(1, "mprg_gather: null slab");
+    }
+    if (ctx->nranks > 1 && !ctx->nccl) fail(84, "mprg_gather: communicator not initialised (call mprg_comm_init)");
 
-    if (ctx->rank == root && nMine > 0) {
-        // own slab: strided device copy (nlev runs of nMine elements)
-        MPRG_CUDA(cudaMemcpy2DAsync((unsigned char *)full_dev + (size_t)tg.slabOffset() * esz, (size_t)nFull * esz,
-                                    slab_dev, (size_t)nMine * esz, (size_t)nMine * esz, (size_t)nlev,
-                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    // own slab: strided device copy (nlev runs of nMine elements)
+    if (ctx->rank == root) {
+        for (int f = 0; f < nfields; ++f) {
+            const Target &tg = ctx->target[stagger[f]];
+            const int64_t nFull = (int64_t)tg.ni * tg.nj, nMine = tg.nSlab();
+            if (nMine > 0 && nlev[f] > 0)
+                MPRG_CUDA(cudaMemcpy2DAsync((unsigned char *)full_dev[f] + (size_t)tg.slabOffset() * esz, (size_t)nFull * esz,
+                                            slab_dev[f], (size_t)nMine * esz, (size_t)nMine * esz, (size_t)nlev[f],
+                                            cudaMemcpyDeviceToDevice, ctx->stream));
+        }
     }
     if (ctx->nranks == 1) return;
-    if (!ctx->nccl) fail(84, "mprg_gather: communicator not initialised (call mprg_comm_init)");
     fn_void gstart = sym<fn_void>(ctx, "ncclGroupStart"), gend = sym<fn_void>(ctx, "ncclGroupEnd");
     fn_send send = sym<fn_send>(ctx, "ncclSend");
     fn_recv recv = sym<fn_recv>(ctx, "ncclRecv");
     check(ctx, gstart(), "ncclGroupStart");
-    if (ctx->rank != root) {
-        for (int l = 0; l < nlev && nMine > 0; ++l)
-            check(ctx, send((const unsigned char *)slab_dev + (size_t)l * nMine * esz, (size_t)nMine * esz, kNcclInt8,
-                            root, ctx->nccl, ctx->stream), "ncclSend");
-    } else {
-        for (int p = 0; p < ctx->nranks; ++p) {
-            if (p == root) continue;
-            int32_t j0, j1;
-            para_range(tg.nj, ctx->nranks, p, &j0, &j1);
-            const int64_t ns = (int64_t)(j1 - j0) * tg.ni, off = (int64_t)j0 * tg.ni;
-            for (int l = 0; l < nlev && ns > 0; ++l)
-                check(ctx, recv((unsigned char *)full_dev + ((size_t)l * nFull + off) * esz, (size_t)ns * esz,
-                                kNcclInt8, p, ctx->nccl, ctx->stream), "ncclRecv");
+    for (int f = 0; f < nfields; ++f) {
+        const Target &tg = ctx->target[stagger[f]];
+        const int64_t nFull = (int64_t)tg.ni * tg.nj, nMine = tg.nSlab();
+        if (ctx->rank != root) {
+            for (int l = 0; l < nlev[f] && nMine > 0; ++l)
+                check(ctx, send((const unsigned char *)slab_dev[f] + (size_t)l * nMine * esz, (size_t)nMine * esz, kNcclInt8,
+                                root, ctx->nccl, ctx->stream), "ncclSend");
+        } else {
+            for (int p = 0; p < ctx->nranks; ++p) {
+                if (p == root) continue;
+                int32_t j0, j1;
+                para_range(tg.nj, ctx->nranks, p, &j0, &j1);
+                const int64_t ns = (int64_t)(j1 - j0) * tg.ni, off = (int64_t)j0 * tg.ni;
+                for (int l = 0; l < nlev[f] && ns > 0; ++l)
+                    check(ctx, recv((unsigned char *)full_dev[f] + ((size_t)l * nFull + off) * esz, (size_t)ns * esz,
+                                    kNcclInt8, p, ctx->nccl, ctx->stream), "ncclRecv");
+            }
         }
     }
     check(ctx, gend(), "ncclGroupEnd");

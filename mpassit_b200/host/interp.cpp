@@ -81,6 +81,12 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
     void *d_um = nullptr, *d_vm = nullptr;
     std::vector<mprg_route *> held;
     int rc_out = 0;
+    // Host-buffer passes run with asynchronous applies: every Store/Regrid pair below is only QUEUED
+    // (H2D, kernels and D2H of consecutive bundles overlap, and weight generation runs beside them on
+    // its own stream); interp_data as a whole stays blocking, like the reference's.
+    const int was_async = mprg_get_async(ctx);
+    const bool host_pass = io->mem == MPRG_HOST;
+    if (host_pass) mprg_set_async(ctx, 1);
     try {
         int32_t do_u = 0, do_v = 0, u10 = -1, v10 = -1;
         mpassit_classify_fields(cfg, io, &do_u, &do_v, &u10, &v10);
@@ -102,16 +108,39 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
         // stacked into ONE apply (independent fields: order of evaluation does not change any value).
         Batch diagBatch;
         const bool have_diag = cfg->interp_diag && io->n_diag > 0;
+        // 10-m winds are rotated after the bundle regrid (interp.F90:138-139).  With host buffers they are
+        // regridded into device scratch, rotated there and downloaded, so nothing waits on a round trip.
+        const bool rot10 = have_diag && u10 >= 0 && v10 >= 0 && rotate;
+        const bool rot10_dev = rot10 && host_pass;
         if (have_diag)
-            for (int i = 0; i < io->n_diag; ++i) diagBatch.add(io->diag[i].src, io->diag[i].dst, io->diag[i].nlev);
-        auto finish_diag = [&]() {
-            if (have_diag && u10 >= 0 && v10 >= 0 && rotate)  // interp.F90:138-139
+            for (int i = 0; i < io->n_diag; ++i)
+                if (!(rot10_dev && (i == u10 || i == v10)))
+                    diagBatch.add(io->diag[i].src, io->diag[i].dst, io->diag[i].nlev);
+        auto finish_diag = [&](mprg_route *rh) {
+            if (!rot10) return;
+            if (!rot10_dev) {
                 ck(ctx, mprg_rotate_winds(ctx, io->diag[u10].dst, io->diag[v10].dst, 1, ddt, mem), "rotate_winds_cgrid");
+                return;
+            }
+            int32_t j0 = 0, j1 = 0, ni = 0, nj = 0;
+            mpassit_target_dims(cfg, MPRG_CENTER, &ni, &nj);
+            ck(ctx, mprg_get_slab(ctx, MPRG_CENTER, &j0, &j1), "get_slab");
+            const size_t bytes = (size_t)(j1 - j0) * ni * (ddt == MPRG_F64 ? 8 : 4);
+            void *du = nullptr, *dv = nullptr;
+            ck(ctx, mprg_scratch(ctx, 2, bytes, &du), "scratch");
+            ck(ctx, mprg_scratch(ctx, 3, bytes, &dv), "scratch");
+            const void *s2[2] = {io->diag[u10].src, io->diag[v10].src};
+            void *d2[2] = {du, dv};
+            int32_t n2[2] = {1, 1};
+            ck(ctx, mprg_apply(ctx, rh, 2, s2, n2, sdt, mem, d2, ddt, MPRG_DEVICE), "FieldBundleRegrid");
+            ck(ctx, mprg_rotate_winds(ctx, du, dv, 1, ddt, MPRG_DEVICE), "rotate_winds_cgrid");
+            ck(ctx, mprg_download(ctx, du, io->diag[u10].dst, bytes), "download");
+            ck(ctx, mprg_download(ctx, dv, io->diag[v10].dst, bytes), "download");
         };
         if (have_diag && !cfg->interp_hist) {
             mprg_route *rh = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
             run(ctx, rh, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid");
-            finish_diag();
+            finish_diag(rh);
         }
 
         // ---------------- interp_hist_data, interp.F90:183-465 ----------------
@@ -173,6 +202,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 } else if (have_diag) {  // cannot happen with the reference's method sequence; kept for safety
                     mprg_route *rd = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
                     run(ctx, rd, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                    finish_diag(rd);
                 }
                 for (int i = 0; i < io->n_hist_2d; ++i)
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_PATCH) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
@@ -184,11 +214,11 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 for (int i = 0; i < io->n_hist_3d; ++i)
                     if (io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZ || io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZP1)
                         b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
-                if (!b.empty()) {
+                if (!b.empty() || (have_diag && m_bil == MPRG_BILINEAR)) {
                     mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
                     run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                    if (have_diag && m_bil == MPRG_BILINEAR) finish_diag(rh);
                 }
-                finish_diag();
             }
 
             // winds, interp.F90:256-328
@@ -253,6 +283,14 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
     } catch (const Fail &f) {
         if (err && errlen) std::snprintf(err, errlen, "%s", f.msg.c_str());
         rc_out = f.rc ? f.rc : 1;
+    }
+    // interp_data returns with every output in place
+    if (host_pass) {
+        if (mprg_synchronize(ctx) != 0 && rc_out == 0) {
+            if (err && errlen) std::snprintf(err, errlen, "IN interp_data: %s", mprg_last_error(ctx));
+            rc_out = 1;
+        }
+        mprg_set_async(ctx, was_async);
     }
     // interp.F90:449-464 FieldBundleRegridRelease (here: every handle taken above)
     for (mprg_route *rh : held) mprg_release(ctx, rh);

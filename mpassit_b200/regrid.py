@@ -118,6 +118,10 @@ class Regridder:
 
         self._ck(self.L.mprg_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
+    def set_async(self, on: bool) -> None:
+        """Host-buffer applies return once queued; call synchronize() before reading their outputs."""
+        self._ck(self.L.mprg_set_async(self.ctx, int(on)))
+
     def synchronize(self) -> None:
         self._ck(self.L.mprg_synchronize(self.ctx))
 
@@ -246,3 +250,14 @@ class Regridder:
     def gather(self, stagger: int, nlev: int, slab, root: int = 0, full=None) -> None:
         self._ck(self.L.mprg_gather(self.ctx, stagger, int(nlev), _dtype_code(slab), _ptr(slab), int(root),
                                     _ptr(full) if full is not None else None))
+
+    def gather_many(self, items, root: int = 0) -> None:
+        """items: [(stagger, nlev, slab, full-or-None)], one NCCL group for all of them (mprg_gather_v)."""
+        n = len(items)
+        if n == 0:
+            return
+        st = (C.c_int * n)(*[int(i[0]) for i in items])
+        nl = (C.c_int32 * n)(*[int(i[1]) for i in items])
+        sl = (C.c_void_p * n)(*[_ptr(i[2]) for i in items])
+        fu = (C.c_void_p * n)(*[(_ptr(i[3]) if i[3] is not None else None) for i in items])
+        self._ck(self.L.mprg_gather_v(self.ctx, n, st, nl, _dtype_code(items[0][2]), sl, int(root), fu))
