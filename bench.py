@@ -370,7 +370,17 @@ def main():
     if dom is not None:
         d = by_class[dom]
         ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        # DRAM bytes of the same launch class from the committed `ncu --set full` capture (None if the
+        # capture was taken on another launch shape, e.g. a different --gpus)
+        traffic = None
+        try:
+            for c in json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")))["launch_classes"]:
+                if c["kernel"] == KIND_NAMES[dom[0]] and int(c["units_per_launch"]) == int(d["units"] / d["n"]):
+                    traffic = c["dram_bytes_read"] + c["dram_bytes_write"]
+        except Exception:  # noqa: BLE001
+            pass
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": "ncu --set full, profiles/r01/apply_v4_ncu_summary.md" if traffic else None,
                     "kernel": KIND_NAMES[dom[0]], "launches": d["n"], "avg_launch_ms": d["ms"] / d["n"],
                     "alg_bytes_per_launch": d["bytes"] / d["n"], "units_per_launch": d["units"] / d["n"],
                     "share_of_step": d["ms"] / ms_total,
