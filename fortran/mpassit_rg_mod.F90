@@ -33,7 +33,7 @@ module mpassit_rg_mod
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
   public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
-  public :: mprg_set_async, mprg_get_async, mprg_download
+  public :: mprg_set_async, mprg_get_async, mprg_download, mprg_io_bytes
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
   interface
@@ -206,6 +206,11 @@ module mpassit_rg_mod
        import :: c_int, c_ptr, c_size_t
        type(c_ptr), value :: ctx, dev, host
        integer(c_size_t), value :: bytes
+     end function
+     integer(c_int) function mprg_io_bytes(ctx, h2d, d2h) bind(C, name="mprg_io_bytes")
+       import :: c_int, c_ptr, c_int64_t
+       type(c_ptr), value :: ctx
+       integer(c_int64_t), intent(out) :: h2d, d2h
      end function
      !> nfields fields in one NCCL group (the ~20 back-to-back FieldGather calls of write_to_file)
      integer(c_int) function mprg_gather_v(ctx, nfields, stagger, nlev, dtype, slab_dev, root, full_dev) &

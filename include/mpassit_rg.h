@@ -176,6 +176,9 @@ int mprg_gather_v(mprg_ctx *ctx, int32_t nfields, const int *stagger, const int3
 /* ---- instrumentation */
 /* number of engine kernels launched on this context since init */
 int64_t mprg_kernel_launches(const mprg_ctx *ctx);
+/* field bytes copied host->device / device->host by host-buffer applies and downloads since init.
+ * Host sources are halo-sharded: only the id range the rank's weights reference is uploaded. */
+int mprg_io_bytes(const mprg_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
 /* device milliseconds of the most recent store / apply (CUDA events on the
  * context's stream) */
 double mprg_last_ms(const mprg_ctx *ctx);

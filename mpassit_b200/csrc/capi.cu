@@ -201,6 +201,7 @@ int mprg_download(mprg_ctx *ctx, const void *dev, void *host, size_t bytes) {
     MPRG_CUDA(cudaEventRecord(ctx->evDl, ctx->stream));
     MPRG_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->evDl, 0));
     MPRG_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    ctx->d2hBytes += bytes;
     if (!ctx->async) MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
     MPRG_LEAVE(ctx)
 }
@@ -370,13 +371,21 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
         // before it and the D2H of the ones before that.  The slot ring persists across calls, so with
         // mprg_set_async(1) consecutive applies overlap the same way.
         const size_t budget = (size_t)768 << 20;
+        // Source halo-sharding: only the id range [srcLo, srcHi) that this rank's weights reference is
+        // uploaded (file order keeps it contiguous per field); kernels see the field through a virtual
+        // base pointer `staged - srcLo * column`.  With a row-slab decomposition and a mesh numbered with
+        // any spatial locality this is ~1/nranks of the field plus a halo; worst case it is the whole field.
+        const bool range = src_mem == MPRG_HOST && !rh->srcLevelSlowest && rh->srcHi > rh->srcLo;
+        const int64_t lo = range ? rh->srcLo : 0, hi = range ? rh->srcHi : nSrcPts;
+        constexpr size_t kPad = 512;  // slack either side of a staged field: aligned-window reads may start / end up to 15 bytes outside
+        auto in_bytes = [&](int k) { return (size_t)(hi - lo) * nlev[k] * isz; };
+        auto in_slot = [&](int k) { return (in_bytes(k) + 2 * kPad + 255) & ~(size_t)255; };
         int f = 0;
         while (f < nfields) {
             int g = f;
             size_t inB = 0, outB = 0;
             while (g < nfields) {
-                size_t a = (size_t)nSrcPts * nlev[g] * isz, b = (size_t)rh->nDst * nlev[g] * osz;
-                a = (a + 255) & ~(size_t)255; b = (b + 255) & ~(size_t)255;
+                size_t a = in_slot(g), b = ((size_t)rh->nDst * nlev[g] * osz + 255) & ~(size_t)255;
                 if (g > f && (inB + a > budget || outB + b > budget)) break;
                 inB += a; outB += b; ++g;
             }
@@ -391,16 +400,21 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
             std::vector<ApplyField> fl;
             size_t io = 0, oo = 0;
             for (int k = f; k < g; ++k) {
-                size_t a = (size_t)nSrcPts * nlev[k] * isz, b = (size_t)rh->nDst * nlev[k] * osz;
+                size_t b = (size_t)rh->nDst * nlev[k] * osz;
                 const void *s = src[k];
                 void *d = dst[k];
                 if (src_mem == MPRG_HOST) {
-                    MPRG_CUDA(cudaMemcpyAsync(ctx->stageIn[slot].p + io, src[k], a, cudaMemcpyHostToDevice, ctx->h2d_stream));
-                    s = ctx->stageIn[slot].p + io;
+                    const size_t col = (size_t)nlev[k] * isz, skip = (size_t)lo * col;
+                    // keep the 16-byte phase of the original layout so aligned fields stay aligned
+                    unsigned char *data = ctx->stageIn[slot].p + io + kPad + (skip & 15);
+                    MPRG_CUDA(cudaMemcpyAsync(data, (const unsigned char *)src[k] + skip, in_bytes(k), cudaMemcpyHostToDevice,
+                                              ctx->h2d_stream));
+                    ctx->h2dBytes += in_bytes(k);
+                    s = data - skip;
                 }
                 if (dst_mem == MPRG_HOST) d = ctx->stageOut[slot].p + oo;
                 fl.push_back(ApplyField{s, d, nlev[k], epi_op ? epi_op[k] : 0, epi_arg ? epi_arg[k] : 0.0});
-                io += (a + 255) & ~(size_t)255;
+                io += in_slot(k);
                 oo += (b + 255) & ~(size_t)255;
             }
             if (src_mem == MPRG_HOST) {
@@ -415,6 +429,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                 for (int k = f; k < g; ++k) {
                     size_t b = (size_t)rh->nDst * nlev[k] * osz;
                     MPRG_CUDA(cudaMemcpyAsync(dst[k], ctx->stageOut[slot].p + oo, b, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    ctx->d2hBytes += b;
                     oo += (b + 255) & ~(size_t)255;
                 }
             }
@@ -553,6 +568,13 @@ int mprg_profile_read(mprg_ctx *ctx, int32_t max, int32_t *kind, double *ms, dou
 int64_t mprg_route_src_referenced(const mprg_route *rh) { return rh ? rh->nSrcRef : 0; }
 
 int64_t mprg_kernel_launches(const mprg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int mprg_io_bytes(const mprg_ctx *ctx, uint64_t *h2d, uint64_t *d2h) {
+    if (!ctx) return 1;
+    if (h2d) *h2d = ctx->h2dBytes;
+    if (d2h) *d2h = ctx->d2hBytes;
+    return 0;
+}
 
 double mprg_last_ms(const mprg_ctx *ctx) {
     if (!ctx) return 0.0;

@@ -142,6 +142,7 @@ struct mprg_route {
     int method = 0, src_loc = 0, dst_stagger = 0;
     int64_t nDst = 0, nnz = 0, nUnmapped = 0, nSrc = 0;
     int64_t nSrcRef = 0;       // distinct source entities referenced by the weights
+    int64_t srcLo = 0, srcHi = 0;  // [srcLo, srcHi): smallest id range containing all of them
     int32_t tileEntriesMax = 0, tileUniqMax = 0;  // per 32-target tile: CSR entries / distinct columns
     int32_t dstNi = 0;         // destination row length (tiles of the apply kernel never straddle rows)
     // tile schedule for the pipelined apply kernel (apply_pipe.cuh)
@@ -182,6 +183,7 @@ struct mprg_ctx {
     mprg::DevBuf<unsigned char> stageIn[kSlots], stageOut[kSlots];
     cudaEvent_t evIn[kSlots] = {}, evK[kSlots] = {}, evOut[kSlots] = {};
     bool slotUsed[kSlots] = {};
+    unsigned long long h2dBytes = 0, d2hBytes = 0;  // field bytes moved by host-buffer applies / downloads since init
     unsigned slotCursor = 0;
     cudaEvent_t evDl = nullptr;           // mprg_download ordering
     mprg::DevBuf<unsigned char> scratch;  // apply descriptors (device side)

@@ -136,11 +136,17 @@ __global__ void k_mark_cols(int64_t nnz, const int32_t *__restrict__ col, unsign
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) mark[col[i]] = 1;
 }
+// out[0] += referenced sources; out[1] = lowest, out[2] = highest referenced source id
 __global__ void k_count_marks(int64_t n, const unsigned char *__restrict__ mark, unsigned long long *out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned v = (i < n && mark[i]) ? 1u : 0u;
     unsigned b = __ballot_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
+    if ((threadIdx.x & 31) == 0 && b) {
+        atomicAdd(out, (unsigned long long)__popc(b));
+        const int64_t w0 = i;  // lane 0 of the warp
+        atomicMin(out + 1, (unsigned long long)(w0 + __ffs(b) - 1));
+        atomicMax(out + 2, (unsigned long long)(w0 + 31 - __clz(b)));
+    }
 }
 
 __global__ void k_w32(int64_t nnz, const double *__restrict__ w, float *__restrict__ w32) {
@@ -164,8 +170,9 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
         k_w32<<<(unsigned)((r->nnz + 255) / 256), 256, 0, ctx->stream>>>(r->nnz, r->w.p, r->w32.p);
         ctx->launches++;
     }
-    DevBuf<unsigned long long> nref(1);
-    MPRG_CUDA(cudaMemsetAsync(nref.p, 0, sizeof(unsigned long long), ctx->stream));
+    DevBuf<unsigned long long> nref(3);
+    const unsigned long long nref0[3] = {0ULL, ~0ULL, 0ULL};
+    MPRG_CUDA(cudaMemcpyAsync(nref.p, nref0, sizeof nref0, cudaMemcpyHostToDevice, ctx->stream));
     DevBuf<unsigned char> mark;
     if (r->nnz > 0 && r->nSrc > 0) {
         mark.alloc(r->nSrc);
@@ -174,14 +181,17 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
         k_count_marks<<<(unsigned)((r->nSrc + 255) / 256), 256, 0, ctx->stream>>>(r->nSrc, mark.p, nref.p);
         ctx->launches += 2;
     }
-    unsigned long long hun = 0, href = 0;
-    MPRG_CUDA(cudaMemcpyAsync(&href, nref.p, sizeof href, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long hun = 0, href[3] = {0, 0, 0};
+    MPRG_CUDA(cudaMemcpyAsync(href, nref.p, sizeof href, cudaMemcpyDeviceToHost, ctx->stream));
     int32_t hmm[2] = {0, 0};
     MPRG_CUDA(cudaMemcpyAsync(&hun, un.p, sizeof hun, cudaMemcpyDeviceToHost, ctx->stream));
     MPRG_CUDA(cudaMemcpyAsync(hmm, mm.p, sizeof hmm, cudaMemcpyDeviceToHost, ctx->stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     r->nUnmapped = (int64_t)hun;
-    r->nSrcRef = (int64_t)href;
+    r->nSrcRef = (int64_t)href[0];
+    // contiguous id range that holds every referenced source: host-buffer applies upload only this range
+    r->srcLo = href[0] ? (int64_t)href[1] : 0;
+    r->srcHi = href[0] ? (int64_t)href[2] + 1 : 0;
     if (!r->srcLevelSlowest) route_tile_stats(ctx, r);
     r->maxRow = hmm[0];
     r->uniform = (r->nnz > 0 && hmm[0] == hmm[1]);

@@ -129,6 +129,12 @@ class Regridder:
     def kernel_launches(self) -> int:
         return int(self.L.mprg_kernel_launches(self.ctx))
 
+    def io_bytes(self) -> tuple[int, int]:
+        """(host->device, device->host) field bytes moved by host-buffer applies since init."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.mprg_io_bytes(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     @property
     def last_ms(self) -> float:
         return float(self.L.mprg_last_ms(self.ctx))

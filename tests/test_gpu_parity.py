@@ -202,3 +202,30 @@ def test_errors_are_reported_not_fatal(rg):
         rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CORNER if l.CORNER not in rg.shape else 7)
     with pytest.raises(MprgError):
         rg.import_csr(10, np.array([0, 2], np.int32), np.array([1, 11], np.int32), np.ones(2))
+
+
+@pytest.mark.parametrize("nlev", [1, 4, 60, 61])
+def test_host_sources_upload_only_the_referenced_id_range(rg, orc, nlev):
+    """Source halo-sharding: a host-buffer apply copies just the cell-id range [lo, hi) that the route's
+    weights reference; rows outside it are never read (here: NaN) and the byte counter says so."""
+    rng = np.random.default_rng(9)
+    nSrc, nDst, lo, hi = 6000, 2500, 1201, 3456
+    lens = rng.integers(0, 4, nDst)
+    rp = np.zeros(nDst + 1, np.int32)
+    np.cumsum(lens, out=rp[1:])
+    col = rng.integers(lo, hi, rp[-1]).astype(np.int32)
+    col[:2] = (lo, hi - 1)
+    w = rng.random(rp[-1])
+    r = rg.import_csr(nSrc, rp, col, w)
+    src = rng.standard_normal((nSrc, nlev)).astype(np.float32)
+    want = orc.apply(rp, col, w, src, np.float32)
+    src[:lo] = np.nan
+    src[hi:] = np.nan
+    got = np.empty((nlev, nDst), np.float32)
+    b0 = rg.io_bytes()
+    rg.apply(r, [src if nlev > 1 else src.reshape(-1)], [got], nlev=[nlev])
+    b1 = rg.io_bytes()
+    assert not np.isnan(got).any()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+    assert b1[0] - b0[0] == (hi - lo) * nlev * 4 and b1[1] - b0[1] == nDst * nlev * 4
+    r.release()
