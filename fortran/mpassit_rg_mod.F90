@@ -26,7 +26,8 @@ module mpassit_rg_mod
                                         MPRG_CENTER_HALO = 4
   integer(c_int), parameter, public :: MPRG_F32 = 0, MPRG_F64 = 1
   integer(c_int), parameter, public :: MPRG_HOST = 0, MPRG_DEVICE = 1
-  integer(c_int), parameter, public :: MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2
+  integer(c_int), parameter, public :: MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2, &
+                                        MPRG_EPI_ROT_U = 3, MPRG_EPI_ROT_V = 4
 
   public :: mprg_init, mprg_finalize, mprg_last_error, mprg_error_message
   public :: mprg_set_mesh, mprg_set_target, mprg_get_slab

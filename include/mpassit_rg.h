@@ -51,7 +51,12 @@ enum { MPRG_F32 = 0, MPRG_F64 = 1 };
 enum { MPRG_HOST = 0, MPRG_DEVICE = 1 };
 /* per-field fused epilogues (WRF-compat post-ops the reference runs serially on
  * PET 0, write_data.F90:1339-1345 and :1406-1425) */
-enum { MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2 };
+enum { MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2,
+       /* fields f (ROT_U: zonal) and f+1 (ROT_V: meridional), same level count, on CENTER or CENTER_HALO
+        * rows: rotate_winds_cgrid (interp.F90:689-749, v' from the already rotated u') is applied to the
+        * pair as it is stored, with the angles given to mprg_set_rotation -- the separate rotation pass
+        * over both fields disappears.  Bit-identical to mprg_apply + mprg_rotate_winds_on. */
+       MPRG_EPI_ROT_U = 3, MPRG_EPI_ROT_V = 4 };
 
 /* ---- lifetime: replaces ESMF_Initialize / ESMF_VMGet / ESMF_finalize
  *      (mpassit.F90:84-94,140).  `device` is the CUDA ordinal; rank/nranks give

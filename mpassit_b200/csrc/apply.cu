@@ -291,6 +291,8 @@ k_apply_flat(ApplyArgs<TACC> a) {
 // ---------------------------------------------------------------------------
 // source is a level-slowest grid field [lev][srcPlane] (centre -> edge stagger)
 // ---------------------------------------------------------------------------
+constexpr int kPlaneBatch = 4;  // levels whose gathers are all issued before the first FMA (memory-level parallelism)
+
 template <typename TIN, typename TOUT, typename TACC>
 __global__ void __launch_bounds__(256)
 k_apply_planes(ApplyArgs<TACC> a) {
@@ -302,13 +304,35 @@ k_apply_planes(ApplyArgs<TACC> a) {
 #pragma unroll
     for (int k = 0; k < kFlatRow; ++k) {
         const bool h = b + k < e;
-        c[k] = h ? __ldg(a.col + b + k) : 0;
+        c[k] = h ? __ldg(a.col + b + k) : 0;   // absent entries: weight 0 on a valid address (index 0)
         w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
     }
     const FieldDev fd = a.fields[blockIdx.y];
     const TIN *__restrict__ src = (const TIN *)fd.src;
     TOUT *__restrict__ dst = (TOUT *)fd.dst;
-    for (int lev = 0; lev < fd.nlev; ++lev) {
+    const bool shortrow = e - b <= kFlatRow;
+    int lev = 0;
+    if (shortrow && e > b) {
+        // rows of <= 4 entries (the stagger matrices): kPlaneBatch levels x 4 gathers in flight per thread
+        for (; lev + kPlaneBatch <= fd.nlev; lev += kPlaneBatch) {
+            TIN x[kPlaneBatch][kFlatRow];
+#pragma unroll
+            for (int q = 0; q < kPlaneBatch; ++q) {
+                const TIN *pl = src + (size_t)(lev + q) * a.srcPlane;
+#pragma unroll
+                for (int k = 0; k < kFlatRow; ++k) x[q][k] = (b + k < e) ? __ldg(pl + c[k]) : (TIN)0;
+            }
+#pragma unroll
+            for (int q = 0; q < kPlaneBatch; ++q) {
+                TACC acc = 0;
+#pragma unroll
+                for (int k = 0; k < kFlatRow; ++k)
+                    if (b + k < e) acc += w[k] * (TACC)x[q][k];
+                st_stream(dst + (size_t)(lev + q) * a.nDst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+            }
+        }
+    }
+    for (; lev < fd.nlev; ++lev) {
         const TIN *pl = src + (size_t)lev * a.srcPlane;
         TACC acc = 0;
 #pragma unroll
@@ -401,7 +425,13 @@ static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, si
 }
 
 template <typename TIN, typename TOUT, typename TACC, int STAGES>
-static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles, bool allvec, int minb) {
+static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles, bool allvec, int minb,
+                          bool rot) {
+    if (rot) {  // fused wind rotation: 2 stages, 64 registers (it holds the zonal results and four fp64 angles)
+        if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 4, true>, pa, smemBytes, tiles);
+        else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 4, true>, pa, smemBytes, tiles);
+        return;
+    }
     if (allvec && minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 5>, pa, smemBytes, tiles);
     else if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 4>, pa, smemBytes, tiles);
     else if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 5>, pa, smemBytes, tiles);
@@ -409,6 +439,7 @@ static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBy
 }
 
 // returns false if this route / field set does not fit the pipelined kernel
+// fields flagged MPRG_EPI_ROT_U / ROT_V are wind pairs whose rotation is fused into the store
 template <typename TIN, typename TOUT, typename TACC>
 static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields) {
     if (pipe_disabled() || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
@@ -432,15 +463,30 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     int minb = (fixed + (size_t)stages * stage + 1024) * 5 <= smMax ? 5 : 4;
     if (const char *e = getenv("MPASSIT_GPU_PIPE_MINB")) minb = atoi(e) >= 5 ? 5 : 4;
     std::vector<UnitDev> units;
-    for (auto &f : fields) {
-        for (int L0 = 0; L0 < f.nlev; L0 += kPipeLev) {
-            UnitDev u;
-            u.src = f.src; u.dst = f.dst; u.srcBytes = (size_t)r->nSrc * f.nlev * sizeof(TIN);
-            u.nlev = f.nlev; u.L0 = L0; u.Ln = std::min(kPipeLev, f.nlev - L0);
-            const bool aligned = ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0;
-            u.epi_op = (f.epi_op & 0xff) | (aligned ? kUnitAligned : 0);
-            u.epi_arg = f.epi_arg;
-            units.push_back(u);
+    auto unit_of = [&](const FieldDev &f, int L0) {
+        UnitDev u;
+        u.src = f.src; u.dst = f.dst; u.srcBytes = (size_t)r->nSrc * f.nlev * sizeof(TIN);
+        u.nlev = f.nlev; u.L0 = L0; u.Ln = std::min(kPipeLev, f.nlev - L0);
+        const bool aligned = ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0;
+        u.epi_op = (f.epi_op & 0xff) | (aligned ? kUnitAligned : 0);
+        u.epi_arg = f.epi_arg;
+        return u;
+    };
+    // a wind pair (ROT_U field followed by its ROT_V field) contributes alternating zonal / meridional chunks
+    bool rot = false;
+    for (size_t f = 0; f < fields.size(); ++f) {
+        if ((fields[f].epi_op & 0xff) == MPRG_EPI_ROT_U && f + 1 < fields.size()) {
+            rot = true;
+            for (int L0 = 0; L0 < fields[f].nlev; L0 += kPipeLev) {
+                UnitDev uu = unit_of(fields[f], L0), uv = unit_of(fields[f + 1], L0);
+                uu.epi_op = (uu.epi_op & kUnitAligned) | kUnitRotU;
+                uv.epi_op = (uv.epi_op & kUnitAligned) | kUnitRotV;
+                units.push_back(uu);
+                units.push_back(uv);
+            }
+            ++f;
+        } else {
+            for (int L0 = 0; L0 < fields[f].nlev; L0 += kPipeLev) units.push_back(unit_of(fields[f], L0));
         }
     }
     PipeArgs<TACC> pa;
@@ -451,17 +497,28 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     pa.maxU = r->tileUniqMax;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
+    pa.cosa = pa.sina = nullptr;
+    if (rot) {  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
+        const Target &tg = ctx->target[r->dst_stagger];
+        pa.cosa = ctx->cosa.p + tg.slabOffset();
+        pa.sina = ctx->sina.p + tg.slabOffset();
+    }
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
     const size_t smemBytes = fixed + (size_t)stages * stage;
-    for (size_t u0 = 0; u0 < units.size(); u0 += kPipeMaxUnits) {
-        const size_t nu = std::min<size_t>(kPipeMaxUnits, units.size() - u0);
+    for (size_t u0 = 0; u0 < units.size();) {
+        size_t nu = std::min<size_t>(kPipeMaxUnits, units.size() - u0);
+        if (u0 + nu < units.size() && (units[u0 + nu - 1].epi_op & kUnitRotU)) --nu;  // keep a wind pair in one launch
         pa.units = (const UnitDev *)push_desc(ctx, units.data() + u0, nu * sizeof(UnitDev));
         pa.nunits = (int)nu;
-        bool allvec = true;
-        for (size_t k = 0; k < nu; ++k) allvec = allvec && (units[u0 + k].epi_op & kUnitAligned);
-        if (stages == 4) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, smemBytes, tiles, allvec, minb);
-        else if (stages == 3) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, smemBytes, tiles, allvec, minb);
-        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, smemBytes, tiles, allvec, minb);
+        bool allvec = true, anyrot = false;
+        for (size_t k = 0; k < nu; ++k) {
+            allvec = allvec && (units[u0 + k].epi_op & kUnitAligned);
+            anyrot = anyrot || (units[u0 + k].epi_op & (kUnitRotU | kUnitRotV));
+        }
+        if (stages == 4 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, smemBytes, tiles, allvec, minb, false);
+        else if (stages == 3 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, smemBytes, tiles, allvec, minb, false);
+        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, fixed + 2 * stage, tiles, allvec, minb, anyrot);
+        u0 += nu;
     }
     MPRG_CUDA(cudaGetLastError());
     return true;
@@ -501,12 +558,31 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// returns false when wind pairs (fused rotation) are present but the pipelined kernel could not take them
 template <typename TIN, typename TOUT, typename TACC>
-static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols_vec,
+static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols_vec,
                        const std::vector<FieldDev> &cols_sca, const std::vector<FieldDev> &flat,
-                       const std::vector<FieldDev> &planes) {
+                       const std::vector<FieldDev> &planes, const std::vector<FieldDev> &rotp) {
+    bool rot_ok = true;
+    auto has_rot = [](const std::vector<FieldDev> &v) {
+        for (auto &f : v) if (f.epi_op == MPRG_EPI_ROT_U) return true;
+        return false;
+    };
+    // wind pairs go in a launch of their own: the rotating variant costs registers (4 CTAs/SM instead of
+    // 5), which the other fields of the apply should not pay
+    if (!rotp.empty() && r->nDst > 0) {
+        double k = 0;
+        bool vec = true;
+        for (auto &f : rotp) { k += f.nlev; vec = vec && ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0; }
+        ProfScope ps(ctx, vec ? 0 : 1, alg_bytes(r, k, sizeof(TIN), sizeof(TOUT), sizeof(TACC)), k * r->nDst);
+        rot_ok = launch_pipe<TIN, TOUT, TACC>(ctx, r, rotp);
+        if (!rot_ok) {
+            if (ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+            return false;
+        }
+    }
     const size_t total = cols_vec.size() + cols_sca.size() + flat.size() + planes.size();
-    if (total == 0 || r->nDst == 0) return;
+    if (total == 0 || r->nDst == 0) return rot_ok;
     std::vector<FieldDev> all;
     all.reserve(total);
     all.insert(all.end(), cols_vec.begin(), cols_vec.end());
@@ -531,11 +607,13 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
             ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
             piped_vec = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_vec);
             if (!piped_vec && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+            if (!piped_vec && has_rot(cols_vec)) return false;
         }
         if (!cols_sca.empty()) {
             ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
             piped_sca = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_sca);
             if (!piped_sca && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
+            if (!piped_sca && has_rot(cols_sca)) return false;
         }
     }
     if (!cols_vec.empty() && !piped_vec) {
@@ -569,52 +647,98 @@ static void launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         ctx->launches++;
     }
     MPRG_CUDA(cudaGetLastError());
+    return rot_ok;
 }
 
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
                   int dst_dtype) {
-    std::vector<FieldDev> cols_vec, cols_sca, flat, planes;
+    std::vector<FieldDev> cols_vec, cols_sca, flat, planes, rotp;
+    std::vector<std::pair<void *, void *>> pairs;  // every (u, v) destination pair with fused rotation requested
+    std::vector<int32_t> pair_nlev;
+    bool late_rot = false;                          // some pair is too short for the column kernel: rotate afterwards
     const size_t in_sz = src_dtype == MPRG_F32 ? 4 : 8;
+    auto vec_ok = [&](const FieldDev &d) { return (d.nlev * in_sz) % 16 == 0 && ((uintptr_t)d.src % 16) == 0; };
     for (int f = 0; f < nfields; ++f) {
         if (fields[f].nlev <= 0) fail(31, "mprg_apply: field %d has nlev %d", f, fields[f].nlev);
         if (!fields[f].src || !fields[f].dst) fail(32, "mprg_apply: field %d has a null buffer", f);
         FieldDev d{fields[f].src, fields[f].dst, fields[f].nlev, fields[f].epi_op, fields[f].epi_arg};
+        if (d.epi_op == MPRG_EPI_ROT_V) fail(35, "mprg_apply: MPRG_EPI_ROT_V field %d has no MPRG_EPI_ROT_U before it", f);
+        if (d.epi_op == MPRG_EPI_ROT_U) {
+            if (f + 1 >= nfields || fields[f + 1].epi_op != MPRG_EPI_ROT_V || fields[f + 1].nlev != d.nlev)
+                fail(35, "mprg_apply: MPRG_EPI_ROT_U field %d needs a following MPRG_EPI_ROT_V field of the same level count", f);
+            if (!fields[f + 1].src || !fields[f + 1].dst) fail(32, "mprg_apply: field %d has a null buffer", f + 1);
+            if (r->dst_stagger != MPRG_CENTER && r->dst_stagger != MPRG_CENTER_HALO)
+                fail(36, "mprg_apply: wind rotation is defined on CENTER rows");
+            if (!ctx->haveRot) fail(41, "mprg_apply: mprg_set_rotation was not called");
+            if (r->srcLevelSlowest) fail(37, "mprg_apply: wind rotation needs a mesh source");
+            FieldDev v{fields[f + 1].src, fields[f + 1].dst, fields[f + 1].nlev, fields[f + 1].epi_op, fields[f + 1].epi_arg};
+            pairs.emplace_back(d.dst, v.dst);
+            pair_nlev.push_back(d.nlev);
+            if (d.nlev <= kShortLev) {  // flat kernel, rotated in a second (tiny) pass
+                d.epi_op = v.epi_op = MPRG_EPI_NONE;
+                flat.push_back(d); flat.push_back(v);
+                late_rot = true;
+            } else {
+                rotp.push_back(d); rotp.push_back(v);  // adjacent: the unit builder interleaves their chunks
+            }
+            ++f;
+            continue;
+        }
         if (r->srcLevelSlowest) planes.push_back(d);
         else if (d.nlev <= kShortLev) flat.push_back(d);
-        else if ((d.nlev * in_sz) % 16 == 0 && ((uintptr_t)d.src % 16) == 0) cols_vec.push_back(d);
+        else if (vec_ok(d)) cols_vec.push_back(d);
         else cols_sca.push_back(d);
     }
-    const bool f32acc = acc_fp32_requested() && src_dtype == MPRG_F32 && dst_dtype == MPRG_F32;
-    if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F32) {
-        if (f32acc) launch_all<float, float, float>(ctx, r, cols_vec, cols_sca, flat, planes);
-        else launch_all<float, float, double>(ctx, r, cols_vec, cols_sca, flat, planes);
-    } else if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F64) {
-        launch_all<float, double, double>(ctx, r, cols_vec, cols_sca, flat, planes);
-    } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F32) {
-        launch_all<double, float, double>(ctx, r, cols_vec, cols_sca, flat, planes);
-    } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F64) {
-        launch_all<double, double, double>(ctx, r, cols_vec, cols_sca, flat, planes);
-    } else {
+    auto run = [&]() {
+        if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F32) {
+            return acc_fp32_requested() ? launch_all<float, float, float>(ctx, r, cols_vec, cols_sca, flat, planes, rotp)
+                                        : launch_all<float, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+        } else if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F64) {
+            return launch_all<float, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+        } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F32) {
+            return launch_all<double, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+        } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F64) {
+            return launch_all<double, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+        }
         fail(33, "mprg_apply: bad dtype %d/%d", src_dtype, dst_dtype);
+    };
+    bool all_late = false;
+    if (!run()) {
+        // the route does not fit the pipelined kernel: regrid the wind pairs like any field (register-gather
+        // kernels), then rotate them in a second pass
+        for (auto d : rotp) {
+            d.epi_op = MPRG_EPI_NONE;
+            (vec_ok(d) ? cols_vec : cols_sca).push_back(d);
+        }
+        rotp.clear();
+        run();
+        all_late = true;
     }
+    if (late_rot || all_late)
+        for (size_t p = 0; p < pairs.size(); ++p)
+            if (all_late || pair_nlev[p] <= kShortLev)
+                rotate_device(ctx, r->dst_stagger, pairs[p].first, pairs[p].second, pair_nlev[p], dst_dtype);
 }
 
 // ---------------------------------------------------------------------------
 // rotate_winds_cgrid, interp.F90:689-749 (v' uses the already rotated u')
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TR>
 __global__ void k_rotate(T *__restrict__ u, T *__restrict__ v, const double *__restrict__ cosa,
                          const double *__restrict__ sina, int64_t n, int32_t nlev) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double ca = cosa[i], sa = sina[i];
     const double tana = sa / ca;
-    const double den = ca + sa * tana;
+    // u' = (u + v tana) / (cosa + sina tana); v' = (v - u' sina) / cosa: the divisors are per-point
+    // constants, applied as reciprocals; TR = the arithmetic type (RotMath, apply_pipe.cuh), the same
+    // expressions as the rotation fused into k_apply_pipe so both give identical bits
+    const TR rsa = (TR)sa, rtana = (TR)tana, rcai = (TR)(1.0 / ca), rdeni = (TR)(1.0 / (ca + sa * tana));
     for (int l = blockIdx.y; l < nlev; l += gridDim.y) {
         const size_t o = (size_t)l * n + i;
-        double uu = (double)u[o], vv = (double)v[o];
-        uu = (uu + vv * tana) / den;
-        vv = (vv - uu * sa) / ca;
+        TR uu = (TR)u[o], vv = (TR)v[o];
+        uu = (uu + vv * rtana) * rdeni;
+        vv = (vv - uu * rsa) * rcai;
         u[o] = (T)uu;
         v[o] = (T)vv;
     }
@@ -627,8 +751,12 @@ void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, i
     if (n == 0 || nlev <= 0) return;
     const double *cosa = ctx->cosa.p + tg.slabOffset(), *sina = ctx->sina.p + tg.slabOffset();
     dim3 g((unsigned)((n + 255) / 256), (unsigned)min(nlev, 4));  // >= 15 levels per thread: tana, den once per point
-    if (dtype == MPRG_F32) k_rotate<float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, cosa, sina, n, nlev);
-    else k_rotate<double><<<g, 256, 0, ctx->stream>>>((double *)u, (double *)v, cosa, sina, n, nlev);
+    if (dtype == MPRG_F32 && acc_fp32_requested())
+        k_rotate<float, float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, cosa, sina, n, nlev);
+    else if (dtype == MPRG_F32)
+        k_rotate<float, double><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, cosa, sina, n, nlev);
+    else
+        k_rotate<double, double><<<g, 256, 0, ctx->stream>>>((double *)u, (double *)v, cosa, sina, n, nlev);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
 }

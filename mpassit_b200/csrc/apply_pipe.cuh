@@ -39,6 +39,7 @@ struct UnitDev {
     double epi_arg;
 };
 constexpr int kUnitAligned = 0x100;
+constexpr int kUnitRotU = 0x200, kUnitRotV = 0x400;  // wind pair: this unit is the zonal / meridional chunk
 
 template <typename TW>
 struct PipeArgs {
@@ -56,6 +57,8 @@ struct PipeArgs {
     const UnitDev *units;
     int32_t nunits;
     int32_t maxU;       // slot capacity of one stage (>= max unique columns of any tile)
+    // ROT launches only: rotation angles of this rank's destination rows (rotate_winds_cgrid fused into the store)
+    const double *cosa, *sina;
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -93,6 +96,13 @@ __device__ __forceinline__ TACC pipe_epi(TACC v, int op, TACC arg) {
     return op == MPRG_EPI_ADD ? v + arg : (op == MPRG_EPI_MUL ? v * arg : v);
 }
 
+// Arithmetic type of the fused / stand-alone wind rotation: the reference rotates R8 fields in R8
+// (interp.F90:737-748); an all-fp32 apply (fp32 output, fp32 accumulation) rotates in fp32 -- <= 3e-7
+// relative, inside the 1e-5 contract -- because B200's fp64 / conversion throughput would otherwise make
+// the rotation cost as much as regridding the two fields.  MPASSIT_GPU_ACC=f64 selects fp64 throughout.
+template <typename TOUT, typename TACC> struct RotMath { using type = double; };
+template <> struct RotMath<float, float> { using type = float; };
+
 // 4 consecutive levels of one staged column, addressed in the shared window (explicit ld.shared:
 // no generic->shared conversion in the inner loop)
 template <typename TIN, typename TACC>
@@ -119,7 +129,11 @@ __device__ __forceinline__ TIN lds1(unsigned saddr) {
 // ALLVEC: every unit of the launch has 16-byte-aligned columns (compile-time specialisation
 // without the aligned-window arithmetic and without the 4-byte load path).
 // MINB: resident CTAs per SM the kernel is compiled for (register cap 64 at 4, 48 at 5).
-template <typename TIN, typename TOUT, typename TACC, int STAGES, bool ALLVEC, int MINB>
+// ROT: some units are (zonal wind, meridional wind) chunk pairs (kUnitRotU then kUnitRotV, same levels);
+//      the thread that reduces u(t, lev) also reduces v(t, lev) one unit later, so rotate_winds_cgrid
+//      (interp.F90:737-748) runs in registers between the two and both are stored rotated -- no separate
+//      pass over the fields.
+template <typename TIN, typename TOUT, typename TACC, int STAGES, bool ALLVEC, int MINB, bool ROT = false>
 __global__ void __launch_bounds__(kPipeThreads, MINB)
 k_apply_pipe(PipeArgs<TACC> a) {
     constexpr int SLOTB = pipe_slot_bytes<TIN>();
@@ -177,6 +191,18 @@ k_apply_pipe(PipeArgs<TACC> a) {
         rw[j] = h ? s_w[rbeg + j] : (TACC)0;
         ro[j] = h ? s_off[rbeg + j] : 0;
     }
+    // wind rotation: angles of this lane's target (same operation order as k_rotate)
+    // (fp32 arithmetic when the whole apply is fp32 -- RotMath -- : the fp64 pipe would otherwise bound the launch)
+    using TR = typename RotMath<TOUT, TACC>::type;
+    TR rsa = 0, rtana = 0, rcai = 1, rdeni = 1;
+    if (ROT && live) {
+        const double ca = __ldg(a.cosa + t0 + lane), sa = __ldg(a.sina + t0 + lane);
+        const double tana = sa / ca;
+        rsa = (TR)sa; rtana = (TR)tana;
+        rcai = (TR)(1.0 / ca);
+        rdeni = (TR)(1.0 / (ca + sa * tana));
+    }
+    TOUT hold[kPipeLev / 4 / kPipeWarps][4];  // ROT: the zonal unit's results, held until the meridional unit
     const bool fast = __all_sync(0xffffffffu, rlen <= 3);
     // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
     const bool all3 = __all_sync(0xffffffffu, live && rlen == 3);
@@ -253,8 +279,14 @@ k_apply_pipe(PipeArgs<TACC> a) {
             for (int j = 0; j < 3; ++j) po[j] = win_off(ro[j]);
         }
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
-        TOUT *d = (TOUT *)ud.dst + ((size_t)(ud.L0 + 4 * warp) * a.nDst + t0 + lane);
-        for (int g = warp; g < ngroups; g += kPipeWarps, d += grp8) {
+        const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.nDst + t0 + lane;
+        TOUT *d = (TOUT *)ud.dst + dcol;
+        const bool rotU = ROT && (ud.epi_op & kUnitRotU), rotV = ROT && (ud.epi_op & kUnitRotV);
+        TOUT *du = (TOUT *)s_units[rotV ? u - 1 : u].dst + dcol;        // ROT: where the held zonal values go
+#pragma unroll
+        for (int gi = 0; gi < kPipeLev / 4 / kPipeWarps; ++gi, d += grp8, du += grp8) {
+            const int g = warp + gi * kPipeWarps;
+            if (g >= ngroups) break;
             TACC acc[4] = {0, 0, 0, 0};
             const unsigned lp = st + g * GB;
             if (aligned) {
@@ -283,6 +315,26 @@ k_apply_pipe(PipeArgs<TACC> a) {
                 } else {
                     for (int k = rbeg; k < rbeg + rlen; ++k) entry(s_w[k], lp + win_off(s_off[k]));
                 }
+            }
+            if (ROT && rotU) {          // zonal unit: keep, rounded to the output type exactly as a store would
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hold[gi][k] = (TOUT)acc[k];
+                continue;
+            }
+            if (ROT && rotV) {
+                // meridional unit: u' = (u + v tana) / (cosa + sina tana); v' = (v - u' sina) / cosa  (v' uses u');
+                // the two divisors are per-point constants, applied as reciprocals (same in k_rotate)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    TR uu = (TR)hold[gi][k], vv = (TR)(TOUT)acc[k];
+                    uu = (uu + vv * rtana) * rdeni;
+                    vv = (vv - uu * rsa) * rcai;
+                    if (4 * g + k < Ln) {
+                        __stcs(du + (size_t)k * a.nDst, (TOUT)uu);
+                        __stcs(d + (size_t)k * a.nDst, (TOUT)vv);
+                    }
+                }
+                continue;
             }
             if (eop != MPRG_EPI_NONE) {
 #pragma unroll

@@ -386,12 +386,18 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
             size_t inB = 0, outB = 0;
             while (g < nfields) {
                 size_t a = in_slot(g), b = ((size_t)rh->nDst * nlev[g] * osz + 255) & ~(size_t)255;
-                if (g > f && (inB + a > budget || outB + b > budget)) break;
+                const bool pair_tail = epi_op && epi_op[g] == MPRG_EPI_ROT_V;  // never cut a wind pair in two
+                if (g > f && !pair_tail && (inB + a > budget || outB + b > budget)) break;
                 inB += a; outB += b; ++g;
             }
             const int slot = (int)(ctx->slotCursor++ % mprg_ctx::kSlots);
-            if (src_mem == MPRG_HOST) ctx->stageIn[slot].ensure_shared(inB);
-            if (dst_mem == MPRG_HOST) ctx->stageOut[slot].ensure_shared(outB);
+            // a slot that must grow grows every slot of the ring to the same size: the ring rotates across
+            // calls, so otherwise the same growth (a device-wide sync plus a large allocation) would be paid
+            // again on each of the next passes
+            if (src_mem == MPRG_HOST && inB > ctx->stageIn[slot].n)
+                for (auto &b : ctx->stageIn) b.ensure_shared(inB);
+            if (dst_mem == MPRG_HOST && outB > ctx->stageOut[slot].n)
+                for (auto &b : ctx->stageOut) b.ensure_shared(outB);
             // slot reuse: the kernel that last read stageIn[slot] / the D2H that last read stageOut[slot]
             if (ctx->slotUsed[slot]) {
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->evK[slot], 0));

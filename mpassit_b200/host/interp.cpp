@@ -34,14 +34,22 @@ void ck(mprg_ctx *ctx, int rc, const char *where) {
 struct Batch {
     std::vector<const void *> src;
     std::vector<void *> dst;
-    std::vector<int32_t> nlev;
-    void add(const void *s, void *d, int32_t n) { src.push_back(s); dst.push_back(d); nlev.push_back(n); }
+    std::vector<int32_t> nlev, epi;
+    std::vector<double> earg;
+    bool any_epi = false;
+    void add(const void *s, void *d, int32_t n, int32_t op = MPRG_EPI_NONE) {
+        src.push_back(s); dst.push_back(d); nlev.push_back(n); epi.push_back(op); earg.push_back(0.0);
+        any_epi = any_epi || op != MPRG_EPI_NONE;
+    }
     bool empty() const { return src.empty(); }
 };
 
 void run(mprg_ctx *ctx, mprg_route *rh, Batch &b, int sdt, int smem, int ddt, int dmem, const char *where) {
     if (b.empty()) return;
-    ck(ctx, mprg_apply(ctx, rh, (int32_t)b.src.size(), b.src.data(), b.nlev.data(), sdt, smem, b.dst.data(), ddt, dmem),
+    const int32_t n = (int32_t)b.src.size();
+    ck(ctx, b.any_epi ? mprg_apply_ex(ctx, rh, n, b.src.data(), b.nlev.data(), sdt, smem, b.dst.data(), ddt, dmem,
+                                      b.epi.data(), b.earg.data())
+                      : mprg_apply(ctx, rh, n, b.src.data(), b.nlev.data(), sdt, smem, b.dst.data(), ddt, dmem),
        where);
     b = Batch();
 }
@@ -191,6 +199,9 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 if (fv) ck(ctx, mprg_scratch(ctx, 1, nslab * fv->nlev * chain_sz, &d_vm), "scratch");
             }
             // the winds join the main stacked apply when its destinations are device buffers of the same type
+            // rotate_winds_cgrid (interp.F90:291-293) is fused into the store of the (u, v) pair
+            const bool fuse_rot = fu && fv && rotate && fu->nlev == fv->nlev;
+            const int op_u = fuse_rot ? MPRG_EPI_ROT_U : MPRG_EPI_NONE, op_v = fuse_rot ? MPRG_EPI_ROT_V : MPRG_EPI_NONE;
             const bool winds_in_batch = (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR && halo_is_center;
 
             // one stacked apply for everything on the bilinear element->CENTER route:
@@ -208,8 +219,8 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_PATCH) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
                 if (io->ter && io->hgt) b.add(io->ter, io->hgt, 1);
                 if (winds_in_batch) {
-                    if (fu) b.add(fu->src, d_um, fu->nlev);
-                    if (fv) b.add(fv->src, d_vm, fv->nlev);
+                    if (fu) b.add(fu->src, d_um, fu->nlev, op_u);
+                    if (fv) b.add(fv->src, d_vm, fv->nlev, op_v);
                 }
                 for (int i = 0; i < io->n_hist_3d; ++i)
                     if (io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZ || io->hist_3d[i].klass == MPASSIT_CLASS_3D_NZP1)
@@ -226,11 +237,11 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 if (!winds_in_batch) {
                     mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER_HALO, "FieldRegridStore");
                     Batch b;
-                    if (fu) b.add(fu->src, d_um, fu->nlev);
-                    if (fv) b.add(fv->src, d_vm, fv->nlev);
+                    if (fu) b.add(fu->src, d_um, fu->nlev, op_u);
+                    if (fv) b.add(fv->src, d_vm, fv->nlev, op_v);
                     run(ctx, rh, b, sdt, mem, chain_dt, MPRG_DEVICE, "FieldRegrid");
                 }
-                if (fu && fv && rotate)  // interp.F90:291-293
+                if (fu && fv && rotate && !fuse_rot)  // interp.F90:291-293
                     ck(ctx, mprg_rotate_winds_on(ctx, MPRG_CENTER_HALO, d_um, d_vm, fu->nlev, chain_dt, MPRG_DEVICE), "rotate_winds_cgrid");
                 if (fu && io->u_stag) {  // interp.F90:295-311
                     mprg_route *ru = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE1, "FieldRegridStore");

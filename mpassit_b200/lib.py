@@ -21,7 +21,7 @@ SRC_MESH_ELEMENT, SRC_MESH_NODE, SRC_GRID_CENTER = 0, 1, 2
 CENTER, EDGE1, EDGE2, CORNER, CENTER_HALO = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
-EPI_NONE, EPI_ADD, EPI_MUL = 0, 1, 2
+EPI_NONE, EPI_ADD, EPI_MUL, EPI_ROT_U, EPI_ROT_V = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize", "mprg_set_async", "mprg_get_async", "mprg_download",

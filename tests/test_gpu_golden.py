@@ -178,3 +178,39 @@ def test_row_slabs_of_every_rank_tile_the_full_result(engine_lib, g, nranks):
     _close(theta, g["dst_theta"])
     assert np.array_equal(np.concatenate(pieces["xland"], 1).reshape(1, -1), g["dst_xland"])
     _close(np.concatenate(pieces["snow"], 1).reshape(1, -1), g["dst_snow"])
+
+
+@pytest.mark.parametrize("nlev,dt", [(5, "f32"), (60, "f32"), (61, "f32"), (130, "f32"), (60, "f64")])
+def test_fused_wind_rotation_equals_apply_then_rotate(rg, g, nlev, dt):
+    """MPRG_EPI_ROT_U / ROT_V (rotation in the registers of the apply kernel) is bit-identical to
+    mprg_apply followed by mprg_rotate_winds_on, for aligned, unaligned and multi-chunk level counts."""
+    import torch
+
+    from mpassit_b200 import lib as l
+
+    tdt = torch.float32 if dt == "f32" else torch.float64
+    n = g["bil_elem"].size
+    nC = g["lonCell"].size
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(nlev)
+    u = (10.0 * torch.randn((nC, nlev), generator=gen, device="cuda")).to(torch.float32)
+    v = (10.0 * torch.randn((nC, nlev), generator=gen, device="cuda")).to(torch.float32)
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    a_u, a_v, b_u, b_v = (torch.full((nlev, n), float("nan"), dtype=tdt, device="cuda") for _ in range(4))
+    rg.apply(r, [u, v], [a_u, a_v], nlev=[nlev, nlev])
+    rg.rotate_winds(a_u, a_v, nlev)
+    rg.apply(r, [u, v], [b_u, b_v], nlev=[nlev, nlev], epi_op=[l.EPI_ROT_U, l.EPI_ROT_V])
+    rg.synchronize()
+    assert torch.equal(a_u, b_u) and torch.equal(a_v, b_v)
+    assert not torch.isnan(b_u).any() and (b_u[:, torch.from_numpy(g["bil_elem"] < 0).cuda()] == 0).all()
+    # a third, unrelated field stacked behind the pair is untouched by the rotation
+    c_t, c_u, c_v = (torch.empty((nlev, n), dtype=tdt, device="cuda") for _ in range(3))
+    t_src = (u * 0.5 + 3.0).contiguous()
+    plain = torch.empty((nlev, n), dtype=tdt, device="cuda")
+    rg.apply(r, [t_src], [plain], nlev=[nlev])
+    rg.apply(r, [u, v, t_src], [c_u, c_v, c_t], nlev=[nlev] * 3, epi_op=[l.EPI_ROT_U, l.EPI_ROT_V, l.EPI_NONE])
+    rg.synchronize()
+    assert torch.equal(c_t, plain) and torch.equal(c_u, a_u) and torch.equal(c_v, a_v)
+    with pytest.raises(l.MprgError):
+        rg.apply(r, [u], [c_u], nlev=[nlev], epi_op=[l.EPI_ROT_U])
+    r.release()
