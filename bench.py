@@ -202,6 +202,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...)
+    # is sent to stderr instead, at the file-descriptor level
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -243,7 +252,7 @@ def main():
                                        f"{det['weights_s']:.2f}s + apply {det['apply_s']:.2f}s per step"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------- this engine
@@ -478,7 +487,7 @@ def main():
             "store_ms": store_ms, "store_wall_s": store_wall,
             "route_bilinear": info,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

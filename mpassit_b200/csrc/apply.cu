@@ -568,18 +568,24 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         for (auto &f : v) if (f.epi_op == MPRG_EPI_ROT_U) return true;
         return false;
     };
-    // wind pairs go in a launch of their own: the rotating variant costs registers (4 CTAs/SM instead of
-    // 5), which the other fields of the apply should not pay
+    // Wind pairs stay out of the main stacked launch: the rotating variant costs registers (4 CTAs/SM
+    // instead of 5), which the other fields should not pay.  They share a launch with the fields whose
+    // columns are not 16-byte aligned (the per-unit "mixed" variant) when there are any, so the per-tile
+    // prologue is spread over more units.
+    bool sca_done = false;
     if (!rotp.empty() && r->nDst > 0) {
+        std::vector<FieldDev> grp = rotp;
+        grp.insert(grp.end(), cols_sca.begin(), cols_sca.end());
         double k = 0;
         bool vec = true;
-        for (auto &f : rotp) { k += f.nlev; vec = vec && ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0; }
+        for (auto &f : grp) { k += f.nlev; vec = vec && ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0; }
         ProfScope ps(ctx, vec ? 0 : 1, alg_bytes(r, k, sizeof(TIN), sizeof(TOUT), sizeof(TACC)), k * r->nDst);
-        rot_ok = launch_pipe<TIN, TOUT, TACC>(ctx, r, rotp);
+        rot_ok = launch_pipe<TIN, TOUT, TACC>(ctx, r, grp);
         if (!rot_ok) {
             if (ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
             return false;
         }
+        sca_done = true;
     }
     const size_t total = cols_vec.size() + cols_sca.size() + flat.size() + planes.size();
     if (total == 0 || r->nDst == 0) return rot_ok;
@@ -609,7 +615,9 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
             if (!piped_vec && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
             if (!piped_vec && has_rot(cols_vec)) return false;
         }
-        if (!cols_sca.empty()) {
+        if (sca_done) {
+            piped_sca = true;
+        } else if (!cols_sca.empty()) {
             ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
             piped_sca = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_sca);
             if (!piped_sca && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
