@@ -13,10 +13,10 @@
 //             copy moves the 16-byte-aligned window enclosing the column chunk, so any level
 //             count works (60, 55, 61, ...);
 //   math      lanes run along TARGETS: warp w takes level groups w, w+8 (4 levels each); lane t
-//             reads 4 levels of each of its row's columns with one 16-byte shared load
-//             (4-byte loads + in-window offset for unaligned level counts), and the 32 lanes'
-//             results for one level leave as one coalesced 128-byte streaming store into
-//             [lev][j][i].  No transpose through shared memory and one CTA barrier per unit.
+//             reads 4 levels of each of its row's columns with one 16-byte shared load (units whose
+//             columns are not 16-byte aligned are first shifted into place inside their slots), and
+//             the 32 lanes' results for one level leave as one coalesced 128-byte streaming store
+//             into [lev][j][i].  No transpose through shared memory and one CTA barrier per unit.
 #pragma once
 #include "common.cuh"
 
@@ -117,6 +117,11 @@ __device__ __forceinline__ void fma4(TACC (&acc)[4], TACC wt, unsigned saddr) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(z), "=d"(w) : "r"(saddr + 16));
         acc[0] += wt * (TACC)x; acc[1] += wt * (TACC)y; acc[2] += wt * (TACC)z; acc[3] += wt * (TACC)w;
     }
+}
+template <typename TIN>
+__device__ __forceinline__ void sts1(unsigned saddr, TIN v) {
+    if (sizeof(TIN) == 4) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(saddr), "f"(*(float *)&v) : "memory");
+    else asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(saddr), "d"(*(double *)&v) : "memory");
 }
 template <typename TIN>
 __device__ __forceinline__ TIN lds1(unsigned saddr) {
@@ -268,16 +273,27 @@ k_apply_pipe(PipeArgs<TACC> a) {
         const bool aligned = ALLVEC || (ud.epi_op & kUnitAligned) != 0;
         const TACC earg = (TACC)ud.epi_arg;
         const int ngroups = (Ln + 3) >> 2;
-        if (!live) continue;
-        // unaligned units: byte offset of each register-held entry's first wanted level inside its staged
-        // 16-byte-aligned window, (c * nlev + L0) mod EPV = ((c mod EPV) * (nlev mod EPV) + L0 mod EPV) mod EPV
-        const int nm = ud.nlev & (EPV - 1), lm = ud.L0 & (EPV - 1);
-        auto win_off = [&](int so) { return (so & ~15) + ((((so & 15) * nm + lm) & (EPV - 1)) * (int)sizeof(TIN)); };
-        int po[3] = {0, 0, 0};
-        if (!aligned) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) po[j] = win_off(ro[j]);
+        if (!ALLVEC && !aligned) {
+            // Columns whose start is not 16-byte aligned were copied as the aligned window around them, so
+            // the wanted levels begin eo elements into the slot, (c * nlev + L0) mod EPV =
+            // ((c mod EPV) * (nlev mod EPV) + L0 mod EPV) mod EPV.  Each warp shifts its share of the
+            // slots down by eo (conflict-free consecutive words) so that the math below reads every unit
+            // with 16-byte loads; per-lane 4-byte reads at eo would conflict 4-5 way on the banks.
+            const int nm = ud.nlev & (EPV - 1), lm = ud.L0 & (EPV - 1);
+            for (int s = warp; s < nu; s += kPipeWarps) {
+                const int eo = ((s_uniq[s] & (EPV - 1)) * nm + lm) & (EPV - 1);
+                if (eo) {
+                    const unsigned sb = st + s * SLOTB;
+                    const TIN x0 = lds1<TIN>(sb + (eo + lane) * (int)sizeof(TIN));
+                    const TIN x1 = lds1<TIN>(sb + (eo + lane + 32) * (int)sizeof(TIN));  // the window holds EPV-1 elements of slack
+                    __syncwarp();
+                    sts1<TIN>(sb + lane * (int)sizeof(TIN), x0);
+                    sts1<TIN>(sb + (lane + 32) * (int)sizeof(TIN), x1);
+                }
+            }
+            __syncthreads();
         }
+        if (!live) continue;
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
         const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.nDst + t0 + lane;
         TOUT *d = (TOUT *)ud.dst + dcol;
@@ -289,32 +305,16 @@ k_apply_pipe(PipeArgs<TACC> a) {
             if (g >= ngroups) break;
             TACC acc[4] = {0, 0, 0, 0};
             const unsigned lp = st + g * GB;
-            if (aligned) {
-                if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
-                    fma4<TIN, TACC>(acc, rw[0], lp + (ro[0] & ~15));
-                    fma4<TIN, TACC>(acc, rw[1], lp + (ro[1] & ~15));
-                    fma4<TIN, TACC>(acc, rw[2], lp + (ro[2] & ~15));
-                } else if (fast) {
+            if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
+                fma4<TIN, TACC>(acc, rw[0], lp + (ro[0] & ~15));
+                fma4<TIN, TACC>(acc, rw[1], lp + (ro[1] & ~15));
+                fma4<TIN, TACC>(acc, rw[2], lp + (ro[2] & ~15));
+            } else if (fast) {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + (ro[j] & ~15));  // absent entries never touch staging (0 x garbage = NaN)
-                } else {
-                    for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (s_off[k] & ~15));
-                }
+                for (int j = 0; j < 3; ++j)
+                    if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + (ro[j] & ~15));  // absent entries never touch staging (0 x garbage = NaN)
             } else {
-                // 4-byte loads; the staged window holds EPV-1 elements of slack after the chunk, so reads
-                // past Ln stay inside the slot (their results are never stored)
-                auto entry = [&](TACC wt, unsigned p) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[k] += wt * (TACC)lds1<TIN>(p + k * (int)sizeof(TIN));
-                };
-                if (fast) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        if (all3 || j < rlen) entry(rw[j], lp + po[j]);
-                } else {
-                    for (int k = rbeg; k < rbeg + rlen; ++k) entry(s_w[k], lp + win_off(s_off[k]));
-                }
+                for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (s_off[k] & ~15));
             }
             if (ROT && rotU) {          // zonal unit: keep, rounded to the output type exactly as a store would
 #pragma unroll

@@ -260,3 +260,53 @@ def test_interp_data_rank_slabs_equal_single_rank(engine_lib, host, lc_case, nra
         spans = [p[1][k] for p in parts]
         assert spans[0][0] == 0 and spans[-1][1] == shapes[k][0]
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_interp_data_global_latlon_target(engine_lib, orc, host, tmp_path):
+    """BASELINE.json configs[0] in miniature: quasi-uniform global mesh -> global lat-lon target
+    (`target_grid_type='lat-lon'`, no wind rotation: interp.F90:138,291 rotate on Lambert only),
+    histlist_2d/3d/soil through the host mirror, checked against the oracle's interp_data."""
+    from mpassit_b200.regrid import Regridder
+
+    f = tmp_path / "namelist.input"
+    f.write_text("&config\n target_grid_type = 'lat-lon'\n nx = 73\n ny = 37\n is_regional = .false.\n"
+                 " stand_lon = -180.\n interp_diag = .false.\n interp_hist = .true.\n wrf_mod_vars = .true.\n/\n")
+    cfg = host.read_setup_namelist(str(f))
+    assert cfg.proj_code == host.PROJ_LATLON
+    grids = {k: host.target_coords(cfg, s) for k, s in (("M", 0), ("U", 1), ("V", 2), ("CORNER", 3))}
+    assert grids["M"][0].shape == (36, 72)
+    mesh = H.small_global(2562, jitter=0.1, seed=3)
+    nz, nsoil = 7, 4            # 7 levels: columns not 16-byte aligned
+    F = _fields(mesh, nz, nsoil)
+    F["diag"] = []
+    want = H.oracle_interp(orc, mesh, grids, F, None, None, lc=False)
+    rg = Regridder(device=0)
+    rg.set_mesh(mesh.lonCell, mesh.latCell, mesh.lonVertex, mesh.latVertex, mesh.verticesOnCell)
+    for k, s in (("M", 0), ("U", 1), ("V", 2), ("CORNER", 3)):
+        rg.set_target(s, grids[k][1], grids[k][0])
+    nM, nU, nV = grids["M"][0].size, grids["U"][0].size, grids["V"][0].size
+
+    def specs(items, table):
+        tn = dict(table)
+        return [host.FieldSpec(nm, tn.get(nm, nm), a.shape[1], a, np.full((a.shape[1], nM), np.nan, np.float32)) for nm, a in items]
+
+    h2, h3, soil = (specs(F["hist_2d"], defaults.HISTLIST_2D), specs(F["hist_3d"], defaults.HISTLIST_3D),
+                    specs(F["soil"], defaults.HISTLIST_SOIL))
+    hgt = np.full((1, nM), np.nan, np.float32)
+    ust = np.full((nz, nU), np.nan, np.float32)
+    vst = np.full((nz, nV), np.nan, np.float32)
+    host.interp_data(rg, cfg, diag=[], hist_2d=h2, hist_3d=h3, soil=soil, ter=F["ter"], hgt=hgt, u_stag=ust, v_stag=vst, nz=nz)
+    got = {s.name: s.dst for s in h2 + h3 + soil}
+    got["HGT"], got["U"], got["V"] = hgt, ust, vst
+    for nm, w in want.items():
+        if nm.startswith("uReconstruct"):
+            continue
+        g = got[nm]
+        assert not np.isnan(g).any(), nm
+        if nm in {"xland", "tslb", "smois", "sh2o"}:
+            assert np.array_equal(g, w), nm
+        else:
+            assert np.abs(g - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), nm
+    # a global mesh covers every target point: nothing is unmapped (snow: every destination cell fully covered)
+    assert (got["theta"] != 0).all()
+    rg.close()
