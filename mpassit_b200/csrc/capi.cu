@@ -358,6 +358,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
     if (!rh) fail(1, "mprg_apply: null route");
     if (nfields <= 0) return;
     if (!src || !dst || !nlev) fail(1, "mprg_apply: null argument");
+    if (rh->nDst == 0) return;  // this rank owns no destination rows (nranks > nj): nothing to regrid
     const size_t isz = src_dtype == MPRG_F32 ? 4 : 8, osz = dst_dtype == MPRG_F32 ? 4 : 8;
     const int64_t nSrcPts = rh->srcLevelSlowest ? rh->srcPlane : rh->nSrc;
     MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));

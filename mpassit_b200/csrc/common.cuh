@@ -223,6 +223,16 @@ void mesh_need_cell_bvh(mprg_ctx *ctx);
 void mesh_need_tri_bvh(mprg_ctx *ctx);
 void mesh_need_poly_bvh(mprg_ctx *ctx);
 
+// a rank that owns no destination rows (nranks > nj): an empty, valid CSR
+inline bool route_empty_slab(mprg_ctx *ctx, mprg_route *r, int64_t nDst, int64_t nSrc) {
+    if (nDst > 0) return false;
+    r->nDst = 0; r->nnz = 0; r->nSrc = nSrc;
+    r->rowptr.alloc(1); r->col.alloc(1); r->w.alloc(1);
+    MPRG_CUDA(cudaMemsetAsync(r->rowptr.p, 0, sizeof(int32_t), ctx->stream));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return true;
+}
+
 // locate.cu
 void store_nearest(mprg_ctx *ctx, mprg_route *r);
 void store_bilinear_element(mprg_ctx *ctx, mprg_route *r);

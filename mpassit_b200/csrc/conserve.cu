@@ -198,6 +198,7 @@ void store_conserve(mprg_ctx *ctx, mprg_route *r) {
     mesh_need_poly_bvh(ctx);
     Mesh &m = ctx->mesh;
     if (m.maxEdges > 36) fail(64, "mprg_store: maxEdges %d exceeds the clipping buffer", m.maxEdges);
+    if (route_empty_slab(ctx, r, tg.nSlab(), m.nCells)) return;
     r->nDst = tg.nSlab();
     r->nSrc = m.nCells;
     BvhView v{m.polyBvh.nodes.p, m.polyBvh.primId.p, m.polyBvh.nLeafNodes, m.polyBvh.nPrim, m.polyBvh.primBox.p};

@@ -32,6 +32,7 @@ void store_nearest(mprg_ctx *ctx, mprg_route *r) {
     Mesh &m = ctx->mesh;
     Target &tg = ctx->target[r->dst_stagger];
     int64_t n = tg.nSlab();
+    if (route_empty_slab(ctx, r, n, m.nCells)) return;
     r->nDst = n; r->nnz = n; r->nSrc = m.nCells;
     r->rowptr.alloc(n + 1); r->col.alloc(n); r->w.alloc(n);
     BvhView v{m.cellBvh.nodes.p, m.cellBvh.primId.p, m.cellBvh.nLeafNodes, m.cellBvh.nPrim};
@@ -101,6 +102,7 @@ void store_bilinear_element(mprg_ctx *ctx, mprg_route *r) {
     Mesh &m = ctx->mesh;
     Target &tg = ctx->target[r->dst_stagger];
     int64_t n = tg.nSlab();
+    if (route_empty_slab(ctx, r, n, m.nCells)) return;
     r->nDst = n; r->nSrc = m.nCells;
     DevBuf<int32_t> elem(n), ecol(3 * n), cnt(n + 1);
     DevBuf<double> ew(3 * n);

@@ -138,7 +138,7 @@ void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r) {
     r->nSrc = (int64_t)src.ni * srows;
     r->srcLevelSlowest = true;
     r->srcPlane = r->nSrc;
-    if (src.ni < 2 || srows < 2) {
+    if (n == 0 || src.ni < 2 || srows < 2) {
         if (ctx->nranks == 1) fail(57, "mprg_store: CENTER grid too small for quads");
         // a rank with fewer than two source rows owns no mappable edge point: all rows empty
         r->nnz = 0;
@@ -234,6 +234,7 @@ void store_bilinear_node(mprg_ctx *ctx, mprg_route *r) {
     Mesh &m = ctx->mesh;
     Target &tg = ctx->target[r->dst_stagger];
     int64_t n = tg.nSlab();
+    if (route_empty_slab(ctx, r, n, m.nVertices)) return;
     r->nDst = n;
     r->nSrc = m.nVertices;
     DevBuf<int32_t> ecol(3 * n), cnt(n + 1);

@@ -214,3 +214,39 @@ def test_fused_wind_rotation_equals_apply_then_rotate(rg, g, nlev, dt):
     with pytest.raises(l.MprgError):
         rg.apply(r, [u], [c_u], nlev=[nlev], epi_op=[l.EPI_ROT_U])
     r.release()
+
+
+def test_more_ranks_than_rows_gives_empty_slabs(engine_lib, g):
+    """para_range hands no rows to the last ranks when nranks > nj: every call must accept the empty
+    slab (zero destination points) and the non-empty ranks must still tile the result."""
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import Regridder
+
+    nj, ni = g["lat_M"].shape
+    nranks = nj + 3
+    pieces = []
+    for rank in (0, nj - 1, nj, nranks - 1):
+        r = Regridder(device=0, rank=rank, nranks=nranks)
+        _load(r, g)
+        j0, j1 = r.slab(l.CENTER)
+        for method, src_loc, stag in ((l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER), (l.NEAREST_STOD, l.SRC_MESH_ELEMENT, l.CENTER),
+                                      (l.CONSERVE, l.SRC_MESH_ELEMENT, l.CENTER), (l.BILINEAR, l.SRC_MESH_NODE, l.CENTER),
+                                      (l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER_HALO), (l.BILINEAR, l.SRC_GRID_CENTER, l.EDGE1),
+                                      (l.BILINEAR, l.SRC_GRID_CENTER, l.EDGE2)):
+            rt = r.store(method, src_loc, stag)
+            info = rt.info()
+            s0, s1 = r.slab(stag)
+            assert info["nDst"] == (s1 - s0) * r.shape[stag if stag != l.CENTER_HALO else l.CENTER][1]
+            if method == l.BILINEAR and src_loc == l.SRC_MESH_ELEMENT and stag == l.CENTER:
+                out = np.full((5, max(info["nDst"], 1)), np.nan, np.float32)[:, : info["nDst"]]
+                out = np.ascontiguousarray(out)
+                r.apply(rt, [g["src_theta"]], [out])
+                if info["nDst"]:
+                    pieces.append((j0, out.reshape(5, j1 - j0, ni)))
+            rt.release()
+        r.close()
+    assert len(pieces) == 2 and pieces[0][0] == 0 and pieces[1][0] == nj - 1
+    want = g["dst_theta"].reshape(5, nj, ni)
+    for j0, p in pieces:
+        scale = np.abs(want).max()
+        assert np.abs(p - want[:, j0:j0 + p.shape[1]]).max() <= RTOL * scale
