@@ -35,6 +35,7 @@ module mpassit_rg_mod
   public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
   public :: mprg_set_async, mprg_get_async, mprg_download, mprg_io_bytes
+  public :: mprg_post_midlevels, mprg_post_ptop
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
   interface
@@ -207,6 +208,21 @@ module mpassit_rg_mod
        import :: c_int, c_ptr, c_size_t
        type(c_ptr), value :: ctx, dev, host
        integer(c_size_t), value :: bytes
+     end function
+     !> Z_C = 0.5 (PHB(k) + PHB(k-1)) (write_data.F90:1406-1412) on this rank's slab
+     integer(c_int) function mprg_post_midlevels(ctx, stagger, nlev, dtype, mem, x, mid) bind(C, name="mprg_post_midlevels")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, x, mid
+       integer(c_int), value :: stagger, dtype, mem
+       integer(c_int32_t), value :: nlev
+     end function
+     !> this rank's share of P_TOP (write_data.F90:1364-1373): combine with MPI_MAX / MPI_MIN
+     integer(c_int) function mprg_post_ptop(ctx, stagger, nlev, dtype, mem, x, maxval, mincand) bind(C, name="mprg_post_ptop")
+       import :: c_int, c_ptr, c_int32_t, c_double
+       type(c_ptr), value :: ctx, x
+       integer(c_int), value :: stagger, dtype, mem
+       integer(c_int32_t), value :: nlev
+       real(c_double), intent(out) :: maxval, mincand
      end function
      integer(c_int) function mprg_io_bytes(ctx, h2d, d2h) bind(C, name="mprg_io_bytes")
        import :: c_int, c_ptr, c_int64_t

@@ -162,6 +162,18 @@ int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, 
 /* same on the rows of `stagger` = MPRG_CENTER or MPRG_CENTER_HALO (u, v: [nlev][rows][ni]) */
 int mprg_rotate_winds_on(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype, int mem);
 
+/* ---- WRF-compatibility post-ops of the writer (write_data.F90:1339-1432, wrf_mod_vars), on this
+ *      rank's slab, device or host buffers.  T-300 and PHB = 9.81 zgrid are fused epilogues of
+ *      mprg_apply_ex; the two below need neighbouring levels / a reduction.
+ *      mprg_post_midlevels: mid[k] = 0.5 (x[k+1] + x[k]), k = 0..nlev-2  (Z_C from the regridded
+ *      zgrid, write_data.F90:1406-1412; x is [nlev][slab], mid is [nlev-1][slab]).
+ *      mprg_post_ptop: this rank's share of P_TOP (write_data.F90:1364-1373): *maxval = max of the
+ *      whole field, *mincand = min of 0.8 x[nlev-1][.] over the points whose top-level value is >= 10
+ *      (+inf if none).  P_TOP = min(MAX over ranks of maxval, MIN over ranks of mincand). */
+int mprg_post_midlevels(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, int mem, const void *x, void *mid);
+int mprg_post_ptop(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, int mem, const void *x, double *maxval,
+                   double *mincand);
+
 /* ---- gather: replaces ESMF_FieldGather(rootPet=0), write_data.F90:1006-1453.
  *      Collects every rank's slab of a [nlev][nj][ni] field on `root`.
  *      Device buffers; NCCL over NVLink.  With nranks == 1 it is a device copy.

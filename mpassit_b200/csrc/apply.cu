@@ -769,4 +769,81 @@ void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, i
     MPRG_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------
+// WRF-compatibility post-ops (write_data.F90:1364-1373, 1406-1412)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_midlevels(const T *__restrict__ x, T *__restrict__ mid, int64_t n, int32_t nlev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double lo = (double)x[i];
+    for (int k = 1; k < nlev; ++k) {
+        const double hi = (double)x[(size_t)k * n + i];
+        mid[(size_t)(k - 1) * n + i] = (T)(0.5 * (hi + lo));  // 0.5*(dum3dp1(k) + dum3dp1(k-1)), R8 arithmetic
+        lo = hi;
+    }
+}
+
+// out[0] = max over the whole field, out[1] = min of 0.8 * top-level value over points with top >= 10
+// (doubles kept as ordered integers for atomicMax / atomicMin; all values of interest are finite)
+__device__ __forceinline__ long long dbl_key(double v) {
+    long long b = __double_as_longlong(v);
+    return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+template <typename T>
+__global__ void k_ptop(const T *__restrict__ x, int64_t n, int32_t nlev, long long *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double mx = -1.0e300, mn = 1.0e300;
+    if (i < n) {
+        for (int k = 0; k < nlev; ++k) mx = fmax(mx, (double)x[(size_t)k * n + i]);
+        const double top = (double)x[(size_t)(nlev - 1) * n + i];
+        if (top >= 10.0) mn = top * 0.80;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, dbl_key(mx));
+        atomicMin(out + 1, dbl_key(mn));
+    }
+}
+__global__ void k_ptop_finish(const long long *in, double *out) {
+    for (int k = 0; k < 2; ++k) {
+        long long b = in[k];
+        out[k] = __longlong_as_double(b >= 0 ? b : (b ^ 0x7fffffffffffffffLL));
+    }
+}
+
+void post_midlevels_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, void *mid) {
+    if (n <= 0 || nlev < 2) return;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    if (dtype == MPRG_F32) k_midlevels<float><<<g, 256, 0, ctx->stream>>>((const float *)x, (float *)mid, n, nlev);
+    else k_midlevels<double><<<g, 256, 0, ctx->stream>>>((const double *)x, (double *)mid, n, nlev);
+    ctx->launches++;
+    MPRG_CUDA(cudaGetLastError());
+}
+
+void post_ptop_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, double *out2_dev) {
+    DevBuf<long long> keys(2);
+    const double init[2] = {-1.0e300, 1.0e300};
+    long long hk[2];
+    for (int k = 0; k < 2; ++k) {
+        long long b;
+        memcpy(&b, &init[k], 8);
+        hk[k] = b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+    }
+    MPRG_CUDA(cudaMemcpyAsync(keys.p, hk, sizeof hk, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0 && nlev > 0) {
+        const unsigned g = (unsigned)((n + 255) / 256);
+        if (dtype == MPRG_F32) k_ptop<float><<<g, 256, 0, ctx->stream>>>((const float *)x, n, nlev, keys.p);
+        else k_ptop<double><<<g, 256, 0, ctx->stream>>>((const double *)x, n, nlev, keys.p);
+        ctx->launches++;
+    }
+    k_ptop_finish<<<1, 1, 0, ctx->stream>>>(keys.p, out2_dev);
+    ctx->launches++;
+    MPRG_CUDA(cudaGetLastError());
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));  // keys is freed on return; results are read by the caller
+}
+
 }  // namespace mprg

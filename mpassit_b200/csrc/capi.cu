@@ -3,6 +3,7 @@
 // message retrievable with mprg_last_error().
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -510,6 +511,57 @@ int mprg_rotate_winds_on(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t n
 
 int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem) {
     return mprg_rotate_winds_on(ctx, MPRG_CENTER, u, v, nlev, dtype, mem);
+}
+
+// ---------------------------------------------------------------------------
+// WRF-compatibility post-ops
+// ---------------------------------------------------------------------------
+static const Target &post_target(mprg_ctx *ctx, int stagger) {
+    if (stagger < 0 || stagger > MPRG_CENTER_HALO || !ctx->target[stagger].set) fail(44, "mprg_post: stagger %d not set", stagger);
+    return ctx->target[stagger];
+}
+
+int mprg_post_midlevels(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, int mem, const void *x, void *mid) {
+    MPRG_ENTER(ctx)
+    const Target &tg = post_target(ctx, stagger);
+    const int64_t n = tg.nSlab();
+    if (n == 0 || nlev < 2) return 0;
+    if (!x || !mid) fail(1, "mprg_post_midlevels: null argument");
+    const size_t esz = dtype == MPRG_F32 ? 4 : 8, inB = (size_t)n * nlev * esz, outB = (size_t)n * (nlev - 1) * esz;
+    if (mem == MPRG_DEVICE) {
+        post_midlevels_device(ctx, n, nlev, dtype, x, mid);
+    } else {
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        DevBuf<unsigned char> din(inB), dout(outB);
+        MPRG_CUDA(cudaMemcpyAsync(din.p, x, inB, cudaMemcpyHostToDevice, ctx->stream));
+        post_midlevels_device(ctx, n, nlev, dtype, din.p, dout.p);
+        MPRG_CUDA(cudaMemcpyAsync(mid, dout.p, outB, cudaMemcpyDeviceToHost, ctx->stream));
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_post_ptop(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, int mem, const void *x, double *maxval,
+                   double *mincand) {
+    MPRG_ENTER(ctx)
+    const Target &tg = post_target(ctx, stagger);
+    const int64_t n = tg.nSlab();
+    if (!maxval || !mincand) fail(1, "mprg_post_ptop: null argument");
+    if (n > 0 && nlev > 0 && !x) fail(1, "mprg_post_ptop: null field");
+    DevBuf<double> res(2);
+    if (mem == MPRG_DEVICE || n == 0) {
+        post_ptop_device(ctx, n, nlev, dtype, x, res.p);
+    } else {
+        const size_t inB = (size_t)n * nlev * (dtype == MPRG_F32 ? 4 : 8);
+        DevBuf<unsigned char> din(inB);
+        MPRG_CUDA(cudaMemcpyAsync(din.p, x, inB, cudaMemcpyHostToDevice, ctx->stream));
+        post_ptop_device(ctx, n, nlev, dtype, din.p, res.p);
+    }
+    double h[2];
+    MPRG_CUDA(cudaMemcpy(h, res.p, sizeof h, cudaMemcpyDeviceToHost));
+    *maxval = h[0];
+    *mincand = h[1] >= 1.0e300 ? (double)INFINITY : h[1];
+    MPRG_LEAVE(ctx)
 }
 
 // ---------------------------------------------------------------------------

@@ -255,6 +255,9 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
                   int dst_dtype);
 void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype);
 
+void post_midlevels_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, void *mid);
+void post_ptop_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, double *out2_dev);
+
 // gather.cu
 void comm_destroy(mprg_ctx *ctx);
 void comm_id(mprg_ctx *ctx, void *id128);

@@ -243,6 +243,17 @@ class Regridder:
         mem = DEVICE if _is_torch(u) else HOST
         self._ck(self.L.mprg_rotate_winds_on(self.ctx, int(stagger), _ptr(u), _ptr(v), int(nlev), _dtype_code(u), mem))
 
+    # ---- WRF-compatibility post-ops (write_data.F90:1364-1373, 1406-1412) -----------
+    def post_midlevels(self, x, mid, nlev: int, stagger: int = CENTER) -> None:
+        mem = DEVICE if _is_torch(x) else HOST
+        self._ck(self.L.mprg_post_midlevels(self.ctx, int(stagger), int(nlev), _dtype_code(x), mem, _ptr(x), _ptr(mid)))
+
+    def post_ptop(self, x, nlev: int, stagger: int = CENTER) -> tuple[float, float]:
+        mem = DEVICE if _is_torch(x) else HOST
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.mprg_post_ptop(self.ctx, int(stagger), int(nlev), _dtype_code(x), mem, _ptr(x), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- gather ---------------------------------------------------------
     def comm_id(self) -> bytes:
         buf = C.create_string_buffer(128)

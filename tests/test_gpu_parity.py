@@ -229,3 +229,53 @@ def test_host_sources_upload_only_the_referenced_id_range(rg, orc, nlev):
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
     assert b1[0] - b0[0] == (hi - lo) * nlev * 4 and b1[1] - b0[1] == nDst * nlev * 4
     r.release()
+
+
+def test_wrf_post_ops_match_the_writer_formulas(rg, orc):
+    """write_data.F90:1339-1432 (`wrf_mod_vars`): T-300 and PHB = 9.81 zgrid as fused epilogues of the apply,
+    Z_C mid-level average and this rank's share of P_TOP as mprg_post_*, against oracle/post_oracle.py."""
+    import torch
+
+    from mpassit_b200 import lib as l
+    from oracle import post_oracle as po
+
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "regional_ragged")
+    elem, col, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
+    rp, cc, ww = orc.ell_to_csr(elem >= 0, col, w)
+    nz = 9
+    theta = H.synth.smooth_field(mesh.lonCell, mesh.latCell, nz, seed=1) + 20.0
+    zgrid = np.ascontiguousarray(np.cumsum(np.abs(H.synth.smooth_field(mesh.lonCell, mesh.latCell, nz + 1, seed=2)), axis=1))
+    pres = np.ascontiguousarray((1.0e5 * np.exp(-np.arange(nz)[None, :] / 3.0) *
+                                 (1 + 0.01 * H.synth.smooth_field(mesh.lonCell, mesh.latCell, nz, seed=3) / 300)).astype(np.float32))
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    n = lon.size
+    raw_t, raw_z, raw_p = (orc.apply(rp, cc, ww, a, np.float32) for a in (theta, zgrid, pres))
+    t300 = np.empty((nz, n), np.float32)
+    phb = np.empty((nz + 1, n), np.float32)
+    rg.apply(r, [theta], [t300], nlev=[nz], epi_op=[l.EPI_ADD], epi_arg=[-300.0])
+    rg.apply(r, [zgrid], [phb], nlev=[nz + 1], epi_op=[l.EPI_MUL], epi_arg=[9.81])
+    np.testing.assert_allclose(t300, po.t_minus_300(raw_t), rtol=1e-6, atol=1e-4)
+    assert np.all(t300[:, elem < 0] == -300.0)              # quirk: unmapped T is -300, not 0
+    np.testing.assert_allclose(phb, po.phb(raw_z), rtol=1e-6, atol=1e-4)
+    # Z_C and P_TOP on host and on device buffers
+    zreg = np.empty((nz + 1, n), np.float32)
+    preg = np.empty((nz, n), np.float32)
+    rg.apply(r, [zgrid, ], [zreg], nlev=[nz + 1])
+    rg.apply(r, [pres], [preg], nlev=[nz])
+    zc = np.empty((nz, n), np.float32)
+    rg.post_midlevels(zreg, zc, nz + 1)
+    assert np.array_equal(zc, po.z_c(zreg))
+    dz = torch.from_numpy(zreg).cuda()
+    dzc = torch.empty((nz, n), dtype=torch.float32, device="cuda")
+    rg.post_midlevels(dz, dzc, nz + 1)
+    rg.synchronize()
+    assert np.array_equal(dzc.cpu().numpy(), zc)
+    for buf in (preg, torch.from_numpy(preg).cuda()):
+        mx, mn = rg.post_ptop(buf, nz)
+        assert mx == float(preg.astype(np.float64).max())
+        assert min(mx, mn) == po.p_top(preg)
+    # a field whose top level is everywhere below the threshold: only the maxval term survives
+    small = np.full((nz, n), 5.0, np.float32)
+    mx, mn = rg.post_ptop(small, nz)
+    assert mx == 5.0 and mn == float("inf") and min(mx, mn) == po.p_top(small)
+    r.release()
