@@ -43,9 +43,15 @@ struct ApplyArgs {
     const int32_t *col;
     const TW *w;
     int64_t nDst;
-    const FieldDev *fields;
     int32_t nfields;
     int64_t srcPlane;  // k_apply_planes only
+};
+
+// field descriptors of a launch, passed as a kernel parameter (constant bank) instead of through a
+// device-side copy that would sit between launches on the stream
+constexpr int kPackFields = 96;
+struct FieldPack {
+    FieldDev f[kPackFields];
 };
 
 template <typename T>
@@ -88,7 +94,7 @@ namespace mprg {
 // ---------------------------------------------------------------------------
 template <typename TIN, typename TOUT, typename TACC, bool VEC, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
-k_apply_cols(ApplyArgs<TACC> a) {
+k_apply_cols(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     __shared__ int32_t s_rowptr[kTile + 1];
     __shared__ int32_t s_col[kCsrCap];
     __shared__ TACC s_w[kCsrCap];
@@ -115,7 +121,7 @@ k_apply_cols(ApplyArgs<TACC> a) {
     const int f1 = min(f0 + kFieldsPerCta, a.nfields);
     int buf = 0;
     for (int f = f0; f < f1; ++f) {
-        const FieldDev fd = a.fields[f];
+        const FieldDev fd = fp.f[f];
         const TIN *__restrict__ src = (const TIN *)fd.src;
         TOUT *__restrict__ dst = (TOUT *)fd.dst;
         const int nlev = fd.nlev;
@@ -240,7 +246,7 @@ constexpr int kShortLev = 8;  // fields with at most this many levels (2-D field
 
 template <typename TIN, typename TOUT, typename TACC>
 __global__ void __launch_bounds__(256)
-k_apply_flat(ApplyArgs<TACC> a) {
+k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nDst) return;
     const int b = __ldg(a.rowptr + t), e = __ldg(a.rowptr + t + 1);
@@ -253,7 +259,7 @@ k_apply_flat(ApplyArgs<TACC> a) {
         w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
     }
     for (int f = 0; f < a.nfields; ++f) {
-        const FieldDev fd = a.fields[f];
+        const FieldDev fd = fp.f[f];
         const TIN *__restrict__ src = (const TIN *)fd.src;
         const int nlev = fd.nlev;
         if (nlev == 1) {
@@ -295,7 +301,7 @@ constexpr int kPlaneBatch = 4;  // levels whose gathers are all issued before th
 
 template <typename TIN, typename TOUT, typename TACC>
 __global__ void __launch_bounds__(256)
-k_apply_planes(ApplyArgs<TACC> a) {
+k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nDst) return;
     const int b = __ldg(a.rowptr + t), e = __ldg(a.rowptr + t + 1);
@@ -307,7 +313,7 @@ k_apply_planes(ApplyArgs<TACC> a) {
         c[k] = h ? __ldg(a.col + b + k) : 0;   // absent entries: weight 0 on a valid address (index 0)
         w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
     }
-    const FieldDev fd = a.fields[blockIdx.y];
+    const FieldDev fd = fp.f[blockIdx.y];
     const TIN *__restrict__ src = (const TIN *)fd.src;
     TOUT *__restrict__ dst = (TOUT *)fd.dst;
     const bool shortrow = e - b <= kFlatRow;
@@ -397,45 +403,26 @@ static bool pipe_disabled() {
     return e && !strcmp(e, "direct");
 }
 
-// descriptor ring shared by every apply kernel: returns the device address of `bytes` copied from `host`
-static const void *push_desc(mprg_ctx *ctx, const void *host, size_t bytes) {
-    constexpr size_t kRing = 1 << 20;
-    const size_t need = (bytes + 255) & ~(size_t)255;
-    if (need > kRing) fail(34, "mprg_apply: too many stacked fields");
-    ctx->descHost.ensure(kRing);
-    ctx->scratch.ensure(kRing);
-    if (ctx->descCursor + need > kRing) {
-        // wrapping: descriptors of launches still queued (asynchronous applies) must not be overwritten
-        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->descCursor = 0;
-    }
-    unsigned char *h = (unsigned char *)ctx->descHost.p + ctx->descCursor;
-    memcpy(h, host, bytes);
-    unsigned char *d = ctx->scratch.p + ctx->descCursor;
-    MPRG_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->descCursor += need;
-    return d;
-}
-
 template <typename KERN, typename TACC>
-static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles) {
+static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes,
+                          unsigned tiles) {
     MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa);
+    kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa, up);
     ctx->launches++;
 }
 
 template <typename TIN, typename TOUT, typename TACC, int STAGES>
-static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, size_t smemBytes, unsigned tiles, bool allvec, int minb,
-                          bool rot) {
-    if (rot) {  // fused wind rotation: 2 stages, 64 registers (it holds the zonal results and four fp64 angles)
-        if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 4, true>, pa, smemBytes, tiles);
-        else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 4, true>, pa, smemBytes, tiles);
+static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes, unsigned tiles,
+                          bool allvec, int minb, bool rot) {
+    if (rot) {  // fused wind rotation: 2 stages, 64 registers (it holds the zonal results and the angles)
+        if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 4, true>, pa, up, smemBytes, tiles);
+        else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 4, true>, pa, up, smemBytes, tiles);
         return;
     }
-    if (allvec && minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 5>, pa, smemBytes, tiles);
-    else if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 4>, pa, smemBytes, tiles);
-    else if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 5>, pa, smemBytes, tiles);
-    else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 4>, pa, smemBytes, tiles);
+    if (allvec && minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 5>, pa, up, smemBytes, tiles);
+    else if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 4>, pa, up, smemBytes, tiles);
+    else if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 5>, pa, up, smemBytes, tiles);
+    else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 4>, pa, up, smemBytes, tiles);
 }
 
 // returns false if this route / field set does not fit the pipelined kernel
@@ -508,16 +495,17 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     for (size_t u0 = 0; u0 < units.size();) {
         size_t nu = std::min<size_t>(kPipeMaxUnits, units.size() - u0);
         if (u0 + nu < units.size() && (units[u0 + nu - 1].epi_op & kUnitRotU)) --nu;  // keep a wind pair in one launch
-        pa.units = (const UnitDev *)push_desc(ctx, units.data() + u0, nu * sizeof(UnitDev));
+        UnitPack up;
+        memcpy(up.u, units.data() + u0, nu * sizeof(UnitDev));
         pa.nunits = (int)nu;
         bool allvec = true, anyrot = false;
         for (size_t k = 0; k < nu; ++k) {
             allvec = allvec && (units[u0 + k].epi_op & kUnitAligned);
             anyrot = anyrot || (units[u0 + k].epi_op & (kUnitRotU | kUnitRotV));
         }
-        if (stages == 4 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, smemBytes, tiles, allvec, minb, false);
-        else if (stages == 3 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, smemBytes, tiles, allvec, minb, false);
-        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, fixed + 2 * stage, tiles, allvec, minb, anyrot);
+        if (stages == 4 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, up, smemBytes, tiles, allvec, minb, false);
+        else if (stages == 3 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, up, smemBytes, tiles, allvec, minb, false);
+        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, up, fixed + 2 * stage, tiles, allvec, minb, anyrot);
         u0 += nu;
     }
     MPRG_CUDA(cudaGetLastError());
@@ -589,14 +577,6 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     }
     const size_t total = cols_vec.size() + cols_sca.size() + flat.size() + planes.size();
     if (total == 0 || r->nDst == 0) return rot_ok;
-    std::vector<FieldDev> all;
-    all.reserve(total);
-    all.insert(all.end(), cols_vec.begin(), cols_vec.end());
-    all.insert(all.end(), cols_sca.begin(), cols_sca.end());
-    all.insert(all.end(), flat.begin(), flat.end());
-    all.insert(all.end(), planes.begin(), planes.end());
-    // descriptors travel through a pinned host ring into a device ring: the copy is truly asynchronous
-    const FieldDev *dev = (const FieldDev *)push_desc(ctx, all.data(), total * sizeof(FieldDev));
     ApplyArgs<TACC> a;
     a.rowptr = r->rowptr.p;
     a.col = r->col.p;
@@ -605,8 +585,19 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
     auto ksum = [](const std::vector<FieldDev> &v) { double k = 0; for (auto &f : v) k += f.nlev; return k; };
-    // every 3-D field of the apply goes through ONE pipelined launch (aligned and unaligned level
-    // counts are told apart per unit); the register-gather kernels below are the fallback
+    // field-descriptor kernels take their fields kPackFields at a time, as a kernel parameter
+    auto packs = [&](const std::vector<FieldDev> &v, auto &&launch) {
+        for (size_t f0 = 0; f0 < v.size(); f0 += kPackFields) {
+            const size_t n = std::min<size_t>(kPackFields, v.size() - f0);
+            FieldPack fp;
+            memcpy(fp.f, v.data() + f0, n * sizeof(FieldDev));
+            a.nfields = (int)n;
+            launch(fp, n);
+            ctx->launches++;
+        }
+    };
+    // every 3-D field of the apply goes through the pipelined kernel; the register-gather kernels below
+    // are the fallback for routes whose tiles exceed its caps
     bool piped_vec = false, piped_sca = false;
     if (!cols_vec.empty() || !cols_sca.empty()) {
         if (!cols_vec.empty()) {
@@ -626,33 +617,33 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     }
     if (!cols_vec.empty() && !piped_vec) {
         ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
-        a.fields = dev; a.nfields = (int)cols_vec.size();
-        dim3 g(tiles, (unsigned)((cols_vec.size() + kFieldsPerCta - 1) / kFieldsPerCta));
         const int minb = tune_minb();
-        if (minb == 2) k_apply_cols<TIN, TOUT, TACC, true, 2><<<g, kThreads, 0, ctx->stream>>>(a);
-        else if (minb == 4) k_apply_cols<TIN, TOUT, TACC, true, 4><<<g, kThreads, 0, ctx->stream>>>(a);
-        else k_apply_cols<TIN, TOUT, TACC, true, 3><<<g, kThreads, 0, ctx->stream>>>(a);
-        ctx->launches++;
+        packs(cols_vec, [&](const FieldPack &fp, size_t n) {
+            dim3 g(tiles, (unsigned)((n + kFieldsPerCta - 1) / kFieldsPerCta));
+            if (minb == 2) k_apply_cols<TIN, TOUT, TACC, true, 2><<<g, kThreads, 0, ctx->stream>>>(a, fp);
+            else if (minb == 4) k_apply_cols<TIN, TOUT, TACC, true, 4><<<g, kThreads, 0, ctx->stream>>>(a, fp);
+            else k_apply_cols<TIN, TOUT, TACC, true, 3><<<g, kThreads, 0, ctx->stream>>>(a, fp);
+        });
     }
     if (!cols_sca.empty() && !piped_sca) {
         ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
-        a.fields = dev + cols_vec.size(); a.nfields = (int)cols_sca.size();
-        dim3 g(tiles, (unsigned)((cols_sca.size() + kFieldsPerCta - 1) / kFieldsPerCta));
-        k_apply_cols<TIN, TOUT, TACC, false, 3><<<g, kThreads, 0, ctx->stream>>>(a);
-        ctx->launches++;
+        packs(cols_sca, [&](const FieldPack &fp, size_t n) {
+            dim3 g(tiles, (unsigned)((n + kFieldsPerCta - 1) / kFieldsPerCta));
+            k_apply_cols<TIN, TOUT, TACC, false, 3><<<g, kThreads, 0, ctx->stream>>>(a, fp);
+        });
     }
     if (!flat.empty()) {
         ProfScope ps(ctx, 2, alg_bytes(r, ksum(flat), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(flat) * r->nDst);
-        a.fields = dev + cols_vec.size() + cols_sca.size(); a.nfields = (int)flat.size();
-        k_apply_flat<TIN, TOUT, TACC><<<(unsigned)((r->nDst + 255) / 256), 256, 0, ctx->stream>>>(a);
-        ctx->launches++;
+        packs(flat, [&](const FieldPack &fp, size_t) {
+            k_apply_flat<TIN, TOUT, TACC><<<(unsigned)((r->nDst + 255) / 256), 256, 0, ctx->stream>>>(a, fp);
+        });
     }
     if (!planes.empty()) {
         ProfScope ps(ctx, 3, alg_bytes(r, ksum(planes), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(planes) * r->nDst);
-        a.fields = dev + cols_vec.size() + cols_sca.size() + flat.size(); a.nfields = (int)planes.size();
-        dim3 g((unsigned)((r->nDst + 255) / 256), (unsigned)planes.size());
-        k_apply_planes<TIN, TOUT, TACC><<<g, 256, 0, ctx->stream>>>(a);
-        ctx->launches++;
+        packs(planes, [&](const FieldPack &fp, size_t n) {
+            dim3 g((unsigned)((r->nDst + 255) / 256), (unsigned)n);
+            k_apply_planes<TIN, TOUT, TACC><<<g, 256, 0, ctx->stream>>>(a, fp);
+        });
     }
     MPRG_CUDA(cudaGetLastError());
     return rot_ok;

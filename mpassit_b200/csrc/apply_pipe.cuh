@@ -38,6 +38,11 @@ struct UnitDev {
     int32_t epi_op;    // bits 0-7: MPRG_EPI_*;  bit 8: columns are 16-byte aligned (vector loads)
     double epi_arg;
 };
+// the unit descriptors of a launch travel as a kernel parameter (3 KB of constant bank): no
+// descriptor copy sits between consecutive launches on the stream
+struct UnitPack {
+    UnitDev u[kPipeMaxUnits];
+};
 constexpr int kUnitAligned = 0x100;
 constexpr int kUnitRotU = 0x200, kUnitRotV = 0x400;  // wind pair: this unit is the zonal / meridional chunk
 
@@ -54,7 +59,6 @@ struct PipeArgs {
     int64_t nDst;
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
-    const UnitDev *units;
     int32_t nunits;
     int32_t maxU;       // slot capacity of one stage (>= max unique columns of any tile)
     // ROT launches only: rotation angles of this rank's destination rows (rotate_winds_cgrid fused into the store)
@@ -140,7 +144,7 @@ __device__ __forceinline__ TIN lds1(unsigned saddr) {
 //      pass over the fields.
 template <typename TIN, typename TOUT, typename TACC, int STAGES, bool ALLVEC, int MINB, bool ROT = false>
 __global__ void __launch_bounds__(kPipeThreads, MINB)
-k_apply_pipe(PipeArgs<TACC> a) {
+k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     constexpr int SLOTB = pipe_slot_bytes<TIN>();
     constexpr int EPV = 16 / (int)sizeof(TIN);            // elements per 16-byte chunk
     constexpr int GB = 4 * (int)sizeof(TIN);              // bytes of one 4-level group in a staged column
@@ -163,7 +167,7 @@ k_apply_pipe(PipeArgs<TACC> a) {
     // ---- prologue: CSR slice + the tile's schedule ---------------------------------
     if (tid <= kPipeTile) s_rowptr[tid] = a.rowptr[min(t0 + min(tid, ntile), a.nDst)];
     for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
-        ((int32_t *)s_units)[i] = __ldg((const int32_t *)a.units + i);
+        ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < STAGES; ++i) mbar_init(s_mbar + i, ALLVEC ? 1 : kPipeWarps);  // arrivals per unit

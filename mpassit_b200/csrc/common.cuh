@@ -186,9 +186,6 @@ struct mprg_ctx {
     unsigned long long h2dBytes = 0, d2hBytes = 0;  // field bytes moved by host-buffer applies / downloads since init
     unsigned slotCursor = 0;
     cudaEvent_t evDl = nullptr;           // mprg_download ordering
-    mprg::DevBuf<unsigned char> scratch;  // apply descriptors (device side)
-    mprg::PinnedBuf descHost;             // apply descriptors (pinned ring, host side)
-    size_t descCursor = 0;
     mprg::DevBuf<unsigned char> userScratch[8];  // mprg_scratch slots
     void *nccl = nullptr;                 // ncclComm_t
     void *ncclLib = nullptr;
