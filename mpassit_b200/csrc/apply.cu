@@ -258,7 +258,29 @@ k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
         c[k] = h ? __ldg(a.col + b + k) : 0;
         w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
     }
-    for (int f = 0; f < a.nfields; ++f) {
+    int f = 0;
+    if (e - b <= kFlatRow) {
+        // 2-D fields, rows of <= 4 entries (bilinear, nearest): four fields' gathers in flight per thread
+        for (; f + 4 <= a.nfields; f += 4) {
+            if (fp.f[f].nlev != 1 || fp.f[f + 1].nlev != 1 || fp.f[f + 2].nlev != 1 || fp.f[f + 3].nlev != 1) break;
+            TIN x[4][kFlatRow];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const TIN *__restrict__ src = (const TIN *)fp.f[f + q].src;
+#pragma unroll
+                for (int k = 0; k < kFlatRow; ++k) x[q][k] = (b + k < e) ? __ldg(src + c[k]) : (TIN)0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                TACC acc = 0;
+#pragma unroll
+                for (int k = 0; k < kFlatRow; ++k)
+                    if (b + k < e) acc += w[k] * (TACC)x[q][k];
+                st_stream((TOUT *)fp.f[f + q].dst + t, (TOUT)epilogue(acc, fp.f[f + q].epi_op, fp.f[f + q].epi_arg));
+            }
+        }
+    }
+    for (; f < a.nfields; ++f) {
         const FieldDev fd = fp.f[f];
         const TIN *__restrict__ src = (const TIN *)fd.src;
         const int nlev = fd.nlev;
@@ -498,7 +520,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         UnitPack up;
         memcpy(up.u, units.data() + u0, nu * sizeof(UnitDev));
         pa.nunits = (int)nu;
-        bool allvec = true, anyrot = false;
+        bool allvec = getenv("MPASSIT_GPU_FORCE_MIXED") == nullptr, anyrot = false;
         for (size_t k = 0; k < nu; ++k) {
             allvec = allvec && (units[u0 + k].epi_op & kUnitAligned);
             anyrot = anyrot || (units[u0 + k].epi_op & (kUnitRotU | kUnitRotV));

@@ -235,6 +235,16 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             if (bcol >= 0)
                 bulk_g2s(bstage + (u % STAGES) * stageBytes,
                          (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * sizeof(TIN), colB, bar);
+        } else if (ud.epi_op & kUnitAligned) {
+            // aligned unit of a mixed launch: exact chunks again, but this barrier counts one arrival per
+            // warp (lane 0 posts the bytes of the warp's own copies; an mbarrier's transaction count may
+            // run ahead of the expectation, so no ordering between the two is needed)
+            const unsigned colB = (unsigned)ud.Ln * (unsigned)sizeof(TIN);
+            const unsigned mine = __popc(__ballot_sync(0xffffffffu, bcol >= 0));
+            if (lane == 0) mbar_arrive_tx(bar, colB * mine);
+            if (bcol >= 0)
+                bulk_g2s(bstage + (u % STAGES) * stageBytes,
+                         (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * sizeof(TIN), colB, bar);
         } else {
             // lane 0 of every warp arrives with the warp's byte count; the owner of a slot then
             // launches one bulk copy of the 16-byte-aligned window enclosing the column chunk
@@ -257,7 +267,6 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             const unsigned wb = __reduce_add_sync(0xffffffffu, nb);
             __syncwarp();  // hand-copied tail words are ordered before the arrival that publishes them
             if (lane == 0) mbar_arrive_tx(bar, wb);
-            __syncwarp();  // the expected byte count is posted before any of this warp's copies can complete
             if (nb) bulk_g2s(bstage + (u % STAGES) * stageBytes, (const char *)ud.src + al, nb, bar);
         }
     };
