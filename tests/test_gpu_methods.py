@@ -310,3 +310,39 @@ def test_interp_data_global_latlon_target(engine_lib, orc, host, tmp_path):
     # a global mesh covers every target point: nothing is unmapped (snow: every destination cell fully covered)
     assert (got["theta"] != 0).all()
     rg.close()
+
+
+def test_interp_data_mid_workload_against_oracle(engine_lib, orc, host):
+    """The bench's own code path (workload.make / run_interp, device buffers, stock var-lists, wind chain
+    with fused rotation) on the 12-km miniature of the CONUS case (153 k cells, 60 levels -> 450 x 265):
+    every output field against the oracle."""
+    import torch
+
+    from mpassit_b200 import lib as l
+    from mpassit_b200 import workload
+    from mpassit_b200.regrid import Regridder
+
+    wl = workload.make("mid")
+    rg = Regridder(device=0)
+    workload.load_geometry(rg, wl)
+    F = workload.make_fields(wl, device="cuda:0")
+    workload.run_interp(rg, wl, F["dev"], l.DEVICE)
+    rg.synchronize()
+    fields = {g: [(s.name, s.src.cpu().numpy()) for s in F["dev"][g]] for g in ("diag", "hist_2d", "hist_3d", "soil")}
+    fields["ter"] = F["dev"]["ter"].cpu().numpy()
+    want = H.oracle_interp(orc, wl.mesh, wl.grids, fields, wl.cosa, wl.sina)
+    got = {s.name: s.dst.cpu().numpy() for g in ("diag", "hist_2d", "hist_3d", "soil") for s in F["dev"][g]}
+    got["HGT"], got["U"], got["V"] = (F["dev"][k].cpu().numpy() for k in ("hgt", "u_stag", "v_stag"))
+    exact = {"xland", "tslb", "smois", "sh2o"}
+    checked = 0
+    for nm, w in want.items():
+        if nm.startswith("uReconstruct"):
+            continue
+        g = got[nm].reshape(w.shape)
+        if nm in exact:
+            assert np.array_equal(g, w), nm
+        else:
+            assert np.abs(g - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), (nm, np.abs(g - w).max())
+        checked += 1
+    assert checked >= 40
+    rg.close()
