@@ -437,6 +437,12 @@ template <typename TIN, typename TOUT, typename TACC, int STAGES>
 static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes, unsigned tiles,
                           bool allvec, int minb, bool rot) {
     if (rot) {  // fused wind rotation: 2 stages, 64 registers (it holds the zonal results and the angles)
+        static const bool rot5 = getenv("MPASSIT_GPU_ROT_MINB") && atoi(getenv("MPASSIT_GPU_ROT_MINB")) >= 5;
+        if (rot5 && minb >= 5) {
+            if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 5, true>, pa, up, smemBytes, tiles);
+            else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 5, true>, pa, up, smemBytes, tiles);
+            return;
+        }
         if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 4, true>, pa, up, smemBytes, tiles);
         else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 4, true>, pa, up, smemBytes, tiles);
         return;
@@ -506,12 +512,9 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     pa.maxU = r->tileUniqMax;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
-    pa.cosa = pa.sina = nullptr;
-    if (rot) {  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
-        const Target &tg = ctx->target[r->dst_stagger];
-        pa.cosa = ctx->cosa.p + tg.slabOffset();
-        pa.sina = ctx->sina.p + tg.slabOffset();
-    }
+    pa.rotc = nullptr;
+    if (rot)  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
+        pa.rotc = ctx->rotc.p + 4 * ctx->target[r->dst_stagger].slabOffset();
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
     const size_t smemBytes = fixed + (size_t)stages * stage;
     for (size_t u0 = 0; u0 < units.size();) {
@@ -744,17 +747,35 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
 // ---------------------------------------------------------------------------
 // rotate_winds_cgrid, interp.F90:689-749 (v' uses the already rotated u')
 // ---------------------------------------------------------------------------
-template <typename T, typename TR>
-__global__ void k_rotate(T *__restrict__ u, T *__restrict__ v, const double *__restrict__ cosa,
-                         const double *__restrict__ sina, int64_t n, int32_t nlev) {
+// per-point constants of rotate_winds_cgrid: u' = (u + v tana) / (cosa + sina tana); v' = (v - u' sina) / cosa.
+// The divisors do not depend on the level, so they are applied as reciprocals prepared once per grid
+// (<= 1 ulp of fp64 from the divisions); both the stand-alone pass and the rotation fused into
+// k_apply_pipe read them, which keeps the two bit-identical.
+__global__ void k_rot_consts(const double *__restrict__ cosa, const double *__restrict__ sina, int64_t n,
+                             double *__restrict__ rotc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double ca = cosa[i], sa = sina[i];
     const double tana = sa / ca;
-    // u' = (u + v tana) / (cosa + sina tana); v' = (v - u' sina) / cosa: the divisors are per-point
-    // constants, applied as reciprocals; TR = the arithmetic type (RotMath, apply_pipe.cuh), the same
-    // expressions as the rotation fused into k_apply_pipe so both give identical bits
-    const TR rsa = (TR)sa, rtana = (TR)tana, rcai = (TR)(1.0 / ca), rdeni = (TR)(1.0 / (ca + sa * tana));
+    rotc[4 * i + 0] = sa;
+    rotc[4 * i + 1] = tana;
+    rotc[4 * i + 2] = 1.0 / ca;
+    rotc[4 * i + 3] = 1.0 / (ca + sa * tana);
+}
+
+void rotation_constants(mprg_ctx *ctx, int64_t n) {
+    ctx->rotc.alloc(4 * (size_t)n);
+    k_rot_consts<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->cosa.p, ctx->sina.p, n, ctx->rotc.p);
+    ctx->launches++;
+    MPRG_CUDA(cudaGetLastError());
+}
+
+// TR = the arithmetic type (RotMath, apply_pipe.cuh): the same expressions as the fused rotation
+template <typename T, typename TR>
+__global__ void k_rotate(T *__restrict__ u, T *__restrict__ v, const double *__restrict__ rotc, int64_t n, int32_t nlev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TR rsa = (TR)rotc[4 * i], rtana = (TR)rotc[4 * i + 1], rcai = (TR)rotc[4 * i + 2], rdeni = (TR)rotc[4 * i + 3];
     for (int l = blockIdx.y; l < nlev; l += gridDim.y) {
         const size_t o = (size_t)l * n + i;
         TR uu = (TR)u[o], vv = (TR)v[o];
@@ -770,14 +791,14 @@ void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, i
     const Target &tg = ctx->target[stagger];
     const int64_t n = tg.nSlab();
     if (n == 0 || nlev <= 0) return;
-    const double *cosa = ctx->cosa.p + tg.slabOffset(), *sina = ctx->sina.p + tg.slabOffset();
+    const double *rotc = ctx->rotc.p + 4 * tg.slabOffset();
     dim3 g((unsigned)((n + 255) / 256), (unsigned)min(nlev, 4));  // >= 15 levels per thread: tana, den once per point
     if (dtype == MPRG_F32 && acc_fp32_requested())
-        k_rotate<float, float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, cosa, sina, n, nlev);
+        k_rotate<float, float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, rotc, n, nlev);
     else if (dtype == MPRG_F32)
-        k_rotate<float, double><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, cosa, sina, n, nlev);
+        k_rotate<float, double><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, rotc, n, nlev);
     else
-        k_rotate<double, double><<<g, 256, 0, ctx->stream>>>((double *)u, (double *)v, cosa, sina, n, nlev);
+        k_rotate<double, double><<<g, 256, 0, ctx->stream>>>((double *)u, (double *)v, rotc, n, nlev);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
 }

@@ -62,7 +62,7 @@ struct PipeArgs {
     int32_t nunits;
     int32_t maxU;       // slot capacity of one stage (>= max unique columns of any tile)
     // ROT launches only: rotation angles of this rank's destination rows (rotate_winds_cgrid fused into the store)
-    const double *cosa, *sina;
+    const double *rotc;  // [nDst][4]: sina, tana, 1/cosa, 1/(cosa + sina tana)
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -204,12 +204,10 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     // (fp32 arithmetic when the whole apply is fp32 -- RotMath -- : the fp64 pipe would otherwise bound the launch)
     using TR = typename RotMath<TOUT, TACC>::type;
     TR rsa = 0, rtana = 0, rcai = 1, rdeni = 1;
-    if (ROT && live) {
-        const double ca = __ldg(a.cosa + t0 + lane), sa = __ldg(a.sina + t0 + lane);
-        const double tana = sa / ca;
-        rsa = (TR)sa; rtana = (TR)tana;
-        rcai = (TR)(1.0 / ca);
-        rdeni = (TR)(1.0 / (ca + sa * tana));
+    if (ROT && live) {  // per-point constants prepared once by mprg_set_rotation (k_rot_consts)
+        const double2 c0 = __ldg((const double2 *)(a.rotc + 4 * (t0 + lane)));
+        const double2 c1 = __ldg((const double2 *)(a.rotc + 4 * (t0 + lane)) + 1);
+        rsa = (TR)c0.x; rtana = (TR)c0.y; rcai = (TR)c1.x; rdeni = (TR)c1.y;
     }
     TOUT hold[kPipeLev / 4 / kPipeWarps][4];  // ROT: the zonal unit's results, held until the meridional unit
     const bool fast = __all_sync(0xffffffffu, rlen <= 3);

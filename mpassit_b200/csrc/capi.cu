@@ -482,6 +482,7 @@ int mprg_set_rotation(mprg_ctx *ctx, const double *cosa, const double *sina) {
     ctx->sina.alloc(n);
     MPRG_CUDA(cudaMemcpyAsync(ctx->cosa.p, cosa, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     MPRG_CUDA(cudaMemcpyAsync(ctx->sina.p, sina, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rotation_constants(ctx, n);
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->haveRot = true;
     MPRG_LEAVE(ctx)

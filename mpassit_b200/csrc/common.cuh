@@ -173,6 +173,7 @@ struct mprg_ctx {
     std::map<std::tuple<int, int, int>, mprg_route *> routes;
     std::vector<mprg_route *> imported;
     mprg::DevBuf<double> cosa, sina;  // CENTER, full grid
+    mprg::DevBuf<double> rotc;        // [n][4] per-point rotation constants (sina, tana, 1/cosa, 1/(cosa + sina tana))
     bool haveRot = false;
     int64_t launches = 0;
     double last_ms = 0.0;
@@ -251,6 +252,7 @@ struct ApplyField {
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
                   int dst_dtype);
 void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype);
+void rotation_constants(mprg_ctx *ctx, int64_t n);  // fills ctx->rotc from ctx->cosa / ctx->sina
 
 void post_midlevels_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, void *mid);
 void post_ptop_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, double *out2_dev);

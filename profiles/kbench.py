@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--fields", type=int, default=12, help="number of stacked nz-level fields")
     ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
     ap.add_argument("--stack", default="", help="explicit stack, e.g. 60x12,61x2 (levels x fields)")
+    ap.add_argument("--rot", action="store_true", help="the first two fields are a wind pair with fused rotation")
     args = ap.parse_args()
     t0 = time.time()
     wl = workload.make(args.config)
@@ -41,6 +42,7 @@ def main():
     rg.use_torch_stream()
     workload.load_geometry(rg, wl)
     route = rg.store(L.BILINEAR, L.SRC_MESH_ELEMENT, L.CENTER)
+    epi = None
     info = route.info()
     nlev = args.nlev or wl.nz
     n = wl.mesh.nCells
@@ -49,6 +51,8 @@ def main():
         levs = [int(a.split("x")[0]) for a in args.stack.split(",") for _ in range(int(a.split("x")[1]))]
     srcs = [torch.randn((n, L), device="cuda", dtype=torch.float32) for L in levs]
     dsts = [torch.empty((L, wl.n_mass), device="cuda", dtype=torch.float32) for L in levs]
+    if args.rot:
+        epi = [L.EPI_ROT_U, L.EPI_ROT_V] + [L.EPI_NONE] * (len(levs) - 2)
     import ctypes
     em, um = ctypes.c_int32(), ctypes.c_int32()
     rg.L.mprg_debug_route_tiles(ctypes.c_void_p(route.handle), ctypes.byref(em), ctypes.byref(um))
@@ -73,10 +77,10 @@ def main():
             os.environ["MPASSIT_GPU_APPLY"] = "direct"
             os.environ["MPASSIT_GPU_MINB"] = mode[1:] or "3"
         for _ in range(2):
-            rg.apply(route, srcs, dsts, nlev=levs)
+            rg.apply(route, srcs, dsts, nlev=levs, epi_op=epi)
         rg.profile(True)
         for _ in range(args.iters):
-            rg.apply(route, srcs, dsts, nlev=levs)
+            rg.apply(route, srcs, dsts, nlev=levs, epi_op=epi)
         recs = rg.profile_read()
         rg.profile(False)
         out = {}
