@@ -36,6 +36,7 @@ module mpassit_rg_mod
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
   public :: mprg_set_async, mprg_get_async, mprg_download, mprg_io_bytes
   public :: mprg_post_midlevels, mprg_post_ptop
+  public :: mprg_apply_into, mprg_put_slab, mprg_ipc_export, mprg_ipc_open, mprg_ipc_close_all
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
   interface
@@ -208,6 +209,42 @@ module mpassit_rg_mod
        import :: c_int, c_ptr, c_size_t
        type(c_ptr), value :: ctx, dev, host
        integer(c_size_t), value :: bytes
+     end function
+     !> apply fused with the gather: dst_full(f) is the whole field of the destination stagger (the
+     !! writing rank's buffer, own or mapped with mprg_ipc_open); each rank stores its rows into it
+     integer(c_int) function mprg_apply_into(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst_full, dst_dtype, &
+                                             epi_op, epi_arg) bind(C, name="mprg_apply_into")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, rh
+       integer(c_int32_t), value :: nfields
+       type(c_ptr), intent(in) :: src(*), dst_full(*)
+       integer(c_int32_t), intent(in) :: nlev(*)
+       integer(c_int), value :: src_dtype, src_mem, dst_dtype
+       type(c_ptr), value :: epi_op, epi_arg   ! c_null_ptr: no epilogues
+     end function
+     integer(c_int) function mprg_put_slab(ctx, stagger, nlev, dtype, slab_dev, full_dev) bind(C, name="mprg_put_slab")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, slab_dev, full_dev
+       integer(c_int), value :: stagger, dtype
+       integer(c_int32_t), value :: nlev
+     end function
+     !> CUDA IPC: the writing rank exports (handle, offset) of each full field (MPI_Bcast them), the others map them
+     integer(c_int) function mprg_ipc_export(ctx, dev_ptr, handle64, offset) bind(C, name="mprg_ipc_export")
+       import :: c_int, c_ptr, c_char, c_size_t
+       type(c_ptr), value :: ctx, dev_ptr
+       character(kind=c_char), intent(out) :: handle64(64)
+       integer(c_size_t), intent(out) :: offset
+     end function
+     integer(c_int) function mprg_ipc_open(ctx, handle64, offset, peer_ptr) bind(C, name="mprg_ipc_open")
+       import :: c_int, c_ptr, c_char, c_size_t
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(in) :: handle64(64)
+       integer(c_size_t), value :: offset
+       type(c_ptr), intent(out) :: peer_ptr
+     end function
+     integer(c_int) function mprg_ipc_close_all(ctx) bind(C, name="mprg_ipc_close_all")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
      end function
      !> Z_C = 0.5 (PHB(k) + PHB(k-1)) (write_data.F90:1406-1412) on this rank's slab
      integer(c_int) function mprg_post_midlevels(ctx, stagger, nlev, dtype, mem, x, mid) bind(C, name="mprg_post_midlevels")

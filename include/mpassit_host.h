@@ -107,6 +107,11 @@ typedef struct mpassit_interp_io {
      * [nz][nj+1][ni]; the rotated mass-point winds (UMASS/VMASS, never written to the
      * output file) stay on the device */
     void *u_stag, *v_stag;
+    /* dst_full != 0 (device buffers only): every dst / hgt / u_stag / v_stag above is the FULL field
+     * [nlev][nj][ni] of its stagger -- the writing rank's own buffer, or that buffer mapped with
+     * mprg_ipc_open on the other ranks -- and each rank stores its rows straight into it
+     * (mprg_apply_into): the FieldGather of write_to_file is fused into the regrid */
+    int32_t dst_full;
     /* wind rotation (interp.F90:138,291) uses the angles registered once with mprg_set_rotation,
      * the analogue of cosa/sina_target_grid created in define_target_grid (model_grid.F90:1113-1185) */
 } mpassit_interp_io;

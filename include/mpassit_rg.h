@@ -152,6 +152,25 @@ int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields,
                   void *const *dst, int dst_dtype, int dst_mem,
                   const int32_t *epi_op, const double *epi_arg);
 
+/* ---- apply fused with the gather: like mprg_apply_ex, but dst_full[f] is the FULL field
+ *      [nlev[f]][nj][ni] of the route's destination stagger (device memory) and this rank writes only
+ *      its own rows into it.  On the writing rank that is its own buffer; on the other ranks it is the
+ *      writing rank's buffer mapped with mprg_ipc_open, so the apply kernels store straight into the
+ *      writer's memory over NVLink and ESMF_FieldGather (write_data.F90:1006-1453) needs no pass of its
+ *      own.  Wind pairs (MPRG_EPI_ROT_*) are intermediates and not accepted here.  Every rank must have
+ *      finished (mprg_synchronize + the host's barrier) before the writer reads the fields.
+ *      mprg_ipc_export: handle (64 bytes) + offset of a device buffer of this process;
+ *      mprg_ipc_open: the same buffer in this process's address space (mappings are cached per
+ *      allocation and released by mprg_ipc_close_all / mprg_finalize). */
+int mprg_apply_into(mprg_ctx *ctx, mprg_route *rh, int32_t nfields,
+                    const void *const *src, const int32_t *nlev, int src_dtype, int src_mem,
+                    void *const *dst_full, int dst_dtype, const int32_t *epi_op, const double *epi_arg);
+/* this rank's slab [nlev][nj_slab][ni] -> its rows of a full field (own or mapped), on the context's stream */
+int mprg_put_slab(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void *slab_dev, void *full_dev);
+int mprg_ipc_export(mprg_ctx *ctx, const void *dev_ptr, void *handle64, size_t *offset);
+int mprg_ipc_open(mprg_ctx *ctx, const void *handle64, size_t offset, void **peer_ptr);
+int mprg_ipc_close_all(mprg_ctx *ctx);
+
 /* ---- wind rotation: replaces rotate_winds_cgrid, interp.F90:689-749.
  *      cosa/sina: CENTER stagger, full grid [nj][ni], fp64 (cosa_target_grid /
  *      sina_target_grid, model_grid.F90:1113-1185).  u, v: this rank's CENTER

@@ -43,12 +43,16 @@ struct ApplyArgs {
     const int32_t *col;
     const TW *w;
     int64_t nDst;
+    int64_t dstLev, dstOff;  // dst[l * dstLev + dstOff + t]: slab buffer (nDst, 0) or full-grid field (see PipeArgs)
     int32_t nfields;
     int64_t srcPlane;  // k_apply_planes only
 };
 
 // field descriptors of a launch, passed as a kernel parameter (constant bank) instead of through a
 // device-side copy that would sit between launches on the stream
+struct DstLayout {
+    int64_t lev, off;  // dst[l * lev + off + t]
+};
 constexpr int kPackFields = 96;
 struct FieldPack {
     FieldDev f[kPackFields];
@@ -229,7 +233,7 @@ k_apply_cols(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
             // ---- phase B: transposed, coalesced streaming store --------------
             if (lane < ntile) {
                 for (int lev = warp; lev < Ln; lev += kThreads / 32)
-                    st_stream(dst + (size_t)(L0 + lev) * a.nDst + t0 + lane, s_out[buf][lev][lane]);
+                    st_stream(dst + (size_t)(L0 + lev) * a.dstLev + a.dstOff + t0 + lane, s_out[buf][lev][lane]);
             }
             // s_out is double buffered: the next pass writes the other buffer, and the
             // barrier of that pass orders this pass's reads before the buffer is reused.
@@ -276,7 +280,7 @@ k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
 #pragma unroll
                 for (int k = 0; k < kFlatRow; ++k)
                     if (b + k < e) acc += w[k] * (TACC)x[q][k];
-                st_stream((TOUT *)fp.f[f + q].dst + t, (TOUT)epilogue(acc, fp.f[f + q].epi_op, fp.f[f + q].epi_arg));
+                st_stream((TOUT *)fp.f[f + q].dst + a.dstOff + t, (TOUT)epilogue(acc, fp.f[f + q].epi_op, fp.f[f + q].epi_arg));
             }
         }
     }
@@ -290,7 +294,7 @@ k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
             for (int k = 0; k < kFlatRow; ++k)
                 if (b + k < e) acc += w[k] * (TACC)__ldg(src + c[k]);
             for (int k = b + kFlatRow; k < e; ++k) acc += __ldg(a.w + k) * (TACC)__ldg(src + __ldg(a.col + k));
-            st_stream((TOUT *)fd.dst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+            st_stream((TOUT *)fd.dst + a.dstOff + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
         } else {
             // short columns (soil layers): the whole column of every row entry, one coalesced store per level
             TACC acc[kShortLev];
@@ -311,7 +315,7 @@ k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
             }
 #pragma unroll
             for (int l = 0; l < kShortLev; ++l)
-                if (l < nlev) st_stream((TOUT *)fd.dst + (size_t)l * a.nDst + t, (TOUT)epilogue(acc[l], fd.epi_op, fd.epi_arg));
+                if (l < nlev) st_stream((TOUT *)fd.dst + (size_t)l * a.dstLev + a.dstOff + t, (TOUT)epilogue(acc[l], fd.epi_op, fd.epi_arg));
         }
     }
 }
@@ -356,7 +360,7 @@ k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
 #pragma unroll
                 for (int k = 0; k < kFlatRow; ++k)
                     if (b + k < e) acc += w[k] * (TACC)x[q][k];
-                st_stream(dst + (size_t)(lev + q) * a.nDst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+                st_stream(dst + (size_t)(lev + q) * a.dstLev + a.dstOff + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
             }
         }
     }
@@ -367,7 +371,7 @@ k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
         for (int k = 0; k < kFlatRow; ++k)
             if (b + k < e) acc += w[k] * (TACC)__ldg(pl + c[k]);
         for (int k = b + kFlatRow; k < e; ++k) acc += __ldg(a.w + k) * (TACC)__ldg(pl + __ldg(a.col + k));
-        st_stream(dst + (size_t)lev * a.nDst + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
+        st_stream(dst + (size_t)lev * a.dstLev + a.dstOff + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
     }
 }
 
@@ -456,7 +460,7 @@ static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, const UnitPac
 // returns false if this route / field set does not fit the pipelined kernel
 // fields flagged MPRG_EPI_ROT_U / ROT_V are wind pairs whose rotation is fused into the store
 template <typename TIN, typename TOUT, typename TACC>
-static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields) {
+static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields, DstLayout dl) {
     if (pipe_disabled() || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
     const int slotBytes = pipe_slot_bytes<TIN>();
     const size_t stage = (size_t)r->tileUniqMax * slotBytes;
@@ -509,6 +513,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     if (sizeof(TACC) == 8) pa.w = (const TACC *)r->w.p; else pa.w = (const TACC *)r->w32.p;
     pa.tileUPtr = r->tileUPtr.p; pa.tileUCols = r->tileUCols.p; pa.entrySlot = r->entrySlot.p;
     pa.nDst = r->nDst;
+    pa.dstLev = dl.lev; pa.dstOff = dl.off;
     pa.maxU = r->tileUniqMax;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
@@ -575,7 +580,7 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
 template <typename TIN, typename TOUT, typename TACC>
 static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols_vec,
                        const std::vector<FieldDev> &cols_sca, const std::vector<FieldDev> &flat,
-                       const std::vector<FieldDev> &planes, const std::vector<FieldDev> &rotp) {
+                       const std::vector<FieldDev> &planes, const std::vector<FieldDev> &rotp, DstLayout dl) {
     bool rot_ok = true;
     auto has_rot = [](const std::vector<FieldDev> &v) {
         for (auto &f : v) if (f.epi_op == MPRG_EPI_ROT_U) return true;
@@ -593,7 +598,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         bool vec = true;
         for (auto &f : grp) { k += f.nlev; vec = vec && ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0; }
         ProfScope ps(ctx, vec ? 0 : 1, alg_bytes(r, k, sizeof(TIN), sizeof(TOUT), sizeof(TACC)), k * r->nDst);
-        rot_ok = launch_pipe<TIN, TOUT, TACC>(ctx, r, grp);
+        rot_ok = launch_pipe<TIN, TOUT, TACC>(ctx, r, grp, dl);
         if (!rot_ok) {
             if (ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
             return false;
@@ -607,6 +612,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     a.col = r->col.p;
     if (sizeof(TACC) == 8) a.w = (const TACC *)r->w.p; else a.w = (const TACC *)r->w32.p;
     a.nDst = r->nDst;
+    a.dstLev = dl.lev; a.dstOff = dl.off;
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
     auto ksum = [](const std::vector<FieldDev> &v) { double k = 0; for (auto &f : v) k += f.nlev; return k; };
@@ -627,7 +633,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     if (!cols_vec.empty() || !cols_sca.empty()) {
         if (!cols_vec.empty()) {
             ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
-            piped_vec = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_vec);
+            piped_vec = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_vec, dl);
             if (!piped_vec && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
             if (!piped_vec && has_rot(cols_vec)) return false;
         }
@@ -635,7 +641,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
             piped_sca = true;
         } else if (!cols_sca.empty()) {
             ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
-            piped_sca = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_sca);
+            piped_sca = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_sca, dl);
             if (!piped_sca && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
             if (!piped_sca && has_rot(cols_sca)) return false;
         }
@@ -675,7 +681,15 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
 }
 
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
-                  int dst_dtype) {
+                  int dst_dtype, bool into_full) {
+    // destination layout: this rank's slab buffer, or (into_full) its rows inside a full-grid field
+    DstLayout dl{r->nDst, 0};
+    if (into_full) {
+        if (r->dst_stagger < MPRG_CENTER || r->dst_stagger > MPRG_CORNER) fail(38, "mprg_apply_into: the route has no full-grid destination");
+        const Target &tg = ctx->target[r->dst_stagger];
+        dl.lev = (int64_t)tg.ni * tg.nj;
+        dl.off = tg.slabOffset();
+    }
     std::vector<FieldDev> cols_vec, cols_sca, flat, planes, rotp;
     std::vector<std::pair<void *, void *>> pairs;  // every (u, v) destination pair with fused rotation requested
     std::vector<int32_t> pair_nlev;
@@ -688,6 +702,7 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
         FieldDev d{fields[f].src, fields[f].dst, fields[f].nlev, fields[f].epi_op, fields[f].epi_arg};
         if (d.epi_op == MPRG_EPI_ROT_V) fail(35, "mprg_apply: MPRG_EPI_ROT_V field %d has no MPRG_EPI_ROT_U before it", f);
         if (d.epi_op == MPRG_EPI_ROT_U) {
+            if (into_full) fail(39, "mprg_apply_into: wind pairs (fused rotation) are intermediates of the wind chain, not gathered fields");
             if (f + 1 >= nfields || fields[f + 1].epi_op != MPRG_EPI_ROT_V || fields[f + 1].nlev != d.nlev)
                 fail(35, "mprg_apply: MPRG_EPI_ROT_U field %d needs a following MPRG_EPI_ROT_V field of the same level count", f);
             if (!fields[f + 1].src || !fields[f + 1].dst) fail(32, "mprg_apply: field %d has a null buffer", f + 1);
@@ -715,14 +730,14 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
     }
     auto run = [&]() {
         if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F32) {
-            return acc_fp32_requested() ? launch_all<float, float, float>(ctx, r, cols_vec, cols_sca, flat, planes, rotp)
-                                        : launch_all<float, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+            return acc_fp32_requested() ? launch_all<float, float, float>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl)
+                                        : launch_all<float, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
         } else if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F64) {
-            return launch_all<float, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+            return launch_all<float, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
         } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F32) {
-            return launch_all<double, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+            return launch_all<double, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
         } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F64) {
-            return launch_all<double, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp);
+            return launch_all<double, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
         }
         fail(33, "mprg_apply: bad dtype %d/%d", src_dtype, dst_dtype);
     };

@@ -57,6 +57,11 @@ struct PipeArgs {
     const int32_t *tileUCols;       // [tileUPtr[nTiles]]
     const unsigned char *entrySlot; // [nnz]
     int64_t nDst;
+    // destination addressing: point t of level l of a field goes to dst[l * dstLev + dstOff + t].  A slab
+    // buffer has dstLev = nDst, dstOff = 0; writing straight into a full-grid [lev][nj][ni] field (this
+    // rank's own, or the writing rank's mapped over NVLink: the gather fused into the store) has
+    // dstLev = ni * nj, dstOff = first owned point.
+    int64_t dstLev, dstOff;
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
     int32_t nunits;
@@ -272,7 +277,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
 #pragma unroll
     for (int u = 0; u < STAGES - 1; ++u) issue(u);
 
-    const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.nDst;  // elements between a warp's consecutive level groups
+    const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
     for (int u = 0; u < a.nunits; ++u) {
         if (u > 0) __syncthreads();     // every warp has finished reading unit u-1: its buffer may be refilled
         issue(u + STAGES - 1);
@@ -306,7 +311,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
         if (!live) continue;
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
-        const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.nDst + t0 + lane;
+        const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane;
         TOUT *d = (TOUT *)ud.dst + dcol;
         const bool rotU = ROT && (ud.epi_op & kUnitRotU), rotV = ROT && (ud.epi_op & kUnitRotV);
         TOUT *du = (TOUT *)s_units[rotV ? u - 1 : u].dst + dcol;        // ROT: where the held zonal values go
@@ -341,8 +346,8 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                     uu = (uu + vv * rtana) * rdeni;
                     vv = (vv - uu * rsa) * rcai;
                     if (4 * g + k < Ln) {
-                        __stcs(du + (size_t)k * a.nDst, (TOUT)uu);
-                        __stcs(d + (size_t)k * a.nDst, (TOUT)vv);
+                        __stcs(du + (size_t)k * a.dstLev, (TOUT)uu);
+                        __stcs(d + (size_t)k * a.dstLev, (TOUT)vv);
                     }
                 }
                 continue;
@@ -353,7 +358,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             }
             // one coalesced 128-byte (fp32) streaming store per level
             if (4 * g + 3 < Ln) {
-                TOUT *d1 = d + a.nDst, *d2 = d1 + a.nDst, *d3 = d2 + a.nDst;
+                TOUT *d1 = d + a.dstLev, *d2 = d1 + a.dstLev, *d3 = d2 + a.dstLev;
                 __stcs(d, (TOUT)acc[0]);
                 __stcs(d1, (TOUT)acc[1]);
                 __stcs(d2, (TOUT)acc[2]);
@@ -361,7 +366,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (4 * g + k < Ln) __stcs(d + (size_t)k * a.nDst, (TOUT)acc[k]);
+                    if (4 * g + k < Ln) __stcs(d + (size_t)k * a.dstLev, (TOUT)acc[k]);
             }
         }
     }

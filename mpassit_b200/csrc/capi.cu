@@ -106,6 +106,8 @@ int mprg_finalize(mprg_ctx *ctx) {
     ctx->routes.clear();
     ctx->imported.clear();
     mprg::comm_destroy(ctx);
+    for (auto &kv : ctx->ipcOpen) cudaIpcCloseMemHandle(kv.second);
+    ctx->ipcOpen.clear();
     if (ctx->evDl) cudaEventDestroy(ctx->evDl);
     if (ctx->store_stream) cudaStreamDestroy(ctx->store_stream);
     for (int i = 0; i < mprg_ctx::kSlots; ++i) {
@@ -355,7 +357,7 @@ int mprg_route_import_csr(mprg_ctx *ctx, int64_t nSrc, int64_t nDst, const int32
 // ---------------------------------------------------------------------------
 static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
                        int src_dtype, int src_mem, void *const *dst, int dst_dtype, int dst_mem,
-                       const int32_t *epi_op, const double *epi_arg) {
+                       const int32_t *epi_op, const double *epi_arg, bool into_full = false) {
     if (!rh) fail(1, "mprg_apply: null route");
     if (nfields <= 0) return;
     if (!src || !dst || !nlev) fail(1, "mprg_apply: null argument");
@@ -367,7 +369,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
         std::vector<ApplyField> fl(nfields);
         for (int f = 0; f < nfields; ++f)
             fl[f] = ApplyField{src[f], dst[f], nlev[f], epi_op ? epi_op[f] : 0, epi_arg ? epi_arg[f] : 0.0};
-        apply_device(ctx, rh, fl.data(), nfields, src_dtype, dst_dtype);
+        apply_device(ctx, rh, fl.data(), nfields, src_dtype, dst_dtype, into_full);
     } else {
         // Pipelined staging: fields are cut into batches; a batch's H2D overlaps the kernels of the batch
         // before it and the D2H of the ones before that.  The slot ring persists across calls, so with
@@ -429,7 +431,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                 MPRG_CUDA(cudaEventRecord(ctx->evIn[slot], ctx->h2d_stream));
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evIn[slot], 0));
             }
-            apply_device(ctx, rh, fl.data(), (int)fl.size(), src_dtype, dst_dtype);
+            apply_device(ctx, rh, fl.data(), (int)fl.size(), src_dtype, dst_dtype, into_full);
             MPRG_CUDA(cudaEventRecord(ctx->evK[slot], ctx->stream));
             if (dst_mem == MPRG_HOST) {
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->evK[slot], 0));
@@ -461,6 +463,82 @@ int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *co
     Trace tr("apply", nfields, src_mem * 2 + dst_mem);
     MPRG_ENTER(ctx)
     apply_impl(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst, dst_dtype, dst_mem, epi_op, epi_arg);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_apply_into(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
+                    int src_dtype, int src_mem, void *const *dst_full, int dst_dtype, const int32_t *epi_op,
+                    const double *epi_arg) {
+    Trace tr("apply_into", nfields, src_mem);
+    MPRG_ENTER(ctx)
+    apply_impl(ctx, rh, nfields, src, nlev, src_dtype, src_mem, dst_full, dst_dtype, MPRG_DEVICE, epi_op, epi_arg, true);
+    MPRG_LEAVE(ctx)
+}
+
+// ---- CUDA IPC: the writing rank exports its full-grid output buffers, the others map them
+int mprg_ipc_export(mprg_ctx *ctx, const void *dev_ptr, void *handle64, size_t *offset) {
+    MPRG_ENTER(ctx)
+    if (!dev_ptr || !handle64 || !offset) fail(1, "mprg_ipc_export: null argument");
+    // the handle names the whole allocation: find its base (driver entry point, no libcuda link)
+    typedef int (*fn_range)(unsigned long long *, size_t *, unsigned long long);
+    static fn_range range = nullptr;
+    if (!range) {
+        cudaDriverEntryPointQueryResult q;
+        void *f = nullptr;
+        MPRG_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q));
+        if (!f || q != cudaDriverEntryPointSuccess) fail(87, "mprg_ipc_export: cuMemGetAddressRange unavailable");
+        range = (fn_range)f;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0) fail(88, "mprg_ipc_export: not a device allocation");
+    cudaIpcMemHandle_t h;
+    MPRG_CUDA(cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    *offset = (size_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_ipc_open(mprg_ctx *ctx, const void *handle64, size_t offset, void **peer_ptr) {
+    MPRG_ENTER(ctx)
+    if (!handle64 || !peer_ptr) fail(1, "mprg_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    // one mapping per exported allocation: several buffers usually share an allocation
+    std::string key((const char *)handle64, 64);
+    auto it = ctx->ipcOpen.find(key);
+    void *base = nullptr;
+    if (it != ctx->ipcOpen.end()) {
+        base = it->second;
+    } else {
+        MPRG_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipcOpen[key] = base;
+    }
+    *peer_ptr = (unsigned char *)base + offset;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_put_slab(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, const void *slab_dev, void *full_dev) {
+    MPRG_ENTER(ctx)
+    if (stagger < 0 || stagger > MPRG_CORNER || !ctx->target[stagger].set) fail(83, "mprg_put_slab: stagger %d not set", stagger);
+    const Target &tg = ctx->target[stagger];
+    const size_t esz = dtype == MPRG_F32 ? 4 : 8;
+    const int64_t nFull = (int64_t)tg.ni * tg.nj, nMine = tg.nSlab();
+    if (nMine > 0 && nlev > 0) {
+        if (!slab_dev || !full_dev) fail(1, "mprg_put_slab: null argument");
+        MPRG_CUDA(cudaMemcpy2DAsync((unsigned char *)full_dev + (size_t)tg.slabOffset() * esz, (size_t)nFull * esz, slab_dev,
+                                    (size_t)nMine * esz, (size_t)nMine * esz, (size_t)nlev, cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
+    }
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_ipc_close_all(mprg_ctx *ctx) {
+    MPRG_ENTER(ctx)
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &kv : ctx->ipcOpen) cudaIpcCloseMemHandle(kv.second);
+    ctx->ipcOpen.clear();
     MPRG_LEAVE(ctx)
 }
 

@@ -188,6 +188,7 @@ struct mprg_ctx {
     unsigned slotCursor = 0;
     cudaEvent_t evDl = nullptr;           // mprg_download ordering
     mprg::DevBuf<unsigned char> userScratch[8];  // mprg_scratch slots
+    std::map<std::string, void *> ipcOpen;  // peer allocations mapped with mprg_ipc_open (handle bytes -> base)
     void *nccl = nullptr;                 // ncclComm_t
     void *ncclLib = nullptr;
     // optional per-launch profiling of the apply kernels (mprg_profile_*)
@@ -250,7 +251,7 @@ struct ApplyField {
     double epi_arg;
 };
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
-                  int dst_dtype);
+                  int dst_dtype, bool into_full = false);
 void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype);
 void rotation_constants(mprg_ctx *ctx, int64_t n);  // fills ctx->rotc from ctx->cosa / ctx->sina
 

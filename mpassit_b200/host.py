@@ -58,7 +58,8 @@ class InterpIO(C.Structure):
                 ("n_hist_2d", C.c_int32), ("hist_2d", C.POINTER(Field)),
                 ("n_hist_3d", C.c_int32), ("hist_3d", C.POINTER(Field)),
                 ("n_soil", C.c_int32), ("soil", C.POINTER(Field)),
-                ("ter", C.c_void_p), ("hgt", C.c_void_p), ("u_stag", C.c_void_p), ("v_stag", C.c_void_p)]
+                ("ter", C.c_void_p), ("hgt", C.c_void_p), ("u_stag", C.c_void_p), ("v_stag", C.c_void_p),
+                ("dst_full", C.c_int32)]
 
 
 _lib = None
@@ -202,6 +203,8 @@ class FieldSpec:
 def _ptr(x):
     if x is None:
         return None
+    if isinstance(x, int):  # raw device address (a mapped peer buffer)
+        return x
     if type(x).__module__.startswith("torch"):
         return x.data_ptr()
     return x.ctypes.data
@@ -219,7 +222,7 @@ def _farr(specs):
 
 
 def interp_data(rg, cfg: Config, *, diag=(), hist_2d=(), hist_3d=(), soil=(), ter=None, hgt=None, u_stag=None,
-                v_stag=None, nz=0, src_dtype=_l.F32, dst_dtype=_l.F32, mem=_l.HOST) -> InterpIO:
+                v_stag=None, nz=0, src_dtype=_l.F32, dst_dtype=_l.F32, mem=_l.HOST, dst_full=False) -> InterpIO:
     """interp_data (interp.F90:92) on Regridder ``rg``; field lists are FieldSpec sequences in
     var-list order.  Returns the InterpIO (with the regrid class of every field filled in)."""
     io = InterpIO()
@@ -230,6 +233,7 @@ def interp_data(rg, cfg: Config, *, diag=(), hist_2d=(), hist_3d=(), soil=(), te
     io.n_hist_3d, io.hist_3d = len(hist_3d), keep[2]
     io.n_soil, io.soil = len(soil), keep[3]
     io.ter, io.hgt, io.u_stag, io.v_stag = _ptr(ter), _ptr(hgt), _ptr(u_stag), _ptr(v_stag)
+    io.dst_full = int(bool(dst_full))
     e = _err()
     rc = load().mpassit_interp_data(rg.ctx, C.byref(cfg), C.byref(io), e, len(e))
     if rc:

@@ -44,9 +44,16 @@ struct Batch {
     bool empty() const { return src.empty(); }
 };
 
-void run(mprg_ctx *ctx, mprg_route *rh, Batch &b, int sdt, int smem, int ddt, int dmem, const char *where) {
+void run(mprg_ctx *ctx, mprg_route *rh, Batch &b, int sdt, int smem, int ddt, int dmem, const char *where,
+         bool into_full = false) {
     if (b.empty()) return;
     const int32_t n = (int32_t)b.src.size();
+    if (into_full) {
+        ck(ctx, mprg_apply_into(ctx, rh, n, b.src.data(), b.nlev.data(), sdt, smem, b.dst.data(), ddt,
+                                b.any_epi ? b.epi.data() : nullptr, b.any_epi ? b.earg.data() : nullptr), where);
+        b = Batch();
+        return;
+    }
     ck(ctx, b.any_epi ? mprg_apply_ex(ctx, rh, n, b.src.data(), b.nlev.data(), sdt, smem, b.dst.data(), ddt, dmem,
                                       b.epi.data(), b.earg.data())
                       : mprg_apply(ctx, rh, n, b.src.data(), b.nlev.data(), sdt, smem, b.dst.data(), ddt, dmem),
@@ -94,6 +101,11 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
     // its own stream); interp_data as a whole stays blocking, like the reference's.
     const int was_async = mprg_get_async(ctx);
     const bool host_pass = io->mem == MPRG_HOST;
+    const bool into = io->dst_full != 0;  // outputs are full-grid fields (own or mapped): gather fused into the store
+    if (into && host_pass) {
+        if (err && errlen) std::snprintf(err, errlen, "IN interp_data: dst_full needs device buffers");
+        return 1;
+    }
     if (host_pass) mprg_set_async(ctx, 1);
     try {
         int32_t do_u = 0, do_v = 0, u10 = -1, v10 = -1;
@@ -119,7 +131,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
         // 10-m winds are rotated after the bundle regrid (interp.F90:138-139).  With host buffers they are
         // regridded into device scratch, rotated there and downloaded, so nothing waits on a round trip.
         const bool rot10 = have_diag && u10 >= 0 && v10 >= 0 && rotate;
-        const bool rot10_dev = rot10 && host_pass;
+        const bool rot10_dev = rot10 && (host_pass || into);
         if (have_diag)
             for (int i = 0; i < io->n_diag; ++i)
                 if (!(rot10_dev && (i == u10 || i == v10)))
@@ -142,12 +154,17 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             int32_t n2[2] = {1, 1};
             ck(ctx, mprg_apply(ctx, rh, 2, s2, n2, sdt, mem, d2, ddt, MPRG_DEVICE), "FieldBundleRegrid");
             ck(ctx, mprg_rotate_winds(ctx, du, dv, 1, ddt, MPRG_DEVICE), "rotate_winds_cgrid");
-            ck(ctx, mprg_download(ctx, du, io->diag[u10].dst, bytes), "download");
-            ck(ctx, mprg_download(ctx, dv, io->diag[v10].dst, bytes), "download");
+            if (into) {
+                ck(ctx, mprg_put_slab(ctx, MPRG_CENTER, 1, ddt, du, io->diag[u10].dst), "put_slab");
+                ck(ctx, mprg_put_slab(ctx, MPRG_CENTER, 1, ddt, dv, io->diag[v10].dst), "put_slab");
+            } else {
+                ck(ctx, mprg_download(ctx, du, io->diag[u10].dst, bytes), "download");
+                ck(ctx, mprg_download(ctx, dv, io->diag[v10].dst, bytes), "download");
+            }
         };
         if (have_diag && !cfg->interp_hist) {
             mprg_route *rh = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
-            run(ctx, rh, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid");
+            run(ctx, rh, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
             finish_diag(rh);
         }
 
@@ -202,7 +219,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             // rotate_winds_cgrid (interp.F90:291-293) is fused into the store of the (u, v) pair
             const bool fuse_rot = fu && fv && rotate && fu->nlev == fv->nlev;
             const int op_u = fuse_rot ? MPRG_EPI_ROT_U : MPRG_EPI_NONE, op_v = fuse_rot ? MPRG_EPI_ROT_V : MPRG_EPI_NONE;
-            const bool winds_in_batch = (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR && halo_is_center;
+            const bool winds_in_batch = (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR && halo_is_center && !into;
 
             // one stacked apply for everything on the bilinear element->CENTER route:
             // 2d_patch (:207-221), hgt (:226-238), 3d_nz (:240-254), 3d_nzp1 (:331-347)
@@ -212,7 +229,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                     b = diagBatch;
                 } else if (have_diag) {  // cannot happen with the reference's method sequence; kept for safety
                     mprg_route *rd = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
-                    run(ctx, rd, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                    run(ctx, rd, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
                     finish_diag(rd);
                 }
                 for (int i = 0; i < io->n_hist_2d; ++i)
@@ -227,7 +244,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                         b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
                 if (!b.empty() || (have_diag && m_bil == MPRG_BILINEAR)) {
                     mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
-                    run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                    run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
                     if (have_diag && m_bil == MPRG_BILINEAR) finish_diag(rh);
                 }
             }
@@ -246,12 +263,14 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 if (fu && io->u_stag) {  // interp.F90:295-311
                     mprg_route *ru = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE1, "FieldRegridStore");
                     const void *s = d_um; void *d = io->u_stag; int32_t nl = fu->nlev;
-                    ck(ctx, mprg_apply(ctx, ru, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                    ck(ctx, into ? mprg_apply_into(ctx, ru, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, nullptr, nullptr)
+                                 : mprg_apply(ctx, ru, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
                 }
                 if (fv && io->v_stag) {  // interp.F90:313-328
                     mprg_route *rv = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE2, "FieldRegridStore");
                     const void *s = d_vm; void *d = io->v_stag; int32_t nl = fv->nlev;
-                    ck(ctx, mprg_apply(ctx, rv, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                    ck(ctx, into ? mprg_apply_into(ctx, rv, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, nullptr, nullptr)
+                                 : mprg_apply(ctx, rv, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
                 }
             }
 
@@ -262,7 +281,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 for (int i = 0; i < io->n_hist_3d; ++i)
                     if (io->hist_3d[i].klass == MPASSIT_CLASS_3D_VERT)
                         b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
             }
             // 2d_cons bundle, interp.F90:368-416 (bundle and per-field paths apply the same matrix)
             if (n2c > 0) {
@@ -271,7 +290,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 Batch b;
                 for (int i = 0; i < io->n_hist_2d; ++i)
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_CONS) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
             }
             // 2d_nstd bundle, interp.F90:418-434
             if (n2n > 0) {
@@ -280,7 +299,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 Batch b;
                 for (int i = 0; i < io->n_hist_2d; ++i)
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_NSTD) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
             }
             // soil bundle: whatever `method` holds now, interp.F90:436-447
             if (io->n_soil > 0) {
@@ -288,7 +307,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 mprg_route *rh = store(m_soil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
                 Batch b;
                 for (int i = 0; i < io->n_soil; ++i) b.add(io->soil[i].src, io->soil[i].dst, io->soil[i].nlev);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid");
+                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
             }
         }
     } catch (const Fail &f) {

@@ -27,7 +27,7 @@ EXPORTS = [
     "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize", "mprg_set_async", "mprg_get_async", "mprg_download",
     "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_get_slab", "mprg_store",
     "mprg_release", "mprg_clear_routes", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
-    "mprg_apply", "mprg_apply_ex", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
+    "mprg_apply", "mprg_apply_ex", "mprg_apply_into", "mprg_put_slab", "mprg_ipc_export", "mprg_ipc_open", "mprg_ipc_close_all", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
     "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
     "mprg_profile_reset", "mprg_route_src_referenced",
 ]
@@ -84,6 +84,11 @@ def load() -> C.CDLL:
     L.mprg_comm_init.argtypes = [vp, vp]
     L.mprg_post_midlevels.argtypes = [vp, C.c_int, i32, C.c_int, C.c_int, vp, vp]
     L.mprg_post_ptop.argtypes = [vp, C.c_int, i32, C.c_int, C.c_int, vp, vp, vp]
+    L.mprg_apply_into.argtypes = [vp, vp, i32, pp, C.POINTER(i32), C.c_int, C.c_int, pp, C.c_int, C.POINTER(i32), C.POINTER(dbl)]
+    L.mprg_put_slab.argtypes = [vp, C.c_int, i32, C.c_int, vp, vp]
+    L.mprg_ipc_export.argtypes = [vp, vp, vp, vp]
+    L.mprg_ipc_open.argtypes = [vp, vp, C.c_size_t, vp]
+    L.mprg_ipc_close_all.argtypes = [vp]
     L.mprg_io_bytes.argtypes = [vp, vp, vp]
     L.mprg_set_async.argtypes = [vp, C.c_int]
     L.mprg_get_async.argtypes = [vp]

@@ -45,6 +45,8 @@ def _dtype_code(x) -> int:
 
 
 def _ptr(x) -> int:
+    if isinstance(x, int):       # a raw device address (e.g. the writing rank's buffer mapped with ipc_open)
+        return x
     if _is_torch(x):
         if not x.is_contiguous():
             raise ValueError("device fields must be contiguous")
@@ -232,6 +234,39 @@ class Regridder:
             ea = (C.c_double * n)(*[float(v) for v in (epi_arg or [0.0] * n)])
             rc = self.L.mprg_apply_ex(self.ctx, route.handle, n, sp, nl, s_dt, s_mem, dp, d_dt, d_mem, eo, ea)
         self._ck(rc)
+
+    def apply_into(self, route: Route, srcs: Sequence, dsts_full: Sequence, nlev: Sequence[int], dst_dtype: int = F32,
+                   epi_op: Sequence[int] | None = None, epi_arg: Sequence[float] | None = None) -> None:
+        """Like apply, but dsts_full[f] is the FULL [nlev][nj][ni] field (a CUDA tensor of this process or a
+        raw address from ipc_open) and this rank writes only its own rows: the gather fused into the store."""
+        n = len(srcs)
+        if n == 0:
+            return
+        s_mem = DEVICE if _is_torch(srcs[0]) else HOST
+        sp = (C.c_void_p * n)(*[_ptr(s) for s in srcs])
+        dp = (C.c_void_p * n)(*[_ptr(d) for d in dsts_full])
+        nl = (C.c_int32 * n)(*[int(v) for v in nlev])
+        eo = (C.c_int32 * n)(*[int(v) for v in epi_op]) if epi_op is not None else None
+        ea = (C.c_double * n)(*[float(v) for v in (epi_arg or [0.0] * n)]) if epi_op is not None else None
+        self._ck(self.L.mprg_apply_into(self.ctx, route.handle, n, sp, nl, _dtype_code(srcs[0]), s_mem, dp, dst_dtype, eo, ea))
+
+    def put_slab(self, stagger: int, nlev: int, slab, full, dtype: int = F32) -> None:
+        self._ck(self.L.mprg_put_slab(self.ctx, int(stagger), int(nlev), dtype, _ptr(slab), _ptr(full)))
+
+    def ipc_export(self, buf) -> tuple[bytes, int]:
+        """(64-byte handle, offset) of a device buffer of this process, for the other ranks' ipc_open."""
+        h = C.create_string_buffer(64)
+        off = C.c_size_t()
+        self._ck(self.L.mprg_ipc_export(self.ctx, _ptr(buf), h, C.byref(off)))
+        return h.raw, off.value
+
+    def ipc_open(self, handle: bytes, offset: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.mprg_ipc_open(self.ctx, C.create_string_buffer(handle, 64), offset, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close_all(self) -> None:
+        self._ck(self.L.mprg_ipc_close_all(self.ctx))
 
     # ---- winds ----------------------------------------------------------
     def set_rotation(self, cosa, sina) -> None:

@@ -182,19 +182,57 @@ def make_fields(wl: Workload, device="cuda", pinned_host: bool = False, rg=None)
 
 def _np(x):
     """numpy view of a (pinned) host torch tensor, or the tensor itself if on device."""
+    if isinstance(x, int):
+        return x
     if type(x).__module__.startswith("torch") and not x.is_cuda:
         return x.numpy()
     return x
 
 
-def run_interp(rg, wl: Workload, F: dict, mem: int):
-    """One interp_data pass (interp.F90:92) through the host mirror + C ABI."""
+def run_interp(rg, wl: Workload, F: dict, mem: int, dst_full: bool = False):
+    """One interp_data pass (interp.F90:92) through the host mirror + C ABI.  dst_full: the destinations in
+    F are full-grid fields (the writing rank's, own or mapped) and every rank stores its rows into them."""
     def conv(specs):
         return [host.FieldSpec(s.name, s.target_name, s.nlev, _np(s.src), _np(s.dst)) for s in specs]
 
     return host.interp_data(rg, wl.cfg, diag=conv(F["diag"]), hist_2d=conv(F["hist_2d"]), hist_3d=conv(F["hist_3d"]),
                             soil=conv(F["soil"]), ter=_np(F["ter"]), hgt=_np(F["hgt"]), u_stag=_np(F["u_stag"]),
-                            v_stag=_np(F["v_stag"]), nz=wl.nz, mem=mem)
+                            v_stag=_np(F["v_stag"]), nz=wl.nz, mem=mem, dst_full=dst_full)
+
+
+# ---- fused gather: full-grid outputs on the writing rank, mapped into the other ranks with CUDA IPC --------
+def full_outputs(wl: Workload, device) -> dict:
+    """Full-grid output fields [nlev][nj*ni] of one pass (allocated on the writing rank)."""
+    import torch
+
+    nM, nU, nV = wl.n_mass, wl.grids["U"][0].size, wl.grids["V"][0].size
+    out = {g: [torch.empty((wl.levels_of(g, nm), nM), dtype=torch.float32, device=device) for nm, _ in wl.lists[g]]
+           for g in ("diag", "hist_2d", "hist_3d", "soil")}
+    out["hgt"] = torch.empty((1, nM), dtype=torch.float32, device=device)
+    out["u_stag"] = torch.empty((wl.nz, nU), dtype=torch.float32, device=device)
+    out["v_stag"] = torch.empty((wl.nz, nV), dtype=torch.float32, device=device)
+    return out
+
+
+def export_full(rg, full: dict) -> dict:
+    """Picklable (handle, offset) pairs for every field of `full` (mprg_ipc_export)."""
+    return {k: ([rg.ipc_export(t) for t in v] if isinstance(v, list) else rg.ipc_export(v)) for k, v in full.items()}
+
+
+def open_full(rg, exported: dict) -> dict:
+    """Device addresses of the writing rank's fields in this process (mprg_ipc_open)."""
+    return {k: ([rg.ipc_open(*h) for h in v] if isinstance(v, list) else rg.ipc_open(*v)) for k, v in exported.items()}
+
+
+def with_destinations(F: dict, dst: dict) -> dict:
+    """The field set F with every destination replaced by the matching entry of `dst`."""
+    out = {}
+    for g in ("diag", "hist_2d", "hist_3d", "soil"):
+        out[g] = [host.FieldSpec(s.name, s.target_name, s.nlev, s.src, d) for s, d in zip(F[g], dst[g])]
+    out["ter"] = F["ter"]
+    for k in ("hgt", "u_stag", "v_stag"):
+        out[k] = dst[k]
+    return out
 
 
 def io_bytes(wl: Workload, F: dict) -> tuple[int, int]:

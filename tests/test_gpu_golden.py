@@ -250,3 +250,58 @@ def test_more_ranks_than_rows_gives_empty_slabs(engine_lib, g):
     for j0, p in pieces:
         scale = np.abs(want).max()
         assert np.abs(p - want[:, j0:j0 + p.shape[1]]).max() <= RTOL * scale
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_apply_into_full_fields_fuses_the_gather(engine_lib, g, nranks):
+    """mprg_apply_into: every rank stores its rows straight into the FULL field (here one device buffer
+    shared by ranks emulated one after another; on real multi-GPU runs the writing rank's buffer mapped with
+    CUDA IPC).  After all ranks ran, the full fields equal slab apply + gather, bit for bit, for the column
+    kernel (aligned / unaligned levels), the flat kernel (2-D, short columns) and the stagger (planes) kernel."""
+    import torch
+
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import Regridder
+
+    nj, ni = g["lat_M"].shape
+    nC = g["lonCell"].size
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(3)
+    srcs = {nl: torch.randn((nC, nl), generator=gen, device="cuda") for nl in (1, 4, 60, 61)}
+    um = torch.randn((6, nj * ni), generator=gen, device="cuda")   # mass-point wind on the full CENTER grid
+
+    def one_rank_reference():
+        r = Regridder(device=0)
+        _load(r, g)
+        out = {}
+        rt = r.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+        for nl, s in srcs.items():
+            d = torch.empty((nl, nj * ni), device="cuda")
+            r.apply(rt, [s], [d], nlev=[nl])
+            out[nl] = d
+        rs = r.store(l.BILINEAR, l.SRC_GRID_CENTER, l.EDGE1)
+        d = torch.empty((6, g["lat_U"].size), device="cuda")
+        r.apply(rs, [um], [d], nlev=[6])
+        out["U"] = d
+        r.synchronize()
+        r.close()
+        return out
+
+    want = one_rank_reference()
+    full = {nl: torch.full((nl, nj * ni), float("nan"), device="cuda") for nl in srcs}
+    fullU = torch.full((6, g["lat_U"].size), float("nan"), device="cuda")
+    for rank in range(nranks):
+        r = Regridder(device=0, rank=rank, nranks=nranks)
+        _load(r, g)
+        rt = r.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+        r.apply_into(rt, [srcs[60], srcs[61], srcs[1], srcs[4]], [full[60], full[61], full[1], full[4]], nlev=[60, 61, 1, 4])
+        # the stagger reads this rank's CENTER_HALO rows of the mass-point field
+        h0, h1 = r.slab(l.CENTER_HALO)
+        halo = um.reshape(6, nj, ni)[:, h0:h1].contiguous()
+        rs = r.store(l.BILINEAR, l.SRC_GRID_CENTER, l.EDGE1)
+        r.apply_into(rs, [halo], [fullU], nlev=[6])
+        r.synchronize()
+        r.close()
+    for nl in srcs:
+        assert torch.equal(full[nl], want[nl]), nl
+    assert torch.equal(fullU, want["U"])

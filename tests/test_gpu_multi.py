@@ -53,6 +53,22 @@ def _worker(rank, world, port, q):
             got[nm] = full
         rg.synchronize()
         dist.barrier()
+        # ---- the same pass with the gather fused into the store: rank 0 owns full-grid fields, rank 1 maps
+        #      them with CUDA IPC and its apply kernels write their rows straight into rank 0's memory
+        full = workload.full_outputs(wl, "cuda") if rank == 0 else None
+        if rank == 0:
+            for v in full.values():
+                for t in (v if isinstance(v, list) else [v]):
+                    t.fill_(float("nan"))
+            torch.cuda.synchronize()
+        box = [workload.export_full(rg, full) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        dst = full if rank == 0 else workload.open_full(rg, box[0])
+        workload.run_interp(rg, wl, workload.with_destinations(F["dev"], dst), l.DEVICE, dst_full=True)
+        rg.synchronize()
+        dist.barrier()
+        if rank != 0:
+            rg.ipc_close_all()
         if rank == 0:
             # the same pass on one rank, same device, same synthetic inputs (seeded per field)
             r1 = Regridder(device=0)
@@ -63,6 +79,14 @@ def _worker(rank, world, port, q):
             want = {nm: next(x for x in F1["dev"][grp] if x.name == nm).dst for nm, (grp, _) in names.items()}
             want["U"], want["V"] = F1["dev"]["u_stag"], F1["dev"]["v_stag"]
             res = {nm: bool(torch.equal(got[nm], want[nm])) and not bool(torch.isnan(got[nm]).any()) for nm in want}
+            # fused gather: every field of the pass
+            for grp in ("diag", "hist_2d", "hist_3d", "soil"):
+                for s1, t in zip(F1["dev"][grp], full[grp]):
+                    if s1.name.startswith("uReconstruct"):
+                        continue
+                    res["fused:" + s1.name] = bool(torch.equal(t, s1.dst))
+            for k in ("hgt", "u_stag", "v_stag"):
+                res["fused:" + k] = bool(torch.equal(full[k], F1["dev"][k]))
             q.put(res)
             r1.close()
         dist.barrier()
