@@ -558,15 +558,14 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
                                                                    mm.p, mm.p + 1, cnt.p, nullptr, nullptr, nullptr);
     ctx->launches++;
     int32_t h[2] = {0, 0};
-    MPRG_CUDA(cudaMemcpyAsync(h, mm.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    peek(ctx, h, mm.p, sizeof h);
     r->tileEntriesMax = h[0];
     r->tileUniqMax = h[1];
     if (h[0] > kPipeCap) return;  // no schedule: register-gather kernels only
     r->tileUPtr.alloc(tiles + 1);
     scan_counts(ctx, cnt.p, r->tileUPtr.p, (int64_t)tiles + 1);
     int32_t total = 0;
-    MPRG_CUDA(cudaMemcpy(&total, r->tileUPtr.p + tiles, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    peek(ctx, &total, r->tileUPtr.p + tiles, sizeof(int32_t));
     r->tileUCols.alloc(total > 0 ? total : 1);
     r->entrySlot.alloc(r->nnz);
     k_tile_schedule<true><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
@@ -882,7 +881,7 @@ void post_ptop_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const v
         memcpy(&b, &init[k], 8);
         hk[k] = b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
     }
-    MPRG_CUDA(cudaMemcpyAsync(keys.p, hk, sizeof hk, cudaMemcpyHostToDevice, ctx->stream));
+    poke(ctx, keys.p, hk, sizeof hk);
     if (n > 0 && nlev > 0) {
         const unsigned g = (unsigned)((n + 255) / 256);
         if (dtype == MPRG_F32) k_ptop<float><<<g, 256, 0, ctx->stream>>>((const float *)x, n, nlev, keys.p);

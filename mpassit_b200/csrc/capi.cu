@@ -81,6 +81,7 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
         MPRG_CUDA(cudaEventCreate(&c->ev0));
         MPRG_CUDA(cudaEventCreate(&c->ev1));
         MPRG_CUDA(cudaEventCreateWithFlags(&c->evDl, cudaEventDisableTiming));
+        MPRG_CUDA(cudaMallocHost(&c->peekBuf, 256));
         if (const char *e = getenv("MPASSIT_GPU_ASYNC")) c->async = atoi(e) != 0;
         for (int i = 0; i < mprg_ctx::kSlots; ++i) {
             MPRG_CUDA(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
@@ -109,6 +110,7 @@ int mprg_finalize(mprg_ctx *ctx) {
     for (auto &kv : ctx->ipcOpen) cudaIpcCloseMemHandle(kv.second);
     ctx->ipcOpen.clear();
     if (ctx->evDl) cudaEventDestroy(ctx->evDl);
+    if (ctx->peekBuf) cudaFreeHost(ctx->peekBuf);
     if (ctx->store_stream) cudaStreamDestroy(ctx->store_stream);
     for (int i = 0; i < mprg_ctx::kSlots; ++i) {
         if (ctx->evIn[i]) cudaEventDestroy(ctx->evIn[i]);

@@ -188,6 +188,7 @@ struct mprg_ctx {
     unsigned slotCursor = 0;
     cudaEvent_t evDl = nullptr;           // mprg_download ordering
     mprg::DevBuf<unsigned char> userScratch[8];  // mprg_scratch slots
+    void *peekBuf = nullptr;              // pinned, device-visible: scalar readbacks without a copy engine (peek)
     std::map<std::string, void *> ipcOpen;  // peer allocations mapped with mprg_ipc_open (handle bytes -> base)
     void *nccl = nullptr;                 // ncclComm_t
     void *ncclLib = nullptr;
@@ -208,6 +209,14 @@ inline void para_range(int32_t n, int nprocs, int irank, int32_t *begin, int32_t
     *begin = ista;
     *end = iend;
 }
+
+// Scalars move between host and device WITHOUT a copy engine: during a host-buffer pass the DMA queues
+// are busy with 100-MB field transfers and a 4-byte cudaMemcpy would wait behind them (milliseconds per
+// readback, a dozen readbacks per weight generation).  peek: a one-block kernel stores the words into
+// pinned, device-visible memory, then the stream is synchronised.  poke: the bytes travel as kernel
+// parameters.  bytes must be a multiple of 4, at most 64.  (locate.cu)
+void peek(mprg_ctx *ctx, void *host, const void *dev, size_t bytes);
+void poke(mprg_ctx *ctx, void *dev, const void *host, size_t bytes);
 
 // bvh.cu
 void bvh_build_points(mprg_ctx *ctx, const double *xyz_dev, int32_t n, Bvh &out, DevBuf<double> *sortedXyz);

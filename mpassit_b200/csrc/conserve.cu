@@ -157,7 +157,7 @@ static void conserve_launch(mprg_ctx *ctx, mprg_route *r, const BvhView &v, cons
     auto finish_sizes = [&]() {
         scan_counts(ctx, cnt.p, r->rowptr.p, n + 1);
         int32_t nnz = 0;
-        MPRG_CUDA(cudaMemcpy(&nnz, r->rowptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        peek(ctx, &nnz, r->rowptr.p + n, sizeof(int32_t));
         r->nnz = nnz;
         r->col.alloc(nnz > 0 ? nnz : 1);
         r->w.alloc(nnz > 0 ? nnz : 1);
@@ -170,9 +170,9 @@ static void conserve_launch(mprg_ctx *ctx, mprg_route *r, const BvhView &v, cons
                                                            cnt.p, nullptr, ecol.p, ew.p, flag.p);
         ctx->launches++;
         MPRG_CUDA(cudaGetLastError());
-        int32_t over = 0;
-        MPRG_CUDA(cudaMemcpyAsync(&over, flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         finish_sizes();  // synchronises the stream
+        int32_t over = 0;
+        peek(ctx, &over, flag.p, sizeof(int32_t));
         if (!over) {
             k_compact_ell<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, r->rowptr.p, ecol.p, ew.p, r->col.p, r->w.p);
             ctx->launches++;

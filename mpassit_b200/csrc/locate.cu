@@ -11,6 +11,31 @@
 
 namespace mprg {
 
+// ---- scalar traffic without a copy engine (common.cuh) -------------------------
+struct PokeWords { uint32_t w[16]; };
+__global__ void k_peek(const uint32_t *__restrict__ dev, uint32_t *host_visible, int nwords) {
+    if ((int)threadIdx.x < nwords) host_visible[threadIdx.x] = dev[threadIdx.x];
+}
+__global__ void k_poke(uint32_t *dev, PokeWords p, int nwords) {
+    if ((int)threadIdx.x < nwords) dev[threadIdx.x] = p.w[threadIdx.x];
+}
+void peek(mprg_ctx *ctx, void *host, const void *dev, size_t bytes) {
+    if (bytes == 0) return;
+    if (bytes % 4 || bytes > 64) fail(95, "peek: %zu bytes", bytes);
+    k_peek<<<1, 32, 0, ctx->stream>>>((const uint32_t *)dev, (uint32_t *)ctx->peekBuf, (int)(bytes / 4));
+    MPRG_CUDA(cudaGetLastError());
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(host, ctx->peekBuf, bytes);
+}
+void poke(mprg_ctx *ctx, void *dev, const void *host, size_t bytes) {
+    if (bytes == 0) return;
+    if (bytes % 4 || bytes > 64) fail(95, "poke: %zu bytes", bytes);
+    PokeWords p;
+    memcpy(p.w, host, bytes);
+    k_poke<<<1, 32, 0, ctx->stream>>>((uint32_t *)dev, p, (int)(bytes / 4));
+    MPRG_CUDA(cudaGetLastError());
+}
+
 // ---- NEAREST_STOD (interp.F90:420-431; soil bundle :436-443) ----------------
 __global__ void __launch_bounds__(128)
 k_nearest(BvhView bvh, const double *__restrict__ sortedXyz, const double *__restrict__ dstXyz, int64_t nDst,
@@ -114,7 +139,7 @@ void store_bilinear_element(mprg_ctx *ctx, mprg_route *r) {
     r->rowptr.alloc(n + 1);
     scan_counts(ctx, cnt.p, r->rowptr.p, n + 1);
     int32_t nnz = 0;
-    MPRG_CUDA(cudaMemcpy(&nnz, r->rowptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    peek(ctx, &nnz, r->rowptr.p + n, sizeof(int32_t));
     r->nnz = nnz;
     r->col.alloc(nnz > 0 ? nnz : 1);
     r->w.alloc(nnz > 0 ? nnz : 1);
@@ -161,7 +186,7 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
     DevBuf<int32_t> mm(2);
     int32_t init[2] = {0, 0x7fffffff};
     MPRG_CUDA(cudaMemsetAsync(un.p, 0, sizeof(unsigned long long), ctx->stream));
-    MPRG_CUDA(cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    poke(ctx, mm.p, init, sizeof init);
     if (r->nDst > 0) {
         k_route_stats<<<(unsigned)((r->nDst + 255) / 256), 256, 0, ctx->stream>>>(r->nDst, r->rowptr.p, un.p, mm.p,
                                                                                  mm.p + 1);
@@ -174,7 +199,7 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
     }
     DevBuf<unsigned long long> nref(3);
     const unsigned long long nref0[3] = {0ULL, ~0ULL, 0ULL};
-    MPRG_CUDA(cudaMemcpyAsync(nref.p, nref0, sizeof nref0, cudaMemcpyHostToDevice, ctx->stream));
+    poke(ctx, nref.p, nref0, sizeof nref0);
     DevBuf<unsigned char> mark;
     if (r->nnz > 0 && r->nSrc > 0) {
         mark.alloc(r->nSrc);
@@ -184,11 +209,10 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
         ctx->launches += 2;
     }
     unsigned long long hun = 0, href[3] = {0, 0, 0};
-    MPRG_CUDA(cudaMemcpyAsync(href, nref.p, sizeof href, cudaMemcpyDeviceToHost, ctx->stream));
     int32_t hmm[2] = {0, 0};
-    MPRG_CUDA(cudaMemcpyAsync(&hun, un.p, sizeof hun, cudaMemcpyDeviceToHost, ctx->stream));
-    MPRG_CUDA(cudaMemcpyAsync(hmm, mm.p, sizeof hmm, cudaMemcpyDeviceToHost, ctx->stream));
-    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    peek(ctx, href, nref.p, sizeof href);
+    peek(ctx, &hun, un.p, sizeof hun);
+    peek(ctx, hmm, mm.p, sizeof hmm);
     r->nUnmapped = (int64_t)hun;
     r->nSrcRef = (int64_t)href[0];
     // contiguous id range that holds every referenced source: host-buffer applies upload only this range

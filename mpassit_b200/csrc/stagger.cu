@@ -165,7 +165,7 @@ void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r) {
     r->rowptr.alloc(n + 1);
     scan_counts(ctx, cnt.p, r->rowptr.p, n + 1);
     int32_t nnz = 0;
-    MPRG_CUDA(cudaMemcpy(&nnz, r->rowptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    peek(ctx, &nnz, r->rowptr.p + n, sizeof(int32_t));
     r->nnz = nnz;
     r->col.alloc(nnz > 0 ? nnz : 1);
     r->w.alloc(nnz > 0 ? nnz : 1);
@@ -247,7 +247,7 @@ void store_bilinear_node(mprg_ctx *ctx, mprg_route *r) {
     r->rowptr.alloc(n + 1);
     scan_counts(ctx, cnt.p, r->rowptr.p, n + 1);
     int32_t nnz = 0;
-    MPRG_CUDA(cudaMemcpy(&nnz, r->rowptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    peek(ctx, &nnz, r->rowptr.p + n, sizeof(int32_t));
     r->nnz = nnz;
     r->col.alloc(nnz > 0 ? nnz : 1);
     r->w.alloc(nnz > 0 ? nnz : 1);
