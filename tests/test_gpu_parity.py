@@ -279,3 +279,34 @@ def test_wrf_post_ops_match_the_writer_formulas(rg, orc):
     mx, mn = rg.post_ptop(small, nz)
     assert mx == 5.0 and mn == float("inf") and min(mx, mn) == po.p_top(small)
     r.release()
+
+
+def test_new_entry_points_report_errors(rg, orc):
+    """apply_into / ipc / rotation epilogues: misuse is an error code + message, never a crash."""
+    import torch
+
+    from mpassit_b200 import lib as l
+
+    mesh, lon, lat, *_ = _setup(rg, orc, "global_icos_jit")
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    n = lon.size
+    u = torch.zeros((mesh.nCells, 8), device="cuda")
+    full = torch.zeros((8, n), device="cuda")
+    with pytest.raises(l.MprgError) as e:   # wind pairs are intermediates, not gathered fields
+        rg.apply_into(r, [u, u], [full, full], nlev=[8, 8], epi_op=[l.EPI_ROT_U, l.EPI_ROT_V])
+    assert "wind pairs" in str(e.value)
+    with pytest.raises(l.MprgError):        # ROT_V without its ROT_U
+        rg.apply(r, [u], [full], nlev=[8], epi_op=[l.EPI_ROT_V])
+    with pytest.raises(l.MprgError):        # not a device allocation
+        rg.ipc_export(12345678)
+    imp = rg.import_csr(mesh.nCells, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([1.0]))
+    with pytest.raises(l.MprgError) as e:   # an imported CSR has no grid to place its rows in
+        rg.apply_into(imp, [u], [full], nlev=[8])
+    assert "full-grid" in str(e.value)
+    imp.release()
+    # the context is still usable afterwards
+    out = torch.empty((8, n), device="cuda")
+    rg.apply(r, [u], [out], nlev=[8])
+    rg.synchronize()
+    assert float(out.abs().max()) == 0.0
+    r.release()
