@@ -129,3 +129,45 @@ def test_rank_slab_equals_rows_of_the_single_rank_result(c2):
     assert torch.equal(slab.reshape(60, j1 - j0, 1800), full.reshape(60, 1060, 1800)[:, j0:j1])
     rt.release()
     r8.close()
+
+
+def test_large_target_needs_64_bit_offsets(engine_lib):
+    """BASELINE.json configs[3] in spirit: a fine global lat-lon target (6000 x 3000 = 18 M points) from a coarse
+    global mesh; one 61-level field is 4.4 GB of output, so every destination offset beyond 2^32 bytes is
+    exercised.  Checked through reproduction of a constant and of nearest-neighbour indices at the far end."""
+    import torch
+
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import Regridder
+    from tests import helpers as H
+
+    mesh = H.small_global(2562, jitter=0.1, seed=4)
+    ni, nj = 6000, 3000
+    lon = (-180.0 + (np.arange(ni) + 0.5) * 360.0 / ni)[None, :].repeat(nj, 0)
+    lat = (-90.0 + (np.arange(nj) + 0.5) * 180.0 / nj)[:, None].repeat(ni, 1)
+    rg = Regridder(device=0)
+    rg.set_mesh(mesh.lonCell, mesh.latCell, mesh.lonVertex, mesh.latVertex, mesh.verticesOnCell)
+    rg.set_target(l.CENTER, np.ascontiguousarray(lon), np.ascontiguousarray(lat))
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    info = r.info()
+    assert info["nDst"] == ni * nj and info["nUnmapped"] == 0 and info["nnz"] == 3 * ni * nj
+    nlev = 61
+    src = torch.full((mesh.nCells, nlev), 250.0, device="cuda") + torch.arange(nlev, device="cuda")[None, :]
+    dst = torch.empty((nlev, ni * nj), device="cuda")
+    assert dst.numel() * 4 > 2 ** 32
+    rg.apply(r, [src], [dst], nlev=[nlev])
+    rg.synchronize()
+    want = 250.0 + torch.arange(nlev, device="cuda", dtype=torch.float32)
+    err = (dst - want[:, None]).abs().amax(dim=1)
+    assert float((err / want).max()) <= 2.4e-7
+    r.release()
+    del dst
+    rn = rg.store(l.NEAREST_STOD, l.SRC_MESH_ELEMENT, l.CENTER)
+    ids = torch.arange(mesh.nCells, device="cuda", dtype=torch.float32).reshape(-1, 1).repeat(1, 4).contiguous()
+    out = torch.empty((4, ni * nj), device="cuda")
+    rg.apply(rn, [ids], [out], nlev=[4])
+    rg.synchronize()
+    rp, col, w = rn.export_csr()
+    assert torch.equal(out[3], torch.from_numpy(col.astype(np.float32)).cuda())
+    rn.release()
+    rg.close()
