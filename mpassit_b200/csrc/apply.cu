@@ -323,7 +323,7 @@ k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
 // ---------------------------------------------------------------------------
 // source is a level-slowest grid field [lev][srcPlane] (centre -> edge stagger)
 // ---------------------------------------------------------------------------
-constexpr int kPlaneBatch = 4;  // levels whose gathers are all issued before the first FMA (memory-level parallelism)
+constexpr int kPlaneBatch = 8;  // levels whose gathers are all issued before the first FMA (memory-level parallelism)
 
 template <typename TIN, typename TOUT, typename TACC>
 __global__ void __launch_bounds__(256)
