@@ -53,6 +53,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(HERE, "..", "include", "mpassit_rg.h"))
     headers.append(os.path.abspath(__file__))
     units = [(s, fl, mac) for (s, fl, mac) in UNITS if os.path.exists(os.path.join(CSRC, s))]
+    # the library travels to the GPU box without its object files (mpassit_b200/_build is not shipped):
+    # a library newer than every source is up to date, whatever is in _build
+    if not force and not _stale(LIB, [os.path.join(CSRC, s) for (s, _, _) in units] + headers):
+        return LIB
     macros = [f"-D{m}" for (_, _, mac) in units for m in mac]
     nvcc = _nvcc()
     jobs = []
