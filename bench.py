@@ -516,7 +516,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(wl),
                        "units_per_step": units, "target_points": wl.n_mass, "l2_policy": "inputs (>9 GB) exceed L2; no flush",
-                       "parallelism": f"target row slabs x{world}", "weights": "resident (memoised) in `value`; rebuilt per step in `e2e`"},
+                       "parallelism": f"target row slabs x{world}", "weights": "resident (memoised) in `value`; rebuilt per step in `e2e`",
+                       "cell_numbering": wl.mesh.meta.get("cell_order", "rowmajor (as generated)"),
+                       "tma_copies_per_tile": round(info["tile_runs"] / max(info["tiles"], 1), 2),
+                       "columns_per_tile": round(info["tile_columns"] / max(info["tiles"], 1), 2)},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gather": gather,
             "store_ms": store_ms, "store_wall_s": store_wall,

@@ -35,7 +35,7 @@ module mpassit_rg_mod
   public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
   public :: mprg_set_async, mprg_get_async, mprg_download, mprg_io_bytes
-  public :: mprg_post_midlevels, mprg_post_ptop
+  public :: mprg_post_midlevels, mprg_post_ptop, mprg_route_schedule_info
   public :: mprg_apply_into, mprg_put_slab, mprg_ipc_export, mprg_ipc_open, mprg_ipc_close_all
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
@@ -245,6 +245,11 @@ module mpassit_rg_mod
      integer(c_int) function mprg_ipc_close_all(ctx) bind(C, name="mprg_ipc_close_all")
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function mprg_route_schedule_info(rh, tiles, columns, runs) bind(C, name="mprg_route_schedule_info")
+       import :: c_int, c_ptr, c_int64_t
+       type(c_ptr), value :: rh
+       integer(c_int64_t), intent(out) :: tiles, columns, runs
      end function
      !> Z_C = 0.5 (PHB(k) + PHB(k-1)) (write_data.F90:1406-1412) on this rank's slab
      integer(c_int) function mprg_post_midlevels(ctx, stagger, nlev, dtype, mem, x, mid) bind(C, name="mprg_post_midlevels")

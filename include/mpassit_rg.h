@@ -231,6 +231,10 @@ int mprg_profile_read(mprg_ctx *ctx, int32_t max, int32_t *kind, double *ms, dou
 int mprg_profile_reset(mprg_ctx *ctx);
 /* distinct source entities referenced by a route's weights (nSrcT of the roofline model) */
 int64_t mprg_route_src_referenced(const mprg_route *rh);
+/* the route's tile schedule: 32-target tiles, distinct source columns summed over tiles, and runs of
+ * consecutively numbered columns summed over tiles.  The column kernel issues one bulk copy per run (all-
+ * aligned launches), so columns / runs says how much the mesh numbering helps it. */
+int mprg_route_schedule_info(const mprg_route *rh, int64_t *tiles, int64_t *columns, int64_t *runs);
 
 #ifdef __cplusplus
 }

@@ -555,7 +555,7 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
     MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 2 * sizeof(int32_t), ctx->stream));
     MPRG_CUDA(cudaMemsetAsync(cnt.p, 0, (tiles + 1) * sizeof(int32_t), ctx->stream));
     k_tile_schedule<false><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
-                                                                   mm.p, mm.p + 1, cnt.p, nullptr, nullptr, nullptr);
+                                                                   mm.p, mm.p + 1, cnt.p, nullptr, nullptr, nullptr, nullptr);
     ctx->launches++;
     int32_t h[2] = {0, 0};
     peek(ctx, h, mm.p, sizeof h);
@@ -568,11 +568,15 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
     peek(ctx, &total, r->tileUPtr.p + tiles, sizeof(int32_t));
     r->tileUCols.alloc(total > 0 ? total : 1);
     r->entrySlot.alloc(r->nnz);
+    DevBuf<unsigned long long> runs(1);
+    MPRG_CUDA(cudaMemsetAsync(runs.p, 0, sizeof(unsigned long long), ctx->stream));
     k_tile_schedule<true><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
                                                                   nullptr, nullptr, nullptr, r->tileUPtr.p, r->tileUCols.p,
-                                                                  r->entrySlot.p);
+                                                                  r->entrySlot.p, runs.p);
     ctx->launches++;
-    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long hruns = 0;
+    peek(ctx, &hruns, runs.p, sizeof hruns);
+    r->schedTiles = tiles; r->schedCols = total; r->schedRuns = (int64_t)hruns;
 }
 
 // returns false when wind pairs (fused rotation) are present but the pipelined kernel could not take them

@@ -6,7 +6,8 @@
 //             built once per route by k_tile_schedule) go to shared memory; every lane keeps the
 //             (weight, staged-column offset) pairs of ITS target in registers for the whole sweep
 //             when the row has <= 3 entries (bilinear, nearest);
-//   pipeline  for unit u (= one field x one 64-level chunk) every distinct column is fetched by
+//   pipeline  for unit u (= one field x one 64-level chunk) every distinct column -- every RUN of
+//             consecutively numbered columns, which file order keeps contiguous -- is fetched by
 //             ONE bulk asynchronous copy (cp.async.bulk -> UBLKCP, completion counted on an
 //             mbarrier) STAGES-1 units ahead of the math: no registers or LSU wavefronts are
 //             spent on the gather and HBM latency is covered by the depth of the pipeline; the
@@ -94,7 +95,7 @@ __host__ __device__ constexpr int pipe_slot_bytes() { return kPipeLev * (int)siz
 template <typename TACC>
 __host__ __device__ constexpr size_t pipe_fixed_bytes() {
     return 64 * 4                                   // s_rowptr (33 used) + mbarriers
-           + kPipeCap * 4                           // s_off (slot byte offset | column id mod EPV)
+           + kPipeCap * 4                           // s_off (slot index of every entry's column)
            + kPipeCap * 4                           // s_uniq
            + kPipeCap * sizeof(TACC)                // s_w
            + kPipeMaxUnits * sizeof(UnitDev);       // s_units
@@ -157,7 +158,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t *s_rowptr = (int32_t *)smem;            // [33]; mbarriers at [48..55]
     unsigned long long *s_mbar = (unsigned long long *)(s_rowptr + 48);  // one per stage
-    int32_t *s_off = s_rowptr + 64;                 // per entry: slot byte offset | (column id mod EPV)
+    int32_t *s_off = s_rowptr + 64;                 // per entry: slot index of its column in the tile's list
     int32_t *s_uniq = s_off + kPipeCap;
     TACC *s_w = (TACC *)(s_uniq + kPipeCap);
     UnitDev *s_units = (UnitDev *)(s_w + kPipeCap);
@@ -186,10 +187,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     const int cnt = s_rowptr[ntile] - base;  // host guarantees cnt <= kPipeCap
     if (tid < cnt) {
         s_w[tid] = __ldg(a.w + base + tid);
-        const int eslot = __ldg(a.entrySlot + base + tid);
-        // SLOTB is a multiple of 16, so the low 4 bits of the offset are free for (column id mod EPV),
-        // which the unaligned path needs to find a column inside its staged 16-byte-aligned window
-        s_off[tid] = eslot * SLOTB | (s_uniq[eslot] & (EPV - 1));
+        s_off[tid] = __ldg(a.entrySlot + base + tid);
     }
     __syncthreads();
 
@@ -224,6 +222,18 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     // issue is spread evenly over all warps instead of queuing behind the first two
     const int bslot = lane * kPipeWarps + warp;
     const int bcol = bslot < nu ? s_uniq[bslot] : -1;
+    // ALLVEC: the list is in ascending id order and columns of consecutive ids are contiguous in memory, so
+    // the owner of the first slot of a run fetches the whole run with one bulk copy (brun = its length in
+    // columns, 0 for the other slots of the run).  The TMA unit accepts a request every ~19 cycles per SM,
+    // which is what bounds this kernel: fewer, larger requests are the lever.
+    int brun = bcol >= 0 ? 1 : 0;
+    if (ALLVEC && bcol >= 0) {
+        if (bslot > 0 && s_uniq[bslot - 1] == bcol - 1) {
+            brun = 0;
+        } else {
+            while (bslot + brun < nu && s_uniq[bslot + brun] == bcol + brun) ++brun;
+        }
+    }
     const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
     const unsigned bstage = stage0 + bslot * SLOTB;
 
@@ -232,12 +242,22 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         const UnitDev &ud = s_units[u];
         unsigned long long *bar = s_mbar + (u % STAGES);
         if (ALLVEC) {
-            // equal, exact column chunks: thread 0 posts the unit's byte count, slot owners copy
+            // equal, exact column chunks: thread 0 posts the unit's byte count, run owners copy.  Slots are
+            // packed at the column size so that a run is contiguous in shared memory too -- unless that size
+            // is a multiple of 128 bytes (every slot would start on bank 0): then slots keep 16 bytes of
+            // padding and every column is its own copy.  Whole-field units only: a run of columns is
+            // contiguous in memory only when the chunk is the entire column.
             const unsigned colB = (unsigned)ud.Ln * (unsigned)sizeof(TIN);
+            const bool packed = (colB & 127u) != 0 && ud.Ln == ud.nlev;
+            const unsigned stride = packed ? colB : colB + 16;
             if (tid == 0) mbar_arrive_tx(bar, colB * (unsigned)nu);
-            if (bcol >= 0)
-                bulk_g2s(bstage + (u % STAGES) * stageBytes,
-                         (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * sizeof(TIN), colB, bar);
+            const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * sizeof(TIN);
+            const unsigned sdst = stage0 + (u % STAGES) * stageBytes + bslot * stride;
+            if (packed) {
+                if (brun > 0) bulk_g2s(sdst, g, colB * (unsigned)brun, bar);
+            } else if (bcol >= 0) {
+                bulk_g2s(sdst, g, colB, bar);
+            }
         } else if (ud.epi_op & kUnitAligned) {
             // aligned unit of a mixed launch: exact chunks again, but this barrier counts one arrival per
             // warp (lane 0 posts the bytes of the warp's own copies; an mbarrier's transaction count may
@@ -310,6 +330,9 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             __syncthreads();
         }
         if (!live) continue;
+        // byte offsets of this lane's columns in the unit's staging (slot index x the unit's slot stride)
+        const int colBu = Ln * (int)sizeof(TIN);
+        const int ustride = !ALLVEC ? SLOTB : (((colBu & 127) != 0 && Ln == ud.nlev) ? colBu : colBu + 16);
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
         const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane;
         TOUT *d = (TOUT *)ud.dst + dcol;
@@ -322,15 +345,15 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             TACC acc[4] = {0, 0, 0, 0};
             const unsigned lp = st + g * GB;
             if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
-                fma4<TIN, TACC>(acc, rw[0], lp + (ro[0] & ~15));
-                fma4<TIN, TACC>(acc, rw[1], lp + (ro[1] & ~15));
-                fma4<TIN, TACC>(acc, rw[2], lp + (ro[2] & ~15));
+                fma4<TIN, TACC>(acc, rw[0], lp + ro[0] * ustride);
+                fma4<TIN, TACC>(acc, rw[1], lp + ro[1] * ustride);
+                fma4<TIN, TACC>(acc, rw[2], lp + ro[2] * ustride);
             } else if (fast) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
-                    if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + (ro[j] & ~15));  // absent entries never touch staging (0 x garbage = NaN)
+                    if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + ro[j] * ustride);  // absent entries never touch staging (0 x garbage = NaN)
             } else {
-                for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (s_off[k] & ~15));
+                for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + s_off[k] * ustride);
             }
             if (ROT && rotU) {          // zonal unit: keep, rounded to the output type exactly as a store would
 #pragma unroll
@@ -373,16 +396,18 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
 }
 
 // Tile schedule of a route: for every row-aligned 32-target tile the list of distinct source
-// columns (first-occurrence order) and, per CSR entry, the index of its column in that list.
+// columns in ASCENDING id order and, per CSR entry, the index of its column in that list.  Ascending
+// order makes columns of consecutively numbered cells neighbours in the list; they are also
+// neighbours in memory (file order), so the apply kernel fetches each such run with ONE bulk copy.
 // FILL == false: per-tile unique counts (+ global maxima);  FILL == true: write the lists.
 template <bool FILL>
 __global__ void __launch_bounds__(kPipeThreads)
 k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t nDst, int32_t ni,
                 int32_t tilesPerRow, int32_t *maxEntries, int32_t *maxUniq, int32_t *tileCount,
                 const int32_t *__restrict__ tileUPtr, int32_t *__restrict__ tileUCols,
-                unsigned char *__restrict__ entrySlot) {
-    __shared__ int32_t s_col[kPipeCap];
-    __shared__ int32_t s_slot[kPipeCap];
+                unsigned char *__restrict__ entrySlot, unsigned long long *runsTotal) {
+    __shared__ int32_t s_col[kPipeCap];   // sort keys (column ids; INT_MAX padding)
+    __shared__ int32_t s_idx[kPipeCap];   // entry index within the tile that the key came from
     __shared__ int32_t s_cnt[kPipeWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = blockIdx.x / tilesPerRow;
@@ -396,33 +421,44 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
         if (!FILL && tid == 0) { atomicMax(maxUniq, cnt); tileCount[blockIdx.x] = 0; }
         return;
     }
-    int c = -1;
-    if (tid < cnt) { c = col[base + tid]; s_col[tid] = c; }
+    s_col[tid] = tid < cnt ? col[base + tid] : 0x7fffffff;
+    s_idx[tid] = tid;
     __syncthreads();
-    int first = tid;
-    bool uniq = false;
-    if (tid < cnt) {
-        for (int i = 0; i < tid; ++i)
-            if (s_col[i] == c) { first = i; break; }
-        uniq = first == tid;
-    }
+    // bitonic sort of the kPipeCap (key, index) pairs
+    for (int k = 2; k <= kPipeCap; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int p = tid ^ j;
+            if (p > tid) {
+                const bool up = (tid & k) == 0;
+                const int a = s_col[tid], b = s_col[p];
+                if ((a > b) == up) {
+                    s_col[tid] = b; s_col[p] = a;
+                    const int ia = s_idx[tid]; s_idx[tid] = s_idx[p]; s_idx[p] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    const bool uniq = tid < cnt && (tid == 0 || s_col[tid] != s_col[tid - 1]);
     const unsigned bal = __ballot_sync(0xffffffffu, uniq);
     if (lane == 0) s_cnt[warp] = __popc(bal);
     __syncthreads();
-    int slot = __popc(bal & ((1u << lane) - 1u)), nu = 0;
+    int incl = __popc(bal & ((2u << lane) - 1u)), nu = 0;  // unique keys up to and including this position
 #pragma unroll
     for (int w = 0; w < kPipeWarps; ++w) {
         const int v = s_cnt[w];
-        if (w < warp) slot += v;
+        if (w < warp) incl += v;
         nu += v;
     }
     if (!FILL) {
         if (tid == 0) { atomicMax(maxUniq, nu); tileCount[blockIdx.x] = nu; }
         return;
     }
-    if (uniq) { s_slot[tid] = slot; tileUCols[tileUPtr[blockIdx.x] + slot] = c; }
-    __syncthreads();
-    if (tid < cnt) entrySlot[base + tid] = (unsigned char)s_slot[first];
+    if (uniq) tileUCols[tileUPtr[blockIdx.x] + incl - 1] = s_col[tid];
+    if (tid < cnt) entrySlot[base + s_idx[tid]] = (unsigned char)(incl - 1);
+    // statistics: runs of consecutive ids (= bulk copies per unit of an all-aligned launch)
+    const bool runStart = uniq && (tid == 0 || s_col[tid - 1] != s_col[tid] - 1);
+    const unsigned rb = __ballot_sync(0xffffffffu, runStart);
+    if (lane == 0 && rb && runsTotal) atomicAdd(runsTotal, (unsigned long long)__popc(rb));
 }
 
 }  // namespace mprg

@@ -707,6 +707,14 @@ int mprg_profile_read(mprg_ctx *ctx, int32_t max, int32_t *kind, double *ms, dou
 
 int64_t mprg_route_src_referenced(const mprg_route *rh) { return rh ? rh->nSrcRef : 0; }
 
+int mprg_route_schedule_info(const mprg_route *rh, int64_t *tiles, int64_t *columns, int64_t *runs) {
+    if (!rh) return 1;
+    if (tiles) *tiles = rh->schedTiles;
+    if (columns) *columns = rh->schedCols;
+    if (runs) *runs = rh->schedRuns;
+    return 0;
+}
+
 int64_t mprg_kernel_launches(const mprg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int mprg_io_bytes(const mprg_ctx *ctx, uint64_t *h2d, uint64_t *d2h) {

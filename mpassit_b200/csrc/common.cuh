@@ -148,6 +148,7 @@ struct mprg_route {
     // tile schedule for the pipelined apply kernel (apply_pipe.cuh)
     mprg::DevBuf<int32_t> tileUPtr, tileUCols;
     mprg::DevBuf<unsigned char> entrySlot;
+    int64_t schedTiles = 0, schedCols = 0, schedRuns = 0;  // tiles, distinct columns and id-runs summed over tiles
     int32_t maxRow = 0;        // longest row
     bool uniform = false;      // every mapped row has exactly `maxRow` entries, stored ELL-like
     mprg::DevBuf<int32_t> rowptr;  // [nDst+1]

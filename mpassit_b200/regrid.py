@@ -67,8 +67,11 @@ class Route:
         v = [C.c_int64() for _ in range(4)]
         rc = _l.load().mprg_route_info(self.handle, *[C.byref(x) for x in v])
         _l.check(self.owner.ctx, rc)
+        t = [C.c_int64() for _ in range(3)]
+        _l.load().mprg_route_schedule_info(self.handle, *[C.byref(x) for x in t])
         return dict(nDst=v[0].value, nnz=v[1].value, nUnmapped=v[2].value, nSrc=v[3].value,
-                    nSrcRef=int(_l.load().mprg_route_src_referenced(self.handle)))
+                    nSrcRef=int(_l.load().mprg_route_src_referenced(self.handle)),
+                    tiles=t[0].value, tile_columns=t[1].value, tile_runs=t[2].value)
 
     def export_csr(self):
         i = self.info()

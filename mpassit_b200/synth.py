@@ -309,6 +309,35 @@ def regional_delaunay_mesh(n_points: int = 4000, extent_x_m: float = 600e3, exte
                                    meta={"kind": "regional-delaunay", "seed": seed})
 
 
+def renumber_cells(mesh: MpasMesh, order: str, seed: int = SEED) -> MpasMesh:
+    """The same mesh with its cells renumbered (vertices keep their ids): `rowmajor` = as generated,
+    `morton` = along a Z-order curve of (lon, lat) (what a locality sort such as MPAS-Tools' sort_mesh
+    produces), `random` = no locality at all.  The apply kernel fetches runs of consecutively numbered
+    cells with one bulk copy, so its speed depends on the numbering; results do not."""
+    if order in ("rowmajor", "", None):
+        return mesh
+    n = mesh.nCells
+    if order == "random":
+        perm = np.random.default_rng(seed).permutation(n)          # new id k holds old cell perm[k]
+    elif order == "morton":
+        def spread(v):
+            v = v.astype(np.uint64) & np.uint64(0xFFFF)
+            v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF)
+            v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+            v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+            v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+            return v
+        lon = np.where(mesh.lonCell > np.pi, mesh.lonCell - 2 * np.pi, mesh.lonCell)
+        qx = ((lon - lon.min()) / max(np.ptp(lon), 1e-30) * 65535).astype(np.uint64)
+        qy = ((mesh.latCell - mesh.latCell.min()) / max(np.ptp(mesh.latCell), 1e-30) * 65535).astype(np.uint64)
+        perm = np.argsort(spread(qx) | (spread(qy) << np.uint64(1)), kind="stable")
+    else:
+        raise ValueError(order)
+    meta = dict(mesh.meta, cell_order=order)
+    return MpasMesh(np.ascontiguousarray(mesh.lonCell[perm]), np.ascontiguousarray(mesh.latCell[perm]), mesh.lonVertex,
+                    mesh.latVertex, np.ascontiguousarray(mesh.verticesOnCell[perm]), meta)
+
+
 # --------------------------------------------------------------------------
 # fields (SURVEY.md §8(d) value recipes)
 # --------------------------------------------------------------------------

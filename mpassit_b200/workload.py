@@ -71,8 +71,10 @@ _SPECS = {
 }
 
 
-def make(name: str = "c2", rundir: str | None = None, seed: int = synth.SEED) -> Workload:
+def make(name: str = "c2", rundir: str | None = None, seed: int = synth.SEED, cell_order: str | None = None) -> Workload:
+    """cell_order (or $MPASSIT_CELL_ORDER): rowmajor (as generated) | morton | random -- see synth.renumber_cells."""
     rundir = rundir or tempfile.mkdtemp(prefix=f"mpassit_{name}_")
+    cell_order = cell_order or os.environ.get("MPASSIT_CELL_ORDER", "rowmajor")
     if name == "c1":
         mesh = synth.global_mesh(40962)
         nl = os.path.join(rundir, "namelist.input")
@@ -82,7 +84,7 @@ def make(name: str = "c2", rundir: str | None = None, seed: int = synth.SEED) ->
         nz, nsoil = 55, 4
     else:
         mk, nk, nz, nsoil = _SPECS[name]
-        mesh = synth.regional_hex_mesh(seed=seed, **mk)
+        mesh = synth.renumber_cells(synth.regional_hex_mesh(seed=seed, **mk), cell_order, seed)
         nl = defaults.write_namelist(os.path.join(rundir, "namelist.input"), **nk)
     paths = defaults.write_varlists(rundir)
     cfg = host.read_setup_namelist(nl)

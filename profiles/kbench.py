@@ -33,15 +33,17 @@ def main():
     ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
     ap.add_argument("--stack", default="", help="explicit stack, e.g. 60x12,61x2 (levels x fields)")
     ap.add_argument("--rot", action="store_true", help="the first two fields are a wind pair with fused rotation")
+    ap.add_argument("--order", default="rowmajor", choices=["rowmajor", "morton", "random"], help="cell numbering of the synthetic mesh")
+    ap.add_argument("--method", default="bilinear", choices=["bilinear", "nearest"], help="route the stack is applied with")
     args = ap.parse_args()
     t0 = time.time()
-    wl = workload.make(args.config)
+    wl = workload.make(args.config, cell_order=args.order)
     rg = Regridder(0)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     rg.use_torch_stream()
     workload.load_geometry(rg, wl)
-    route = rg.store(L.BILINEAR, L.SRC_MESH_ELEMENT, L.CENTER)
+    route = rg.store(L.BILINEAR if args.method == "bilinear" else L.NEAREST_STOD, L.SRC_MESH_ELEMENT, L.CENTER)
     epi = None
     info = route.info()
     nlev = args.nlev or wl.nz

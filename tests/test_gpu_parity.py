@@ -310,3 +310,42 @@ def test_new_entry_points_report_errors(rg, orc):
     rg.synchronize()
     assert float(out.abs().max()) == 0.0
     r.release()
+
+
+@pytest.mark.parametrize("order", ["morton", "random"])
+def test_results_do_not_depend_on_the_cell_numbering(engine_lib, orc, order):
+    """The column kernel fetches runs of consecutively numbered cells with one bulk copy; a renumbered mesh
+    (Z-order / random) changes which copies are issued but must give the same output, bit for bit, and
+    the same weights as the oracle."""
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import Regridder
+
+    mesh = H.synth.regional_hex_mesh(spacing_m=40000.0, extent_x_m=2400e3, extent_y_m=1600e3, seed=5)
+    ren = H.synth.renumber_cells(mesh, order, seed=2)
+    lon, lat = H.latlon_grid(96, 64, lon0=-108.0, lon1=-87.0, lat0=32.0, lat1=45.0)
+    # match renumbered cells to the originals by coordinates
+    key = {(a, b): i for i, (a, b) in enumerate(zip(mesh.lonCell, mesh.latCell))}
+    perm = np.array([key[(a, b)] for a, b in zip(ren.lonCell, ren.latCell)])
+    src = H.synth.smooth_field(mesh.lonCell, mesh.latCell, 60, seed=8)
+    outs, infos = [], []
+    for m, f in ((mesh, src), (ren, np.ascontiguousarray(src[perm]))):
+        rg = Regridder(device=0)
+        rg.set_mesh(m.lonCell, m.latCell, m.lonVertex, m.latVertex, m.verticesOnCell)
+        rg.set_target(l.CENTER, lon, lat)
+        r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+        infos.append(r.info())
+        out = np.empty((60, lon.size), np.float32)
+        rg.apply(r, [f], [out], nlev=[60])
+        outs.append(out)
+        if m is ren:
+            cxyz, vxyz, tri = H.oracle_geometry(orc, m)
+            e, c, w = orc.bilinear(cxyz, tri, m.verticesOnCell, orc.sph_deg_to_cart(lon, lat))
+            rp, cc, ww = orc.ell_to_csr(e >= 0, c, w)
+            grp, gc, gw = r.export_csr()
+            assert np.array_equal(grp, rp) and np.array_equal(gc, cc) and np.abs(gw - ww).max() <= 1e-12
+        r.release()
+        rg.close()
+    # same three cells, same weights; the order of the three products inside a row follows the cell ids
+    np.testing.assert_allclose(outs[1], outs[0], rtol=3e-7, atol=0)
+    assert infos[0]["tile_columns"] == infos[1]["tile_columns"]
+    assert infos[0]["tile_runs"] < infos[1]["tile_runs"] <= infos[1]["tile_columns"]  # row-major numbering has the longest runs
