@@ -447,7 +447,7 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_source": "ncu --set full, profiles/r01/apply_v5_ncu_summary.md" if traffic else None,
+                    "traffic_source": "ncu --set full, profiles/r01/apply_v6_ncu_summary.md" if traffic else None,
                     "kernel": KIND_NAMES[dom[0]], "launches": d["n"], "avg_launch_ms": d["ms"] / d["n"],
                     "alg_bytes_per_launch": d["bytes"] / d["n"], "units_per_launch": d["units"] / d["n"],
                     "share_of_step": d["ms"] / ms_total,
