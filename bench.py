@@ -382,14 +382,31 @@ def main():
         # ranks map them with CUDA IPC and their apply kernels write their rows straight into rank 0's memory
         # over NVLink (mprg_apply_into) -- compute and collective in one set of kernels, no slab round trip.
         fused = None
+
+        def all_ok(flag: bool) -> bool:   # every rank takes the same branch, whatever failed where
+            t = torch.tensor([1 if flag else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item())
+
+        err, full, Ff = "", None, None
         try:
             full = workload.full_outputs(wl, "cuda") if rank == 0 else None
             box = [workload.export_full(rg, full) if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
+        except Exception as e:  # noqa: BLE001
+            err, box = str(e)[:200], [None]
+        dist.broadcast_object_list(box, src=0)
+        try:
+            if box[0] is None:
+                raise RuntimeError(err or "the writing rank could not export its buffers")
             dstf = full if rank == 0 else workload.open_full(rg, box[0])
             Ff = workload.with_destinations(F["dev"], dstf)
             for _ in range(3):
                 workload.run_interp(rg, wl, Ff, L.DEVICE, dst_full=True)
+            torch.cuda.synchronize()
+            ok_here = True
+        except Exception as e:  # noqa: BLE001
+            err, ok_here = str(e)[:200], False
+        if all_ok(ok_here):
             barrier()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record()
@@ -408,11 +425,14 @@ def main():
                      "GBps_into_root": to_root / (fms * 1e-3) / 1e9,
                      "note": "interp_data with every rank storing its rows directly into rank 0's full fields "
                              "(CUDA IPC peer stores over NVLink): the result is complete on the writing rank when the pass ends"}
+        else:
+            fused = {"error": err or "CUDA IPC mapping failed on another rank"}
+        try:
             if rank != 0:
                 rg.ipc_close_all()
-            del full
-        except Exception as e:  # noqa: BLE001
-            fused = {"error": str(e)[:200]}
+        except Exception:  # noqa: BLE001
+            pass
+        del full, Ff
         gather = {"ms_per_pass": gms, "bytes_into_root": to_root, "GBps_into_root": to_root / (gms * 1e-3) / 1e9, "fused": fused,
                   "nvlink_peak_GBps": 770.0, "peak_source": "B200_PROFILING.md measured peer copy, per direction",
                   "fields": len(gather_items), "note": "slabs of every output field -> rank 0, one NCCL group; not part of "
