@@ -56,3 +56,26 @@ def test_product_never_imports_oracle():
                         or "orc_" in src:
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_fortran_module_binds_every_reference_facing_entry():
+    """fortran/mpassit_rg_mod.F90 (what interp.F90 / model_grid.F90 / write_data.F90 would `use`) declares an
+    ISO_C_BINDING interface for every entry point of the header, under its exact C name, and nothing else."""
+    txt = open(os.path.join(ROOT, "fortran", "mpassit_rg_mod.F90")).read()
+    bound = sorted(set(re.findall(r'bind\(C,\s*name="(mprg_[a-z0-9_]+)"\)', txt)))
+    declared = _declared()
+    # instrumentation that only the bench / tuning scripts use
+    tooling = {"mprg_profile_enable", "mprg_profile_read", "mprg_profile_reset", "mprg_set_stream", "mprg_version",
+               "mprg_route_export_csr", "mprg_route_import_csr", "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc",
+               "mprg_device_free", "mprg_kernel_launches", "mprg_last_ms", "mprg_route_src_referenced", "mprg_clear_routes",
+               "mprg_route_info", "mprg_scratch", "mprg_has_rotation", "mprg_synchronize", "mprg_get_slab"}
+    assert not [b for b in bound if b not in declared], "Fortran binds a name the header does not declare"
+    missing = [d for d in declared if d not in bound and d not in tooling]
+    assert not missing, missing
+    # the stagger / method / memory constants agree with the header
+    hdr = open(os.path.join(ROOT, "include", "mpassit_rg.h")).read()
+    for name in ("MPRG_BILINEAR", "MPRG_CONSERVE", "MPRG_NEAREST_STOD", "MPRG_CENTER", "MPRG_EDGE1", "MPRG_EDGE2", "MPRG_CORNER",
+                 "MPRG_CENTER_HALO", "MPRG_F32", "MPRG_F64", "MPRG_HOST", "MPRG_DEVICE", "MPRG_EPI_ROT_U", "MPRG_EPI_ROT_V"):
+        hv = re.search(name + r"\s*=\s*(\d+)", hdr)
+        fv = re.search(name + r"\s*=\s*(\d+)", txt)
+        assert hv and fv and hv.group(1) == fv.group(1), name
