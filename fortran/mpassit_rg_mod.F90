@@ -37,6 +37,7 @@ module mpassit_rg_mod
   public :: mprg_set_async, mprg_get_async, mprg_download, mprg_io_bytes
   public :: mprg_post_midlevels, mprg_post_ptop, mprg_route_schedule_info
   public :: mprg_apply_into, mprg_put_slab, mprg_ipc_export, mprg_ipc_open, mprg_ipc_close_all
+  public :: mprg_device_alloc, mprg_device_free
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
   interface
@@ -209,6 +210,17 @@ module mpassit_rg_mod
        import :: c_int, c_ptr, c_size_t
        type(c_ptr), value :: ctx, dev, host
        integer(c_size_t), value :: bytes
+     end function
+     !> device memory for buffers that live on the GPU (the writing rank's full fields of the fused gather)
+     integer(c_int) function mprg_device_alloc(ctx, bytes, ptr) bind(C, name="mprg_device_alloc")
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value :: ctx
+       integer(c_size_t), value :: bytes
+       type(c_ptr), intent(out) :: ptr
+     end function
+     integer(c_int) function mprg_device_free(ctx, ptr) bind(C, name="mprg_device_free")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, ptr
      end function
      !> apply fused with the gather: dst_full(f) is the whole field of the destination stagger (the
      !! writing rank's buffer, own or mapped with mprg_ipc_open); each rank stores its rows into it
