@@ -441,12 +441,6 @@ template <typename TIN, typename TOUT, typename TACC, int STAGES>
 static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes, unsigned tiles,
                           bool allvec, int minb, bool rot) {
     if (rot) {  // fused wind rotation: 2 stages, 64 registers (it holds the zonal results and the angles)
-        static const bool rot5 = getenv("MPASSIT_GPU_ROT_MINB") && atoi(getenv("MPASSIT_GPU_ROT_MINB")) >= 5;
-        if (rot5 && minb >= 5) {
-            if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 5, true>, pa, up, smemBytes, tiles);
-            else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 5, true>, pa, up, smemBytes, tiles);
-            return;
-        }
         if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 4, true>, pa, up, smemBytes, tiles);
         else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 4, true>, pa, up, smemBytes, tiles);
         return;
