@@ -334,6 +334,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    def all_ok(flag: bool) -> bool:   # every rank takes the same branch, whatever failed where
+        if not dist:
+            return flag
+        t = torch.tensor([1 if flag else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     for _ in range(max(args.warmup, 3)):
         device_step()
     barrier()
@@ -361,6 +368,38 @@ def main():
     units = wl.units_per_pass()
     value = units / (ms_step * 1e-3)
 
+    # The same pass replayed from a CUDA graph (mprg_capture_*): one launch call per pass instead of nine kernel
+    # launches.  Reported beside `value`, which stays the eager pass whose launches the roofline events time.
+    graph_replay = None
+    gerr, graph = "", None
+    try:
+        rg.capture_begin()
+        device_step()
+        graph = rg.capture_end()
+        for _ in range(3):
+            rg.graph_launch(graph)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        gerr, graph = str(e)[:200], None
+    if all_ok(graph is not None):
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(args.steps):
+            rg.graph_launch(graph)
+        q1.record()
+        barrier()
+        qms = q0.elapsed_time(q1) / args.steps
+        if dist:
+            tt = torch.tensor([qms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            qms = float(tt.item())
+        graph_replay = {"ms_per_step": qms, "value": units / (qms * 1e-3), "unit": UNIT}
+    else:
+        graph_replay = {"error": gerr or "capture failed on another rank"}
+    if graph is not None:
+        rg.graph_release(graph)
+
     gather = None
     if world > 1:
         rg.gather_many(gather_items, 0)      # warm-up (NCCL channel setup)
@@ -382,12 +421,6 @@ def main():
         # ranks map them with CUDA IPC and their apply kernels write their rows straight into rank 0's memory
         # over NVLink (mprg_apply_into) -- compute and collective in one set of kernels, no slab round trip.
         fused = None
-
-        def all_ok(flag: bool) -> bool:   # every rank takes the same branch, whatever failed where
-            t = torch.tensor([1 if flag else 0], device="cuda", dtype=torch.int32)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            return bool(t.item())
-
         err, full, Ff = "", None, None
         try:
             full = workload.full_outputs(wl, "cuda") if rank == 0 else None
@@ -541,7 +574,7 @@ def main():
                        "tma_copies_per_tile": round(info["tile_runs"] / max(info["tiles"], 1), 2),
                        "columns_per_tile": round(info["tile_columns"] / max(info["tiles"], 1), 2)},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gather": gather,
+            "gather": gather, "graph_replay": graph_replay,
             "store_ms": store_ms, "store_wall_s": store_wall,
             "route_bilinear": info,
         }

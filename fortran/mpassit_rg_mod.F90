@@ -38,6 +38,7 @@ module mpassit_rg_mod
   public :: mprg_post_midlevels, mprg_post_ptop, mprg_route_schedule_info
   public :: mprg_apply_into, mprg_put_slab, mprg_ipc_export, mprg_ipc_open, mprg_ipc_close_all
   public :: mprg_device_alloc, mprg_device_free
+  public :: mprg_capture_begin, mprg_capture_end, mprg_graph_launch, mprg_graph_release
   public :: mprg_host_alloc, mprg_host_free, mprg_scratch, mprg_synchronize
 
   interface
@@ -210,6 +211,24 @@ module mpassit_rg_mod
        import :: c_int, c_ptr, c_size_t
        type(c_ptr), value :: ctx, dev, host
        integer(c_size_t), value :: bytes
+     end function
+     !> CUDA graph of a device-buffer pass: record once, replay per output time
+     integer(c_int) function mprg_capture_begin(ctx) bind(C, name="mprg_capture_begin")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function mprg_capture_end(ctx, graph) bind(C, name="mprg_capture_end")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr), intent(out) :: graph
+     end function
+     integer(c_int) function mprg_graph_launch(ctx, graph) bind(C, name="mprg_graph_launch")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, graph
+     end function
+     integer(c_int) function mprg_graph_release(ctx, graph) bind(C, name="mprg_graph_release")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, graph
      end function
      !> device memory for buffers that live on the GPU (the writing rank's full fields of the fused gather)
      integer(c_int) function mprg_device_alloc(ctx, bytes, ptr) bind(C, name="mprg_device_alloc")

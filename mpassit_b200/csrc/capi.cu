@@ -176,6 +176,7 @@ int mprg_scratch(mprg_ctx *ctx, int slot, size_t bytes, void **ptr) {
     MPRG_ENTER(ctx)
     if (!ptr || slot < 0 || slot >= 8) fail(1, "mprg_scratch: bad slot/pointer");
     if (bytes > ctx->userScratch[slot].n) {
+        if (ctx->capturing) fail(45, "mprg_scratch: a slot cannot grow while capturing a graph");
         MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->userScratch[slot].alloc(bytes);
         MPRG_CUDA(cudaStreamSynchronize(ctx->stream));  // callers may use the block on their own streams
@@ -258,6 +259,7 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
         StreamSwap(mprg_ctx *c_) : c(c_), saved(c_->stream) { c->stream = c->store_stream; mprg::tl_stream = c->stream; }
         ~StreamSwap() { c->stream = saved; mprg::tl_stream = saved; }
     } swap(ctx);
+    if (ctx->capturing) fail(46, "mprg_store: this route is not memoised yet; build it before mprg_capture_begin");
     std::unique_ptr<mprg_route> r(new mprg_route());  // after `swap`: on failure its buffers are freed on the store stream
     r->method = method; r->src_loc = src_loc; r->dst_stagger = dst_stagger;
     MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -366,7 +368,9 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
     if (rh->nDst == 0) return;  // this rank owns no destination rows (nranks > nj): nothing to regrid
     const size_t isz = src_dtype == MPRG_F32 ? 4 : 8, osz = dst_dtype == MPRG_F32 ? 4 : 8;
     const int64_t nSrcPts = rh->srcLevelSlowest ? rh->srcPlane : rh->nSrc;
-    MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->capturing && (src_mem != MPRG_DEVICE || dst_mem != MPRG_DEVICE))
+        fail(45, "mprg_apply: host buffers cannot be used while capturing a graph");
+    if (!ctx->capturing) MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     if (src_mem == MPRG_DEVICE && dst_mem == MPRG_DEVICE) {
         std::vector<ApplyField> fl(nfields);
         for (int f = 0; f < nfields; ++f)
@@ -456,7 +460,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
             if (dst_mem == MPRG_HOST) MPRG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
         }
     }
-    MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!ctx->capturing) MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
 }
 
 int mprg_apply_ex(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
@@ -716,6 +720,67 @@ int mprg_route_schedule_info(const mprg_route *rh, int64_t *tiles, int64_t *colu
 }
 
 int64_t mprg_kernel_launches(const mprg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// CUDA graphs
+// ---------------------------------------------------------------------------
+int mprg_capture_begin(mprg_ctx *ctx) {
+    MPRG_ENTER(ctx)
+    if (ctx->capturing) fail(47, "mprg_capture_begin: already capturing");
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    MPRG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    ctx->captureLaunches0 = ctx->launches;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_capture_end(mprg_ctx *ctx, mprg_graph **graph) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    cudaGraph_t g = nullptr;
+    const bool was = ctx->capturing;
+    ctx->capturing = false;
+    cudaError_t e = was ? cudaStreamEndCapture(ctx->stream, &g) : cudaErrorInvalidValue;
+    if (graph) *graph = nullptr;
+    if (e != cudaSuccess || !g || !graph) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        ctx->err = std::string("mprg_capture_end: ") + (was ? cudaGetErrorString(e) : "no capture in progress");
+        return 48;
+    }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("mprg_capture_end: cudaGraphInstantiate: ") + cudaGetErrorString(e);
+        return 49;
+    }
+    mprg_graph *out = new mprg_graph();
+    out->exec = ex;
+    out->launches = ctx->launches - ctx->captureLaunches0;
+    ctx->launches = ctx->captureLaunches0;  // recorded, not run
+    *graph = out;
+    return 0;
+}
+
+int mprg_graph_launch(mprg_ctx *ctx, mprg_graph *graph) {
+    MPRG_ENTER(ctx)
+    if (!graph || !graph->exec) fail(1, "mprg_graph_launch: null graph");
+    if (ctx->capturing) fail(47, "mprg_graph_launch: a capture is in progress");
+    MPRG_CUDA(cudaGraphLaunch(graph->exec, ctx->stream));
+    ctx->launches += graph->launches;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_graph_release(mprg_ctx *ctx, mprg_graph *graph) {
+    MPRG_ENTER(ctx)
+    if (graph) {
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (graph->exec) cudaGraphExecDestroy(graph->exec);
+        delete graph;
+    }
+    MPRG_LEAVE(ctx)
+}
 
 int mprg_io_bytes(const mprg_ctx *ctx, uint64_t *h2d, uint64_t *d2h) {
     if (!ctx) return 1;

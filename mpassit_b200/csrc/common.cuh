@@ -162,12 +162,19 @@ struct mprg_route {
     int64_t srcPlane = 0;      // points per source level plane
 };
 
+struct mprg_graph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;   // engine kernels inside
+};
+
 struct mprg_ctx {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t store_stream = nullptr;  // weight generation runs here, beside the copy-bound apply pipeline
     bool async = false;                   // host-buffer applies return once enqueued (mprg_set_async)
+    bool capturing = false;               // between mprg_capture_begin / _end
+    int64_t captureLaunches0 = 0;
     std::string err;
     mprg::Mesh mesh;
     mprg::Target target[5];           // + MPRG_CENTER_HALO (derived from CENTER)

@@ -28,7 +28,7 @@ EXPORTS = [
     "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_get_slab", "mprg_store",
     "mprg_release", "mprg_clear_routes", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
     "mprg_apply", "mprg_apply_ex", "mprg_apply_into", "mprg_put_slab", "mprg_ipc_export", "mprg_ipc_open", "mprg_ipc_close_all", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
-    "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
+    "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_capture_begin", "mprg_capture_end", "mprg_graph_launch", "mprg_graph_release", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
     "mprg_profile_reset", "mprg_route_src_referenced", "mprg_route_schedule_info",
 ]
 
@@ -91,6 +91,10 @@ def load() -> C.CDLL:
     L.mprg_ipc_close_all.argtypes = [vp]
     L.mprg_route_schedule_info.argtypes = [vp, vp, vp, vp]
     L.mprg_io_bytes.argtypes = [vp, vp, vp]
+    L.mprg_capture_begin.argtypes = [vp]
+    L.mprg_capture_end.argtypes = [vp, pp]
+    L.mprg_graph_launch.argtypes = [vp, vp]
+    L.mprg_graph_release.argtypes = [vp, vp]
     L.mprg_set_async.argtypes = [vp, C.c_int]
     L.mprg_get_async.argtypes = [vp]
     L.mprg_download.argtypes = [vp, vp, vp, C.c_size_t]

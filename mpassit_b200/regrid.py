@@ -127,6 +127,21 @@ class Regridder:
         """Host-buffer applies return once queued; call synchronize() before reading their outputs."""
         self._ck(self.L.mprg_set_async(self.ctx, int(on)))
 
+    # ---- CUDA graphs ------------------------------------------------------
+    def capture_begin(self) -> None:
+        self._ck(self.L.mprg_capture_begin(self.ctx))
+
+    def capture_end(self) -> int:
+        g = C.c_void_p()
+        self._ck(self.L.mprg_capture_end(self.ctx, C.byref(g)))
+        return g.value
+
+    def graph_launch(self, graph: int) -> None:
+        self._ck(self.L.mprg_graph_launch(self.ctx, C.c_void_p(graph)))
+
+    def graph_release(self, graph: int) -> None:
+        self._ck(self.L.mprg_graph_release(self.ctx, C.c_void_p(graph)))
+
     def synchronize(self) -> None:
         self._ck(self.L.mprg_synchronize(self.ctx))
 

@@ -346,3 +346,51 @@ def test_interp_data_mid_workload_against_oracle(engine_lib, orc, host):
         checked += 1
     assert checked >= 40
     rg.close()
+
+
+def test_cuda_graph_replay_of_a_pass(engine_lib, host):
+    """mprg_capture_begin / _end record a device-buffer interp_data pass; replaying the graph after the sources
+    changed gives exactly what an eager pass gives, and calls that cannot be captured are refused."""
+    import torch
+
+    from mpassit_b200 import lib as l
+    from mpassit_b200 import workload
+    from mpassit_b200.regrid import Regridder
+
+    wl = workload.make("mini")
+    rg = Regridder(device=0)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        rg.use_torch_stream()
+        workload.load_geometry(rg, wl)
+        F = workload.make_fields(wl, device="cuda:0")
+        workload.run_interp(rg, wl, F["dev"], l.DEVICE)          # builds (memoises) every route, sizes scratch
+        rg.synchronize()
+        n0 = rg.kernel_launches
+        rg.capture_begin()
+        workload.run_interp(rg, wl, F["dev"], l.DEVICE)
+        with pytest.raises(l.MprgError):                          # host buffers cannot be captured
+            r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+            rg.apply(r, [np.zeros((wl.mesh.nCells, 3), np.float32)], [np.zeros((3, wl.n_mass), np.float32)], nlev=[3])
+        g = rg.capture_end()
+        assert rg.kernel_launches == n0                           # recorded, not run
+        # new data in the same buffers
+        for grp in ("diag", "hist_2d", "hist_3d", "soil"):
+            for s in F["dev"][grp]:
+                s.src.mul_(1.25).add_(0.5) if grp != "soil" and s.name != "xland" else None
+                s.dst.fill_(float("nan"))
+        rg.graph_launch(g)
+        rg.synchronize()
+        assert rg.kernel_launches > n0
+        got = {s.name: s.dst.clone() for grp in ("diag", "hist_2d", "hist_3d", "soil") for s in F["dev"][grp]}
+        gu, gv = F["dev"]["u_stag"].clone(), F["dev"]["v_stag"].clone()
+        workload.run_interp(rg, wl, F["dev"], l.DEVICE)           # eager pass on the same data
+        rg.synchronize()
+        for grp in ("diag", "hist_2d", "hist_3d", "soil"):
+            for s in F["dev"][grp]:
+                if s.name.startswith("uReconstruct"):
+                    continue
+                assert torch.equal(got[s.name], s.dst), s.name
+        assert torch.equal(gu, F["dev"]["u_stag"]) and torch.equal(gv, F["dev"]["v_stag"])
+        rg.graph_release(g)
+        rg.close()
