@@ -221,10 +221,36 @@ def _farr(specs):
     return arr
 
 
-def interp_data(rg, cfg: Config, *, diag=(), hist_2d=(), hist_3d=(), soil=(), ter=None, hgt=None, u_stag=None,
-                v_stag=None, nz=0, src_dtype=_l.F32, dst_dtype=_l.F32, mem=_l.HOST, dst_full=False) -> InterpIO:
+class PreparedInterp:
+    """interp_data with its argument block marshalled once: calling the object is one C call
+    (mpassit_interp_data), which is what a compiled host pays per output time."""
+
+    def __init__(self, rg, cfg: Config, io: "InterpIO", keep):
+        self.rg, self.cfg, self.io, self._keep = rg, cfg, io, keep
+        self._fn = load().mpassit_interp_data
+        self._err = _err()
+
+    def __call__(self) -> "InterpIO":
+        rc = self._fn(self.rg.ctx, C.byref(self.cfg), C.byref(self.io), self._err, len(self._err))
+        if rc:
+            raise HostError(rc, self._err.value.decode())
+        return self.io
+
+
+def prepare_interp(rg, cfg: Config, **kw) -> PreparedInterp:
+    """Same arguments as interp_data; returns the reusable call."""
+    io, keep = _build_io(**kw)
+    return PreparedInterp(rg, cfg, io, keep)
+
+
+def interp_data(rg, cfg: Config, **kw) -> InterpIO:
     """interp_data (interp.F90:92) on Regridder ``rg``; field lists are FieldSpec sequences in
     var-list order.  Returns the InterpIO (with the regrid class of every field filled in)."""
+    return prepare_interp(rg, cfg, **kw)()
+
+
+def _build_io(*, diag=(), hist_2d=(), hist_3d=(), soil=(), ter=None, hgt=None, u_stag=None,
+              v_stag=None, nz=0, src_dtype=_l.F32, dst_dtype=_l.F32, mem=_l.HOST, dst_full=False):
     io = InterpIO()
     io.src_dtype, io.dst_dtype, io.mem, io.nz = src_dtype, dst_dtype, mem, nz
     keep = [_farr(diag), _farr(hist_2d), _farr(hist_3d), _farr(soil)]
@@ -234,9 +260,5 @@ def interp_data(rg, cfg: Config, *, diag=(), hist_2d=(), hist_3d=(), soil=(), te
     io.n_soil, io.soil = len(soil), keep[3]
     io.ter, io.hgt, io.u_stag, io.v_stag = _ptr(ter), _ptr(hgt), _ptr(u_stag), _ptr(v_stag)
     io.dst_full = int(bool(dst_full))
-    e = _err()
-    rc = load().mpassit_interp_data(rg.ctx, C.byref(cfg), C.byref(io), e, len(e))
-    if rc:
-        raise HostError(rc, e.value.decode())
     io._keep = keep
-    return io
+    return io, keep

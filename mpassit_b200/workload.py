@@ -197,9 +197,21 @@ def run_interp(rg, wl: Workload, F: dict, mem: int, dst_full: bool = False):
     def conv(specs):
         return [host.FieldSpec(s.name, s.target_name, s.nlev, _np(s.src), _np(s.dst)) for s in specs]
 
-    return host.interp_data(rg, wl.cfg, diag=conv(F["diag"]), hist_2d=conv(F["hist_2d"]), hist_3d=conv(F["hist_3d"]),
-                            soil=conv(F["soil"]), ter=_np(F["ter"]), hgt=_np(F["hgt"]), u_stag=_np(F["u_stag"]),
-                            v_stag=_np(F["v_stag"]), nz=wl.nz, mem=mem, dst_full=dst_full)
+    return prepare_interp(rg, wl, F, mem, dst_full)()
+
+
+def prepare_interp(rg, wl: Workload, F: dict, mem: int, dst_full: bool = False):
+    """The pass of run_interp with its argument block marshalled once (host.PreparedInterp): a time loop
+    over many output times pays one C call per pass, as a compiled host would."""
+    def conv(specs):
+        return [host.FieldSpec(s.name, s.target_name, s.nlev, _np(s.src), _np(s.dst)) for s in specs]
+
+    keep = [conv(F[g]) for g in ("diag", "hist_2d", "hist_3d", "soil")]
+    p = host.prepare_interp(rg, wl.cfg, diag=keep[0], hist_2d=keep[1], hist_3d=keep[2], soil=keep[3], ter=_np(F["ter"]),
+                            hgt=_np(F["hgt"]), u_stag=_np(F["u_stag"]), v_stag=_np(F["v_stag"]), nz=wl.nz, mem=mem,
+                            dst_full=dst_full)
+    p._fields = (keep, F)  # the buffers behind the raw pointers stay alive with the call
+    return p
 
 
 # ---- fused gather: full-grid outputs on the writing rank, mapped into the other ranks with CUDA IPC --------
