@@ -217,6 +217,27 @@ def global_mesh(n_cells: int = 40962, kind: str = "icos", lloyd_iters: int = 0, 
                                    meta={"kind": f"global-{kind}", "seed": seed})
 
 
+def variable_global_mesh(n_cells: int = 655362, focus_lat: float = 38.5, focus_lon: float = -97.5,
+                         spacing_ratio: float = 5.0, max_edges: int = 10) -> MpasMesh:
+    """Variable-resolution global mesh (config C4's shape: 15 km -> 3 km is spacing_ratio = 5): Fibonacci
+    points pulled towards a focus by a Schmidt transformation (sin(lat') = (D + sin lat) / (1 + D sin lat),
+    D = (r - 1) / (r + 1) for a coarse/fine spacing ratio r), then the pole rotated onto the focus.  Cell ids
+    follow the Fibonacci spiral, i.e. rings around the focus."""
+    xyz = fibonacci_points(n_cells)
+    D = (spacing_ratio - 1.0) / (spacing_ratio + 1.0)
+    z = xyz[:, 2]
+    z2 = (D + z) / (1.0 + D * z)
+    s = np.sqrt(np.maximum(0.0, 1.0 - z2 * z2)) / np.sqrt(np.maximum(1e-300, 1.0 - z * z))
+    p = np.stack([xyz[:, 0] * s, xyz[:, 1] * s, z2], axis=1)
+    la, lo = math.radians(focus_lat), math.radians(focus_lon)
+    ez = np.array([math.cos(la) * math.cos(lo), math.cos(la) * math.sin(lo), math.sin(la)])
+    ex = _unit(np.cross([0.0, 0.0, 1.0], ez)[None, :])[0]
+    ey = np.cross(ez, ex)
+    p = _unit(p[:, :1] * ex + p[:, 1:2] * ey + p[:, 2:] * ez)
+    return mesh_from_triangulation(p, _sphere_delaunay(p), max_edges=max_edges,
+                                   meta={"kind": "global-variable", "spacing_ratio": spacing_ratio})
+
+
 # --------------------------------------------------------------------------
 # Lambert-conformal plane <-> sphere (generator-side only; the product's
 # projection code lives in mpassit_b200/host/)

@@ -67,6 +67,8 @@ _SPECS = {
     #        mesh builder kwargs                                  namelist                      nz  nsoil
     "c2": (dict(spacing_m=3000.0, extent_x_m=5600e3, extent_y_m=3400e3), dict(nx=1801, ny=1061, dx=3000.0), 60, 4),
     "mid": (dict(spacing_m=12000.0, extent_x_m=5600e3, extent_y_m=3400e3), dict(nx=451, ny=266, dx=12000.0), 60, 4),
+    # BASELINE.json configs[4]: 1-km regional mesh -> 1-km Lambert 1001 x 1001 (conservative snow fields)
+    "c5": (dict(spacing_m=1000.0, extent_x_m=1100e3, extent_y_m=1100e3), dict(nx=1001, ny=1001, dx=1000.0), 60, 4),
     "mini": (dict(spacing_m=30000.0, extent_x_m=2000e3, extent_y_m=1400e3), dict(nx=61, ny=41, dx=30000.0), 8, 4),
 }
 

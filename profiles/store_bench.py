@@ -41,6 +41,24 @@ def main():
             line.append(f"{name} {rg.last_ms:7.2f}/{wall:7.2f}")
             r.release()
         print(("warm-up " if it == 0 else f"iter {it}  ") + "  ".join(line) + "   (device ms / wall ms)")
+    # BASELINE.json configs[4]'s own step: conservative weights rebuilt + snow/snowh applied, every iteration
+    n, nd = wl.mesh.nCells, wl.n_mass
+    snow = torch.rand((n, 1), device="cuda")
+    snowh = torch.rand((n, 1), device="cuda")
+    o1, o2 = torch.empty((1, nd), device="cuda"), torch.empty((1, nd), device="cuda")
+    ts = []
+    for it in range(a.iters + 2):
+        rg.clear_routes()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = rg.store(*ROUTES["conserve"])
+        rg.apply(r, [snow, snowh], [o1, o2], nlev=[1, 1])
+        rg.synchronize()
+        ts.append(1e3 * (time.perf_counter() - t0))
+        r.release()
+    best = min(ts[2:])
+    print(f"conservative weights + apply(snow, snowh), rebuilt per iteration: {best:.2f} ms wall "
+          f"({nd / best * 1e3:.3e} destination cells/s; all: {[round(t, 2) for t in ts]})")
     rg.close()
 
 

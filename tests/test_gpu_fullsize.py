@@ -171,3 +171,104 @@ def test_large_target_needs_64_bit_offsets(engine_lib):
     assert torch.equal(out[3], torch.from_numpy(col.astype(np.float32)).cuda())
     rn.release()
     rg.close()
+
+
+def test_c4_variable_resolution_global_to_0p03_degree(engine_lib, orc):
+    """BASELINE.json configs[3]: variable-resolution global mesh (spacing ratio 5, refined over CONUS; 655 k cells,
+    a tenth of the 6.5 M of the real mesh so that it triangulates in seconds) -> the full 0.03-degree global lat-lon
+    target, 12000 x 6000 = 72 M points; one bilinear 55-level field (15.8 GB of output) and one nearest-neighbour
+    integer field.  Parity against the oracle on every 47th target row (128 rows, 1.5 M points): indices bit-exact,
+    nearest output bit-exact, bilinear within 1e-5; over the whole target: nothing unmapped, constants reproduced."""
+    import torch
+
+    from mpassit_b200 import lib as l
+    from mpassit_b200 import synth
+    from mpassit_b200.regrid import Regridder
+    from tests import helpers as H
+
+    mesh = synth.variable_global_mesh(655362)
+    ni, nj, nlev = 12000, 6000, 55
+    lon, lat = H.latlon_grid(ni, nj)
+    rg = Regridder(device=0)
+    rg.set_mesh(mesh.lonCell, mesh.latCell, mesh.lonVertex, mesh.latVertex, mesh.verticesOnCell)
+    rg.set_target(l.CENTER, lon, lat)
+    rows = np.arange(23, nj, 47)
+    pick = torch.from_numpy((rows[:, None] * ni + np.arange(ni)[None, :]).reshape(-1)).cuda()
+    cxyz, _, tri = H.oracle_geometry(orc, mesh)
+    dxyz = orc.sph_deg_to_cart(lon[rows], lat[rows])
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4)
+    src = (280.0 + 20.0 * torch.randn((mesh.nCells, nlev), generator=g, device="cuda")).contiguous()
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    info = r.info()
+    assert info["nDst"] == ni * nj and info["nUnmapped"] == 0 and info["nnz"] == 3 * ni * nj
+    dst = torch.empty((nlev, ni * nj), device="cuda")
+    rg.apply(r, [src], [dst], nlev=[nlev])
+    rg.synchronize()
+    got = dst[:, pick].cpu().numpy()
+    lo_, hi_ = src.amin(dim=0), src.amax(dim=0)   # a convex combination stays inside the source range, everywhere
+    assert torch.all(dst.amin(dim=1) >= lo_ - 1e-3) and torch.all(dst.amax(dim=1) <= hi_ + 1e-3)
+    del dst
+    e, c, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
+    assert (e >= 0).all()
+    want = orc.apply(*orc.ell_to_csr(e >= 0, c, w), src.cpu().numpy(), np.float32)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    r.release()
+
+    rn = rg.store(l.NEAREST_STOD, l.SRC_MESH_ELEMENT, l.CENTER)
+    ids = torch.arange(mesh.nCells, device="cuda", dtype=torch.float32).reshape(-1, 1).contiguous()  # exact below 2^24
+    veg = (torch.arange(mesh.nCells, device="cuda") * 2654435761 % 20 + 1).to(torch.float32).reshape(-1, 1).contiguous()
+    oi, ov = torch.empty((1, ni * nj), device="cuda"), torch.empty((1, ni * nj), device="cuda")
+    rg.apply(rn, [ids, veg], [oi, ov], nlev=[1, 1])
+    rg.synchronize()
+    near = orc.nearest(cxyz, dxyz)
+    assert np.array_equal(oi[0, pick].cpu().numpy().astype(np.int64), near.astype(np.int64))
+    assert torch.equal(ov[0], veg[:, 0][oi[0].long()])          # every one of the 72 M values is drawn from the source
+    rn.release()
+    rg.close()
+
+
+def test_c5_conservative_1km_weights_rebuilt_every_run(engine_lib, orc):
+    """BASELINE.json configs[4] at full size: 1-km regional mesh (1.4 M cells) -> 1-km Lambert 1001 x 1001
+    (1 M destination cells), first-order conservative `snow` / `snowh`, the weights rebuilt on every run.
+    The oracle finishes this one in seconds, so parity is direct: which sources each destination cell
+    overlaps (bit-exact, ascending ids), the overlap fractions (1e-12), and both fields (1e-5) -- and the
+    rebuilt routes are identical run after run."""
+    import torch
+
+    from mpassit_b200 import build, workload
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import Regridder
+    from tests import helpers as H
+
+    build.build_host()
+    wl = workload.make("c5")
+    mesh = wl.mesh
+    rg = Regridder(device=0)
+    workload.load_geometry(rg, wl)
+    cxyz, vxyz, _ = H.oracle_geometry(orc, mesh)
+    clat, clon = wl.grids["CORNER"]
+    cor = orc.sph_deg_to_cart(clon, clat).reshape(clat.shape[0], clat.shape[1], 3)
+    rp, cc, ww = orc.conserve(cxyz, vxyz, mesh.verticesOnCell, cor)
+    assert rp.size - 1 == 1000 * 1000
+    snow = H.synth.patchy_field(mesh.lonCell, mesh.latCell)
+    snowh = (0.01 * snow).astype(np.float32)
+    want = [orc.apply(rp, cc, ww, f, np.float32) for f in (snow, snowh)]
+    ds, dh = torch.from_numpy(snow).cuda(), torch.from_numpy(snowh).cuda()
+    for run in range(3):
+        rg.clear_routes()                      # a new run: nothing memoised
+        r = rg.store(l.CONSERVE, l.SRC_MESH_ELEMENT, l.CENTER)
+        o1, o2 = torch.full((1, 1000 * 1000), float("nan"), device="cuda"), torch.full((1, 1000 * 1000), float("nan"), device="cuda")
+        rg.apply(r, [ds, dh], [o1, o2], nlev=[1, 1])
+        rg.synchronize()
+        grp, gc, gw = r.export_csr()
+        assert np.array_equal(grp, rp) and np.array_equal(gc, cc), run
+        assert np.abs(gw - ww).max() <= 1e-12, run
+        for got, w in zip((o1, o2), want):
+            g = got.cpu().numpy()
+            assert np.abs(g - w).max() <= 1e-5 * np.abs(w).max(), run
+    # the mesh overhangs the target on every side: each destination cell is fully covered
+    frac = np.add.reduceat(gw, grp[:-1])
+    assert np.abs(frac - 1).max() <= 1e-9
+    rg.close()
