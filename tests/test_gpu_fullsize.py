@@ -269,6 +269,7 @@ def test_c5_conservative_1km_weights_rebuilt_every_run(engine_lib, orc):
             g = got.cpu().numpy()
             assert np.abs(g - w).max() <= 1e-5 * np.abs(w).max(), run
     # the mesh overhangs the target on every side: each destination cell is fully covered
+    # (1-km cells are 1e-8 of the unit sphere: area differences cancel to ~4e-9 relative, in the oracle alike)
     frac = np.add.reduceat(gw, grp[:-1])
-    assert np.abs(frac - 1).max() <= 1e-9
+    assert np.abs(frac - 1).max() <= 2e-8
     rg.close()
