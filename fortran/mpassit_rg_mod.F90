@@ -36,6 +36,7 @@ module mpassit_rg_mod
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
   public :: mprg_set_async, mprg_get_async, mprg_download, mprg_io_bytes
   public :: mprg_post_midlevels, mprg_post_ptop, mprg_route_schedule_info
+  public :: mprg_set_source_byte_order, mprg_bswap, mprg_post_affine
   public :: mprg_apply_into, mprg_put_slab, mprg_ipc_export, mprg_ipc_open, mprg_ipc_close_all
   public :: mprg_device_alloc, mprg_device_free
   public :: mprg_capture_begin, mprg_capture_end, mprg_graph_launch, mprg_graph_release
@@ -296,6 +297,27 @@ module mpassit_rg_mod
        integer(c_int), value :: stagger, dtype, mem
        integer(c_int32_t), value :: nlev
        real(c_double), intent(out) :: maxval, mincand
+     end function
+     !> sources handed over straight from a classic-NetCDF file mapping are big-endian: swapped on the device
+     integer(c_int) function mprg_set_source_byte_order(ctx, big_endian) bind(C, name="mprg_set_source_byte_order")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: big_endian
+     end function
+     !> in-place word swap of a device buffer (the writer's last step before mprg_download)
+     integer(c_int) function mprg_bswap(ctx, dev, count, dtype) bind(C, name="mprg_bswap")
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value :: ctx, dev
+       integer(c_size_t), value :: count
+       integer(c_int), value :: dtype
+     end function
+     !> x = x*scale + offset on the device: T-300, PHB = 9.81 zgrid, zero fields (write_data.F90:1339-1432)
+     integer(c_int) function mprg_post_affine(ctx, dev, count, dtype, scale, offset) bind(C, name="mprg_post_affine")
+       import :: c_int, c_ptr, c_size_t, c_double
+       type(c_ptr), value :: ctx, dev
+       integer(c_size_t), value :: count
+       integer(c_int), value :: dtype
+       real(c_double), value :: scale, offset
      end function
      integer(c_int) function mprg_io_bytes(ctx, h2d, d2h) bind(C, name="mprg_io_bytes")
        import :: c_int, c_ptr, c_int64_t

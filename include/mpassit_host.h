@@ -112,6 +112,10 @@ typedef struct mpassit_interp_io {
      * mprg_ipc_open on the other ranks -- and each rank stores its rows straight into it
      * (mprg_apply_into): the FieldGather of write_to_file is fused into the regrid */
     int32_t dst_full;
+    /* dst_device != 0 with mem == MPRG_HOST: sources are host buffers (e.g. variables mapped from the input
+     * file) but every dst / hgt / u_stag / v_stag is a DEVICE slab -- the file writer keeps the outputs in
+     * HBM for the WRF post-ops and downloads them in file byte order */
+    int32_t dst_device;
     /* wind rotation (interp.F90:138,291) uses the angles registered once with mprg_set_rotation,
      * the analogue of cosa/sina_target_grid created in define_target_grid (model_grid.F90:1113-1185) */
 } mpassit_interp_io;

@@ -181,6 +181,16 @@ int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, 
 /* same on the rows of `stagger` = MPRG_CENTER or MPRG_CENTER_HALO (u, v: [nlev][rows][ni]) */
 int mprg_rotate_winds_on(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype, int mem);
 
+/* ---- file byte order.  NetCDF classic / CDF-5 data is big-endian; the reference lets the NetCDF library
+ *      swap on the host inside nf90_get_var / nf90_put_var (input_data.F90:186,205,437..., write_data.F90:1010...).
+ *      Here file bytes cross PCIe untouched and are swapped in HBM.
+ *      mprg_set_source_byte_order(1): MPRG_HOST sources of mprg_apply* hold big-endian words (a variable
+ *      mapped straight from the input file); each uploaded range is swapped on the device before the apply.
+ *      mprg_bswap: swap `count` words (4 bytes for MPRG_F32 / int32, 8 for MPRG_F64) of a device buffer in
+ *      place -- the writer's last step before mprg_download + pwrite. */
+int mprg_set_source_byte_order(mprg_ctx *ctx, int big_endian);
+int mprg_bswap(mprg_ctx *ctx, void *dev, size_t count, int dtype);
+
 /* ---- WRF-compatibility post-ops of the writer (write_data.F90:1339-1432, wrf_mod_vars), on this
  *      rank's slab, device or host buffers.  T-300 and PHB = 9.81 zgrid are fused epilogues of
  *      mprg_apply_ex; the two below need neighbouring levels / a reduction.
@@ -189,6 +199,10 @@ int mprg_rotate_winds_on(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t n
  *      mprg_post_ptop: this rank's share of P_TOP (write_data.F90:1364-1373): *maxval = max of the
  *      whole field, *mincand = min of 0.8 x[nlev-1][.] over the points whose top-level value is >= 10
  *      (+inf if none).  P_TOP = min(MAX over ranks of maxval, MIN over ranks of mincand). */
+/* x = x * scale + offset over `count` values of a device buffer: T - 300 (write_data.F90:1339-1345, applied to
+ * every column: the reference's `< 10` guard is a no-op `continue`), PHB = 9.81 zgrid (:1417), and the
+ * all-zero MU / PH / P fields (:1356,1424,1468) with scale = offset = 0 */
+int mprg_post_affine(mprg_ctx *ctx, void *dev, size_t count, int dtype, double scale, double offset);
 int mprg_post_midlevels(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, int mem, const void *x, void *mid);
 int mprg_post_ptop(mprg_ctx *ctx, int stagger, int32_t nlev, int dtype, int mem, const void *x, double *maxval,
                    double *mincand);

@@ -861,6 +861,51 @@ __global__ void k_ptop_finish(const long long *in, double *out) {
     }
 }
 
+// Byte order of file data: NetCDF classic / CDF-5 variables are big-endian.  The reference lets the NetCDF
+// library swap on the host (nf90_get_var / nf90_put_var, input_data.F90:186, write_data.F90:1010); here file
+// bytes cross PCIe untouched and are swapped in HBM (2 x bytes of traffic at TB/s instead of a host pass).
+template <typename U>
+__device__ __forceinline__ U bswap_word(U v);
+template <>
+__device__ __forceinline__ uint32_t bswap_word<uint32_t>(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+template <>
+__device__ __forceinline__ unsigned long long bswap_word<unsigned long long>(unsigned long long v) {
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    return ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+template <typename U>
+__global__ void k_bswap(U *__restrict__ x, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = bswap_word<U>(x[i]);
+}
+template <typename T>
+__global__ void k_affine(T *__restrict__ x, size_t n, T scale, T offset) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = x[i] * scale + offset;
+}
+static unsigned stream_grid(size_t n) {  // enough CTAs to fill the device, grid-stride beyond
+    const size_t want = (n + 1023) / 1024;
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(want, (size_t)148 * 16));
+}
+
+void bswap_device(mprg_ctx *ctx, void *x, size_t count, size_t elem, cudaStream_t st) {
+    if (count == 0) return;
+    if (elem == 4) k_bswap<uint32_t><<<stream_grid(count), 256, 0, st>>>((uint32_t *)x, count);
+    else k_bswap<unsigned long long><<<stream_grid(count), 256, 0, st>>>((unsigned long long *)x, count);
+    ctx->launches++;
+    MPRG_CUDA(cudaGetLastError());
+}
+
+void post_affine_device(mprg_ctx *ctx, void *x, size_t count, int dtype, double scale, double offset) {
+    if (count == 0) return;
+    // fp32 fields: the reference computes `dum3d - 300.0` / `dum3dp1*9.81` in R8 and the NetCDF layer rounds to
+    // NF90_FLOAT; one fp32 multiply-add of fp32 data differs from that by at most one rounding (<= 6e-8 relative)
+    if (dtype == MPRG_F32) k_affine<float><<<stream_grid(count), 256, 0, ctx->stream>>>((float *)x, count, (float)scale, (float)offset);
+    else k_affine<double><<<stream_grid(count), 256, 0, ctx->stream>>>((double *)x, count, scale, offset);
+    ctx->launches++;
+    MPRG_CUDA(cudaGetLastError());
+}
+
 void post_midlevels_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, void *mid) {
     if (n <= 0 || nlev < 2) return;
     const unsigned g = (unsigned)((n + 255) / 256);

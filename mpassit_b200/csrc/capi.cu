@@ -212,6 +212,26 @@ int mprg_download(mprg_ctx *ctx, const void *dev, void *host, size_t bytes) {
     MPRG_LEAVE(ctx)
 }
 
+int mprg_set_source_byte_order(mprg_ctx *ctx, int big_endian) {
+    MPRG_ENTER(ctx)
+    ctx->srcBigEndian = big_endian != 0;
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_bswap(mprg_ctx *ctx, void *dev, size_t count, int dtype) {
+    MPRG_ENTER(ctx)
+    if (!dev && count) fail(1, "mprg_bswap: null argument");
+    bswap_device(ctx, dev, count, dtype == MPRG_F32 ? 4 : 8, ctx->stream);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_post_affine(mprg_ctx *ctx, void *dev, size_t count, int dtype, double scale, double offset) {
+    MPRG_ENTER(ctx)
+    if (!dev && count) fail(1, "mprg_post_affine: null argument");
+    post_affine_device(ctx, dev, count, dtype, scale, offset);
+    MPRG_LEAVE(ctx)
+}
+
 int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonCell_rad,
                   const double *latCell_rad, const double *lonVertex_rad, const double *latVertex_rad,
                   const int32_t *verticesOnCell) {
@@ -414,6 +434,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evOut[slot], 0));
             }
             std::vector<ApplyField> fl;
+            std::vector<std::pair<unsigned char *, size_t>> staged;  // (device address, elements) of each uploaded field
             size_t io = 0, oo = 0;
             for (int k = f; k < g; ++k) {
                 size_t b = (size_t)rh->nDst * nlev[k] * osz;
@@ -426,6 +447,7 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                     MPRG_CUDA(cudaMemcpyAsync(data, (const unsigned char *)src[k] + skip, in_bytes(k), cudaMemcpyHostToDevice,
                                               ctx->h2d_stream));
                     ctx->h2dBytes += in_bytes(k);
+                    staged.emplace_back(data, in_bytes(k) / isz);
                     s = data - skip;
                 }
                 if (dst_mem == MPRG_HOST) d = ctx->stageOut[slot].p + oo;
@@ -436,6 +458,8 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
             if (src_mem == MPRG_HOST) {
                 MPRG_CUDA(cudaEventRecord(ctx->evIn[slot], ctx->h2d_stream));
                 MPRG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evIn[slot], 0));
+                if (ctx->srcBigEndian)  // file bytes crossed PCIe untouched: swap them where bandwidth is cheap
+                    for (auto &sf : staged) bswap_device(ctx, sf.first, sf.second, isz, ctx->stream);
             }
             apply_device(ctx, rh, fl.data(), (int)fl.size(), src_dtype, dst_dtype, into_full);
             MPRG_CUDA(cudaEventRecord(ctx->evK[slot], ctx->stream));

@@ -174,6 +174,7 @@ struct mprg_ctx {
     cudaStream_t store_stream = nullptr;  // weight generation runs here, beside the copy-bound apply pipeline
     bool async = false;                   // host-buffer applies return once enqueued (mprg_set_async)
     bool capturing = false;               // between mprg_capture_begin / _end
+    bool srcBigEndian = false;            // host sources hold file-order (big-endian) words (mprg_set_source_byte_order)
     int64_t captureLaunches0 = 0;
     std::string err;
     mprg::Mesh mesh;
@@ -272,6 +273,8 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
 void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype);
 void rotation_constants(mprg_ctx *ctx, int64_t n);  // fills ctx->rotc from ctx->cosa / ctx->sina
 
+void bswap_device(mprg_ctx *ctx, void *x, size_t count, size_t elem, cudaStream_t st);
+void post_affine_device(mprg_ctx *ctx, void *x, size_t count, int dtype, double scale, double offset);
 void post_midlevels_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, void *mid);
 void post_ptop_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, double *out2_dev);
 

@@ -59,7 +59,7 @@ class InterpIO(C.Structure):
                 ("n_hist_3d", C.c_int32), ("hist_3d", C.POINTER(Field)),
                 ("n_soil", C.c_int32), ("soil", C.POINTER(Field)),
                 ("ter", C.c_void_p), ("hgt", C.c_void_p), ("u_stag", C.c_void_p), ("v_stag", C.c_void_p),
-                ("dst_full", C.c_int32)]
+                ("dst_full", C.c_int32), ("dst_device", C.c_int32)]
 
 
 _lib = None

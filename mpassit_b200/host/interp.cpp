@@ -101,8 +101,9 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
     // its own stream); interp_data as a whole stays blocking, like the reference's.
     const int was_async = mprg_get_async(ctx);
     const bool host_pass = io->mem == MPRG_HOST;
+    const int dmem = io->dst_device ? MPRG_DEVICE : io->mem;  // where the outputs live (sources: io->mem)
     const bool into = io->dst_full != 0;  // outputs are full-grid fields (own or mapped): gather fused into the store
-    if (into && host_pass) {
+    if (into && dmem == MPRG_HOST) {
         if (err && errlen) std::snprintf(err, errlen, "IN interp_data: dst_full needs device buffers");
         return 1;
     }
@@ -131,7 +132,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
         // 10-m winds are rotated after the bundle regrid (interp.F90:138-139).  With host buffers they are
         // regridded into device scratch, rotated there and downloaded, so nothing waits on a round trip.
         const bool rot10 = have_diag && u10 >= 0 && v10 >= 0 && rotate;
-        const bool rot10_dev = rot10 && (host_pass || into);
+        const bool rot10_dev = rot10 && (dmem == MPRG_HOST || into);
         if (have_diag)
             for (int i = 0; i < io->n_diag; ++i)
                 if (!(rot10_dev && (i == u10 || i == v10)))
@@ -139,7 +140,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
         auto finish_diag = [&](mprg_route *rh) {
             if (!rot10) return;
             if (!rot10_dev) {
-                ck(ctx, mprg_rotate_winds(ctx, io->diag[u10].dst, io->diag[v10].dst, 1, ddt, mem), "rotate_winds_cgrid");
+                ck(ctx, mprg_rotate_winds(ctx, io->diag[u10].dst, io->diag[v10].dst, 1, ddt, dmem), "rotate_winds_cgrid");
                 return;
             }
             int32_t j0 = 0, j1 = 0, ni = 0, nj = 0;
@@ -164,7 +165,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
         };
         if (have_diag && !cfg->interp_hist) {
             mprg_route *rh = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
-            run(ctx, rh, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
+            run(ctx, rh, diagBatch, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
             finish_diag(rh);
         }
 
@@ -229,7 +230,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                     b = diagBatch;
                 } else if (have_diag) {  // cannot happen with the reference's method sequence; kept for safety
                     mprg_route *rd = store(MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
-                    run(ctx, rd, diagBatch, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
+                    run(ctx, rd, diagBatch, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
                     finish_diag(rd);
                 }
                 for (int i = 0; i < io->n_hist_2d; ++i)
@@ -244,7 +245,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                         b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
                 if (!b.empty() || (have_diag && m_bil == MPRG_BILINEAR)) {
                     mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
-                    run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
+                    run(ctx, rh, b, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
                     if (have_diag && m_bil == MPRG_BILINEAR) finish_diag(rh);
                 }
             }
@@ -264,13 +265,13 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                     mprg_route *ru = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE1, "FieldRegridStore");
                     const void *s = d_um; void *d = io->u_stag; int32_t nl = fu->nlev;
                     ck(ctx, into ? mprg_apply_into(ctx, ru, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, nullptr, nullptr)
-                                 : mprg_apply(ctx, ru, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                                 : mprg_apply(ctx, ru, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, dmem), "FieldRegrid");
                 }
                 if (fv && io->v_stag) {  // interp.F90:313-328
                     mprg_route *rv = store(m_bil, MPRG_SRC_GRID_CENTER, MPRG_EDGE2, "FieldRegridStore");
                     const void *s = d_vm; void *d = io->v_stag; int32_t nl = fv->nlev;
                     ck(ctx, into ? mprg_apply_into(ctx, rv, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, nullptr, nullptr)
-                                 : mprg_apply(ctx, rv, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, mem), "FieldRegrid");
+                                 : mprg_apply(ctx, rv, 1, &s, &nl, chain_dt, MPRG_DEVICE, &d, ddt, dmem), "FieldRegrid");
                 }
             }
 
@@ -281,7 +282,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 for (int i = 0; i < io->n_hist_3d; ++i)
                     if (io->hist_3d[i].klass == MPASSIT_CLASS_3D_VERT)
                         b.add(io->hist_3d[i].src, io->hist_3d[i].dst, io->hist_3d[i].nlev);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
+                run(ctx, rh, b, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
             }
             // 2d_cons bundle, interp.F90:368-416 (bundle and per-field paths apply the same matrix)
             if (n2c > 0) {
@@ -290,7 +291,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 Batch b;
                 for (int i = 0; i < io->n_hist_2d; ++i)
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_CONS) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
+                run(ctx, rh, b, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
             }
             // 2d_nstd bundle, interp.F90:418-434
             if (n2n > 0) {
@@ -299,7 +300,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 Batch b;
                 for (int i = 0; i < io->n_hist_2d; ++i)
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_NSTD) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
+                run(ctx, rh, b, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
             }
             // soil bundle: whatever `method` holds now, interp.F90:436-447
             if (io->n_soil > 0) {
@@ -307,7 +308,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 mprg_route *rh = store(m_soil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
                 Batch b;
                 for (int i = 0; i < io->n_soil; ++i) b.add(io->soil[i].src, io->soil[i].dst, io->soil[i].nlev);
-                run(ctx, rh, b, sdt, mem, ddt, mem, "FieldBundleRegrid", into);
+                run(ctx, rh, b, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
             }
         }
     } catch (const Fail &f) {

@@ -172,6 +172,46 @@ int mpassit_target_coords(const mpassit_config *cfg, int stagger, double *lat, d
     return 0;
 }
 
+int mpassit_xytoll(const mpassit_config *cfg, double x, double y, int stagger, double *lat, double *lon) {
+    // xytoll, llxy_module.F90:166-216 (stagger: MPASSIT_M / _U / _V / _CORNER)
+    if (!cfg || !lat || !lon) return 1;
+    Proj p;
+    std::string why;
+    if (!make_proj(cfg, p, why)) return 2;
+    const double rx = x - ((stagger == MPASSIT_U || stagger == MPASSIT_CORNER) ? 0.5 : 0.0);
+    const double ry = y - ((stagger == MPASSIT_V || stagger == MPASSIT_CORNER) ? 0.5 : 0.0);
+    if (p.code == MPASSIT_PROJ_LC) ijll_lc(rx, ry, p, lat, lon);
+    else ijll_latlon(rx, ry, p, lat, lon);
+    return 0;
+}
+
+int mpassit_get_map_factor(const mpassit_config *cfg, const double *xlat, int64_t n, double *mapfac) {
+    // get_map_factor, model_grid.F90:2229-2365 (Saucier pp. 32-33); mapfac_x == mapfac_y for Lambert.
+    // For 'lat-lon' targets no branch of the reference assigns the array (it is written uninitialised);
+    // this mirror writes 0 there.
+    if (!cfg || !xlat || !mapfac) return 1;
+    if (cfg->proj_code == MPASSIT_PROJ_LC) {
+        if (cfg->truelat1 != cfg->truelat2) {
+            const double colat1 = RAD_PER_DEG * (90.0 - cfg->truelat1), colat2 = RAD_PER_DEG * (90.0 - cfg->truelat2);
+            const double nn = (std::log(std::sin(colat1)) - std::log(std::sin(colat2))) /
+                              (std::log(std::tan(colat1 / 2.0)) - std::log(std::tan(colat2 / 2.0)));
+            for (int64_t k = 0; k < n; ++k) {
+                const double colat = RAD_PER_DEG * (90.0 - xlat[k]);
+                mapfac[k] = std::sin(colat2) / std::sin(colat) * std::pow(std::tan(colat / 2.0) / std::tan(colat2 / 2.0), nn);
+            }
+        } else {
+            const double colat0 = RAD_PER_DEG * (90.0 - cfg->truelat1);
+            for (int64_t k = 0; k < n; ++k) {
+                const double colat = RAD_PER_DEG * (90.0 - xlat[k]);
+                mapfac[k] = std::sin(colat0) / std::sin(colat) * std::pow(std::tan(colat / 2.0) / std::tan(colat0 / 2.0), std::cos(colat0));
+            }
+        }
+        return 0;
+    }
+    for (int64_t k = 0; k < n; ++k) mapfac[k] = 0.0;
+    return 0;
+}
+
 void mpassit_get_rotang(const double *xlat, const double *xlon, int32_t ni, int32_t nj, double *cosa, double *sina) {
     // get_rotang, model_grid.F90:2450-2507: centred in j, one-sided on the first/last row.
     // (The reference evaluates this per PET tile, so with >1 PET its one-sided rows sit

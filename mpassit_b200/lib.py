@@ -29,7 +29,7 @@ EXPORTS = [
     "mprg_release", "mprg_clear_routes", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
     "mprg_apply", "mprg_apply_ex", "mprg_apply_into", "mprg_put_slab", "mprg_ipc_export", "mprg_ipc_open", "mprg_ipc_close_all", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
     "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_capture_begin", "mprg_capture_end", "mprg_graph_launch", "mprg_graph_release", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
-    "mprg_profile_reset", "mprg_route_src_referenced", "mprg_route_schedule_info",
+    "mprg_profile_reset", "mprg_route_src_referenced", "mprg_route_schedule_info", "mprg_set_source_byte_order", "mprg_bswap", "mprg_post_affine",
 ]
 
 
@@ -95,6 +95,9 @@ def load() -> C.CDLL:
     L.mprg_capture_end.argtypes = [vp, pp]
     L.mprg_graph_launch.argtypes = [vp, vp]
     L.mprg_graph_release.argtypes = [vp, vp]
+    L.mprg_set_source_byte_order.argtypes = [vp, C.c_int]
+    L.mprg_bswap.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.mprg_post_affine.argtypes = [vp, vp, C.c_size_t, C.c_int, dbl, dbl]
     L.mprg_set_async.argtypes = [vp, C.c_int]
     L.mprg_get_async.argtypes = [vp]
     L.mprg_download.argtypes = [vp, vp, vp, C.c_size_t]
