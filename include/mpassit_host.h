@@ -127,6 +127,45 @@ int mpassit_classify_fields(const mpassit_config *cfg, mpassit_interp_io *io, in
 /* interp_data: every Store/Regrid pair in the reference's order, through the engine */
 int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp_io *io, char *err, size_t errlen);
 
+
+/* xytoll, llxy_module.F90:166-216: grid index (x, y) of stagger MPASSIT_M/_U/_V/_CORNER -> lat, lon (degrees) */
+int mpassit_xytoll(const mpassit_config *cfg, double x, double y, int stagger, double *lat, double *lon);
+/* get_map_factor, model_grid.F90:2229-2365, on n latitudes (Lambert; 0 for lat-lon targets, which the
+ * reference leaves unassigned) */
+int mpassit_get_map_factor(const mpassit_config *cfg, const double *xlat, int64_t n, double *mapfac);
+
+/* ---- program mpassit, mpassit.F90:23-146, files on both sides ------------------------------------------
+ * read_setup_namelist -> define_target_grid -> define_input_grid -> read_input_data -> interp_data ->
+ * write_to_file for this rank's row slab.  Input files: NetCDF classic (CDF-1/2/5) MPAS grid / diag / history
+ * files, mapped and consumed in file order and byte order (no transpose, no host swap); output: one NetCDF
+ * classic file holding the reference's dimensions, variables and attributes (write_data.F90:170-994), each
+ * rank writing its own rows with pwrite.  The var-list files diaglist / histlist_2d / histlist_3d /
+ * histlist_soil are read from `varlist_dir` (NULL = the working directory, as the reference does).
+ * `comm` stands in for the MPI the reference's host already has: it is called collectively by every rank
+ * with op = MPASSIT_COMM_BARRIER (vals NULL), or MPASSIT_COMM_MAX / _MIN to all-reduce vals[0..n) in place
+ * (P_TOP, write_data.F90:1364-1373).  May be NULL when nranks == 1. */
+enum { MPASSIT_COMM_BARRIER = 0, MPASSIT_COMM_MAX = 1, MPASSIT_COMM_MIN = 2 };
+typedef void (*mpassit_comm_fn)(void *arg, int op, double *vals, int n);
+typedef struct mpassit_run_stats {
+    double setup_ms, read_ms, interp_ms, write_ms, total_ms; /* wall clock of the stages on this rank */
+    int64_t n_cells, bytes_in, bytes_out;                    /* source bytes referenced in the input files; bytes this rank wrote */
+    int32_t n_vars_written, output_version;                  /* regridded variables; 2 = CDF-2, 5 = CDF-5 */
+    double p_top;
+} mpassit_run_stats;
+int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, int rank, int nranks,
+                mpassit_comm_fn comm, void *comm_arg, mpassit_run_stats *stats, char *err, size_t errlen);
+
+/* ---- NetCDF classic container (host/ncio.cpp), test hooks.  No CUDA involved.
+ * mpassit_nc_describe: one line per header item -- "version V numrecs N", "dim NAME LEN", "gatt NAME TYPE NELEMS",
+ *   "var NAME TYPE BEGIN DIM...", "vatt VAR NAME TYPE NELEMS" -- into out (truncated to outlen).
+ * mpassit_nc_get: elements [first, first+n) of record `rec` of a numeric variable as doubles.
+ * mpassit_nc_copy: read src with the reader and write every dimension, attribute, variable and record again
+ *   with the writer in format `version` (1, 2, 5; 0 = automatic). */
+int mpassit_nc_describe(const char *path, char *out, size_t outlen, char *err, size_t errlen);
+int mpassit_nc_get(const char *path, const char *var, int64_t rec, int64_t first, int64_t n, double *out,
+                   char *err, size_t errlen);
+int mpassit_nc_copy(const char *src, const char *dst, int version, char *err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,14 +94,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 HOST_LIB = os.path.join(HERE, "libmpassit_host.so")
-HOST_SRC = ["setup.cpp", "target_grid.cpp", "interp.cpp"]
+HOST_SRC = ["setup.cpp", "target_grid.cpp", "interp.cpp", "ncio.cpp", "run.cpp"]
 
 
 def build_host(force: bool = False) -> str:
     """libmpassit_host.so: C++ mirror of the reference's Fortran host stages (no CUDA code;
     calls the engine through its C ABI, resolved from the same directory via rpath)."""
     srcs = [os.path.join(HERE, "host", s) for s in HOST_SRC]
-    deps = srcs + [os.path.join(HERE, "..", "include", "mpassit_host.h"), os.path.join(HERE, "..", "include", "mpassit_rg.h"), LIB]
+    deps = srcs + [os.path.join(HERE, "host", "ncio.hpp"), os.path.join(HERE, "..", "include", "mpassit_host.h"), os.path.join(HERE, "..", "include", "mpassit_rg.h"), LIB]
     if force or _stale(HOST_LIB, deps):
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOST_LIB, *srcs,
                "-L" + HERE, "-lmpassit_rg", "-Wl,-rpath,$ORIGIN"]

@@ -62,6 +62,15 @@ class InterpIO(C.Structure):
                 ("dst_full", C.c_int32), ("dst_device", C.c_int32)]
 
 
+class RunStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("setup_ms", "read_ms", "interp_ms", "write_ms", "total_ms")] + \
+               [(n, C.c_int64) for n in ("n_cells", "bytes_in", "bytes_out")] + \
+               [("n_vars_written", C.c_int32), ("output_version", C.c_int32), ("p_top", C.c_double)]
+
+
+COMM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int)
+COMM_BARRIER, COMM_MAX, COMM_MIN = 0, 1, 2
+
 _lib = None
 
 
@@ -88,6 +97,12 @@ def load() -> C.CDLL:
     L.mpassit_get_rotang.restype = None
     L.mpassit_classify_fields.argtypes = [C.POINTER(Config), C.POINTER(InterpIO)] + [C.POINTER(i32)] * 4
     L.mpassit_interp_data.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(InterpIO), cp, C.c_size_t]
+    L.mpassit_xytoll.argtypes = [C.POINTER(Config), C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.mpassit_get_map_factor.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64, C.c_void_p]
+    L.mpassit_run.argtypes = [cp, cp, C.c_int, C.c_int, C.c_int, COMM_FN, C.c_void_p, C.POINTER(RunStats), cp, C.c_size_t]
+    L.mpassit_nc_describe.argtypes = [cp, cp, C.c_size_t, cp, C.c_size_t]
+    L.mpassit_nc_get.argtypes = [cp, cp, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, cp, C.c_size_t]
+    L.mpassit_nc_copy.argtypes = [cp, cp, C.c_int, cp, C.c_size_t]
     _lib = L
     return L
 
@@ -262,3 +277,70 @@ def _build_io(*, diag=(), hist_2d=(), hist_3d=(), soil=(), ter=None, hgt=None, u
     io.dst_full = int(bool(dst_full))
     io._keep = keep
     return io, keep
+
+
+# ---- program mpassit with files on both sides (host/run.cpp) -------------------------------------------
+def xytoll(cfg: Config, x: float, y: float, stagger: int = 1) -> tuple[float, float]:
+    lat, lon = C.c_double(), C.c_double()
+    load().mpassit_xytoll(C.byref(cfg), x, y, stagger, C.byref(lat), C.byref(lon))
+    return lat.value, lon.value
+
+
+def get_map_factor(cfg: Config, lat: np.ndarray) -> np.ndarray:
+    lat = np.ascontiguousarray(lat, np.float64)
+    out = np.empty_like(lat)
+    load().mpassit_get_map_factor(C.byref(cfg), lat.ctypes.data, lat.size, out.ctypes.data)
+    return out
+
+
+def torch_comm(group=None):
+    """The `comm` callback of mpassit_run on top of torch.distributed (what MPI is to the reference's host)."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(_arg, op, vals, n):
+        if op == COMM_BARRIER:
+            dist.barrier(group=group)
+            return
+        t = torch.tensor([vals[i] for i in range(n)], dtype=torch.float64)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == COMM_MAX else dist.ReduceOp.MIN, group=group)
+        for i, v in enumerate(t.cpu().tolist()):
+            vals[i] = v
+
+    return COMM_FN(fn)
+
+
+def run(namelist: str, varlist_dir: str | None = None, device: int = 0, rank: int = 0, nranks: int = 1, comm=None) -> RunStats:
+    """`mpassit <namelist>` (mpassit.F90:23-146): MPAS NetCDF-classic files in, one WRF-style file out."""
+    st, e = RunStats(), _err()
+    cb = comm if comm is not None else C.cast(None, COMM_FN)
+    rc = load().mpassit_run(namelist.encode(), varlist_dir.encode() if varlist_dir else None, device, rank, nranks, cb, None,
+                            C.byref(st), e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return st
+
+
+def nc_describe(path: str) -> list[list[str]]:
+    out, e = C.create_string_buffer(1 << 20), _err()
+    rc = load().mpassit_nc_describe(path.encode(), out, len(out), e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return [ln.split(" ") for ln in out.value.decode().splitlines()]
+
+
+def nc_get(path: str, var: str, n: int, rec: int = 0, first: int = 0) -> np.ndarray:
+    out, e = np.empty(n, np.float64), _err()
+    rc = load().mpassit_nc_get(path.encode(), var.encode(), rec, first, n, out.ctypes.data, e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return out
+
+
+def nc_copy(src: str, dst: str, version: int = 0) -> None:
+    e = _err()
+    rc = load().mpassit_nc_copy(src.encode(), dst.encode(), version, e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())

@@ -145,7 +145,7 @@ void to_big_endian(void *p, size_t elem, size_t n) {
         for (size_t k = 0; k < elem / 2; ++k) std::swap(b[k], b[elem - 1 - k]);
 }
 
-static double be_number(const uint8_t *p, int type) {
+double be_number(const uint8_t *p, int type) {
     switch (type) {
         case NC_BYTE: return (double)(int8_t)p[0];
         case NC_CHAR: case NC_UBYTE: return (double)p[0];
@@ -371,6 +371,12 @@ Att *Writer::new_att(int varid, const std::string &name) {
     list.back().name = name;
     return &list.back();
 }
+void Writer::att_raw(int varid, const Att &a) {
+    Att *t = new_att(varid, a.name);
+    t->type = a.type;
+    t->nelems = a.nelems;
+    t->raw = a.raw;
+}
 void Writer::att_text(int varid, const std::string &name, const std::string &value) {
     Att *a = new_att(varid, name);
     a->type = NC_CHAR;
@@ -555,3 +561,99 @@ bool Writer::close(std::string &err) {
 }
 
 }  // namespace ncio
+
+// ---------------------------------------------------------------------------
+// C test hooks (include/mpassit_host.h)
+// ---------------------------------------------------------------------------
+#include <cstdio>
+
+#include "../../include/mpassit_host.h"
+
+namespace {
+void put_err(char *err, size_t n, const std::string &m) {
+    if (err && n) std::snprintf(err, n, "%s", m.c_str());
+}
+}  // namespace
+
+extern "C" {
+
+int mpassit_nc_describe(const char *path, char *out, size_t outlen, char *err, size_t errlen) {
+    ncio::Reader r;
+    std::string why;
+    if (!path || !r.open(path, why)) {
+        put_err(err, errlen, why);
+        return 1;
+    }
+    std::string s = "version " + std::to_string(r.version) + " numrecs " + std::to_string(r.numrecs) + "\n";
+    for (const ncio::Dim &d : r.dims) s += "dim " + d.name + " " + std::to_string(d.len) + "\n";
+    for (const ncio::Att &a : r.gatts) s += "gatt " + a.name + " " + std::to_string(a.type) + " " + std::to_string(a.nelems) + "\n";
+    for (const ncio::Var &v : r.vars) {
+        s += "var " + v.name + " " + std::to_string(v.type) + " " + std::to_string(v.begin);
+        for (int d : v.dimids) s += " " + r.dims[d].name;
+        s += "\n";
+        for (const ncio::Att &a : v.atts)
+            s += "vatt " + v.name + " " + a.name + " " + std::to_string(a.type) + " " + std::to_string(a.nelems) + "\n";
+    }
+    if (out && outlen) std::snprintf(out, outlen, "%s", s.c_str());
+    return 0;
+}
+
+int mpassit_nc_get(const char *path, const char *var, int64_t rec, int64_t first, int64_t n, double *out, char *err,
+                   size_t errlen) {
+    ncio::Reader r;
+    std::string why;
+    if (!path || !var || !r.open(path, why)) {
+        put_err(err, errlen, why);
+        return 1;
+    }
+    const ncio::Var *v = r.var(var);
+    if (!v) {
+        put_err(err, errlen, std::string("NetCDF: Variable not found: ") + var);
+        return 2;
+    }
+    const uint8_t *p = r.data(*v, (uint64_t)rec);
+    if (!p || first < 0 || n < 0 || (uint64_t)(first + n) > r.count(*v)) {
+        put_err(err, errlen, "NetCDF: Start+count exceeds dimension bound");
+        return 3;
+    }
+    const size_t es = ncio::type_size(v->type);
+    for (int64_t i = 0; i < n; ++i) out[i] = ncio::be_number(p + (first + i) * es, v->type);
+    return 0;
+}
+
+int mpassit_nc_copy(const char *src, const char *dst, int version, char *err, size_t errlen) {
+    ncio::Reader r;
+    std::string why;
+    if (!src || !dst || !r.open(src, why)) {
+        put_err(err, errlen, why);
+        return 1;
+    }
+    ncio::Writer w(version);
+    for (const ncio::Dim &d : r.dims) w.def_dim(d.name, d.len);
+    for (const ncio::Att &a : r.gatts) w.att_raw(-1, a);
+    for (const ncio::Var &v : r.vars) {
+        const int id = w.def_var(v.name, v.type, v.dimids);
+        for (const ncio::Att &a : v.atts) w.att_raw(id, a);
+    }
+    if (!w.enddef(dst, r.numrecs, true, why)) {
+        put_err(err, errlen, why);
+        return 2;
+    }
+    for (size_t i = 0; i < r.vars.size(); ++i) {
+        const ncio::Var &v = r.vars[i];
+        const uint64_t bytes = r.count(v) * ncio::type_size(v.type);
+        const uint64_t nrec = v.record ? r.numrecs : 1;
+        for (uint64_t k = 0; k < nrec; ++k)
+            if (!w.write_raw((int)i, k, 0, r.data(v, k), bytes, why)) {
+                put_err(err, errlen, why);
+                return 3;
+            }
+    }
+    if (!w.close(why)) {
+        put_err(err, errlen, why);
+        return 4;
+    }
+    return 0;
+}
+
+}  // extern "C"

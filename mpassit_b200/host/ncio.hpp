@@ -87,6 +87,7 @@ class Writer {
     ~Writer();
     int def_dim(const std::string &name, uint64_t len);  // len 0 = record dimension
     // varid < 0: global attribute
+    void att_raw(int varid, const Att &a);  // big-endian payload as read
     void att_text(int varid, const std::string &name, const std::string &value);
     void att_int(int varid, const std::string &name, int32_t value);
     void att_double(int varid, const std::string &name, double value);
@@ -115,6 +116,8 @@ class Writer {
     Att *new_att(int varid, const std::string &name);
 };
 
+// one big-endian value of NetCDF type `type` as a double
+double be_number(const uint8_t *p, int type);
 // host byte swap of small arrays
 void to_big_endian(void *p, size_t elem, size_t n);
 

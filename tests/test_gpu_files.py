@@ -1,0 +1,158 @@
+"""`mpassit <namelist>` with files on both sides (mpassit_b200/host/run.cpp) on the GPU:
+MPAS NetCDF-classic files -> mapped sources, byte swap in HBM, interp_data, WRF post-ops in HBM, per-slab pwrite ->
+output file, compared with the in-memory pass of the same fields (itself held to the oracle by test_gpu_methods)
+plus the writer's arithmetic (write_data.F90:1339-1432) restated in numpy."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import mpas_files
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def host(engine_lib):
+    from mpassit_b200 import build, host
+
+    build.build_host()
+    host.load()
+    return host
+
+
+def _reference_pass(wl):
+    """Device-buffer interp_data of the synthetic fields: {output name: [nlev][nj][ni] fp32}, plus the sources."""
+    from mpassit_b200 import lib as l
+    from mpassit_b200 import workload
+    from mpassit_b200.regrid import Regridder
+
+    rg = Regridder(device=0)
+    workload.load_geometry(rg, wl)
+    F = workload.make_fields(wl, device="cuda:0")
+    workload.run_interp(rg, wl, F["dev"], l.DEVICE)
+    rg.synchronize()
+    D = F["dev"]
+    src = {g: [(s.name, s.src.cpu().numpy()) for s in D[g]] for g in ("diag", "hist_2d", "hist_3d", "soil")}
+    ter = D["ter"].cpu().numpy()
+    njM, niM = wl.grids["M"][0].shape
+    got = {}
+    for g in ("diag", "hist_2d", "hist_3d", "soil"):
+        for s in D[g]:
+            if s.name.startswith("uReconstruct"):
+                continue
+            got[s.target_name] = s.dst.cpu().numpy().reshape(s.nlev, njM, niM)
+    got["HGT"] = D["hgt"].cpu().numpy().reshape(njM, niM)
+    got["U"] = D["u_stag"].cpu().numpy().reshape((wl.nz,) + wl.grids["U"][0].shape)
+    got["V"] = D["v_stag"].cpu().numpy().reshape((wl.nz,) + wl.grids["V"][0].shape)
+    rg.close()
+    return got, src, ter
+
+
+def _expect_file(got, wl):
+    """What write_to_file puts in the file for the regridded fields `got` (wrf_mod_vars = .true.)."""
+    f32 = np.float32
+    # 2-D variables are [south_north][west_east] in the file (record dimension dropped by the reader)
+    want = {k: (v[0] if (v.ndim == 3 and v.shape[0] == 1) else v) for k, v in got.items()}
+    want["T"] = got["T"] * f32(1.0) + f32(-300.0)               # write_data.F90:1339-1345 (the `< 10` guard is a no-op)
+    phb = got["PHB"]
+    zc = np.empty_like(phb)
+    zc[:-1] = f32(0.5) * (phb[1:] + phb[:-1])                    # :1406-1412
+    zc[-1] = 9.9692099683868690e+36                              # the level the reference never writes: fill value
+    want["Z_C"] = zc
+    want["PHB"] = phb * f32(9.81)                                # :1414
+    want["PB"] = got["P_HYD"]                                    # :1376 writes dum3dt, which still holds P_HYD
+    for z, like in (("MU", "MUB"), ("P", "P_HYD"), ("PH", "PHB")):
+        want[z] = np.zeros_like(got[like])                       # :1356, :1468, :1424
+    p = got["P_HYD"].astype(np.float64)
+    top = p[-1]
+    cand = top[top >= 10.0] * 0.8
+    want["P_TOP"] = f32(min(p.max(), cand.min() if cand.size else np.inf))   # :1364-1373
+    return want
+
+
+def _check(out, want, exact=("XLAND", "TSLB", "SMOIS", "SH2O", "MU", "P", "PH", "PB")):
+    checked = 0
+    for k, w in want.items():
+        g = out[k]
+        assert g.shape == w.shape, (k, g.shape, w.shape)
+        if k in exact:
+            assert np.array_equal(g, w), k
+        else:
+            scale = max(float(np.abs(w[np.abs(w) < 1e30]).max()), 1e-30)
+            assert np.abs(g.astype(np.float64) - w.astype(np.float64)).max() <= 2e-6 * scale, (k, np.abs(g - w).max(), scale)
+        checked += 1
+    return checked
+
+
+def test_files_in_files_out_single_rank(host, tmp_path):
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    got, src, ter = _reference_pass(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), src, ter)
+    st = host.run(nl, str(tmp_path), device=0)
+    out, g, va, dims, order = mpas_files.read_output(paths["out"])
+    want = _expect_file(got, wl)
+    assert set(want) <= set(out)
+    assert _check(out, want) >= 45
+    assert st.n_vars_written == len(got) - 1 and st.output_version == 2  # HGT is written apart
+    assert abs(st.p_top - float(want["P_TOP"])) <= 1e-6 * abs(float(want["P_TOP"]))
+    nM = wl.n_mass
+    assert st.bytes_in == sum(a.size for gl in src.values() for _, a in gl) * 4
+    assert st.bytes_out >= sum(v.size for k, v in got.items()) * 4 + got["P_HYD"].size * 4 + (wl.nz * nM) * 4
+    # a field the engine never wrote stays zero; the grid description is there
+    assert not out["P"].any() and out["XLAT"].shape == wl.grids["M"][0].shape
+
+
+def test_files_double_precision_sources(host, tmp_path):
+    """An MPAS file written in double precision (input_data.F90 reads into R8 either way): NC_DOUBLE sources are
+    swapped as 8-byte words and regridded to the same fp32 outputs."""
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    got, src, ter = _reference_pass(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), src, ter, real="f8")
+    host.run(nl, str(tmp_path), device=0)
+    out = mpas_files.read_output(paths["out"])[0]
+    want = _expect_file(got, wl)
+    # fp64 sources accumulate in fp64: equal to the fp32 pass within its accumulation error
+    for k in ("T", "QVAPOR", "PSFC", "U", "V", "REFL_10CM", "SNOW", "HGT"):
+        scale = float(np.abs(want[k]).max())
+        assert np.abs(out[k].astype(np.float64) - want[k]).max() <= 1e-5 * scale, k
+    for k in ("XLAND", "TSLB"):
+        assert np.array_equal(out[k], want[k]), k
+
+
+def test_files_two_rank_slabs_tile_the_single_rank_file(host, tmp_path):
+    """Two ranks (emulated one after the other on one device) write their own rows of the same file with pwrite;
+    the result equals the single-rank file byte for byte, P_TOP included (its max / min partials are combined by
+    the host's comm callback, here replayed from a recording pass)."""
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    got, src, ter = _reference_pass(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), src, ter)
+    host.run(nl, str(tmp_path), device=0)
+    single = open(paths["out"], "rb").read()
+    os.remove(paths["out"])
+
+    rec = {host.COMM_MAX: [], host.COMM_MIN: []}
+
+    def recording(_a, op, vals, n):
+        if op != host.COMM_BARRIER:
+            rec[op].append(vals[0])
+
+    def combined(_a, op, vals, n):
+        if op == host.COMM_MAX:
+            vals[0] = max(rec[op])
+        elif op == host.COMM_MIN:
+            vals[0] = min(rec[op])
+
+    for cb in (recording, combined):
+        fn = host.COMM_FN(cb)
+        for rank in (0, 1):
+            host.run(nl, str(tmp_path), device=0, rank=rank, nranks=2, comm=fn)
+    assert len(rec[host.COMM_MAX]) == 2
+    assert open(paths["out"], "rb").read() == single

@@ -109,3 +109,59 @@ def test_gather_runs_cover_the_field_exactly_once(engine_lib):
                 cover[fo:fo + n] += 1
                 total += n
         assert (cover == 1).all() and total == cover.size
+
+
+def _file_worker(rank, world, port, rundir, q):
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    from mpassit_b200 import host
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        host.load()
+        cb = host.torch_comm()
+        # the reductions mpassit_run asks of its host for P_TOP (write_data.F90:1364-1373)
+        v = (C.c_double * 2)(10.0 + rank, -3.0 * rank)
+        cb(None, host.COMM_MAX, v, 2)
+        mx = list(v)
+        v = (C.c_double * 1)(5.0 - rank)
+        cb(None, host.COMM_MIN, v, 1)
+        # header-only run: rank 0 creates the file, the others wait at the barrier and open the same layout
+        st = host.run(os.path.join(rundir, "namelist.files"), rundir, device=-1, rank=rank, nranks=world, comm=cb)
+        dist.barrier()
+        q.put((rank, mx, v[0], st.output_version, os.path.getsize(os.path.join(rundir, "mpassit_out.nc"))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_file_driver_comm_callback_and_shared_output_file(engine_lib, tmp_path):
+    import torch.multiprocessing as mp
+
+    from mpassit_b200 import build, host, workload
+    from tests import mpas_files
+
+    build.build_host()
+    host.load()
+    wl = workload.make("mini", rundir=str(tmp_path))
+    F = {g: [(nm, workload._field_values_torch(wl, g, nm, wl.levels_of(g, nm), k, "cpu").numpy())
+             for k, (nm, _) in enumerate(wl.lists[g])] for g in ("diag", "hist_2d", "hist_3d", "soil")}
+    mpas_files.write_case(wl, str(tmp_path), F, np.zeros(wl.mesh.lonCell.size, np.float32))
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_file_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, mx, mn, ver, size in res:
+        assert mx == [11.0, 0.0] and mn == 4.0 and ver == 2
+        assert size == res[0][4] > 0
+    out, g, va, dims, order = mpas_files.read_output(str(tmp_path / "mpassit_out.nc"))
+    assert dims["west_east"] == wl.cfg.i_target and "PB" in order

@@ -1,0 +1,264 @@
+"""NetCDF classic container of the host mirror (mpassit_b200/host/ncio.cpp) against scipy.io.netcdf_file, an
+independent implementation of the same format; and the CPU-side behaviour of the file driver (mpassit_run)."""
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from mpassit_b200 import defaults
+from tests import mpas_files
+
+
+@pytest.fixture(scope="module")
+def host(engine_lib):
+    from mpassit_b200 import build, host
+
+    build.build_host()
+    host.load()
+    return host
+
+
+def _sample(path, version):
+    rng = np.random.default_rng(7)
+    data = {}
+    with netcdf_file(path, "w", version=version) as f:
+        f.createDimension("Time", None)
+        f.createDimension("nCells", 37)
+        f.createDimension("nVertLevels", 5)
+        f.createDimension("StrLen", 7)  # odd sizes: padding to 4 bytes matters
+        f.title = b"sample"
+        f.config_dt = np.float64(18.0)
+        f.levels = np.int32(5)
+        v = f.createVariable("fixed", "f8", ("nCells",))
+        v.units = b"m"
+        data["fixed"] = rng.normal(size=37)
+        v[:] = data["fixed"]
+        v = f.createVariable("idx", "i4", ("nCells", "nVertLevels"))
+        data["idx"] = rng.integers(-5, 1 << 20, size=(37, 5)).astype(np.int32)
+        v[:] = data["idx"]
+        v = f.createVariable("theta", "f4", ("Time", "nCells", "nVertLevels"))
+        v.long_name = b"potential temperature"
+        data["theta"] = rng.normal(300, 5, size=(3, 37, 5)).astype(np.float32)
+        v = f.createVariable("xtime", "S1", ("Time", "StrLen"))
+        data["xtime"] = np.frombuffer(b"abcdefghijklmnopqrstu", "S1").reshape(3, 7)
+        v2 = f.createVariable("s", "i2", ("Time",))
+        data["s"] = np.array([3, -2, 9], np.int16)
+        for r in range(3):
+            f.variables["theta"][r] = data["theta"][r]
+            f.variables["xtime"][r] = data["xtime"][r]
+            v2[r] = data["s"][r]
+    return data
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_reader_against_scipy_files(host, tmp_path, version):
+    p = str(tmp_path / f"s{version}.nc")
+    data = _sample(p, version)
+    d = host.nc_describe(p)
+    assert d[0] == ["version", str(version), "numrecs", "3"]
+    dims = {r[1]: int(r[2]) for r in d if r[0] == "dim"}
+    assert dims == {"Time": 0, "nCells": 37, "nVertLevels": 5, "StrLen": 7}
+    assert {r[1] for r in d if r[0] == "gatt"} == {"title", "config_dt", "levels"}
+    assert sorted(r[1] for r in d if r[0] == "var") == sorted(["fixed", "idx", "theta", "xtime", "s"])  # scipy orders variables by size
+    assert np.array_equal(host.nc_get(p, "fixed", 37), data["fixed"])
+    assert np.array_equal(host.nc_get(p, "idx", 37 * 5), data["idx"].reshape(-1))
+    for r in range(3):
+        assert np.array_equal(host.nc_get(p, "theta", 37 * 5, rec=r), data["theta"][r].reshape(-1).astype(np.float64))
+        assert host.nc_get(p, "s", 1, rec=r)[0] == data["s"][r]
+    assert np.array_equal(host.nc_get(p, "theta", 4, rec=1, first=11), data["theta"][1].reshape(-1)[11:15].astype(np.float64))
+    with pytest.raises(host.HostError, match="Variable not found"):
+        host.nc_get(p, "nope", 1)
+    with pytest.raises(host.HostError, match="exceeds"):
+        host.nc_get(p, "fixed", 38)
+    with pytest.raises(host.HostError, match="exceeds"):
+        host.nc_get(p, "theta", 1, rec=3)
+
+
+@pytest.mark.parametrize("src_version,dst_version", [(1, 1), (1, 2), (2, 2), (2, 1), (2, 5), (1, 0)])
+def test_writer_round_trip(host, tmp_path, src_version, dst_version):
+    """reader -> writer -> (scipy for CDF-1/2, the reader itself for CDF-5): same dimensions, attributes and values."""
+    p, q = str(tmp_path / "a.nc"), str(tmp_path / "b.nc")
+    data = _sample(p, src_version)
+    host.nc_copy(p, q, dst_version)
+    want_version = dst_version or 2
+    dq = host.nc_describe(q)
+    assert dq[0] == ["version", str(want_version), "numrecs", "3"]
+    strip = lambda d: [[x for i, x in enumerate(r) if not (r[0] == "var" and i == 3)] for r in d[1:]]  # noqa: E731  (offsets differ)
+    assert strip(dq) == strip(host.nc_describe(p))
+    if want_version in (1, 2):
+        with netcdf_file(q, "r", mmap=False) as f:
+            assert f.version_byte == want_version
+            assert f.title == b"sample" and f.config_dt == 18.0 and f.levels == 5
+            assert f.variables["fixed"].units == b"m"
+            assert f.variables["theta"].long_name == b"potential temperature"
+            for k, a in data.items():
+                assert np.array_equal(f.variables[k][:], a), k
+    for r in range(3):
+        assert np.array_equal(host.nc_get(q, "theta", 37 * 5, rec=r), data["theta"][r].reshape(-1).astype(np.float64))
+        assert host.nc_get(q, "s", 1, rec=r)[0] == data["s"][r]
+    assert np.array_equal(host.nc_get(q, "idx", 37 * 5), data["idx"].reshape(-1))
+
+
+def test_reader_rejects_what_it_cannot_read(host, tmp_path):
+    h5 = tmp_path / "h5.nc"
+    h5.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(host.HostError, match="NetCDF-4 / HDF5"):
+        host.nc_describe(str(h5))
+    junk = tmp_path / "junk.nc"
+    junk.write_bytes(b"not a netcdf file at all")
+    with pytest.raises(host.HostError, match="magic"):
+        host.nc_describe(str(junk))
+    p = str(tmp_path / "ok.nc")
+    _sample(p, 2)
+    raw = open(p, "rb").read()
+    cut = tmp_path / "cut.nc"
+    cut.write_bytes(raw[: len(raw) - 40])  # data section shorter than the header promises
+    with pytest.raises(host.HostError, match="past the end"):
+        host.nc_describe(str(cut))
+    cut.write_bytes(raw[:60])  # header itself truncated
+    with pytest.raises(host.HostError):
+        host.nc_describe(str(cut))
+    with pytest.raises(host.HostError):
+        host.nc_describe(str(tmp_path / "missing.nc"))
+
+
+def test_mpas_file_helper_matches_the_reference_input_contract(host, tmp_path):
+    """The synthetic init file carries what define_input_grid reads (model_grid.F90:286-419), in file order."""
+    from mpassit_b200 import synth
+
+    mesh = synth.regional_delaunay_mesh(n_points=300)
+    p = str(tmp_path / "init.nc")
+    ter = np.linspace(0, 1500, mesh.lonCell.size).astype(np.float32)
+    mpas_files.write_grid_file(p, mesh, nz=6, nsoil=4, ter=ter)
+    dims = {r[1]: int(r[2]) for r in host.nc_describe(p) if r[0] == "dim"}
+    assert dims["nCells"] == mesh.lonCell.size and dims["nVertLevelsP1"] == 7 and dims["nSoilLevels"] == 4
+    assert np.array_equal(host.nc_get(p, "lonCell", mesh.lonCell.size), mesh.lonCell)
+    assert np.array_equal(host.nc_get(p, "verticesOnCell", mesh.verticesOnCell.size), mesh.verticesOnCell.reshape(-1))
+    assert np.allclose(host.nc_get(p, "zs", 4), [0.05, 0.25, 0.7, 1.5])
+    assert np.array_equal(host.nc_get(p, "ter", ter.size), ter.astype(np.float64))
+
+
+def test_xytoll_and_map_factor(host, tmp_path):
+    """xytoll (llxy_module.F90:166-216) agrees with the coordinate arrays; the Lambert map factor is 1 on the true
+    latitude and follows Saucier's formula elsewhere (model_grid.F90:2229-2365)."""
+    from mpassit_b200 import lib as L
+
+    cfg = host.read_setup_namelist(defaults.write_namelist(str(tmp_path / "namelist.input"), nx=61, ny=41, dx=30000.0))
+    lat, lon = host.target_coords(cfg, L.CENTER)
+    la, lo = host.xytoll(cfg, 7.0, 5.0, 1)
+    assert (la, lo) == (lat[4, 6], lon[4, 6])
+    latu, lonu = host.target_coords(cfg, L.EDGE1)
+    assert host.xytoll(cfg, 7.0, 5.0, 2) == (latu[4, 6], lonu[4, 6])
+    mf = host.get_map_factor(cfg, np.array([38.5, 30.0, 50.0]))
+    assert abs(mf[0] - 1.0) < 1e-12
+    colat0, n = np.deg2rad(90 - 38.5), np.cos(np.deg2rad(90 - 38.5))
+    for k, la in ((1, 30.0), (2, 50.0)):
+        c = np.deg2rad(90 - la)
+        assert abs(mf[k] - np.sin(colat0) / np.sin(c) * (np.tan(c / 2) / np.tan(colat0 / 2)) ** n) < 1e-12
+    assert mf[1] > 1.0 and mf[2] > 1.0
+
+
+def test_run_fails_loudly(host, tmp_path):
+    """error_handler behaviour of the driver: bad namelist, nothing to do, and -- without a GPU -- no CPU fallback."""
+    import torch
+
+    with pytest.raises(host.HostError, match="NAMELIST"):
+        host.run(str(tmp_path / "nope.nml"))
+    nl = tmp_path / "namelist.input"
+    nl.write_text("&config\n target_grid_type='lambert'\n nx=61\n ny=41\n dx=30000.\n dy=30000.\n ref_lat=38.5\n ref_lon=-97.5\n"
+                  " truelat1=38.5\n truelat2=38.5\n stand_lon=-97.5\n interp_diag=.false.\n interp_hist=.false.\n/\n")
+    with pytest.raises(host.HostError, match="INTERP_DIAG AND/OR INTERP_HIST"):
+        host.run(str(nl))
+    if not torch.cuda.is_available():
+        p = defaults.write_namelist(str(tmp_path / "nl2"), nx=61, ny=41, dx=30000.0)
+        with pytest.raises(host.HostError, match="CUDA"):
+            host.run(p, str(tmp_path))
+
+
+def _cpu_fields(wl):
+    from mpassit_b200 import workload
+
+    F = {g: [(nm, workload._field_values_torch(wl, g, nm, wl.levels_of(g, nm), k, "cpu").numpy())
+             for k, (nm, _) in enumerate(wl.lists[g])] for g in ("diag", "hist_2d", "hist_3d", "soil")}
+    ter = workload._field_values_torch(wl, "hist_2d", "ter", 1, 99, "cpu").numpy()
+    return F, ter
+
+
+def test_output_file_contract_header_only(host, tmp_path):
+    """mpassit_run(device = -1) lays the output file out without a GPU: dimensions, global attributes, variable
+    names / order / attributes and the grid description of write_to_file (write_data.F90:170-1210), quirks included."""
+    from mpassit_b200 import lib as L
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    F, ter = _cpu_fields(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), F, ter)
+    st = host.run(nl, str(tmp_path), device=-1)
+    assert st.output_version == 2 and st.n_cells == wl.mesh.lonCell.size
+    out, g, va, dims, order = mpas_files.read_output(paths["out"])
+    it, jt, nz = wl.cfg.i_target, wl.cfg.j_target, wl.nz
+    assert dims == {"Time": None, "west_east": it, "west_east_stag": it + 1, "south_north": jt, "south_north_stag": jt + 1,
+                    "bottom_top": nz, "bottom_top_stag": nz + 1, "soil_layers_stag": wl.nsoil, "StrLen": 19}
+    assert list(dims) == ["Time", "west_east", "west_east_stag", "south_north", "south_north_stag", "bottom_top",
+                          "bottom_top_stag", "soil_layers_stag", "StrLen"]
+    # global attributes, write_data.F90:199-300
+    assert g["WEST-EAST_GRID_DIMENSION"] == it + 1 and g["BOTTOM-TOP_GRID_DIMENSION"] == nz + 1
+    assert g["SIMULATION_START_DATE"] == mpas_files.START_TIME and g["START_DATE"] == mpas_files.START_TIME
+    assert g["DX"] == 30000.0 and g["DY"] == 30000.0 and g["DT"] == 18.0
+    assert (g["SF_SURFACE_PHYSICS"], g["MP_PHYSICS"], g["CU_PHYSICS"]) == (2, 18, 3)
+    clat, clon = host.xytoll(wl.cfg, it / 2.0, jt / 2.0, 1)
+    assert g["CEN_LAT"] == clat and g["CEN_LON"] == clon and g["MOAD_CEN_LAT"] == clat
+    assert g["TRUELAT1"] == 38.5 and g["STAND_LON"] == -97.5 and g["POLE_LAT"] == 90.0 and g["POL_ELAT"] == 90.0
+    assert g["MAP_PROJ"] == 1 and g["MAP_PROJ_CHAR"] == "Lambert Conformal" and g["PREC_ACC_DT"] == 3600
+    assert g["WEST-EAST_PATCH_END_STAG"] == it + 1 and g["SOUTH-NORTH_PATCH_END_UNSTAG"] == jt
+    # definition order, write_data.F90:303-893
+    head = ["XLONG", "XLONG_U", "XLONG_V", "XLAT", "XLAT_U", "XLAT_V", "MAPFAC_M", "MAPFAC_U", "MAPFAC_V", "SINALPHA",
+            "COSALPHA", "Z_C", "ZS", "HGT", "Times", "ITIMESTEP", "XTIME"]
+    diag = [t for _, t in wl.lists["diag"]]  # 2-D and 3-D diag variables are defined as the list meets them (:571-613)
+    want = (head + diag + ["SNOW", "SNOWH"] + ["PSFC", "TSK", "SST"] + ["XLAND"] + ["TSLB", "SMOIS", "SH2O"] +
+            ["T", "QVAPOR", "QCLOUD", "QRAIN", "QICE", "QSNOW", "QGRAUP", "QNICE", "QNRAIN", "P_HYD", "P_TOP", "MUB", "MU"] +
+            ["U", "V"] + ["PHB", "PH", "W"] + ["P", "PB"])
+    assert order == want
+    # shapes: NetCDF order is the Fortran dimension list reversed
+    assert out["XLONG_U"].shape == (jt, it + 1) and out["XLAT_V"].shape == (jt + 1, it)
+    assert out["U"].shape == (nz, jt, it + 1) and out["V"].shape == (nz, jt + 1, it) and out["PHB"].shape == (nz + 1, jt, it)
+    assert out["Z_C"].shape == (nz + 1, jt, it) and out["TSLB"].shape == (wl.nsoil, jt, it) and out["P_TOP"].shape == ()
+    # attributes and the writer's quirks
+    assert va["XLONG"] == {"description": "LONGITUDE, WEST IS NEGATIVE", "units": "degree_east", "MemoryOrder": "XY ",
+                           "coordinates": "XLONG XLAT", "stagger": "", "FieldType": 104}
+    assert va["SINALPHA"]["description"] == "COSINE OF GRID ROTATION ANGLE ALPHA" and va["COSALPHA"] == {}
+    assert va["MAPFAC_U"]["description"] == "LATITUDE, SOUTH IS NEGATIVE" and va["MAPFAC_U"]["stagger"] == "X"
+    assert va["T"] == {"MemoryOrder": "XYZ ", "coordinates": "XLONG XLAT XTIME", "units": "unit_of_theta",
+                       "description": "long name of theta", "stagger": "", "FieldType": 104}
+    assert va["PHB"]["units"] == "gpm" and va["PHB"]["description"] == "Base Geopotential Height" and va["PHB"]["stagger"] == "Z"
+    assert va["PH"]["description"] == "Perturbation Geopotential Height" and va["W"]["units"] == "unit_of_w"
+    assert va["MU"]["description"] == "Perturbation long name of rho" and va["P_TOP"]["description"] == "PRESSURE TOP OF THE MODEL"
+    assert va["U"]["coordinates"] == "XLONG_U XLAT_U XTIME" and va["U"]["units"] == "m s^{-1}" and va["V"]["stagger"] == "Y"
+    assert va["PB"]["description"] == "BASE STATE PRESSURE (pfull)" and va["ITIMESTEP"]["FieldType"] == 106
+    assert va["XTIME"]["units"] == "minutes since " + mpas_files.START_TIME
+    # grid description
+    for nm, s in (("", L.CENTER), ("_U", L.EDGE1), ("_V", L.EDGE2)):
+        lat, lon = host.target_coords(wl.cfg, s)
+        assert np.array_equal(out["XLAT" + nm], lat.astype(np.float32)) and np.array_equal(out["XLONG" + nm], lon.astype(np.float32))
+        assert np.array_equal(out["MAPFAC" + (nm or "_M")], host.get_map_factor(wl.cfg, lat).astype(np.float32))
+    assert np.array_equal(out["COSALPHA"], wl.cosa.astype(np.float32)) and np.array_equal(out["SINALPHA"], wl.sina.astype(np.float32))
+    assert np.allclose(out["ZS"], [0.05, 0.25, 0.7, 1.5]) and out["Times"].tobytes().decode() == mpas_files.VALID_TIME
+    assert out["XTIME"] == -540.0 and out["ITIMESTEP"] == int(-540 * 60 / 18.0)  # (start - valid), write_data.F90:1198
+    assert not out["T"].any() and not out["P"].any()  # nothing regridded in this mode
+
+
+def test_run_reports_input_file_errors(host, tmp_path):
+    """netcdf_err-style failures (utils.F90:35-60) of read_input_data: missing variable, missing attribute, NetCDF-4."""
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    F, ter = _cpu_fields(wl)
+    F2 = dict(F, hist_3d=[x for x in F["hist_3d"] if x[0] != "qv"])
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), F2, ter)
+    with pytest.raises(host.HostError, match="reading field id - qv"):
+        host.run(nl, str(tmp_path), device=-1)
+    open(paths["history"], "wb").write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(host.HostError, match="opening: .*NetCDF-4"):
+        host.run(nl, str(tmp_path), device=-1)
+    (tmp_path / "histlist_soil").unlink()
+    with pytest.raises(host.HostError, match="VARLIST FILE"):
+        host.run(nl, str(tmp_path), device=-1)
