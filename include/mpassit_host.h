@@ -148,6 +148,7 @@ enum { MPASSIT_COMM_BARRIER = 0, MPASSIT_COMM_MAX = 1, MPASSIT_COMM_MIN = 2 };
 typedef void (*mpassit_comm_fn)(void *arg, int op, double *vals, int n);
 typedef struct mpassit_run_stats {
     double setup_ms, read_ms, interp_ms, write_ms, total_ms; /* wall clock of the stages on this rank */
+    double init_ms, target_ms, gridfile_ms, mesh_ms;         /* setup_ms split: mprg_init, target grid, grid file, mprg_set_mesh */
     int64_t n_cells, bytes_in, bytes_out;                    /* source bytes referenced in the input files; bytes this rank wrote */
     int32_t n_vars_written, output_version;                  /* regridded variables; 2 = CDF-2, 5 = CDF-5 */
     double p_top;

@@ -85,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 print(f"==== {name}\n{out}")
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for (s, _, _) in units]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-ldl"]
+        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-ldl", "-lpthread"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             sys.stderr.write(p.stdout + p.stderr)
@@ -101,9 +101,9 @@ def build_host(force: bool = False) -> str:
     """libmpassit_host.so: C++ mirror of the reference's Fortran host stages (no CUDA code;
     calls the engine through its C ABI, resolved from the same directory via rpath)."""
     srcs = [os.path.join(HERE, "host", s) for s in HOST_SRC]
-    deps = srcs + [os.path.join(HERE, "host", "ncio.hpp"), os.path.join(HERE, "..", "include", "mpassit_host.h"), os.path.join(HERE, "..", "include", "mpassit_rg.h"), LIB]
+    deps = srcs + [os.path.join(HERE, "host", "ncio.hpp"), os.path.join(HERE, "host", "par.hpp"), os.path.join(HERE, "..", "include", "mpassit_host.h"), os.path.join(HERE, "..", "include", "mpassit_rg.h"), LIB]
     if force or _stale(HOST_LIB, deps):
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOST_LIB, *srcs,
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wall", "-o", HOST_LIB, *srcs,
                "-L" + HERE, "-lmpassit_rg", "-Wl,-rpath,$ORIGIN"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:

@@ -2,8 +2,10 @@
 // No exception crosses the boundary: every entry returns an rc and records a
 // message retrievable with mprg_last_error().
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <thread>
 
 #include "common.cuh"
 
@@ -110,6 +112,9 @@ int mprg_finalize(mprg_ctx *ctx) {
     for (auto &kv : ctx->ipcOpen) cudaIpcCloseMemHandle(kv.second);
     ctx->ipcOpen.clear();
     if (ctx->evDl) cudaEventDestroy(ctx->evDl);
+    if (ctx->bounce) cudaFreeHost(ctx->bounce);
+    for (auto &e : ctx->evBounce)
+        if (e) cudaEventDestroy(e);
     if (ctx->peekBuf) cudaFreeHost(ctx->peekBuf);
     if (ctx->store_stream) cudaStreamDestroy(ctx->store_stream);
     for (int i = 0; i < mprg_ctx::kSlots; ++i) {
@@ -379,6 +384,73 @@ int mprg_route_import_csr(mprg_ctx *ctx, int64_t nSrc, int64_t nDst, const int32
 // ---------------------------------------------------------------------------
 // apply
 // ---------------------------------------------------------------------------
+// Host -> device copy of a source that is not page-locked (typically a variable inside a memory-mapped input
+// file).  cudaMemcpyAsync from pageable memory is staged by the driver on ONE host thread (page faults of the
+// mapping included): ~10 GB/s measured on the 3-km history file.  Here a few host threads copy 8-MiB chunks into a
+// ring of pinned slots and the copy engine drains the slots in order on the H2D stream, so the page-cache reads
+// run in parallel and overlap the DMA.  Returns when the last chunk has been handed to the copy engine and its
+// slot is free again (the device-side copy is then complete); kernels queued behind it stay asynchronous.
+static void upload_unpinned(mprg_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    constexpr int R = mprg_ctx::kBounce;
+    constexpr size_t C = mprg_ctx::kBounceBytes;
+    if (!ctx->bounce) {
+        MPRG_CUDA(cudaHostAlloc((void **)&ctx->bounce, (size_t)R * C, cudaHostAllocDefault));
+        for (auto &e : ctx->evBounce) MPRG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int64_t nChunks = (int64_t)((bytes + C - 1) / C);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<int64_t>(std::min<unsigned>(std::max(2u, hw / 2), 8), nChunks);
+    std::atomic<int64_t> next{0}, released{0};  // next chunk to claim; chunks whose slot is free again
+    std::vector<std::atomic<int>> done(nChunks);
+    for (auto &d : done) d.store(0, std::memory_order_relaxed);
+    std::atomic<bool> abort{false};
+    const unsigned char *src = (const unsigned char *)src_host;
+    unsigned char *ring = ctx->bounce;
+    std::vector<std::thread> workers;
+    for (unsigned t = 0; t < nt; ++t)
+        workers.emplace_back([&] {
+            for (;;) {
+                const int64_t i = next.fetch_add(1);
+                if (i >= nChunks) return;
+                while (i - released.load(std::memory_order_acquire) >= R) {  // slot still owned by chunk i - R
+                    if (abort.load()) return;
+                    std::this_thread::yield();
+                }
+                const size_t off = (size_t)i * C, len = std::min(C, bytes - off);
+                std::memcpy(ring + (size_t)(i % R) * C, src + off, len);
+                done[i].store(1, std::memory_order_release);
+            }
+        });
+    cudaError_t bad = cudaSuccess;
+    int64_t freed = 0;
+    for (int64_t i = 0; i < nChunks && bad == cudaSuccess; ++i) {
+        while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+        const size_t off = (size_t)i * C, len = std::min(C, bytes - off);
+        bad = cudaMemcpyAsync((unsigned char *)dst_dev + off, ring + (size_t)(i % R) * C, len, cudaMemcpyHostToDevice, ctx->h2d_stream);
+        if (bad == cudaSuccess) bad = cudaEventRecord(ctx->evBounce[i % R], ctx->h2d_stream);
+        // keep at most R/2 transfers in flight; the slots of the completed ones go back to the workers
+        while (bad == cudaSuccess && freed <= i - R / 2) {
+            bad = cudaEventSynchronize(ctx->evBounce[freed % R]);
+            released.store(++freed, std::memory_order_release);
+        }
+    }
+    if (bad != cudaSuccess) abort.store(true);
+    released.store(nChunks + R, std::memory_order_release);  // unblock (after an error: let the workers run out)
+    for (auto &w : workers) w.join();
+    MPRG_CUDA(bad);
+    // the last R/2 slots: the next upload reuses the ring from slot 0
+    for (; freed < nChunks; ++freed) MPRG_CUDA(cudaEventSynchronize(ctx->evBounce[freed % R]));
+}
+
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type != cudaMemoryTypeUnregistered;
+}
+
 static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const void *const *src, const int32_t *nlev,
                        int src_dtype, int src_mem, void *const *dst, int dst_dtype, int dst_mem,
                        const int32_t *epi_op, const double *epi_arg, bool into_full = false) {
@@ -444,8 +516,11 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                     const size_t col = (size_t)nlev[k] * isz, skip = (size_t)lo * col;
                     // keep the 16-byte phase of the original layout so aligned fields stay aligned
                     unsigned char *data = ctx->stageIn[slot].p + io + kPad + (skip & 15);
-                    MPRG_CUDA(cudaMemcpyAsync(data, (const unsigned char *)src[k] + skip, in_bytes(k), cudaMemcpyHostToDevice,
-                                              ctx->h2d_stream));
+                    const unsigned char *from = (const unsigned char *)src[k] + skip;
+                    if (in_bytes(k) >= ((size_t)16 << 20) && !is_pinned_host(from))
+                        upload_unpinned(ctx, data, from, in_bytes(k));
+                    else
+                        MPRG_CUDA(cudaMemcpyAsync(data, from, in_bytes(k), cudaMemcpyHostToDevice, ctx->h2d_stream));
                     ctx->h2dBytes += in_bytes(k);
                     staged.emplace_back(data, in_bytes(k) / isz);
                     s = data - skip;

@@ -193,6 +193,12 @@ struct mprg_ctx {
     mprg::DevBuf<unsigned char> stageIn[kSlots], stageOut[kSlots];
     cudaEvent_t evIn[kSlots] = {}, evK[kSlots] = {}, evOut[kSlots] = {};
     bool slotUsed[kSlots] = {};
+    // bounce ring for host sources that are NOT page-locked (a variable mapped from a file): host threads copy
+    // chunks into pinned slots, the copy engine takes them from there (capi.cu: upload_unpinned)
+    static constexpr int kBounce = 8;
+    static constexpr size_t kBounceBytes = (size_t)8 << 20;
+    unsigned char *bounce = nullptr;
+    cudaEvent_t evBounce[kBounce] = {};
     unsigned long long h2dBytes = 0, d2hBytes = 0;  // field bytes moved by host-buffer applies / downloads since init
     unsigned slotCursor = 0;
     cudaEvent_t evDl = nullptr;           // mprg_download ordering

@@ -2,13 +2,17 @@
 // grammar ("NetCDF Classic Format Specification": header = magic numrecs dim_list gatt_list var_list).
 #include "ncio.hpp"
 
+#include "par.hpp"
+
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cerrno>
 #include <cstring>
+#include <thread>
 
 namespace ncio {
 
@@ -339,7 +343,25 @@ bool Reader::read_doubles(const Var &v, uint64_t first, uint64_t n, double *out,
         return false;
     }
     p += first * es;
-    for (uint64_t i = 0; i < n; ++i) out[i] = be_number(p + i * es, v.type);
+    const int type = v.type;
+    // geometry arrays of a 3-km mesh are 10^7 values: convert on a few threads, the common types without the switch
+    par::range((int64_t)n, 1 << 16, [&](int64_t b, int64_t e) {
+        if (type == NC_DOUBLE) {
+            for (int64_t i = b; i < e; ++i) {
+                uint64_t u = be64(p + i * 8);
+                std::memcpy(&out[i], &u, 8);
+            }
+        } else if (type == NC_FLOAT) {
+            for (int64_t i = b; i < e; ++i) {
+                uint32_t u = be32(p + i * 4);
+                float f;
+                std::memcpy(&f, &u, 4);
+                out[i] = (double)f;
+            }
+        } else {
+            for (int64_t i = b; i < e; ++i) out[i] = be_number(p + i * es, type);
+        }
+    });
     return true;
 }
 bool Reader::read_ints(const Var &v, uint64_t first, uint64_t n, int32_t *out, std::string &err) const {
@@ -349,7 +371,9 @@ bool Reader::read_ints(const Var &v, uint64_t first, uint64_t n, int32_t *out, s
         return false;
     }
     p += first * 4;
-    for (uint64_t i = 0; i < n; ++i) out[i] = (int32_t)be32(p + i * 4);
+    par::range((int64_t)n, 1 << 16, [&](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) out[i] = (int32_t)be32(p + i * 4);
+    });
     return true;
 }
 
@@ -514,7 +538,29 @@ bool Writer::write_raw(int varid, uint64_t rec, uint64_t byte_off, const void *p
         err = "write past the end of variable " + vars_[varid].name;
         return false;
     }
-    return pwrite_all(fd_, p, n, var_offset(varid, rec) + byte_off, err);
+    const uint64_t off = var_offset(varid, rec) + byte_off;
+    // Large blocks (a rank's slab of a 3-D field is 10^8 bytes) are cut across a few threads: one pwrite copies
+    // into the page cache at a single core's memcpy speed, and the regions are disjoint by construction.
+    constexpr size_t kParallelFrom = (size_t)8 << 20, kAlign = (size_t)1 << 20;
+    unsigned nt = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    if (n < kParallelFrom || nt < 2) return pwrite_all(fd_, p, n, off, err);
+    const size_t chunk = ((n + nt - 1) / nt + kAlign - 1) & ~(kAlign - 1);
+    nt = (unsigned)((n + chunk - 1) / chunk);
+    std::vector<std::string> errs(nt);
+    std::vector<char> ok(nt, 1);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t] {
+            const size_t a = (size_t)t * chunk, len = std::min(chunk, n - a);
+            ok[t] = pwrite_all(fd_, (const uint8_t *)p + a, len, off + a, errs[t]) ? 1 : 0;
+        });
+    for (auto &x : th) x.join();
+    for (unsigned t = 0; t < nt; ++t)
+        if (!ok[t]) {
+            err = errs[t];
+            return false;
+        }
+    return true;
 }
 bool Writer::put_doubles(int varid, const double *v, uint64_t n, std::string &err) {
     const Var &var = vars_[varid];

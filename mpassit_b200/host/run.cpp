@@ -25,6 +25,7 @@
 #include <limits>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mpassit_host.h"
@@ -124,7 +125,10 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
     mpassit_run_stats st;
     std::memset(&st, 0, sizeof st);
     std::vector<void *> dev_allocs;
-    void *pinned = nullptr;
+    void *pinned[2] = {nullptr, nullptr};
+    std::thread writer;  // background pwrite of the field downloaded last
+    bool writer_ok = true;
+    std::string writer_err;
     auto barrier = [&]() {
         if (nranks > 1 && comm) comm(comm_arg, MPASSIT_COMM_BARRIER, nullptr, 0);
     };
@@ -146,7 +150,10 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         // device < 0: lay the output file out (header, grid description, times) without touching a GPU -- no field
         // is regridded or written; the regular run needs a device and fails without one (no CPU path)
         const bool dry = device < 0;
+        double tq = now_ms();
         if (!dry) ck(nullptr, mprg_init(device, rank, nranks, &ctx), "mprg_init");
+        st.init_ms = now_ms() - tq;
+        tq = now_ms();
 
         // ------------------------------------------------------------------ define_target_grid (param mode)
         const int staggers[4] = {MPRG_CENTER, MPRG_EDGE1, MPRG_EDGE2, MPRG_CORNER};
@@ -177,6 +184,9 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
             mpassit_get_rotang(lat[0].data(), lon[0].data(), it, jt, cosa.data(), sina.data());
             if (!dry) ck(ctx, mprg_set_rotation(ctx, cosa.data(), sina.data()), "get_rotang");
         }
+
+        st.target_ms = now_ms() - tq;
+        tq = now_ms();
 
         // ------------------------------------------------------------------ define_input_grid, model_grid.F90:263-640
         ncio::Reader grid;
@@ -211,9 +221,12 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         need_d("ter", "reading ter", ter.data(), nCells);
         if (!grid.read_ints(getvar(grid, "verticesOnCell", "reading verticesOnCell id"), 0, voc.size(), voc.data(), why))
             netcdf_err("reading verticesOnCell", why);
+        st.gridfile_ms = now_ms() - tq;
+        tq = now_ms();
         if (!dry)
             ck(ctx, mprg_set_mesh(ctx, (int32_t)nCells, (int32_t)nVertices, maxEdges, lonCell.data(), latCell.data(),
                                   lonVert.data(), latVert.data(), voc.data()), "MeshCreate");
+        st.mesh_ms = now_ms() - tq;
         st.n_cells = nCells;
         st.setup_ms = now_ms() - t0;
 
@@ -390,6 +403,12 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         // ------------------------------------------------------------------ write_to_file, write_data.F90:96-1496
         const double t3 = now_ms();
         ncio::Writer w(0);
+        struct JoinOnExit {  // declared after `w`: the background writer is joined before the Writer goes away
+            std::thread &t;
+            ~JoinOnExit() {
+                if (t.joinable()) t.join();
+            }
+        } join_on_exit{writer};
         const int dTime = w.def_dim("Time", 0), dWE = w.def_dim("west_east", it), dWEs = w.def_dim("west_east_stag", it + 1),
                   dSN = w.def_dim("south_north", jt), dSNs = w.def_dim("south_north_stag", jt + 1),
                   dZ = w.def_dim("bottom_top", nz), dZs = w.def_dim("bottom_top_stag", nzp1),
@@ -619,20 +638,50 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
             const int s = o.stagger == MPRG_EDGE1 ? 1 : o.stagger == MPRG_EDGE2 ? 2 : 0;
             maxslab = std::max(maxslab, (size_t)(j1[s] - j0[s]) * ni[s] * o.nlev * 4);
         }
-        if (!dry) ck(ctx, mprg_host_alloc(ctx, maxslab, &pinned), "host_alloc");
-        auto write_slab = [&](int varid, int s, int32_t nlev, const void *dev, size_t lev_first = 0) {
+        // two pinned buffers: while a background thread writes field k from one, field k+1 is downloaded into the other
+        if (!dry)
+            for (void *&pb : pinned) ck(ctx, mprg_host_alloc(ctx, maxslab, &pb), "host_alloc");
+        struct Job {
+            int varid;
+            uint64_t off;
+            const uint8_t *p;
+            size_t n;
+        };
+        int cur = 0;
+        auto flush = [&]() {
+            if (writer.joinable()) writer.join();
+            if (!writer_ok) netcdf_err("writing to " + std::string(cfg.output_file), writer_err);
+        };
+        auto submit = [&](std::vector<Job> jobs) {
+            flush();  // at most one field in flight: it owns the other buffer
+            writer = std::thread([&w, &writer_ok, &writer_err, jobs]() {
+                for (const Job &j : jobs)
+                    if (!w.write_raw(j.varid, 0, j.off, j.p, j.n, writer_err)) {
+                        writer_ok = false;
+                        return;
+                    }
+            });
+        };
+        // also_varid: a second variable that receives the same bytes (PB <- P_HYD)
+        auto write_slab = [&](int varid, int s, int32_t nlev, const void *dev, int also_varid = -1) {
             const size_t rows = (size_t)(j1[s] - j0[s]), slab = rows * ni[s];
             if (slab == 0 || nlev == 0) return;
-            ck(ctx, mprg_download(ctx, dev, pinned, slab * nlev * 4), "download");
+            const uint8_t *buf = (const uint8_t *)pinned[cur];
+            cur ^= 1;
+            ck(ctx, mprg_download(ctx, dev, (void *)buf, slab * nlev * 4), "download");
             const size_t plane = (size_t)nj[s] * ni[s];
-            if (rows == (size_t)nj[s]) {  // whole field: one run
-                wr(w.write_raw(varid, 0, lev_first * plane * 4, pinned, slab * nlev * 4, why));
-            } else {
-                for (int32_t l = 0; l < nlev; ++l)
-                    wr(w.write_raw(varid, 0, ((lev_first + l) * plane + (size_t)j0[s] * ni[s]) * 4, (const uint8_t *)pinned + l * slab * 4,
-                                   slab * 4, why));
+            std::vector<Job> jobs;
+            for (int id : {varid, also_varid}) {
+                if (id < 0) continue;
+                if (rows == (size_t)nj[s]) {  // whole field: one run
+                    jobs.push_back(Job{id, 0, buf, slab * nlev * 4});
+                } else {
+                    for (int32_t l = 0; l < nlev; ++l)
+                        jobs.push_back(Job{id, (l * plane + (size_t)j0[s] * ni[s]) * 4, buf + l * slab * 4, slab * 4});
+                }
+                st.bytes_out += (int64_t)(slab * nlev * 4);
             }
-            st.bytes_out += (int64_t)(slab * nlev * 4);
+            submit(std::move(jobs));
         };
         auto swap_dev = [&](void *dev, int s, int32_t nlev) {
             if (!dry) ck(ctx, mprg_bswap(ctx, dev, (size_t)(j1[s] - j0[s]) * ni[s] * nlev, MPRG_F32), "bswap");
@@ -674,15 +723,9 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
                 ck(ctx, mprg_post_affine(ctx, o.dev, slabM * nzp1, MPRG_F32, 9.81, 0.0), "post_affine");
             }
             swap_dev(o.dev, s, o.nlev);
-            write_slab(o.varid, s, o.nlev, o.dev);
-            if ((int)k == o_phyd && id_pb >= 0) {  // same bytes again (already in file order in `pinned`)
-                const size_t plane = (size_t)nj[0] * ni[0];
-                for (int32_t l = 0; l < nz; ++l)
-                    wr(w.write_raw(id_pb, 0, (l * plane + (size_t)j0[0] * ni[0]) * 4, (const uint8_t *)pinned + l * slabM * 4,
-                                   slabM * 4, why));
-                st.bytes_out += (int64_t)(slabM * nz * 4);
-            }
+            write_slab(o.varid, s, o.nlev, o.dev, (int)k == o_phyd ? id_pb : -1);  // PB: the same bytes again (:1376)
         }
+        flush();
         st.n_vars_written = (int32_t)outs.size();
         wr(w.close(why));
         barrier();
@@ -693,8 +736,10 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         if (err && errlen) std::snprintf(err, errlen, "%s", f.msg.c_str());
         rc_out = f.rc;
     }
+    if (writer.joinable()) writer.join();
     if (ctx) {
-        if (pinned) mprg_host_free(ctx, pinned);
+        for (void *pb : pinned)
+            if (pb) mprg_host_free(ctx, pb);
         for (void *p : dev_allocs) mprg_device_free(ctx, p);
         mprg_finalize(ctx);  // cleanup_input_target_grid_data + ESMF_finalize, mpassit.F90:137-142
     }

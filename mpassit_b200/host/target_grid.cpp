@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/mpassit_host.h"
+#include "par.hpp"
 
 namespace {
 
@@ -159,7 +160,9 @@ int mpassit_target_coords(const mpassit_config *cfg, int stagger, double *lat, d
     // xytoll stagger offsets, llxy_module.F90:182-203:  U: x-0.5   V: y-0.5   CORNER: both
     const double ox = (stagger == MPRG_EDGE1 || stagger == MPRG_CORNER) ? 0.5 : 0.0;
     const double oy = (stagger == MPRG_EDGE2 || stagger == MPRG_CORNER) ? 0.5 : 0.0;
-    for (int32_t j = 1; j <= nj; ++j) {
+    // rows are independent: a few host threads (1.9 M points x 4 staggers of inverse-Lambert trig on the CONUS grid)
+    par::range(nj, 16, [&](int64_t jb, int64_t je) {
+    for (int32_t j = (int32_t)jb + 1; j <= (int32_t)je; ++j) {
         for (int32_t i = 1; i <= ni; ++i) {
             // get_lat_lon_fields, model_grid.F90:2212-2217 with rx = ry = 1
             double x = ((double)i - 0.5) / 1.0 + 0.5, y = ((double)j - 0.5) / 1.0 + 0.5;
@@ -169,6 +172,7 @@ int mpassit_target_coords(const mpassit_config *cfg, int stagger, double *lat, d
             else ijll_latlon(rx, ry, p, &lat[o], &lon[o]);
         }
     }
+    });
     return 0;
 }
 
@@ -195,16 +199,20 @@ int mpassit_get_map_factor(const mpassit_config *cfg, const double *xlat, int64_
             const double colat1 = RAD_PER_DEG * (90.0 - cfg->truelat1), colat2 = RAD_PER_DEG * (90.0 - cfg->truelat2);
             const double nn = (std::log(std::sin(colat1)) - std::log(std::sin(colat2))) /
                               (std::log(std::tan(colat1 / 2.0)) - std::log(std::tan(colat2 / 2.0)));
-            for (int64_t k = 0; k < n; ++k) {
-                const double colat = RAD_PER_DEG * (90.0 - xlat[k]);
-                mapfac[k] = std::sin(colat2) / std::sin(colat) * std::pow(std::tan(colat / 2.0) / std::tan(colat2 / 2.0), nn);
-            }
+            par::range(n, 1 << 15, [&](int64_t kb, int64_t ke) {
+                for (int64_t k = kb; k < ke; ++k) {
+                    const double colat = RAD_PER_DEG * (90.0 - xlat[k]);
+                    mapfac[k] = std::sin(colat2) / std::sin(colat) * std::pow(std::tan(colat / 2.0) / std::tan(colat2 / 2.0), nn);
+                }
+            });
         } else {
             const double colat0 = RAD_PER_DEG * (90.0 - cfg->truelat1);
-            for (int64_t k = 0; k < n; ++k) {
-                const double colat = RAD_PER_DEG * (90.0 - xlat[k]);
-                mapfac[k] = std::sin(colat0) / std::sin(colat) * std::pow(std::tan(colat / 2.0) / std::tan(colat0 / 2.0), std::cos(colat0));
-            }
+            par::range(n, 1 << 15, [&](int64_t kb, int64_t ke) {
+                for (int64_t k = kb; k < ke; ++k) {
+                    const double colat = RAD_PER_DEG * (90.0 - xlat[k]);
+                    mapfac[k] = std::sin(colat0) / std::sin(colat) * std::pow(std::tan(colat / 2.0) / std::tan(colat0 / 2.0), std::cos(colat0));
+                }
+            });
         }
         return 0;
     }
@@ -224,7 +232,8 @@ void mpassit_get_rotang(const double *xlat, const double *xlon, int32_t ni, int3
         sina[(size_t)j * ni + i] = std::sin(alpha);
         cosa[(size_t)j * ni + i] = std::cos(alpha);
     };
-    for (int i = 0; i < ni; ++i) {
+    par::range(ni, 64, [&](int64_t ib, int64_t ie) {
+    for (int i = (int)ib; i < (int)ie; ++i) {
         for (int j = 1; j < nj - 1; ++j)
             rot(i, j, at(xlon, i, j + 1) - at(xlon, i, j - 1), at(xlat, i, j + 1) - at(xlat, i, j - 1));
         if (nj >= 2) {
@@ -232,6 +241,7 @@ void mpassit_get_rotang(const double *xlat, const double *xlon, int32_t ni, int3
             rot(i, nj - 1, at(xlon, i, nj - 1) - at(xlon, i, nj - 2), at(xlat, i, nj - 1) - at(xlat, i, nj - 2));
         }
     }
+    });
 }
 
 }  // extern "C"

@@ -149,6 +149,17 @@ class Regridder:
     def kernel_launches(self) -> int:
         return int(self.L.mprg_kernel_launches(self.ctx))
 
+    def set_source_byte_order(self, big_endian: bool) -> None:
+        """Host sources of the following applies hold big-endian words (a variable mapped from a NetCDF classic file)."""
+        self._ck(self.L.mprg_set_source_byte_order(self.ctx, int(big_endian)))
+
+    def bswap(self, buf) -> None:
+        """In-place word swap of a torch CUDA tensor (fp32 / int32 / fp64)."""
+        self._ck(self.L.mprg_bswap(self.ctx, _ptr(buf), buf.numel(), F32 if buf.element_size() == 4 else F64))
+
+    def post_affine(self, buf, scale: float, offset: float) -> None:
+        self._ck(self.L.mprg_post_affine(self.ctx, _ptr(buf), buf.numel(), _dtype_code(buf), scale, offset))
+
     def io_bytes(self) -> tuple[int, int]:
         """(host->device, device->host) field bytes moved by host-buffer applies since init."""
         a, b = C.c_uint64(), C.c_uint64()

@@ -156,3 +156,45 @@ def test_files_two_rank_slabs_tile_the_single_rank_file(host, tmp_path):
             host.run(nl, str(tmp_path), device=0, rank=rank, nranks=2, comm=fn)
     assert len(rec[host.COMM_MAX]) == 2
     assert open(paths["out"], "rb").read() == single
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_unpinned_big_endian_sources_take_the_bounce_ring(engine_lib, dtype):
+    """A large host source that is not page-locked (what a mapped file variable is) goes through the engine's
+    parallel bounce ring (capi.cu: upload_unpinned) and, flagged big-endian, is swapped in HBM: same result, bit for
+    bit, as the native-order array uploaded from a small (direct-copy) or device buffer."""
+    import torch
+
+    from mpassit_b200.regrid import Regridder
+
+    rg = Regridder(device=0)
+    rng = np.random.default_rng(11)
+    nSrc, nDst, nlev = 450_001, 30_000, 23          # 41 / 83 MB per field: several 8-MiB chunks, ragged tail
+    lens = rng.integers(0, 4, nDst)
+    rp = np.zeros(nDst + 1, np.int32)
+    np.cumsum(lens, out=rp[1:])
+    col = rng.integers(0, nSrc, rp[-1]).astype(np.int32)
+    col[:2] = (0, nSrc - 1)
+    r = rg.import_csr(nSrc, rp, col, rng.random(rp[-1]))
+    a = rng.standard_normal((nSrc, nlev)).astype(dtype)
+    b = rng.standard_normal((nSrc, nlev)).astype(dtype)
+    want = [torch.empty((nlev, nDst), dtype=torch.float32, device="cuda") for _ in range(2)]
+    rg.apply(r, [torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()], want, nlev=[nlev, nlev])
+    got = [np.empty((nlev, nDst), np.float32) for _ in range(2)]
+    rg.apply(r, [a, b], got, nlev=[nlev, nlev])                     # native order, unpinned
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w.cpu().numpy())
+    got = [np.empty((nlev, nDst), np.float32) for _ in range(2)]
+    rg.set_source_byte_order(True)
+    rg.apply(r, [a.byteswap(), b.byteswap()], got, nlev=[nlev, nlev])  # file order
+    rg.set_source_byte_order(False)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w.cpu().numpy())
+    # device-side swap is an involution
+    t = torch.from_numpy(a[:1000]).cuda()
+    rg.bswap(t)
+    assert np.array_equal(t.cpu().numpy().view(np.uint8), a[:1000].byteswap().view(np.uint8))
+    rg.bswap(t)
+    assert np.array_equal(t.cpu().numpy(), a[:1000])
+    r.release()
+    rg.close()

@@ -262,3 +262,22 @@ def test_run_reports_input_file_errors(host, tmp_path):
     (tmp_path / "histlist_soil").unlink()
     with pytest.raises(host.HostError, match="VARLIST FILE"):
         host.run(nl, str(tmp_path), device=-1)
+
+
+def test_large_blocks_are_written_in_parallel_chunks(host, tmp_path):
+    """Blocks of 8 MiB and more are cut across threads (disjoint pwrite regions): same bytes in the same place."""
+    p, q = str(tmp_path / "big.nc"), str(tmp_path / "big_copy.nc")
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 1 << 31, size=(2, 1500, 1001)).astype(np.int32)  # 12 MB per record, not a multiple of the chunk
+    with netcdf_file(p, "w", version=2) as f:
+        f.createDimension("Time", None)
+        f.createDimension("y", 1500)
+        f.createDimension("x", 1001)
+        v = f.createVariable("a", "i4", ("Time", "y", "x"))
+        w = f.createVariable("b", "i4", ("y", "x"))
+        w[:] = a[1]
+        v[0] = a[0]
+        v[1] = a[1]
+    host.nc_copy(p, q, 2)
+    with netcdf_file(q, "r", mmap=False) as f:
+        assert np.array_equal(f.variables["a"][:], a) and np.array_equal(f.variables["b"][:], a[1])
