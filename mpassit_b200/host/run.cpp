@@ -649,7 +649,9 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         };
         int cur = 0;
         auto flush = [&]() {
+            const double tw = now_ms();
             if (writer.joinable()) writer.join();
+            st.writer_wait_ms += now_ms() - tw;
             if (!writer_ok) netcdf_err("writing to " + std::string(cfg.output_file), writer_err);
         };
         auto submit = [&](std::vector<Job> jobs) {
@@ -668,7 +670,9 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
             if (slab == 0 || nlev == 0) return;
             const uint8_t *buf = (const uint8_t *)pinned[cur];
             cur ^= 1;
+            const double td = now_ms();
             ck(ctx, mprg_download(ctx, dev, (void *)buf, slab * nlev * 4), "download");
+            st.download_ms += now_ms() - td;
             const size_t plane = (size_t)nj[s] * ni[s];
             std::vector<Job> jobs;
             for (int id : {varid, also_varid}) {

@@ -56,7 +56,8 @@ def main():
         wall = (time.time() - t) * 1e3
         row = dict(run=r, wall_ms=round(wall, 1), setup_ms=round(st.setup_ms, 1),
                    setup_split=[round(x, 1) for x in (st.init_ms, st.target_ms, st.gridfile_ms, st.mesh_ms)], read_ms=round(st.read_ms, 1),
-                   interp_ms=round(st.interp_ms, 1), write_ms=round(st.write_ms, 1), total_ms=round(st.total_ms, 1),
+                   interp_ms=round(st.interp_ms, 1), write_ms=round(st.write_ms, 1),
+                   write_split=[round(st.download_ms, 1), round(st.writer_wait_ms, 1)], total_ms=round(st.total_ms, 1),
                    in_GB=round(st.bytes_in / 1e9, 3), out_GB=round(st.bytes_out / 1e9, 3),
                    interp_GBps_in=round(st.bytes_in / 1e6 / max(st.interp_ms, 1e-9), 1),
                    write_GBps_out=round(st.bytes_out / 1e6 / max(st.write_ms, 1e-9), 1),
