@@ -386,20 +386,24 @@ int mprg_route_import_csr(mprg_ctx *ctx, int64_t nSrc, int64_t nDst, const int32
 // ---------------------------------------------------------------------------
 // Host -> device copy of a source that is not page-locked (typically a variable inside a memory-mapped input
 // file).  cudaMemcpyAsync from pageable memory is staged by the driver on ONE host thread (page faults of the
-// mapping included): ~10 GB/s measured on the 3-km history file.  Here a few host threads copy 8-MiB chunks into a
+// mapping included): ~10 GB/s measured on the 3-km history file.  Here a few host threads copy chunks into a
 // ring of pinned slots and the copy engine drains the slots in order on the H2D stream, so the page-cache reads
-// run in parallel and overlap the DMA.  Returns when the last chunk has been handed to the copy engine and its
+// run in parallel and overlap the DMA (4-MiB chunks, 32 slots: 4 in flight on the copy engine, the rest being filled).  Returns when the last chunk has been handed to the copy engine and its
 // slot is free again (the device-side copy is then complete); kernels queued behind it stay asynchronous.
 static void upload_unpinned(mprg_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
     constexpr int R = mprg_ctx::kBounce;
     constexpr size_t C = mprg_ctx::kBounceBytes;
+    constexpr int64_t kInflight = 4;  // chunks handed to the copy engine and not yet known complete (< R)
     if (!ctx->bounce) {
         MPRG_CUDA(cudaHostAlloc((void **)&ctx->bounce, (size_t)R * C, cudaHostAllocDefault));
         for (auto &e : ctx->evBounce) MPRG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     const int64_t nChunks = (int64_t)((bytes + C - 1) / C);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nt = (unsigned)std::min<int64_t>(std::min<unsigned>(std::max(2u, hw / 2), 8), nChunks);
+    // three quarters of the cores, shared between the ranks of the box
+    unsigned want = std::max(2u, hw * 3 / 4 / (unsigned)std::max(1, ctx->nranks));
+    if (const char *e = std::getenv("MPASSIT_UPLOAD_THREADS")) want = (unsigned)std::max(1, std::atoi(e));
+    const unsigned nt = (unsigned)std::min<int64_t>(std::min<unsigned>(want, 16), nChunks);
     std::atomic<int64_t> next{0}, released{0};  // next chunk to claim; chunks whose slot is free again
     std::vector<std::atomic<int>> done(nChunks);
     for (auto &d : done) d.store(0, std::memory_order_relaxed);
@@ -428,8 +432,8 @@ static void upload_unpinned(mprg_ctx *ctx, void *dst_dev, const void *src_host, 
         const size_t off = (size_t)i * C, len = std::min(C, bytes - off);
         bad = cudaMemcpyAsync((unsigned char *)dst_dev + off, ring + (size_t)(i % R) * C, len, cudaMemcpyHostToDevice, ctx->h2d_stream);
         if (bad == cudaSuccess) bad = cudaEventRecord(ctx->evBounce[i % R], ctx->h2d_stream);
-        // keep at most R/2 transfers in flight; the slots of the completed ones go back to the workers
-        while (bad == cudaSuccess && freed <= i - R / 2) {
+        // keep a few transfers in flight; the slots of the completed ones go back to the workers
+        while (bad == cudaSuccess && freed <= i - kInflight) {
             bad = cudaEventSynchronize(ctx->evBounce[freed % R]);
             released.store(++freed, std::memory_order_release);
         }
@@ -438,7 +442,7 @@ static void upload_unpinned(mprg_ctx *ctx, void *dst_dev, const void *src_host, 
     released.store(nChunks + R, std::memory_order_release);  // unblock (after an error: let the workers run out)
     for (auto &w : workers) w.join();
     MPRG_CUDA(bad);
-    // the last R/2 slots: the next upload reuses the ring from slot 0
+    // the last few slots: the next upload reuses the ring from slot 0
     for (; freed < nChunks; ++freed) MPRG_CUDA(cudaEventSynchronize(ctx->evBounce[freed % R]));
 }
 

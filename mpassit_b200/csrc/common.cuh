@@ -195,8 +195,8 @@ struct mprg_ctx {
     bool slotUsed[kSlots] = {};
     // bounce ring for host sources that are NOT page-locked (a variable mapped from a file): host threads copy
     // chunks into pinned slots, the copy engine takes them from there (capi.cu: upload_unpinned)
-    static constexpr int kBounce = 8;
-    static constexpr size_t kBounceBytes = (size_t)8 << 20;
+    static constexpr int kBounce = 32;
+    static constexpr size_t kBounceBytes = (size_t)4 << 20;
     unsigned char *bounce = nullptr;
     cudaEvent_t evBounce[kBounce] = {};
     unsigned long long h2dBytes = 0, d2hBytes = 0;  // field bytes moved by host-buffer applies / downloads since init

@@ -633,14 +633,12 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         }
 
         // this rank's rows of every regridded field: post-op + byte swap in HBM, one download, pwrite per level run
-        size_t maxslab = 4;
-        for (const OutVar &o : outs) {
-            const int s = o.stagger == MPRG_EDGE1 ? 1 : o.stagger == MPRG_EDGE2 ? 2 : 0;
-            maxslab = std::max(maxslab, (size_t)(j1[s] - j0[s]) * ni[s] * o.nlev * 4);
-        }
-        // two pinned buffers: while a background thread writes field k from one, field k+1 is downloaded into the other
+        // Two pinned buffers of a few levels each (page-locking memory costs ~0.3 s per GB: whole-field buffers would
+        // cost more than they save): while a background thread writes one chunk, the next is downloaded into the other.
+        size_t pin_bytes = (size_t)64 << 20;
+        for (int s = 0; s < 3; ++s) pin_bytes = std::max(pin_bytes, (size_t)(j1[s] - j0[s]) * ni[s] * 4);
         if (!dry)
-            for (void *&pb : pinned) ck(ctx, mprg_host_alloc(ctx, maxslab, &pb), "host_alloc");
+            for (void *&pb : pinned) ck(ctx, mprg_host_alloc(ctx, pin_bytes, &pb), "host_alloc");
         struct Job {
             int varid;
             uint64_t off;
@@ -668,24 +666,28 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         auto write_slab = [&](int varid, int s, int32_t nlev, const void *dev, int also_varid = -1) {
             const size_t rows = (size_t)(j1[s] - j0[s]), slab = rows * ni[s];
             if (slab == 0 || nlev == 0) return;
-            const uint8_t *buf = (const uint8_t *)pinned[cur];
-            cur ^= 1;
-            const double td = now_ms();
-            ck(ctx, mprg_download(ctx, dev, (void *)buf, slab * nlev * 4), "download");
-            st.download_ms += now_ms() - td;
             const size_t plane = (size_t)nj[s] * ni[s];
-            std::vector<Job> jobs;
-            for (int id : {varid, also_varid}) {
-                if (id < 0) continue;
-                if (rows == (size_t)nj[s]) {  // whole field: one run
-                    jobs.push_back(Job{id, 0, buf, slab * nlev * 4});
-                } else {
-                    for (int32_t l = 0; l < nlev; ++l)
-                        jobs.push_back(Job{id, (l * plane + (size_t)j0[s] * ni[s]) * 4, buf + l * slab * 4, slab * 4});
+            const int32_t per = (int32_t)std::max<size_t>(1, pin_bytes / (slab * 4));  // levels per chunk
+            for (int32_t l0 = 0; l0 < nlev; l0 += per) {
+                const int32_t n = std::min(per, nlev - l0);
+                const uint8_t *buf = (const uint8_t *)pinned[cur];
+                cur ^= 1;  // the writer in flight (at most one) reads the other buffer
+                const double td = now_ms();
+                ck(ctx, mprg_download(ctx, (const uint8_t *)dev + (size_t)l0 * slab * 4, (void *)buf, slab * n * 4), "download");
+                st.download_ms += now_ms() - td;
+                std::vector<Job> jobs;
+                for (int id : {varid, also_varid}) {
+                    if (id < 0) continue;
+                    if (rows == (size_t)nj[s]) {  // whole rows of the grid: the levels are one run in the file
+                        jobs.push_back(Job{id, (size_t)l0 * plane * 4, buf, slab * n * 4});
+                    } else {
+                        for (int32_t l = 0; l < n; ++l)
+                            jobs.push_back(Job{id, ((size_t)(l0 + l) * plane + (size_t)j0[s] * ni[s]) * 4, buf + l * slab * 4, slab * 4});
+                    }
+                    st.bytes_out += (int64_t)(slab * n * 4);
                 }
-                st.bytes_out += (int64_t)(slab * nlev * 4);
+                submit(std::move(jobs));
             }
-            submit(std::move(jobs));
         };
         auto swap_dev = [&](void *dev, int s, int32_t nlev) {
             if (!dry) ck(ctx, mprg_bswap(ctx, dev, (size_t)(j1[s] - j0[s]) * ni[s] * nlev, MPRG_F32), "bswap");
