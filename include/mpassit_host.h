@@ -149,6 +149,7 @@ typedef void (*mpassit_comm_fn)(void *arg, int op, double *vals, int n);
 typedef struct mpassit_run_stats {
     double setup_ms, read_ms, interp_ms, write_ms, total_ms; /* wall clock of the stages on this rank */
     double init_ms, target_ms, gridfile_ms, mesh_ms;         /* setup_ms split: mprg_init, target grid, grid file, mprg_set_mesh */
+    double alloc_ms;                                         /* output slabs in HBM (between read and interp) */
     double download_ms, writer_wait_ms;                      /* write_ms split: device->host copies; waiting for the pwrite thread */
     int64_t n_cells, bytes_in, bytes_out;                    /* source bytes referenced in the input files; bytes this rank wrote */
     int32_t n_vars_written, output_version;                  /* regridded variables; 2 = CDF-2, 5 = CDF-5 */

@@ -64,7 +64,7 @@ class InterpIO(C.Structure):
 
 class RunStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("setup_ms", "read_ms", "interp_ms", "write_ms", "total_ms", "init_ms", "target_ms",
-                                          "gridfile_ms", "mesh_ms", "download_ms", "writer_wait_ms")] + \
+                                          "gridfile_ms", "mesh_ms", "alloc_ms", "download_ms", "writer_wait_ms")] + \
                [(n, C.c_int64) for n in ("n_cells", "bytes_in", "bytes_out")] + \
                [("n_vars_written", C.c_int32), ("output_version", C.c_int32), ("p_top", C.c_double)]
 

@@ -366,31 +366,45 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
             j0[s] = j1[s] = 0;
             if (!dry) ck(ctx, mprg_get_slab(ctx, staggers[s], &j0[s], &j1[s]), "get_slab");
         }
-        auto dalloc = [&](int s, int32_t nlev) {
-            void *p = nullptr;
-            if (dry) return p;
-            const size_t bytes = std::max<size_t>((size_t)(j1[s] - j0[s]) * ni[s] * nlev * 4, 4);
-            ck(ctx, mprg_device_alloc(ctx, bytes, &p), "FieldCreate");
-            dev_allocs.push_back(p);
+        // One device arena for every output slab (plus Z_C's scratch): a single allocation instead of ~45 -- on a
+        // shared host each cudaMalloc can stall behind other tenants' driver calls.  Pass 0 sizes it, pass 1 carves it.
+        unsigned char *arena = nullptr;
+        size_t arena_used = 0;
+        auto dalloc = [&](int s, int32_t nlev) -> void * {
+            const size_t bytes = (std::max<size_t>((size_t)(j1[s] - j0[s]) * ni[s] * nlev * 4, 4) + 255) & ~(size_t)255;
+            void *p = arena ? arena + arena_used : nullptr;
+            arena_used += bytes;
             return p;
         };
-        for (size_t i = 0; i < fd.size(); ++i) { fd[i].src = sd[i].ptr; fd[i].dst = dalloc(0, fd[i].nlev); }
-        for (size_t i = 0; i < f2.size(); ++i) { f2[i].src = s2[i].ptr; f2[i].dst = dalloc(0, 1); }
-        for (size_t i = 0; i < fs.size(); ++i) { fs[i].src = ss[i].ptr; fs[i].dst = dalloc(0, fs[i].nlev); }
-        for (size_t i = 0; i < f3.size(); ++i) {
-            f3[i].src = s3[i].ptr;
-            // U / V of the wrf_mod_vars wind chain leave through u_stag / v_stag (interp.F90:295-328)
-            if (f3[i].klass != MPASSIT_CLASS_U && f3[i].klass != MPASSIT_CLASS_V) f3[i].dst = dalloc(0, f3[i].nlev);
-        }
-        if (cfg.interp_hist) {
-            io.ter = ter_be.data();
-            io.hgt = dalloc(0, 1);
-            if (do_u) io.u_stag = dalloc(1, nz);
-            if (do_v) io.v_stag = dalloc(2, nz);
+        void *d_mid = nullptr;
+        for (int pass = 0; pass < 2; ++pass) {
+            arena_used = 0;
+            for (size_t i = 0; i < fd.size(); ++i) { fd[i].src = sd[i].ptr; fd[i].dst = dalloc(0, fd[i].nlev); }
+            for (size_t i = 0; i < f2.size(); ++i) { f2[i].src = s2[i].ptr; f2[i].dst = dalloc(0, 1); }
+            for (size_t i = 0; i < fs.size(); ++i) { fs[i].src = ss[i].ptr; fs[i].dst = dalloc(0, fs[i].nlev); }
+            for (size_t i = 0; i < f3.size(); ++i) {
+                f3[i].src = s3[i].ptr;
+                // U / V of the wrf_mod_vars wind chain leave through u_stag / v_stag (interp.F90:295-328)
+                if (f3[i].klass != MPASSIT_CLASS_U && f3[i].klass != MPASSIT_CLASS_V) f3[i].dst = dalloc(0, f3[i].nlev);
+            }
+            if (cfg.interp_hist) {
+                io.ter = ter_be.data();
+                io.hgt = dalloc(0, 1);
+                if (do_u) io.u_stag = dalloc(1, nz);
+                if (do_v) io.v_stag = dalloc(2, nz);
+                d_mid = dalloc(0, nzp1 - 1);  // Z_C (write_data.F90:1406-1413)
+            }
+            if (pass == 0 && !dry) {
+                void *p = nullptr;
+                ck(ctx, mprg_device_alloc(ctx, arena_used, &p), "FieldCreate");
+                dev_allocs.push_back(p);
+                arena = (unsigned char *)p;
+            }
         }
 
         // ------------------------------------------------------------------ interp_data
         const double t2 = now_ms();
+        st.alloc_ms = t2 - (t1 + st.read_ms);
         if (!dry) {
             ck(ctx, mprg_set_source_byte_order(ctx, 1), "set_source_byte_order");
             rc = mpassit_interp_data(ctx, &cfg, &io, e, sizeof e);
@@ -716,7 +730,7 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
             if ((int)k == o_T && !dry) ck(ctx, mprg_post_affine(ctx, o.dev, slabM * nz, MPRG_F32, 1.0, -300.0), "post_affine");
             if ((int)k == o_phb && !dry) {
                 // Z_C = mid-level average of the regridded zgrid (:1406-1413), THEN zgrid x 9.81 (:1414)
-                void *mid = dalloc(0, nzp1 - 1);
+                void *mid = d_mid;
                 ck(ctx, mprg_post_midlevels(ctx, MPRG_CENTER, nzp1, MPRG_F32, MPRG_DEVICE, o.dev, mid), "post_midlevels");
                 swap_dev(mid, 0, nzp1 - 1);
                 write_slab(id_z, 0, nzp1 - 1, mid);

@@ -55,7 +55,7 @@ def main():
         st = host.run(nl, rundir, device=0)
         wall = (time.time() - t) * 1e3
         row = dict(run=r, wall_ms=round(wall, 1), setup_ms=round(st.setup_ms, 1),
-                   setup_split=[round(x, 1) for x in (st.init_ms, st.target_ms, st.gridfile_ms, st.mesh_ms)], read_ms=round(st.read_ms, 1),
+                   setup_split=[round(x, 1) for x in (st.init_ms, st.target_ms, st.gridfile_ms, st.mesh_ms)], read_ms=round(st.read_ms, 1), alloc_ms=round(st.alloc_ms, 1),
                    interp_ms=round(st.interp_ms, 1), write_ms=round(st.write_ms, 1),
                    write_split=[round(st.download_ms, 1), round(st.writer_wait_ms, 1)], total_ms=round(st.total_ms, 1),
                    in_GB=round(st.bytes_in / 1e9, 3), out_GB=round(st.bytes_out / 1e9, 3),
@@ -64,6 +64,8 @@ def main():
                    point_levels_per_s=round(st.bytes_out / 4 / max(st.total_ms, 1e-9) * 1e3, 0), vars=st.n_vars_written)
         rows.append(row)
         print(json.dumps(row), flush=True)
+    best = min(rows, key=lambda r: r["total_ms"])
+    print("best:", json.dumps(best))
     print(f"output file {os.path.getsize(paths['out']) / 1e9:.2f} GB, CDF-{rows[-1] and st.output_version}")
 
 
