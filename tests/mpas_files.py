@@ -98,9 +98,20 @@ def write_case(wl, rundir, fields, ter, real="f4"):
                      vert_names=("vorticity",))
     c = wl.cfg
     nl = os.path.join(rundir, "namelist.files")
+    tf = lambda b: ".true." if b else ".false."  # noqa: E731
+    lines = ["&config", f' grid_file_input_grid = "{paths["init"]}"', f' hist_file_input_grid = "{paths["history"]}"',
+             f' diag_file_input_grid = "{paths["diag"]}"', f' output_file = "{paths["out"]}"',
+             f" interp_diag = {tf(c.interp_diag)}", f" interp_hist = {tf(c.interp_hist)}", f" wrf_mod_vars = {tf(c.wrf_mod_vars)}",
+             " esmf_log = .false.", f" nx = {c.nx}", f" ny = {c.ny}"]
     if c.proj_code == 1:
-        defaults.write_namelist(nl, nx=c.nx, ny=c.ny, dx=c.dx, grid=paths["init"], hist=paths["history"], diag=paths["diag"],
-                                out=paths["out"])
+        lines += [" target_grid_type = 'lambert'", f" dx = {c.dx}", f" dy = {c.dy}", f" ref_lat = {c.ref_lat}",
+                  f" ref_lon = {c.ref_lon}", f" truelat1 = {c.truelat1}", f" truelat2 = {c.truelat2}", f" stand_lon = {c.stand_lon}"]
+    elif c.proj_code == 0:
+        lines += [" target_grid_type = 'lat-lon'", f" is_regional = {tf(c.is_regional)}", f" stand_lon = {c.stand_lon}"]
+        if c.is_regional:
+            lines += [f" ref_lat = {c.ref_lat}", f" ref_lon = {c.ref_lon}", f" dx = {c.dx}", f" dy = {c.dy}"]
     else:
-        raise NotImplementedError("write_case: Lambert workloads only")
+        raise NotImplementedError("write_case: Lambert and lat-lon workloads only")
+    with open(nl, "w") as fh:
+        fh.write("\n".join(lines) + "\n/\n")
     return nl, paths

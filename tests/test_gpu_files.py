@@ -38,14 +38,17 @@ def _reference_pass(wl):
     ter = D["ter"].cpu().numpy()
     njM, niM = wl.grids["M"][0].shape
     got = {}
+    wrf = bool(wl.cfg.wrf_mod_vars)
     for g in ("diag", "hist_2d", "hist_3d", "soil"):
         for s in D[g]:
-            if s.name.startswith("uReconstruct"):
-                continue
+            if wrf and s.name.startswith("uReconstruct"):
+                continue  # they leave through the staggered U / V
             got[s.target_name] = s.dst.cpu().numpy().reshape(s.nlev, njM, niM)
-    got["HGT"] = D["hgt"].cpu().numpy().reshape(njM, niM)
-    got["U"] = D["u_stag"].cpu().numpy().reshape((wl.nz,) + wl.grids["U"][0].shape)
-    got["V"] = D["v_stag"].cpu().numpy().reshape((wl.nz,) + wl.grids["V"][0].shape)
+    if wl.cfg.interp_hist:
+        got["HGT"] = D["hgt"].cpu().numpy().reshape(njM, niM)
+    if wrf:
+        got["U"] = D["u_stag"].cpu().numpy().reshape((wl.nz,) + wl.grids["U"][0].shape)
+        got["V"] = D["v_stag"].cpu().numpy().reshape((wl.nz,) + wl.grids["V"][0].shape)
     rg.close()
     return got, src, ter
 
@@ -55,13 +58,17 @@ def _expect_file(got, wl):
     f32 = np.float32
     # 2-D variables are [south_north][west_east] in the file (record dimension dropped by the reader)
     want = {k: (v[0] if (v.ndim == 3 and v.shape[0] == 1) else v) for k, v in got.items()}
-    want["T"] = got["T"] * f32(1.0) + f32(-300.0)               # write_data.F90:1339-1345 (the `< 10` guard is a no-op)
+    wrf = bool(wl.cfg.wrf_mod_vars)
+    if wrf:
+        want["T"] = got["T"] * f32(1.0) + f32(-300.0)           # write_data.F90:1339-1345 (the `< 10` guard is a no-op)
     phb = got["PHB"]
     zc = np.empty_like(phb)
     zc[:-1] = f32(0.5) * (phb[1:] + phb[:-1])                    # :1406-1412
     zc[-1] = 9.9692099683868690e+36                              # the level the reference never writes: fill value
     want["Z_C"] = zc
-    want["PHB"] = phb * f32(9.81)                                # :1414
+    want["PHB"] = phb * f32(9.81)                                # :1414 (keyed on the name alone, like Z_C)
+    if not wrf:
+        return want
     want["PB"] = got["P_HYD"]                                    # :1376 writes dum3dt, which still holds P_HYD
     for z, like in (("MU", "MUB"), ("P", "P_HYD"), ("PH", "PHB")):
         want[z] = np.zeros_like(got[like])                       # :1356, :1468, :1424
@@ -198,3 +205,38 @@ def test_unpinned_big_endian_sources_take_the_bounce_ring(engine_lib, dtype):
     assert np.array_equal(t.cpu().numpy(), a[:1000])
     r.release()
     rg.close()
+
+
+def test_files_global_latlon_target(host, tmp_path):
+    """BASELINE configs[0] through files: 40,962-cell global mesh, 55 levels -> 1-degree lat-lon, hist lists only,
+    no rotation (the projection is not Lambert), winds staggered on the non-periodic grid."""
+    from mpassit_b200 import workload
+
+    wl = workload.make("c1", rundir=str(tmp_path))
+    got, src, ter = _reference_pass(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), src, ter)
+    st = host.run(nl, str(tmp_path), device=0)
+    out, g, va, dims, order = mpas_files.read_output(paths["out"])
+    want = _expect_file(got, wl)
+    assert _check(out, want) >= 28 and "SINALPHA" not in out and g["MAP_PROJ"] == 0
+    assert st.n_cells == 40962 and dims["bottom_top"] == 55
+
+
+def test_files_without_wrf_mod_vars_and_cdf5_inputs(host, tmp_path):
+    """wrf_mod_vars = .false.: the winds are ordinary 3d_nz fields at mass points (no rotation, no staggering), T is
+    written as regridded, none of MU / P_TOP / PH / P / PB exists; the inputs are in the 64-bit-data format (CDF-5)."""
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    wl.cfg.wrf_mod_vars = 0
+    got, src, ter = _reference_pass(wl)
+    assert got["U"].shape == (wl.nz,) + wl.grids["M"][0].shape
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), src, ter)
+    for k in ("init", "diag", "history"):
+        host.nc_copy(paths[k], paths[k] + ".cdf5", 5)
+        os.replace(paths[k] + ".cdf5", paths[k])
+    host.run(nl, str(tmp_path), device=0)
+    out, g, va, dims, order = mpas_files.read_output(paths["out"])
+    want = _expect_file(got, wl)
+    assert _check(out, want) >= 44
+    assert np.array_equal(out["T"], got["T"]) and not ({"MU", "P_TOP", "PH", "P", "PB"} & set(order))

@@ -116,3 +116,60 @@ def test_two_gpu_slabs_gather_equals_single_rank(engine_lib):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res and all(res.values()), res
+
+
+def _file_worker(rank, world, port, rundir, q):
+    import torch
+    import torch.distributed as dist
+
+    from mpassit_b200 import host
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        host.load()
+        st = host.run(os.path.join(rundir, "namelist.files"), rundir, device=rank, rank=rank, nranks=world,
+                      comm=host.torch_comm())
+        dist.barrier()
+        q.put((rank, st.bytes_out, st.p_top, st.total_ms))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_file_run_equals_single_rank_file(engine_lib, tmp_path):
+    """mpassit_run on two GPUs, one process each: both ranks map the same input files, regrid their row slab and
+    pwrite it into the one output file (rank 0 creates it); P_TOP's max / min go through the host's communicator.
+    The file equals the single-rank file byte for byte."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from mpassit_b200 import build, host, workload
+    from tests import mpas_files
+    from tests.test_gpu_files import _reference_pass
+
+    build.build_host()
+    host.load()
+    wl = workload.make("mid", rundir=str(tmp_path))
+    got, src, ter = _reference_pass(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), src, ter)
+    st1 = host.run(nl, str(tmp_path), device=0)
+    single = open(paths["out"], "rb").read()
+    os.remove(paths["out"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_file_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res[0][2] == res[1][2] == st1.p_top
+    assert res[0][1] + res[1][1] == st1.bytes_out
+    assert open(paths["out"], "rb").read() == single
+    print("file run, mid workload: 1 GPU %.0f ms, 2 GPUs %.0f / %.0f ms" % (st1.total_ms, res[0][3], res[1][3]))

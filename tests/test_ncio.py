@@ -281,3 +281,51 @@ def test_large_blocks_are_written_in_parallel_chunks(host, tmp_path):
     host.nc_copy(p, q, 2)
     with netcdf_file(q, "r", mmap=False) as f:
         assert np.array_equal(f.variables["a"][:], a) and np.array_equal(f.variables["b"][:], a[1])
+
+
+def test_output_contract_variants_header_only(host, tmp_path):
+    """(a) lat-lon global target, hist only (BASELINE configs[0] shape): no rotation fields, MAP_PROJ 0, no PREC_ACC_DT;
+    (b) wrf_mod_vars = .false.: winds are plain 3d_nz variables on the mass grid, no MU / P_TOP / PH / P / PB;
+    (c) the same inputs in the 64-bit-data format (CDF-5) are read the same way."""
+    from mpassit_b200 import workload
+
+    # (a)
+    da = tmp_path / "a"
+    da.mkdir()
+    wl = workload.make("c1", rundir=str(da))
+    wl.nz = 3  # a thin column keeps the synthetic files small; the grid and lists are those of configs[0]
+    F, ter = _cpu_fields(wl)
+    nl, paths = mpas_files.write_case(wl, str(da), F, ter)
+    host.run(nl, str(da), device=-1)
+    out, g, va, dims, order = mpas_files.read_output(paths["out"])
+    assert dims["west_east"] == 360 and dims["south_north"] == 180 and dims["bottom_top"] == 3
+    assert g["MAP_PROJ"] == 0 and g["MAP_PROJ_CHAR"] == "Lat/Lon" and "PREC_ACC_DT" not in g
+    assert "SINALPHA" not in order and "COSALPHA" not in order and "RAINC" not in order
+    assert order.index("Z_C") == order.index("MAPFAC_V") + 1 and not out["MAPFAC_M"].any()
+    assert order[-2:] == ["P", "PB"] and out["U"].shape == (3, 180, 361) and out["V"].shape == (3, 181, 360)
+    # (b)
+    db = tmp_path / "b"
+    db.mkdir()
+    wl = workload.make("mini", rundir=str(db))
+    wl.cfg.wrf_mod_vars = 0
+    wl.cfg.interp_diag = 0
+    F, ter = _cpu_fields(wl)
+    nl, paths = mpas_files.write_case(wl, str(db), F, ter)
+    host.run(nl, str(db), device=-1)
+    out, g, va, dims, order = mpas_files.read_output(paths["out"])
+    for absent in ("MU", "P_TOP", "PH", "P", "PB", "RAINC", "REFL_10CM"):
+        assert absent not in order
+    it, jt = wl.cfg.i_target, wl.cfg.j_target
+    assert out["U"].shape == (wl.nz, jt, it) and va["U"]["units"] == "unit_of_uReconstructZonal" and va["U"]["stagger"] == ""
+    assert va["PHB"]["units"] == "unit_of_zgrid"  # the 'gpm' relabelling is a wrf_mod_vars feature (write_data.F90:814)
+    i3 = [order.index(n) for n in ("T", "U", "V", "QVAPOR", "MUB", "PHB", "W")]
+    assert i3 == sorted(i3)  # 3d_nz in list order (winds included), then 3d_nzp1
+    # (c)
+    for k in ("init", "diag", "history"):
+        host.nc_copy(paths[k], paths[k] + ".cdf5", 5)
+        import os
+        os.replace(paths[k] + ".cdf5", paths[k])
+    assert host.nc_describe(paths["history"])[0][:2] == ["version", "5"]
+    raw = open(paths["out"], "rb").read()
+    host.run(nl, str(db), device=-1)
+    assert open(paths["out"], "rb").read() == raw
