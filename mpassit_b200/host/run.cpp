@@ -23,7 +23,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
-#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -532,8 +531,8 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
             return (int)outs.size() - 1;
         };
         const char *cM = "XLONG XLAT XTIME";
-        int o_T = -1, o_mub = -1, o_phyd = -1, o_phb = -1, id_mu = -1, id_ptop = -1, id_ph = -1, id_p = -1, id_pb = -1;
-        (void)o_mub;
+        // MU, PH and P are defined but never written: the file is created zero-filled, which is their content
+        int o_T = -1, o_phyd = -1, o_phb = -1, id_ptop = -1, id_pb = -1;
         // diag fields, defined in list order whatever their rank (write_data.F90:571-613)
         for (size_t i = 0; i < fd.size(); ++i) {
             if (fd[i].nlev == 1) def_field(fd[i].target_name, MPRG_CENTER, 1, -1, "XY ", cM, sd[i].units, sd[i].longname, "", fd[i].dst);
@@ -554,8 +553,7 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
                 const std::string tn = f3[i].target_name;
                 if (cfg.wrf_mod_vars && tn == "T") o_T = o;
                 if (cfg.wrf_mod_vars && tn == "MUB") {
-                    o_mub = o;
-                    id_mu = w.def_var("MU", ncio::NC_FLOAT, {dTime, dZ, dSN, dWE});
+                    const int id_mu = w.def_var("MU", ncio::NC_FLOAT, {dTime, dZ, dSN, dWE});
                     w.att_text(id_mu, "MemoryOrder", "XYZ ");
                     w.att_text(id_mu, "coordinates", cM);
                     w.att_text(id_mu, "units", s3[i].units);
@@ -583,7 +581,7 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
                 // Z_C and the x 9.81 are keyed on the name alone (write_data.F90:1403), PH on wrf_mod_vars too
                 if (std::string(f3[i].target_name) == "PHB") o_phb = o;
                 if (phb) {
-                    id_ph = w.def_var("PH", ncio::NC_FLOAT, {dTime, dZs, dSN, dWE});
+                    const int id_ph = w.def_var("PH", ncio::NC_FLOAT, {dTime, dZs, dSN, dWE});
                     w.att_text(id_ph, "MemoryOrder", "XYZ ");
                     w.att_text(id_ph, "coordinates", cM);
                     w.att_text(id_ph, "units", "gpm");
@@ -607,10 +605,9 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
                 w.att_int(id, "FieldType", 104);
                 return id;
             };
-            id_p = def_dummy("P", "perturbation pressure (0.0)");
+            def_dummy("P", "perturbation pressure (0.0)");
             id_pb = def_dummy("PB", "BASE STATE PRESSURE (pfull)");
         }
-        (void)id_p;  // P, MU and PH are all zero: the file is created zero-filled, nothing to write
 
         // every rank lays out the same header; rank 0 creates the file, the others open it
         if (rank == 0 && !w.enddef(cfg.output_file, 1, true, why)) netcdf_err(std::string("opening") + cfg.output_file, why);
