@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the file-to-file run of the 12-km case (file_run)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...)
     # is sent to stderr instead, at the file-descriptor level
@@ -563,6 +564,40 @@ def main():
                "sample": f"{det['rows']}/{det['of_rows']} target rows x all fields (weights {det['weights_s']:.2f}s + "
                          f"apply {det['apply_s']:.2f}s); CPU restatement of the ESMF path, not ESMF"}
 
+    # `mpassit <namelist>` with NetCDF-classic files on both sides (host/run.cpp), 12-km miniature of the
+    # workload (0.6 GB in, 0.6 GB out): reported beside the metric, not part of it.  The 3-km case at full size
+    # (10 GB each way) is profiles/file_bench.py c2.
+    file_run = None
+    if rank == 0 and world == 1 and not args.no_files:
+        try:
+            import tempfile
+
+            from mpassit_b200 import host, mpas_files
+
+            host.load()
+            fdir = tempfile.mkdtemp(prefix="mpassit_bench_files_")
+            fwl = workload.make("mid", rundir=fdir)
+            FF = workload.make_fields(fwl, device="cuda:0")["dev"]
+            fsrc = {g: [(s.name, s.src.cpu().numpy()) for s in FF[g]] for g in ("diag", "hist_2d", "hist_3d", "soil")}
+            fnl, fpaths = mpas_files.write_case(fwl, fdir, fsrc, FF["ter"].cpu().numpy())
+            del FF, fsrc
+            runs = []
+            for _ in range(3):
+                st = host.run(fnl, fdir, device=local_rank)
+                runs.append(st)
+            st = min(runs, key=lambda r: r.total_ms)
+            file_run = {"workload": workload_name(fwl), "ms_total": round(st.total_ms, 1),
+                        "ms": {"setup": round(st.setup_ms, 1), "read": round(st.read_ms, 1), "interp": round(st.interp_ms, 1),
+                               "write": round(st.write_ms, 1)},
+                        "bytes_in": st.bytes_in, "bytes_out": st.bytes_out, "value": fwl.units_per_pass() / (st.total_ms * 1e-3),
+                        "unit": UNIT, "stat": "best of 3", "output": f"CDF-{st.output_version}",
+                        "note": "files in the page cache; big-endian sources swapped in HBM; each rank pwrites its slab"}
+            import shutil
+
+            shutil.rmtree(fdir, ignore_errors=True)
+        except Exception as ex:  # the metric does not depend on it
+            file_run = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -576,7 +611,7 @@ def main():
                        "tma_copies_per_tile": round(info["tile_runs"] / max(info["tiles"], 1), 2),
                        "columns_per_tile": round(info["tile_columns"] / max(info["tiles"], 1), 2)},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gather": gather, "graph_replay": graph_replay,
+            "gather": gather, "graph_replay": graph_replay, "file_run": file_run,
             "host_issue_ms_per_step": round(t_issue / args.steps * 1e3, 4),
             "store_ms": store_ms, "store_wall_s": store_wall,
             "route_bilinear": info,

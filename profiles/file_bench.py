@@ -28,7 +28,7 @@ def main():
     a = ap.parse_args()
 
     from mpassit_b200 import build, host, workload
-    from tests import mpas_files
+    from mpassit_b200 import mpas_files
 
     build.build_all()
     host.load()
