@@ -169,6 +169,19 @@ int mpassit_nc_get(const char *path, const char *var, int64_t rec, int64_t first
                    char *err, size_t errlen);
 int mpassit_nc_copy(const char *src, const char *dst, int version, char *err, size_t errlen);
 
+
+/* ---- ESMF regrid weight files (host/weights.cpp): dimensions n_a / n_b / n_s, variables col(n_s), row(n_s) (1-based)
+ * and S(n_s) -- what `ESMF_RegridWeightGen -w` and ESMF_SparseMatrixWrite produce.  The bridge for pinning parity on a
+ * machine that has ESMF: read ESMF's matrix as a 0-based CSR (rows sorted, ESMF's order kept inside a row) to compare
+ * with mprg_route_export_csr or to run the engine on it (mprg_route_import_csr); write the engine's matrix in the
+ * same format for ESMF-side tools.  (Classic NetCDF has no zero-length fixed dimension: an empty matrix is written
+ * as one entry (row 1, col 1) with weight 0.) */
+int mpassit_weights_sizes(const char *path, int64_t *n_a, int64_t *n_b, int64_t *n_s, char *err, size_t errlen);
+int mpassit_weights_read_csr(const char *path, int64_t n_b, int64_t n_s, int32_t *rowptr /*[n_b+1]*/, int32_t *col /*[n_s]*/,
+                             double *w /*[n_s]*/, char *err, size_t errlen);
+int mpassit_weights_write(const char *path, int64_t n_a, int64_t n_b, const int32_t *rowptr, const int32_t *col,
+                          const double *w, const char *method, char *err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

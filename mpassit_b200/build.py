@@ -94,7 +94,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 HOST_LIB = os.path.join(HERE, "libmpassit_host.so")
-HOST_SRC = ["setup.cpp", "target_grid.cpp", "interp.cpp", "ncio.cpp", "run.cpp"]
+HOST_SRC = ["setup.cpp", "target_grid.cpp", "interp.cpp", "ncio.cpp", "run.cpp", "weights.cpp"]
 
 
 def build_host(force: bool = False) -> str:

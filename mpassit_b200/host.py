@@ -104,6 +104,10 @@ def load() -> C.CDLL:
     L.mpassit_nc_describe.argtypes = [cp, cp, C.c_size_t, cp, C.c_size_t]
     L.mpassit_nc_get.argtypes = [cp, cp, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, cp, C.c_size_t]
     L.mpassit_nc_copy.argtypes = [cp, cp, C.c_int, cp, C.c_size_t]
+    i64p = C.POINTER(C.c_int64)
+    L.mpassit_weights_sizes.argtypes = [cp, i64p, i64p, i64p, cp, C.c_size_t]
+    L.mpassit_weights_read_csr.argtypes = [cp, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, cp, C.c_size_t]
+    L.mpassit_weights_write.argtypes = [cp, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, cp, cp, C.c_size_t]
     _lib = L
     return L
 
@@ -343,5 +347,32 @@ def nc_get(path: str, var: str, n: int, rec: int = 0, first: int = 0) -> np.ndar
 def nc_copy(src: str, dst: str, version: int = 0) -> None:
     e = _err()
     rc = load().mpassit_nc_copy(src.encode(), dst.encode(), version, e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+
+
+# ---- ESMF regrid weight files (host/weights.cpp) --------------------------------------------------------
+def read_esmf_weights(path: str) -> tuple[int, int, np.ndarray, np.ndarray, np.ndarray]:
+    """(n_a, n_b, rowptr[n_b+1], col[n_s] 0-based, S[n_s]) of an ESMF weight file, rows sorted, ESMF's order inside a row."""
+    na, nb, ns, e = C.c_int64(), C.c_int64(), C.c_int64(), _err()
+    rc = load().mpassit_weights_sizes(path.encode(), C.byref(na), C.byref(nb), C.byref(ns), e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    rowptr = np.empty(nb.value + 1, np.int32)
+    col = np.empty(ns.value, np.int32)
+    w = np.empty(ns.value, np.float64)
+    rc = load().mpassit_weights_read_csr(path.encode(), nb.value, ns.value, rowptr.ctypes.data, col.ctypes.data, w.ctypes.data, e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return na.value, nb.value, rowptr, col, w
+
+
+def write_esmf_weights(path: str, n_a: int, rowptr, col, w, method: str = "Bilinear") -> None:
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    col = np.ascontiguousarray(col, np.int32)
+    w = np.ascontiguousarray(w, np.float64)
+    e = _err()
+    rc = load().mpassit_weights_write(path.encode(), n_a, rowptr.size - 1, rowptr.ctypes.data, col.ctypes.data if col.size else None,
+                                      w.ctypes.data if w.size else None, method.encode(), e, len(e))
     if rc:
         raise HostError(rc, e.value.decode())

@@ -329,3 +329,106 @@ def test_output_contract_variants_header_only(host, tmp_path):
     raw = open(paths["out"], "rb").read()
     host.run(nl, str(db), device=-1)
     assert open(paths["out"], "rb").read() == raw
+
+
+def test_esmf_weight_files(host, tmp_path):
+    """The ESMF weight-file bridge (host/weights.cpp): a file laid out like ESMF_RegridWeightGen's (entries in no
+    particular order, 1-based, extra variables present) reads back as a sorted 0-based CSR with ESMF's order kept
+    inside each row; the engine-side writer produces a file scipy reads with the same matrix."""
+    rng = np.random.default_rng(5)
+    n_a, n_b = 500, 300
+    lens = rng.integers(0, 5, n_b)
+    rp = np.zeros(n_b + 1, np.int32)
+    np.cumsum(lens, out=rp[1:])
+    col = rng.integers(0, n_a, rp[-1]).astype(np.int32)
+    w = rng.random(rp[-1])
+    row = np.repeat(np.arange(n_b), lens)
+    perm = rng.permutation(rp[-1])            # ESMF promises no order
+    p = str(tmp_path / "esmf_w.nc")
+    with netcdf_file(p, "w", version=2) as f:
+        for n, l in (("n_a", n_a), ("n_b", n_b), ("n_s", int(rp[-1])), ("nv_a", 3), ("src_grid_rank", 1)):
+            f.createDimension(n, l)
+        f.title = b"ESMF Offline Regridding Weight Generator"
+        f.createVariable("frac_b", "f8", ("n_b",))[:] = 1.0
+        f.createVariable("col", "i4", ("n_s",))[:] = col[perm] + 1
+        f.createVariable("row", "i4", ("n_s",))[:] = row[perm] + 1
+        f.createVariable("S", "f8", ("n_s",))[:] = w[perm]
+    na, nb, rp2, col2, w2 = host.read_esmf_weights(p)
+    assert (na, nb) == (n_a, n_b) and np.array_equal(rp2, rp)
+    for i in range(n_b):                      # same entries per row, in the file's order
+        k = np.flatnonzero(row[perm] == i)
+        assert np.array_equal(col2[rp[i]:rp[i + 1]], col[perm][k]) and np.array_equal(w2[rp[i]:rp[i + 1]], w[perm][k])
+    q = str(tmp_path / "ours_w.nc")
+    host.write_esmf_weights(q, n_a, rp, col, w, "Bilinear")
+    with netcdf_file(q, "r", mmap=False) as f:
+        assert f.dimensions["n_a"] == n_a and f.dimensions["n_b"] == n_b and f.dimensions["n_s"] == rp[-1]
+        assert np.array_equal(f.variables["col"][:], col + 1) and np.array_equal(f.variables["row"][:], row + 1)
+        assert np.array_equal(f.variables["S"][:], w)
+    na, nb, rp3, col3, w3 = host.read_esmf_weights(q)
+    assert np.array_equal(rp3, rp) and np.array_equal(col3, col) and np.array_equal(w3, w)
+    # an empty matrix survives the trip as a single zero weight; junk is refused
+    host.write_esmf_weights(q, 7, np.zeros(4, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    na, nb, rp4, col4, w4 = host.read_esmf_weights(q)
+    assert (na, nb) == (7, 3) and rp4.tolist() == [0, 1, 1, 1] and w4.tolist() == [0.0]
+    with netcdf_file(p, "w", version=2) as f:
+        f.createDimension("n_s", 2)
+        f.createVariable("S", "f8", ("n_s",))[:] = 1.0
+    with pytest.raises(host.HostError, match="not an ESMF weight file"):
+        host.read_esmf_weights(p)
+
+
+def test_esmf_kit_mesh_grid_files_and_compare(host, tmp_path):
+    """tools/esmf_kit.py: the ESMF unstructured-mesh file follows what the reference hands to ESMF_MeshCreate
+    (model_grid.F90:446-497), the SCRIP file carries the CENTER points with their 4 CORNER-stagger corners, and
+    `compare` tells identical / perturbed / restructured matrices apart."""
+    from mpassit_b200 import workload
+    from tools import esmf_kit
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    paths = esmf_kit.export("mini", str(tmp_path))
+    m = wl.mesh
+    with netcdf_file(paths["mesh"], "r", mmap=False) as f:
+        assert f.gridType == b"unstructured" and f.dimensions["elementCount"] == m.lonCell.size
+        nc, conn, num = f.variables["nodeCoords"][:], f.variables["elementConn"][:], f.variables["numElementConn"][:]
+        cc = f.variables["centerCoords"][:]
+        assert f.variables["elementConn"].start_index == 1 and f.variables["nodeCoords"].units == b"degrees"
+    lonV, latV = esmf_kit.mesh_degrees(m.lonVertex, m.latVertex)
+    assert np.array_equal(nc[:, 0], lonV) and np.array_equal(nc[:, 1], latV) and nc[:, 0].max() <= 180.0
+    assert np.array_equal(num, (m.verticesOnCell > 0).sum(axis=1))
+    for c in (0, 17, m.lonCell.size - 1):
+        v = m.verticesOnCell[c][m.verticesOnCell[c] > 0]
+        assert np.array_equal(conn[c, :v.size], v) and (conn[c, v.size:] == -1).all()
+    assert np.array_equal(cc[:, 1], esmf_kit.mesh_degrees(m.lonCell, m.latCell)[1])
+    latM, lonM = wl.grids["M"]
+    latQ, lonQ = wl.grids["CORNER"]
+    with netcdf_file(paths["grid"], "r", mmap=False) as f:
+        assert f.variables["grid_dims"][:].tolist() == [latM.shape[1], latM.shape[0]]
+        assert np.array_equal(f.variables["grid_center_lat"][:], latM.reshape(-1))
+        cl = f.variables["grid_corner_lat"][:].reshape(latM.shape + (4,))
+        co = f.variables["grid_corner_lon"][:].reshape(latM.shape + (4,))
+    j, i = 5, 9
+    assert cl[j, i].tolist() == [latQ[j, i], latQ[j, i + 1], latQ[j + 1, i + 1], latQ[j + 1, i]]
+    assert co[j, i].tolist() == [lonQ[j, i], lonQ[j, i + 1], lonQ[j + 1, i + 1], lonQ[j + 1, i]]
+    # counter-clockwise: positive signed area in the (lon, lat) plane
+    x, y = co[j, i], cl[j, i]
+    assert sum(x[k] * y[(k + 1) % 4] - x[(k + 1) % 4] * y[k] for k in range(4)) > 0
+    # compare
+    rng = np.random.default_rng(2)
+    rp = np.arange(0, 3 * 200 + 1, 3).astype(np.int32)
+    col = rng.integers(0, 900, 600).astype(np.int32)
+    w = rng.random(600)
+    a, b = str(tmp_path / "wa.nc"), str(tmp_path / "wb.nc")
+    host.write_esmf_weights(a, 900, rp, col, w)
+    shuffled = col.reshape(200, 3)[:, ::-1].reshape(-1)        # same sources, another order inside the rows
+    host.write_esmf_weights(b, 900, rp, shuffled, w.reshape(200, 3)[:, ::-1].reshape(-1))
+    r = esmf_kit.compare(a, b)
+    assert r["rows_same_sources"] == 200 and r["max_weight_difference"] == 0.0 and r["verdict"].startswith("identical structure, weights")
+    w2 = w.copy()
+    w2[301] += 1e-6
+    host.write_esmf_weights(b, 900, rp, col, w2)
+    r = esmf_kit.compare(a, b)
+    assert r["verdict"] == "identical structure" and abs(r["max_weight_difference"] - 1e-6) < 1e-12 and r["worst_row"] == 100
+    col2 = col.copy()
+    col2[0] = (col2[0] + 1) % 900
+    host.write_esmf_weights(b, 900, rp, col2, w)
+    assert esmf_kit.compare(a, b)["verdict"] == "structures differ"
