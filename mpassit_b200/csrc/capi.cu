@@ -500,8 +500,15 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
             // a slot that must grow grows every slot of the ring to the same size: the ring rotates across
             // calls, so otherwise the same growth (a device-wide sync plus a large allocation) would be paid
             // again on each of the next passes
-            if (src_mem == MPRG_HOST && inB > ctx->stageIn[slot].n)
-                for (auto &b : ctx->stageIn) b.ensure_shared(inB);
+            if (src_mem == MPRG_HOST && inB > ctx->stageIn[slot].n) {
+                // size for the largest batch a pass can bring, not just this one: a wind pair is never cut in two, so
+                // leave room for two of the largest field seen (growing 4 x 1.2 GB a second time cost 0.6 - 2.3 s of
+                // physical allocation in the file driver, where every run starts with a fresh context)
+                size_t big = 0;
+                for (int k = 0; k < nfields; ++k) big = std::max(big, in_slot(k));
+                const size_t want = std::max(inB, 2 * big);
+                for (auto &b : ctx->stageIn) b.ensure_shared(want);
+            }
             if (dst_mem == MPRG_HOST && outB > ctx->stageOut[slot].n)
                 for (auto &b : ctx->stageOut) b.ensure_shared(outB);
             // slot reuse: the kernel that last read stageIn[slot] / the D2H that last read stageOut[slot]
