@@ -81,6 +81,10 @@ int mpassit_target_dims(const mpassit_config *cfg, int mprg_stagger, int32_t *ni
  * lat, lon: [nj][ni] degrees.  LC and lat-lon projections. */
 int mpassit_target_coords(const mpassit_config *cfg, int mprg_stagger, double *lat, double *lon,
                           char *err, size_t errlen);
+/* get_cell_corners, model_grid.F90:1902-1972 (target_grid_type = 'file'): CORNER-stagger points [nj+1][ni+1]
+ * synthesised from the mass points [nj][ni] and the cell size, bearings and truncated pi as in the reference */
+void mpassit_get_cell_corners(const double *lat, const double *lon, int32_t ni, int32_t nj, double dx, double *clat,
+                              double *clon);
 /* get_rotang, model_grid.F90:2450-2507, on an [nj][ni] lat/lon pair */
 void mpassit_get_rotang(const double *lat, const double *lon, int32_t ni, int32_t nj, double *cosa, double *sina);
 
@@ -137,7 +141,8 @@ int mpassit_get_map_factor(const mpassit_config *cfg, const double *xlat, int64_
 /* ---- program mpassit, mpassit.F90:23-146, files on both sides ------------------------------------------
  * read_setup_namelist -> define_target_grid -> define_input_grid -> read_input_data -> interp_data ->
  * write_to_file for this rank's row slab.  Input files: NetCDF classic (CDF-1/2/5) MPAS grid / diag / history
- * files, mapped and consumed in file order and byte order (no transpose, no host swap); output: one NetCDF
+ * files, mapped and consumed in file order and byte order (no transpose, no host swap); with target_grid_type =
+ * 'file' the target comes from a WRF-style file (define_target_grid_file, model_grid.F90:1203-1890); output: one NetCDF
  * classic file holding the reference's dimensions, variables and attributes (write_data.F90:170-994), each
  * rank writing its own rows with pwrite.  The var-list files diaglist / histlist_2d / histlist_3d /
  * histlist_soil are read from `varlist_dir` (NULL = the working directory, as the reference does).

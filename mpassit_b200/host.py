@@ -96,6 +96,8 @@ def load() -> C.CDLL:
     L.mpassit_target_coords.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_void_p, cp, C.c_size_t]
     L.mpassit_get_rotang.argtypes = [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p]
     L.mpassit_get_rotang.restype = None
+    L.mpassit_get_cell_corners.argtypes = [C.c_void_p, C.c_void_p, i32, i32, C.c_double, C.c_void_p, C.c_void_p]
+    L.mpassit_get_cell_corners.restype = None
     L.mpassit_classify_fields.argtypes = [C.POINTER(Config), C.POINTER(InterpIO)] + [C.POINTER(i32)] * 4
     L.mpassit_interp_data.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(InterpIO), cp, C.c_size_t]
     L.mpassit_xytoll.argtypes = [C.POINTER(Config), C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -209,6 +211,16 @@ def get_rotang(lat: np.ndarray, lon: np.ndarray) -> tuple[np.ndarray, np.ndarray
     cosa, sina = np.empty_like(lat), np.empty_like(lat)
     load().mpassit_get_rotang(lat.ctypes.data, lon.ctypes.data, ni, nj, cosa.ctypes.data, sina.ctypes.data)
     return cosa, sina
+
+
+def get_cell_corners(lat: np.ndarray, lon: np.ndarray, dx: float) -> tuple[np.ndarray, np.ndarray]:
+    """get_cell_corners (model_grid.F90:1902-1972): CORNER-stagger (lat, lon) [nj+1][ni+1] of a file-mode target."""
+    lat = np.ascontiguousarray(lat, np.float64)
+    lon = np.ascontiguousarray(lon, np.float64)
+    nj, ni = lat.shape
+    clat, clon = np.empty((nj + 1, ni + 1)), np.empty((nj + 1, ni + 1))
+    load().mpassit_get_cell_corners(lat.ctypes.data, lon.ctypes.data, ni, nj, float(dx), clat.ctypes.data, clon.ctypes.data)
+    return clat, clon
 
 
 @dataclass

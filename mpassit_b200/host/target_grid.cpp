@@ -220,6 +220,35 @@ int mpassit_get_map_factor(const mpassit_config *cfg, const double *xlat, int64_
     return 0;
 }
 
+void mpassit_get_cell_corners(const double *lat, const double *lon, int32_t ni, int32_t nj, double dx, double *clat,
+                              double *clon) {
+    // get_cell_corners, model_grid.F90:1902-1972, as written: every interior corner (i, j) is the point at bearing
+    // 135 degrees (clockwise from north, i.e. SOUTH-EAST despite the `_sw` names) and distance sqrt(dx^2 / 2) from
+    // centre (i, j); the last column uses bearing 225 from centre (ni, j), the last row bearing 45 from centre (i, nj),
+    // the last corner bearing 315 from centre (ni, nj).  pi is the truncated literal 3.14159265359 (R8 under -r8),
+    // R = 6370000 m.  lat/lon: [nj][ni]; clat/clon: [nj+1][ni+1].
+    const double pi = 3.14159265359, R = 6370000.0;
+    const double d = std::sqrt((dx * dx) / 2.0);
+    auto step = [&](double lat_deg, double lon_deg, double brng_deg, double *olat, double *olon) {
+        const double lat1 = lat_deg * (pi / 180.0), lon1 = lon_deg * (pi / 180.0), brng = brng_deg * pi / 180.0;
+        const double lat2 = std::asin(std::sin(lat1) * std::cos(d / R) + std::cos(lat1) * std::sin(d / R) * std::cos(brng));
+        const double lon2 = lon1 + std::atan2(std::sin(brng) * std::sin(d / R) * std::cos(lat1), std::cos(d / R) - std::sin(lat1) * std::sin(lat2));
+        *olat = lat2 * 180.0 / pi;
+        *olon = lon2 * 180.0 / pi;
+    };
+    const int32_t nic = ni + 1;
+    par::range(nj + 1, 16, [&](int64_t jb, int64_t je) {
+        for (int32_t j = (int32_t)jb; j < (int32_t)je; ++j)
+            for (int32_t i = 0; i <= ni; ++i) {
+                double *olat = &clat[(size_t)j * nic + i], *olon = &clon[(size_t)j * nic + i];
+                if (j == nj && i == ni) step(lat[(size_t)(nj - 1) * ni + ni - 1], lon[(size_t)(nj - 1) * ni + ni - 1], 315.0, olat, olon);
+                else if (i == ni) step(lat[(size_t)j * ni + ni - 1], lon[(size_t)j * ni + ni - 1], 225.0, olat, olon);
+                else if (j == nj) step(lat[(size_t)(nj - 1) * ni + i], lon[(size_t)(nj - 1) * ni + i], 45.0, olat, olon);
+                else step(lat[(size_t)j * ni + i], lon[(size_t)j * ni + i], 135.0, olat, olon);
+            }
+    });
+}
+
 void mpassit_get_rotang(const double *xlat, const double *xlon, int32_t ni, int32_t nj, double *cosa, double *sina) {
     // get_rotang, model_grid.F90:2450-2507: centred in j, one-sided on the first/last row.
     // (The reference evaluates this per PET tile, so with >1 PET its one-sided rows sit

@@ -76,7 +76,7 @@ def read_output(path):
     return out, gatts, vatts, dims, order
 
 
-def write_case(wl, rundir, fields, ter, real="f4"):
+def write_case(wl, rundir, fields, ter, real="f4", target_file=None):
     """The three input files of a workload + a namelist pointing at them.  fields: {group: [(mpas_name, array)]}
     for group in diag / hist_2d / hist_3d / soil ([n][nlev] level-fastest, as MPAS stores them)."""
     import os
@@ -103,7 +103,10 @@ def write_case(wl, rundir, fields, ter, real="f4"):
              f' diag_file_input_grid = "{paths["diag"]}"', f' output_file = "{paths["out"]}"',
              f" interp_diag = {tf(c.interp_diag)}", f" interp_hist = {tf(c.interp_hist)}", f" wrf_mod_vars = {tf(c.wrf_mod_vars)}",
              " esmf_log = .false.", f" nx = {c.nx}", f" ny = {c.ny}"]
-    if c.proj_code == 1:
+    if target_file:  # define_target_grid_file: sizes and projection come from a WRF-style file
+        lines = [ln for ln in lines if not ln.startswith((" nx", " ny"))]
+        lines += [" target_grid_type = 'file'", f' file_target_grid = "{target_file}"']
+    elif c.proj_code == 1:
         lines += [" target_grid_type = 'lambert'", f" dx = {c.dx}", f" dy = {c.dy}", f" ref_lat = {c.ref_lat}",
                   f" ref_lon = {c.ref_lon}", f" truelat1 = {c.truelat1}", f" truelat2 = {c.truelat2}", f" stand_lon = {c.stand_lon}"]
     elif c.proj_code == 0:

@@ -274,3 +274,38 @@ def test_engine_weights_round_trip_through_esmf_weight_files(engine_lib, host, t
         r.release()
         r2.release()
     rg.close()
+
+
+def test_files_target_grid_from_a_wrf_style_file(host, tmp_path):
+    """target_grid_type = 'file': the target comes from a WRF-style file (here: the output of a parameter-mode run).
+    The run must equal an in-memory pass on the grid such a file holds -- float-rounded centres, staggers and rotation
+    angles, corners synthesised by get_cell_corners -- plus the writer's arithmetic."""
+    import dataclasses
+
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    got, src, ter = _reference_pass(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), src, ter)
+    host.run(nl, str(tmp_path), device=0)
+    target = str(tmp_path / "wrf_target.nc")
+    os.replace(paths["out"], target)
+    t = mpas_files.read_output(target)[0]
+    f8 = lambda k: t[k].astype(np.float64)  # noqa: E731
+    grids = {"M": (f8("XLAT"), f8("XLONG")), "U": (f8("XLAT_U"), f8("XLONG_U")), "V": (f8("XLAT_V"), f8("XLONG_V"))}
+    grids["CORNER"] = host.get_cell_corners(*grids["M"], wl.cfg.dx)
+    wl2 = dataclasses.replace(wl, grids=grids, cosa=f8("COSALPHA"), sina=f8("SINALPHA"))
+    got2, _, _ = _reference_pass(wl2)
+    nl2, paths2 = mpas_files.write_case(wl, str(tmp_path), src, ter, target_file=target)
+    host.run(nl2, str(tmp_path), device=0)
+    out, g, va, dims, order = mpas_files.read_output(paths2["out"])
+    want = _expect_file(got2, wl)
+    # the reference's corner bearings turn the last column / row of target cells inside out (DESIGN.md): conservative
+    # fields are compared as the same bits, whatever they are there
+    for k in ("SNOW", "SNOWH"):
+        assert np.array_equal(out[k], want.pop(k), equal_nan=True), k
+    assert _check(out, want) >= 44
+    assert np.array_equal(out["XLAT"], t["XLAT"]) and np.array_equal(out["MAPFAC_U"], t["MAPFAC_U"])
+    # and the float-rounded grid really is another grid: the parameter-mode result differs in the last bits
+    assert not np.array_equal(got2["PSFC"], got["PSFC"])
+    assert np.abs(got2["PSFC"] - got["PSFC"]).max() <= 1e-3 * np.abs(got["PSFC"]).max()

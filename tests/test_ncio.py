@@ -432,3 +432,75 @@ def test_esmf_kit_mesh_grid_files_and_compare(host, tmp_path):
     col2[0] = (col2[0] + 1) % 900
     host.write_esmf_weights(b, 900, rp, col2, w)
     assert esmf_kit.compare(a, b)["verdict"] == "structures differ"
+
+
+def _corners_numpy(lat, lon, dx):
+    """get_cell_corners (model_grid.F90:1902-1972) restated with numpy: bearings 135 / 225 / 45 / 315, truncated pi."""
+    pi, R = 3.14159265359, 6370000.0
+    d = np.sqrt(dx ** 2.0 / 2.0)
+    nj, ni = lat.shape
+
+    def step(la, lo, b):
+        lat1, lon1, br = la * (pi / 180.0), lo * (pi / 180.0), b * pi / 180.0
+        lat2 = np.arcsin(np.sin(lat1) * np.cos(d / R) + np.cos(lat1) * np.sin(d / R) * np.cos(br))
+        lon2 = lon1 + np.arctan2(np.sin(br) * np.sin(d / R) * np.cos(lat1), np.cos(d / R) - np.sin(lat1) * np.sin(lat2))
+        return lat2 * 180.0 / pi, lon2 * 180.0 / pi
+
+    clat, clon = np.empty((nj + 1, ni + 1)), np.empty((nj + 1, ni + 1))
+    clat[:nj, :ni], clon[:nj, :ni] = step(lat, lon, 135.0)
+    clat[:nj, ni], clon[:nj, ni] = step(lat[:, -1], lon[:, -1], 225.0)
+    clat[nj, :ni], clon[nj, :ni] = step(lat[-1, :], lon[-1, :], 45.0)
+    clat[nj, ni], clon[nj, ni] = step(lat[-1, -1], lon[-1, -1], 315.0)
+    return clat, clon
+
+
+def test_target_grid_from_a_wrf_style_file(host, tmp_path):
+    """target_grid_type = 'file' (define_target_grid_file, model_grid.F90:1203-1890): the output of a parameter-mode
+    run is itself a valid target file; a run that reads it reproduces its grid description (stored as float, so
+    bit-identical), takes sizes / projection from its attributes, keeps its terrain when no hist data is regridded, and
+    synthesises the corners the way get_cell_corners does."""
+    from mpassit_b200 import lib as L
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    F, ter = _cpu_fields(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), F, ter)
+    host.run(nl, str(tmp_path), device=-1)
+    out1, g1, va1, dims1, order1 = mpas_files.read_output(paths["out"])
+    target = str(tmp_path / "wrf_target.nc")
+    import os
+    os.replace(paths["out"], target)
+    wl.cfg.interp_hist = 0
+    nl2, paths2 = mpas_files.write_case(wl, str(tmp_path), F, ter, target_file=target)
+    host.run(nl2, str(tmp_path), device=-1)
+    out2, g2, va2, dims2, order2 = mpas_files.read_output(paths2["out"])
+    for k in ("west_east", "south_north", "west_east_stag", "south_north_stag"):
+        assert dims2[k] == dims1[k]
+    for k in ("XLAT", "XLONG", "XLAT_U", "XLONG_U", "XLAT_V", "XLONG_V", "MAPFAC_M", "MAPFAC_U", "MAPFAC_V", "SINALPHA", "COSALPHA"):
+        assert np.array_equal(out2[k], out1[k]), k
+    for k in ("DX", "DY", "CEN_LAT", "CEN_LON", "MOAD_CEN_LAT", "TRUELAT1", "TRUELAT2", "STAND_LON", "POLE_LAT", "MAP_PROJ",
+              "MAP_PROJ_CHAR", "WEST-EAST_GRID_DIMENSION"):
+        assert g2[k] == g1[k], k
+    assert "PSFC" not in order2 and "RAINC" in order2          # diag only this time
+    assert np.array_equal(out2["HGT"], out1["HGT"])            # hgt_target_grid as read from the target file
+    # corners: the C mirror against the numpy restatement, on the float-rounded centres the file holds
+    lat = out1["XLAT"].astype(np.float64)
+    lon = out1["XLONG"].astype(np.float64)
+    clat, clon = host.get_cell_corners(lat, lon, 30000.0)
+    wlat, wlon = _corners_numpy(lat, lon, 30000.0)
+    assert np.abs(clat - wlat).max() < 1e-12 and np.abs(clon - wlon).max() < 1e-12
+    # what the reference's bearings mean on the ground: interior corners sit south-EAST of their centre (bearing 135),
+    # half a cell diagonal away
+    assert (clat[:-1, :-1] < lat).all() and (clon[:-1, :-1] > lon).all()
+    d = 6370000.0 * np.hypot(np.deg2rad(clat[:-1, :-1] - lat), np.deg2rad(clon[:-1, :-1] - lon) * np.cos(np.deg2rad(lat)))
+    assert np.abs(d / np.sqrt(30000.0 ** 2 / 2) - 1).max() < 1e-3
+    # a target file without the staggered coordinates is refused like netcdf_err does
+    from scipy.io import netcdf_file as ncf
+    bad = str(tmp_path / "bad_target.nc")
+    with ncf(bad, "w", version=2) as f:
+        f.createDimension("west_east", 4)
+        f.createDimension("south_north", 3)
+        f.DX = 30000.0
+    nl3, _ = mpas_files.write_case(wl, str(tmp_path), F, ter, target_file=bad)
+    with pytest.raises(host.HostError, match="reading CEN_LAT"):
+        host.run(nl3, str(tmp_path), device=-1)
