@@ -16,7 +16,7 @@ def _xtime(f, stamp):
     v[0, :] = np.frombuffer(stamp.ljust(64).encode(), "S1")
 
 
-def write_grid_file(path, mesh, nz, nsoil, ter, version=2, real="f4"):
+def write_grid_file(path, mesh, nz, nsoil, ter, version=2, real="f4", start=None):
     nC, nV = mesh.lonCell.size, mesh.lonVertex.size
     with netcdf_file(path, "w", version=version) as f:
         f.createDimension("Time", None)
@@ -33,10 +33,10 @@ def write_grid_file(path, mesh, nz, nsoil, ter, version=2, real="f4"):
         v[:] = ter
         v = f.createVariable("zs", real, ("Time", "nCells", "nSoilLevels"))
         v[0, :, :] = np.tile(np.array([0.05, 0.25, 0.7, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5][:nsoil]), (nC, 1))
-        _xtime(f, START_TIME)
+        _xtime(f, start or START_TIME)
 
 
-def write_field_file(path, fields, nCells, nVertices, nz, nsoil, attrs, version=2, vert_names=()):
+def write_field_file(path, fields, nCells, nVertices, nz, nsoil, attrs, version=2, vert_names=(), valid=None):
     """fields: list of (name, array [n][nlev] or [n]); every variable gets a Time record dimension, units and long_name."""
     with netcdf_file(path, "w", version=version) as f:
         f.createDimension("Time", None)
@@ -45,7 +45,7 @@ def write_field_file(path, fields, nCells, nVertices, nz, nsoil, attrs, version=
             f.createDimension(n, l)
         for k, v in attrs.items():
             setattr(f, k, v)
-        _xtime(f, VALID_TIME)
+        _xtime(f, valid or VALID_TIME)
         for name, a in fields:
             a = np.asarray(a)
             hdim = "nVertices" if name in vert_names else "nCells"
@@ -76,7 +76,7 @@ def read_output(path):
     return out, gatts, vatts, dims, order
 
 
-def write_case(wl, rundir, fields, ter, real="f4", target_file=None):
+def write_case(wl, rundir, fields, ter, real="f4", target_file=None, start=None, valid=None, config_dt=18.0):
     """The three input files of a workload + a namelist pointing at them.  fields: {group: [(mpas_name, array)]}
     for group in diag / hist_2d / hist_3d / soil ([n][nlev] level-fastest, as MPAS stores them)."""
     import os
@@ -86,16 +86,18 @@ def write_case(wl, rundir, fields, ter, real="f4", target_file=None):
     m = wl.mesh
     paths = {k: os.path.join(rundir, f"mpas.{k}.nc") for k in ("init", "diag", "history")}
     paths["out"] = os.path.join(rundir, "mpassit_out.nc")
-    write_grid_file(paths["init"], m, wl.nz, wl.nsoil, np.asarray(ter).reshape(-1), real=real)
+    start = start or START_TIME
+    write_grid_file(paths["init"], m, wl.nz, wl.nsoil, np.asarray(ter).reshape(-1), real=real, start=start)
     nC, nV = m.lonCell.size, m.lonVertex.size
     cast = (lambda a: np.asarray(a, np.float64)) if real == "f8" else (lambda a: np.asarray(a, np.float32))
     write_field_file(paths["diag"], [(n, cast(a)) for n, a in fields.get("diag", [])], nC, nV, wl.nz, wl.nsoil,
-                     dict(config_start_time=START_TIME.encode(), config_dt=np.float64(18.0), output_interval=np.int32(3600)))
+                     dict(config_start_time=start.encode(), config_dt=np.float64(config_dt), output_interval=np.int32(3600)),
+                     valid=valid)
     hist = [(n, cast(a)) for g in ("hist_2d", "hist_3d", "soil") for n, a in fields.get(g, [])]
     write_field_file(paths["history"], hist, nC, nV, wl.nz, wl.nsoil,
-                     dict(config_start_time=START_TIME.encode(), config_dt=np.float64(18.0), config_lsm_scheme=b"noah",
+                     dict(config_start_time=start.encode(), config_dt=np.float64(config_dt), config_lsm_scheme=b"noah",
                           config_microp_scheme=b"mp_nssl2m", config_convection_scheme=b"cu_grell_freitas"),
-                     vert_names=("vorticity",))
+                     vert_names=("vorticity",), valid=valid)
     c = wl.cfg
     nl = os.path.join(rundir, "namelist.files")
     tf = lambda b: ".true." if b else ".false."  # noqa: E731

@@ -504,3 +504,39 @@ def test_target_grid_from_a_wrf_style_file(host, tmp_path):
     nl3, _ = mpas_files.write_case(wl, str(tmp_path), F, ter, target_file=bad)
     with pytest.raises(host.HostError, match="reading CEN_LAT"):
         host.run(nl3, str(tmp_path), device=-1)
+
+
+@pytest.mark.parametrize("start,valid,dt,minutes", [
+    ("2024-02-28_18:00:00", "2024-03-01_06:00:00", 20.0, -36 * 60.0),                 # across a leap day
+    ("2023-12-31_23:30:00", "2024-01-01_00:15:30", 0.0, -45.5),                        # across a year, dt unknown
+    ("2024-03-25_09:00:00", "2024-03-25_09:00:00", 18.0, 0.0),
+    ("2100-02-28_00:00:00", "2100-03-01_00:00:00", 60.0, -1440.0),                     # 2100 is not a leap year
+])
+def test_xtime_and_itimestep(host, tmp_path, start, valid, dt, minutes):
+    """XTIME = (start - valid) in minutes and ITIMESTEP = int(seconds / config_dt), 0 when config_dt is not positive
+    (write_data.F90:1184-1210, datetime arithmetic of datetime_module)."""
+    from mpassit_b200 import workload
+
+    wl = workload.make("mini", rundir=str(tmp_path))
+    wl.cfg.interp_hist = 0
+    F, ter = _cpu_fields(wl)
+    nl, paths = mpas_files.write_case(wl, str(tmp_path), {"diag": F["diag"]}, ter, start=start, valid=valid, config_dt=dt)
+    host.run(nl, str(tmp_path), device=-1)
+    out, g, va, dims, order = mpas_files.read_output(paths["out"])
+    assert out["XTIME"] == np.float32(minutes) and out["Times"].tobytes().decode() == valid
+    assert out["ITIMESTEP"] == (int(minutes * 60.0 / dt) if dt > 0 else 0)
+    assert g["START_DATE"] == start and va["XTIME"]["description"] == "minutes since " + start
+
+
+def test_command_line_entry(host, tmp_path, monkeypatch, capsys):
+    """`python -m mpassit_b200 <namelist>`: missing namelist and error_handler-style failures give non-zero exits."""
+    from mpassit_b200 import __main__ as cli
+
+    monkeypatch.chdir(tmp_path)
+    assert cli.main([]) == 1                      # no fort.41 here (mpassit.F90:60-65)
+    assert "fort.41" in capsys.readouterr().err
+    (tmp_path / "fort.41").write_text("&config\n target_grid_type='lambert'\n nx=61\n ny=41\n dx=30000.\n dy=30000.\n"
+                                      " ref_lat=38.5\n ref_lon=-97.5\n truelat1=38.5\n truelat2=38.5\n stand_lon=-97.5\n"
+                                      " interp_diag=.false.\n interp_hist=.false.\n/\n")
+    assert cli.main([]) == 999
+    assert "INTERP_DIAG AND/OR INTERP_HIST" in capsys.readouterr().err
