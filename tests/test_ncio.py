@@ -540,3 +540,102 @@ def test_command_line_entry(host, tmp_path, monkeypatch, capsys):
                                       " interp_diag=.false.\n interp_hist=.false.\n/\n")
     assert cli.main([]) == 999
     assert "INTERP_DIAG AND/OR INTERP_HIST" in capsys.readouterr().err
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_lone_record_variable_is_not_padded(host, tmp_path, version):
+    """The classic format pads every variable to 4 bytes EXCEPT a single record variable of a 1- or 2-byte type,
+    whose records are packed (format specification, 'vsize' note): read scipy's packing, write the same."""
+    p, q = str(tmp_path / "one.nc"), str(tmp_path / "one_copy.nc")
+    a = np.arange(15, dtype=np.int16).reshape(5, 3) - 7            # 6 bytes per record
+    with netcdf_file(p, "w", version=version) as f:
+        f.createDimension("t", None)
+        f.createDimension("x", 3)
+        v = f.createVariable("s", "i2", ("t", "x"))
+        for r in range(5):
+            v[r] = a[r]
+    for r in range(5):
+        assert np.array_equal(host.nc_get(p, "s", 3, rec=r), a[r].astype(np.float64))
+    host.nc_copy(p, q, version)
+    with netcdf_file(q, "r", mmap=False) as f:
+        assert np.array_equal(f.variables["s"][:], a)
+    # with a second record variable the padding is back
+    with netcdf_file(p, "w", version=version) as f:
+        f.createDimension("t", None)
+        f.createDimension("x", 3)
+        v = f.createVariable("s", "i2", ("t", "x"))
+        u = f.createVariable("b", "i1", ("t",))
+        for r in range(5):
+            v[r] = a[r]
+            u[r] = r - 2
+    host.nc_copy(p, q, version)
+    for r in range(5):
+        assert np.array_equal(host.nc_get(p, "s", 3, rec=r), a[r].astype(np.float64)) and host.nc_get(p, "b", 1, rec=r)[0] == r - 2
+    with netcdf_file(q, "r", mmap=False) as f:
+        assert np.array_equal(f.variables["s"][:], a) and f.variables["b"][:].tolist() == [-2, -1, 0, 1, 2]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_files_round_trip(host, tmp_path, seed):
+    """Seeded random classic files (dimension counts, record / fixed variables of every classic type, odd sizes,
+    text / numeric attributes): scipy writes, the reader + writer copy, scipy reads the copy back unchanged."""
+    rng = np.random.default_rng(100 + seed)
+    p, q = str(tmp_path / "r.nc"), str(tmp_path / "r_copy.nc")
+    vs = int(rng.integers(1, 3))
+    types = ["i1", "i2", "i4", "f4", "f8", "S1"]
+    data, atts = {}, {}
+    nrec = int(rng.integers(0, 4))
+    with netcdf_file(p, "w", version=vs) as f:
+        f.createDimension("rec", None)
+        dims = {}
+        for k in range(int(rng.integers(1, 4))):
+            dims[f"d{k}"] = int(rng.integers(1, 8))
+            f.createDimension(f"d{k}", dims[f"d{k}"])
+        f.note = ("x" * int(rng.integers(1, 9))).encode()
+        f.scale = np.float64(rng.normal())
+        nvar = int(rng.integers(1, 6))
+        for k in range(nvar):
+            t = types[int(rng.integers(0, len(types)))]
+            names = list(rng.choice(list(dims), size=int(rng.integers(0, len(dims) + 1)), replace=False))
+            isrec = bool(rng.integers(0, 2))
+            if not isrec and not names:
+                names = [list(dims)[0]]  # (scipy cannot assign 0-d fixed variables)
+            shape = tuple(dims[n] for n in names)
+            v = f.createVariable(f"v{k}", t, (("rec",) if isrec else ()) + tuple(names))
+            if rng.integers(0, 2):
+                v.units = b"K"
+                v.fill = np.int32(rng.integers(-5, 5))
+            def draw(sh):
+                if t == "S1":
+                    return rng.integers(97, 123, size=sh).astype(np.uint8).view("S1").reshape(sh)
+                if t[0] == "i":
+                    return rng.integers(-100, 100, size=sh).astype(t)
+                return rng.normal(size=sh).astype(t)
+            if isrec:
+                a = draw((nrec,) + shape)
+                for r in range(nrec):
+                    v[r] = a[r]
+                if nrec == 0:
+                    a = a.reshape((0,) + shape)
+            else:
+                a = draw(shape)
+                v[:] = a
+            data[f"v{k}"] = a
+    out_version = int(rng.choice([1, 2]))
+    host.nc_copy(p, q, out_version)
+    with netcdf_file(q, "r", mmap=False) as f:
+        assert f.version_byte == out_version and f.note == getattr(netcdf_file(p, "r", mmap=False), "note")
+        for k, a in data.items():
+            got = f.variables[k][:] if f.variables[k].shape else f.variables[k].getValue()
+            assert np.array_equal(np.asarray(got).reshape(a.shape), a), k
+    host.nc_copy(p, q, 5)                                   # and through the 64-bit-data format with the reader alone
+    desc = host.nc_describe(q)
+    any_rec = any(r[0] == "var" and r[4:5] == ["rec"] for r in desc)
+    assert desc[0] == ["version", "5", "numrecs", str(nrec if any_rec else 0)]
+    for k, a in data.items():
+        if a.dtype.kind == "S" or a.size == 0:
+            continue
+        isrec = [r for r in desc if r[0] == "var" and r[1] == k][0][4:5] == ["rec"]
+        flat = a.reshape(nrec, -1) if isrec else a.reshape(1, -1)
+        for r in range(flat.shape[0]):
+            assert np.array_equal(host.nc_get(q, k, flat.shape[1], rec=r), flat[r].astype(np.float64)), k
