@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <limits>
 #include <string>
 #include <thread>
@@ -157,101 +158,101 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         std::vector<double> lat[4], lon[4], mapfac[3], cosa, sina, hgt_file;
         double cen_lat = cfg.ref_lat, cen_lon = cfg.ref_lon;
         std::string why;
-        if (from_file) {
-            // define_target_grid_file, model_grid.F90:1203-1890: sizes, projection attributes, the three staggers, map
-            // factors, rotation angles and terrain come from a WRF-style file; the corners are synthesised
-            ncio::Reader tf;
-            if (!tf.open(cfg.file_target_grid, why)) netcdf_err(std::string("opening: ") + cfg.file_target_grid, why);
-            auto tdim = [&](const char *name) -> int32_t {
-                const ncio::Dim *d = tf.dim(name);
-                if (!d) netcdf_err(std::string("reading ") + name + " id", "NetCDF: Invalid dimension ID or name");
-                return (int32_t)d->len;
-            };
-            auto gnum = [&](const char *name, double *out, bool required) {
-                const ncio::Att *a = tf.gatt(name);
-                if (!a) {
-                    if (required) netcdf_err(std::string("reading ") + name, "NetCDF: Attribute not found");
-                    return;
+        // The host-only part of define_target_grid (coordinate tables, map factors, rotation angles, or the target
+        // file) runs on its own thread beside define_input_grid; the engine calls follow once both are done.
+        auto define_target = [&]() {
+            std::string twhy;
+            char te[2048] = {0};
+            if (from_file) {
+                // define_target_grid_file, model_grid.F90:1203-1890: sizes, projection attributes, the three staggers, map
+                // factors, rotation angles and terrain come from a WRF-style file; the corners are synthesised
+                ncio::Reader tf;
+                if (!tf.open(cfg.file_target_grid, twhy)) netcdf_err(std::string("opening: ") + cfg.file_target_grid, twhy);
+                auto tdim = [&](const char *name) -> int32_t {
+                    const ncio::Dim *d = tf.dim(name);
+                    if (!d) netcdf_err(std::string("reading ") + name + " id", "NetCDF: Invalid dimension ID or name");
+                    return (int32_t)d->len;
+                };
+                auto gnum = [&](const char *name, double *out, bool required) {
+                    const ncio::Att *a = tf.gatt(name);
+                    if (!a) {
+                        if (required) netcdf_err(std::string("reading ") + name, "NetCDF: Attribute not found");
+                        return;
+                    }
+                    *out = a->number();
+                };
+                cfg.i_target = tdim("west_east");
+                cfg.j_target = tdim("south_north");
+                gnum("DX", &cfg.dx, true);
+                double pc = cfg.proj_code;
+                gnum("CEN_LAT", &cfg.ref_lat, true);
+                gnum("CEN_LON", &cfg.ref_lon, true);
+                gnum("TRUELAT1", &cfg.truelat1, true);
+                gnum("TRUELAT2", &cfg.truelat2, true);
+                gnum("MOAD_CEN_LAT", &cfg.ref_lat, true);  // overrides CEN_LAT, model_grid.F90:1273
+                gnum("STAND_LON", &cfg.stand_lon, true);
+                gnum("POLE_LAT", &cfg.pole_lat, true);
+                gnum("POLE_LON", &cfg.pole_lon, true);
+                gnum("MAP_PROJ", &pc, true);
+                cfg.proj_code = (int32_t)pc;
+                if (const ncio::Att *a = tf.gatt("MAP_PROJ_CHAR")) std::snprintf(cfg.map_proj_char, MPASSIT_NAMELEN, "%s", a->text().c_str());
+                else std::snprintf(cfg.map_proj_char, MPASSIT_NAMELEN, "%s", cfg.proj_code == 1 ? "Lambert Conformal" : "Lat/Lon");
+                cen_lat = cfg.ref_lat;
+                cen_lon = cfg.ref_lon;
+                for (int s = 0; s < 4; ++s) {
+                    mpassit_target_dims(&cfg, staggers[s], &ni[s], &nj[s]);
+                    lat[s].resize((size_t)ni[s] * nj[s]);
+                    lon[s].resize((size_t)ni[s] * nj[s]);
                 }
-                *out = a->number();
-            };
-            cfg.i_target = tdim("west_east");
-            cfg.j_target = tdim("south_north");
-            gnum("DX", &cfg.dx, true);
-            double pc = cfg.proj_code;
-            gnum("CEN_LAT", &cfg.ref_lat, true);
-            gnum("CEN_LON", &cfg.ref_lon, true);
-            gnum("TRUELAT1", &cfg.truelat1, true);
-            gnum("TRUELAT2", &cfg.truelat2, true);
-            gnum("MOAD_CEN_LAT", &cfg.ref_lat, true);  // overrides CEN_LAT, model_grid.F90:1273
-            gnum("STAND_LON", &cfg.stand_lon, true);
-            gnum("POLE_LAT", &cfg.pole_lat, true);
-            gnum("POLE_LON", &cfg.pole_lon, true);
-            gnum("MAP_PROJ", &pc, true);
-            cfg.proj_code = (int32_t)pc;
-            if (const ncio::Att *a = tf.gatt("MAP_PROJ_CHAR")) std::snprintf(cfg.map_proj_char, MPASSIT_NAMELEN, "%s", a->text().c_str());
-            else std::snprintf(cfg.map_proj_char, MPASSIT_NAMELEN, "%s", cfg.proj_code == 1 ? "Lambert Conformal" : "Lat/Lon");
-            cen_lat = cfg.ref_lat;
-            cen_lon = cfg.ref_lon;
-            for (int s = 0; s < 4; ++s) {
-                mpassit_target_dims(&cfg, staggers[s], &ni[s], &nj[s]);
-                lat[s].resize((size_t)ni[s] * nj[s]);
-                lon[s].resize((size_t)ni[s] * nj[s]);
+                auto tvar = [&](const char *name, const char *alt, size_t n, double *out) {
+                    const ncio::Var *v = tf.var(name);
+                    if (!v && alt) v = tf.var(alt);
+                    if (!v) netcdf_err(std::string("reading ") + name + " id", "NetCDF: Variable not found");
+                    if (tf.count(*v) != n) netcdf_err(std::string("reading ") + name, "NetCDF: Start+count exceeds dimension bound");
+                    if (!tf.read_doubles(*v, 0, n, out, twhy)) netcdf_err(std::string("reading ") + name, twhy);
+                };
+                tvar("XLONG", "XLONG_M", lon[0].size(), lon[0].data());
+                tvar("XLAT", "XLAT_M", lat[0].size(), lat[0].data());
+                tvar("XLONG_U", nullptr, lon[1].size(), lon[1].data());
+                tvar("XLAT_U", nullptr, lat[1].size(), lat[1].data());
+                tvar("XLONG_V", nullptr, lon[2].size(), lon[2].data());
+                tvar("XLAT_V", nullptr, lat[2].size(), lat[2].data());
+                mpassit_get_cell_corners(lat[0].data(), lon[0].data(), ni[0], nj[0], cfg.dx, lat[3].data(), lon[3].data());
+                const char *mf[3] = {"MAPFAC_M", "MAPFAC_U", "MAPFAC_V"};
+                for (int s = 0; s < 3; ++s) {
+                    mapfac[s].resize(lat[s].size());
+                    tvar(mf[s], nullptr, mapfac[s].size(), mapfac[s].data());
+                }
+                if (cfg.proj_code == MPASSIT_PROJ_LC) {
+                    sina.resize(lat[0].size());
+                    cosa.resize(lat[0].size());
+                    tvar("SINALPHA", nullptr, sina.size(), sina.data());
+                    tvar("COSALPHA", nullptr, cosa.size(), cosa.data());
+                }
+                hgt_file.resize(lat[0].size());
+                tvar("HGT", "HGT_M", hgt_file.size(), hgt_file.data());
+            } else {
+                for (int s = 0; s < 4; ++s) {
+                    mpassit_target_dims(&cfg, staggers[s], &ni[s], &nj[s]);
+                    lat[s].resize((size_t)ni[s] * nj[s]);
+                    lon[s].resize((size_t)ni[s] * nj[s]);
+                    const int trc = mpassit_target_coords(&cfg, staggers[s], lat[s].data(), lon[s].data(), te, sizeof te);
+                    if (trc) die(trc, te);
+                }
+                for (int s = 0; s < 3; ++s) {  // get_map_factor on the M / U / V latitudes, model_grid.F90:1022-1036
+                    mapfac[s].resize(lat[s].size());
+                    mpassit_get_map_factor(&cfg, lat[s].data(), (int64_t)lat[s].size(), mapfac[s].data());
+                }
+                // model_grid.F90:1113: ref_lat / ref_lon become the grid-centre coordinates (they end up in CEN_LAT / CEN_LON)
+                mpassit_xytoll(&cfg, cfg.i_target / 2.0, cfg.j_target / 2.0, MPASSIT_M, &cen_lat, &cen_lon);
+                if (cfg.proj_code == MPASSIT_PROJ_LC) {  // model_grid.F90:1114-1185
+                    cosa.resize(lat[0].size());
+                    sina.resize(lat[0].size());
+                    mpassit_get_rotang(lat[0].data(), lon[0].data(), cfg.i_target, cfg.j_target, cosa.data(), sina.data());
+                }
             }
-            auto tvar = [&](const char *name, const char *alt, size_t n, double *out) {
-                const ncio::Var *v = tf.var(name);
-                if (!v && alt) v = tf.var(alt);
-                if (!v) netcdf_err(std::string("reading ") + name + " id", "NetCDF: Variable not found");
-                if (tf.count(*v) != n) netcdf_err(std::string("reading ") + name, "NetCDF: Start+count exceeds dimension bound");
-                if (!tf.read_doubles(*v, 0, n, out, why)) netcdf_err(std::string("reading ") + name, why);
-            };
-            tvar("XLONG", "XLONG_M", lon[0].size(), lon[0].data());
-            tvar("XLAT", "XLAT_M", lat[0].size(), lat[0].data());
-            tvar("XLONG_U", nullptr, lon[1].size(), lon[1].data());
-            tvar("XLAT_U", nullptr, lat[1].size(), lat[1].data());
-            tvar("XLONG_V", nullptr, lon[2].size(), lon[2].data());
-            tvar("XLAT_V", nullptr, lat[2].size(), lat[2].data());
-            mpassit_get_cell_corners(lat[0].data(), lon[0].data(), ni[0], nj[0], cfg.dx, lat[3].data(), lon[3].data());
-            const char *mf[3] = {"MAPFAC_M", "MAPFAC_U", "MAPFAC_V"};
-            for (int s = 0; s < 3; ++s) {
-                mapfac[s].resize(lat[s].size());
-                tvar(mf[s], nullptr, mapfac[s].size(), mapfac[s].data());
-            }
-            if (cfg.proj_code == MPASSIT_PROJ_LC) {
-                sina.resize(lat[0].size());
-                cosa.resize(lat[0].size());
-                tvar("SINALPHA", nullptr, sina.size(), sina.data());
-                tvar("COSALPHA", nullptr, cosa.size(), cosa.data());
-            }
-            hgt_file.resize(lat[0].size());
-            tvar("HGT", "HGT_M", hgt_file.size(), hgt_file.data());
-            if (!dry)
-                for (int s = 0; s < 4; ++s)
-                    ck(ctx, mprg_set_target(ctx, staggers[s], ni[s], nj[s], lon[s].data(), lat[s].data()), "GridAddCoord");
-        } else {
-            for (int s = 0; s < 4; ++s) {
-                mpassit_target_dims(&cfg, staggers[s], &ni[s], &nj[s]);
-                lat[s].resize((size_t)ni[s] * nj[s]);
-                lon[s].resize((size_t)ni[s] * nj[s]);
-                rc = mpassit_target_coords(&cfg, staggers[s], lat[s].data(), lon[s].data(), e, sizeof e);
-                if (rc) die(rc, e);
-                if (!dry) ck(ctx, mprg_set_target(ctx, staggers[s], ni[s], nj[s], lon[s].data(), lat[s].data()), "GridAddCoord");
-            }
-            for (int s = 0; s < 3; ++s) {  // get_map_factor on the M / U / V latitudes, model_grid.F90:1022-1036
-                mapfac[s].resize(lat[s].size());
-                mpassit_get_map_factor(&cfg, lat[s].data(), (int64_t)lat[s].size(), mapfac[s].data());
-            }
-            // model_grid.F90:1113: ref_lat / ref_lon become the grid-centre coordinates (they end up in CEN_LAT / CEN_LON)
-            mpassit_xytoll(&cfg, cfg.i_target / 2.0, cfg.j_target / 2.0, MPASSIT_M, &cen_lat, &cen_lon);
-            if (cfg.proj_code == MPASSIT_PROJ_LC) {  // model_grid.F90:1114-1185
-                cosa.resize(lat[0].size());
-                sina.resize(lat[0].size());
-                mpassit_get_rotang(lat[0].data(), lon[0].data(), cfg.i_target, cfg.j_target, cosa.data(), sina.data());
-            }
-        }
-        const int32_t it = cfg.i_target, jt = cfg.j_target;
-        const bool lc = cfg.proj_code == MPASSIT_PROJ_LC;
-        if (lc && !dry) ck(ctx, mprg_set_rotation(ctx, cosa.data(), sina.data()), "get_rotang");
+        };
+        std::future<void> target_job = std::async(std::launch::async, define_target);
         st.target_ms = now_ms() - tq;
         tq = now_ms();
 
@@ -294,6 +295,15 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
                                   lonVert.data(), latVert.data(), voc.data()), "MeshCreate");
         st.mesh_ms = now_ms() - tq;
         st.n_cells = nCells;
+        tq = now_ms();
+        target_job.get();  // rethrows what define_target threw
+        if (!dry)
+            for (int s = 0; s < 4; ++s)
+                ck(ctx, mprg_set_target(ctx, staggers[s], ni[s], nj[s], lon[s].data(), lat[s].data()), "GridAddCoord");
+        const int32_t it = cfg.i_target, jt = cfg.j_target;
+        const bool lc = cfg.proj_code == MPASSIT_PROJ_LC;
+        if (lc && !dry) ck(ctx, mprg_set_rotation(ctx, cosa.data(), sina.data()), "get_rotang");
+        st.target_ms += now_ms() - tq;  // what the main thread still waited for, plus the uploads
         st.setup_ms = now_ms() - t0;
 
         // ------------------------------------------------------------------ read_input_data, input_data.F90:97-812
