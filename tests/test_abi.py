@@ -79,3 +79,21 @@ def test_fortran_module_binds_every_reference_facing_entry():
         hv = re.search(name + r"\s*=\s*(\d+)", hdr)
         fv = re.search(name + r"\s*=\s*(\d+)", txt)
         assert hv and fv and hv.group(1) == fv.group(1), name
+
+
+def test_host_header_symbols_exported(engine_lib):
+    """libmpassit_host.so (the C++ mirror of the Fortran host stages) exports every function include/mpassit_host.h
+    declares, and the Python binding gives each of them an argument list."""
+    from mpassit_b200 import build, host
+
+    build.build_host()
+    txt = open(os.path.join(ROOT, "include", "mpassit_host.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"typedef[^;]*\(\*\w+\)[^;]*;", "", txt)          # function-pointer typedefs are not exports
+    names = sorted(set(re.findall(r"\b(mpassit_[a-z0-9_]+)\s*\(", txt)))
+    assert len(names) >= 20, names
+    L = host.load()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    unbound = [n for n in names if getattr(L, n).argtypes is None]
+    assert not unbound, unbound
