@@ -144,6 +144,18 @@ size_t type_size(int t) {
 }
 
 void to_big_endian(void *p, size_t elem, size_t n) {
+    if (elem == 4 || elem == 8) {  // the coordinate tables of a 3-km target are 10^7 words: word swaps, a few threads
+        par::range((int64_t)n, 1 << 16, [&](int64_t b, int64_t e) {
+            if (elem == 4) {
+                uint32_t *q = (uint32_t *)p;
+                for (int64_t i = b; i < e; ++i) q[i] = __builtin_bswap32(q[i]);
+            } else {
+                uint64_t *q = (uint64_t *)p;
+                for (int64_t i = b; i < e; ++i) q[i] = __builtin_bswap64(q[i]);
+            }
+        });
+        return;
+    }
     uint8_t *b = (uint8_t *)p;
     for (size_t i = 0; i < n; ++i, b += elem)
         for (size_t k = 0; k < elem / 2; ++k) std::swap(b[k], b[elem - 1 - k]);
@@ -566,7 +578,9 @@ bool Writer::put_doubles(int varid, const double *v, uint64_t n, std::string &er
     const Var &var = vars_[varid];
     if (var.type == NC_FLOAT) {
         std::vector<float> f(n);
-        for (uint64_t i = 0; i < n; ++i) f[i] = (float)v[i];
+        par::range((int64_t)n, 1 << 16, [&](int64_t b, int64_t e) {
+            for (int64_t i = b; i < e; ++i) f[i] = (float)v[i];
+        });
         to_big_endian(f.data(), 4, n);
         return write_raw(varid, 0, 0, f.data(), n * 4, err);
     }
