@@ -195,14 +195,14 @@ def measure_file_run(local_rank: int) -> dict:
     """`mpassit <namelist>` with NetCDF-classic files on both sides (host/run.cpp) on the 12-km
     miniature of the workload (0.6 GB in, 0.6 GB out): reported beside the metric, not part of it.  The 3-km case at
     full size (10 GB each way) is profiles/file_bench.py c2."""
-    try:
-        import shutil
-        import tempfile
+    import shutil
+    import tempfile
 
+    fdir = tempfile.mkdtemp(prefix="mpassit_bench_files_")
+    try:
         from mpassit_b200 import host, mpas_files, workload
 
         host.load()
-        fdir = tempfile.mkdtemp(prefix="mpassit_bench_files_")
         fwl = workload.make("mid", rundir=fdir)
         FF = workload.make_fields(fwl, device=f"cuda:{local_rank}")["dev"]
         fsrc = {g: [(s.name, s.src.cpu().numpy()) for s in FF[g]] for g in ("diag", "hist_2d", "hist_3d", "soil")}
@@ -216,10 +216,11 @@ def measure_file_run(local_rank: int) -> dict:
                "bytes_in": st.bytes_in, "bytes_out": st.bytes_out, "value": fwl.units_per_pass() / (st.total_ms * 1e-3),
                "unit": UNIT, "stat": "best of 3 after one warm-up run", "output": f"CDF-{st.output_version}",
                "note": "files in the page cache; big-endian sources swapped in HBM; each rank pwrites its slab"}
-        shutil.rmtree(fdir, ignore_errors=True)
         return out
     except Exception as ex:  # the metric does not depend on it
         return {"error": f"{type(ex).__name__}: {ex}"}
+    finally:
+        shutil.rmtree(fdir, ignore_errors=True)
 
 
 def main():
