@@ -494,6 +494,14 @@ def test_target_grid_from_a_wrf_style_file(host, tmp_path):
     assert (clat[:-1, :-1] < lat).all() and (clon[:-1, :-1] > lon).all()
     d = 6370000.0 * np.hypot(np.deg2rad(clat[:-1, :-1] - lat), np.deg2rad(clon[:-1, :-1] - lon) * np.cos(np.deg2rad(lat)))
     assert np.abs(d / np.sqrt(30000.0 ** 2 / 2) - 1).max() < 1e-3
+    # ... so the quad ESMF builds from corners (i,j), (i+1,j), (i+1,j+1), (i,j+1) is centred on mass point (i+1, j):
+    # in this mode the reference's conservative cells are shifted one column east
+    qlat = 0.25 * (clat[:-2, :-2] + clat[:-2, 1:-1] + clat[1:-1, 1:-1] + clat[1:-1, :-2])
+    qlon = 0.25 * (clon[:-2, :-2] + clon[:-2, 1:-1] + clon[1:-1, 1:-1] + clon[1:-1, :-2])
+    def km(la1, lo1, la2, lo2):
+        return 6370.0 * np.hypot(np.deg2rad(la1 - la2), np.deg2rad(lo1 - lo2) * np.cos(np.deg2rad(la2)))
+    assert km(qlat, qlon, lat[:-1, 1:], lon[:-1, 1:]).max() < 0.15 * 30.0     # (true bearings on a rotated Lambert grid)
+    assert km(qlat, qlon, lat[:-1, :-1], lon[:-1, :-1]).min() > 0.8 * 30.0     # a whole cell away from its own centre
     # a target file without the staggered coordinates is refused like netcdf_err does
     from scipy.io import netcdf_file as ncf
     bad = str(tmp_path / "bad_target.nc")
