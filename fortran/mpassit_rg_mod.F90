@@ -24,13 +24,14 @@ module mpassit_rg_mod
   integer(c_int), parameter, public :: MPRG_SRC_MESH_ELEMENT = 0, MPRG_SRC_MESH_NODE = 1, MPRG_SRC_GRID_CENTER = 2
   integer(c_int), parameter, public :: MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3, &
                                         MPRG_CENTER_HALO = 4
+  integer(c_int), parameter, public :: MPRG_GRID_NOPERI = 0, MPRG_GRID_1PERI_MONOPOLE = 1
   integer(c_int), parameter, public :: MPRG_F32 = 0, MPRG_F64 = 1
   integer(c_int), parameter, public :: MPRG_HOST = 0, MPRG_DEVICE = 1
   integer(c_int), parameter, public :: MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2, &
                                         MPRG_EPI_ROT_U = 3, MPRG_EPI_ROT_V = 4
 
   public :: mprg_init, mprg_finalize, mprg_last_error, mprg_error_message
-  public :: mprg_set_mesh, mprg_set_target, mprg_get_slab
+  public :: mprg_set_mesh, mprg_set_target, mprg_set_grid_kind, mprg_set_option, mprg_get_slab
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
   public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
@@ -100,6 +101,20 @@ module mpassit_rg_mod
        integer(c_int), value :: stagger
        integer(c_int32_t), value :: ni, nj
        real(c_double), intent(in) :: lon_deg(*), lat_deg(*)
+     end function
+     !> replaces the choice between ESMF_GridCreate1PeriDim (polekindflag=MONOPOLE, periodicDim=1) and
+     !! ESMF_GridCreateNoPeriDim (model_grid.F90:684-703): kind = MPRG_GRID_1PERI_MONOPOLE when .not. is_regional
+     integer(c_int) function mprg_set_grid_kind(ctx, kind) bind(C, name="mprg_set_grid_kind")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: kind
+     end function
+     !> tuning knob (include/mpassit_rg.h); key and value are NUL-terminated C strings,
+     !! e.g. mprg_set_option(ctx, "accumulate"//c_null_char, "f64"//c_null_char) for the reference's R8 arithmetic
+     integer(c_int) function mprg_set_option(ctx, key, val) bind(C, name="mprg_set_option")
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(in) :: key(*), val(*)
      end function
      !> rows [j0, j1) (0-based) of a stagger owned by this rank == ESMF_GridGet bounds (clb/cub)
      integer(c_int) function mprg_get_slab(ctx, stagger, j0, j1) bind(C, name="mprg_get_slab")
@@ -345,7 +360,7 @@ contains
     character(len=:), allocatable :: msg
     character(kind=c_char), pointer :: p(:)
     type(c_ptr) :: cp
-    integer :: n
+    integer :: n, k
     cp = mprg_last_error(ctx)
     msg = ""
     if (.not. c_associated(cp)) return
@@ -355,8 +370,11 @@ contains
        if (p(n + 1) == c_null_char) exit
        n = n + 1
     end do
-    allocate (character(len=n) :: msg)
-    if (n > 0) msg = transfer(p(1:n), msg)
+    ! msg is already allocated (zero length) by the assignment above: re-assign, never ALLOCATE it again
+    msg = repeat(" ", n)
+    do k = 1, n
+       msg(k:k) = p(k)
+    end do
   end function mprg_error_message
 
 end module mpassit_rg_mod

@@ -75,6 +75,20 @@ int mprg_synchronize(mprg_ctx *ctx);
  * buffers of queued applies until mprg_synchronize returns.  Environment MPASSIT_GPU_ASYNC=1 sets the
  * initial mode. */
 int mprg_set_async(mprg_ctx *ctx, int on);
+/* Tuning knobs (never needed for correctness).  Each has an environment variable that is read ONCE, by mprg_init;
+ * mprg_set_option changes it afterwards.  key / values [environment variable]:
+ *   "accumulate"  "f32" (default) | "f64": arithmetic of fp32-in / fp32-out applies and of the wind rotation; f64 is
+ *                 the reference's R8 arithmetic (one rounding on store)                          [MPASSIT_GPU_ACC]
+ *   "staging"     "auto" (default: by the route's tile schedule) | "bulk" | "ldg": how the column kernel brings
+ *                 source columns into shared memory -- one TMA bulk copy per run of consecutively numbered cells,
+ *                 or per-thread cp.async for meshes whose numbering has no locality          [MPASSIT_GPU_STAGING]
+ *   "ldg_below"   auto staging picks ldg when (distinct columns / runs) of the route is below this (2.5)
+ *   "apply"       "pipe" (default) | "direct": register-gather kernels only                    [MPASSIT_GPU_APPLY]
+ *   "pipe_minb"   0 (default: by shared memory) | 4 | 5 resident CTAs per SM               [MPASSIT_GPU_PIPE_MINB]
+ *   "cols_minb"   2 | 3 (default) | 4: register cap of the register-gather kernel               [MPASSIT_GPU_MINB]
+ *   "upload_threads"  host threads of the unpinned-source bounce ring (0 = 3/4 of the cores) [MPASSIT_UPLOAD_THREADS] */
+int mprg_set_option(mprg_ctx *ctx, const char *key, const char *value);
+int mprg_get_option(const mprg_ctx *ctx, const char *key, char *value, size_t len);
 int mprg_get_async(const mprg_ctx *ctx);
 /* device -> host copy ordered after everything queued on the context so far (blocking unless async) */
 int mprg_download(mprg_ctx *ctx, const void *dev, void *host, size_t bytes);
@@ -107,6 +121,17 @@ int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxE
  *      CORNER (ni+1) x (nj+1)  (interp.F90:477-520). */
 int mprg_set_target(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj,
                     const double *lon_deg, const double *lat_deg);
+/* Topology of the target grid: which ESMF_GridCreate* call the reference makes, model_grid.F90:684-703.
+ *   MPRG_GRID_NOPERI         ESMF_GridCreateNoPeriDim (is_regional = .true., the default here);
+ *   MPRG_GRID_1PERI_MONOPOLE ESMF_GridCreate1PeriDim(periodicDim=1, poleDim=2, polekindflag=MONOPOLE)
+ *                            (is_regional = .false.): the grid wraps in i and is closed at both poles.
+ * It only matters where the grid itself is a regrid SOURCE -- the centre -> EDGE1 / EDGE2 staggering of the
+ * winds (interp.F90:298,316): with a periodic grid the quad between the last and the first centre column
+ * exists (U on the seam columns is interpolated across the seam), and the polar caps (ESMF's default
+ * polemethod ALLAVG: an artificial pole node whose value is the average of the end row) map V on the pole
+ * rows.  Set it before the first mprg_store; changing it drops the memoised grid-source routes. */
+enum { MPRG_GRID_NOPERI = 0, MPRG_GRID_1PERI_MONOPOLE = 1 };
+int mprg_set_grid_kind(mprg_ctx *ctx, int kind);
 /* rows [j0, j1) of `stagger` owned by this rank (0-based; para_range) */
 int mprg_get_slab(const mprg_ctx *ctx, int stagger, int32_t *j0, int32_t *j1);
 

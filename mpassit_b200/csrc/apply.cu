@@ -378,20 +378,12 @@ k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
 // ---------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------
-static int tune_minb() {  // resident CTAs/SM the vector kernel is compiled for (register cap)
-    const char *e = getenv("MPASSIT_GPU_MINB");
-    return e ? atoi(e) : 3;
-}
-
 // Accumulation type for fp32-in / fp32-out fields.  Default fp32: every weight set on this path is a
 // convex combination (bilinear, conservative) or a single 1.0 (nearest), so fp32 FMA accumulation
 // stays within ~2e-7 of the fp64 result -- 50x inside the 1e-5 contract -- and nearest-neighbour
-// output remains bit-exact (1.0f * x).  MPASSIT_GPU_ACC=f64 restores the reference's R8 arithmetic
-// (one rounding on store) at ~25 % lower throughput.
-static bool acc_fp32_requested() {
-    const char *e = getenv("MPASSIT_GPU_ACC");
-    return !(e && (!strcmp(e, "f64") || !strcmp(e, "fp64")));
-}
+// output remains bit-exact (1.0f * x).  mprg_set_option("accumulate", "f64") / MPASSIT_GPU_ACC=f64 restores
+// the reference's R8 arithmetic (one rounding on store).
+static bool acc_fp32_requested(const mprg_ctx *ctx) { return !ctx->tune.acc64; }
 
 // ---- per-launch profiling (bench.py's live roofline measurement) ---------------
 static cudaEvent_t prof_event(mprg_ctx *ctx) {
@@ -410,11 +402,16 @@ struct ProfScope {
     mprg_ctx *ctx;
     bool on;
     mprg_ctx::ProfRec rec;
-    ProfScope(mprg_ctx *c, int kind, double bytes, double units) : ctx(c), on(c->profile) {
+    ProfScope(mprg_ctx *c, int kind, double bytes, double units) : ctx(c), on(c->profile && !c->capturing) {
         if (!on) return;
         rec.kind = kind; rec.algBytes = bytes; rec.units = units;
         rec.a = prof_event(c); rec.b = prof_event(c);
         cudaEventRecord(rec.a, c->stream);
+    }
+    void cancel() {
+        if (!on) return;
+        on = false;
+        ctx->evPool.push_back(rec.a); ctx->evPool.push_back(rec.b);
     }
     ~ProfScope() {
         if (!on) return;
@@ -424,11 +421,6 @@ struct ProfScope {
 };
 
 // ---- pipelined column kernel (apply_pipe.cuh) -------------------------------------
-static bool pipe_disabled() {
-    const char *e = getenv("MPASSIT_GPU_APPLY");
-    return e && !strcmp(e, "direct");
-}
-
 template <typename KERN, typename TACC>
 static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes,
                           unsigned tiles) {
@@ -437,51 +429,29 @@ static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, co
     ctx->launches++;
 }
 
-template <typename TIN, typename TOUT, typename TACC, int STAGES>
-static void launch_pipe_s(mprg_ctx *ctx, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes, unsigned tiles,
-                          bool allvec, int minb, bool rot) {
-    if (rot) {  // fused wind rotation: 2 stages, 64 registers (it holds the zonal results and the angles)
-        if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, true, 4, true>, pa, up, smemBytes, tiles);
-        else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, 2, false, 4, true>, pa, up, smemBytes, tiles);
-        return;
-    }
-    if (allvec && minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 5>, pa, up, smemBytes, tiles);
-    else if (allvec) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, true, 4>, pa, up, smemBytes, tiles);
-    else if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 5>, pa, up, smemBytes, tiles);
-    else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, STAGES, false, 4>, pa, up, smemBytes, tiles);
+// staging mode of a route: BULK (one TMA bulk copy per run of consecutively numbered columns) when its tiles'
+// columns form long runs, LDG (per-thread cp.async) when they do not
+static bool route_uses_ldg(const mprg_ctx *ctx, const mprg_route *r) {
+    if (ctx->tune.staging >= 0) return ctx->tune.staging == 1;
+    return r->schedRuns > 0 && (double)r->schedCols < ctx->tune.ldgBelow * (double)r->schedRuns;
 }
 
-// returns false if this route / field set does not fit the pipelined kernel
-// fields flagged MPRG_EPI_ROT_U / ROT_V are wind pairs whose rotation is fused into the store
+// Every 3-D field of an apply in ONE launch of the pipelined kernel (kPipeMaxUnits units per launch).
+// Fields flagged MPRG_EPI_ROT_U / ROT_V are wind pairs whose rotation is fused into the store.
+// Returns false if this route / field set does not fit the kernel (the register-gather kernel takes over).
 template <typename TIN, typename TOUT, typename TACC>
 static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields, DstLayout dl) {
-    if (pipe_disabled() || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
-    const int slotBytes = pipe_slot_bytes<TIN>();
-    const size_t stage = (size_t)r->tileUniqMax * slotBytes;
-    const size_t fixed = pipe_fixed_bytes<TACC>();
-    // Measured on B200 (profiles/r01): resident CTAs per SM matter more than pipeline depth (2 stages x
-    // 4 CTAs beats 3 x 3 and 4 x 2 by 10-40 %), so take the shallowest pipeline that fits.
-    const size_t smMax = 227 * 1024;
-    int stages = 0;
-    for (int s : {2}) {
-        const size_t need = fixed + (size_t)s * stage + 1024;
-        if (need <= smMax) { stages = s; break; }
-    }
-    if (const char *e = getenv("MPASSIT_GPU_STAGES")) {
-        const int s = atoi(e);
-        if (s >= 2 && s <= 4 && fixed + (size_t)s * stage + 1024 <= smMax) stages = s;
-    }
-    if (!stages) return false;
-    // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
-    int minb = (fixed + (size_t)stages * stage + 1024) * 5 <= smMax ? 5 : 4;
-    if (const char *e = getenv("MPASSIT_GPU_PIPE_MINB")) minb = atoi(e) >= 5 ? 5 : 4;
+    if (ctx->tune.pipeOff || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
+    const bool ldg = route_uses_ldg(ctx, r);
     std::vector<UnitDev> units;
     auto unit_of = [&](const FieldDev &f, int L0) {
         UnitDev u;
         u.src = f.src; u.dst = f.dst; u.srcBytes = (size_t)r->nSrc * f.nlev * sizeof(TIN);
         u.nlev = f.nlev; u.L0 = L0; u.Ln = std::min(kPipeLev, f.nlev - L0);
-        const bool aligned = ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0;
-        u.epi_op = (f.epi_op & 0xff) | (aligned ? kUnitAligned : 0);
+        // aligned: every column chunk starts on a 16-byte boundary and is a multiple of 16 bytes long
+        const bool aligned = ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0 &&
+                             ((size_t)L0 * sizeof(TIN)) % 16 == 0 && ((size_t)u.Ln * sizeof(TIN)) % 16 == 0;
+        u.flags = (f.epi_op & 0xff) | (aligned ? kUnitAligned : 0) | (u.Ln == f.nlev ? kUnitMerged : 0);
         u.epi_arg = f.epi_arg;
         return u;
     };
@@ -492,8 +462,8 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             rot = true;
             for (int L0 = 0; L0 < fields[f].nlev; L0 += kPipeLev) {
                 UnitDev uu = unit_of(fields[f], L0), uv = unit_of(fields[f + 1], L0);
-                uu.epi_op = (uu.epi_op & kUnitAligned) | kUnitRotU;
-                uv.epi_op = (uv.epi_op & kUnitAligned) | kUnitRotV;
+                uu.flags = (uu.flags & ~0xff) | kUnitRotU;
+                uv.flags = (uv.flags & ~0xff) | kUnitRotV;
                 units.push_back(uu);
                 units.push_back(uv);
             }
@@ -502,34 +472,49 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             for (int L0 = 0; L0 < fields[f].nlev; L0 += kPipeLev) units.push_back(unit_of(fields[f], L0));
         }
     }
+    // one stage holds the largest unit of the launch at the route's tile maxima
+    size_t stage = 0;
+    for (const UnitDev &u : units)
+        stage = std::max(stage, pipe_unit_stage_bytes(ldg, (u.flags & kUnitAligned) != 0, (u.flags & kUnitMerged) != 0,
+                                                      (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
+    stage = (stage + 15) & ~(size_t)15;
+    const size_t fixed = pipe_fixed_bytes<TACC>();
+    const size_t hold = rot ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
+    const size_t smemBytes = fixed + kPipeStages * stage + hold;
+    if (smemBytes + 1024 > (size_t)227 * 1024) return false;
+    // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
+    int minb = (smemBytes + 1024) * 5 <= (size_t)228 * 1024 ? 5 : 4;
+    if (ctx->tune.pipeMinb) minb = ctx->tune.pipeMinb >= 5 ? 5 : 4;
     PipeArgs<TACC> pa;
     pa.rowptr = r->rowptr.p; pa.col = r->col.p;
     if (sizeof(TACC) == 8) pa.w = (const TACC *)r->w.p; else pa.w = (const TACC *)r->w32.p;
-    pa.tileUPtr = r->tileUPtr.p; pa.tileUCols = r->tileUCols.p; pa.entrySlot = r->entrySlot.p;
+    pa.tileUPtr = r->tileUPtr.p; pa.tileUCols = r->tileUCols.p; pa.tileURun = r->tileURun.p; pa.entrySlot = r->entrySlot.p;
     pa.nDst = r->nDst;
     pa.dstLev = dl.lev; pa.dstOff = dl.off;
-    pa.maxU = r->tileUniqMax;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
+    pa.stageBytes = (int32_t)stage;
+    pa.holdOff = (int32_t)(fixed + kPipeStages * stage);
     pa.rotc = nullptr;
-    if (rot)  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
-        pa.rotc = ctx->rotc.p + 4 * ctx->target[r->dst_stagger].slabOffset();
+    if (rot) {  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
+        using TR = typename RotMath<TOUT, TACC>::type;
+        const int64_t off = 4 * ctx->target[r->dst_stagger].slabOffset();
+        pa.rotc = sizeof(TR) == 4 ? (const void *)(ctx->rotc32.p + off) : (const void *)(ctx->rotc.p + off);
+    }
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
-    const size_t smemBytes = fixed + (size_t)stages * stage;
     for (size_t u0 = 0; u0 < units.size();) {
         size_t nu = std::min<size_t>(kPipeMaxUnits, units.size() - u0);
-        if (u0 + nu < units.size() && (units[u0 + nu - 1].epi_op & kUnitRotU)) --nu;  // keep a wind pair in one launch
+        if (u0 + nu < units.size() && (units[u0 + nu - 1].flags & kUnitRotU)) --nu;  // keep a wind pair in one launch
         UnitPack up;
         memcpy(up.u, units.data() + u0, nu * sizeof(UnitDev));
         pa.nunits = (int)nu;
-        bool allvec = getenv("MPASSIT_GPU_FORCE_MIXED") == nullptr, anyrot = false;
-        for (size_t k = 0; k < nu; ++k) {
-            allvec = allvec && (units[u0 + k].epi_op & kUnitAligned);
-            anyrot = anyrot || (units[u0 + k].epi_op & (kUnitRotU | kUnitRotV));
+        if (ldg) {
+            if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, true, 5>, pa, up, smemBytes, tiles);
+            else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, true, 4>, pa, up, smemBytes, tiles);
+        } else {
+            if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, false, 5>, pa, up, smemBytes, tiles);
+            else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, false, 4>, pa, up, smemBytes, tiles);
         }
-        if (stages == 4 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 4>(ctx, pa, up, smemBytes, tiles, allvec, minb, false);
-        else if (stages == 3 && !anyrot) launch_pipe_s<TIN, TOUT, TACC, 3>(ctx, pa, up, smemBytes, tiles, allvec, minb, false);
-        else launch_pipe_s<TIN, TOUT, TACC, 2>(ctx, pa, up, fixed + 2 * stage, tiles, allvec, minb, anyrot);
         u0 += nu;
     }
     MPRG_CUDA(cudaGetLastError());
@@ -540,70 +525,62 @@ void scan_counts(mprg_ctx *ctx, const int32_t *cnt, int32_t *rowptr, int64_t nPl
 
 // builds the route's tile schedule (the "communication schedule" half of an ESMF route handle)
 void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
-    r->tileEntriesMax = r->tileUniqMax = 0;
+    r->tileEntriesMax = r->tileUniqMax = r->tileRunsMax = 0;
     if (r->nDst <= 0 || r->nnz <= 0) return;
     if (r->dstNi <= 0) r->dstNi = (int32_t)std::min<int64_t>(r->nDst, 0x7fffffff);
     const int tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * tilesPerRow);
-    DevBuf<int32_t> mm(2), cnt(tiles + 1);
-    MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    DevBuf<int32_t> mm(3), cnt(tiles + 1);
+    MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 3 * sizeof(int32_t), ctx->stream));
     MPRG_CUDA(cudaMemsetAsync(cnt.p, 0, (tiles + 1) * sizeof(int32_t), ctx->stream));
     k_tile_schedule<false><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
-                                                                   mm.p, mm.p + 1, cnt.p, nullptr, nullptr, nullptr, nullptr);
+                                                                   mm.p, mm.p + 1, mm.p + 2, cnt.p, nullptr, nullptr, nullptr,
+                                                                   nullptr, nullptr);
     ctx->launches++;
-    int32_t h[2] = {0, 0};
+    int32_t h[3] = {0, 0, 0};
     peek(ctx, h, mm.p, sizeof h);
     r->tileEntriesMax = h[0];
     r->tileUniqMax = h[1];
+    r->tileRunsMax = h[2];
     if (h[0] > kPipeCap) return;  // no schedule: register-gather kernels only
     r->tileUPtr.alloc(tiles + 1);
     scan_counts(ctx, cnt.p, r->tileUPtr.p, (int64_t)tiles + 1);
     int32_t total = 0;
     peek(ctx, &total, r->tileUPtr.p + tiles, sizeof(int32_t));
     r->tileUCols.alloc(total > 0 ? total : 1);
+    r->tileURun.alloc(total > 0 ? total : 1);
     r->entrySlot.alloc(r->nnz);
     DevBuf<unsigned long long> runs(1);
     MPRG_CUDA(cudaMemsetAsync(runs.p, 0, sizeof(unsigned long long), ctx->stream));
     k_tile_schedule<true><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
-                                                                  nullptr, nullptr, nullptr, r->tileUPtr.p, r->tileUCols.p,
-                                                                  r->entrySlot.p, runs.p);
+                                                                  nullptr, nullptr, nullptr, nullptr, r->tileUPtr.p,
+                                                                  r->tileUCols.p, r->tileURun.p, r->entrySlot.p, runs.p);
     ctx->launches++;
     unsigned long long hruns = 0;
     peek(ctx, &hruns, runs.p, sizeof hruns);
     r->schedTiles = tiles; r->schedCols = total; r->schedRuns = (int64_t)hruns;
 }
 
-// returns false when wind pairs (fused rotation) are present but the pipelined kernel could not take them
+// cols: every 3-D field of the apply (wind pairs adjacent, ROT_U then ROT_V); flat: 2-D fields and short columns;
+// planes: grid-source fields.  Returns false when wind pairs (fused rotation) are present but the pipelined
+// kernel could not take the route.
 template <typename TIN, typename TOUT, typename TACC>
-static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols_vec,
-                       const std::vector<FieldDev> &cols_sca, const std::vector<FieldDev> &flat,
-                       const std::vector<FieldDev> &planes, const std::vector<FieldDev> &rotp, DstLayout dl) {
-    bool rot_ok = true;
+static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &cols,
+                       const std::vector<FieldDev> &flat, const std::vector<FieldDev> &planes, DstLayout dl) {
     auto has_rot = [](const std::vector<FieldDev> &v) {
         for (auto &f : v) if (f.epi_op == MPRG_EPI_ROT_U) return true;
         return false;
     };
-    // Wind pairs stay out of the main stacked launch: the rotating variant costs registers (4 CTAs/SM
-    // instead of 5), which the other fields should not pay.  They share a launch with the fields whose
-    // columns are not 16-byte aligned (the per-unit "mixed" variant) when there are any, so the per-tile
-    // prologue is spread over more units.
-    bool sca_done = false;
-    if (!rotp.empty() && r->nDst > 0) {
-        std::vector<FieldDev> grp = rotp;
-        grp.insert(grp.end(), cols_sca.begin(), cols_sca.end());
-        double k = 0;
-        bool vec = true;
-        for (auto &f : grp) { k += f.nlev; vec = vec && ((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0; }
-        ProfScope ps(ctx, vec ? 0 : 1, alg_bytes(r, k, sizeof(TIN), sizeof(TOUT), sizeof(TACC)), k * r->nDst);
-        rot_ok = launch_pipe<TIN, TOUT, TACC>(ctx, r, grp, dl);
-        if (!rot_ok) {
-            if (ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
-            return false;
-        }
-        sca_done = true;
+    const size_t total = cols.size() + flat.size() + planes.size();
+    if (total == 0 || r->nDst == 0) return true;
+    auto ksum = [](const std::vector<FieldDev> &v) { double k = 0; for (auto &f : v) k += f.nlev; return k; };
+    bool piped = false;
+    if (!cols.empty()) {
+        ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols) * r->nDst);
+        piped = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols, dl);
+        if (!piped) ps.cancel();
+        if (!piped && has_rot(cols)) return false;
     }
-    const size_t total = cols_vec.size() + cols_sca.size() + flat.size() + planes.size();
-    if (total == 0 || r->nDst == 0) return rot_ok;
     ApplyArgs<TACC> a;
     a.rowptr = r->rowptr.p;
     a.col = r->col.p;
@@ -612,7 +589,6 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     a.dstLev = dl.lev; a.dstOff = dl.off;
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
-    auto ksum = [](const std::vector<FieldDev> &v) { double k = 0; for (auto &f : v) k += f.nlev; return k; };
     // field-descriptor kernels take their fields kPackFields at a time, as a kernel parameter
     auto packs = [&](const std::vector<FieldDev> &v, auto &&launch) {
         for (size_t f0 = 0; f0 < v.size(); f0 += kPackFields) {
@@ -624,38 +600,20 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
             ctx->launches++;
         }
     };
-    // every 3-D field of the apply goes through the pipelined kernel; the register-gather kernels below
-    // are the fallback for routes whose tiles exceed its caps
-    bool piped_vec = false, piped_sca = false;
-    if (!cols_vec.empty() || !cols_sca.empty()) {
-        if (!cols_vec.empty()) {
-            ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
-            piped_vec = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_vec, dl);
-            if (!piped_vec && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
-            if (!piped_vec && has_rot(cols_vec)) return false;
-        }
-        if (sca_done) {
-            piped_sca = true;
-        } else if (!cols_sca.empty()) {
-            ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
-            piped_sca = launch_pipe<TIN, TOUT, TACC>(ctx, r, cols_sca, dl);
-            if (!piped_sca && ps.on) { ps.on = false; ctx->evPool.push_back(ps.rec.a); ctx->evPool.push_back(ps.rec.b); }
-            if (!piped_sca && has_rot(cols_sca)) return false;
-        }
-    }
-    if (!cols_vec.empty() && !piped_vec) {
-        ProfScope ps(ctx, 0, alg_bytes(r, ksum(cols_vec), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_vec) * r->nDst);
-        const int minb = tune_minb();
-        packs(cols_vec, [&](const FieldPack &fp, size_t n) {
+    if (!cols.empty() && !piped) {
+        // register-gather fallback for routes whose tiles exceed the pipelined kernel's caps
+        ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols) * r->nDst);
+        std::vector<FieldDev> vec, sca;
+        for (auto &f : cols)
+            (((size_t)f.nlev * sizeof(TIN)) % 16 == 0 && ((uintptr_t)f.src % 16) == 0 ? vec : sca).push_back(f);
+        const int minb = ctx->tune.colsMinb;
+        packs(vec, [&](const FieldPack &fp, size_t n) {
             dim3 g(tiles, (unsigned)((n + kFieldsPerCta - 1) / kFieldsPerCta));
             if (minb == 2) k_apply_cols<TIN, TOUT, TACC, true, 2><<<g, kThreads, 0, ctx->stream>>>(a, fp);
             else if (minb == 4) k_apply_cols<TIN, TOUT, TACC, true, 4><<<g, kThreads, 0, ctx->stream>>>(a, fp);
             else k_apply_cols<TIN, TOUT, TACC, true, 3><<<g, kThreads, 0, ctx->stream>>>(a, fp);
         });
-    }
-    if (!cols_sca.empty() && !piped_sca) {
-        ProfScope ps(ctx, 1, alg_bytes(r, ksum(cols_sca), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(cols_sca) * r->nDst);
-        packs(cols_sca, [&](const FieldPack &fp, size_t n) {
+        packs(sca, [&](const FieldPack &fp, size_t n) {
             dim3 g(tiles, (unsigned)((n + kFieldsPerCta - 1) / kFieldsPerCta));
             k_apply_cols<TIN, TOUT, TACC, false, 3><<<g, kThreads, 0, ctx->stream>>>(a, fp);
         });
@@ -674,7 +632,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         });
     }
     MPRG_CUDA(cudaGetLastError());
-    return rot_ok;
+    return true;
 }
 
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
@@ -687,15 +645,16 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
         dl.lev = (int64_t)tg.ni * tg.nj;
         dl.off = tg.slabOffset();
     }
-    std::vector<FieldDev> cols_vec, cols_sca, flat, planes, rotp;
+    std::vector<FieldDev> cols, rots, flat, planes;   // cols: plain 3-D fields; rots: wind pairs (appended to cols)
     std::vector<std::pair<void *, void *>> pairs;  // every (u, v) destination pair with fused rotation requested
     std::vector<int32_t> pair_nlev;
     bool late_rot = false;                          // some pair is too short for the column kernel: rotate afterwards
-    const size_t in_sz = src_dtype == MPRG_F32 ? 4 : 8;
-    auto vec_ok = [&](const FieldDev &d) { return (d.nlev * in_sz) % 16 == 0 && ((uintptr_t)d.src % 16) == 0; };
     for (int f = 0; f < nfields; ++f) {
         if (fields[f].nlev <= 0) fail(31, "mprg_apply: field %d has nlev %d", f, fields[f].nlev);
         if (!fields[f].src || !fields[f].dst) fail(32, "mprg_apply: field %d has a null buffer", f);
+        const size_t esz = src_dtype == MPRG_F32 ? 4 : 8;
+        if ((uintptr_t)fields[f].src % esz || (uintptr_t)fields[f].dst % (dst_dtype == MPRG_F32 ? 4 : 8))
+            fail(34, "mprg_apply: field %d is not aligned to its element size", f);
         FieldDev d{fields[f].src, fields[f].dst, fields[f].nlev, fields[f].epi_op, fields[f].epi_arg};
         if (d.epi_op == MPRG_EPI_ROT_V) fail(35, "mprg_apply: MPRG_EPI_ROT_V field %d has no MPRG_EPI_ROT_U before it", f);
         if (d.epi_op == MPRG_EPI_ROT_U) {
@@ -715,26 +674,33 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
                 flat.push_back(d); flat.push_back(v);
                 late_rot = true;
             } else {
-                rotp.push_back(d); rotp.push_back(v);  // adjacent: the unit builder interleaves their chunks
+                rots.push_back(d); rots.push_back(v);  // adjacent: the unit builder interleaves their chunks
             }
             ++f;
             continue;
         }
         if (r->srcLevelSlowest) planes.push_back(d);
         else if (d.nlev <= kShortLev) flat.push_back(d);
-        else if (vec_ok(d)) cols_vec.push_back(d);
-        else cols_sca.push_back(d);
+        else cols.push_back(d);
     }
+    // one column launch: aligned level counts first (the LDG staging caches the first unit's chunk offsets), then
+    // the others, then the wind pairs
+    std::stable_sort(cols.begin(), cols.end(), [&](const FieldDev &x, const FieldDev &y) {
+        const size_t esz = src_dtype == MPRG_F32 ? 4 : 8;
+        return ((x.nlev * esz) % 16 == 0) > ((y.nlev * esz) % 16 == 0);
+    });
+    const size_t nplain = cols.size();
+    cols.insert(cols.end(), rots.begin(), rots.end());
     auto run = [&]() {
         if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F32) {
-            return acc_fp32_requested() ? launch_all<float, float, float>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl)
-                                        : launch_all<float, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
+            return acc_fp32_requested(ctx) ? launch_all<float, float, float>(ctx, r, cols, flat, planes, dl)
+                                           : launch_all<float, float, double>(ctx, r, cols, flat, planes, dl);
         } else if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F64) {
-            return launch_all<float, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
+            return launch_all<float, double, double>(ctx, r, cols, flat, planes, dl);
         } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F32) {
-            return launch_all<double, float, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
+            return launch_all<double, float, double>(ctx, r, cols, flat, planes, dl);
         } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F64) {
-            return launch_all<double, double, double>(ctx, r, cols_vec, cols_sca, flat, planes, rotp, dl);
+            return launch_all<double, double, double>(ctx, r, cols, flat, planes, dl);
         }
         fail(33, "mprg_apply: bad dtype %d/%d", src_dtype, dst_dtype);
     };
@@ -742,11 +708,7 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
     if (!run()) {
         // the route does not fit the pipelined kernel: regrid the wind pairs like any field (register-gather
         // kernels), then rotate them in a second pass
-        for (auto d : rotp) {
-            d.epi_op = MPRG_EPI_NONE;
-            (vec_ok(d) ? cols_vec : cols_sca).push_back(d);
-        }
-        rotp.clear();
+        for (size_t k = nplain; k < cols.size(); ++k) cols[k].epi_op = MPRG_EPI_NONE;
         run();
         all_late = true;
     }
@@ -764,7 +726,7 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
 // (<= 1 ulp of fp64 from the divisions); both the stand-alone pass and the rotation fused into
 // k_apply_pipe read them, which keeps the two bit-identical.
 __global__ void k_rot_consts(const double *__restrict__ cosa, const double *__restrict__ sina, int64_t n,
-                             double *__restrict__ rotc) {
+                             double *__restrict__ rotc, float *__restrict__ rotc32) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double ca = cosa[i], sa = sina[i];
@@ -773,11 +735,13 @@ __global__ void k_rot_consts(const double *__restrict__ cosa, const double *__re
     rotc[4 * i + 1] = tana;
     rotc[4 * i + 2] = 1.0 / ca;
     rotc[4 * i + 3] = 1.0 / (ca + sa * tana);
+    for (int k = 0; k < 4; ++k) rotc32[4 * i + k] = (float)rotc[4 * i + k];   // what an all-fp32 apply rotates with
 }
 
 void rotation_constants(mprg_ctx *ctx, int64_t n) {
     ctx->rotc.alloc(4 * (size_t)n);
-    k_rot_consts<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->cosa.p, ctx->sina.p, n, ctx->rotc.p);
+    ctx->rotc32.alloc(4 * (size_t)n);
+    k_rot_consts<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->cosa.p, ctx->sina.p, n, ctx->rotc.p, ctx->rotc32.p);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
 }
@@ -805,7 +769,7 @@ void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, i
     if (n == 0 || nlev <= 0) return;
     const double *rotc = ctx->rotc.p + 4 * tg.slabOffset();
     dim3 g((unsigned)((n + 255) / 256), (unsigned)min(nlev, 4));  // >= 15 levels per thread: tana, den once per point
-    if (dtype == MPRG_F32 && acc_fp32_requested())
+    if (dtype == MPRG_F32 && acc_fp32_requested(ctx))
         k_rotate<float, float><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, rotc, n, nlev);
     else if (dtype == MPRG_F32)
         k_rotate<float, double><<<g, 256, 0, ctx->stream>>>((float *)u, (float *)v, rotc, n, nlev);

@@ -1,23 +1,32 @@
-// apply_pipe.cuh -- TMA-staged, pipelined column apply kernel (the hot kernel).
+// apply_pipe.cuh -- staged, pipelined column apply kernel (the hot kernel), v7.
 //
-// One CTA owns a tile of up to 32 consecutive destination points of one grid row and
-// sweeps EVERY stacked 3-D field of the launch for it:
-//   prologue  the tile's CSR slice and its tile schedule (distinct source columns of the tile,
-//             built once per route by k_tile_schedule) go to shared memory; every lane keeps the
-//             (weight, staged-column offset) pairs of ITS target in registers for the whole sweep
-//             when the row has <= 3 entries (bilinear, nearest);
-//   pipeline  for unit u (= one field x one 64-level chunk) every distinct column -- every RUN of
-//             consecutively numbered columns, which file order keeps contiguous -- is fetched by
-//             ONE bulk asynchronous copy (cp.async.bulk -> UBLKCP, completion counted on an
-//             mbarrier) STAGES-1 units ahead of the math: no registers or LSU wavefronts are
-//             spent on the gather and HBM latency is covered by the depth of the pipeline; the
-//             copy moves the 16-byte-aligned window enclosing the column chunk, so any level
-//             count works (60, 55, 61, ...);
-//   math      lanes run along TARGETS: warp w takes level groups w, w+8 (4 levels each); lane t
-//             reads 4 levels of each of its row's columns with one 16-byte shared load (units whose
-//             columns are not 16-byte aligned are first shifted into place inside their slots), and
-//             the 32 lanes' results for one level leave as one coalesced 128-byte streaming store
-//             into [lev][j][i].  No transpose through shared memory and one CTA barrier per unit.
+// One CTA owns a tile of up to 32 consecutive destination points of one grid row and sweeps EVERY
+// stacked 3-D field of the launch for it -- aligned level counts (60, 64, ...), unaligned ones (55, 61, ...)
+// and wind pairs with fused rotation alike, in ONE launch at 5 resident CTAs per SM:
+//   prologue  the tile's CSR slice and its tile schedule (distinct source columns of the tile in ascending
+//             id order, their runs of consecutive ids; built once per route by k_tile_schedule) go to shared
+//             memory; every lane keeps the (weight, staged-column slot) pairs of ITS target in registers for
+//             the whole sweep when the row has <= 3 entries (bilinear, nearest);
+//   staging   unit u + 1 (= one field x one 64-level chunk) is fetched while unit u is reduced.  Two modes,
+//             chosen per launch from the route's schedule statistics:
+//             BULK  (mesh numbered with locality: a tile's ~64 columns form a few runs of consecutive ids, which
+//                   file order keeps contiguous in memory) -- ONE cp.async.bulk (UBLKCP, completion counted on
+//                   an mbarrier) per RUN.  Columns whose byte size is a multiple of 16 land packed, 16-byte
+//                   aligned; others (61 levels: 244 B) are fetched as the 16-byte-aligned window around the run
+//                   and read in place with 4-byte shared loads at stride 61 words (odd: conflict-free) -- no
+//                   realignment pass, no second barrier;
+//             LDG   (no locality: every column its own DRAM page) -- the TMA unit accepts one request per
+//                   ~17 cycles per SM, which bounds a copy-per-column design at ~75 % of the HBM peak; here
+//                   every thread issues 16-byte cp.async (LDGSTS) for its share of the tile's chunks instead
+//                   (4-byte cp.async for unaligned columns, which lands them aligned), completion by
+//                   cp.async.wait_group + the per-unit CTA barrier;
+//   math      lanes run along TARGETS: warp w takes level groups w, w + 8 (4 levels each); lane t reads 4 levels
+//             of each of its row's columns with one 16-byte shared load and the 32 lanes' results for one level
+//             leave as one coalesced 128-byte streaming store into [lev][j][i].  No transpose through shared
+//             memory, one CTA barrier per unit;
+//   rotation  units of a wind pair alternate zonal / meridional chunks of the same levels; the zonal results wait
+//             in shared memory (8 KB) until the meridional unit, rotate_winds_cgrid (interp.F90:737-748) runs
+//             between the two, both are stored rotated.
 #pragma once
 #include "common.cuh"
 
@@ -29,6 +38,9 @@ constexpr int kPipeTile = 32;
 constexpr int kPipeCap = 256;      // CSR entries per tile accepted (== threads: one entry per thread in the prologue)
 constexpr int kPipeLev = 64;       // levels per unit
 constexpr int kPipeMaxUnits = 64;  // units (field x 64-level chunk) per launch; the host splits longer stacks
+constexpr int kPipeStages = 2;     // resident CTAs beat pipeline depth (profiles/r01: 2 x 5 CTAs > 3 x 4 > 4 x 3)
+constexpr int kRunPad = 40;        // BULK, unaligned units: slack per run so that 16-byte-aligned windows never overlap
+constexpr int kLdgCache = 5;       // LDG: per-thread chunk offsets kept in registers (covers tiles of <= 85 columns x 240 B)
 
 struct UnitDev {
     const void *src;
@@ -36,7 +48,7 @@ struct UnitDev {
     size_t srcBytes;   // size of the source array (guards the last aligned window)
     int32_t nlev;      // column stride of the field, in elements
     int32_t L0, Ln;    // level chunk [L0, L0+Ln)
-    int32_t epi_op;    // bits 0-7: MPRG_EPI_*;  bit 8: columns are 16-byte aligned (vector loads)
+    int32_t flags;     // bits 0-7: MPRG_EPI_*; kUnit* below
     double epi_arg;
 };
 // the unit descriptors of a launch travel as a kernel parameter (3 KB of constant bank): no
@@ -44,18 +56,20 @@ struct UnitDev {
 struct UnitPack {
     UnitDev u[kPipeMaxUnits];
 };
-constexpr int kUnitAligned = 0x100;
+constexpr int kUnitAligned = 0x100;                  // column chunks start 16-byte aligned and are a multiple of 16 bytes long
 constexpr int kUnitRotU = 0x200, kUnitRotV = 0x400;  // wind pair: this unit is the zonal / meridional chunk
+constexpr int kUnitMerged = 0x800;                   // the chunk is the whole column: runs of consecutive ids are contiguous in memory
 
 template <typename TW>
 struct PipeArgs {
     const int32_t *rowptr;
     const int32_t *col;
     const TW *w;
-    // tile schedule built once per route (k_tile_schedule): unique source columns of every tile
-    // and, per CSR entry, the index of its column in that list
+    // tile schedule built once per route (k_tile_schedule): unique source columns of every tile in ascending
+    // order, the run each of them belongs to, and per CSR entry the index of its column in that list
     const int32_t *tileUPtr;        // [nTiles + 1]
     const int32_t *tileUCols;       // [tileUPtr[nTiles]]
+    const unsigned char *tileURun;  // [tileUPtr[nTiles]] run index of the column within its tile
     const unsigned char *entrySlot; // [nnz]
     int64_t nDst;
     // destination addressing: point t of level l of a field goes to dst[l * dstLev + dstOff + t].  A slab
@@ -66,9 +80,11 @@ struct PipeArgs {
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
     int32_t nunits;
-    int32_t maxU;       // slot capacity of one stage (>= max unique columns of any tile)
-    // ROT launches only: rotation angles of this rank's destination rows (rotate_winds_cgrid fused into the store)
-    const double *rotc;  // [nDst][4]: sina, tana, 1/cosa, 1/(cosa + sina tana)
+    int32_t stageBytes; // bytes of one stage (host: the largest unit's need at the route's tile maxima)
+    int32_t holdOff;    // byte offset of the wind-pair hold buffer in dynamic shared memory (ROT launches), else 0
+    // ROT launches only: per-point rotation constants of this rank's destination rows, in the arithmetic type
+    // of the rotation (RotMath): [nDst][4] = sina, tana, 1/cosa, 1/(cosa + sina tana)
+    const void *rotc;
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -87,18 +103,36 @@ __device__ __forceinline__ void bulk_g2s(unsigned smemDst, const void *gmem, uns
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smemDst),
                  "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+// LDGSTS: 16 bytes global -> shared, L2 only (.cg); 4 / 8 bytes through L1 (.ca, the only form for short copies)
+__device__ __forceinline__ void ldgsts16(unsigned smemDst, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smemDst), "l"(gmem) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void ldgsts_small(unsigned smemDst, const void *gmem) {
+    if (BYTES == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smemDst), "l"(gmem) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smemDst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-template <typename TIN>
-__host__ __device__ constexpr int pipe_slot_bytes() { return kPipeLev * (int)sizeof(TIN) + 16; }
-
-// fixed part of the dynamic shared memory (bytes); STAGES * maxU * slotBytes of staging follow
+// fixed part of the dynamic shared memory (bytes); the stages follow, then (ROT launches) the hold buffer
 template <typename TACC>
 __host__ __device__ constexpr size_t pipe_fixed_bytes() {
     return 64 * 4                                   // s_rowptr (33 used) + mbarriers
-           + kPipeCap * 4                           // s_off (slot index of every entry's column)
+           + kPipeCap * 2                           // s_off: slot | run << 8 of every entry's column
            + kPipeCap * 4                           // s_uniq
-           + kPipeCap * sizeof(TACC)                // s_w
-           + kPipeMaxUnits * sizeof(UnitDev);       // s_units
+           + kPipeCap                               // s_urun: run index of every slot
+           + kPipeCap                               // s_runFirst: first slot of every run
+           + kPipeCap * sizeof(TACC);               // s_w
+}
+// slot stride of an aligned unit in shared memory: packed at the column size so that a run is contiguous there
+// too -- unless that size is a multiple of 128 bytes (every slot would start on bank 0): 16 bytes of padding then
+__host__ __device__ constexpr unsigned pipe_aligned_stride(unsigned colB) { return (colB & 127u) ? colB : colB + 16u; }
+// bytes of one stage that a unit needs for a tile of nu columns in nruns runs
+__host__ __device__ inline size_t pipe_unit_stage_bytes(bool ldg, bool aligned, bool merged, unsigned chunkB, int nu, int nruns) {
+    if (ldg) return (size_t)nu * pipe_aligned_stride((chunkB + 15u) & ~15u);
+    if (aligned) return (size_t)nu * ((merged && (chunkB & 127u)) ? chunkB : chunkB + 16u);
+    return (size_t)nu * chunkB + (size_t)kRunPad * (merged ? nruns : nu) + 32;
 }
 
 template <typename TACC>
@@ -109,7 +143,7 @@ __device__ __forceinline__ TACC pipe_epi(TACC v, int op, TACC arg) {
 // Arithmetic type of the fused / stand-alone wind rotation: the reference rotates R8 fields in R8
 // (interp.F90:737-748); an all-fp32 apply (fp32 output, fp32 accumulation) rotates in fp32 -- <= 3e-7
 // relative, inside the 1e-5 contract -- because B200's fp64 / conversion throughput would otherwise make
-// the rotation cost as much as regridding the two fields.  MPASSIT_GPU_ACC=f64 selects fp64 throughout.
+// the rotation cost as much as regridding the two fields.  accumulate = f64 selects fp64 throughout.
 template <typename TOUT, typename TACC> struct RotMath { using type = double; };
 template <> struct RotMath<float, float> { using type = float; };
 
@@ -128,40 +162,63 @@ __device__ __forceinline__ void fma4(TACC (&acc)[4], TACC wt, unsigned saddr) {
         acc[0] += wt * (TACC)x; acc[1] += wt * (TACC)y; acc[2] += wt * (TACC)z; acc[3] += wt * (TACC)w;
     }
 }
-template <typename TIN>
-__device__ __forceinline__ void sts1(unsigned saddr, TIN v) {
-    if (sizeof(TIN) == 4) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(saddr), "f"(*(float *)&v) : "memory");
-    else asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(saddr), "d"(*(double *)&v) : "memory");
+// the same from a column that is only element-aligned in shared memory (BULK staging of unaligned units)
+template <typename TIN, typename TACC>
+__device__ __forceinline__ void fma4u(TACC (&acc)[4], TACC wt, unsigned saddr) {
+    if (sizeof(TIN) == 4) {
+        float x, y, z, w;
+        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(saddr));
+        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(y) : "r"(saddr + 4));
+        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(z) : "r"(saddr + 8));
+        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(w) : "r"(saddr + 12));
+        acc[0] += wt * (TACC)x; acc[1] += wt * (TACC)y; acc[2] += wt * (TACC)z; acc[3] += wt * (TACC)w;
+    } else {
+        double x, y, z, w;
+        asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(x) : "r"(saddr));
+        asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(y) : "r"(saddr + 8));
+        asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(z) : "r"(saddr + 16));
+        asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(w) : "r"(saddr + 24));
+        acc[0] += wt * (TACC)x; acc[1] += wt * (TACC)y; acc[2] += wt * (TACC)z; acc[3] += wt * (TACC)w;
+    }
 }
-template <typename TIN>
-__device__ __forceinline__ TIN lds1(unsigned saddr) {
-    TIN v;
-    if (sizeof(TIN) == 4) asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(*(float *)&v) : "r"(saddr));
-    else asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(*(double *)&v) : "r"(saddr));
-    return v;
+template <typename T>
+__device__ __forceinline__ void sts4(unsigned saddr, const T (&v)[4]) {
+    if (sizeof(T) == 4) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "f"(*(const float *)&v[0]), "f"(*(const float *)&v[1]),
+                     "f"(*(const float *)&v[2]), "f"(*(const float *)&v[3]) : "memory");
+    } else {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(saddr), "d"(*(const double *)&v[0]), "d"(*(const double *)&v[1]) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(saddr + 16), "d"(*(const double *)&v[2]), "d"(*(const double *)&v[3]) : "memory");
+    }
+}
+template <typename T>
+__device__ __forceinline__ void lds4(unsigned saddr, T (&v)[4]) {
+    if (sizeof(T) == 4) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(*(float *)&v[0]), "=f"(*(float *)&v[1]), "=f"(*(float *)&v[2]),
+                     "=f"(*(float *)&v[3]) : "r"(saddr));
+    } else {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(*(double *)&v[0]), "=d"(*(double *)&v[1]) : "r"(saddr));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(*(double *)&v[2]), "=d"(*(double *)&v[3]) : "r"(saddr + 16));
+    }
 }
 
-// ALLVEC: every unit of the launch has 16-byte-aligned columns (compile-time specialisation
-// without the aligned-window arithmetic and without the 4-byte load path).
-// MINB: resident CTAs per SM the kernel is compiled for (register cap 64 at 4, 48 at 5).
-// ROT: some units are (zonal wind, meridional wind) chunk pairs (kUnitRotU then kUnitRotV, same levels);
-//      the thread that reduces u(t, lev) also reduces v(t, lev) one unit later, so rotate_winds_cgrid
-//      (interp.F90:737-748) runs in registers between the two and both are stored rotated -- no separate
-//      pass over the fields.
-template <typename TIN, typename TOUT, typename TACC, int STAGES, bool ALLVEC, int MINB, bool ROT = false>
+// LDG: staging mode (see the header).  MINB: resident CTAs per SM the kernel is compiled for (register cap
+// 48 at 5, 64 at 4).
+template <typename TIN, typename TOUT, typename TACC, bool LDG, int MINB>
 __global__ void __launch_bounds__(kPipeThreads, MINB)
 k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
-    constexpr int SLOTB = pipe_slot_bytes<TIN>();
-    constexpr int EPV = 16 / (int)sizeof(TIN);            // elements per 16-byte chunk
-    constexpr int GB = 4 * (int)sizeof(TIN);              // bytes of one 4-level group in a staged column
+    constexpr int ESZ = (int)sizeof(TIN);
+    constexpr int GB = 4 * ESZ;                           // bytes of one 4-level group in a staged column
+    using TR = typename RotMath<TOUT, TACC>::type;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    int32_t *s_rowptr = (int32_t *)smem;            // [33]; mbarriers at [48..55]
+    int32_t *s_rowptr = (int32_t *)smem;            // [33]; mbarriers at [48..51]
     unsigned long long *s_mbar = (unsigned long long *)(s_rowptr + 48);  // one per stage
-    int32_t *s_off = s_rowptr + 64;                 // per entry: slot index of its column in the tile's list
-    int32_t *s_uniq = s_off + kPipeCap;
-    TACC *s_w = (TACC *)(s_uniq + kPipeCap);
-    UnitDev *s_units = (UnitDev *)(s_w + kPipeCap);
+    unsigned short *s_off = (unsigned short *)(s_rowptr + 64);  // per entry: slot | run << 8 of its column
+    int32_t *s_uniq = (int32_t *)(s_off + kPipeCap);
+    unsigned char *s_urun = (unsigned char *)(s_uniq + kPipeCap);
+    unsigned char *s_runFirst = s_urun + kPipeCap;
+    TACC *s_w = (TACC *)(s_runFirst + kPipeCap);
     unsigned char *s_stage = smem + pipe_fixed_bytes<TACC>();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -172,23 +229,26 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
 
     // ---- prologue: CSR slice + the tile's schedule ---------------------------------
     if (tid <= kPipeTile) s_rowptr[tid] = a.rowptr[min(t0 + min(tid, ntile), a.nDst)];
-    for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
-        ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
-    if (tid == 0) {
+    if (!LDG && tid == 0) {
 #pragma unroll
-        for (int i = 0; i < STAGES; ++i) mbar_init(s_mbar + i, ALLVEC ? 1 : kPipeWarps);  // arrivals per unit
+        for (int i = 0; i < kPipeStages; ++i) mbar_init(s_mbar + i, kPipeWarps);  // one arrival per warp per unit
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const int ub = __ldg(a.tileUPtr + blockIdx.x);
     const int nu = __ldg(a.tileUPtr + blockIdx.x + 1) - ub;
-    if (tid < nu) s_uniq[tid] = __ldg(a.tileUCols + ub + tid);
+    if (tid < nu) {
+        s_uniq[tid] = __ldg(a.tileUCols + ub + tid);
+        if (!LDG) s_urun[tid] = __ldg(a.tileURun + ub + tid);
+    }
     __syncthreads();
     const int base = s_rowptr[0];
     const int cnt = s_rowptr[ntile] - base;  // host guarantees cnt <= kPipeCap
     if (tid < cnt) {
         s_w[tid] = __ldg(a.w + base + tid);
-        s_off[tid] = __ldg(a.entrySlot + base + tid);
+        const int sl = __ldg(a.entrySlot + base + tid);
+        s_off[tid] = (unsigned short)(LDG ? sl : (sl | ((int)s_urun[sl] << 8)));
     }
+    if (!LDG && tid < nu && (tid == 0 || s_urun[tid] != s_urun[tid - 1])) s_runFirst[s_urun[tid]] = (unsigned char)tid;
     __syncthreads();
 
     // this lane's target; rows with <= 3 entries stay in registers
@@ -201,173 +261,219 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     for (int j = 0; j < 3; ++j) {
         const bool h = j < rlen && rlen <= 3;
         rw[j] = h ? s_w[rbeg + j] : (TACC)0;
-        ro[j] = h ? s_off[rbeg + j] : 0;
+        ro[j] = h ? (int)s_off[rbeg + j] : 0;
     }
-    // wind rotation: angles of this lane's target (same operation order as k_rotate)
-    // (fp32 arithmetic when the whole apply is fp32 -- RotMath -- : the fp64 pipe would otherwise bound the launch)
-    using TR = typename RotMath<TOUT, TACC>::type;
-    TR rsa = 0, rtana = 0, rcai = 1, rdeni = 1;
-    if (ROT && live) {  // per-point constants prepared once by mprg_set_rotation (k_rot_consts)
-        const double2 c0 = __ldg((const double2 *)(a.rotc + 4 * (t0 + lane)));
-        const double2 c1 = __ldg((const double2 *)(a.rotc + 4 * (t0 + lane)) + 1);
-        rsa = (TR)c0.x; rtana = (TR)c0.y; rcai = (TR)c1.x; rdeni = (TR)c1.y;
-    }
-    TOUT hold[kPipeLev / 4 / kPipeWarps][4];  // ROT: the zonal unit's results, held until the meridional unit
     const bool fast = __all_sync(0xffffffffu, rlen <= 3);
     // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
     const bool all3 = __all_sync(0xffffffffu, live && rlen == 3);
 
-    const int stageBytes = a.maxU * SLOTB;
-    // slot s = lane * warps + warp is copied by that lane, so the (warp-serialised) bulk-copy
-    // issue is spread evenly over all warps instead of queuing behind the first two
+    const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
+    const unsigned hold0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.holdOff;
+
+    // ---- staging state -----------------------------------------------------------------------------------
+    // BULK: slot s = lane * warps + warp is copied by that lane, so the (warp-serialised) bulk-copy issue is
+    // spread evenly over all warps.  The owner of the first slot of a run fetches the whole run of a merged unit.
     const int bslot = lane * kPipeWarps + warp;
-    const int bcol = bslot < nu ? s_uniq[bslot] : -1;
-    // ALLVEC: the list is in ascending id order and columns of consecutive ids are contiguous in memory, so
-    // the owner of the first slot of a run fetches the whole run with one bulk copy (brun = its length in
-    // columns, 0 for the other slots of the run).  The TMA unit accepts a request every ~19 cycles per SM,
-    // which is what bounds this kernel: fewer, larger requests are the lever.
-    int brun = bcol >= 0 ? 1 : 0;
-    if (ALLVEC && bcol >= 0) {
-        if (bslot > 0 && s_uniq[bslot - 1] == bcol - 1) {
-            brun = 0;
-        } else {
-            while (bslot + brun < nu && s_uniq[bslot + brun] == bcol + brun) ++brun;
+    int bcol = -1, brun = 0;
+    // LDG: byte offsets (within a field of the first unit's shape) of this thread's 16-byte chunks
+    unsigned goff[kLdgCache];
+    bool gcached = false;   // goff[] holds the offsets of units shaped like the first one
+    if (!LDG) {
+        bcol = bslot < nu ? s_uniq[bslot] : -1;
+        if (bcol >= 0 && (bslot == 0 || s_urun[bslot] != s_urun[bslot - 1])) {
+            brun = 1;
+            while (bslot + brun < nu && s_urun[bslot + brun] == s_urun[bslot]) ++brun;
+        }
+    } else {
+        const UnitDev &u0 = up.u[0];
+        if ((u0.flags & kUnitAligned) && u0.srcBytes <= 0xffffffffull) {
+            gcached = true;
+            const int cpc = (u0.Ln * ESZ) >> 4;
+#pragma unroll
+            for (int k = 0; k < kLdgCache; ++k) {
+                const int q = tid + k * kPipeThreads, sl = q / cpc;
+                goff[k] = sl < nu ? (unsigned)(((size_t)s_uniq[sl] * u0.nlev + u0.L0) * ESZ + (size_t)(q - sl * cpc) * 16) : 0u;
+            }
         }
     }
-    const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
-    const unsigned bstage = stage0 + bslot * SLOTB;
 
     auto issue = [&](int u) {
         if (u >= a.nunits) return;
-        const UnitDev &ud = s_units[u];
-        unsigned long long *bar = s_mbar + (u % STAGES);
-        if (ALLVEC) {
-            // equal, exact column chunks: thread 0 posts the unit's byte count, run owners copy.  Slots are
-            // packed at the column size so that a run is contiguous in shared memory too -- unless that size
-            // is a multiple of 128 bytes (every slot would start on bank 0): then slots keep 16 bytes of
-            // padding and every column is its own copy.  Whole-field units only: a run of columns is
-            // contiguous in memory only when the chunk is the entire column.
-            const unsigned colB = (unsigned)ud.Ln * (unsigned)sizeof(TIN);
-            const bool packed = (colB & 127u) != 0 && ud.Ln == ud.nlev;
-            const unsigned stride = packed ? colB : colB + 16;
-            if (tid == 0) mbar_arrive_tx(bar, colB * (unsigned)nu);
-            const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * sizeof(TIN);
-            const unsigned sdst = stage0 + (u % STAGES) * stageBytes + bslot * stride;
-            if (packed) {
-                if (brun > 0) bulk_g2s(sdst, g, colB * (unsigned)brun, bar);
-            } else if (bcol >= 0) {
-                bulk_g2s(sdst, g, colB, bar);
-            }
-        } else if (ud.epi_op & kUnitAligned) {
-            // aligned unit of a mixed launch: exact chunks again, but this barrier counts one arrival per
-            // warp (lane 0 posts the bytes of the warp's own copies; an mbarrier's transaction count may
-            // run ahead of the expectation, so no ordering between the two is needed)
-            const unsigned colB = (unsigned)ud.Ln * (unsigned)sizeof(TIN);
-            const unsigned mine = __popc(__ballot_sync(0xffffffffu, bcol >= 0));
-            if (lane == 0) mbar_arrive_tx(bar, colB * mine);
-            if (bcol >= 0)
-                bulk_g2s(bstage + (u % STAGES) * stageBytes,
-                         (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * sizeof(TIN), colB, bar);
-        } else {
-            // lane 0 of every warp arrives with the warp's byte count; the owner of a slot then
-            // launches one bulk copy of the 16-byte-aligned window enclosing the column chunk
-            unsigned nb = 0;
-            size_t al = 0;
-            if (bcol >= 0) {
-                const size_t byte0 = ((size_t)bcol * ud.nlev + ud.L0) * sizeof(TIN);
-                al = byte0 & ~(size_t)15;
-                size_t n = ((byte0 + (size_t)ud.Ln * sizeof(TIN) + 15) & ~(size_t)15) - al;
-                if (al + n > ud.srcBytes) {
-                    // last window of the allocation: bulk-copy the whole chunks, hand-copy the tail words
-                    const size_t full = (ud.srcBytes - al) & ~(size_t)15;
-                    for (size_t b = full; al + b < ud.srcBytes; b += 4)
-                        *(int32_t *)(s_stage + (size_t)(u % STAGES) * stageBytes + bslot * SLOTB + b) =
-                            *(const int32_t *)((const char *)ud.src + al + b);
-                    n = full;
+        const UnitDev &ud = up.u[u];
+        const unsigned chunkB = (unsigned)ud.Ln * ESZ;
+        const unsigned sbase = stage0 + (u % kPipeStages) * a.stageBytes;
+        if (LDG) {
+            const unsigned stride = pipe_aligned_stride((chunkB + 15u) & ~15u);
+            const char *src = (const char *)ud.src;
+            if (ud.flags & kUnitAligned) {
+                const int cpc = (int)(chunkB >> 4), total = nu * cpc;
+                if (gcached && ud.nlev == up.u[0].nlev && ud.L0 == up.u[0].L0 && ud.Ln == up.u[0].Ln && ud.srcBytes <= 0xffffffffull) {
+#pragma unroll
+                    for (int k = 0; k < kLdgCache; ++k) {
+                        const int q = tid + k * kPipeThreads;
+                        if (q < total) {
+                            const int sl = q / cpc;
+                            ldgsts16(sbase + sl * stride + (q - sl * cpc) * 16, src + goff[k]);
+                        }
+                    }
+                    for (int q = tid + kLdgCache * kPipeThreads; q < total; q += kPipeThreads) {
+                        const int sl = q / cpc, part = q - sl * cpc;
+                        ldgsts16(sbase + sl * stride + part * 16, src + ((size_t)s_uniq[sl] * ud.nlev + ud.L0) * ESZ + (size_t)part * 16);
+                    }
+                } else {
+                    for (int q = tid; q < total; q += kPipeThreads) {
+                        const int sl = q / cpc, part = q - sl * cpc;
+                        ldgsts16(sbase + sl * stride + part * 16, src + ((size_t)s_uniq[sl] * ud.nlev + ud.L0) * ESZ + (size_t)part * 16);
+                    }
                 }
-                nb = (unsigned)n;
+            } else {
+                // element-wise copies land every column at the start of its (16-byte aligned) slot
+                const int total = nu * ud.Ln;
+                for (int q = tid; q < total; q += kPipeThreads) {
+                    const int sl = q / ud.Ln, l = q - sl * ud.Ln;
+                    ldgsts_small<ESZ>(sbase + sl * stride + l * ESZ, src + ((size_t)s_uniq[sl] * ud.nlev + ud.L0 + l) * ESZ);
+                }
             }
-            const unsigned wb = __reduce_add_sync(0xffffffffu, nb);
-            __syncwarp();  // hand-copied tail words are ordered before the arrival that publishes them
-            if (lane == 0) mbar_arrive_tx(bar, wb);
-            if (nb) bulk_g2s(bstage + (u % STAGES) * stageBytes, (const char *)ud.src + al, nb, bar);
+            cp_async_commit();
+            return;
         }
+        unsigned long long *bar = s_mbar + (u % kPipeStages);
+        const bool merged = (ud.flags & kUnitMerged) != 0;
+        unsigned nb = 0, sdst = 0;
+        const char *g = nullptr;
+        if (ud.flags & kUnitAligned) {
+            // exact column chunks.  Merged units whose column size is not a multiple of 128 bytes pack their slots
+            // at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
+            const bool packed = merged && (chunkB & 127u);
+            if (packed ? brun > 0 : bcol >= 0) {
+                nb = packed ? chunkB * (unsigned)brun : chunkB;
+                sdst = sbase + bslot * (packed ? chunkB : chunkB + 16u);
+                g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
+            }
+        } else if (merged ? brun > 0 : bcol >= 0) {
+            // unaligned columns: the 16-byte-aligned window around the run (or the single column chunk); it lands at
+            // a 16-byte-aligned address chosen so that windows never overlap, and the math reads it where it lies
+            const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
+            // (absolute addresses: the source base itself need only be element-aligned; device allocations are
+            // 256-byte aligned, so the window's first 16-byte chunk always lies inside the caller's allocation)
+            const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
+            const uintptr_t al = a0 & ~(uintptr_t)15, aend = (uintptr_t)ud.src + ud.srcBytes;
+            size_t n = ((a0 + (size_t)(ncol - 1) * ud.nlev * ESZ + chunkB + 15) & ~(uintptr_t)15) - al;
+            sdst = sbase + (((unsigned)bslot * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u);
+            if (al + n > aend) {
+                // last window of the array: bulk-copy the whole 16-byte chunks, hand-copy the tail words
+                const size_t full = (aend - al) & ~(size_t)15;
+                for (size_t b = full; al + b < aend; b += 4) {
+                    const int32_t v = *(const int32_t *)(al + b);
+                    asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(sdst + (unsigned)b), "r"(v) : "memory");
+                }
+                n = full;
+            }
+            nb = (unsigned)n;
+            g = (const char *)al;
+        }
+        const unsigned wb = __reduce_add_sync(0xffffffffu, nb);   // (also orders the hand-copied tail before the arrival)
+        if (lane == 0) mbar_arrive_tx(bar, wb);
+        if (nb) bulk_g2s(sdst, g, nb, bar);
     };
 
-#pragma unroll
-    for (int u = 0; u < STAGES - 1; ++u) issue(u);
+    issue(0);
 
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
     for (int u = 0; u < a.nunits; ++u) {
-        if (u > 0) __syncthreads();     // every warp has finished reading unit u-1: its buffer may be refilled
-        issue(u + STAGES - 1);
-        mbar_wait(s_mbar + (u % STAGES), (unsigned)((u / STAGES) & 1));  // unit u's bytes have landed
-        const UnitDev &ud = s_units[u];
-        const unsigned st = stage0 + (u % STAGES) * stageBytes;  // shared-window address of unit u's staging
+        if (LDG) cp_async_wait_all();   // this thread's share of unit u has landed ...
+        __syncthreads();                // ... everyone's has, and every warp has finished reading unit u - 1
+        issue(u + 1);                   // into the buffer unit u - 1 occupied
+        if (!LDG) mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
+        const UnitDev &ud = up.u[u];
+        const unsigned st = stage0 + (u % kPipeStages) * a.stageBytes;  // shared-window address of unit u's staging
         const int Ln = ud.Ln;
-        const int eop = ud.epi_op & 0xff;
-        const bool aligned = ALLVEC || (ud.epi_op & kUnitAligned) != 0;
+        const int eop = ud.flags & 0xff;
         const TACC earg = (TACC)ud.epi_arg;
         const int ngroups = (Ln + 3) >> 2;
-        if (!ALLVEC && !aligned) {
-            // Columns whose start is not 16-byte aligned were copied as the aligned window around them, so
-            // the wanted levels begin eo elements into the slot, (c * nlev + L0) mod EPV =
-            // ((c mod EPV) * (nlev mod EPV) + L0 mod EPV) mod EPV.  Each warp shifts its share of the
-            // slots down by eo (conflict-free consecutive words) so that the math below reads every unit
-            // with 16-byte loads; per-lane 4-byte reads at eo would conflict 4-5 way on the banks.
-            const int nm = ud.nlev & (EPV - 1), lm = ud.L0 & (EPV - 1);
-            for (int s = warp; s < nu; s += kPipeWarps) {
-                const int eo = ((s_uniq[s] & (EPV - 1)) * nm + lm) & (EPV - 1);
-                if (eo) {
-                    const unsigned sb = st + s * SLOTB;
-                    const TIN x0 = lds1<TIN>(sb + (eo + lane) * (int)sizeof(TIN));
-                    const TIN x1 = lds1<TIN>(sb + (eo + lane + 32) * (int)sizeof(TIN));  // the window holds EPV-1 elements of slack
-                    __syncwarp();
-                    sts1<TIN>(sb + lane * (int)sizeof(TIN), x0);
-                    sts1<TIN>(sb + (lane + 32) * (int)sizeof(TIN), x1);
-                }
-            }
-            __syncthreads();
-        }
         if (!live) continue;
-        // byte offsets of this lane's columns in the unit's staging (slot index x the unit's slot stride)
-        const int colBu = Ln * (int)sizeof(TIN);
-        const int ustride = !ALLVEC ? SLOTB : (((colBu & 127) != 0 && Ln == ud.nlev) ? colBu : colBu + 16);
+        const unsigned chunkB = (unsigned)Ln * ESZ;
+        const bool direct = LDG || (ud.flags & kUnitAligned);     // columns sit 16-byte aligned at slot * ustride
+        // byte offsets of this lane's columns in the unit's staging
+        unsigned co[3] = {0, 0, 0};
+        unsigned ustride = 0;
+        if (direct) {
+            ustride = LDG ? pipe_aligned_stride((chunkB + 15u) & ~15u)
+                          : (((ud.flags & kUnitMerged) && (chunkB & 127u)) ? chunkB : chunkB + 16u);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) co[j] = (unsigned)(ro[j] & 0xff) * ustride;
+        } else {
+            // BULK, unaligned: column of slot s in run r lies at window(r) + (its global byte offset - the window's)
+            const bool merged = (ud.flags & kUnitMerged) != 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int sl = ro[j] & 0xff, r = merged ? (ro[j] >> 8) : sl;
+                const int f = merged ? (int)s_runFirst[r] : sl;
+                const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)s_uniq[f] * ud.nlev + ud.L0) * ESZ;
+                co[j] = (((unsigned)f * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u) + (unsigned)(a0 & 15) +
+                        (unsigned)(sl - f) * (unsigned)(ud.nlev * ESZ);
+            }
+        }
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
         const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane;
         TOUT *d = (TOUT *)ud.dst + dcol;
-        const bool rotU = ROT && (ud.epi_op & kUnitRotU), rotV = ROT && (ud.epi_op & kUnitRotV);
-        TOUT *du = (TOUT *)s_units[rotV ? u - 1 : u].dst + dcol;        // ROT: where the held zonal values go
+        const bool rotU = (ud.flags & kUnitRotU) != 0, rotV = (ud.flags & kUnitRotV) != 0;
 #pragma unroll
-        for (int gi = 0; gi < kPipeLev / 4 / kPipeWarps; ++gi, d += grp8, du += grp8) {
+        for (int gi = 0; gi < kPipeLev / 4 / kPipeWarps; ++gi, d += grp8) {
             const int g = warp + gi * kPipeWarps;
             if (g >= ngroups) break;
             TACC acc[4] = {0, 0, 0, 0};
             const unsigned lp = st + g * GB;
-            if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
-                fma4<TIN, TACC>(acc, rw[0], lp + ro[0] * ustride);
-                fma4<TIN, TACC>(acc, rw[1], lp + ro[1] * ustride);
-                fma4<TIN, TACC>(acc, rw[2], lp + ro[2] * ustride);
+            if (direct) {
+                if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
+                    fma4<TIN, TACC>(acc, rw[0], lp + co[0]);
+                    fma4<TIN, TACC>(acc, rw[1], lp + co[1]);
+                    fma4<TIN, TACC>(acc, rw[2], lp + co[2]);
+                } else if (fast) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + co[j]);  // absent entries never touch staging (0 x garbage = NaN)
+                } else {
+                    for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (unsigned)(s_off[k] & 0xff) * ustride);
+                }
             } else if (fast) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
-                    if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + ro[j] * ustride);  // absent entries never touch staging (0 x garbage = NaN)
+                    if (j < rlen) fma4u<TIN, TACC>(acc, rw[j], lp + co[j]);
             } else {
-                for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + s_off[k] * ustride);
+                const bool merged = (ud.flags & kUnitMerged) != 0;
+                for (int k = rbeg; k < rbeg + rlen; ++k) {
+                    const int sl = s_off[k] & 0xff, r = merged ? (s_off[k] >> 8) : sl;
+                    const int f = merged ? (int)s_runFirst[r] : sl;
+                    const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)s_uniq[f] * ud.nlev + ud.L0) * ESZ;
+                    fma4u<TIN, TACC>(acc, s_w[k], lp + (((unsigned)f * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u) +
+                                                      (unsigned)(a0 & 15) + (unsigned)(sl - f) * (unsigned)(ud.nlev * ESZ));
+                }
             }
-            if (ROT && rotU) {          // zonal unit: keep, rounded to the output type exactly as a store would
-#pragma unroll
-                for (int k = 0; k < 4; ++k) hold[gi][k] = (TOUT)acc[k];
+            if (rotU) {          // zonal unit: park the results, rounded to the output type exactly as a store would
+                TOUT h[4] = {(TOUT)acc[0], (TOUT)acc[1], (TOUT)acc[2], (TOUT)acc[3]};
+                sts4<TOUT>(hold0 + (unsigned)((gi * kPipeThreads + tid) * 4 * (int)sizeof(TOUT)), h);
                 continue;
             }
-            if (ROT && rotV) {
+            if (rotV) {
                 // meridional unit: u' = (u + v tana) / (cosa + sina tana); v' = (v - u' sina) / cosa  (v' uses u');
                 // the two divisors are per-point constants, applied as reciprocals (same in k_rotate)
+                TOUT h[4];
+                lds4<TOUT>(hold0 + (unsigned)((gi * kPipeThreads + tid) * 4 * (int)sizeof(TOUT)), h);
+                TR c[4];   // sina, tana, 1/cosa, 1/(cosa + sina tana) of this lane's target
+                if (sizeof(TR) == 4) {
+                    const float4 q = __ldg((const float4 *)a.rotc + (t0 + lane));
+                    c[0] = (TR)q.x; c[1] = (TR)q.y; c[2] = (TR)q.z; c[3] = (TR)q.w;
+                } else {
+                    const double2 q0 = __ldg((const double2 *)a.rotc + 2 * (t0 + lane)), q1 = __ldg((const double2 *)a.rotc + 2 * (t0 + lane) + 1);
+                    c[0] = (TR)q0.x; c[1] = (TR)q0.y; c[2] = (TR)q1.x; c[3] = (TR)q1.y;
+                }
+                TOUT *du = (TOUT *)up.u[u - 1].dst + dcol + (size_t)gi * grp8;   // where the held zonal values go
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    TR uu = (TR)hold[gi][k], vv = (TR)(TOUT)acc[k];
-                    uu = (uu + vv * rtana) * rdeni;
-                    vv = (vv - uu * rsa) * rcai;
+                    TR uu = (TR)h[k], vv = (TR)(TOUT)acc[k];
+                    uu = (uu + vv * c[1]) * c[3];
+                    vv = (vv - uu * c[0]) * c[2];
                     if (4 * g + k < Ln) {
                         __stcs(du + (size_t)k * a.dstLev, (TOUT)uu);
                         __stcs(d + (size_t)k * a.dstLev, (TOUT)vv);
@@ -396,19 +502,20 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
 }
 
 // Tile schedule of a route: for every row-aligned 32-target tile the list of distinct source
-// columns in ASCENDING id order and, per CSR entry, the index of its column in that list.  Ascending
-// order makes columns of consecutively numbered cells neighbours in the list; they are also
-// neighbours in memory (file order), so the apply kernel fetches each such run with ONE bulk copy.
+// columns in ASCENDING id order, the run (maximal sequence of consecutive ids) each belongs to and, per CSR
+// entry, the index of its column in that list.  Ascending order makes columns of consecutively numbered cells
+// neighbours in the list; they are also neighbours in memory (file order), so the apply kernel fetches each
+// such run with ONE bulk copy.
 // FILL == false: per-tile unique counts (+ global maxima);  FILL == true: write the lists.
 template <bool FILL>
 __global__ void __launch_bounds__(kPipeThreads)
 k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t nDst, int32_t ni,
-                int32_t tilesPerRow, int32_t *maxEntries, int32_t *maxUniq, int32_t *tileCount,
-                const int32_t *__restrict__ tileUPtr, int32_t *__restrict__ tileUCols,
+                int32_t tilesPerRow, int32_t *maxEntries, int32_t *maxUniq, int32_t *maxRuns, int32_t *tileCount,
+                const int32_t *__restrict__ tileUPtr, int32_t *__restrict__ tileUCols, unsigned char *__restrict__ tileURun,
                 unsigned char *__restrict__ entrySlot, unsigned long long *runsTotal) {
     __shared__ int32_t s_col[kPipeCap];   // sort keys (column ids; INT_MAX padding)
     __shared__ int32_t s_idx[kPipeCap];   // entry index within the tile that the key came from
-    __shared__ int32_t s_cnt[kPipeWarps];
+    __shared__ int32_t s_cnt[kPipeWarps], s_rcnt[kPipeWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = blockIdx.x / tilesPerRow;
     const int i0 = (blockIdx.x - row * tilesPerRow) * kPipeTile;
@@ -439,26 +546,30 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
             __syncthreads();
         }
     const bool uniq = tid < cnt && (tid == 0 || s_col[tid] != s_col[tid - 1]);
-    const unsigned bal = __ballot_sync(0xffffffffu, uniq);
-    if (lane == 0) s_cnt[warp] = __popc(bal);
+    // a run starts at a distinct column whose predecessor in the sorted list is not id - 1 (equal ids were skipped above)
+    const bool runStart = uniq && (tid == 0 || s_col[tid - 1] != s_col[tid] - 1);
+    const unsigned bal = __ballot_sync(0xffffffffu, uniq), rb = __ballot_sync(0xffffffffu, runStart);
+    if (lane == 0) { s_cnt[warp] = __popc(bal); s_rcnt[warp] = __popc(rb); }
     __syncthreads();
-    int incl = __popc(bal & ((2u << lane) - 1u)), nu = 0;  // unique keys up to and including this position
+    int incl = __popc(bal & ((2u << lane) - 1u)), nu = 0;   // unique keys up to and including this position
+    int rincl = __popc(rb & ((2u << lane) - 1u)), nr = 0;   // run starts up to and including this position
 #pragma unroll
     for (int w = 0; w < kPipeWarps; ++w) {
-        const int v = s_cnt[w];
-        if (w < warp) incl += v;
-        nu += v;
+        const int v = s_cnt[w], rv = s_rcnt[w];
+        if (w < warp) { incl += v; rincl += rv; }
+        nu += v; nr += rv;
     }
     if (!FILL) {
-        if (tid == 0) { atomicMax(maxUniq, nu); tileCount[blockIdx.x] = nu; }
+        if (tid == 0) { atomicMax(maxUniq, nu); atomicMax(maxRuns, nr); tileCount[blockIdx.x] = nu; }
         return;
     }
-    if (uniq) tileUCols[tileUPtr[blockIdx.x] + incl - 1] = s_col[tid];
+    if (uniq) {
+        tileUCols[tileUPtr[blockIdx.x] + incl - 1] = s_col[tid];
+        tileURun[tileUPtr[blockIdx.x] + incl - 1] = (unsigned char)(rincl - 1);
+    }
     if (tid < cnt) entrySlot[base + s_idx[tid]] = (unsigned char)(incl - 1);
-    // statistics: runs of consecutive ids (= bulk copies per unit of an all-aligned launch)
-    const bool runStart = uniq && (tid == 0 || s_col[tid - 1] != s_col[tid] - 1);
-    const unsigned rb = __ballot_sync(0xffffffffu, runStart);
-    if (lane == 0 && rb && runsTotal) atomicAdd(runsTotal, (unsigned long long)__popc(rb));
+    // statistics: runs of consecutive ids (= bulk copies per unit of a merged launch)
+    if (tid == 0 && nr && runsTotal) atomicAdd(runsTotal, (unsigned long long)nr);
 }
 
 }  // namespace mprg

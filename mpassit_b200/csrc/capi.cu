@@ -50,6 +50,36 @@ struct Trace {
         return 3;                                           \
     }
 
+// returns false for an unknown key / value
+static bool set_option(mprg_ctx *c, const char *key, const char *val) {
+    const std::string k = key ? key : "", v = val ? val : "";
+    mprg_tuning &t = c->tune;
+    if (k == "accumulate") {
+        if (v == "f64" || v == "fp64") t.acc64 = true;
+        else if (v == "f32" || v == "fp32" || v.empty()) t.acc64 = false;
+        else return false;
+    } else if (k == "apply") {
+        t.pipeOff = v == "direct";
+        if (v != "direct" && v != "pipe" && !v.empty()) return false;
+    } else if (k == "staging") {
+        if (v == "bulk") t.staging = 0;
+        else if (v == "ldg") t.staging = 1;
+        else if (v == "auto" || v.empty()) t.staging = -1;
+        else return false;
+    } else if (k == "pipe_minb") {
+        t.pipeMinb = atoi(v.c_str());
+    } else if (k == "cols_minb") {
+        t.colsMinb = v.empty() ? 3 : atoi(v.c_str());
+    } else if (k == "upload_threads") {
+        t.uploadThreads = std::max(0, atoi(v.c_str()));
+    } else if (k == "ldg_below") {
+        t.ldgBelow = atof(v.c_str());
+    } else {
+        return false;
+    }
+    return true;
+}
+
 extern "C" {
 
 const char *mprg_version(void) { return "mpassit-rg 0.1 (sm_100a)"; }
@@ -85,6 +115,13 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
         MPRG_CUDA(cudaEventCreateWithFlags(&c->evDl, cudaEventDisableTiming));
         MPRG_CUDA(cudaMallocHost(&c->peekBuf, 256));
         if (const char *e = getenv("MPASSIT_GPU_ASYNC")) c->async = atoi(e) != 0;
+        // tuning knobs: the environment is read here, once; mprg_set_option changes them afterwards
+        for (const char *const *kv = (const char *const[]){"MPASSIT_GPU_ACC", "accumulate", "MPASSIT_GPU_APPLY", "apply",
+                                                           "MPASSIT_GPU_PIPE_MINB", "pipe_minb", "MPASSIT_GPU_STAGING", "staging",
+                                                           "MPASSIT_GPU_MINB", "cols_minb", "MPASSIT_UPLOAD_THREADS",
+                                                           "upload_threads", "MPASSIT_GPU_LDG_BELOW", "ldg_below", nullptr};
+             *kv; kv += 2)
+            if (const char *e = getenv(kv[0])) set_option(c, kv[1], e);
         for (int i = 0; i < mprg_ctx::kSlots; ++i) {
             MPRG_CUDA(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
             MPRG_CUDA(cudaEventCreateWithFlags(&c->evK[i], cudaEventDisableTiming));
@@ -192,6 +229,30 @@ int mprg_scratch(mprg_ctx *ctx, int slot, size_t bytes, void **ptr) {
 
 int mprg_has_rotation(const mprg_ctx *ctx) { return ctx && ctx->haveRot ? 1 : 0; }
 
+int mprg_set_option(mprg_ctx *ctx, const char *key, const char *value) {
+    MPRG_ENTER(ctx)
+    if (ctx->capturing) fail(45, "mprg_set_option: not while capturing a graph");
+    if (!set_option(ctx, key, value)) fail(59, "mprg_set_option: unknown option %s=%s", key ? key : "(null)", value ? value : "(null)");
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_get_option(const mprg_ctx *ctx, const char *key, char *value, size_t len) {
+    if (!ctx || !key || !value || !len) return 1;
+    const std::string k = key;
+    const mprg_tuning &t = ctx->tune;
+    std::string v;
+    if (k == "accumulate") v = t.acc64 ? "f64" : "f32";
+    else if (k == "apply") v = t.pipeOff ? "direct" : "pipe";
+    else if (k == "staging") v = t.staging == 0 ? "bulk" : t.staging == 1 ? "ldg" : "auto";
+    else if (k == "pipe_minb") v = std::to_string(t.pipeMinb);
+    else if (k == "cols_minb") v = std::to_string(t.colsMinb);
+    else if (k == "upload_threads") v = std::to_string(t.uploadThreads);
+    else if (k == "ldg_below") v = std::to_string(t.ldgBelow);
+    else return 59;
+    snprintf(value, len, "%s", v.c_str());
+    return 0;
+}
+
 int mprg_set_async(mprg_ctx *ctx, int on) {
     MPRG_ENTER(ctx)
     if (ctx->async && !on) {  // leaving asynchronous mode: drain what is in flight
@@ -250,6 +311,27 @@ int mprg_set_target(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const do
                     const double *lat_deg) {
     MPRG_ENTER(ctx)
     target_set(ctx, stagger, ni, nj, lon_deg, lat_deg);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_set_grid_kind(mprg_ctx *ctx, int kind) {
+    MPRG_ENTER(ctx)
+    if (kind != MPRG_GRID_NOPERI && kind != MPRG_GRID_1PERI_MONOPOLE) fail(58, "mprg_set_grid_kind: bad kind %d", kind);
+    if (kind != ctx->gridKind) {
+        if (ctx->capturing) fail(45, "mprg_set_grid_kind: not while capturing a graph");
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (auto it = ctx->routes.begin(); it != ctx->routes.end();) {  // grid-source routes depend on the topology
+            if (std::get<1>(it->first) == MPRG_SRC_GRID_CENTER) {
+                it->second->memoised = false;
+                if (it->second->refcount <= 0) delete it->second;
+                else ctx->imported.push_back(it->second);
+                it = ctx->routes.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        ctx->gridKind = kind;
+    }
     MPRG_LEAVE(ctx)
 }
 
@@ -402,7 +484,7 @@ static void upload_unpinned(mprg_ctx *ctx, void *dst_dev, const void *src_host, 
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     // three quarters of the cores, shared between the ranks of the box
     unsigned want = std::max(2u, hw * 3 / 4 / (unsigned)std::max(1, ctx->nranks));
-    if (const char *e = std::getenv("MPASSIT_UPLOAD_THREADS")) want = (unsigned)std::max(1, std::atoi(e));
+    if (ctx->tune.uploadThreads > 0) want = (unsigned)ctx->tune.uploadThreads;
     const unsigned nt = (unsigned)std::min<int64_t>(std::min<unsigned>(want, 16), nChunks);
     std::atomic<int64_t> next{0}, released{0};  // next chunk to claim; chunks whose slot is free again
     std::vector<std::atomic<int>> done(nChunks);

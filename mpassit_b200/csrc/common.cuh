@@ -144,10 +144,11 @@ struct mprg_route {
     int64_t nSrcRef = 0;       // distinct source entities referenced by the weights
     int64_t srcLo = 0, srcHi = 0;  // [srcLo, srcHi): smallest id range containing all of them
     int32_t tileEntriesMax = 0, tileUniqMax = 0;  // per 32-target tile: CSR entries / distinct columns
+    int32_t tileRunsMax = 0;                      // per tile: runs of consecutive column ids
     int32_t dstNi = 0;         // destination row length (tiles of the apply kernel never straddle rows)
     // tile schedule for the pipelined apply kernel (apply_pipe.cuh)
     mprg::DevBuf<int32_t> tileUPtr, tileUCols;
-    mprg::DevBuf<unsigned char> entrySlot;
+    mprg::DevBuf<unsigned char> entrySlot, tileURun;
     int64_t schedTiles = 0, schedCols = 0, schedRuns = 0;  // tiles, distinct columns and id-runs summed over tiles
     int32_t maxRow = 0;        // longest row
     bool uniform = false;      // every mapped row has exactly `maxRow` entries, stored ELL-like
@@ -167,8 +168,23 @@ struct mprg_graph {
     int64_t launches = 0;   // engine kernels inside
 };
 
+// Tuning knobs: read once from the environment at mprg_init, changed at run time with mprg_set_option
+// (never getenv on the launch path).
+struct mprg_tuning {
+    bool acc64 = false;        // MPASSIT_GPU_ACC=f64 | option "accumulate": fp32 fields accumulate (and rotate) in fp64, the reference's R8
+    bool pipeOff = false;      // MPASSIT_GPU_APPLY=direct | option "apply": register-gather kernels only
+    int pipeMinb = 0;          // MPASSIT_GPU_PIPE_MINB | option "pipe_minb": 4 / 5 resident CTAs per SM (0 = by shared memory)
+    int staging = -1;          // MPASSIT_GPU_STAGING=bulk|ldg|auto | option "staging": 0 bulk, 1 ldg, -1 by the route's run length
+    double ldgBelow = 2.5;     // option "ldg_below": auto staging picks LDG when columns / runs of the route is below this
+    int colsMinb = 3;          // MPASSIT_GPU_MINB | option "cols_minb": register cap of the fallback kernel
+    int uploadThreads = 0;     // MPASSIT_UPLOAD_THREADS | option "upload_threads" (0 = 3/4 of the cores / ranks)
+    bool overlapSmall = true;  // option "overlap_small": 2-D / soil launches run beside the column launch on a second stream
+};
+
 struct mprg_ctx {
     int device = 0, rank = 0, nranks = 1;
+    mprg_tuning tune;
+    int gridKind = MPRG_GRID_NOPERI;      // mprg_set_grid_kind: topology of the target grid as a regrid source
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t store_stream = nullptr;  // weight generation runs here, beside the copy-bound apply pipeline
@@ -183,6 +199,7 @@ struct mprg_ctx {
     std::vector<mprg_route *> imported;
     mprg::DevBuf<double> cosa, sina;  // CENTER, full grid
     mprg::DevBuf<double> rotc;        // [n][4] per-point rotation constants (sina, tana, 1/cosa, 1/(cosa + sina tana))
+    mprg::DevBuf<float> rotc32;       // the same rounded to fp32 (all-fp32 applies rotate in fp32)
     bool haveRot = false;
     int64_t launches = 0;
     double last_ms = 0.0;

@@ -62,13 +62,27 @@ __device__ bool quad_locate(const double *q0, const double *q1, const double *q2
     return true;
 }
 
-__global__ void k_quad_boxes(int32_t ni, int32_t nj, const double *__restrict__ sxyz, float *lo, float *hi) {
+// Topology of the source grid (mprg_set_grid_kind; model_grid.F90:684-703):
+//   nqi      quads per source row: ni - 1 (ESMF_GridCreateNoPeriDim) or ni (ESMF_GridCreate1PeriDim: the last quad
+//            joins column ni-1 to column 0 across the seam)
+//   caps     bit 0 / bit 1: this row block holds grid row 0 / the last grid row of a MONOPOLE grid, closed by the fan
+//            of triangles (pole, P_i, P_i+1) around ESMF's artificial pole node (polemethod ALLAVG: the centre of
+//            the row projected onto the sphere, value = average of the row)
+// Element ids (tie rule: smallest wins): quads j * nqi + i, then the south cap's triangles, then the north cap's.
+struct QuadTopo {
+    int32_t ni, nrows, nqi, caps;
+    const double *pole;  // [8]: south pole xyz, cos(cap radius), north pole xyz, cos(cap radius)
+};
+
+__global__ void k_quad_boxes(QuadTopo tp, const double *__restrict__ sxyz, float *lo, float *hi) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t nq = (int64_t)(ni - 1) * (nj - 1);
+    int64_t nq = (int64_t)tp.nqi * (tp.nrows - 1);
     if (q >= nq) return;
-    int32_t i = (int32_t)(q % (ni - 1)), j = (int32_t)(q / (ni - 1));
-    const double *p0 = sxyz + 3 * ((size_t)j * ni + i);
-    d3 a = ld3(p0), b = ld3(p0 + 3), c = ld3(p0 + 3 * ((size_t)ni + 1)), d = ld3(p0 + 3 * (size_t)ni);
+    const int32_t ni = tp.ni;
+    int32_t i = (int32_t)(q % tp.nqi), j = (int32_t)(q / tp.nqi);
+    int32_t i1 = (i + 1 == ni) ? 0 : i + 1;
+    const double *p0 = sxyz + 3 * ((size_t)j * ni + i), *p1 = sxyz + 3 * ((size_t)j * ni + i1);
+    d3 a = ld3(p0), b = ld3(p1), c = ld3(p1 + 3 * (size_t)ni), d = ld3(p0 + 3 * (size_t)ni);
     double e2 = fmax(fmax(fmax(dist2(a, b), dist2(b, c)), fmax(dist2(c, d), dist2(d, a))), fmax(dist2(a, c), dist2(b, d)));
     // points of the bilinear patch lie in the hull of the 4 corners: |x|^2 >= 1 - 3E^2/8
     double m = (1.0 - sqrt(fmax(0.0, 1.0 - 0.375 * e2))) * 1.01 + sqrt(e2) * 1e-9 + 1e-12;
@@ -81,11 +95,32 @@ __global__ void k_quad_boxes(int32_t ni, int32_t nj, const double *__restrict__ 
     h[2] = f_up(fmax(fmax(a.z, b.z), fmax(c.z, d.z)) + m);
 }
 
+// artificial pole nodes of a monopole grid: sequential sums in column order (the oracle's order), one thread
+__global__ void k_pole_nodes(QuadTopo tp, const double *__restrict__ sxyz, double *__restrict__ pole) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int side = 0; side < 2; ++side) {
+        double *o = pole + 4 * side;
+        o[0] = 0.0; o[1] = 0.0; o[2] = side ? 1.0 : -1.0; o[3] = 2.0;  // cos(radius) = 2: no cap
+        if (!(tp.caps & (1 << side))) continue;
+        const double *row = sxyz + 3 * (size_t)(side ? tp.nrows - 1 : 0) * tp.ni;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int32_t i = 0; i < tp.ni; ++i) { sx = sx + row[3 * (size_t)i]; sy = sy + row[3 * (size_t)i + 1]; sz = sz + row[3 * (size_t)i + 2]; }
+        const double inv = 1.0 / sqrt((sx * sx + sy * sy) + sz * sz);
+        const d3 pn{sx * inv, sy * inv, sz * inv};
+        double c = 1.0;
+        for (int32_t i = 0; i < tp.ni; ++i) { const double d = dot(pn, ld3(row + 3 * (size_t)i)); if (d < c) c = d; }
+        o[0] = pn.x; o[1] = pn.y; o[2] = pn.z; o[3] = c - 1e-9;
+    }
+}
+
+// Per destination point: ecol / ew, 4 wide.  Quad: columns (q0,q1,q2,q3), bilinear weights, cnt 4.  Cap triangle:
+// columns (P_i, P_i+1, first point of the pole row, -1), weights (a, b, ws, 0), cnt ni (expanded by k_compact4).
 __global__ void __launch_bounds__(128)
-k_bilinear_quad(BvhView bvh, int32_t ni, const double *__restrict__ sxyz, const double *__restrict__ dstXyz,
+k_bilinear_quad(BvhView bvh, QuadTopo tp, const double *__restrict__ sxyz, const double *__restrict__ dstXyz,
                 int64_t nDst, int32_t *__restrict__ ecol, double *__restrict__ ew, int32_t *__restrict__ cnt) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDst) return;
+    const int32_t ni = tp.ni;
     d3 p = ld3(dstXyz + 3 * t);
     double pp[3] = {p.x, p.y, p.z};
     int32_t best = -1;
@@ -94,33 +129,75 @@ k_bilinear_quad(BvhView bvh, int32_t ni, const double *__restrict__ sxyz, const 
         for (int s = s0; s < s1; ++s) {
             int32_t q = __ldg(bvh.primId + s);
             if (best >= 0 && q >= best) continue;  // smallest source element id wins
-            int32_t i = q % (ni - 1), j = q / (ni - 1);
-            const double *q0 = sxyz + 3 * ((size_t)j * ni + i);
+            int32_t i = q % tp.nqi, j = q / tp.nqi;
+            int32_t i1 = (i + 1 == ni) ? 0 : i + 1;
+            const double *q0 = sxyz + 3 * ((size_t)j * ni + i), *q1 = sxyz + 3 * ((size_t)j * ni + i1);
             double w[4];
-            if (quad_locate(q0, q0 + 3, q0 + 3 * ((size_t)ni + 1), q0 + 3 * (size_t)ni, pp, kTol, w)) {
+            if (quad_locate(q0, q1, q1 + 3 * (size_t)ni, q0 + 3 * (size_t)ni, pp, kTol, w)) {
                 best = q;
                 bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; bw[3] = w[3];
             }
         }
     });
     if (best >= 0) {
-        int32_t i = best % (ni - 1), j = best / (ni - 1);
-        int32_t b = j * ni + i;
-        ecol[4 * t + 0] = b; ecol[4 * t + 1] = b + 1; ecol[4 * t + 2] = b + ni + 1; ecol[4 * t + 3] = b + ni;
+        int32_t i = best % tp.nqi, j = best / tp.nqi;
+        int32_t i1 = (i + 1 == ni) ? 0 : i + 1;
+        int32_t b0 = j * ni + i, b1 = j * ni + i1;
+        ecol[4 * t + 0] = b0; ecol[4 * t + 1] = b1; ecol[4 * t + 2] = b1 + ni; ecol[4 * t + 3] = b0 + ni;
         for (int k = 0; k < 4; ++k) ew[4 * t + k] = bw[k];
         cnt[t] = 4;
     } else {
-        cnt[t] = 0;
+        // no quad took the point: the polar caps (their ids follow the quads'), first accepting triangle wins
+        int32_t cc[3] = {-1, -1, -1};
+        double cw[3] = {0.0, 0.0, 0.0};
+        bool got = false;
+        for (int side = 0; side < 2 && !got; ++side) {
+            if (!(tp.caps & (1 << side))) continue;
+            const d3 pn = ld3(tp.pole + 4 * side);
+            if (!(dot(p, pn) >= tp.pole[4 * side + 3])) continue;
+            const int32_t row = side ? tp.nrows - 1 : 0;
+            for (int32_t i = 0; i < ni && !got; ++i) {
+                const int32_t i1 = (i + 1 == ni) ? 0 : i + 1;
+                const int32_t a = row * ni + i, b = row * ni + i1;
+                double w[3];
+                if (tri_locate(pn, ld3(sxyz + 3 * (size_t)a), ld3(sxyz + 3 * (size_t)b), p, kTol, w)) {
+                    got = true;
+                    cc[0] = a; cc[1] = b; cc[2] = row * ni;
+                    cw[0] = w[1]; cw[1] = w[2]; cw[2] = w[0];
+                }
+            }
+        }
+        if (got) {
+            for (int k = 0; k < 3; ++k) { ecol[4 * t + k] = cc[k]; ew[4 * t + k] = cw[k]; }
+            ecol[4 * t + 3] = -1; ew[4 * t + 3] = 0.0;
+            cnt[t] = ni;
+        } else {
+            cnt[t] = 0;
+        }
     }
     if (t == 0) cnt[nDst] = 0;
 }
 
-__global__ void k_compact4(int64_t nDst, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ ecol,
+__global__ void k_compact4(int64_t nDst, int32_t ni, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ ecol,
                            const double *__restrict__ ew, int32_t *__restrict__ col, double *__restrict__ w) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDst) return;
     int32_t b = rowptr[t], e = rowptr[t + 1];
-    for (int k = 0; k < e - b; ++k) { col[b + k] = ecol[4 * t + k]; w[b + k] = ew[4 * t + k]; }
+    if (e - b == 4 && ecol[4 * t + 3] >= 0) {
+        for (int k = 0; k < 4; ++k) { col[b + k] = ecol[4 * t + k]; w[b + k] = ew[4 * t + k]; }
+    } else if (e > b) {
+        // cap row: the pole's value is the average of its row -> ws / ni on every point of the row, plus the
+        // triangle's weights on its two row points; ascending column order
+        const int32_t ca = ecol[4 * t], cb = ecol[4 * t + 1], base = ecol[4 * t + 2];
+        const double share = ew[4 * t + 2] / (double)ni;
+        for (int32_t i = 0; i < ni; ++i) {
+            double v = share;
+            if (base + i == ca) v = v + ew[4 * t];
+            if (base + i == cb) v = v + ew[4 * t + 1];
+            col[b + i] = base + i;
+            w[b + i] = v;
+        }
+    }
 }
 
 void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r) {
@@ -148,18 +225,25 @@ void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r) {
         return;
     }
     const double *sxyz = src.x() + 3 * src.slabOffset();
-    int64_t nq = (int64_t)(src.ni - 1) * (srows - 1);
+    const bool peri = ctx->gridKind == MPRG_GRID_1PERI_MONOPOLE;
+    DevBuf<double> pole(8);
+    QuadTopo tp;
+    tp.ni = src.ni; tp.nrows = srows; tp.nqi = peri ? src.ni : src.ni - 1;
+    tp.caps = peri ? ((src.j0 == 0 ? 1 : 0) | (src.j1 == src.nj ? 2 : 0)) : 0;
+    tp.pole = pole.p;
+    k_pole_nodes<<<1, 32, 0, ctx->stream>>>(tp, sxyz, pole.p);
+    ctx->launches++;
+    int64_t nq = (int64_t)tp.nqi * (srows - 1);
     DevBuf<float> lo(3 * nq), hi(3 * nq);
-    k_quad_boxes<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(src.ni, srows, sxyz, lo.p, hi.p);
+    k_quad_boxes<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(tp, sxyz, lo.p, hi.p);
     ctx->launches++;
     Bvh bvh;
     bvh_build_boxes(ctx, lo.p, hi.p, (int32_t)nq, bvh);
     DevBuf<int32_t> ecol(4 * n), cnt(n + 1);
     DevBuf<double> ew(4 * n);
     BvhView v{bvh.nodes.p, bvh.primId.p, bvh.nLeafNodes, bvh.nPrim};
-    k_bilinear_quad<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(v, src.ni, sxyz,
-                                                                          tg.x() + 3 * tg.slabOffset(), n, ecol.p,
-                                                                          ew.p, cnt.p);
+    k_bilinear_quad<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(v, tp, sxyz, tg.x() + 3 * tg.slabOffset(), n,
+                                                                          ecol.p, ew.p, cnt.p);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
     r->rowptr.alloc(n + 1);
@@ -169,7 +253,7 @@ void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r) {
     r->nnz = nnz;
     r->col.alloc(nnz > 0 ? nnz : 1);
     r->w.alloc(nnz > 0 ? nnz : 1);
-    k_compact4<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, r->rowptr.p, ecol.p, ew.p, r->col.p, r->w.p);
+    k_compact4<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, src.ni, r->rowptr.p, ecol.p, ew.p, r->col.p, r->w.p);
     ctx->launches++;
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
 }

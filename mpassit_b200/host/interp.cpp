@@ -109,6 +109,9 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
     }
     if (host_pass) mprg_set_async(ctx, 1);
     try {
+        // the target grid's topology decides how its centres act as a regrid SOURCE (centre -> edge staggering):
+        // ESMF_GridCreate1PeriDim + MONOPOLE for global targets, GridCreateNoPeriDim otherwise (model_grid.F90:684-703)
+        ck(ctx, mprg_set_grid_kind(ctx, cfg->is_regional ? MPRG_GRID_NOPERI : MPRG_GRID_1PERI_MONOPOLE), "GridCreate");
         int32_t do_u = 0, do_v = 0, u10 = -1, v10 = -1;
         mpassit_classify_fields(cfg, io, &do_u, &do_v, &u10, &v10);
         const int sdt = io->src_dtype, ddt = io->dst_dtype, mem = io->mem;
@@ -198,8 +201,9 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 if (io->hist_3d[i].klass == MPASSIT_CLASS_U) fu = &io->hist_3d[i];
                 if (io->hist_3d[i].klass == MPASSIT_CLASS_V) fv = &io->hist_3d[i];
             }
-            const char *acc_env = std::getenv("MPASSIT_GPU_ACC");
-            const bool chain64 = acc_env && (!std::strcmp(acc_env, "f64") || !std::strcmp(acc_env, "fp64"));
+            char accv[16] = "";
+            mprg_get_option(ctx, "accumulate", accv, sizeof accv);
+            const bool chain64 = !std::strcmp(accv, "f64");
             const int chain_dt = chain64 ? MPRG_F64 : ddt;
             const size_t chain_sz = chain_dt == MPRG_F64 ? 8 : 4;
             // Mass-point winds live on MPRG_CENTER_HALO rows: this rank's CENTER slab plus the one row

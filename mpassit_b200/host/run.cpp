@@ -297,6 +297,8 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         st.n_cells = nCells;
         tq = now_ms();
         target_job.get();  // rethrows what define_target threw
+        if (!dry)  // GridCreate1PeriDim (global) or GridCreateNoPeriDim (regional), model_grid.F90:684-703
+            ck(ctx, mprg_set_grid_kind(ctx, cfg.is_regional ? MPRG_GRID_NOPERI : MPRG_GRID_1PERI_MONOPOLE), "GridCreate");
         if (!dry)
             for (int s = 0; s < 4; ++s)
                 ck(ctx, mprg_set_target(ctx, staggers[s], ni[s], nj[s], lon[s].data(), lat[s].data()), "GridAddCoord");

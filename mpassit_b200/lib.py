@@ -21,11 +21,12 @@ SRC_MESH_ELEMENT, SRC_MESH_NODE, SRC_GRID_CENTER = 0, 1, 2
 CENTER, EDGE1, EDGE2, CORNER, CENTER_HALO = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
+GRID_NOPERI, GRID_1PERI_MONOPOLE = 0, 1
 EPI_NONE, EPI_ADD, EPI_MUL, EPI_ROT_U, EPI_ROT_V = 0, 1, 2, 3, 4
 
 EXPORTS = [
-    "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize", "mprg_set_async", "mprg_get_async", "mprg_download",
-    "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_get_slab", "mprg_store",
+    "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize", "mprg_set_async", "mprg_get_async", "mprg_set_option", "mprg_get_option", "mprg_download",
+    "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_set_grid_kind", "mprg_get_slab", "mprg_store",
     "mprg_release", "mprg_clear_routes", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
     "mprg_apply", "mprg_apply_ex", "mprg_apply_into", "mprg_put_slab", "mprg_ipc_export", "mprg_ipc_open", "mprg_ipc_close_all", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
     "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_capture_begin", "mprg_capture_end", "mprg_graph_launch", "mprg_graph_release", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
@@ -67,6 +68,9 @@ def load() -> C.CDLL:
     L.mprg_has_rotation.argtypes = [vp]
     L.mprg_set_mesh.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mprg_set_target.argtypes = [vp, C.c_int, i32, i32, vp, vp]
+    L.mprg_set_grid_kind.argtypes = [vp, C.c_int]
+    L.mprg_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.mprg_get_option.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
     L.mprg_get_slab.argtypes = [vp, C.c_int, C.POINTER(i32), C.POINTER(i32)]
     L.mprg_store.argtypes = [vp, C.c_int, C.c_int, C.c_int, pp]
     L.mprg_release.argtypes = [vp, vp]

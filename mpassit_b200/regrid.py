@@ -207,6 +207,22 @@ class Regridder:
         if stagger == CENTER:
             self.nSrc[SRC_GRID_CENTER] = nj * ni
 
+    def set_option(self, key: str, value) -> None:
+        """Tuning knob (include/mpassit_rg.h: mprg_set_option), e.g. ("accumulate", "f64"), ("staging", "ldg")."""
+        self._ck(self.L.mprg_set_option(self.ctx, key.encode(), str(value).encode()))
+
+    def get_option(self, key: str) -> str:
+        import ctypes as C
+        buf = C.create_string_buffer(64)
+        rc = self.L.mprg_get_option(self.ctx, key.encode(), buf, len(buf))
+        if rc:
+            raise KeyError(key)
+        return buf.value.decode()
+
+    def set_grid_kind(self, kind: int) -> None:
+        """ESMF_GridCreateNoPeriDim (0) or ESMF_GridCreate1PeriDim + MONOPOLE (1), model_grid.F90:684-703."""
+        self._ck(self.L.mprg_set_grid_kind(self.ctx, int(kind)))
+
     def slab(self, stagger: int) -> tuple[int, int]:
         j0, j1 = C.c_int32(), C.c_int32()
         self._ck(self.L.mprg_get_slab(self.ctx, stagger, C.byref(j0), C.byref(j1)))

@@ -182,6 +182,92 @@ def icosahedral_points(level: int) -> np.ndarray:
     return v
 
 
+def geodesic_mesh_points(freq: int):
+    """Class-I geodesic subdivision of the icosahedron at frequency `freq` (every edge cut into `freq` parts):
+    10 freq^2 + 2 points and their 20 freq^2 triangles, written down analytically -- no O(n log n) hull, so the
+    6.5 M-cell mesh of BASELINE.json configs[3] (freq = 806) takes seconds instead of minutes.  Point ids: the
+    12 corners, then the interior points of the 30 edges, then the interior points of the 20 faces row by row
+    (spatially coherent, like an MPAS mesh ordered by its generator)."""
+    t = (1.0 + math.sqrt(5.0)) / 2.0
+    v = _unit(np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t],
+                        [0, -1, -t], [0, 1, -t], [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64))
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4],
+                  [11, 10, 2], [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8],
+                  [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    n = int(freq)
+    edges = {}
+    for a, b, c in f.tolist():
+        for x, y in ((a, b), (a, c), (b, c)):
+            edges.setdefault((min(x, y), max(x, y)), len(edges))
+    ne, T = len(edges), (n - 1) * (n - 2) // 2
+    e0, f0 = 12, 12 + ne * (n - 1)
+    npts = f0 + 20 * T
+    pts = np.empty((npts, 3), np.float64)
+    pts[:12] = v
+    k = np.arange(1, n, dtype=np.float64)[:, None] / n
+    for (a, b), e in edges.items():                      # edge points from the smaller corner id: shared by both faces
+        pts[e0 + e * (n - 1): e0 + (e + 1) * (n - 1)] = v[a] + k * (v[b] - v[a])
+    I, J = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    inside = (I >= 1) & (J >= 1) & (I + J <= n - 1)
+    # interior index of (i, j): rows j = 1 .. n-2, each with n-1-j points i = 1 .. n-1-j
+    row0 = np.concatenate([[0], np.cumsum(n - 1 - np.arange(1, n - 1))])[:-1] if n > 2 else np.zeros(0, np.int64)
+    tris = []
+    for fi, (a, b, c) in enumerate(f.tolist()):
+        ids = np.full((n + 1, n + 1), -1, np.int64)
+        if T:
+            ii, jj = I[inside], J[inside]
+            loc = row0[jj - 1] + (ii - 1)
+            ids[ii, jj] = f0 + fi * T + loc
+            pts[f0 + fi * T + loc] = v[a] + (ii[:, None] / n) * (v[b] - v[a]) + (jj[:, None] / n) * (v[c] - v[a])
+        ids[0, 0], ids[n, 0], ids[0, n] = a, b, c
+
+        def edge_ids(x, y, par):       # par = steps from x towards y, 1 .. n-1
+            e = edges[(min(x, y), max(x, y))]
+            kk = par if x < y else n - par
+            return e0 + e * (n - 1) + (kk - 1)
+
+        m = np.arange(1, n)
+        ids[m, 0] = edge_ids(a, b, m)
+        ids[0, m] = edge_ids(a, c, m)
+        ids[n - m, m] = edge_ids(b, c, m)
+        up = (I + J <= n - 1) & (I < n) & (J < n)
+        iu, ju = I[up], J[up]
+        tris.append(np.stack([ids[iu, ju], ids[iu + 1, ju], ids[iu, ju + 1]], 1))
+        dn = (I + J <= n - 2) & (I < n) & (J < n)
+        idn, jdn = I[dn], J[dn]
+        tris.append(np.stack([ids[idn + 1, jdn], ids[idn + 1, jdn + 1], ids[idn, jdn + 1]], 1))
+    return _unit(pts), np.concatenate(tris, 0)
+
+
+def schmidt_focus(xyz: np.ndarray, focus_lat: float, focus_lon: float, spacing_ratio: float) -> np.ndarray:
+    """Schmidt transformation (sin lat' = (D + sin lat) / (1 + D sin lat), D = (r - 1) / (r + 1)) followed by a
+    rotation of the pole onto the focus.  It is a Moebius map of the sphere: circles go to circles, so the
+    (spherical) Delaunay triangulation of the points is unchanged."""
+    D = (spacing_ratio - 1.0) / (spacing_ratio + 1.0)
+    z = xyz[:, 2]
+    z2 = (D + z) / (1.0 + D * z)
+    s = np.sqrt(np.maximum(0.0, 1.0 - z2 * z2)) / np.sqrt(np.maximum(1e-300, 1.0 - z * z))
+    p = np.stack([xyz[:, 0] * s, xyz[:, 1] * s, z2], axis=1)
+    la, lo = math.radians(focus_lat), math.radians(focus_lon)
+    ez = np.array([math.cos(la) * math.cos(lo), math.cos(la) * math.sin(lo), math.sin(la)])
+    ex = _unit(np.cross([0.0, 0.0, 1.0], ez)[None, :])[0]
+    ey = np.cross(ez, ex)
+    return _unit(p[:, :1] * ex + p[:, 1:2] * ey + p[:, 2:] * ez)
+
+
+def variable_geodesic_mesh(freq: int = 806, focus_lat: float = 38.5, focus_lon: float = -97.5,
+                           spacing_ratio: float = 5.0, max_edges: int = 10) -> MpasMesh:
+    """BASELINE.json configs[3] at its stated size: freq = 806 -> 6,496,362 cells ("~6.5 M"), spacing graded 5:1
+    (15 km -> 3 km) towards CONUS.  Topology from geodesic_mesh_points, geometry through schmidt_focus."""
+    xyz, tri = geodesic_mesh_points(freq)
+    # a tiny rotation first so that no icosahedron corner sits exactly on the Schmidt axis
+    c, s_ = math.cos(0.3), math.sin(0.3)
+    xyz = np.stack([xyz[:, 0], c * xyz[:, 1] - s_ * xyz[:, 2], s_ * xyz[:, 1] + c * xyz[:, 2]], 1)
+    p = schmidt_focus(xyz, focus_lat, focus_lon, spacing_ratio)
+    return mesh_from_triangulation(p, tri, keep=np.ones(p.shape[0], bool), max_edges=max_edges,
+                                   meta={"kind": "global-geodesic-variable", "freq": freq, "spacing_ratio": spacing_ratio})
+
+
 def _sphere_delaunay(xyz: np.ndarray) -> np.ndarray:
     from scipy.spatial import ConvexHull
 

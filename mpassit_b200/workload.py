@@ -8,6 +8,11 @@ BASELINE.json configs:
   c1  120-km quasi-uniform global mesh (40,962 cells, 55 levels) -> 1 deg lat-lon
   c2  3-km regional mesh (~2.4 M cells, 60 levels) -> Lambert 1801 x 1061, dx = 3 km,
       diaglist + histlist_2d/3d/soil  (the configuration the metric is quoted on)
+  c3  the c2 geometry with every 3-D + soil field stacked into ONE batched apply on the bilinear route:
+      11 x 60 + 2 x 61 + 2 x 60 + 3 x 4 = 914 level-columns (stacked_fields / run_stacked)
+  c4  15-3 km variable-resolution global mesh (6,496,362 cells) -> 0.03 deg global lat-lon (12000 x 6000),
+      one bilinear 55-level field + one nearest-neighbour integer field (CENTER stagger only)
+  c5  1-km regional mesh -> 1-km Lambert 1001 x 1001, conservative snow fields, weights rebuilt per run
   mini  a 30-km, 8-level miniature of c2 (smoke / tests)
 """
 from __future__ import annotations
@@ -77,6 +82,18 @@ def make(name: str = "c2", rundir: str | None = None, seed: int = synth.SEED, ce
     """cell_order (or $MPASSIT_CELL_ORDER): rowmajor (as generated) | morton | random -- see synth.renumber_cells."""
     rundir = rundir or tempfile.mkdtemp(prefix=f"mpassit_{name}_")
     cell_order = cell_order or os.environ.get("MPASSIT_CELL_ORDER", "rowmajor")
+    if name == "c4":
+        mesh = synth.variable_geodesic_mesh(int(os.environ.get("MPASSIT_C4_FREQ", "806")))
+        nl = os.path.join(rundir, "namelist.input")
+        with open(nl, "w") as fh:
+            fh.write("&config\n target_grid_type = 'lat-lon'\n nx = 12001\n ny = 6001\n is_regional = .false.\n"
+                     " stand_lon = -180.\n interp_diag = .false.\n interp_hist = .true.\n wrf_mod_vars = .false.\n/\n")
+        paths = defaults.write_varlists(rundir)
+        cfg = host.read_setup_namelist(nl)
+        # only the CENTER stagger is needed (one bilinear 3-D field + one nearest 2-D field): 72 M points
+        grids = {"M": host.target_coords(cfg, L.CENTER)}
+        lists = {"diag": [], "hist_2d": [("ivgtyp", "IVGTYP")], "hist_3d": [("theta", "T")], "soil": []}
+        return Workload(name, cfg, mesh, grids, None, None, 55, 4, rundir, lists)
     if name == "c1":
         mesh = synth.global_mesh(40962)
         nl = os.path.join(rundir, "namelist.input")
@@ -85,7 +102,7 @@ def make(name: str = "c2", rundir: str | None = None, seed: int = synth.SEED, ce
                      " stand_lon = -180.\n interp_diag = .false.\n interp_hist = .true.\n wrf_mod_vars = .true.\n/\n")
         nz, nsoil = 55, 4
     else:
-        mk, nk, nz, nsoil = _SPECS[name]
+        mk, nk, nz, nsoil = _SPECS["c2" if name == "c3" else name]
         mesh = synth.renumber_cells(synth.regional_hex_mesh(seed=seed, **mk), cell_order, seed)
         nl = defaults.write_namelist(os.path.join(rundir, "namelist.input"), **nk)
     paths = defaults.write_varlists(rundir)
@@ -105,7 +122,10 @@ def load_geometry(rg, wl: Workload) -> None:
     """mprg_set_mesh + mprg_set_target for every stagger (define_input_grid / define_target_grid)."""
     m = wl.mesh
     rg.set_mesh(m.lonCell, m.latCell, m.lonVertex, m.latVertex, m.verticesOnCell)
+    rg.set_grid_kind(L.GRID_NOPERI if wl.cfg.is_regional else L.GRID_1PERI_MONOPOLE)   # model_grid.F90:684-703
     for k, s in (("M", L.CENTER), ("U", L.EDGE1), ("V", L.EDGE2), ("CORNER", L.CORNER)):
+        if k not in wl.grids:
+            continue
         lat, lon = wl.grids[k]
         rg.set_target(s, lon, lat)
     if wl.cosa is not None:  # cosa/sina_target_grid, model_grid.F90:1113-1185
@@ -182,6 +202,29 @@ def make_fields(wl: Workload, device="cuda", pinned_host: bool = False, rg=None)
         groups.update(extra)
         out[where] = groups
     return out
+
+
+def stacked_fields(wl: Workload) -> list[tuple[str, int]]:
+    """BASELINE.json configs[2]: every histlist_3d field (winds included, as plain fields) and every histlist_soil
+    field in ONE batched apply on the bilinear route: (name, levels); 914 level-columns on the stock lists."""
+    return ([(nm, wl.levels_of("hist_3d", nm)) for nm, _ in wl.lists["hist_3d"]] +
+            [(nm, wl.nsoil) for nm, _ in wl.lists["soil"]])
+
+
+def make_stacked(wl: Workload, device="cuda"):
+    """(names, sources [nCells][nlev], destinations [nlev][nMass]) of the c3 stack, on `device`."""
+    import torch
+
+    names, srcs, dsts = [], [], []
+    for k, (nm, nlev) in enumerate(stacked_fields(wl)):
+        grp = "hist_3d" if k < len(wl.lists["hist_3d"]) else "soil"
+        src = _field_values_torch(wl, grp, nm, nlev, k, device)
+        if grp == "soil":   # bilinear here: use smooth values, not class labels
+            src = _field_values_torch(wl, "hist_3d", "soil_" + nm, nlev, 50 + k, device)
+        names.append(nm)
+        srcs.append(src)
+        dsts.append(torch.empty((nlev, wl.n_mass), dtype=torch.float32, device=device))
+    return names, srcs, dsts
 
 
 def _np(x):

@@ -19,7 +19,7 @@
  * Each function cites the reference call site (file:line under /root/reference)
  * whose ESMF call it stands in for.
  *
- * Build: see oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off -shared).
+ * Build: see oracle/Makefile (gcc -O3 -march=x86-64-v3 -fopenmp -ffp-contract=off -shared).
  * -ffp-contract=off matters: index/mask decisions must not depend on FMA
  * contraction so that a GPU build with -fmad=false reproduces them bit-exactly.
  */
@@ -519,24 +519,65 @@ static int quad_locate(const double *q0, const double *q1, const double *q2, con
     return 1;
 }
 
+/* Grid topology of the centre -> edge source grid (the reference's target_grid):
+ *   ORC_TOPO_NOPERI  ESMF_GridCreateNoPeriDim (model_grid.F90:698-703, regional targets): (ni-1) x (nj-1) quads;
+ *   ORC_TOPO_PERI    bit 0: ESMF_GridCreate1PeriDim(periodicDim=1) (model_grid.F90:684-696, is_regional=.false.):
+ *                    ni quads per row, the last one joins column ni-1 to column 0 across the seam;
+ *   ORC_TOPO_SPOLE / ORC_TOPO_NPOLE  bits 1, 2: polekindflag = MONOPOLE at the bottom / top row of THIS row block
+ *                    (a row block carries the cap only when it holds grid row 0 / nj-1).  ESMF's default
+ *                    polemethod (ALLAVG) closes the grid with an artificial pole node "in the centre of the row,
+ *                    projected onto the sphere", whose value is the average of the row's ni values; the cap is
+ *                    the fan of triangles (pole, P_i, P_i+1).  A destination point inside cap triangle i with
+ *                    triangle weights (ws, a, b) therefore has ni entries: ws/ni on every point of the row, plus
+ *                    a on P_i and b on P_i+1.
+ * Element ids (tie rule: smallest id wins): quads j*nqi + i, then the south cap's triangles, then the north cap's.
+ * Output stays 4 wide: quads -> col = (q0,q1,q2,q3), w = bilinear weights; cap triangles -> elem >= nquads,
+ * col = (P_i, P_i+1, first point of the pole row, -1), w = (a, b, ws, 0): orc.quadgrid_to_csr expands them. */
+#define ORC_TOPO_PERI 1
+#define ORC_TOPO_SPOLE 2
+#define ORC_TOPO_NPOLE 4
+
 typedef struct {
     const double *sxyz;
-    int32_t ni, nj;
+    int32_t ni, nj, nqi, topo;
+    int64_t nquads;
+    const double *spole, *npole;
     const double *p;
     int64_t best;
+    int32_t col[4];
     double w[4];
 } quad_ctx;
 
 static void quad_try(int32_t i, int32_t j, quad_ctx *c) {
-    if (i < 0 || j < 0 || i >= c->ni - 1 || j >= c->nj - 1) return;
-    int64_t id = (int64_t)j * (c->ni - 1) + i;
+    if (c->topo & ORC_TOPO_PERI) i = (i % c->ni + c->ni) % c->ni;
+    if (i < 0 || j < 0 || i >= c->nqi || j >= c->nj - 1) return;
+    int64_t id = (int64_t)j * c->nqi + i;
     if (c->best >= 0 && id >= c->best) return;
-    const double *q0 = c->sxyz + 3 * ((int64_t)j * c->ni + i);
-    const double *q1 = q0 + 3, *q3 = q0 + 3 * (int64_t)c->ni, *q2 = q3 + 3;
+    int32_t i1 = (i + 1 == c->ni) ? 0 : i + 1;
+    int32_t b0 = j * c->ni + i, b1 = j * c->ni + i1;
+    const double *q0 = c->sxyz + 3 * (int64_t)b0, *q1 = c->sxyz + 3 * (int64_t)b1;
+    const double *q3 = q0 + 3 * (int64_t)c->ni, *q2 = q1 + 3 * (int64_t)c->ni;
     double w[4];
     if (quad_locate(q0, q1, q2, q3, c->p, w)) {
         c->best = id;
+        c->col[0] = b0; c->col[1] = b1; c->col[2] = b1 + c->ni; c->col[3] = b0 + c->ni;
         for (int k = 0; k < 4; ++k) c->w[k] = w[k];
+    }
+}
+/* cap triangle i of the south (north = 0) or north (north = 1) pole */
+static void cap_try(int32_t i, int north, quad_ctx *c) {
+    if (!(c->topo & (north ? ORC_TOPO_NPOLE : ORC_TOPO_SPOLE))) return;
+    i = (i % c->ni + c->ni) % c->ni;
+    int64_t id = c->nquads + ((north && (c->topo & ORC_TOPO_SPOLE)) ? c->ni : 0) + i;
+    if (c->best >= 0 && id >= c->best) return;
+    int32_t row = north ? c->nj - 1 : 0;
+    int32_t i1 = (i + 1 == c->ni) ? 0 : i + 1;
+    int32_t a = row * c->ni + i, b = row * c->ni + i1;
+    double w[3];
+    if (tri_locate(north ? c->npole : c->spole, c->sxyz + 3 * (int64_t)a, c->sxyz + 3 * (int64_t)b, c->p, w)) {
+        c->best = id;
+        c->col[0] = a; c->col[1] = b; c->col[2] = row * c->ni; c->col[3] = -1;
+        c->w[0] = w[1]; c->w[1] = w[2]; c->w[2] = w[0]; c->w[3] = 0.0;
     }
 }
 static void quad_visit_point(int32_t pt, void *vctx) {
@@ -548,19 +589,32 @@ static void quad_visit_point(int32_t pt, void *vctx) {
     quad_try(i, j, c);
 }
 
-/* elem = winning quad id or -1; col [nDst][4] = source point ids (j*ni+i) of
- * (q0,q1,q2,q3); w [nDst][4]. */
-int orc_bilinear_quadgrid(int32_t ni, int32_t nj, const double *sxyz, int64_t nDst, const double *dxyz,
-                          int64_t *elem, int32_t *col, double *w, int brute) {
+/* artificial pole node: centre of the row's points, projected onto the unit sphere */
+static void pole_node(const double *row, int32_t ni, double *out) {
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int32_t i = 0; i < ni; ++i)
+        for (int d = 0; d < 3; ++d) s[d] = s[d] + row[3 * (int64_t)i + d];
+    double inv = 1.0 / sqrt(dot3(s, s));
+    for (int d = 0; d < 3; ++d) out[d] = s[d] * inv;
+}
+
+/* elem = winning element id or -1; col [nDst][4], w [nDst][4] as described above. */
+int orc_bilinear_quadgrid_topo(int32_t ni, int32_t nj, const double *sxyz, int64_t nDst, const double *dxyz,
+                               int64_t *elem, int32_t *col, double *w, int brute, int topo) {
     if (ni < 2 || nj < 2) return -1;
+    const int32_t nqi = (topo & ORC_TOPO_PERI) ? ni : ni - 1;
+    double spole[3] = {0, 0, -1}, npole[3] = {0, 0, 1};
+    if (topo & ORC_TOPO_SPOLE) pole_node(sxyz, ni, spole);
+    if (topo & ORC_TOPO_NPOLE) pole_node(sxyz + 3 * (int64_t)(nj - 1) * ni, ni, npole);
     kdtree *t = NULL;
     double r2 = 0.0;
     if (!brute) {
         double m2 = 0.0;
         for (int32_t j = 0; j < nj - 1; ++j)
-            for (int32_t i = 0; i < ni - 1; ++i) {
-                const double *q0 = sxyz + 3 * ((int64_t)j * ni + i);
-                double d1 = dist2(q0, q0 + 3 * ((int64_t)ni + 1)), d2 = dist2(q0 + 3, q0 + 3 * (int64_t)ni);
+            for (int32_t i = 0; i < nqi; ++i) {
+                int32_t i1 = (i + 1 == ni) ? 0 : i + 1;
+                const double *q0 = sxyz + 3 * ((int64_t)j * ni + i), *q1 = sxyz + 3 * ((int64_t)j * ni + i1);
+                double d1 = dist2(q0, q1 + 3 * (int64_t)ni), d2 = dist2(q1, q0 + 3 * (int64_t)ni);
                 if (d1 > m2) m2 = d1;
                 if (d2 > m2) m2 = d2;
             }
@@ -568,29 +622,45 @@ int orc_bilinear_quadgrid(int32_t ni, int32_t nj, const double *sxyz, int64_t nD
         r2 = r * r;
         t = kd_build(ni * nj, sxyz);
     }
+    /* polar caps: a destination point within the cap's angular radius (+ margin) tries every cap triangle */
+    double scap = 2.0, ncap = 2.0; /* cos of the cap radius; 2 = no cap */
+    if (topo & ORC_TOPO_SPOLE) {
+        scap = 1.0;
+        for (int32_t i = 0; i < ni; ++i) { double d = dot3(spole, sxyz + 3 * (int64_t)i); if (d < scap) scap = d; }
+        scap -= 1e-9;
+    }
+    if (topo & ORC_TOPO_NPOLE) {
+        ncap = 1.0;
+        for (int32_t i = 0; i < ni; ++i) { double d = dot3(npole, sxyz + 3 * ((int64_t)(nj - 1) * ni + i)); if (d < ncap) ncap = d; }
+        ncap -= 1e-9;
+    }
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t n = 0; n < nDst; ++n) {
         quad_ctx c;
-        c.sxyz = sxyz; c.ni = ni; c.nj = nj; c.p = dxyz + 3 * n; c.best = -1;
-        c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.0;
+        c.sxyz = sxyz; c.ni = ni; c.nj = nj; c.nqi = nqi; c.topo = topo; c.nquads = (int64_t)nqi * (nj - 1);
+        c.spole = spole; c.npole = npole;
+        c.p = dxyz + 3 * n; c.best = -1;
+        for (int k = 0; k < 4; ++k) { c.w[k] = 0.0; c.col[k] = -1; }
         if (brute) {
             for (int32_t j = 0; j < nj - 1; ++j)
-                for (int32_t i = 0; i < ni - 1; ++i) quad_try(i, j, &c);
+                for (int32_t i = 0; i < nqi; ++i) quad_try(i, j, &c);
         } else {
             kd_radius_rec(t, 0, ni * nj, c.p, r2, quad_visit_point, &c);
         }
-        elem[n] = c.best;
-        if (c.best >= 0) {
-            int32_t i = (int32_t)(c.best % (ni - 1)), j = (int32_t)(c.best / (ni - 1));
-            int32_t b = j * ni + i;
-            col[4 * n + 0] = b; col[4 * n + 1] = b + 1; col[4 * n + 2] = b + ni + 1; col[4 * n + 3] = b + ni;
-            for (int k = 0; k < 4; ++k) w[4 * n + k] = c.w[k];
-        } else {
-            for (int k = 0; k < 4; ++k) { col[4 * n + k] = -1; w[4 * n + k] = 0.0; }
+        if (c.best < 0) { /* quads have the smaller ids: caps are tried only when no quad accepted the point */
+            if (dot3(c.p, spole) >= scap) for (int32_t i = 0; i < ni; ++i) cap_try(i, 0, &c);
+            if (c.best < 0 && dot3(c.p, npole) >= ncap) for (int32_t i = 0; i < ni; ++i) cap_try(i, 1, &c);
         }
+        elem[n] = c.best;
+        for (int k = 0; k < 4; ++k) { col[4 * n + k] = c.col[k]; w[4 * n + k] = c.best >= 0 ? c.w[k] : 0.0; }
     }
     if (t) kd_free(t);
     return 0;
+}
+
+int orc_bilinear_quadgrid(int32_t ni, int32_t nj, const double *sxyz, int64_t nDst, const double *dxyz,
+                          int64_t *elem, int32_t *col, double *w, int brute) {
+    return orc_bilinear_quadgrid_topo(ni, nj, sxyz, nDst, dxyz, elem, col, w, brute, 0);
 }
 
 /* Level-slowest source variant of the apply (source is itself a [lev][plane]

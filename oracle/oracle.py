@@ -57,6 +57,8 @@ def lib():
         _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
         L.orc_bilinear_quadgrid.argtypes = [C.c_int32, C.c_int32, _f64p, C.c_int64, _f64p, _i64p, _i32p, _f64p, C.c_int]
         L.orc_bilinear_quadgrid.restype = C.c_int
+        L.orc_bilinear_quadgrid_topo.argtypes = [C.c_int32, C.c_int32, _f64p, C.c_int64, _f64p, _i64p, _i32p, _f64p, C.c_int, C.c_int]
+        L.orc_bilinear_quadgrid_topo.restype = C.c_int
         L.orc_apply_planes_f64.argtypes = [C.c_int64, _i32p, _i32p, _f64p, C.c_int32, C.c_int64, _f64p, _f64p]
         L.orc_conserve.argtypes = [C.c_int32, _f64p, _f64p, C.c_int32, _i32p, C.c_int32, C.c_int32, _f64p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -174,8 +176,14 @@ def rotate_winds(u, v, cosa, sina):
     return u, v
 
 
-def bilinear_quadgrid(src_xyz_grid, dst_xyz, brute=False):
-    """src_xyz_grid [nj][ni][3] (CENTER points) -> (elem, col [n][4], w [n][4])."""
+TOPO_PERI, TOPO_SPOLE, TOPO_NPOLE = 1, 2, 4
+
+
+def bilinear_quadgrid(src_xyz_grid, dst_xyz, brute=False, topo=0):
+    """src_xyz_grid [nj][ni][3] (CENTER points) -> (elem, col [n][4], w [n][4]).
+    topo: 0 = ESMF_GridCreateNoPeriDim; TOPO_PERI (| TOPO_SPOLE | TOPO_NPOLE) = ESMF_GridCreate1PeriDim with monopole
+    caps at the bottom / top row of this block (model_grid.F90:684-696).  Cap rows come back 4 wide (see
+    mpassit_oracle.c); quadgrid_csr expands them."""
     src = np.ascontiguousarray(src_xyz_grid, np.float64)
     nj, ni = src.shape[0], src.shape[1]
     dst = np.ascontiguousarray(dst_xyz, np.float64).reshape(-1, 3)
@@ -183,10 +191,38 @@ def bilinear_quadgrid(src_xyz_grid, dst_xyz, brute=False):
     elem = np.empty(n, np.int64)
     col = np.empty((n, 4), np.int32)
     w = np.empty((n, 4), np.float64)
-    rc = lib().orc_bilinear_quadgrid(ni, nj, src.reshape(-1, 3), n, dst, elem, col, w, int(brute))
+    rc = lib().orc_bilinear_quadgrid_topo(ni, nj, src.reshape(-1, 3), n, dst, elem, col, w, int(brute), int(topo))
     if rc != 0:
         raise ValueError(f"orc_bilinear_quadgrid rc={rc}")
     return elem, col, w
+
+
+def quadgrid_csr(ni, nj, elem, col, w, topo=0):
+    """CSR of a centre -> edge matrix.  Quad rows: 4 entries.  Monopole-cap rows (elem >= number of quads): the
+    artificial pole's value is the average of its row, so the row holds ni entries ws/ni, plus a and b on the
+    cap triangle's two row points -- emitted in ascending column order."""
+    n = elem.shape[0]
+    nquads = (ni if topo & TOPO_PERI else ni - 1) * (nj - 1)
+    cap = elem >= nquads
+    cnt = np.where(elem < 0, 0, np.where(cap, ni, 4)).astype(np.int64)
+    rowptr = np.zeros(n + 1, np.int32)
+    np.cumsum(cnt, out=rowptr[1:])
+    C = np.empty(int(rowptr[-1]), np.int32)
+    W = np.empty(int(rowptr[-1]), np.float64)
+    q = np.flatnonzero((elem >= 0) & ~cap)
+    idx = rowptr[q][:, None] + np.arange(4)[None, :]
+    C[idx] = col[q]
+    W[idx] = w[q]
+    for t in np.flatnonzero(cap):
+        base = int(col[t, 2])
+        a_col, b_col, a, b, ws = int(col[t, 0]), int(col[t, 1]), w[t, 0], w[t, 1], w[t, 2]
+        cc = base + np.arange(ni, dtype=np.int32)
+        ww = np.full(ni, ws / ni)
+        ww[a_col - base] = ww[a_col - base] + a
+        ww[b_col - base] = ww[b_col - base] + b
+        C[rowptr[t]:rowptr[t + 1]] = cc
+        W[rowptr[t]:rowptr[t + 1]] = ww
+    return rowptr, C, W
 
 
 def apply_planes(rowptr, col, w, src_planes):

@@ -2,7 +2,7 @@
 
   python profiles/kbench.py [--config c2] [--variants f64:3,f64:2,f32:4] [--iters 5] [--only-3d]
 
-Builds the workload once, then for every variant (accumulate type : compiled CTAs/SM)
+Builds the workload once, then for every variant (accumulate type : staging mode [b<CTAs/SM>])
 runs the bilinear-route stacked apply over the 3-D fields and prints per-kernel GB/s
 from the engine's per-launch CUDA events.  Also used as the short command under ncu.
 """
@@ -21,13 +21,13 @@ from mpassit_b200 import lib as L  # noqa: E402
 from mpassit_b200 import workload  # noqa: E402
 from mpassit_b200.regrid import Regridder  # noqa: E402
 
-KIND = {0: "cols_vec", 1: "cols_scalar", 2: "flat", 3: "planes"}
+KIND = {0: "pipe", 1: "cols_fallback", 2: "flat", 3: "planes"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--variants", default="f32:p2b4,f32:p2b5,f32:p3b4,f64:p2")
+    ap.add_argument("--variants", default="f32:bulk,f32:ldg,f64:bulk,f64:ldg")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--fields", type=int, default=12, help="number of stacked nz-level fields")
     ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
@@ -58,26 +58,25 @@ def main():
     import ctypes
     em, um = ctypes.c_int32(), ctypes.c_int32()
     rg.L.mprg_debug_route_tiles(ctypes.c_void_p(route.handle), ctypes.byref(em), ctypes.byref(um))
-    print(f"setup {time.time() - t0:.1f}s  route {info} tile entries max {em.value} uniq max {um.value}", file=sys.stderr)
+    print(f"setup {time.time() - t0:.1f}s  order {args.order} route {info} tile entries max {em.value} uniq max {um.value}", file=sys.stderr)
     peak = 6450.0
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
     for var in args.variants.split(","):
-        acc, mode = var.split(":")          # f32:p2 / f32:p2b5 (TMA-bulk pipeline, 2 stages[, 5 CTAs/SM]) f32:d3 (register gathers)
-        os.environ["MPASSIT_GPU_ACC"] = acc
-        if mode[0] == "p":
-            os.environ["MPASSIT_GPU_APPLY"] = "pipe"
-            st, _, mb = mode[1:].partition("b")
-            os.environ["MPASSIT_GPU_STAGES"] = st or "0"
-            if mb:
-                os.environ["MPASSIT_GPU_PIPE_MINB"] = mb
-            else:
-                os.environ.pop("MPASSIT_GPU_PIPE_MINB", None)
+        # accumulate : staging [b4|b5]   e.g. f32:bulk  f32:ldg  f64:bulk  f32:bulkb4  f32:direct
+        acc, mode = var.split(":")
+        rg.set_option("accumulate", acc)
+        mb = ""
+        if "b" in mode[1:] and mode[-2] == "b":
+            mode, mb = mode[:-2], mode[-1]
+        rg.set_option("pipe_minb", mb or "0")
+        if mode == "direct":
+            rg.set_option("apply", "direct")
         else:
-            os.environ["MPASSIT_GPU_APPLY"] = "direct"
-            os.environ["MPASSIT_GPU_MINB"] = mode[1:] or "3"
+            rg.set_option("apply", "pipe")
+            rg.set_option("staging", mode)
         for _ in range(2):
             rg.apply(route, srcs, dsts, nlev=levs, epi_op=epi)
         rg.profile(True)
@@ -91,7 +90,7 @@ def main():
             k[0] += r["ms"]; k[1] += r["alg_bytes"]; k[2] += 1
         for k, (ms, by, cnt) in out.items():
             gbs = by / (ms * 1e-3) / 1e9
-            print(f"{var:8s} {k:12s} {args.stack or f'{nlev}x{args.fields}':>14s}: {ms / cnt:8.3f} ms/launch  {gbs:8.1f} GB/s  "
+            print(f"{args.order:8s} {var:10s} {k:12s} {args.stack or f'{nlev}x{args.fields}':>14s}: {ms / cnt:8.3f} ms/launch  {gbs:8.1f} GB/s  "
                   f"{100 * gbs / peak:5.1f}% of {peak:.0f}")
     rg.close()
 

@@ -68,14 +68,15 @@ def test_fortran_module_binds_every_reference_facing_entry():
     tooling = {"mprg_profile_enable", "mprg_profile_read", "mprg_profile_reset", "mprg_set_stream", "mprg_version",
                "mprg_route_export_csr", "mprg_route_import_csr", "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc",
                "mprg_device_free", "mprg_kernel_launches", "mprg_last_ms", "mprg_route_src_referenced", "mprg_clear_routes",
-               "mprg_route_info", "mprg_scratch", "mprg_has_rotation", "mprg_synchronize", "mprg_get_slab"}
+               "mprg_route_info", "mprg_scratch", "mprg_has_rotation", "mprg_synchronize", "mprg_get_slab", "mprg_get_option"}
     assert not [b for b in bound if b not in declared], "Fortran binds a name the header does not declare"
     missing = [d for d in declared if d not in bound and d not in tooling]
     assert not missing, missing
     # the stagger / method / memory constants agree with the header
     hdr = open(os.path.join(ROOT, "include", "mpassit_rg.h")).read()
     for name in ("MPRG_BILINEAR", "MPRG_CONSERVE", "MPRG_NEAREST_STOD", "MPRG_CENTER", "MPRG_EDGE1", "MPRG_EDGE2", "MPRG_CORNER",
-                 "MPRG_CENTER_HALO", "MPRG_F32", "MPRG_F64", "MPRG_HOST", "MPRG_DEVICE", "MPRG_EPI_ROT_U", "MPRG_EPI_ROT_V"):
+                 "MPRG_CENTER_HALO", "MPRG_F32", "MPRG_F64", "MPRG_HOST", "MPRG_DEVICE", "MPRG_EPI_ROT_U", "MPRG_EPI_ROT_V",
+                 "MPRG_GRID_NOPERI", "MPRG_GRID_1PERI_MONOPOLE"):
         hv = re.search(name + r"\s*=\s*(\d+)", hdr)
         fv = re.search(name + r"\s*=\s*(\d+)", txt)
         assert hv and fv and hv.group(1) == fv.group(1), name

@@ -8,6 +8,7 @@ import os
 import numpy as np
 import pytest
 
+from mpassit_b200 import check
 from tests import mpas_files
 
 pytestmark = pytest.mark.gpu
@@ -126,8 +127,7 @@ def test_files_double_precision_sources(host, tmp_path):
     want = _expect_file(got, wl)
     # fp64 sources accumulate in fp64: equal to the fp32 pass within its accumulation error
     for k in ("T", "QVAPOR", "PSFC", "U", "V", "REFL_10CM", "SNOW", "HGT"):
-        scale = float(np.abs(want[k]).max())
-        assert np.abs(out[k].astype(np.float64) - want[k]).max() <= 1e-5 * scale, k
+        check.assert_field_close(out[k], want[k], k)
     for k in ("XLAND", "TSLB"):
         assert np.array_equal(out[k], want[k]), k
 

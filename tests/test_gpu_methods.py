@@ -4,7 +4,7 @@ call sequence (interp.F90:92-465) end to end, all through the C ABI."""
 import numpy as np
 import pytest
 
-from mpassit_b200 import defaults
+from mpassit_b200 import check, defaults
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -198,8 +198,7 @@ def test_interp_data_end_to_end(rg, orc, host, lc_case):
         if nm in exact:
             assert np.array_equal(g, w), nm
         else:
-            scale = max(np.abs(w).max(), 1e-30)
-            assert np.abs(g - w).max() <= 1e-5 * scale, (nm, np.abs(g - w).max(), scale)
+            check.assert_field_close(g, w, nm)      # per element: |g - w| <= 1e-5 |w| + 1e-7 max|w|
     # the wind inputs are peeled off into U/V (their own dst buffers stay untouched)
     assert np.isnan(got["uReconstructZonal"]).all()
     # soil really used nearest neighbour (values are integers from the source, never blended)
@@ -279,7 +278,7 @@ def test_interp_data_global_latlon_target(engine_lib, orc, host, tmp_path):
     nz, nsoil = 7, 4            # 7 levels: columns not 16-byte aligned
     F = _fields(mesh, nz, nsoil)
     F["diag"] = []
-    want = H.oracle_interp(orc, mesh, grids, F, None, None, lc=False)
+    want = H.oracle_interp(orc, mesh, grids, F, None, None, lc=False, periodic=True)   # is_regional = .false.
     rg = Regridder(device=0)
     rg.set_mesh(mesh.lonCell, mesh.latCell, mesh.lonVertex, mesh.latVertex, mesh.verticesOnCell)
     for k, s in (("M", 0), ("U", 1), ("V", 2), ("CORNER", 3)):
@@ -306,7 +305,7 @@ def test_interp_data_global_latlon_target(engine_lib, orc, host, tmp_path):
         if nm in {"xland", "tslb", "smois", "sh2o"}:
             assert np.array_equal(g, w), nm
         else:
-            assert np.abs(g - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), nm
+            check.assert_field_close(g, w, nm)
     # a global mesh covers every target point: nothing is unmapped (snow: every destination cell fully covered)
     assert (got["theta"] != 0).all()
     rg.close()
@@ -332,7 +331,8 @@ def test_interp_data_workload_against_oracle(engine_lib, orc, host, name):
     rg.synchronize()
     fields = {g: [(s.name, s.src.cpu().numpy()) for s in F["dev"][g]] for g in ("diag", "hist_2d", "hist_3d", "soil")}
     fields["ter"] = F["dev"]["ter"].cpu().numpy()
-    want = H.oracle_interp(orc, wl.mesh, wl.grids, fields, wl.cosa, wl.sina, lc=wl.cosa is not None)
+    want = H.oracle_interp(orc, wl.mesh, wl.grids, fields, wl.cosa, wl.sina, lc=wl.cosa is not None,
+                           periodic=not wl.cfg.is_regional)
     got = {s.name: s.dst.cpu().numpy() for g in ("diag", "hist_2d", "hist_3d", "soil") for s in F["dev"][g]}
     got["HGT"], got["U"], got["V"] = (F["dev"][k].cpu().numpy() for k in ("hgt", "u_stag", "v_stag"))
     exact = {"xland", "tslb", "smois", "sh2o"}
@@ -344,7 +344,7 @@ def test_interp_data_workload_against_oracle(engine_lib, orc, host, name):
         if nm in exact:
             assert np.array_equal(g, w), nm
         else:
-            assert np.abs(g - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), (nm, np.abs(g - w).max())
+            check.assert_field_close(g, w, nm)
         checked += 1
     assert checked >= (40 if name == "mid" else 25)
     rg.close()

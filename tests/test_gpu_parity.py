@@ -6,6 +6,7 @@ indices; weights <= 1e-12 abs; fp32 bilinear fields <= 1e-5 relative (here far t
 import numpy as np
 import pytest
 
+from mpassit_b200 import check
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -70,12 +71,22 @@ def test_bilinear_structure_and_weights(rg, orc, name):
     r.release()
 
 
+@pytest.fixture
+def knobs(rg):
+    """Tuning options are restored after the test (the engine is shared by the module)."""
+    yield rg
+    for k, v in (("accumulate", "f32"), ("staging", "auto"), ("apply", "pipe"), ("pipe_minb", "0")):
+        rg.set_option(k, v)
+
+
+@pytest.mark.parametrize("staging", ["bulk", "ldg"])
 @pytest.mark.parametrize("acc", ["f32", "f64"])
-@pytest.mark.parametrize("nlev", [1, 4, 55, 60, 61, 130])
-def test_apply_bilinear_levels(rg, orc, nlev, acc, monkeypatch):
+@pytest.mark.parametrize("nlev", [1, 4, 55, 60, 61, 62, 64, 130])
+def test_apply_bilinear_levels(knobs, rg, orc, nlev, acc, staging):
     from mpassit_b200 import lib as l
 
-    monkeypatch.setenv("MPASSIT_GPU_ACC", acc)   # default is f32 accumulation; f64 = the reference's R8 arithmetic
+    rg.set_option("accumulate", acc)   # default is f32 accumulation; f64 = the reference's R8 arithmetic
+    rg.set_option("staging", staging)  # both staging modes of the column kernel (TMA bulk runs / per-thread cp.async)
 
     mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "regional_ragged")
     elem, col, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
@@ -89,13 +100,52 @@ def test_apply_bilinear_levels(rg, orc, nlev, acc, monkeypatch):
     unm = elem < 0
     assert np.all(got[:, unm] == 0.0)                # zero fill of unmapped rows
     # contract (BASELINE.json north_star): <= 1e-5 relative for fp32 bilinear fields
-    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    check.assert_field_close(got, want, f"nlev={nlev} acc={acc}")   # per element
     if acc == "f64":
         # fp64 accumulation, one rounding: at most 1 ulp from the oracle's rounding of the same sum
         np.testing.assert_allclose(got, want, rtol=2e-7, atol=0)
     else:
         # fp32 FMA accumulation of a convex combination: a few ulp
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("staging", ["bulk", "ldg"])
+def test_device_sources_at_any_element_alignment_and_mixed_stacks(knobs, rg, orc, staging):
+    """Device sources are used in place.  A view that starts 4 bytes into an allocation (base not 16-byte aligned)
+    and stacks mixing aligned / unaligned level counts and a wind pair go through ONE column launch and must give
+    exactly what each field gives on its own from an aligned copy."""
+    import torch
+
+    from mpassit_b200 import lib as l
+
+    rg.set_option("staging", staging)
+    mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "regional_ragged")
+    n, nd = mesh.nCells, lon.size
+    r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    levs = [60, 61, 55, 64, 60, 9, 130]
+    srcs, views = [], []
+    for k, nl in enumerate(levs):
+        off = k % 4                                              # 0, 4, 8, 12 bytes into the allocation
+        buf = torch.randn(n * nl + 4, generator=g, device="cuda")
+        views.append(buf[off:off + n * nl].view(n, nl))
+        srcs.append(views[-1].clone())                           # aligned copy of the same values
+        assert views[-1].data_ptr() % 16 == 4 * off
+    stacked = [torch.full((nl, nd), float("nan"), device="cuda") for nl in levs]
+    n0 = rg.kernel_launches
+    rg.apply(r, views, stacked, nlev=levs)
+    rg.synchronize()
+    assert rg.kernel_launches - n0 <= 2                          # every 3-D field in one column launch (+ nothing flat here)
+    for k, nl in enumerate(levs):
+        one = torch.full((nl, nd), float("nan"), device="cuda")
+        rg.apply(r, [srcs[k]], [one], nlev=[nl])
+        rg.synchronize()
+        assert torch.equal(one, stacked[k]), (staging, nl)
+    e, c, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
+    want = orc.apply(*orc.ell_to_csr(e >= 0, c, w), srcs[1].cpu().numpy(), np.float32)
+    check.assert_field_close(stacked[1].cpu().numpy(), want, "61 levels, base + 4 bytes")
+    r.release()
 
 
 def test_apply_nearest_bit_exact_and_stacked(rg, orc):

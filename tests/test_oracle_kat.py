@@ -163,3 +163,90 @@ def test_rotate_winds_kat(orc):
     assert np.allclose(u1, ue, rtol=1e-15) and np.allclose(v1, (v - ue * sa) / ca, rtol=1e-15)
     # algebraically: u' = u cos + v sin, v' = v cos - u sin  (earth -> grid rotation by alpha)
     assert np.allclose(u1, u * ca + v * sa, rtol=1e-13) and np.allclose(v1, v * ca - u * sa, rtol=1e-13)
+
+
+# ---------------------------------------------------------------------------
+# global targets: ESMF_GridCreate1PeriDim + MONOPOLE (model_grid.F90:684-696)
+# ---------------------------------------------------------------------------
+def _global_staggers(ni=24, nj=12):
+    """Cell-centred global lat-lon target the way the reference lays it out (program_setup.F90:197-210):
+    centres (i + .5) dlon, U at i dlon (ni + 1 columns, first and last on the seam), V at rows -90 ... +90."""
+    dlon, dlat = 360.0 / ni, 180.0 / nj
+    lonc = -180.0 + (np.arange(ni) + 0.5) * dlon
+    latc = -90.0 + (np.arange(nj) + 0.5) * dlat
+    lonu = -180.0 + np.arange(ni + 1) * dlon
+    latv = -90.0 + np.arange(nj + 1) * dlat
+    M = np.meshgrid(lonc, latc)
+    U = np.meshgrid(lonu, latc)
+    V = np.meshgrid(lonc, latv)
+    return M, U, V
+
+
+def test_periodic_grid_maps_the_seam_columns(orc):
+    """Centre -> EDGE1 on a periodic grid: the quad between the last and the first centre column exists, so the two
+    seam columns of U are interpolated across the seam (the same weights, on columns ni-1 and 0) instead of being
+    left unmapped as on a GridCreateNoPeriDim grid."""
+    ni, nj = 24, 12
+    (lonM, latM), (lonU, latU), _ = _global_staggers(ni, nj)
+    sx = orc.sph_deg_to_cart(lonM, latM).reshape(nj, ni, 3)
+    dU = orc.sph_deg_to_cart(lonU, latU)
+    e0, c0, w0 = orc.bilinear_quadgrid(sx, dU)                               # non-periodic
+    assert (e0.reshape(nj, ni + 1)[:, [0, ni]] < 0).all() and (e0.reshape(nj, ni + 1)[:, 1:ni] >= 0).all()
+    topo = orc.TOPO_PERI | orc.TOPO_SPOLE | orc.TOPO_NPOLE
+    e, c, w = orc.bilinear_quadgrid(sx, dU, topo=topo)
+    eb, cb, wb = orc.bilinear_quadgrid(sx, dU, topo=topo, brute=True)        # kd-tree search == brute force
+    assert np.array_equal(e, eb) and np.array_equal(c, cb) and np.array_equal(w, wb)
+    assert (e >= 0).all() and (e < ni * (nj - 1)).all()                      # every U point sits in a quad
+    rp, cc, ww = orc.quadgrid_csr(ni, nj, e, c, w, topo)
+    assert np.array_equal(np.diff(rp), np.full(dU.shape[0], 4))
+    W = ww.reshape(nj, ni + 1, 4)
+    Cc = cc.reshape(nj, ni + 1, 4)
+    assert np.abs(W.sum(-1) - 1).max() <= 1e-12
+    # interior columns agree with the non-periodic matrix (same quads, same ids order within a row)
+    assert np.array_equal(c.reshape(nj, ni + 1, 4)[:, 1:ni], c0.reshape(nj, ni + 1, 4)[:, 1:ni])
+    assert np.array_equal(w.reshape(nj, ni + 1, 4)[:, 1:ni], w0.reshape(nj, ni + 1, 4)[:, 1:ni])
+    # seam: column 0 and column ni are the same point, mapped by the wrap quad onto columns ni-1 and 0
+    assert np.array_equal(Cc[:, 0], Cc[:, ni]) and np.abs(W[:, 0] - W[:, ni]).max() <= 1e-12
+    cols = Cc[:, 0] % ni
+    heavy = np.take_along_axis(cols, np.argsort(-W[:, 0], axis=1)[:, :2], axis=1)
+    assert all(set(r) == {ni - 1, 0} for r in heavy.tolist())
+    # the interpolated position t p is parallel to p: weights reproduce Cartesian coordinates along the ray
+    pos = (W[..., None] * sx.reshape(-1, 3)[Cc]).sum(2).reshape(-1, 3)
+    assert np.abs(np.cross(pos, dU)).max() <= 1e-12
+    # a zonally periodic field is continuous across the seam
+    f = (np.cos(np.radians(latM)) * np.cos(np.radians(lonM))).reshape(1, -1)
+    u = orc.apply_planes(rp, cc, ww, f).reshape(nj, ni + 1)
+    assert np.abs(u[:, 0] - u[:, ni]).max() <= 1e-13
+    assert np.abs(u[:, 0] - np.cos(np.radians(latU[:, 0])) * np.cos(np.radians(-180.0))).max() <= 0.01
+
+
+def test_monopole_caps_average_the_end_rows(orc):
+    """Centre -> EDGE2: the V rows at +-90 lie at the artificial pole node, whose value is the average of the
+    neighbouring centre row (polemethod ALLAVG): ni entries of 1/ni.  Interior rows are untouched."""
+    ni, nj = 24, 12
+    (lonM, latM), _, (lonV, latV) = _global_staggers(ni, nj)
+    sx = orc.sph_deg_to_cart(lonM, latM).reshape(nj, ni, 3)
+    dV = orc.sph_deg_to_cart(lonV, latV)
+    e0, c0, w0 = orc.bilinear_quadgrid(sx, dV)
+    assert (e0.reshape(nj + 1, ni)[[0, nj]] < 0).all()                        # no caps: pole rows unmapped
+    topo = orc.TOPO_PERI | orc.TOPO_SPOLE | orc.TOPO_NPOLE
+    e, c, w = orc.bilinear_quadgrid(sx, dV, topo=topo)
+    E = e.reshape(nj + 1, ni)
+    nq = ni * (nj - 1)
+    assert (E[1:nj] >= 0).all() and (E[1:nj] < nq).all()
+    assert (E[0] >= nq).all() and (E[0] < nq + ni).all() and (E[nj] >= nq + ni).all()
+    rp, cc, ww = orc.quadgrid_csr(ni, nj, e, c, w, topo)
+    cnt = np.diff(rp).reshape(nj + 1, ni)
+    assert (cnt[[0, nj]] == ni).all() and (cnt[1:nj] == 4).all()
+    for row, base in ((0, 0), (nj, (nj - 1) * ni)):
+        for i in range(ni):
+            t = row * ni + i
+            assert np.array_equal(cc[rp[t]:rp[t + 1]], base + np.arange(ni))
+            assert np.abs(ww[rp[t]:rp[t + 1]] - 1.0 / ni).max() <= 1e-12
+    f = (3.0 + np.sin(np.radians(latM)) + 0.3 * np.cos(np.radians(lonM))).reshape(1, -1)
+    v = orc.apply_planes(rp, cc, ww, f).reshape(nj + 1, ni)
+    assert np.abs(v[0] - f.reshape(nj, ni)[0].mean()).max() <= 1e-12
+    assert np.abs(v[nj] - f.reshape(nj, ni)[nj - 1].mean()).max() <= 1e-12
+    # a row block that does not hold the pole row carries no cap
+    eb, _, _ = orc.bilinear_quadgrid(sx[2:6], dV.reshape(nj + 1, ni, 3)[3:6].reshape(-1, 3), topo=orc.TOPO_PERI)
+    assert (eb >= 0).all()
