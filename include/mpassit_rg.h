@@ -79,10 +79,9 @@ int mprg_set_async(mprg_ctx *ctx, int on);
  * mprg_set_option changes it afterwards.  key / values [environment variable]:
  *   "accumulate"  "f32" (default) | "f64": arithmetic of fp32-in / fp32-out applies and of the wind rotation; f64 is
  *                 the reference's R8 arithmetic (one rounding on store)                          [MPASSIT_GPU_ACC]
- *   "staging"     "auto" (default: by the route's tile schedule) | "bulk" | "ldg": how the column kernel brings
- *                 source columns into shared memory -- one TMA bulk copy per run of consecutively numbered cells,
- *                 or per-thread cp.async for meshes whose numbering has no locality          [MPASSIT_GPU_STAGING]
- *   "ldg_below"   auto staging picks ldg when (distinct columns / runs) of the route is below this (2.5)
+ *   "pipe_split"  "1" (default) | "0": the column kernel is compiled per launch content; with 1 the aligned plain
+ *                 fields of an apply run in their own (leanest) launch and wind pairs / unaligned level counts in a
+ *                 second one, with 0 everything shares one launch                          [MPASSIT_GPU_PIPE_SPLIT]
  *   "apply"       "pipe" (default) | "direct": register-gather kernels only                    [MPASSIT_GPU_APPLY]
  *   "pipe_minb"   0 (default: by shared memory) | 4 | 5 resident CTAs per SM               [MPASSIT_GPU_PIPE_MINB]
  *   "cols_minb"   2 | 3 (default) | 4: register cap of the register-gather kernel               [MPASSIT_GPU_MINB]

@@ -429,20 +429,12 @@ static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, co
     ctx->launches++;
 }
 
-// staging mode of a route: BULK (one TMA bulk copy per run of consecutively numbered columns) when its tiles'
-// columns form long runs, LDG (per-thread cp.async) when they do not
-static bool route_uses_ldg(const mprg_ctx *ctx, const mprg_route *r) {
-    if (ctx->tune.staging >= 0) return ctx->tune.staging == 1;
-    return r->schedRuns > 0 && (double)r->schedCols < ctx->tune.ldgBelow * (double)r->schedRuns;
-}
-
 // Every 3-D field of an apply in ONE launch of the pipelined kernel (kPipeMaxUnits units per launch).
 // Fields flagged MPRG_EPI_ROT_U / ROT_V are wind pairs whose rotation is fused into the store.
 // Returns false if this route / field set does not fit the kernel (the register-gather kernel takes over).
 template <typename TIN, typename TOUT, typename TACC>
 static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields, DstLayout dl) {
     if (ctx->tune.pipeOff || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
-    const bool ldg = route_uses_ldg(ctx, r);
     std::vector<UnitDev> units;
     auto unit_of = [&](const FieldDev &f, int L0) {
         UnitDev u;
@@ -472,19 +464,19 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             for (int L0 = 0; L0 < fields[f].nlev; L0 += kPipeLev) units.push_back(unit_of(fields[f], L0));
         }
     }
-    // one stage holds the largest unit of the launch at the route's tile maxima
-    size_t stage = 0;
-    for (const UnitDev &u : units)
-        stage = std::max(stage, pipe_unit_stage_bytes(ldg, (u.flags & kUnitAligned) != 0, (u.flags & kUnitMerged) != 0,
-                                                      (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
-    stage = (stage + 15) & ~(size_t)15;
-    const size_t fixed = pipe_fixed_bytes<TACC>();
-    const size_t hold = rot ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
-    const size_t smemBytes = fixed + kPipeStages * stage + hold;
-    if (smemBytes + 1024 > (size_t)227 * 1024) return false;
-    // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
-    int minb = (smemBytes + 1024) * 5 <= (size_t)228 * 1024 ? 5 : 4;
-    if (ctx->tune.pipeMinb) minb = ctx->tune.pipeMinb >= 5 ? 5 : 4;
+    // Launch groups.  "split" (default): the aligned plain units -- the bulk of every pass -- run in the leanest
+    // variant of the kernel (48 registers, no spills, one barrier arrival per unit), everything that needs more
+    // (unaligned columns, wind pairs) in a second launch compiled for exactly that content; "one": a single launch.
+    std::vector<std::vector<UnitDev>> groups;
+    if (ctx->tune.pipeSplit) {
+        std::vector<UnitDev> plain, rest;
+        for (const UnitDev &u : units)
+            (((u.flags & kUnitAligned) && !(u.flags & (kUnitRotU | kUnitRotV))) ? plain : rest).push_back(u);
+        if (!plain.empty()) groups.push_back(std::move(plain));
+        if (!rest.empty()) groups.push_back(std::move(rest));
+    } else {
+        groups.push_back(units);
+    }
     PipeArgs<TACC> pa;
     pa.rowptr = r->rowptr.p; pa.col = r->col.p;
     if (sizeof(TACC) == 8) pa.w = (const TACC *)r->w.p; else pa.w = (const TACC *)r->w32.p;
@@ -493,8 +485,6 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     pa.dstLev = dl.lev; pa.dstOff = dl.off;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
-    pa.stageBytes = (int32_t)stage;
-    pa.holdOff = (int32_t)(fixed + kPipeStages * stage);
     pa.rotc = nullptr;
     if (rot) {  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
         using TR = typename RotMath<TOUT, TACC>::type;
@@ -502,20 +492,52 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         pa.rotc = sizeof(TR) == 4 ? (const void *)(ctx->rotc32.p + off) : (const void *)(ctx->rotc.p + off);
     }
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
-    for (size_t u0 = 0; u0 < units.size();) {
-        size_t nu = std::min<size_t>(kPipeMaxUnits, units.size() - u0);
-        if (u0 + nu < units.size() && (units[u0 + nu - 1].flags & kUnitRotU)) --nu;  // keep a wind pair in one launch
-        UnitPack up;
-        memcpy(up.u, units.data() + u0, nu * sizeof(UnitDev));
-        pa.nunits = (int)nu;
-        if (ldg) {
-            if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, true, 5>, pa, up, smemBytes, tiles);
-            else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, true, 4>, pa, up, smemBytes, tiles);
-        } else {
-            if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, false, 5>, pa, up, smemBytes, tiles);
-            else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, false, 4>, pa, up, smemBytes, tiles);
+    struct Launch { size_t g, u0, nu, smem; int mode, minb; int32_t stageOff, stageBytes, holdOff; };
+    std::vector<Launch> plan;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const std::vector<UnitDev> &us = groups[g];
+        for (size_t u0 = 0; u0 < us.size();) {
+            size_t nu = std::min<size_t>(kPipeMaxUnits, us.size() - u0);
+            if (u0 + nu < us.size() && (us[u0 + nu - 1].flags & kUnitRotU)) --nu;  // keep a wind pair in one launch
+            int mode = 0;
+            size_t stage = 0;   // one stage holds the largest unit of the launch at the route's tile maxima
+            for (size_t k = 0; k < nu; ++k) {
+                const UnitDev &u = us[u0 + k];
+                if (!(u.flags & kUnitAligned)) mode |= kModeUnal;
+                if (u.flags & (kUnitRotU | kUnitRotV)) mode |= kModeRot;
+                stage = std::max(stage, pipe_unit_stage_bytes((u.flags & kUnitAligned) != 0, (u.flags & kUnitMerged) != 0,
+                                                              (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
+            }
+            stage = (stage + 15) & ~(size_t)15;
+            const size_t fixed = (pipe_fixed_bytes<TACC>() + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
+            const size_t hold = (mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
+            const size_t smemBytes = fixed + kPipeStages * stage + hold;
+            if (smemBytes + 1024 > (size_t)227 * 1024) return false;
+            // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
+            int minb = (smemBytes + 1024) * 5 <= (size_t)228 * 1024 ? 5 : 4;
+            if (ctx->tune.pipeMinb) minb = ctx->tune.pipeMinb >= 5 ? 5 : 4;
+            plan.push_back(Launch{g, u0, nu, smemBytes, mode, minb, (int32_t)fixed, (int32_t)stage,
+                                  (int32_t)(fixed + kPipeStages * stage)});
+            u0 += nu;
         }
-        u0 += nu;
+    }
+    for (const Launch &l : plan) {   // nothing is launched unless every launch of the apply fits
+        UnitPack up;
+        memcpy(up.u, groups[l.g].data() + l.u0, l.nu * sizeof(UnitDev));
+        pa.nunits = (int)l.nu;
+        pa.stageOff = l.stageOff; pa.stageBytes = l.stageBytes; pa.holdOff = l.holdOff;
+        const size_t smemBytes = l.smem;
+        const int minb = l.minb;
+#define MPRG_PIPE_LAUNCH(M)                                                                                        \
+    if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, M, 5>, pa, up, smemBytes, tiles);             \
+    else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, M, 4>, pa, up, smemBytes, tiles)
+        switch (l.mode) {
+            case 0: MPRG_PIPE_LAUNCH(0); break;
+            case kModeUnal: MPRG_PIPE_LAUNCH(kModeUnal); break;
+            case kModeRot: MPRG_PIPE_LAUNCH(kModeRot); break;
+            default: MPRG_PIPE_LAUNCH(kModeUnal | kModeRot); break;
+        }
+#undef MPRG_PIPE_LAUNCH
     }
     MPRG_CUDA(cudaGetLastError());
     return true;

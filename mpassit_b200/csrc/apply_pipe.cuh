@@ -1,25 +1,18 @@
-// apply_pipe.cuh -- staged, pipelined column apply kernel (the hot kernel), v7.
+// apply_pipe.cuh -- TMA-staged, pipelined column apply kernel (the hot kernel), v7.
 //
 // One CTA owns a tile of up to 32 consecutive destination points of one grid row and sweeps EVERY
-// stacked 3-D field of the launch for it -- aligned level counts (60, 64, ...), unaligned ones (55, 61, ...)
-// and wind pairs with fused rotation alike, in ONE launch at 5 resident CTAs per SM:
+// stacked 3-D field of the launch for it:
 //   prologue  the tile's CSR slice and its tile schedule (distinct source columns of the tile in ascending
 //             id order, their runs of consecutive ids; built once per route by k_tile_schedule) go to shared
 //             memory; every lane keeps the (weight, staged-column slot) pairs of ITS target in registers for
 //             the whole sweep when the row has <= 3 entries (bilinear, nearest);
-//   staging   unit u + 1 (= one field x one 64-level chunk) is fetched while unit u is reduced.  Two modes,
-//             chosen per launch from the route's schedule statistics:
-//             BULK  (mesh numbered with locality: a tile's ~64 columns form a few runs of consecutive ids, which
-//                   file order keeps contiguous in memory) -- ONE cp.async.bulk (UBLKCP, completion counted on
-//                   an mbarrier) per RUN.  Columns whose byte size is a multiple of 16 land packed, 16-byte
-//                   aligned; others (61 levels: 244 B) are fetched as the 16-byte-aligned window around the run
-//                   and read in place with 4-byte shared loads at stride 61 words (odd: conflict-free) -- no
-//                   realignment pass, no second barrier;
-//             LDG   (no locality: every column its own DRAM page) -- the TMA unit accepts one request per
-//                   ~17 cycles per SM, which bounds a copy-per-column design at ~75 % of the HBM peak; here
-//                   every thread issues 16-byte cp.async (LDGSTS) for its share of the tile's chunks instead
-//                   (4-byte cp.async for unaligned columns, which lands them aligned), completion by
-//                   cp.async.wait_group + the per-unit CTA barrier;
+//   staging   unit u + 1 (= one field x one 64-level chunk) is fetched while unit u is reduced: ONE
+//             cp.async.bulk (UBLKCP, completion counted on an mbarrier) per RUN of consecutively numbered
+//             columns, which file order keeps contiguous in memory -- the TMA unit accepts one request per
+//             ~17 cycles per SM, so fewer, larger requests are the lever.  Columns whose byte size is a
+//             multiple of 16 land packed, 16-byte aligned; others (61 levels: 244 B) are fetched as the
+//             16-byte-aligned window around the run and read in place with 4-byte shared loads at stride 61
+//             words (odd: conflict-free) -- no realignment pass, no second barrier;
 //   math      lanes run along TARGETS: warp w takes level groups w, w + 8 (4 levels each); lane t reads 4 levels
 //             of each of its row's columns with one 16-byte shared load and the 32 lanes' results for one level
 //             leave as one coalesced 128-byte streaming store into [lev][j][i].  No transpose through shared
@@ -27,6 +20,11 @@
 //   rotation  units of a wind pair alternate zonal / meridional chunks of the same levels; the zonal results wait
 //             in shared memory (8 KB) until the meridional unit, rotate_winds_cgrid (interp.F90:737-748) runs
 //             between the two, both are stored rotated.
+// The kernel is compiled per launch content (MODE): only launches that hold unaligned units / wind pairs carry
+// the code and registers for them, so the main stack of aligned fields keeps its 48-register, 5-CTA/SM shape.
+// (Negative result, profiles/r02: staging with per-thread cp.async (LDGSTS) instead of bulk copies -- meant for
+// meshes numbered without locality -- ran at 60-68 % of the HBM peak against 71-88 % for bulk copies on every
+// numbering, and was removed.)
 #pragma once
 #include "common.cuh"
 
@@ -39,8 +37,10 @@ constexpr int kPipeCap = 256;      // CSR entries per tile accepted (== threads:
 constexpr int kPipeLev = 64;       // levels per unit
 constexpr int kPipeMaxUnits = 64;  // units (field x 64-level chunk) per launch; the host splits longer stacks
 constexpr int kPipeStages = 2;     // resident CTAs beat pipeline depth (profiles/r01: 2 x 5 CTAs > 3 x 4 > 4 x 3)
-constexpr int kRunPad = 40;        // BULK, unaligned units: slack per run so that 16-byte-aligned windows never overlap
-constexpr int kLdgCache = 5;       // LDG: per-thread chunk offsets kept in registers (covers tiles of <= 85 columns x 240 B)
+constexpr int kRunPad = 40;        // unaligned units: slack per run so that 16-byte-aligned windows never overlap
+// launch content the kernel is compiled for
+constexpr int kModeUnal = 1;       // some unit's column chunks are not 16-byte aligned
+constexpr int kModeRot = 2;        // some units are wind pairs (fused rotation)
 
 struct UnitDev {
     const void *src;
@@ -80,9 +80,10 @@ struct PipeArgs {
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
     int32_t nunits;
+    int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the unit descriptors)
     int32_t stageBytes; // bytes of one stage (host: the largest unit's need at the route's tile maxima)
-    int32_t holdOff;    // byte offset of the wind-pair hold buffer in dynamic shared memory (ROT launches), else 0
-    // ROT launches only: per-point rotation constants of this rank's destination rows, in the arithmetic type
+    int32_t holdOff;    // byte offset of the wind-pair hold buffer (kModeRot launches)
+    // kModeRot launches only: per-point rotation constants of this rank's destination rows, in the arithmetic type
     // of the rotation (RotMath): [nDst][4] = sina, tana, 1/cosa, 1/(cosa + sina tana)
     const void *rotc;
 };
@@ -103,19 +104,8 @@ __device__ __forceinline__ void bulk_g2s(unsigned smemDst, const void *gmem, uns
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smemDst),
                  "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
-// LDGSTS: 16 bytes global -> shared, L2 only (.cg); 4 / 8 bytes through L1 (.ca, the only form for short copies)
-__device__ __forceinline__ void ldgsts16(unsigned smemDst, const void *gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smemDst), "l"(gmem) : "memory");
-}
-template <int BYTES>
-__device__ __forceinline__ void ldgsts_small(unsigned smemDst, const void *gmem) {
-    if (BYTES == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smemDst), "l"(gmem) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smemDst), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// fixed part of the dynamic shared memory (bytes); the stages follow, then (ROT launches) the hold buffer
+// fixed part of the dynamic shared memory (bytes); the unit descriptors, the stages and (kModeRot) the hold buffer follow
 template <typename TACC>
 __host__ __device__ constexpr size_t pipe_fixed_bytes() {
     return 64 * 4                                   // s_rowptr (33 used) + mbarriers
@@ -125,12 +115,10 @@ __host__ __device__ constexpr size_t pipe_fixed_bytes() {
            + kPipeCap                               // s_runFirst: first slot of every run
            + kPipeCap * sizeof(TACC);               // s_w
 }
-// slot stride of an aligned unit in shared memory: packed at the column size so that a run is contiguous there
-// too -- unless that size is a multiple of 128 bytes (every slot would start on bank 0): 16 bytes of padding then
-__host__ __device__ constexpr unsigned pipe_aligned_stride(unsigned colB) { return (colB & 127u) ? colB : colB + 16u; }
-// bytes of one stage that a unit needs for a tile of nu columns in nruns runs
-__host__ __device__ inline size_t pipe_unit_stage_bytes(bool ldg, bool aligned, bool merged, unsigned chunkB, int nu, int nruns) {
-    if (ldg) return (size_t)nu * pipe_aligned_stride((chunkB + 15u) & ~15u);
+// bytes of one stage that a unit needs for a tile of nu columns in nruns runs.  Aligned units: slots packed at the
+// column size so that a run is contiguous in shared memory too -- unless that size is a multiple of 128 bytes (every
+// slot would start on bank 0) or the chunk is not the whole column: 16 bytes of padding and one copy per column then.
+__host__ __device__ inline size_t pipe_unit_stage_bytes(bool aligned, bool merged, unsigned chunkB, int nu, int nruns) {
     if (aligned) return (size_t)nu * ((merged && (chunkB & 127u)) ? chunkB : chunkB + 16u);
     return (size_t)nu * chunkB + (size_t)kRunPad * (merged ? nruns : nu) + 32;
 }
@@ -162,7 +150,7 @@ __device__ __forceinline__ void fma4(TACC (&acc)[4], TACC wt, unsigned saddr) {
         acc[0] += wt * (TACC)x; acc[1] += wt * (TACC)y; acc[2] += wt * (TACC)z; acc[3] += wt * (TACC)w;
     }
 }
-// the same from a column that is only element-aligned in shared memory (BULK staging of unaligned units)
+// the same from a column that is only element-aligned in shared memory (unaligned units)
 template <typename TIN, typename TACC>
 __device__ __forceinline__ void fma4u(TACC (&acc)[4], TACC wt, unsigned saddr) {
     if (sizeof(TIN) == 4) {
@@ -202,11 +190,12 @@ __device__ __forceinline__ void lds4(unsigned saddr, T (&v)[4]) {
     }
 }
 
-// LDG: staging mode (see the header).  MINB: resident CTAs per SM the kernel is compiled for (register cap
-// 48 at 5, 64 at 4).
-template <typename TIN, typename TOUT, typename TACC, bool LDG, int MINB>
+// MODE: launch content (kModeUnal | kModeRot).  MINB: resident CTAs per SM the kernel is compiled for
+// (register cap 48 at 5, 64 at 4).
+template <typename TIN, typename TOUT, typename TACC, int MODE, int MINB>
 __global__ void __launch_bounds__(kPipeThreads, MINB)
 k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
+    constexpr bool UNAL = (MODE & kModeUnal) != 0, ROT = (MODE & kModeRot) != 0;
     constexpr int ESZ = (int)sizeof(TIN);
     constexpr int GB = 4 * ESZ;                           // bytes of one 4-level group in a staged column
     using TR = typename RotMath<TOUT, TACC>::type;
@@ -219,7 +208,8 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     unsigned char *s_urun = (unsigned char *)(s_uniq + kPipeCap);
     unsigned char *s_runFirst = s_urun + kPipeCap;
     TACC *s_w = (TACC *)(s_runFirst + kPipeCap);
-    unsigned char *s_stage = smem + pipe_fixed_bytes<TACC>();
+    UnitDev *s_units = (UnitDev *)(smem + pipe_fixed_bytes<TACC>());
+    unsigned char *s_stage = smem + a.stageOff;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = blockIdx.x / a.tilesPerRow;
@@ -229,16 +219,18 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
 
     // ---- prologue: CSR slice + the tile's schedule ---------------------------------
     if (tid <= kPipeTile) s_rowptr[tid] = a.rowptr[min(t0 + min(tid, ntile), a.nDst)];
-    if (!LDG && tid == 0) {
+    for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
+        ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
+    if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kPipeStages; ++i) mbar_init(s_mbar + i, kPipeWarps);  // one arrival per warp per unit
+        for (int i = 0; i < kPipeStages; ++i) mbar_init(s_mbar + i, UNAL ? kPipeWarps : 1);  // arrivals per unit
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const int ub = __ldg(a.tileUPtr + blockIdx.x);
     const int nu = __ldg(a.tileUPtr + blockIdx.x + 1) - ub;
     if (tid < nu) {
         s_uniq[tid] = __ldg(a.tileUCols + ub + tid);
-        if (!LDG) s_urun[tid] = __ldg(a.tileURun + ub + tid);
+        s_urun[tid] = __ldg(a.tileURun + ub + tid);
     }
     __syncthreads();
     const int base = s_rowptr[0];
@@ -246,9 +238,9 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     if (tid < cnt) {
         s_w[tid] = __ldg(a.w + base + tid);
         const int sl = __ldg(a.entrySlot + base + tid);
-        s_off[tid] = (unsigned short)(LDG ? sl : (sl | ((int)s_urun[sl] << 8)));
+        s_off[tid] = (unsigned short)(UNAL ? (sl | ((int)s_urun[sl] << 8)) : sl);
     }
-    if (!LDG && tid < nu && (tid == 0 || s_urun[tid] != s_urun[tid - 1])) s_runFirst[s_urun[tid]] = (unsigned char)tid;
+    if (UNAL && tid < nu && (tid == 0 || s_urun[tid] != s_urun[tid - 1])) s_runFirst[s_urun[tid]] = (unsigned char)tid;
     __syncthreads();
 
     // this lane's target; rows with <= 3 entries stay in registers
@@ -270,122 +262,84 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
     const unsigned hold0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.holdOff;
 
-    // ---- staging state -----------------------------------------------------------------------------------
-    // BULK: slot s = lane * warps + warp is copied by that lane, so the (warp-serialised) bulk-copy issue is
-    // spread evenly over all warps.  The owner of the first slot of a run fetches the whole run of a merged unit.
+    // slot s = lane * warps + warp is copied by that lane, so the (warp-serialised) bulk-copy issue is spread
+    // evenly over all warps instead of queuing behind the first two.  The list is in ascending id order and columns
+    // of consecutive ids are contiguous in memory, so the owner of the first slot of a run fetches the whole run
+    // with one bulk copy (brun = its length in columns, 0 for the other slots of the run).
     const int bslot = lane * kPipeWarps + warp;
-    int bcol = -1, brun = 0;
-    // LDG: byte offsets (within a field of the first unit's shape) of this thread's 16-byte chunks
-    unsigned goff[kLdgCache];
-    bool gcached = false;   // goff[] holds the offsets of units shaped like the first one
-    if (!LDG) {
-        bcol = bslot < nu ? s_uniq[bslot] : -1;
-        if (bcol >= 0 && (bslot == 0 || s_urun[bslot] != s_urun[bslot - 1])) {
-            brun = 1;
-            while (bslot + brun < nu && s_urun[bslot + brun] == s_urun[bslot]) ++brun;
-        }
-    } else {
-        const UnitDev &u0 = up.u[0];
-        if ((u0.flags & kUnitAligned) && u0.srcBytes <= 0xffffffffull) {
-            gcached = true;
-            const int cpc = (u0.Ln * ESZ) >> 4;
-#pragma unroll
-            for (int k = 0; k < kLdgCache; ++k) {
-                const int q = tid + k * kPipeThreads, sl = q / cpc;
-                goff[k] = sl < nu ? (unsigned)(((size_t)s_uniq[sl] * u0.nlev + u0.L0) * ESZ + (size_t)(q - sl * cpc) * 16) : 0u;
-            }
-        }
+    const int bcol = bslot < nu ? s_uniq[bslot] : -1;
+    int brun = 0;
+    if (bcol >= 0 && (bslot == 0 || s_urun[bslot] != s_urun[bslot - 1])) {
+        brun = 1;
+        while (bslot + brun < nu && s_urun[bslot + brun] == s_urun[bslot]) ++brun;
     }
 
     auto issue = [&](int u) {
         if (u >= a.nunits) return;
-        const UnitDev &ud = up.u[u];
+        const UnitDev &ud = s_units[u];
         const unsigned chunkB = (unsigned)ud.Ln * ESZ;
         const unsigned sbase = stage0 + (u % kPipeStages) * a.stageBytes;
-        if (LDG) {
-            const unsigned stride = pipe_aligned_stride((chunkB + 15u) & ~15u);
-            const char *src = (const char *)ud.src;
-            if (ud.flags & kUnitAligned) {
-                const int cpc = (int)(chunkB >> 4), total = nu * cpc;
-                if (gcached && ud.nlev == up.u[0].nlev && ud.L0 == up.u[0].L0 && ud.Ln == up.u[0].Ln && ud.srcBytes <= 0xffffffffull) {
-#pragma unroll
-                    for (int k = 0; k < kLdgCache; ++k) {
-                        const int q = tid + k * kPipeThreads;
-                        if (q < total) {
-                            const int sl = q / cpc;
-                            ldgsts16(sbase + sl * stride + (q - sl * cpc) * 16, src + goff[k]);
-                        }
-                    }
-                    for (int q = tid + kLdgCache * kPipeThreads; q < total; q += kPipeThreads) {
-                        const int sl = q / cpc, part = q - sl * cpc;
-                        ldgsts16(sbase + sl * stride + part * 16, src + ((size_t)s_uniq[sl] * ud.nlev + ud.L0) * ESZ + (size_t)part * 16);
-                    }
-                } else {
-                    for (int q = tid; q < total; q += kPipeThreads) {
-                        const int sl = q / cpc, part = q - sl * cpc;
-                        ldgsts16(sbase + sl * stride + part * 16, src + ((size_t)s_uniq[sl] * ud.nlev + ud.L0) * ESZ + (size_t)part * 16);
-                    }
-                }
-            } else {
-                // element-wise copies land every column at the start of its (16-byte aligned) slot
-                const int total = nu * ud.Ln;
-                for (int q = tid; q < total; q += kPipeThreads) {
-                    const int sl = q / ud.Ln, l = q - sl * ud.Ln;
-                    ldgsts_small<ESZ>(sbase + sl * stride + l * ESZ, src + ((size_t)s_uniq[sl] * ud.nlev + ud.L0 + l) * ESZ);
-                }
-            }
-            cp_async_commit();
-            return;
-        }
         unsigned long long *bar = s_mbar + (u % kPipeStages);
         const bool merged = (ud.flags & kUnitMerged) != 0;
-        unsigned nb = 0, sdst = 0;
-        const char *g = nullptr;
-        if (ud.flags & kUnitAligned) {
-            // exact column chunks.  Merged units whose column size is not a multiple of 128 bytes pack their slots
-            // at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
+        if (!UNAL || (ud.flags & kUnitAligned)) {
+            // exact column chunks.  Whole-column units whose column size is not a multiple of 128 bytes pack their
+            // slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
             const bool packed = merged && (chunkB & 127u);
-            if (packed ? brun > 0 : bcol >= 0) {
-                nb = packed ? chunkB * (unsigned)brun : chunkB;
-                sdst = sbase + bslot * (packed ? chunkB : chunkB + 16u);
-                g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
+            const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
+            if (!UNAL) {
+                if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)nu);   // one arrival posts the unit's bytes
+                if (packed) {
+                    if (brun > 0) bulk_g2s(sbase + bslot * chunkB, g, chunkB * (unsigned)brun, bar);
+                } else if (bcol >= 0) {
+                    bulk_g2s(sbase + bslot * (chunkB + 16u), g, chunkB, bar);
+                }
+            } else {
+                // mixed launch: the barrier counts one arrival per warp (lane 0 posts the bytes of the warp's copies)
+                const bool mine = packed ? brun > 0 : bcol >= 0;
+                const unsigned nb = mine ? (packed ? chunkB * (unsigned)brun : chunkB) : 0u;
+                const unsigned wb = __reduce_add_sync(0xffffffffu, nb);
+                if (lane == 0) mbar_arrive_tx(bar, wb);
+                if (nb) bulk_g2s(sbase + bslot * (packed ? chunkB : chunkB + 16u), g, nb, bar);
             }
-        } else if (merged ? brun > 0 : bcol >= 0) {
+        } else {
             // unaligned columns: the 16-byte-aligned window around the run (or the single column chunk); it lands at
-            // a 16-byte-aligned address chosen so that windows never overlap, and the math reads it where it lies
-            const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
+            // a 16-byte-aligned address chosen so that windows never overlap, and the math reads it where it lies.
             // (absolute addresses: the source base itself need only be element-aligned; device allocations are
             // 256-byte aligned, so the window's first 16-byte chunk always lies inside the caller's allocation)
-            const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
-            const uintptr_t al = a0 & ~(uintptr_t)15, aend = (uintptr_t)ud.src + ud.srcBytes;
-            size_t n = ((a0 + (size_t)(ncol - 1) * ud.nlev * ESZ + chunkB + 15) & ~(uintptr_t)15) - al;
-            sdst = sbase + (((unsigned)bslot * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u);
-            if (al + n > aend) {
-                // last window of the array: bulk-copy the whole 16-byte chunks, hand-copy the tail words
-                const size_t full = (aend - al) & ~(size_t)15;
-                for (size_t b = full; al + b < aend; b += 4) {
-                    const int32_t v = *(const int32_t *)(al + b);
-                    asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(sdst + (unsigned)b), "r"(v) : "memory");
+            unsigned nb = 0, sdst = 0;
+            uintptr_t al = 0;
+            if (merged ? brun > 0 : bcol >= 0) {
+                const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
+                const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
+                const uintptr_t aend = (uintptr_t)ud.src + ud.srcBytes;
+                al = a0 & ~(uintptr_t)15;
+                size_t n = ((a0 + (size_t)(ncol - 1) * ud.nlev * ESZ + chunkB + 15) & ~(uintptr_t)15) - al;
+                sdst = sbase + (((unsigned)bslot * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u);
+                if (al + n > aend) {
+                    // last window of the array: bulk-copy the whole 16-byte chunks, hand-copy the tail words
+                    const size_t full = (aend - al) & ~(size_t)15;
+                    for (size_t b = full; al + b < aend; b += 4) {
+                        const int32_t v = *(const int32_t *)(al + b);
+                        asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(sdst + (unsigned)b), "r"(v) : "memory");
+                    }
+                    n = full;
                 }
-                n = full;
+                nb = (unsigned)n;
             }
-            nb = (unsigned)n;
-            g = (const char *)al;
+            const unsigned wb = __reduce_add_sync(0xffffffffu, nb);   // (also orders the hand-copied tail before the arrival)
+            if (lane == 0) mbar_arrive_tx(bar, wb);
+            if (nb) bulk_g2s(sdst, (const void *)al, nb, bar);
         }
-        const unsigned wb = __reduce_add_sync(0xffffffffu, nb);   // (also orders the hand-copied tail before the arrival)
-        if (lane == 0) mbar_arrive_tx(bar, wb);
-        if (nb) bulk_g2s(sdst, g, nb, bar);
     };
 
     issue(0);
 
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
     for (int u = 0; u < a.nunits; ++u) {
-        if (LDG) cp_async_wait_all();   // this thread's share of unit u has landed ...
-        __syncthreads();                // ... everyone's has, and every warp has finished reading unit u - 1
-        issue(u + 1);                   // into the buffer unit u - 1 occupied
-        if (!LDG) mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
-        const UnitDev &ud = up.u[u];
+        if (u > 0) __syncthreads();     // every warp has finished reading unit u - 1: its buffer may be refilled
+        issue(u + 1);
+        mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
+        const UnitDev &ud = s_units[u];
         const unsigned st = stage0 + (u % kPipeStages) * a.stageBytes;  // shared-window address of unit u's staging
         const int Ln = ud.Ln;
         const int eop = ud.flags & 0xff;
@@ -393,17 +347,12 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         const int ngroups = (Ln + 3) >> 2;
         if (!live) continue;
         const unsigned chunkB = (unsigned)Ln * ESZ;
-        const bool direct = LDG || (ud.flags & kUnitAligned);     // columns sit 16-byte aligned at slot * ustride
-        // byte offsets of this lane's columns in the unit's staging
+        const bool direct = !UNAL || (ud.flags & kUnitAligned);     // columns sit 16-byte aligned at slot * ustride
+        const unsigned ustride = ((ud.flags & kUnitMerged) && (chunkB & 127u)) ? chunkB : chunkB + 16u;
+        // byte offsets of this lane's columns in an unaligned unit's staging: the column of slot s in run r lies at
+        // window(r) + (its global byte offset - the window's)
         unsigned co[3] = {0, 0, 0};
-        unsigned ustride = 0;
-        if (direct) {
-            ustride = LDG ? pipe_aligned_stride((chunkB + 15u) & ~15u)
-                          : (((ud.flags & kUnitMerged) && (chunkB & 127u)) ? chunkB : chunkB + 16u);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) co[j] = (unsigned)(ro[j] & 0xff) * ustride;
-        } else {
-            // BULK, unaligned: column of slot s in run r lies at window(r) + (its global byte offset - the window's)
+        if (UNAL && !direct) {
             const bool merged = (ud.flags & kUnitMerged) != 0;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -417,7 +366,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
         const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane;
         TOUT *d = (TOUT *)ud.dst + dcol;
-        const bool rotU = (ud.flags & kUnitRotU) != 0, rotV = (ud.flags & kUnitRotV) != 0;
+        const bool rotU = ROT && (ud.flags & kUnitRotU), rotV = ROT && (ud.flags & kUnitRotV);
 #pragma unroll
         for (int gi = 0; gi < kPipeLev / 4 / kPipeWarps; ++gi, d += grp8) {
             const int g = warp + gi * kPipeWarps;
@@ -426,13 +375,13 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             const unsigned lp = st + g * GB;
             if (direct) {
                 if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
-                    fma4<TIN, TACC>(acc, rw[0], lp + co[0]);
-                    fma4<TIN, TACC>(acc, rw[1], lp + co[1]);
-                    fma4<TIN, TACC>(acc, rw[2], lp + co[2]);
+                    fma4<TIN, TACC>(acc, rw[0], lp + (unsigned)(ro[0] & 0xff) * ustride);
+                    fma4<TIN, TACC>(acc, rw[1], lp + (unsigned)(ro[1] & 0xff) * ustride);
+                    fma4<TIN, TACC>(acc, rw[2], lp + (unsigned)(ro[2] & 0xff) * ustride);
                 } else if (fast) {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + co[j]);  // absent entries never touch staging (0 x garbage = NaN)
+                    for (int j = 0; j < 3; ++j)   // absent entries never touch staging (0 x garbage = NaN)
+                        if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + (unsigned)(ro[j] & 0xff) * ustride);
                 } else {
                     for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (unsigned)(s_off[k] & 0xff) * ustride);
                 }
@@ -468,7 +417,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                     const double2 q0 = __ldg((const double2 *)a.rotc + 2 * (t0 + lane)), q1 = __ldg((const double2 *)a.rotc + 2 * (t0 + lane) + 1);
                     c[0] = (TR)q0.x; c[1] = (TR)q0.y; c[2] = (TR)q1.x; c[3] = (TR)q1.y;
                 }
-                TOUT *du = (TOUT *)up.u[u - 1].dst + dcol + (size_t)gi * grp8;   // where the held zonal values go
+                TOUT *du = (TOUT *)s_units[u - 1].dst + dcol + (size_t)gi * grp8;   // where the held zonal values go
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     TR uu = (TR)h[k], vv = (TR)(TOUT)acc[k];

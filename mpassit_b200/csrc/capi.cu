@@ -61,19 +61,14 @@ static bool set_option(mprg_ctx *c, const char *key, const char *val) {
     } else if (k == "apply") {
         t.pipeOff = v == "direct";
         if (v != "direct" && v != "pipe" && !v.empty()) return false;
-    } else if (k == "staging") {
-        if (v == "bulk") t.staging = 0;
-        else if (v == "ldg") t.staging = 1;
-        else if (v == "auto" || v.empty()) t.staging = -1;
-        else return false;
+    } else if (k == "pipe_split") {
+        t.pipeSplit = v.empty() || atoi(v.c_str()) != 0;
     } else if (k == "pipe_minb") {
         t.pipeMinb = atoi(v.c_str());
     } else if (k == "cols_minb") {
         t.colsMinb = v.empty() ? 3 : atoi(v.c_str());
     } else if (k == "upload_threads") {
         t.uploadThreads = std::max(0, atoi(v.c_str()));
-    } else if (k == "ldg_below") {
-        t.ldgBelow = atof(v.c_str());
     } else {
         return false;
     }
@@ -117,9 +112,9 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
         if (const char *e = getenv("MPASSIT_GPU_ASYNC")) c->async = atoi(e) != 0;
         // tuning knobs: the environment is read here, once; mprg_set_option changes them afterwards
         for (const char *const *kv = (const char *const[]){"MPASSIT_GPU_ACC", "accumulate", "MPASSIT_GPU_APPLY", "apply",
-                                                           "MPASSIT_GPU_PIPE_MINB", "pipe_minb", "MPASSIT_GPU_STAGING", "staging",
+                                                           "MPASSIT_GPU_PIPE_MINB", "pipe_minb", "MPASSIT_GPU_PIPE_SPLIT", "pipe_split",
                                                            "MPASSIT_GPU_MINB", "cols_minb", "MPASSIT_UPLOAD_THREADS",
-                                                           "upload_threads", "MPASSIT_GPU_LDG_BELOW", "ldg_below", nullptr};
+                                                           "upload_threads", nullptr};
              *kv; kv += 2)
             if (const char *e = getenv(kv[0])) set_option(c, kv[1], e);
         for (int i = 0; i < mprg_ctx::kSlots; ++i) {
@@ -243,11 +238,10 @@ int mprg_get_option(const mprg_ctx *ctx, const char *key, char *value, size_t le
     std::string v;
     if (k == "accumulate") v = t.acc64 ? "f64" : "f32";
     else if (k == "apply") v = t.pipeOff ? "direct" : "pipe";
-    else if (k == "staging") v = t.staging == 0 ? "bulk" : t.staging == 1 ? "ldg" : "auto";
+    else if (k == "pipe_split") v = t.pipeSplit ? "1" : "0";
     else if (k == "pipe_minb") v = std::to_string(t.pipeMinb);
     else if (k == "cols_minb") v = std::to_string(t.colsMinb);
     else if (k == "upload_threads") v = std::to_string(t.uploadThreads);
-    else if (k == "ldg_below") v = std::to_string(t.ldgBelow);
     else return 59;
     snprintf(value, len, "%s", v.c_str());
     return 0;

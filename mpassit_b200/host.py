@@ -263,6 +263,10 @@ class PreparedInterp:
         self._err = _err()
 
     def __call__(self) -> "InterpIO":
+        if self.io.mem == _l.DEVICE and not getattr(self.rg, "_torch_stream", None):
+            import torch   # device tensors came from torch's stream; the engine is on its own (regrid.order_after_torch)
+
+            torch.cuda.current_stream().synchronize()
         rc = self._fn(self.rg.ctx, C.byref(self.cfg), C.byref(self.io), self._err, len(self._err))
         if rc:
             raise HostError(rc, self._err.value.decode())

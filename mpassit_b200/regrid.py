@@ -121,7 +121,20 @@ class Regridder:
         """Run engine work on torch's current CUDA stream (so torch events time it)."""
         import torch
 
-        self._ck(self.L.mprg_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self._torch_stream = torch.cuda.current_stream().cuda_stream
+        self._ck(self.L.mprg_set_stream(self.ctx, C.c_void_p(self._torch_stream)))
+
+    def order_after_torch(self, *bufs) -> None:
+        """Device tensors handed to the engine were produced on torch's current stream; the engine runs on its own
+        (non-blocking) stream unless use_torch_stream() was called.  Make what torch has queued visible first --
+        marshalling only: a compiled host orders its own streams (mprg_set_stream)."""
+        if not any(_is_torch(b) for b in bufs):
+            return
+        import torch
+
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_torch_stream", None) != cur.cuda_stream:
+            cur.synchronize()
 
     def set_async(self, on: bool) -> None:
         """Host-buffer applies return once queued; call synchronize() before reading their outputs."""
@@ -256,6 +269,7 @@ class Regridder:
             return
         if len(dsts) != n:
             raise ValueError("srcs/dsts length mismatch")
+        self.order_after_torch(srcs[0], dsts[0])
         s_mem = DEVICE if _is_torch(srcs[0]) else HOST
         d_mem = DEVICE if _is_torch(dsts[0]) else HOST
         s_dt, d_dt = _dtype_code(srcs[0]), _dtype_code(dsts[0])
@@ -287,6 +301,7 @@ class Regridder:
         n = len(srcs)
         if n == 0:
             return
+        self.order_after_torch(srcs[0], dsts_full[0])
         s_mem = DEVICE if _is_torch(srcs[0]) else HOST
         sp = (C.c_void_p * n)(*[_ptr(s) for s in srcs])
         dp = (C.c_void_p * n)(*[_ptr(d) for d in dsts_full])
@@ -296,6 +311,7 @@ class Regridder:
         self._ck(self.L.mprg_apply_into(self.ctx, route.handle, n, sp, nl, _dtype_code(srcs[0]), s_mem, dp, dst_dtype, eo, ea))
 
     def put_slab(self, stagger: int, nlev: int, slab, full, dtype: int = F32) -> None:
+        self.order_after_torch(slab, full)
         self._ck(self.L.mprg_put_slab(self.ctx, int(stagger), int(nlev), dtype, _ptr(slab), _ptr(full)))
 
     def ipc_export(self, buf) -> tuple[bytes, int]:
@@ -320,15 +336,18 @@ class Regridder:
         self._ck(self.L.mprg_set_rotation(self.ctx, ca.ctypes.data, sa.ctypes.data))
 
     def rotate_winds(self, u, v, nlev: int, stagger: int = CENTER) -> None:
+        self.order_after_torch(u, v)
         mem = DEVICE if _is_torch(u) else HOST
         self._ck(self.L.mprg_rotate_winds_on(self.ctx, int(stagger), _ptr(u), _ptr(v), int(nlev), _dtype_code(u), mem))
 
     # ---- WRF-compatibility post-ops (write_data.F90:1364-1373, 1406-1412) -----------
     def post_midlevels(self, x, mid, nlev: int, stagger: int = CENTER) -> None:
+        self.order_after_torch(x, mid)
         mem = DEVICE if _is_torch(x) else HOST
         self._ck(self.L.mprg_post_midlevels(self.ctx, int(stagger), int(nlev), _dtype_code(x), mem, _ptr(x), _ptr(mid)))
 
     def post_ptop(self, x, nlev: int, stagger: int = CENTER) -> tuple[float, float]:
+        self.order_after_torch(x)
         mem = DEVICE if _is_torch(x) else HOST
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.mprg_post_ptop(self.ctx, int(stagger), int(nlev), _dtype_code(x), mem, _ptr(x), C.byref(a), C.byref(b)))

@@ -2,7 +2,7 @@
 
   python profiles/kbench.py [--config c2] [--variants f64:3,f64:2,f32:4] [--iters 5] [--only-3d]
 
-Builds the workload once, then for every variant (accumulate type : staging mode [b<CTAs/SM>])
+Builds the workload once, then for every variant (accumulate type : launch grouping [b<CTAs/SM>])
 runs the bilinear-route stacked apply over the 3-D fields and prints per-kernel GB/s
 from the engine's per-launch CUDA events.  Also used as the short command under ncu.
 """
@@ -27,7 +27,7 @@ KIND = {0: "pipe", 1: "cols_fallback", 2: "flat", 3: "planes"}
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--variants", default="f32:bulk,f32:ldg,f64:bulk,f64:ldg")
+    ap.add_argument("--variants", default="f32:split,f32:one,f64:split")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--fields", type=int, default=12, help="number of stacked nz-level fields")
     ap.add_argument("--nlev", type=int, default=0, help="override level count (default: workload nz)")
@@ -65,18 +65,18 @@ def main():
     except Exception:
         pass
     for var in args.variants.split(","):
-        # accumulate : staging [b4|b5]   e.g. f32:bulk  f32:ldg  f64:bulk  f32:bulkb4  f32:direct
+        # accumulate : launch grouping [b4|b5]   e.g. f32:split  f32:one  f64:split  f32:splitb4  f32:direct
         acc, mode = var.split(":")
         rg.set_option("accumulate", acc)
         mb = ""
-        if "b" in mode[1:] and mode[-2] == "b":
+        if len(mode) > 2 and mode[-2] == "b" and mode[-1].isdigit():
             mode, mb = mode[:-2], mode[-1]
         rg.set_option("pipe_minb", mb or "0")
         if mode == "direct":
             rg.set_option("apply", "direct")
         else:
             rg.set_option("apply", "pipe")
-            rg.set_option("staging", mode)
+            rg.set_option("pipe_split", "1" if mode == "split" else "0")
         for _ in range(2):
             rg.apply(route, srcs, dsts, nlev=levs, epi_op=epi)
         rg.profile(True)

@@ -180,17 +180,17 @@ def test_row_slabs_of_every_rank_tile_the_full_result(engine_lib, g, nranks):
     _close(np.concatenate(pieces["snow"], 1).reshape(1, -1), g["dst_snow"])
 
 
-@pytest.mark.parametrize("staging", ["bulk", "ldg"])
+@pytest.mark.parametrize("split", ["1", "0"])
 @pytest.mark.parametrize("nlev,dt", [(5, "f32"), (60, "f32"), (61, "f32"), (130, "f32"), (60, "f64")])
-def test_fused_wind_rotation_equals_apply_then_rotate(rg, g, nlev, dt, staging):
+def test_fused_wind_rotation_equals_apply_then_rotate(rg, g, nlev, dt, split):
     """MPRG_EPI_ROT_U / ROT_V (rotation fused into the store of the apply kernel) is bit-identical to
-    mprg_apply followed by mprg_rotate_winds_on, for aligned, unaligned and multi-chunk level counts and both
-    staging modes of the column kernel."""
+    mprg_apply followed by mprg_rotate_winds_on, for aligned, unaligned and multi-chunk level counts, with the
+    pair in its own launch or sharing one with the other fields."""
     import torch
 
     from mpassit_b200 import lib as l
 
-    rg.set_option("staging", staging)
+    rg.set_option("pipe_split", split)
 
     tdt = torch.float32 if dt == "f32" else torch.float64
     n = g["bil_elem"].size
@@ -218,7 +218,7 @@ def test_fused_wind_rotation_equals_apply_then_rotate(rg, g, nlev, dt, staging):
     with pytest.raises(l.MprgError):
         rg.apply(r, [u], [c_u], nlev=[nlev], epi_op=[l.EPI_ROT_U])
     r.release()
-    rg.set_option("staging", "auto")
+    rg.set_option("pipe_split", "1")
 
 
 def test_more_ranks_than_rows_gives_empty_slabs(engine_lib, g):

@@ -75,18 +75,16 @@ def test_bilinear_structure_and_weights(rg, orc, name):
 def knobs(rg):
     """Tuning options are restored after the test (the engine is shared by the module)."""
     yield rg
-    for k, v in (("accumulate", "f32"), ("staging", "auto"), ("apply", "pipe"), ("pipe_minb", "0")):
+    for k, v in (("accumulate", "f32"), ("pipe_split", "1"), ("apply", "pipe"), ("pipe_minb", "0")):
         rg.set_option(k, v)
 
 
-@pytest.mark.parametrize("staging", ["bulk", "ldg"])
 @pytest.mark.parametrize("acc", ["f32", "f64"])
 @pytest.mark.parametrize("nlev", [1, 4, 55, 60, 61, 62, 64, 130])
-def test_apply_bilinear_levels(knobs, rg, orc, nlev, acc, staging):
+def test_apply_bilinear_levels(knobs, rg, orc, nlev, acc):
     from mpassit_b200 import lib as l
 
     rg.set_option("accumulate", acc)   # default is f32 accumulation; f64 = the reference's R8 arithmetic
-    rg.set_option("staging", staging)  # both staging modes of the column kernel (TMA bulk runs / per-thread cp.async)
 
     mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "regional_ragged")
     elem, col, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
@@ -109,8 +107,8 @@ def test_apply_bilinear_levels(knobs, rg, orc, nlev, acc, staging):
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("staging", ["bulk", "ldg"])
-def test_device_sources_at_any_element_alignment_and_mixed_stacks(knobs, rg, orc, staging):
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_device_sources_at_any_element_alignment_and_mixed_stacks(knobs, rg, orc, split):
     """Device sources are used in place.  A view that starts 4 bytes into an allocation (base not 16-byte aligned)
     and stacks mixing aligned / unaligned level counts and a wind pair go through ONE column launch and must give
     exactly what each field gives on its own from an aligned copy."""
@@ -118,7 +116,7 @@ def test_device_sources_at_any_element_alignment_and_mixed_stacks(knobs, rg, orc
 
     from mpassit_b200 import lib as l
 
-    rg.set_option("staging", staging)
+    rg.set_option("pipe_split", split)   # aligned plain fields in their own launch, or everything in one
     mesh, lon, lat, cxyz, vxyz, tri, dxyz = _setup(rg, orc, "regional_ragged")
     n, nd = mesh.nCells, lon.size
     r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
@@ -136,12 +134,12 @@ def test_device_sources_at_any_element_alignment_and_mixed_stacks(knobs, rg, orc
     n0 = rg.kernel_launches
     rg.apply(r, views, stacked, nlev=levs)
     rg.synchronize()
-    assert rg.kernel_launches - n0 <= 2                          # every 3-D field in one column launch (+ nothing flat here)
+    assert rg.kernel_launches - n0 <= (2 if split == "1" else 1)   # the 3-D fields of an apply take one or two column launches
     for k, nl in enumerate(levs):
         one = torch.full((nl, nd), float("nan"), device="cuda")
         rg.apply(r, [srcs[k]], [one], nlev=[nl])
         rg.synchronize()
-        assert torch.equal(one, stacked[k]), (staging, nl)
+        assert torch.equal(one, stacked[k]), (split, nl)
     e, c, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
     want = orc.apply(*orc.ell_to_csr(e >= 0, c, w), srcs[1].cpu().numpy(), np.float32)
     check.assert_field_close(stacked[1].cpu().numpy(), want, "61 levels, base + 4 bytes")
