@@ -148,8 +148,11 @@ int mpassit_get_map_factor(const mpassit_config *cfg, const double *xlat, int64_
  * histlist_soil are read from `varlist_dir` (NULL = the working directory, as the reference does).
  * `comm` stands in for the MPI the reference's host already has: it is called collectively by every rank
  * with op = MPASSIT_COMM_BARRIER (vals NULL), or MPASSIT_COMM_MAX / _MIN to all-reduce vals[0..n) in place
- * (P_TOP, write_data.F90:1364-1373).  May be NULL when nranks == 1. */
-enum { MPASSIT_COMM_BARRIER = 0, MPASSIT_COMM_MAX = 1, MPASSIT_COMM_MIN = 2 };
+ * (P_TOP, write_data.F90:1364-1373).  A rank that fails calls it ONCE, not collectively, with op =
+ * MPASSIT_COMM_ABORT and vals[0] = its rc before it returns: the counterpart of error_handler's mpi_abort
+ * (utils.F90:16-33) -- the communicator must bring the other ranks down (MPI_Abort), which may be blocked in a
+ * barrier or a reduction.  May be NULL when nranks == 1. */
+enum { MPASSIT_COMM_BARRIER = 0, MPASSIT_COMM_MAX = 1, MPASSIT_COMM_MIN = 2, MPASSIT_COMM_ABORT = 3 };
 typedef void (*mpassit_comm_fn)(void *arg, int op, double *vals, int n);
 typedef struct mpassit_run_stats {
     double setup_ms, read_ms, interp_ms, write_ms, total_ms; /* wall clock of the stages on this rank */

@@ -97,26 +97,35 @@ void gather_slabs(mprg_ctx *ctx, int nfields, const int *stagger, const int32_t 
     fn_send send = sym<fn_send>(ctx, "ncclSend");
     fn_recv recv = sym<fn_recv>(ctx, "ncclRecv");
     check(ctx, gstart(), "ncclGroupStart");
-    for (int f = 0; f < nfields; ++f) {
+    // inside the group nothing may throw: an open NCCL group would poison every later collective on the
+    // communicator.  The first failure is remembered, the group is always closed, then the failure is reported.
+    int bad = 0;
+    const char *badWhat = nullptr;
+    auto note = [&](int rc, const char *what) {
+        if (rc != 0 && !bad) { bad = rc; badWhat = what; }
+    };
+    for (int f = 0; f < nfields && !bad; ++f) {
         const Target &tg = ctx->target[stagger[f]];
         const int64_t nFull = (int64_t)tg.ni * tg.nj, nMine = tg.nSlab();
         if (ctx->rank != root) {
-            for (int l = 0; l < nlev[f] && nMine > 0; ++l)
-                check(ctx, send((const unsigned char *)slab_dev[f] + (size_t)l * nMine * esz, (size_t)nMine * esz, kNcclInt8,
-                                root, ctx->nccl, ctx->stream), "ncclSend");
+            for (int l = 0; l < nlev[f] && nMine > 0 && !bad; ++l)
+                note(send((const unsigned char *)slab_dev[f] + (size_t)l * nMine * esz, (size_t)nMine * esz, kNcclInt8,
+                          root, ctx->nccl, ctx->stream), "ncclSend");
         } else {
             for (int p = 0; p < ctx->nranks; ++p) {
                 if (p == root) continue;
                 int32_t j0, j1;
                 para_range(tg.nj, ctx->nranks, p, &j0, &j1);
                 const int64_t ns = (int64_t)(j1 - j0) * tg.ni, off = (int64_t)j0 * tg.ni;
-                for (int l = 0; l < nlev[f] && ns > 0; ++l)
-                    check(ctx, recv((unsigned char *)full_dev[f] + ((size_t)l * nFull + off) * esz, (size_t)ns * esz,
-                                    kNcclInt8, p, ctx->nccl, ctx->stream), "ncclRecv");
+                for (int l = 0; l < nlev[f] && ns > 0 && !bad; ++l)
+                    note(recv((unsigned char *)full_dev[f] + ((size_t)l * nFull + off) * esz, (size_t)ns * esz,
+                              kNcclInt8, p, ctx->nccl, ctx->stream), "ncclRecv");
             }
         }
     }
-    check(ctx, gend(), "ncclGroupEnd");
+    const int endrc = gend();
+    if (bad) check(ctx, bad, badWhat);
+    check(ctx, endrc, "ncclGroupEnd");
 }
 
 }  // namespace mprg

@@ -70,7 +70,7 @@ class RunStats(C.Structure):
 
 
 COMM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int)
-COMM_BARRIER, COMM_MAX, COMM_MIN = 0, 1, 2
+COMM_BARRIER, COMM_MAX, COMM_MIN, COMM_ABORT = 0, 1, 2, 3
 
 _lib = None
 
@@ -320,6 +320,15 @@ def torch_comm(group=None):
     import torch.distributed as dist
 
     def fn(_arg, op, vals, n):
+        if op == COMM_ABORT:
+            # error_handler -> mpi_abort (utils.F90:16-33): peers may be blocked in a collective, so the whole job
+            # goes down, the failing rank's code first
+            import os
+            import sys
+
+            sys.stderr.write(f"mpassit_run: FATAL ERROR on a rank (rc {int(vals[0])}); aborting the job\n")
+            sys.stderr.flush()
+            os._exit(int(vals[0]) & 0xff or 1)
         if op == COMM_BARRIER:
             dist.barrier(group=group)
             return

@@ -149,6 +149,10 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
         const bool dry = device < 0;
         double tq = now_ms();
         if (!dry) ck(nullptr, mprg_init(device, rank, nranks, &ctx), "mprg_init");
+        // whatever MPASSIT_GPU_ASYNC says: the write stage hands every downloaded buffer to a writer thread as soon
+        // as mprg_download returns, so downloads must be blocking here (interp_data switches asynchronous applies on
+        // for its own host-buffer passes and restores this setting)
+        if (!dry) ck(ctx, mprg_set_async(ctx, 0), "mprg_set_async");
         st.init_ms = now_ms() - tq;
         tq = now_ms();
 
@@ -833,6 +837,12 @@ int mpassit_run(const char *namelist_file, const char *varlist_dir, int device, 
     } catch (const Fail &f) {
         if (err && errlen) std::snprintf(err, errlen, "%s", f.msg.c_str());
         rc_out = f.rc;
+        // error_handler (utils.F90:16-33) ends with mpi_abort: the other ranks must not be left waiting in a barrier
+        // or in the P_TOP reductions.  The host's communicator decides how (MPI_Abort in a Fortran host).
+        if (nranks > 1 && comm) {
+            double code = (double)(f.rc ? f.rc : 1);
+            comm(comm_arg, MPASSIT_COMM_ABORT, &code, 1);
+        }
     }
     if (writer.joinable()) writer.join();
     if (ctx) {
