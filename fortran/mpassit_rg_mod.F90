@@ -31,7 +31,7 @@ module mpassit_rg_mod
                                         MPRG_EPI_ROT_U = 3, MPRG_EPI_ROT_V = 4
 
   public :: mprg_init, mprg_finalize, mprg_last_error, mprg_error_message
-  public :: mprg_set_mesh, mprg_set_target, mprg_set_grid_kind, mprg_set_option, mprg_get_slab
+  public :: mprg_set_mesh, mprg_set_target, mprg_set_grid_kind, mprg_set_option, mprg_set_weight_cache, mprg_get_slab
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
   public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
@@ -108,6 +108,13 @@ module mpassit_rg_mod
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx
        integer(c_int), value :: kind
+     end function
+     !> cross-run weight cache directory (NUL-terminated); the reference regenerates every matrix in every run
+     !! (program_setup.F90:72-75)
+     integer(c_int) function mprg_set_weight_cache(ctx, dir) bind(C, name="mprg_set_weight_cache")
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(in) :: dir(*)
      end function
      !> tuning knob (include/mpassit_rg.h); key and value are NUL-terminated C strings,
      !! e.g. mprg_set_option(ctx, "accumulate"//c_null_char, "f64"//c_null_char) for the reference's R8 arithmetic

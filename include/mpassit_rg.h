@@ -145,6 +145,15 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
 int mprg_release(mprg_ctx *ctx, mprg_route *rh);
 /* drop every memoised route (forces the next store to rebuild) */
 int mprg_clear_routes(mprg_ctx *ctx);
+/* Cross-run weight cache: the reference regenerates every matrix in every run (weights are never
+ * kept, program_setup.F90:72-75).  With a cache directory set (or MPASSIT_WEIGHT_CACHE in the environment at
+ * mprg_init), mprg_store looks the route up under a 128-bit key of everything that determines it -- source mesh,
+ * the destination points of this rank's slab, grid topology, method, source location, stagger, slab bounds, engine
+ * version; computed on the device from the arrays weight generation reads -- loads its CSR from
+ * <dir>/mprg_<key>.w when present and writes that file after generating it otherwise.  NULL or "" switches it off.
+ * Results with and without the cache are byte-identical.  hits / stores count routes loaded / written since init. */
+int mprg_set_weight_cache(mprg_ctx *ctx, const char *dir);
+int mprg_weight_cache_stats(const mprg_ctx *ctx, int64_t *hits, int64_t *stores);
 
 /* sizes of this rank's part of the route: destination points (slab), stored
  * weights, unmapped destination points, source entities (cells/nodes/points) */

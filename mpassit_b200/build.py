@@ -29,6 +29,7 @@ UNITS = [
     ("conserve.cu", ["-fmad=false"], ["MPRG_HAVE_CONSERVE"]),
     ("stagger.cu", ["-fmad=false"], ["MPRG_HAVE_STAGGER", "MPRG_HAVE_NODE"]),
     ("apply.cu", [], []),
+    ("wcache.cu", [], []),
     ("gather.cu", [], []),
 ]
 

@@ -113,7 +113,8 @@ __host__ __device__ constexpr size_t pipe_fixed_bytes() {
            + kPipeCap * 4                           // s_uniq
            + kPipeCap                               // s_urun: run index of every slot
            + kPipeCap                               // s_runFirst: first slot of every run
-           + kPipeCap * sizeof(TACC);               // s_w
+           + kPipeCap * sizeof(TACC)                // s_w
+           + kPipeTile * 8 * sizeof(TACC);          // s_row: per target 3 weights + packed slots / runs / length
 }
 // bytes of one stage that a unit needs for a tile of nu columns in nruns runs.  Aligned units: slots packed at the
 // column size so that a run is contiguous in shared memory too -- unless that size is a multiple of 128 bytes (every
@@ -208,6 +209,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     unsigned char *s_urun = (unsigned char *)(s_uniq + kPipeCap);
     unsigned char *s_runFirst = s_urun + kPipeCap;
     TACC *s_w = (TACC *)(s_runFirst + kPipeCap);
+    TACC *s_row = s_w + kPipeCap;   // [32][8 words of TACC]: w0 w1 w2 | (slot0 | slot1 << 8 | slot2 << 16 | len << 24) | (run0 | run1 << 8 | run2 << 16)
     UnitDev *s_units = (UnitDev *)(smem + pipe_fixed_bytes<TACC>());
     unsigned char *s_stage = smem + a.stageOff;
 
@@ -243,21 +245,34 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     if (UNAL && tid < nu && (tid == 0 || s_urun[tid] != s_urun[tid - 1])) s_runFirst[s_urun[tid]] = (unsigned char)tid;
     __syncthreads();
 
-    // this lane's target; rows with <= 3 entries stay in registers
+    // Per target (= lane): rows with <= 3 entries are packed once -- 3 weights, the 3 slots, the 3 run indices, the
+    // length -- so that every unit re-reads them with one or two 16-byte shared loads instead of keeping 6-8 registers
+    // alive across the copy issue and the barrier (the compiler spilled them to local memory: 14 % of the stall
+    // samples of the first v7 build sat on those reloads)
     const bool live = lane < ntile;
-    int rbeg = 0, rlen = 0;
-    if (live) { rbeg = s_rowptr[lane] - base; rlen = s_rowptr[lane + 1] - s_rowptr[lane]; }
-    TACC rw[3];
-    int ro[3];
+    bool fast, all3;
+    {
+    int rlen = 0;
+    if (live) rlen = s_rowptr[lane + 1] - s_rowptr[lane];
+    if (warp == 0) {
+        const int rbeg0 = live ? s_rowptr[lane] - base : 0;
+        unsigned pk = (unsigned)min(rlen, 255) << 24, pr = 0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const bool h = j < rlen && rlen <= 3;
-        rw[j] = h ? s_w[rbeg + j] : (TACC)0;
-        ro[j] = h ? (int)s_off[rbeg + j] : 0;
+        for (int j = 0; j < 3; ++j) {
+            const bool h = j < rlen && rlen <= 3;
+            s_row[8 * lane + j] = h ? s_w[rbeg0 + j] : (TACC)0;
+            const unsigned o = h ? (unsigned)s_off[rbeg0 + j] : 0u;
+            pk |= (o & 0xffu) << (8 * j);
+            pr |= (o >> 8) << (8 * j);
+        }
+        ((unsigned *)(s_row + 8 * lane + 3))[0] = pk;
+        ((unsigned *)(s_row + 8 * lane + 3))[sizeof(TACC) / 4] = pr;   // fp32: word 4; fp64: word 8 of the 16-word row
     }
-    const bool fast = __all_sync(0xffffffffu, rlen <= 3);
+    fast = __all_sync(0xffffffffu, rlen <= 3);
     // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
-    const bool all3 = __all_sync(0xffffffffu, live && rlen == 3);
+    all3 = __all_sync(0xffffffffu, live && rlen == 3);
+    }
+    const unsigned row0 = (unsigned)__cvta_generic_to_shared(s_row + 8 * lane);
 
     const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
     const unsigned hold0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.holdOff;
@@ -333,6 +348,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     };
 
     issue(0);
+    __syncthreads();   // s_row is visible to every warp
 
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
     for (int u = 0; u < a.nunits; ++u) {
@@ -346,6 +362,24 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         const TACC earg = (TACC)ud.epi_arg;
         const int ngroups = (Ln + 3) >> 2;
         if (!live) continue;
+        // this lane's row (weights, slots, runs): one or two 16-byte shared loads per unit
+        TACC rw[3];
+        unsigned pk, pr = 0;
+        if (sizeof(TACC) == 4) {
+            float4 q;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(row0));
+            rw[0] = (TACC)q.x; rw[1] = (TACC)q.y; rw[2] = (TACC)q.z; pk = __float_as_uint(q.w);
+            if (UNAL) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pr) : "r"(row0 + 16));
+        } else {
+            double x, y, z;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(x), "=d"(y) : "r"(row0));
+            asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(z) : "r"(row0 + 16));
+            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pk) : "r"(row0 + 24));
+            if (UNAL) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pr) : "r"(row0 + 32));
+            rw[0] = (TACC)x; rw[1] = (TACC)y; rw[2] = (TACC)z;
+        }
+        const int rlen = (int)(pk >> 24);                                       // (fast paths: <= 3)
+        const int rbeg = s_rowptr[lane] - base, rend = s_rowptr[lane + 1] - base;   // (generic rows only)
         const unsigned chunkB = (unsigned)Ln * ESZ;
         const bool direct = !UNAL || (ud.flags & kUnitAligned);     // columns sit 16-byte aligned at slot * ustride
         const unsigned ustride = ((ud.flags & kUnitMerged) && (chunkB & 127u)) ? chunkB : chunkB + 16u;
@@ -356,7 +390,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             const bool merged = (ud.flags & kUnitMerged) != 0;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const int sl = ro[j] & 0xff, r = merged ? (ro[j] >> 8) : sl;
+                const int sl = (int)((pk >> (8 * j)) & 0xffu), r = merged ? (int)((pr >> (8 * j)) & 0xffu) : sl;
                 const int f = merged ? (int)s_runFirst[r] : sl;
                 const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)s_uniq[f] * ud.nlev + ud.L0) * ESZ;
                 co[j] = (((unsigned)f * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u) + (unsigned)(a0 & 15) +
@@ -375,15 +409,15 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             const unsigned lp = st + g * GB;
             if (direct) {
                 if (all3) {             // straight line: 3 x (LDS.128 + 4 FFMA)
-                    fma4<TIN, TACC>(acc, rw[0], lp + (unsigned)(ro[0] & 0xff) * ustride);
-                    fma4<TIN, TACC>(acc, rw[1], lp + (unsigned)(ro[1] & 0xff) * ustride);
-                    fma4<TIN, TACC>(acc, rw[2], lp + (unsigned)(ro[2] & 0xff) * ustride);
+                    fma4<TIN, TACC>(acc, rw[0], lp + (pk & 0xffu) * ustride);
+                    fma4<TIN, TACC>(acc, rw[1], lp + ((pk >> 8) & 0xffu) * ustride);
+                    fma4<TIN, TACC>(acc, rw[2], lp + ((pk >> 16) & 0xffu) * ustride);
                 } else if (fast) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j)   // absent entries never touch staging (0 x garbage = NaN)
-                        if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + (unsigned)(ro[j] & 0xff) * ustride);
+                        if (j < rlen) fma4<TIN, TACC>(acc, rw[j], lp + ((pk >> (8 * j)) & 0xffu) * ustride);
                 } else {
-                    for (int k = rbeg; k < rbeg + rlen; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (unsigned)(s_off[k] & 0xff) * ustride);
+                    for (int k = rbeg; k < rend; ++k) fma4<TIN, TACC>(acc, s_w[k], lp + (unsigned)(s_off[k] & 0xff) * ustride);
                 }
             } else if (fast) {
 #pragma unroll
@@ -391,7 +425,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                     if (j < rlen) fma4u<TIN, TACC>(acc, rw[j], lp + co[j]);
             } else {
                 const bool merged = (ud.flags & kUnitMerged) != 0;
-                for (int k = rbeg; k < rbeg + rlen; ++k) {
+                for (int k = rbeg; k < rend; ++k) {
                     const int sl = s_off[k] & 0xff, r = merged ? (s_off[k] >> 8) : sl;
                     const int f = merged ? (int)s_runFirst[r] : sl;
                     const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)s_uniq[f] * ud.nlev + ud.L0) * ESZ;

@@ -110,6 +110,7 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
         MPRG_CUDA(cudaEventCreateWithFlags(&c->evDl, cudaEventDisableTiming));
         MPRG_CUDA(cudaMallocHost(&c->peekBuf, 256));
         if (const char *e = getenv("MPASSIT_GPU_ASYNC")) c->async = atoi(e) != 0;
+        if (const char *e = getenv("MPASSIT_WEIGHT_CACHE")) c->cacheDir = e;
         // tuning knobs: the environment is read here, once; mprg_set_option changes them afterwards
         for (const char *const *kv = (const char *const[]){"MPASSIT_GPU_ACC", "accumulate", "MPASSIT_GPU_APPLY", "apply",
                                                            "MPASSIT_GPU_PIPE_MINB", "pipe_minb", "MPASSIT_GPU_PIPE_SPLIT", "pipe_split",
@@ -223,6 +224,19 @@ int mprg_scratch(mprg_ctx *ctx, int slot, size_t bytes, void **ptr) {
 }
 
 int mprg_has_rotation(const mprg_ctx *ctx) { return ctx && ctx->haveRot ? 1 : 0; }
+
+int mprg_set_weight_cache(mprg_ctx *ctx, const char *dir) {
+    MPRG_ENTER(ctx)
+    ctx->cacheDir = dir ? dir : "";
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_weight_cache_stats(const mprg_ctx *ctx, int64_t *hits, int64_t *stores) {
+    if (!ctx) return 1;
+    if (hits) *hits = ctx->cacheHits;
+    if (stores) *stores = ctx->cacheStores;
+    return 0;
+}
 
 int mprg_set_option(mprg_ctx *ctx, const char *key, const char *value) {
     MPRG_ENTER(ctx)
@@ -364,14 +378,21 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
     std::unique_ptr<mprg_route> r(new mprg_route());  // after `swap`: on failure its buffers are freed on the store stream
     r->method = method; r->src_loc = src_loc; r->dst_stagger = dst_stagger;
     MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_NEAREST_STOD) store_nearest(ctx, r.get());
-    else if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_BILINEAR) store_bilinear_element(ctx, r.get());
-    else if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_CONSERVE) store_conserve(ctx, r.get());
-    else if (src_loc == MPRG_SRC_MESH_NODE && method == MPRG_BILINEAR) store_bilinear_node(ctx, r.get());
-    else if (src_loc == MPRG_SRC_GRID_CENTER && method == MPRG_BILINEAR) store_bilinear_grid(ctx, r.get());
-    else fail(54, "mprg_store: unsupported (method %d, src_loc %d)", method, src_loc);
+    const bool known = (src_loc == MPRG_SRC_MESH_ELEMENT && (method == MPRG_NEAREST_STOD || method == MPRG_BILINEAR || method == MPRG_CONSERVE)) ||
+                       (src_loc == MPRG_SRC_MESH_NODE && method == MPRG_BILINEAR) || (src_loc == MPRG_SRC_GRID_CENTER && method == MPRG_BILINEAR);
+    if (!known) fail(54, "mprg_store: unsupported (method %d, src_loc %d)", method, src_loc);
+    unsigned long long ckey[2] = {0, 0};
+    const bool cached = !ctx->cacheDir.empty() && wcache_load(ctx, r.get(), ckey);   // cross-run weight cache (wcache.cu)
+    if (!cached) {
+        if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_NEAREST_STOD) store_nearest(ctx, r.get());
+        else if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_BILINEAR) store_bilinear_element(ctx, r.get());
+        else if (src_loc == MPRG_SRC_MESH_ELEMENT && method == MPRG_CONSERVE) store_conserve(ctx, r.get());
+        else if (src_loc == MPRG_SRC_MESH_NODE && method == MPRG_BILINEAR) store_bilinear_node(ctx, r.get());
+        else store_bilinear_grid(ctx, r.get());
+    }
     r->dstNi = ctx->target[dst_stagger].ni;
     route_finish(ctx, r.get());
+    if (!cached && !ctx->cacheDir.empty()) wcache_save(ctx, r.get(), ckey);
     MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));  // every allocation and kernel of the route is complete
     float ms = 0.f;

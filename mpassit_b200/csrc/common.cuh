@@ -183,6 +183,8 @@ struct mprg_ctx {
     int device = 0, rank = 0, nranks = 1;
     mprg_tuning tune;
     int gridKind = MPRG_GRID_NOPERI;      // mprg_set_grid_kind: topology of the target grid as a regrid source
+    std::string cacheDir;                 // mprg_set_weight_cache: directory of the cross-run weight cache ("" = off)
+    int64_t cacheHits = 0, cacheStores = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t store_stream = nullptr;  // weight generation runs here, beside the copy-bound apply pipeline
@@ -298,6 +300,10 @@ void bswap_device(mprg_ctx *ctx, void *x, size_t count, size_t elem, cudaStream_
 void post_affine_device(mprg_ctx *ctx, void *x, size_t count, int dtype, double scale, double offset);
 void post_midlevels_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, void *mid);
 void post_ptop_device(mprg_ctx *ctx, int64_t n, int32_t nlev, int dtype, const void *x, double *out2_dev);
+
+// wcache.cu: cross-run weight cache
+bool wcache_load(mprg_ctx *ctx, mprg_route *r, unsigned long long key[2]);
+void wcache_save(mprg_ctx *ctx, const mprg_route *r, const unsigned long long key[2]);
 
 // gather.cu
 void comm_destroy(mprg_ctx *ctx);

@@ -220,6 +220,16 @@ class Regridder:
         if stagger == CENTER:
             self.nSrc[SRC_GRID_CENTER] = nj * ni
 
+    def set_weight_cache(self, directory: str | None) -> None:
+        """Cross-run weight cache directory (mprg_set_weight_cache); None switches it off."""
+        self._ck(self.L.mprg_set_weight_cache(self.ctx, directory.encode() if directory else None))
+
+    def weight_cache_stats(self) -> tuple[int, int]:
+        """(routes loaded from the cache, routes written to it) since init."""
+        h, s_ = C.c_int64(), C.c_int64()
+        self.L.mprg_weight_cache_stats(self.ctx, C.byref(h), C.byref(s_))
+        return h.value, s_.value
+
     def set_option(self, key: str, value) -> None:
         """Tuning knob (include/mpassit_rg.h: mprg_set_option), e.g. ("accumulate", "f64"), ("staging", "ldg")."""
         self._ck(self.L.mprg_set_option(self.ctx, key.encode(), str(value).encode()))
