@@ -429,12 +429,17 @@ static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, co
     ctx->launches++;
 }
 
+static RecLayout route_rec_layout(const mprg_route *r, int wsize);
+static const unsigned char *route_rec64(mprg_ctx *ctx, mprg_route *r);
+
 // Every 3-D field of an apply in ONE launch of the pipelined kernel (kPipeMaxUnits units per launch).
 // Fields flagged MPRG_EPI_ROT_U / ROT_V are wind pairs whose rotation is fused into the store.
 // Returns false if this route / field set does not fit the kernel (the register-gather kernel takes over).
 template <typename TIN, typename TOUT, typename TACC>
 static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<FieldDev> &fields, DstLayout dl) {
-    if (ctx->tune.pipeOff || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->entrySlot.p) return false;
+    if (ctx->tune.pipeOff || r->tileEntriesMax <= 0 || r->tileEntriesMax > kPipeCap || !r->rec32.p) return false;
+    const RecLayout lay = route_rec_layout(r, (int)sizeof(TACC));
+    const unsigned char *rec = sizeof(TACC) == 8 ? route_rec64(ctx, const_cast<mprg_route *>(r)) : r->rec32.p;
     std::vector<UnitDev> units;
     auto unit_of = [&](const FieldDev &f, int L0) {
         UnitDev u;
@@ -478,9 +483,8 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         groups.push_back(units);
     }
     PipeArgs<TACC> pa;
-    pa.rowptr = r->rowptr.p; pa.col = r->col.p;
-    if (sizeof(TACC) == 8) pa.w = (const TACC *)r->w.p; else pa.w = (const TACC *)r->w32.p;
-    pa.tileUPtr = r->tileUPtr.p; pa.tileUCols = r->tileUCols.p; pa.tileURun = r->tileURun.p; pa.entrySlot = r->entrySlot.p;
+    pa.rec = rec;
+    pa.lay = lay;
     pa.nDst = r->nDst;
     pa.dstLev = dl.lev; pa.dstOff = dl.off;
     pa.ni = r->dstNi;
@@ -509,7 +513,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
                                                               (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
             }
             stage = (stage + 15) & ~(size_t)15;
-            const size_t fixed = (pipe_fixed_bytes<TACC>() + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
+            const size_t fixed = ((size_t)kPipeSmemHead + lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
             const size_t hold = (mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
             const size_t smemBytes = fixed + kPipeStages * stage + hold;
             if (smemBytes + 1024 > (size_t)227 * 1024) return false;
@@ -545,42 +549,58 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
 
 void scan_counts(mprg_ctx *ctx, const int32_t *cnt, int32_t *rowptr, int64_t nPlus1);  // locate.cu
 
+static RecLayout route_rec_layout(const mprg_route *r, int wsize) {
+    return rec_layout(wsize, r->tileUniqMax, r->tileRunsMax, r->tileEntriesMax, r->tileRowMax > 3);
+}
+
+template <typename TW>
+static void route_build_records(mprg_ctx *ctx, mprg_route *r, const TW *w, DevBuf<unsigned char> &out) {
+    const int tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
+    const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * tilesPerRow);
+    const RecLayout lay = route_rec_layout(r, (int)sizeof(TW));
+    out.alloc((size_t)tiles * lay.stride);
+    MPRG_CUDA(cudaMemsetAsync(out.p, 0, (size_t)tiles * lay.stride, ctx->stream));
+    k_tile_schedule<true, TW><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, w, r->nDst, r->dstNi, tilesPerRow,
+                                                                       nullptr, nullptr, out.p, lay);
+    ctx->launches++;
+    MPRG_CUDA(cudaGetLastError());
+}
+
+// records with fp64 weights (fp64 accumulation / fp64 fields): built the first time an apply needs them
+static const unsigned char *route_rec64(mprg_ctx *ctx, mprg_route *r) {
+    if (!r->rec64.p) {
+        if (ctx->capturing) fail(46, "mprg_apply: this route's fp64 schedule is not built yet; run the pass once before mprg_capture_begin");
+        route_build_records<double>(ctx, r, r->w.p, r->rec64);
+    }
+    return r->rec64.p;
+}
+
 // builds the route's tile schedule (the "communication schedule" half of an ESMF route handle)
 void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
-    r->tileEntriesMax = r->tileUniqMax = r->tileRunsMax = 0;
+    r->tileEntriesMax = r->tileUniqMax = r->tileRunsMax = r->tileRowMax = 0;
     if (r->nDst <= 0 || r->nnz <= 0) return;
     if (r->dstNi <= 0) r->dstNi = (int32_t)std::min<int64_t>(r->nDst, 0x7fffffff);
     const int tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * tilesPerRow);
-    DevBuf<int32_t> mm(3), cnt(tiles + 1);
-    MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 3 * sizeof(int32_t), ctx->stream));
-    MPRG_CUDA(cudaMemsetAsync(cnt.p, 0, (tiles + 1) * sizeof(int32_t), ctx->stream));
-    k_tile_schedule<false><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
-                                                                   mm.p, mm.p + 1, mm.p + 2, cnt.p, nullptr, nullptr, nullptr,
-                                                                   nullptr, nullptr);
+    DevBuf<int32_t> mm(4);
+    DevBuf<unsigned long long> tot(2);
+    MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 4 * sizeof(int32_t), ctx->stream));
+    MPRG_CUDA(cudaMemsetAsync(tot.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    k_tile_schedule<false, float><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->w32.p, r->nDst, r->dstNi,
+                                                                          tilesPerRow, mm.p, tot.p, nullptr, RecLayout{});
     ctx->launches++;
-    int32_t h[3] = {0, 0, 0};
+    int32_t h[4] = {0, 0, 0, 0};
+    unsigned long long ht[2] = {0, 0};
     peek(ctx, h, mm.p, sizeof h);
+    peek(ctx, ht, tot.p, sizeof ht);
     r->tileEntriesMax = h[0];
     r->tileUniqMax = h[1];
     r->tileRunsMax = h[2];
+    r->tileRowMax = h[3];
     if (h[0] > kPipeCap) return;  // no schedule: register-gather kernels only
-    r->tileUPtr.alloc(tiles + 1);
-    scan_counts(ctx, cnt.p, r->tileUPtr.p, (int64_t)tiles + 1);
-    int32_t total = 0;
-    peek(ctx, &total, r->tileUPtr.p + tiles, sizeof(int32_t));
-    r->tileUCols.alloc(total > 0 ? total : 1);
-    r->tileURun.alloc(total > 0 ? total : 1);
-    r->entrySlot.alloc(r->nnz);
-    DevBuf<unsigned long long> runs(1);
-    MPRG_CUDA(cudaMemsetAsync(runs.p, 0, sizeof(unsigned long long), ctx->stream));
-    k_tile_schedule<true><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->nDst, r->dstNi, tilesPerRow,
-                                                                  nullptr, nullptr, nullptr, nullptr, r->tileUPtr.p,
-                                                                  r->tileUCols.p, r->tileURun.p, r->entrySlot.p, runs.p);
-    ctx->launches++;
-    unsigned long long hruns = 0;
-    peek(ctx, &hruns, runs.p, sizeof hruns);
-    r->schedTiles = tiles; r->schedCols = total; r->schedRuns = (int64_t)hruns;
+    route_build_records<float>(ctx, r, r->w32.p, r->rec32);
+    r->rec64 = DevBuf<unsigned char>();
+    r->schedTiles = tiles; r->schedCols = (int64_t)ht[0]; r->schedRuns = (int64_t)ht[1];
 }
 
 // cols: every 3-D field of the apply (wind pairs adjacent, ROT_U then ROT_V); flat: 2-D fields and short columns;

@@ -60,17 +60,46 @@ constexpr int kUnitAligned = 0x100;                  // column chunks start 16-b
 constexpr int kUnitRotU = 0x200, kUnitRotV = 0x400;  // wind pair: this unit is the zonal / meridional chunk
 constexpr int kUnitMerged = 0x800;                   // the chunk is the whole column: runs of consecutive ids are contiguous in memory
 
+// Tile record: everything the kernel needs to know about one tile, precomputed when the route is built
+// (k_tile_schedule) and laid out so that ONE bulk copy brings it into shared memory -- the prologue of a tile is a
+// single memory latency instead of three dependent ones (row pointers -> weights / slots; tile pointer -> columns),
+// which cost 17 % of the stall samples of the main launch and 38 % of a 4-unit launch.  Fixed stride per route
+// (sized by the route's tile maxima), sections at fixed offsets:
+//   header   16 B   uint16 nu, cnt, nruns, ntile; uint32 flags (bit 0: every row <= 3 entries, bit 1: every row == 3
+//                   entries and the tile is full); int32 reserved
+//   rows     32 x 8 words of the weight type: per target  w0 w1 w2 | slot0 | slot1 << 8 | slot2 << 16 | len << 24 |
+//                   run0 | run1 << 8 | run2 << 16   (rows of <= 3 entries; longer rows: len only)
+//   uniq     int32 [nuCap]   distinct source columns of the tile, ascending
+//   urun     uint8 [nuCap]   run (maximal sequence of consecutive ids) each of them belongs to
+//   runFirst uint8 [runCap]  first slot of every run
+//   (routes with rows of more than 3 entries only -- conservative:)
+//   rowoff   uint16 [34]     entry offset of every target's row
+//   eoff     uint16 [entCap] per entry: slot | run << 8
+//   ew       weight [entCap] per entry
+struct RecLayout {
+    int32_t stride, offUniq, offUrun, offRunFirst, offRowoff, offEoff, offEw;
+};
+__host__ __device__ inline RecLayout rec_layout(int wsize, int nuMax, int runsMax, int entMax, bool generic) {
+    RecLayout L;
+    int o = 16 + kPipeTile * 8 * wsize;
+    L.offUniq = o; o += ((nuMax + 3) & ~3) * 4;
+    L.offUrun = o; o += (nuMax + 15) & ~15;
+    L.offRunFirst = o; o += (runsMax + 15) & ~15;
+    L.offRowoff = L.offEoff = L.offEw = 0;
+    if (generic) {
+        L.offRowoff = o; o += 80;
+        L.offEoff = o; o += ((entMax + 7) & ~7) * 2;
+        L.offEw = o; o += ((entMax + 1) & ~1) * wsize;
+    }
+    L.stride = (o + 15) & ~15;
+    return L;
+}
+constexpr unsigned kRecFast = 1u, kRecAll3 = 2u;
+
 template <typename TW>
 struct PipeArgs {
-    const int32_t *rowptr;
-    const int32_t *col;
-    const TW *w;
-    // tile schedule built once per route (k_tile_schedule): unique source columns of every tile in ascending
-    // order, the run each of them belongs to, and per CSR entry the index of its column in that list
-    const int32_t *tileUPtr;        // [nTiles + 1]
-    const int32_t *tileUCols;       // [tileUPtr[nTiles]]
-    const unsigned char *tileURun;  // [tileUPtr[nTiles]] run index of the column within its tile
-    const unsigned char *entrySlot; // [nnz]
+    const unsigned char *rec;  // tile records of the route for weight type TW (k_tile_schedule)
+    RecLayout lay;
     int64_t nDst;
     // destination addressing: point t of level l of a field goes to dst[l * dstLev + dstOff + t].  A slab
     // buffer has dstLev = nDst, dstOff = 0; writing straight into a full-grid [lev][nj][ni] field (this
@@ -80,7 +109,7 @@ struct PipeArgs {
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
     int32_t nunits;
-    int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the unit descriptors)
+    int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the record and the unit descriptors)
     int32_t stageBytes; // bytes of one stage (host: the largest unit's need at the route's tile maxima)
     int32_t holdOff;    // byte offset of the wind-pair hold buffer (kModeRot launches)
     // kModeRot launches only: per-point rotation constants of this rank's destination rows, in the arithmetic type
@@ -105,17 +134,8 @@ __device__ __forceinline__ void bulk_g2s(unsigned smemDst, const void *gmem, uns
                  "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-// fixed part of the dynamic shared memory (bytes); the unit descriptors, the stages and (kModeRot) the hold buffer follow
-template <typename TACC>
-__host__ __device__ constexpr size_t pipe_fixed_bytes() {
-    return 64 * 4                                   // s_rowptr (33 used) + mbarriers
-           + kPipeCap * 2                           // s_off: slot | run << 8 of every entry's column
-           + kPipeCap * 4                           // s_uniq
-           + kPipeCap                               // s_urun: run index of every slot
-           + kPipeCap                               // s_runFirst: first slot of every run
-           + kPipeCap * sizeof(TACC)                // s_w
-           + kPipeTile * 8 * sizeof(TACC);          // s_row: per target 3 weights + packed slots / runs / length
-}
+// dynamic shared memory: [mbarriers 64 B][tile record][unit descriptors][stages][hold buffer (kModeRot)]
+constexpr int kPipeSmemHead = 64;
 // bytes of one stage that a unit needs for a tile of nu columns in nruns runs.  Aligned units: slots packed at the
 // column size so that a run is contiguous in shared memory too -- unless that size is a multiple of 128 bytes (every
 // slot would start on bank 0) or the chunk is not the whole column: 16 bytes of padding and one copy per column then.
@@ -202,77 +222,45 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     using TR = typename RotMath<TOUT, TACC>::type;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    int32_t *s_rowptr = (int32_t *)smem;            // [33]; mbarriers at [48..51]
-    unsigned long long *s_mbar = (unsigned long long *)(s_rowptr + 48);  // one per stage
-    unsigned short *s_off = (unsigned short *)(s_rowptr + 64);  // per entry: slot | run << 8 of its column
-    int32_t *s_uniq = (int32_t *)(s_off + kPipeCap);
-    unsigned char *s_urun = (unsigned char *)(s_uniq + kPipeCap);
-    unsigned char *s_runFirst = s_urun + kPipeCap;
-    TACC *s_w = (TACC *)(s_runFirst + kPipeCap);
-    TACC *s_row = s_w + kPipeCap;   // [32][8 words of TACC]: w0 w1 w2 | (slot0 | slot1 << 8 | slot2 << 16 | len << 24) | (run0 | run1 << 8 | run2 << 16)
-    UnitDev *s_units = (UnitDev *)(smem + pipe_fixed_bytes<TACC>());
+    unsigned long long *s_mbar = (unsigned long long *)smem;        // [0..1] one per stage, [2] the tile record
+    unsigned char *s_rec = smem + kPipeSmemHead;                    // the tile record (RecLayout)
+    UnitDev *s_units = (UnitDev *)(s_rec + a.lay.stride);
     unsigned char *s_stage = smem + a.stageOff;
+    const int32_t *s_uniq = (const int32_t *)(s_rec + a.lay.offUniq);
+    const unsigned char *s_urun = s_rec + a.lay.offUrun;
+    const unsigned char *s_runFirst = s_rec + a.lay.offRunFirst;
+    const unsigned short *s_rowoff = (const unsigned short *)(s_rec + a.lay.offRowoff);   // (generic routes only)
+    const unsigned short *s_off = (const unsigned short *)(s_rec + a.lay.offEoff);
+    const TACC *s_w = (const TACC *)(s_rec + a.lay.offEw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = blockIdx.x / a.tilesPerRow;
     const int i0 = (blockIdx.x - row * a.tilesPerRow) * kPipeTile;
     const int64_t t0 = (int64_t)row * a.ni + i0;
-    const int ntile = (int)min((int64_t)min(kPipeTile, a.ni - i0), a.nDst - t0);
 
-    // ---- prologue: CSR slice + the tile's schedule ---------------------------------
-    if (tid <= kPipeTile) s_rowptr[tid] = a.rowptr[min(t0 + min(tid, ntile), a.nDst)];
-    for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
-        ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
+    // ---- prologue: ONE bulk copy brings the tile's record (schedule, per-target rows, weights) ---------------
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kPipeStages; ++i) mbar_init(s_mbar + i, UNAL ? kPipeWarps : 1);  // arrivals per unit
+        mbar_init(s_mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        mbar_arrive_tx(s_mbar + 2, (unsigned)a.lay.stride);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec), a.rec + (size_t)blockIdx.x * a.lay.stride, (unsigned)a.lay.stride, s_mbar + 2);
     }
-    const int ub = __ldg(a.tileUPtr + blockIdx.x);
-    const int nu = __ldg(a.tileUPtr + blockIdx.x + 1) - ub;
-    if (tid < nu) {
-        s_uniq[tid] = __ldg(a.tileUCols + ub + tid);
-        s_urun[tid] = __ldg(a.tileURun + ub + tid);
-    }
-    __syncthreads();
-    const int base = s_rowptr[0];
-    const int cnt = s_rowptr[ntile] - base;  // host guarantees cnt <= kPipeCap
-    if (tid < cnt) {
-        s_w[tid] = __ldg(a.w + base + tid);
-        const int sl = __ldg(a.entrySlot + base + tid);
-        s_off[tid] = (unsigned short)(UNAL ? (sl | ((int)s_urun[sl] << 8)) : sl);
-    }
-    if (UNAL && tid < nu && (tid == 0 || s_urun[tid] != s_urun[tid - 1])) s_runFirst[s_urun[tid]] = (unsigned char)tid;
-    __syncthreads();
-
-    // Per target (= lane): rows with <= 3 entries are packed once -- 3 weights, the 3 slots, the 3 run indices, the
-    // length -- so that every unit re-reads them with one or two 16-byte shared loads instead of keeping 6-8 registers
-    // alive across the copy issue and the barrier (the compiler spilled them to local memory: 14 % of the stall
-    // samples of the first v7 build sat on those reloads)
+    for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
+        ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
+    __syncthreads();             // barriers initialised, unit descriptors in place
+    mbar_wait(s_mbar + 2, 0);    // the record has landed
+    const int nu = ((const unsigned short *)s_rec)[0];
+    const int ntile = ((const unsigned short *)s_rec)[3];
+    const unsigned rflags = ((const unsigned *)s_rec)[2];
     const bool live = lane < ntile;
-    bool fast, all3;
-    {
-    int rlen = 0;
-    if (live) rlen = s_rowptr[lane + 1] - s_rowptr[lane];
-    if (warp == 0) {
-        const int rbeg0 = live ? s_rowptr[lane] - base : 0;
-        unsigned pk = (unsigned)min(rlen, 255) << 24, pr = 0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const bool h = j < rlen && rlen <= 3;
-            s_row[8 * lane + j] = h ? s_w[rbeg0 + j] : (TACC)0;
-            const unsigned o = h ? (unsigned)s_off[rbeg0 + j] : 0u;
-            pk |= (o & 0xffu) << (8 * j);
-            pr |= (o >> 8) << (8 * j);
-        }
-        ((unsigned *)(s_row + 8 * lane + 3))[0] = pk;
-        ((unsigned *)(s_row + 8 * lane + 3))[sizeof(TACC) / 4] = pr;   // fp32: word 4; fp64: word 8 of the 16-word row
-    }
-    fast = __all_sync(0xffffffffu, rlen <= 3);
+    const bool fast = (rflags & kRecFast) != 0;   // every row of the tile has <= 3 entries
     // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
-    all3 = __all_sync(0xffffffffu, live && rlen == 3);
-    }
-    const unsigned row0 = (unsigned)__cvta_generic_to_shared(s_row + 8 * lane);
+    const bool all3 = (rflags & kRecAll3) != 0;
+    // this lane's row (3 weights, slots, runs, length): re-read every unit with one or two 16-byte shared loads
+    // instead of living in 6-8 registers across the copy issue and the barrier
+    const unsigned row0 = (unsigned)__cvta_generic_to_shared(s_rec + 16 + lane * 8 * (int)sizeof(TACC));
 
     const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
     const unsigned hold0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.holdOff;
@@ -348,7 +336,6 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     };
 
     issue(0);
-    __syncthreads();   // s_row is visible to every warp
 
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
     for (int u = 0; u < a.nunits; ++u) {
@@ -379,7 +366,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             rw[0] = (TACC)x; rw[1] = (TACC)y; rw[2] = (TACC)z;
         }
         const int rlen = (int)(pk >> 24);                                       // (fast paths: <= 3)
-        const int rbeg = s_rowptr[lane] - base, rend = s_rowptr[lane + 1] - base;   // (generic rows only)
+        const int rbeg = fast ? 0 : (int)s_rowoff[lane], rend = fast ? 0 : (int)s_rowoff[lane + 1];   // (generic rows only)
         const unsigned chunkB = (unsigned)Ln * ESZ;
         const bool direct = !UNAL || (ud.flags & kUnitAligned);     // columns sit 16-byte aligned at slot * ustride
         const unsigned ustride = ((ud.flags & kUnitMerged) && (chunkB & 127u)) ? chunkB : chunkB + 16u;
@@ -486,29 +473,32 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
 
 // Tile schedule of a route: for every row-aligned 32-target tile the list of distinct source
 // columns in ASCENDING id order, the run (maximal sequence of consecutive ids) each belongs to and, per CSR
-// entry, the index of its column in that list.  Ascending order makes columns of consecutively numbered cells
-// neighbours in the list; they are also neighbours in memory (file order), so the apply kernel fetches each
-// such run with ONE bulk copy.
-// FILL == false: per-tile unique counts (+ global maxima);  FILL == true: write the lists.
-template <bool FILL>
+// entry, the index of its column in that list -- written as the tile's RECORD (RecLayout).  Ascending order makes
+// columns of consecutively numbered cells neighbours in the list; they are also neighbours in memory (file order),
+// so the apply kernel fetches each such run with ONE bulk copy.
+// FILL == false: per-tile maxima (entries, distinct columns, runs, longest row) and totals;  FILL == true: the records.
+template <bool FILL, typename TW>
 __global__ void __launch_bounds__(kPipeThreads)
-k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t nDst, int32_t ni,
-                int32_t tilesPerRow, int32_t *maxEntries, int32_t *maxUniq, int32_t *maxRuns, int32_t *tileCount,
-                const int32_t *__restrict__ tileUPtr, int32_t *__restrict__ tileUCols, unsigned char *__restrict__ tileURun,
-                unsigned char *__restrict__ entrySlot, unsigned long long *runsTotal) {
+k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const TW *__restrict__ w, int64_t nDst,
+                int32_t ni, int32_t tilesPerRow, int32_t *maxima /* entries, uniq, runs, row */,
+                unsigned long long *totals /* columns, runs */, unsigned char *__restrict__ rec, RecLayout lay) {
     __shared__ int32_t s_col[kPipeCap];   // sort keys (column ids; INT_MAX padding)
     __shared__ int32_t s_idx[kPipeCap];   // entry index within the tile that the key came from
     __shared__ int32_t s_cnt[kPipeWarps], s_rcnt[kPipeWarps];
+    __shared__ unsigned short s_eoff[kPipeCap];   // per entry (original order): slot | run << 8
+    __shared__ int32_t s_rp[kPipeTile + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = blockIdx.x / tilesPerRow;
     const int i0 = (blockIdx.x - row * tilesPerRow) * kPipeTile;
     const int64_t t0 = (int64_t)row * ni + i0;
     const int64_t t1 = min(t0 + min(kPipeTile, ni - i0), nDst);
+    const int ntile = t0 < nDst ? (int)(t1 - t0) : 0;
     int base = 0, cnt = 0;
     if (t0 < nDst) { base = rowptr[t0]; cnt = rowptr[t1] - base; }
-    if (!FILL && tid == 0) atomicMax(maxEntries, cnt);
+    if (tid <= kPipeTile) s_rp[tid] = (t0 < nDst ? rowptr[min(t0 + min(tid, ntile), nDst)] : 0) - base;
+    if (!FILL && tid == 0) atomicMax(maxima, cnt);
     if (cnt > kPipeCap) {  // tile too fat for the pipelined kernel: the route falls back to register gathers
-        if (!FILL && tid == 0) { atomicMax(maxUniq, cnt); tileCount[blockIdx.x] = 0; }
+        if (!FILL && tid == 0) atomicMax(maxima + 1, cnt);
         return;
     }
     s_col[tid] = tid < cnt ? col[base + tid] : 0x7fffffff;
@@ -537,22 +527,60 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
     int incl = __popc(bal & ((2u << lane) - 1u)), nu = 0;   // unique keys up to and including this position
     int rincl = __popc(rb & ((2u << lane) - 1u)), nr = 0;   // run starts up to and including this position
 #pragma unroll
-    for (int w = 0; w < kPipeWarps; ++w) {
-        const int v = s_cnt[w], rv = s_rcnt[w];
-        if (w < warp) { incl += v; rincl += rv; }
+    for (int wq = 0; wq < kPipeWarps; ++wq) {
+        const int v = s_cnt[wq], rv = s_rcnt[wq];
+        if (wq < warp) { incl += v; rincl += rv; }
         nu += v; nr += rv;
     }
+    int rowMax = 0;
+    if (tid < ntile) rowMax = s_rp[tid + 1] - s_rp[tid];
     if (!FILL) {
-        if (tid == 0) { atomicMax(maxUniq, nu); atomicMax(maxRuns, nr); tileCount[blockIdx.x] = nu; }
+        for (int o = 16; o > 0; o >>= 1) rowMax = max(rowMax, __shfl_xor_sync(0xffffffffu, rowMax, o));
+        if (tid == 0) {
+            atomicMax(maxima + 1, nu); atomicMax(maxima + 2, nr); atomicMax(maxima + 3, rowMax);
+            atomicAdd(totals, (unsigned long long)nu); atomicAdd(totals + 1, (unsigned long long)nr);
+        }
         return;
     }
+    unsigned char *R = rec + (size_t)blockIdx.x * lay.stride;
     if (uniq) {
-        tileUCols[tileUPtr[blockIdx.x] + incl - 1] = s_col[tid];
-        tileURun[tileUPtr[blockIdx.x] + incl - 1] = (unsigned char)(rincl - 1);
+        ((int32_t *)(R + lay.offUniq))[incl - 1] = s_col[tid];
+        R[lay.offUrun + incl - 1] = (unsigned char)(rincl - 1);
+        if (runStart) R[lay.offRunFirst + rincl - 1] = (unsigned char)(incl - 1);
     }
-    if (tid < cnt) entrySlot[base + s_idx[tid]] = (unsigned char)(incl - 1);
-    // statistics: runs of consecutive ids (= bulk copies per unit of a merged launch)
-    if (tid == 0 && nr && runsTotal) atomicAdd(runsTotal, (unsigned long long)nr);
+    if (tid < cnt) s_eoff[s_idx[tid]] = (unsigned short)((incl - 1) | ((rincl - 1) << 8));
+    __syncthreads();
+    // per-target rows
+    const bool shortRow = rowMax <= 3;
+    const unsigned allShort = __ballot_sync(0xffffffffu, tid >= ntile || shortRow);
+    const unsigned allThree = __ballot_sync(0xffffffffu, tid < ntile && rowMax == 3);
+    if (tid < kPipeTile) {
+        TW *rw = (TW *)(R + 16 + tid * 8 * (int)sizeof(TW));
+        unsigned pk = (unsigned)min(rowMax, 255) << 24, pr = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const bool h = tid < ntile && j < rowMax && shortRow;
+            rw[j] = h ? w[base + s_rp[tid] + j] : (TW)0;
+            const unsigned o = h ? (unsigned)s_eoff[s_rp[tid] + j] : 0u;
+            pk |= (o & 0xffu) << (8 * j);
+            pr |= (o >> 8) << (8 * j);
+        }
+        ((unsigned *)(rw + 3))[0] = pk;
+        ((unsigned *)(rw + 3))[sizeof(TW) / 4] = pr;
+    }
+    if (tid == 0) {
+        unsigned short *h = (unsigned short *)R;
+        h[0] = (unsigned short)nu; h[1] = (unsigned short)cnt; h[2] = (unsigned short)nr; h[3] = (unsigned short)ntile;
+        ((unsigned *)R)[2] = (allShort == 0xffffffffu ? kRecFast : 0u) | ((allThree == 0xffffffffu && ntile == kPipeTile) ? kRecAll3 : 0u);
+        ((unsigned *)R)[3] = 0u;
+    }
+    if (lay.offEw) {   // routes with longer rows keep the whole CSR slice of the tile
+        if (tid <= kPipeTile) ((unsigned short *)(R + lay.offRowoff))[tid] = (unsigned short)s_rp[min(tid, ntile)];
+        if (tid < cnt) {
+            ((unsigned short *)(R + lay.offEoff))[tid] = s_eoff[tid];
+            ((TW *)(R + lay.offEw))[tid] = w[base + tid];
+        }
+    }
 }
 
 }  // namespace mprg

@@ -146,9 +146,10 @@ struct mprg_route {
     int32_t tileEntriesMax = 0, tileUniqMax = 0;  // per 32-target tile: CSR entries / distinct columns
     int32_t tileRunsMax = 0;                      // per tile: runs of consecutive column ids
     int32_t dstNi = 0;         // destination row length (tiles of the apply kernel never straddle rows)
-    // tile schedule for the pipelined apply kernel (apply_pipe.cuh)
-    mprg::DevBuf<int32_t> tileUPtr, tileUCols;
-    mprg::DevBuf<unsigned char> entrySlot, tileURun;
+    // tile schedule for the pipelined apply kernel (apply_pipe.cuh): one record per 32-target tile, for fp32 weights
+    // (built with the route) and for fp64 weights (built on first use)
+    mprg::DevBuf<unsigned char> rec32, rec64;
+    int32_t tileRowMax = 0;                       // longest row of any tile (> 3: the records keep the CSR slices)
     int64_t schedTiles = 0, schedCols = 0, schedRuns = 0;  // tiles, distinct columns and id-runs summed over tiles
     int32_t maxRow = 0;        // longest row
     bool uniform = false;      // every mapped row has exactly `maxRow` entries, stored ELL-like
