@@ -30,6 +30,13 @@ module mpassit_rg_mod
   integer(c_int), parameter, public :: MPRG_EPI_NONE = 0, MPRG_EPI_ADD = 1, MPRG_EPI_MUL = 2, &
                                         MPRG_EPI_ROT_U = 3, MPRG_EPI_ROT_V = 4
 
+  !> mirrors struct mprg_projection of include/mpassit_rg.h
+  type, bind(C), public :: mprg_projection
+     integer(c_int32_t) :: code, nxmin, nxmax
+     real(c_double) :: lat1, lon1, knowni, knownj, latinc, loninc, stdlon, truelat1, truelat2, hemi, cone, polei, polej, rebydx
+  end type mprg_projection
+
+  public :: mprg_set_target_projected, mprg_target_map_factor, mprg_set_rotation_from_target
   public :: mprg_init, mprg_finalize, mprg_last_error, mprg_error_message
   public :: mprg_set_mesh, mprg_set_target, mprg_set_grid_kind, mprg_set_option, mprg_set_weight_cache, mprg_get_slab
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
@@ -101,6 +108,28 @@ module mpassit_rg_mod
        integer(c_int), value :: stagger
        integer(c_int32_t), value :: ni, nj
        real(c_double), intent(in) :: lon_deg(*), lat_deg(*)
+     end function
+     !> target coordinates / map factors / rotation angles generated on the device (include/mpassit_rg.h);
+     !! proj = the scalars that map_set / set_lc leave in proj_info (module_map_utils.F90:243-568, 1083-1121)
+     integer(c_int) function mprg_set_target_projected(ctx, stagger, ni, nj, proj) bind(C, name="mprg_set_target_projected")
+       import :: c_int, c_ptr, c_int32_t, mprg_projection
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: stagger
+       integer(c_int32_t), value :: ni, nj
+       type(mprg_projection), intent(in) :: proj
+     end function
+     integer(c_int) function mprg_target_map_factor(ctx, stagger, proj_code, truelat1, truelat2, mapfac) &
+         bind(C, name="mprg_target_map_factor")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: stagger, proj_code
+       real(c_double), value :: truelat1, truelat2
+       real(c_double), intent(out) :: mapfac(*)
+     end function
+     integer(c_int) function mprg_set_rotation_from_target(ctx, cosa, sina) bind(C, name="mprg_set_rotation_from_target")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double), intent(out) :: cosa(*), sina(*)
      end function
      !> replaces the choice between ESMF_GridCreate1PeriDim (polekindflag=MONOPOLE, periodicDim=1) and
      !! ESMF_GridCreateNoPeriDim (model_grid.F90:684-703): kind = MPRG_GRID_1PERI_MONOPOLE when .not. is_regional

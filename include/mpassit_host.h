@@ -79,6 +79,9 @@ int mpassit_target_dims(const mpassit_config *cfg, int mprg_stagger, int32_t *ni
 /* get_lat_lon_fields + xytoll + ij_to_latlon (model_grid.F90:2188-2219,
  * llxy_module.F90:166-216, module_map_utils.F90:1160-1233,1398-1428);
  * lat, lon: [nj][ni] degrees.  LC and lat-lon projections. */
+/* push_source_projection + map_set / set_lc (llxy_module.F90:38-160, module_map_utils.F90:243-568, 1083-1121): the
+ * per-grid scalars of the target projection, for mprg_set_target_projected (coordinates generated on the device) */
+int mpassit_projection(const mpassit_config *cfg, mprg_projection *out, char *err, size_t errlen);
 int mpassit_target_coords(const mpassit_config *cfg, int mprg_stagger, double *lat, double *lon,
                           char *err, size_t errlen);
 /* get_cell_corners, model_grid.F90:1902-1972 (target_grid_type = 'file'): CORNER-stagger points [nj+1][ni+1]

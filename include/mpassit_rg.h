@@ -120,6 +120,33 @@ int mprg_set_mesh(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxE
  *      CORNER (ni+1) x (nj+1)  (interp.F90:477-520). */
 int mprg_set_target(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj,
                     const double *lon_deg, const double *lat_deg);
+/* ---- target grid generated on the device.  The reference computes the coordinates of all four
+ *      staggers, the map factors and the rotation angles on the host, point by point, through the WPS map utilities
+ *      (get_lat_lon_fields model_grid.F90:2188-2219 -> ijll_lc / ijll_latlon module_map_utils.F90:1160-1233,1398-1428;
+ *      get_map_factor :2229-2365; get_rotang :2450-2507).  mprg_projection carries the per-grid scalars of the projection
+ *      (what map_set / set_lc leave in proj_info, module_map_utils.F90:243-568,1083-1121), computed once by the host;
+ *      everything O(nx x ny) then runs on the device in fp64 with the reference's formulas:
+ *        mprg_set_target_projected      one stagger's lon / lat (xytoll offsets: EDGE1 x-0.5, EDGE2 y-0.5, CORNER both)
+ *                                       and its Cartesian coordinates; equivalent to mprg_set_target with those arrays
+ *        mprg_get_target_lonlat         the generated (or given) coordinates, [nj][ni] degrees, for the output file
+ *        mprg_target_map_factor         MAPFAC_M / _U / _V of a stagger (0 for lat-lon, where the reference leaves it unset)
+ *        mprg_set_rotation_from_target  get_rotang on the CENTER stagger + mprg_set_rotation; cosa / sina returned if not NULL
+ *      Device trig differs from the host libm in the last 1-2 ulp, so coordinates are not bit-identical to a CPU run
+ *      (mprg_set_target with host arrays is); tests/test_gpu_targetgen.py bounds the difference and checks that the
+ *      weight matrices' structure is unchanged on the BASELINE configurations. */
+typedef struct mprg_projection {
+    int32_t code;               /* 0 = cylindrical lat-lon (PROJ_LATLON), 1 = Lambert conformal (PROJ_LC) */
+    int32_t nxmin, nxmax;       /* lat-lon: periodic index range (ijll_latlon) */
+    double lat1, lon1;          /* lat-lon: coordinates of the known point */
+    double knowni, knownj;      /* its (i, j) */
+    double latinc, loninc;      /* lat-lon increments, degrees */
+    double stdlon, truelat1, truelat2, hemi, cone, polei, polej, rebydx;   /* Lambert: proj_info after set_lc */
+} mprg_projection;
+int mprg_set_target_projected(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const mprg_projection *proj);
+int mprg_get_target_lonlat(mprg_ctx *ctx, int stagger, double *lon_deg, double *lat_deg);
+int mprg_target_map_factor(mprg_ctx *ctx, int stagger, int proj_code, double truelat1, double truelat2, double *mapfac);
+int mprg_set_rotation_from_target(mprg_ctx *ctx, double *cosa, double *sina);
+
 /* Topology of the target grid: which ESMF_GridCreate* call the reference makes, model_grid.F90:684-703.
  *   MPRG_GRID_NOPERI         ESMF_GridCreateNoPeriDim (is_regional = .true., the default here);
  *   MPRG_GRID_1PERI_MONOPOLE ESMF_GridCreate1PeriDim(periodicDim=1, poleDim=2, polekindflag=MONOPOLE)

@@ -30,6 +30,7 @@ UNITS = [
     ("stagger.cu", ["-fmad=false"], ["MPRG_HAVE_STAGGER", "MPRG_HAVE_NODE"]),
     ("apply.cu", [], []),
     ("wcache.cu", [], []),
+    ("target_gen.cu", ["-fmad=false"], []),
     ("gather.cu", [], []),
 ]
 

@@ -322,6 +322,47 @@ int mprg_set_target(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const do
     MPRG_LEAVE(ctx)
 }
 
+int mprg_set_target_projected(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const mprg_projection *proj) {
+    MPRG_ENTER(ctx)
+    target_generate(ctx, stagger, ni, nj, proj);
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_get_target_lonlat(mprg_ctx *ctx, int stagger, double *lon_deg, double *lat_deg) {
+    MPRG_ENTER(ctx)
+    if (stagger < 0 || stagger > 3 || !ctx->target[stagger].set || !ctx->target[stagger].lon.p) fail(18, "mprg_get_target_lonlat: stagger %d not set", stagger);
+    const Target &t = ctx->target[stagger];
+    const size_t b = (size_t)t.ni * t.nj * sizeof(double);
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (lon_deg) MPRG_CUDA(cudaMemcpy(lon_deg, t.lon.p, b, cudaMemcpyDeviceToHost));
+    if (lat_deg) MPRG_CUDA(cudaMemcpy(lat_deg, t.lat.p, b, cudaMemcpyDeviceToHost));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_target_map_factor(mprg_ctx *ctx, int stagger, int proj_code, double truelat1, double truelat2, double *mapfac) {
+    MPRG_ENTER(ctx)
+    if (stagger < 0 || stagger > 3 || !mapfac) fail(1, "mprg_target_map_factor: bad argument");
+    const Target &t = ctx->target[stagger];
+    DevBuf<double> out((size_t)t.ni * t.nj);
+    target_map_factor(ctx, stagger, proj_code, truelat1, truelat2, out.p);
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    MPRG_CUDA(cudaMemcpy(mapfac, out.p, out.bytes(), cudaMemcpyDeviceToHost));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_set_rotation_from_target(mprg_ctx *ctx, double *cosa, double *sina) {
+    MPRG_ENTER(ctx)
+    target_rotang(ctx);
+    const Target &tg = ctx->target[MPRG_CENTER];
+    const int64_t n = (int64_t)tg.ni * tg.nj;
+    rotation_constants(ctx, n);
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cosa) MPRG_CUDA(cudaMemcpy(cosa, ctx->cosa.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sina) MPRG_CUDA(cudaMemcpy(sina, ctx->sina.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    ctx->haveRot = true;
+    MPRG_LEAVE(ctx)
+}
+
 int mprg_set_grid_kind(mprg_ctx *ctx, int kind) {
     MPRG_ENTER(ctx)
     if (kind != MPRG_GRID_NOPERI && kind != MPRG_GRID_1PERI_MONOPOLE) fail(58, "mprg_set_grid_kind: bad kind %d", kind);

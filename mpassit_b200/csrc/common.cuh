@@ -128,6 +128,7 @@ struct Target {
     int32_t ni = 0, nj = 0;    // full grid
     int32_t j0 = 0, j1 = 0;    // slab rows owned by this rank
     DevBuf<double> xyz;        // full grid [nj][ni][3]
+    DevBuf<double> lon, lat;   // full grid [nj][ni] degrees (as given, or generated by mprg_set_target_projected)
     const double *xyzRef = nullptr;  // MPRG_CENTER_HALO shares CENTER's coordinates
     const double *x() const { return xyzRef ? xyzRef : xyz.p; }
     bool set = false;
@@ -260,6 +261,11 @@ void bvh_build_boxes(mprg_ctx *ctx, const float *lo_dev, const float *hi_dev, in
 void mesh_set(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges, const double *lonC,
               const double *latC, const double *lonV, const double *latV, const int32_t *voc);
 void target_set(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const double *lon, const double *lat);
+void target_register(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj);
+// target_gen.cu: coordinates, map factors and rotation angles of a projected target grid, on the device
+void target_generate(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const mprg_projection *p);
+void target_map_factor(mprg_ctx *ctx, int stagger, int proj_code, double truelat1, double truelat2, double *out_dev);
+void target_rotang(mprg_ctx *ctx);   // fills ctx->cosa / ctx->sina from the CENTER stagger's lon / lat
 void mesh_need_cell_bvh(mprg_ctx *ctx);
 void mesh_need_tri_bvh(mprg_ctx *ctx);
 void mesh_need_poly_bvh(mprg_ctx *ctx);

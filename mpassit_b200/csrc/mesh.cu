@@ -197,21 +197,11 @@ void mesh_need_poly_bvh(mprg_ctx *ctx) {
     m.havePolyBvh = true;
 }
 
-void target_set(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const double *lon, const double *lat) {
-    if (stagger < 0 || stagger > 3) fail(15, "mprg_set_target: bad stagger %d", stagger);
-    if (ni <= 0 || nj <= 0 || !lon || !lat) fail(16, "mprg_set_target: empty grid");
+// the stagger's Cartesian coordinates are in t.xyz: slab bounds, halo view, stale routes
+void target_register(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj) {
     Target &t = ctx->target[stagger];
     t.ni = ni; t.nj = nj;
     para_range(nj, ctx->nranks, ctx->rank, &t.j0, &t.j1);
-    int64_t n = (int64_t)ni * nj;
-    std::vector<double> x(3 * (size_t)n);
-    double *xp = x.data();
-    parallel_for(n, [=](int64_t b, int64_t e) {
-        for (int64_t i = b; i < e; ++i) deg_to_cart(lon[i], lat[i], xp + 3 * i);
-    });
-    t.xyz.alloc(x.size());
-    MPRG_CUDA(cudaMemcpyAsync(t.xyz.p, x.data(), t.xyz.bytes(), cudaMemcpyHostToDevice, ctx->stream));
-    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     t.set = true;
     t.xyzRef = nullptr;
     if (stagger == MPRG_CENTER) {
@@ -236,6 +226,27 @@ void target_set(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const double
             ++it;
         }
     }
+}
+
+void target_set(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj, const double *lon, const double *lat) {
+    if (stagger < 0 || stagger > 3) fail(15, "mprg_set_target: bad stagger %d", stagger);
+    if (ni <= 0 || nj <= 0 || !lon || !lat) fail(16, "mprg_set_target: empty grid");
+    Target &t = ctx->target[stagger];
+    int64_t n = (int64_t)ni * nj;
+    std::vector<double> x(3 * (size_t)n);
+    double *xp = x.data();
+    parallel_for(n, [=](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) deg_to_cart(lon[i], lat[i], xp + 3 * i);
+    });
+    t.xyz.alloc(x.size());
+    // degrees kept too: the device-side map factors / rotation angles (target_gen.cu) read them
+    t.lon.alloc(n);
+    t.lat.alloc(n);
+    MPRG_CUDA(cudaMemcpyAsync(t.xyz.p, x.data(), t.xyz.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+    MPRG_CUDA(cudaMemcpyAsync(t.lon.p, lon, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MPRG_CUDA(cudaMemcpyAsync(t.lat.p, lat, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    target_register(ctx, stagger, ni, nj);
 }
 
 }  // namespace mprg

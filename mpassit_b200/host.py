@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     L.mpassit_para_range.restype = None
     L.mpassit_read_block_decomp_file.argtypes = [cp, i32, i32, C.c_void_p, cp, C.c_size_t]
     L.mpassit_target_dims.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(i32), C.POINTER(i32)]
+    L.mpassit_projection.argtypes = [C.POINTER(Config), C.POINTER(_l.Projection), cp, C.c_size_t]
     L.mpassit_target_coords.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_void_p, cp, C.c_size_t]
     L.mpassit_get_rotang.argtypes = [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p]
     L.mpassit_get_rotang.restype = None
@@ -124,6 +125,15 @@ def read_setup_namelist(path: str) -> Config:
     if rc:
         raise HostError(rc, e.value.decode())
     return cfg
+
+
+def projection(cfg: Config):
+    """The per-grid scalars of the target projection (map_set / set_lc) for Regridder.set_target_projected."""
+    p, e = _l.Projection(), _err()
+    rc = load().mpassit_projection(C.byref(cfg), C.byref(p), e, len(e))
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return p
 
 
 def read_varlist(path: str) -> list[tuple[str, str]]:

@@ -148,6 +148,25 @@ int mpassit_target_dims(const mpassit_config *cfg, int stagger, int32_t *ni, int
     return (stagger < 0 || stagger > 3) ? 2 : 0;
 }
 
+int mpassit_projection(const mpassit_config *cfg, mprg_projection *out, char *err, size_t errlen) {
+    // push_source_projection + map_set (+ set_lc): the per-grid scalars; the O(nx x ny) part can then run on the device
+    // (mprg_set_target_projected)
+    if (!cfg || !out) return 1;
+    Proj p;
+    std::string why;
+    if (!make_proj(cfg, p, why)) {
+        if (err && errlen) std::snprintf(err, errlen, "%s", why.c_str());
+        return 2;
+    }
+    out->code = p.code == MPASSIT_PROJ_LC ? 1 : 0;
+    out->nxmin = p.nxmin; out->nxmax = p.nxmax;
+    out->lat1 = p.lat1; out->lon1 = p.lon1; out->knowni = p.knowni; out->knownj = p.knownj;
+    out->latinc = p.latinc; out->loninc = p.loninc;
+    out->stdlon = p.stdlon; out->truelat1 = p.truelat1; out->truelat2 = p.truelat2; out->hemi = p.hemi;
+    out->cone = p.cone; out->polei = p.polei; out->polej = p.polej; out->rebydx = p.rebydx;
+    return 0;
+}
+
 int mpassit_target_coords(const mpassit_config *cfg, int stagger, double *lat, double *lon, char *err, size_t errlen) {
     int32_t ni, nj;
     if (mpassit_target_dims(cfg, stagger, &ni, &nj) || !lat || !lon) return 1;

@@ -26,12 +26,19 @@ EPI_NONE, EPI_ADD, EPI_MUL, EPI_ROT_U, EPI_ROT_V = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize", "mprg_set_async", "mprg_get_async", "mprg_set_option", "mprg_get_option", "mprg_download",
-    "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_set_grid_kind", "mprg_get_slab", "mprg_store",
+    "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_set_target_projected", "mprg_get_target_lonlat", "mprg_target_map_factor", "mprg_set_rotation_from_target", "mprg_set_grid_kind", "mprg_get_slab", "mprg_store",
     "mprg_release", "mprg_clear_routes", "mprg_set_weight_cache", "mprg_weight_cache_stats", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
     "mprg_apply", "mprg_apply_ex", "mprg_apply_into", "mprg_put_slab", "mprg_ipc_export", "mprg_ipc_open", "mprg_ipc_close_all", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
     "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_capture_begin", "mprg_capture_end", "mprg_graph_launch", "mprg_graph_release", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
     "mprg_profile_reset", "mprg_route_src_referenced", "mprg_route_schedule_info", "mprg_set_source_byte_order", "mprg_bswap", "mprg_post_affine",
 ]
+
+
+class Projection(C.Structure):
+    """mprg_projection (include/mpassit_rg.h): per-grid scalars of the target projection."""
+    _fields_ = [("code", C.c_int32), ("nxmin", C.c_int32), ("nxmax", C.c_int32)] + \
+               [(n, C.c_double) for n in ("lat1", "lon1", "knowni", "knownj", "latinc", "loninc", "stdlon", "truelat1",
+                                          "truelat2", "hemi", "cone", "polei", "polej", "rebydx")]
 
 
 class MprgError(RuntimeError):
@@ -69,6 +76,10 @@ def load() -> C.CDLL:
     L.mprg_set_mesh.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mprg_set_target.argtypes = [vp, C.c_int, i32, i32, vp, vp]
     L.mprg_set_grid_kind.argtypes = [vp, C.c_int]
+    L.mprg_set_target_projected.argtypes = [vp, C.c_int, i32, i32, C.POINTER(Projection)]
+    L.mprg_get_target_lonlat.argtypes = [vp, C.c_int, vp, vp]
+    L.mprg_target_map_factor.argtypes = [vp, C.c_int, C.c_int, dbl, dbl, vp]
+    L.mprg_set_rotation_from_target.argtypes = [vp, vp, vp]
     L.mprg_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.mprg_set_weight_cache.argtypes = [vp, C.c_char_p]
     L.mprg_weight_cache_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]

@@ -242,6 +242,32 @@ class Regridder:
             raise KeyError(key)
         return buf.value.decode()
 
+    def set_target_projected(self, stagger: int, ni: int, nj: int, proj) -> None:
+        """Coordinates of one stagger generated on the device from the projection scalars (mprg_set_target_projected)."""
+        self._ck(self.L.mprg_set_target_projected(self.ctx, int(stagger), int(ni), int(nj), C.byref(proj)))
+        self.shape[stagger] = (nj, ni)
+        if stagger == CENTER:
+            self.nSrc[SRC_GRID_CENTER] = nj * ni
+
+    def target_lonlat(self, stagger: int):
+        nj, ni = self.shape[stagger]
+        lon, lat = np.empty((nj, ni), np.float64), np.empty((nj, ni), np.float64)
+        self._ck(self.L.mprg_get_target_lonlat(self.ctx, int(stagger), lon.ctypes.data, lat.ctypes.data))
+        return lon, lat
+
+    def target_map_factor(self, stagger: int, proj_code: int, truelat1: float, truelat2: float):
+        nj, ni = self.shape[stagger]
+        out = np.empty((nj, ni), np.float64)
+        self._ck(self.L.mprg_target_map_factor(self.ctx, int(stagger), int(proj_code), float(truelat1), float(truelat2), out.ctypes.data))
+        return out
+
+    def set_rotation_from_target(self):
+        """get_rotang on the device from the CENTER stagger + mprg_set_rotation; returns (cosa, sina)."""
+        nj, ni = self.shape[CENTER]
+        ca, sa = np.empty((nj, ni), np.float64), np.empty((nj, ni), np.float64)
+        self._ck(self.L.mprg_set_rotation_from_target(self.ctx, ca.ctypes.data, sa.ctypes.data))
+        return ca, sa
+
     def set_grid_kind(self, kind: int) -> None:
         """ESMF_GridCreateNoPeriDim (0) or ESMF_GridCreate1PeriDim + MONOPOLE (1), model_grid.F90:684-703."""
         self._ck(self.L.mprg_set_grid_kind(self.ctx, int(kind)))

@@ -45,6 +45,7 @@ def test_second_run_loads_every_matrix_and_gives_the_same_bytes(engine_lib, tmp_
     from mpassit_b200 import build, workload
 
     build.build_host()
+    os.makedirs(tmp_path / "run")
     wl = workload.make("mini", rundir=str(tmp_path / "run"))
     cache = str(tmp_path / "wcache")
     plain, csr0, st0 = _pass(wl, None)
@@ -72,6 +73,8 @@ def test_keys_follow_geometry_slab_and_topology(engine_lib, tmp_path):
     from mpassit_b200 import build, workload
 
     build.build_host()
+    os.makedirs(tmp_path / "run")
+    os.makedirs(tmp_path / "run2")
     wl = workload.make("mini", rundir=str(tmp_path / "run"))
     cache = str(tmp_path / "wcache")
     _, _, st = _pass(wl, cache)

@@ -65,6 +65,22 @@ def test_c2_full_pass_every_field_against_the_oracle(c2, orc):
     del F, fields, got
 
 
+def test_c2_device_generated_target_keeps_the_matrix_structure(c2):
+    """SURVEY.md 8 f3 at the full 1801 x 1061 size: coordinates of all four staggers generated on the device agree
+    with the host mirror to a few ulp, and the bilinear / nearest / conservative / stagger matrices built from them
+    have the same mapped mask and the same indices as those built from the host's coordinates."""
+    from mpassit_b200 import lib as l
+    from tests.test_gpu_targetgen import compare_target_generation
+
+    wl, rg, torch = c2
+    routes = [(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER), (l.NEAREST_STOD, l.SRC_MESH_ELEMENT, l.CENTER),
+              (l.CONSERVE, l.SRC_MESH_ELEMENT, l.CENTER), (l.BILINEAR, l.SRC_GRID_CENTER, l.EDGE1),
+              (l.BILINEAR, l.SRC_GRID_CENTER, l.EDGE2)]
+    res = compare_target_generation(wl, routes)
+    print("c2", res)
+    assert res["ulp_lon"] <= 8 and res["ulp_lat"] <= 8 and res["structure_diffs"] == 0, res
+
+
 def test_bilinear_weights_partition_of_unity_and_constant_field(c2):
     from mpassit_b200 import lib as l
 
