@@ -36,7 +36,7 @@ module mpassit_rg_mod
      real(c_double) :: lat1, lon1, knowni, knownj, latinc, loninc, stdlon, truelat1, truelat2, hemi, cone, polei, polej, rebydx
   end type mprg_projection
 
-  public :: mprg_set_target_projected, mprg_target_map_factor, mprg_set_rotation_from_target
+  public :: mprg_set_target_projected, mprg_target_map_factor, mprg_set_rotation_from_target, mprg_host_bind_to_device
   public :: mprg_init, mprg_finalize, mprg_last_error, mprg_error_message
   public :: mprg_set_mesh, mprg_set_target, mprg_set_grid_kind, mprg_set_option, mprg_set_weight_cache, mprg_get_slab
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
@@ -137,6 +137,12 @@ module mpassit_rg_mod
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx
        integer(c_int), value :: kind
+     end function
+     !> bind this rank's process to the NUMA node of its GPU before allocating host buffers (include/mpassit_rg.h)
+     integer(c_int) function mprg_host_bind_to_device(device, node) bind(C, name="mprg_host_bind_to_device")
+       import :: c_int
+       integer(c_int), value :: device
+       integer(c_int), intent(out) :: node
      end function
      !> cross-run weight cache directory (NUL-terminated); the reference regenerates every matrix in every run
      !! (program_setup.F90:72-75)

@@ -92,6 +92,14 @@ int mprg_get_async(const mprg_ctx *ctx);
 /* device -> host copy ordered after everything queued on the context so far (blocking unless async) */
 int mprg_download(mprg_ctx *ctx, const void *dev, void *host, size_t bytes);
 
+/* Host placement.  Every rank moves its share of the fields over ITS GPU's PCIe link; when the page-locked buffers
+ * (or the threads that fill them) live on the other socket, that traffic crosses the inter-socket link and the
+ * ranks of a box end up sharing one bottleneck (round 1: 8 ranks moved 16.8 GB at 142 GB/s in aggregate).
+ * mprg_host_bind_to_device restricts the calling process to the CPUs of the NUMA node the device hangs off and makes
+ * that node the preferred one for its future allocations (sched_setaffinity + set_mempolicy; what `numactl
+ * --cpunodebind --preferred` does).  Call it once per rank BEFORE allocating host buffers.  *node receives the node
+ * (-1: unknown / single-node host, nothing changed).  Needs no context. */
+int mprg_host_bind_to_device(int device, int *node);
 /* pinned host memory for callers that want full-speed H2D/D2H (optional) */
 int mprg_host_alloc(mprg_ctx *ctx, size_t bytes, void **ptr);
 int mprg_host_free(mprg_ctx *ctx, void *ptr);

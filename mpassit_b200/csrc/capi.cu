@@ -1,8 +1,13 @@
 // capi.cu -- extern "C" entry points declared in include/mpassit_rg.h.
 // No exception crosses the boundary: every entry returns an rc and records a
 // message retrievable with mprg_last_error().
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <thread>
@@ -13,21 +18,34 @@ using namespace mprg;
 
 static std::string g_init_error;
 
-// MPASSIT_TRACE=1: host wall time of every store / apply call on stderr (where an end-to-end pass goes)
+// MPASSIT_TRACE=1 / mprg_set_option("trace", "1"): host wall time of every store / apply call on stderr, with the time
+// since the trace was switched on (where an end-to-end pass goes)
+static std::atomic<int> g_trace{-1};
+static std::chrono::steady_clock::time_point g_trace_t0;
+static bool trace_on() {
+    int v = g_trace.load(std::memory_order_relaxed);
+    if (v < 0) {
+        v = getenv("MPASSIT_TRACE") != nullptr ? 1 : 0;
+        g_trace_t0 = std::chrono::steady_clock::now();
+        g_trace.store(v);
+    }
+    return v > 0;
+}
 struct Trace {
     const char *what;
     int a, b;
     std::chrono::steady_clock::time_point t0;
     bool on;
     Trace(const char *w, int a_ = 0, int b_ = 0) : what(w), a(a_), b(b_) {
-        static const bool enabled = getenv("MPASSIT_TRACE") != nullptr;
-        on = enabled;
+        on = trace_on();
         if (on) t0 = std::chrono::steady_clock::now();
     }
     ~Trace() {
         if (!on) return;
-        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        fprintf(stderr, "[mprg] %-14s %3d %3d  %9.3f ms\n", what, a, b, ms);
+        const auto t1 = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        const double at = std::chrono::duration<double, std::milli>(t0 - g_trace_t0).count();
+        fprintf(stderr, "[mprg] +%9.3f ms  %-14s %3d %3d  %9.3f ms\n", at, what, a, b, ms);
     }
 };
 
@@ -61,6 +79,9 @@ static bool set_option(mprg_ctx *c, const char *key, const char *val) {
     } else if (k == "apply") {
         t.pipeOff = v == "direct";
         if (v != "direct" && v != "pipe" && !v.empty()) return false;
+    } else if (k == "trace") {
+        g_trace_t0 = std::chrono::steady_clock::now();
+        g_trace.store(atoi(v.c_str()) != 0 ? 1 : 0);
     } else if (k == "pipe_split") {
         t.pipeSplit = v.empty() || atoi(v.c_str()) != 0;
     } else if (k == "pipe_minb") {
@@ -132,6 +153,60 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
     return 0;
 }
 
+int mprg_host_bind_to_device(int device, int *node) {
+    if (node) *node = -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return 6; }
+    for (char *p = bus; *p; ++p) *p = (char)tolower(*p);
+    int nd = -1;
+    {
+        std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+        FILE *f = fopen(path.c_str(), "r");
+        if (f) { if (fscanf(f, "%d", &nd) != 1) nd = -1; fclose(f); }
+    }
+    if (nd < 0) return 0;   // unknown / single node: leave the process alone
+    // the node's CPUs: /sys/devices/system/node/node<N>/cpulist, e.g. "0-31,64-95"
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int ncpu = 0;
+    {
+        std::string path = "/sys/devices/system/node/node" + std::to_string(nd) + "/cpulist";
+        FILE *f = fopen(path.c_str(), "r");
+        if (f) {
+            int a, b;
+            char sep;
+            while (fscanf(f, "%d", &a) == 1) {
+                b = a;
+                int c = fgetc(f);
+                if (c == '-') { if (fscanf(f, "%d", &b) != 1) b = a; c = fgetc(f); }
+                for (int k = a; k <= b && k < CPU_SETSIZE; ++k) { CPU_SET(k, &set); ++ncpu; }
+                if (c != ',') break;
+            }
+            (void)sep;
+            fclose(f);
+        }
+    }
+    // keep only CPUs this process is allowed to use (containers, cgroups)
+    cpu_set_t cur;
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+        int left = 0;
+        for (int k = 0; k < CPU_SETSIZE; ++k) {
+            if (CPU_ISSET(k, &set) && !CPU_ISSET(k, &cur)) CPU_CLR(k, &set);
+            if (CPU_ISSET(k, &set)) ++left;
+        }
+        ncpu = left;
+    }
+    if (ncpu > 0) sched_setaffinity(0, sizeof set, &set);
+    // MPOL_PREFERRED (1) for this node: pages of later allocations (page-locked ones included) come from it when it has room
+    unsigned long mask[16] = {0};
+    if (nd < (int)(sizeof mask * 8)) {
+        mask[nd / (8 * sizeof(unsigned long))] |= 1UL << (nd % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
+    }
+    if (node) *node = nd;
+    return 0;
+}
+
 int mprg_finalize(mprg_ctx *ctx) {
     if (!ctx) return 1;
     cudaSetDevice(ctx->device);
@@ -176,6 +251,7 @@ int mprg_set_stream(mprg_ctx *ctx, void *cuda_stream) {
 }
 
 int mprg_synchronize(mprg_ctx *ctx) {
+    Trace tr("synchronize");
     MPRG_ENTER(ctx)
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     MPRG_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
@@ -275,6 +351,7 @@ int mprg_set_async(mprg_ctx *ctx, int on) {
 int mprg_get_async(const mprg_ctx *ctx) { return ctx && ctx->async ? 1 : 0; }
 
 int mprg_download(mprg_ctx *ctx, const void *dev, void *host, size_t bytes) {
+    Trace tr("download", (int)(bytes >> 20));
     MPRG_ENTER(ctx)
     if (!dev || !host) fail(1, "mprg_download: null argument");
     // after everything queued so far on the context's stream; on the D2H stream so that it overlaps later kernels

@@ -26,7 +26,7 @@ EPI_NONE, EPI_ADD, EPI_MUL, EPI_ROT_U, EPI_ROT_V = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "mprg_init", "mprg_finalize", "mprg_last_error", "mprg_version", "mprg_set_stream", "mprg_synchronize", "mprg_set_async", "mprg_get_async", "mprg_set_option", "mprg_get_option", "mprg_download",
-    "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_set_target_projected", "mprg_get_target_lonlat", "mprg_target_map_factor", "mprg_set_rotation_from_target", "mprg_set_grid_kind", "mprg_get_slab", "mprg_store",
+    "mprg_host_bind_to_device", "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc", "mprg_device_free", "mprg_scratch", "mprg_has_rotation", "mprg_set_mesh", "mprg_set_target", "mprg_set_target_projected", "mprg_get_target_lonlat", "mprg_target_map_factor", "mprg_set_rotation_from_target", "mprg_set_grid_kind", "mprg_get_slab", "mprg_store",
     "mprg_release", "mprg_clear_routes", "mprg_set_weight_cache", "mprg_weight_cache_stats", "mprg_route_info", "mprg_route_export_csr", "mprg_route_import_csr",
     "mprg_apply", "mprg_apply_ex", "mprg_apply_into", "mprg_put_slab", "mprg_ipc_export", "mprg_ipc_open", "mprg_ipc_close_all", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
     "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_capture_begin", "mprg_capture_end", "mprg_graph_launch", "mprg_graph_release", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
     L.mprg_finalize.argtypes = [vp]
     L.mprg_set_stream.argtypes = [vp, vp]
     L.mprg_synchronize.argtypes = [vp]
+    L.mprg_host_bind_to_device.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.mprg_host_alloc.argtypes = [vp, C.c_size_t, pp]
     L.mprg_host_free.argtypes = [vp, vp]
     L.mprg_device_alloc.argtypes = [vp, C.c_size_t, pp]
@@ -137,6 +138,13 @@ def check(ctx, rc: int) -> None:
     if rc != 0:
         msg = load().mprg_last_error(ctx)
         raise MprgError(rc, msg.decode() if msg else "")
+
+
+def host_bind_to_device(device: int) -> int:
+    """Pin this process to the NUMA node of `device` (CPUs + preferred memory); returns the node or -1."""
+    node = C.c_int(-1)
+    load().mprg_host_bind_to_device(int(device), C.byref(node))
+    return node.value
 
 
 def np_ptr(a: np.ndarray) -> int:

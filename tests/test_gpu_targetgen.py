@@ -54,7 +54,8 @@ def compare_target_generation(wl, routes, min_weight_digits=1e-9):
         mf_dev = rd.target_map_factor(l.CENTER, 1, wl.cfg.truelat1, wl.cfg.truelat2)
         assert np.abs(mf_dev - mf_host).max() <= 1e-13
         ca, sa = rd.set_rotation_from_target()
-        assert np.abs(ca - wl.cosa).max() <= 1e-12 and np.abs(sa - wl.sina).max() <= 1e-12
+        # (alpha comes from differences of neighbouring coordinates: ulp-level coordinate differences are amplified)
+        assert np.abs(ca - wl.cosa).max() <= 1e-10 and np.abs(sa - wl.sina).max() <= 1e-10
         assert rd.has_rotation() if hasattr(rd, "has_rotation") else True
     rh.close(); rd.close()
     return out
