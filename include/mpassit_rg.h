@@ -79,9 +79,9 @@ int mprg_set_async(mprg_ctx *ctx, int on);
  * mprg_set_option changes it afterwards.  key / values [environment variable]:
  *   "accumulate"  "f32" (default) | "f64": arithmetic of fp32-in / fp32-out applies and of the wind rotation; f64 is
  *                 the reference's R8 arithmetic (one rounding on store)                          [MPASSIT_GPU_ACC]
- *   "pipe_split"  "1" (default) | "0": the column kernel is compiled per launch content; with 1 the aligned plain
- *                 fields of an apply run in their own (leanest) launch and wind pairs / unaligned level counts in a
- *                 second one, with 0 everything shares one launch                          [MPASSIT_GPU_PIPE_SPLIT]
+ *   "pipe_split"  "0" (default) | "1": the column kernel runs an apply's plain aligned fields in a lean first phase
+ *                 and wind pairs / unaligned level counts in a second phase of the SAME launch; with 1 the two
+ *                 groups get a launch each                                                  [MPASSIT_GPU_PIPE_SPLIT]
  *   "apply"       "pipe" (default) | "direct": register-gather kernels only                    [MPASSIT_GPU_APPLY]
  *   "pipe_minb"   0 (default: by shared memory) | 4 | 5 resident CTAs per SM               [MPASSIT_GPU_PIPE_MINB]
  *   "cols_minb"   2 | 3 (default) | 4: register cap of the register-gather kernel               [MPASSIT_GPU_MINB]

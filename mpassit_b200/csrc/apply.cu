@@ -469,18 +469,20 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             for (int L0 = 0; L0 < fields[f].nlev; L0 += kPipeLev) units.push_back(unit_of(fields[f], L0));
         }
     }
-    // Launch groups.  "split" (default): the aligned plain units -- the bulk of every pass -- run in the leanest
-    // variant of the kernel (48 registers, no spills, one barrier arrival per unit), everything that needs more
-    // (unaligned columns, wind pairs) in a second launch compiled for exactly that content; "one": a single launch.
+    // One launch, two phases: the plain aligned units first (the kernel's lean phase A), then wind pairs and
+    // unaligned columns (phase B).  pipe_split = 1 puts the two groups into separate launches instead.
+    std::vector<UnitDev> plain, rest;
+    for (const UnitDev &u : units)
+        (((u.flags & kUnitAligned) && !(u.flags & (kUnitRotU | kUnitRotV))) ? plain : rest).push_back(u);
     std::vector<std::vector<UnitDev>> groups;
+    std::vector<size_t> groupPlain;
     if (ctx->tune.pipeSplit) {
-        std::vector<UnitDev> plain, rest;
-        for (const UnitDev &u : units)
-            (((u.flags & kUnitAligned) && !(u.flags & (kUnitRotU | kUnitRotV))) ? plain : rest).push_back(u);
-        if (!plain.empty()) groups.push_back(std::move(plain));
-        if (!rest.empty()) groups.push_back(std::move(rest));
+        if (!plain.empty()) { groupPlain.push_back(plain.size()); groups.push_back(plain); }
+        if (!rest.empty()) { groupPlain.push_back(0); groups.push_back(rest); }
     } else {
-        groups.push_back(units);
+        groupPlain.push_back(plain.size());
+        plain.insert(plain.end(), rest.begin(), rest.end());
+        groups.push_back(std::move(plain));
     }
     PipeArgs<TACC> pa;
     pa.rec = rec;
@@ -496,7 +498,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         pa.rotc = sizeof(TR) == 4 ? (const void *)(ctx->rotc32.p + off) : (const void *)(ctx->rotc.p + off);
     }
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
-    struct Launch { size_t g, u0, nu, smem; int mode, minb; int32_t stageOff, stageBytes, holdOff; };
+    struct Launch { size_t g, u0, nu, smem; int mode, minb, nPlain; int32_t stageOff, stageBytes, holdOff; };
     std::vector<Launch> plan;
     for (size_t g = 0; g < groups.size(); ++g) {
         const std::vector<UnitDev> &us = groups[g];
@@ -505,10 +507,11 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             if (u0 + nu < us.size() && (us[u0 + nu - 1].flags & kUnitRotU)) --nu;  // keep a wind pair in one launch
             int mode = 0;
             size_t stage = 0;   // one stage holds the largest unit of the launch at the route's tile maxima
+            const int nPlain = (int)std::min<size_t>(nu, groupPlain[g] > u0 ? groupPlain[g] - u0 : 0);
             for (size_t k = 0; k < nu; ++k) {
                 const UnitDev &u = us[u0 + k];
-                if (!(u.flags & kUnitAligned)) mode |= kModeUnal;
-                if (u.flags & (kUnitRotU | kUnitRotV)) mode |= kModeRot;
+                if ((int)k >= nPlain && !(u.flags & kUnitAligned)) mode |= kModeUnal;
+                if ((int)k >= nPlain && (u.flags & (kUnitRotU | kUnitRotV))) mode |= kModeRot;
                 stage = std::max(stage, pipe_unit_stage_bytes((u.flags & kUnitAligned) != 0, (u.flags & kUnitMerged) != 0,
                                                               (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
             }
@@ -520,7 +523,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
             int minb = (smemBytes + 1024) * 5 <= (size_t)228 * 1024 ? 5 : 4;
             if (ctx->tune.pipeMinb) minb = ctx->tune.pipeMinb >= 5 ? 5 : 4;
-            plan.push_back(Launch{g, u0, nu, smemBytes, mode, minb, (int32_t)fixed, (int32_t)stage,
+            plan.push_back(Launch{g, u0, nu, smemBytes, mode, minb, nPlain, (int32_t)fixed, (int32_t)stage,
                                   (int32_t)(fixed + kPipeStages * stage)});
             u0 += nu;
         }
@@ -529,6 +532,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         UnitPack up;
         memcpy(up.u, groups[l.g].data() + l.u0, l.nu * sizeof(UnitDev));
         pa.nunits = (int)l.nu;
+        pa.nPlain = l.nPlain;
         pa.stageOff = l.stageOff; pa.stageBytes = l.stageBytes; pa.holdOff = l.holdOff;
         const size_t smemBytes = l.smem;
         const int minb = l.minb;

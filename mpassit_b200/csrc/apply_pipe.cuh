@@ -26,6 +26,8 @@
 // meshes numbered without locality -- ran at 60-68 % of the HBM peak against 71-88 % for bulk copies on every
 // numbering, and was removed.)
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mprg {
@@ -109,6 +111,7 @@ struct PipeArgs {
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
     int32_t nunits;
+    int32_t nPlain;     // the first nPlain units are plain aligned fields (phase A of the kernel)
     int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the record and the unit descriptors)
     int32_t stageBytes; // bytes of one stage (host: the largest unit's need at the route's tile maxima)
     int32_t holdOff;    // byte offset of the wind-pair hold buffer (kModeRot launches)
@@ -222,7 +225,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     using TR = typename RotMath<TOUT, TACC>::type;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *s_mbar = (unsigned long long *)smem;        // [0..1] one per stage, [2] the tile record
+    unsigned long long *s_mbar = (unsigned long long *)smem;        // [0..1] phase A stages, [2] the tile record, [3..4] phase B stages
     unsigned char *s_rec = smem + kPipeSmemHead;                    // the tile record (RecLayout)
     UnitDev *s_units = (UnitDev *)(s_rec + a.lay.stride);
     unsigned char *s_stage = smem + a.stageOff;
@@ -241,7 +244,10 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     // ---- prologue: ONE bulk copy brings the tile's record (schedule, per-target rows, weights) ---------------
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kPipeStages; ++i) mbar_init(s_mbar + i, UNAL ? kPipeWarps : 1);  // arrivals per unit
+        for (int i = 0; i < kPipeStages; ++i) {
+            mbar_init(s_mbar + i, 1);                    // phase A: one arrival per unit
+            mbar_init(s_mbar + 3 + i, kPipeWarps);       // phase B: one arrival per warp per unit
+        }
         mbar_init(s_mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         mbar_arrive_tx(s_mbar + 2, (unsigned)a.lay.stride);
@@ -277,78 +283,80 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         while (bslot + brun < nu && s_urun[bslot + brun] == s_urun[bslot]) ++brun;
     }
 
+    // Two phases in one launch.  Phase A: the first a.nPlain units are plain aligned fields -- the bulk of every
+    // pass -- and run the leanest code (one barrier arrival per unit, 16-byte loads only).  Phase B: wind pairs and
+    // unaligned columns (per-warp arrivals, in-place element loads, rotation).  One launch pays the tile prologue
+    // once; the lean loop is not slowed by the code and registers the general one needs.
+    const int nA = a.nPlain;
     auto issue = [&](int u) {
         if (u >= a.nunits) return;
         const UnitDev &ud = s_units[u];
         const unsigned chunkB = (unsigned)ud.Ln * ESZ;
         const unsigned sbase = stage0 + (u % kPipeStages) * a.stageBytes;
-        unsigned long long *bar = s_mbar + (u % kPipeStages);
         const bool merged = (ud.flags & kUnitMerged) != 0;
-        if (!UNAL || (ud.flags & kUnitAligned)) {
-            // exact column chunks.  Whole-column units whose column size is not a multiple of 128 bytes pack their
-            // slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
-            const bool packed = merged && (chunkB & 127u);
+        // exact column chunks (aligned units).  Whole-column units whose column size is not a multiple of 128 bytes
+        // pack their slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
+        const bool packed = merged && (chunkB & 127u);
+        if (u < nA) {
+            unsigned long long *bar = s_mbar + (u % kPipeStages);
             const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
-            if (!UNAL) {
-                if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)nu);   // one arrival posts the unit's bytes
-                if (packed) {
-                    if (brun > 0) bulk_g2s(sbase + bslot * chunkB, g, chunkB * (unsigned)brun, bar);
-                } else if (bcol >= 0) {
-                    bulk_g2s(sbase + bslot * (chunkB + 16u), g, chunkB, bar);
-                }
-            } else {
-                // mixed launch: the barrier counts one arrival per warp (lane 0 posts the bytes of the warp's copies)
-                const bool mine = packed ? brun > 0 : bcol >= 0;
-                const unsigned nb = mine ? (packed ? chunkB * (unsigned)brun : chunkB) : 0u;
-                const unsigned wb = __reduce_add_sync(0xffffffffu, nb);
-                if (lane == 0) mbar_arrive_tx(bar, wb);
-                if (nb) bulk_g2s(sbase + bslot * (packed ? chunkB : chunkB + 16u), g, nb, bar);
+            if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)nu);   // one arrival posts the unit's bytes
+            if (packed) {
+                if (brun > 0) bulk_g2s(sbase + bslot * chunkB, g, chunkB * (unsigned)brun, bar);
+            } else if (bcol >= 0) {
+                bulk_g2s(sbase + bslot * (chunkB + 16u), g, chunkB, bar);
             }
-        } else {
+            return;
+        }
+        if (MODE == 0) return;
+        // phase B: the barrier counts one arrival per warp (lane 0 posts the bytes of the warp's copies)
+        unsigned long long *bar = s_mbar + 3 + ((u - nA) % kPipeStages);
+        unsigned nb = 0, sdst = 0;
+        uintptr_t ga = 0;
+        if (!UNAL || (ud.flags & kUnitAligned)) {
+            if (packed ? brun > 0 : bcol >= 0) {
+                nb = packed ? chunkB * (unsigned)brun : chunkB;
+                sdst = sbase + bslot * (packed ? chunkB : chunkB + 16u);
+                ga = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
+            }
+        } else if (merged ? brun > 0 : bcol >= 0) {
             // unaligned columns: the 16-byte-aligned window around the run (or the single column chunk); it lands at
             // a 16-byte-aligned address chosen so that windows never overlap, and the math reads it where it lies.
             // (absolute addresses: the source base itself need only be element-aligned; device allocations are
             // 256-byte aligned, so the window's first 16-byte chunk always lies inside the caller's allocation)
-            unsigned nb = 0, sdst = 0;
-            uintptr_t al = 0;
-            if (merged ? brun > 0 : bcol >= 0) {
-                const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
-                const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
-                const uintptr_t aend = (uintptr_t)ud.src + ud.srcBytes;
-                al = a0 & ~(uintptr_t)15;
-                size_t n = ((a0 + (size_t)(ncol - 1) * ud.nlev * ESZ + chunkB + 15) & ~(uintptr_t)15) - al;
-                sdst = sbase + (((unsigned)bslot * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u);
-                if (al + n > aend) {
-                    // last window of the array: bulk-copy the whole 16-byte chunks, hand-copy the tail words
-                    const size_t full = (aend - al) & ~(size_t)15;
-                    for (size_t b = full; al + b < aend; b += 4) {
-                        const int32_t v = *(const int32_t *)(al + b);
-                        asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(sdst + (unsigned)b), "r"(v) : "memory");
-                    }
-                    n = full;
+            const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
+            const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
+            const uintptr_t aend = (uintptr_t)ud.src + ud.srcBytes;
+            ga = a0 & ~(uintptr_t)15;
+            size_t n = ((a0 + (size_t)(ncol - 1) * ud.nlev * ESZ + chunkB + 15) & ~(uintptr_t)15) - ga;
+            sdst = sbase + (((unsigned)bslot * chunkB + (unsigned)(kRunPad * r) + 15u) & ~15u);
+            if (ga + n > aend) {
+                // last window of the array: bulk-copy the whole 16-byte chunks, hand-copy the tail words
+                const size_t full = (aend - ga) & ~(size_t)15;
+                for (size_t b = full; ga + b < aend; b += 4) {
+                    const int32_t v = *(const int32_t *)(ga + b);
+                    asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(sdst + (unsigned)b), "r"(v) : "memory");
                 }
-                nb = (unsigned)n;
+                n = full;
             }
-            const unsigned wb = __reduce_add_sync(0xffffffffu, nb);   // (also orders the hand-copied tail before the arrival)
-            if (lane == 0) mbar_arrive_tx(bar, wb);
-            if (nb) bulk_g2s(sdst, (const void *)al, nb, bar);
+            nb = (unsigned)n;
         }
+        const unsigned wb = __reduce_add_sync(0xffffffffu, nb);   // (also orders the hand-copied tail before the arrival)
+        if (lane == 0) mbar_arrive_tx(bar, wb);
+        if (nb) bulk_g2s(sdst, (const void *)ga, nb, bar);
     };
 
-    issue(0);
-
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
-    for (int u = 0; u < a.nunits; ++u) {
-        if (u > 0) __syncthreads();     // every warp has finished reading unit u - 1: its buffer may be refilled
-        issue(u + 1);
-        mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
+
+    // the reduction of one unit; UN / RT: compile-time content of the phase the unit belongs to
+    auto math = [&](int u, auto UN_c, auto RT_c) {
+        constexpr bool UN = decltype(UN_c)::value, RT = decltype(RT_c)::value;
         const UnitDev &ud = s_units[u];
         const unsigned st = stage0 + (u % kPipeStages) * a.stageBytes;  // shared-window address of unit u's staging
         const int Ln = ud.Ln;
         const int eop = ud.flags & 0xff;
         const TACC earg = (TACC)ud.epi_arg;
         const int ngroups = (Ln + 3) >> 2;
-        if (!live) continue;
         // this lane's row (weights, slots, runs): one or two 16-byte shared loads per unit
         TACC rw[3];
         unsigned pk, pr = 0;
@@ -356,24 +364,24 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             float4 q;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(row0));
             rw[0] = (TACC)q.x; rw[1] = (TACC)q.y; rw[2] = (TACC)q.z; pk = __float_as_uint(q.w);
-            if (UNAL) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pr) : "r"(row0 + 16));
+            if (UN) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pr) : "r"(row0 + 16));
         } else {
             double x, y, z;
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(x), "=d"(y) : "r"(row0));
             asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(z) : "r"(row0 + 16));
             asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pk) : "r"(row0 + 24));
-            if (UNAL) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pr) : "r"(row0 + 32));
+            if (UN) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(pr) : "r"(row0 + 32));
             rw[0] = (TACC)x; rw[1] = (TACC)y; rw[2] = (TACC)z;
         }
         const int rlen = (int)(pk >> 24);                                       // (fast paths: <= 3)
         const int rbeg = fast ? 0 : (int)s_rowoff[lane], rend = fast ? 0 : (int)s_rowoff[lane + 1];   // (generic rows only)
         const unsigned chunkB = (unsigned)Ln * ESZ;
-        const bool direct = !UNAL || (ud.flags & kUnitAligned);     // columns sit 16-byte aligned at slot * ustride
+        const bool direct = !UN || (ud.flags & kUnitAligned);     // columns sit 16-byte aligned at slot * ustride
         const unsigned ustride = ((ud.flags & kUnitMerged) && (chunkB & 127u)) ? chunkB : chunkB + 16u;
         // byte offsets of this lane's columns in an unaligned unit's staging: the column of slot s in run r lies at
         // window(r) + (its global byte offset - the window's)
         unsigned co[3] = {0, 0, 0};
-        if (UNAL && !direct) {
+        if (UN && !direct) {
             const bool merged = (ud.flags & kUnitMerged) != 0;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -387,7 +395,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
         const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane;
         TOUT *d = (TOUT *)ud.dst + dcol;
-        const bool rotU = ROT && (ud.flags & kUnitRotU), rotV = ROT && (ud.flags & kUnitRotV);
+        const bool rotU = RT && (ud.flags & kUnitRotU), rotV = RT && (ud.flags & kUnitRotV);
 #pragma unroll
         for (int gi = 0; gi < kPipeLev / 4 / kPipeWarps; ++gi, d += grp8) {
             const int g = warp + gi * kPipeWarps;
@@ -467,6 +475,23 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                 for (int k = 0; k < 4; ++k)
                     if (4 * g + k < Ln) __stcs(d + (size_t)k * a.dstLev, (TOUT)acc[k]);
             }
+        }
+    };
+
+    issue(0);
+    for (int u = 0; u < nA; ++u) {
+        if (u > 0) __syncthreads();     // every warp has finished reading unit u - 1: its buffer may be refilled
+        issue(u + 1);
+        mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
+        if (live) math(u, std::false_type{}, std::false_type{});
+    }
+    if (MODE != 0) {
+        for (int u = nA; u < a.nunits; ++u) {
+            if (u > 0) __syncthreads();
+            issue(u + 1);
+            const int k = u - nA;
+            mbar_wait(s_mbar + 3 + (k % kPipeStages), (unsigned)((k / kPipeStages) & 1));
+            if (live) math(u, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
         }
     }
 }

@@ -176,7 +176,7 @@ struct mprg_tuning {
     bool acc64 = false;        // MPASSIT_GPU_ACC=f64 | option "accumulate": fp32 fields accumulate (and rotate) in fp64, the reference's R8
     bool pipeOff = false;      // MPASSIT_GPU_APPLY=direct | option "apply": register-gather kernels only
     int pipeMinb = 0;          // MPASSIT_GPU_PIPE_MINB | option "pipe_minb": 4 / 5 resident CTAs per SM (0 = by shared memory)
-    bool pipeSplit = true;     // MPASSIT_GPU_PIPE_SPLIT=0|1 | option "pipe_split": aligned plain units in their own (leanest) launch
+    bool pipeSplit = false;    // MPASSIT_GPU_PIPE_SPLIT=0|1 | option "pipe_split": plain aligned units and the rest in separate launches
     int colsMinb = 3;          // MPASSIT_GPU_MINB | option "cols_minb": register cap of the fallback kernel
     int uploadThreads = 0;     // MPASSIT_UPLOAD_THREADS | option "upload_threads" (0 = 3/4 of the cores / ranks)
 };
