@@ -425,7 +425,11 @@ template <typename KERN, typename TACC>
 static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes,
                           unsigned tiles) {
     MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa, up);
+    // persistent grid: as many CTAs as are resident at once; each walks the tiles with stride gridDim.x
+    int perSM = 1;
+    MPRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kPipeThreads, smemBytes));
+    const unsigned grid = std::min<unsigned>(tiles, (unsigned)std::max(1, perSM) * (unsigned)ctx->numSM);
+    kern<<<grid, kPipeThreads, smemBytes, ctx->stream>>>(pa, up);
     ctx->launches++;
 }
 
@@ -491,6 +495,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     pa.dstLev = dl.lev; pa.dstOff = dl.off;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
+    pa.nTiles = (int32_t)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
     pa.rotc = nullptr;
     if (rot) {  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
         using TR = typename RotMath<TOUT, TACC>::type;
@@ -516,7 +521,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
                                                               (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
             }
             stage = (stage + 15) & ~(size_t)15;
-            const size_t fixed = ((size_t)kPipeSmemHead + lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
+            const size_t fixed = ((size_t)kPipeSmemHead + 2 * (size_t)lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
             const size_t hold = (mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
             const size_t smemBytes = fixed + kPipeStages * stage + hold;
             if (smemBytes + 1024 > (size_t)227 * 1024) return false;

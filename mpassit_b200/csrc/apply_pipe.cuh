@@ -110,6 +110,7 @@ struct PipeArgs {
     int64_t dstLev, dstOff;
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
+    int32_t nTiles;     // tiles of the route; the grid is persistent (a few CTAs per SM), CTA b takes tiles b, b + grid, ...
     int32_t nunits;
     int32_t nPlain;     // the first nPlain units are plain aligned fields (phase A of the kernel)
     int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the record and the unit descriptors)
@@ -137,7 +138,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned smemDst, const void *gmem, uns
                  "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-// dynamic shared memory: [mbarriers 64 B][tile record][unit descriptors][stages][hold buffer (kModeRot)]
+// dynamic shared memory: [mbarriers 64 B][2 tile records][unit descriptors][stages][hold buffer (kModeRot)]
 constexpr int kPipeSmemHead = 64;
 // bytes of one stage that a unit needs for a tile of nu columns in nruns runs.  Aligned units: slots packed at the
 // column size so that a run is contiguous in shared memory too -- unless that size is a multiple of 128 bytes (every
@@ -225,82 +226,80 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     using TR = typename RotMath<TOUT, TACC>::type;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *s_mbar = (unsigned long long *)smem;        // [0..1] phase A stages, [2] the tile record, [3..4] phase B stages
-    unsigned char *s_rec = smem + kPipeSmemHead;                    // the tile record (RecLayout)
-    UnitDev *s_units = (UnitDev *)(s_rec + a.lay.stride);
+    // [0..1] phase A stages, [3..4] phase B stages, [5..6] the two tile-record buffers
+    unsigned long long *s_mbar = (unsigned long long *)smem;
+    unsigned char *s_rec0 = smem + kPipeSmemHead;                   // two tile records (RecLayout), double buffered
+    UnitDev *s_units = (UnitDev *)(s_rec0 + 2 * a.lay.stride);
     unsigned char *s_stage = smem + a.stageOff;
-    const int32_t *s_uniq = (const int32_t *)(s_rec + a.lay.offUniq);
-    const unsigned char *s_urun = s_rec + a.lay.offUrun;
-    const unsigned char *s_runFirst = s_rec + a.lay.offRunFirst;
-    const unsigned short *s_rowoff = (const unsigned short *)(s_rec + a.lay.offRowoff);   // (generic routes only)
-    const unsigned short *s_off = (const unsigned short *)(s_rec + a.lay.offEoff);
-    const TACC *s_w = (const TACC *)(s_rec + a.lay.offEw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = blockIdx.x / a.tilesPerRow;
-    const int i0 = (blockIdx.x - row * a.tilesPerRow) * kPipeTile;
-    const int64_t t0 = (int64_t)row * a.ni + i0;
+    const int G = (int)gridDim.x;
+    int tile = (int)blockIdx.x;          // PERSISTENT: this CTA takes tiles blockIdx.x, + gridDim.x, ...
+    if (tile >= a.nTiles) return;
 
-    // ---- prologue: ONE bulk copy brings the tile's record (schedule, per-target rows, weights) ---------------
+    // The record of a tile (schedule, per-target rows, weights) comes with ONE bulk copy, and it is fetched a whole
+    // tile ahead: no CTA ever waits for the three dependent memory latencies a CSR-driven prologue costs.
+    auto fetch_rec = [&](int t, int buf, bool first) {   // thread 0 only
+        unsigned long long *bar = s_mbar + 5 + buf;
+        (void)first;
+        mbar_arrive_tx(bar, (unsigned)a.lay.stride);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec0 + buf * a.lay.stride), a.rec + (size_t)t * a.lay.stride,
+                 (unsigned)a.lay.stride, bar);
+    };
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kPipeStages; ++i) {
             mbar_init(s_mbar + i, 1);                    // phase A: one arrival per unit
             mbar_init(s_mbar + 3 + i, kPipeWarps);       // phase B: one arrival per warp per unit
+            mbar_init(s_mbar + 5 + i, 1);                // tile records
         }
-        mbar_init(s_mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        mbar_arrive_tx(s_mbar + 2, (unsigned)a.lay.stride);
-        bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec), a.rec + (size_t)blockIdx.x * a.lay.stride, (unsigned)a.lay.stride, s_mbar + 2);
+        fetch_rec(tile, 0, true);
+        if (tile + G < a.nTiles) fetch_rec(tile + G, 1, true);
     }
     for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
         ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
     __syncthreads();             // barriers initialised, unit descriptors in place
-    mbar_wait(s_mbar + 2, 0);    // the record has landed
-    const int nu = ((const unsigned short *)s_rec)[0];
-    const int ntile = ((const unsigned short *)s_rec)[3];
-    const unsigned rflags = ((const unsigned *)s_rec)[2];
-    const bool live = lane < ntile;
-    const bool fast = (rflags & kRecFast) != 0;   // every row of the tile has <= 3 entries
-    // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
-    const bool all3 = (rflags & kRecAll3) != 0;
-    // this lane's row (3 weights, slots, runs, length): re-read every unit with one or two 16-byte shared loads
-    // instead of living in 6-8 registers across the copy issue and the barrier
-    const unsigned row0 = (unsigned)__cvta_generic_to_shared(s_rec + 16 + lane * 8 * (int)sizeof(TACC));
 
     const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
     const unsigned hold0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.holdOff;
+    const int nA = a.nPlain, nB = a.nunits - a.nPlain;
 
+    // ---- copy-issue state: the tile whose units are being FETCHED (one unit ahead of the math, so it moves on to
+    //      the next tile while the last unit of the current one is reduced) ---------------------------------------
     // slot s = lane * warps + warp is copied by that lane, so the (warp-serialised) bulk-copy issue is spread
     // evenly over all warps instead of queuing behind the first two.  The list is in ascending id order and columns
     // of consecutive ids are contiguous in memory, so the owner of the first slot of a run fetches the whole run
     // with one bulk copy (brun = its length in columns, 0 for the other slots of the run).
     const int bslot = lane * kPipeWarps + warp;
-    const int bcol = bslot < nu ? s_uniq[bslot] : -1;
-    int brun = 0;
-    if (bcol >= 0 && (bslot == 0 || s_urun[bslot] != s_urun[bslot - 1])) {
-        brun = 1;
-        while (bslot + brun < nu && s_urun[bslot + brun] == s_urun[bslot]) ++brun;
-    }
+    int inu = 0, bcol = -1, brun = 0, brunIdx = 0;
+    auto issue_state = [&](int buf) {
+        const unsigned char *rec = s_rec0 + buf * a.lay.stride;
+        const int32_t *uq = (const int32_t *)(rec + a.lay.offUniq);
+        const unsigned char *ur = rec + a.lay.offUrun;
+        inu = ((const unsigned short *)rec)[0];
+        bcol = bslot < inu ? uq[bslot] : -1;
+        brun = 0;
+        brunIdx = bcol >= 0 ? (int)ur[bslot] : 0;
+        if (bcol >= 0 && (bslot == 0 || ur[bslot] != ur[bslot - 1])) {
+            brun = 1;
+            while (bslot + brun < inu && ur[bslot + brun] == ur[bslot]) ++brun;
+        }
+    };
 
-    // Two phases in one launch.  Phase A: the first a.nPlain units are plain aligned fields -- the bulk of every
-    // pass -- and run the leanest code (one barrier arrival per unit, 16-byte loads only).  Phase B: wind pairs and
-    // unaligned columns (per-warp arrivals, in-place element loads, rotation).  One launch pays the tile prologue
-    // once; the lean loop is not slowed by the code and registers the general one needs.
-    const int nA = a.nPlain;
-    auto issue = [&](int u) {
-        if (u >= a.nunits) return;
+    // kk: how many tiles this CTA has taken before the one the unit belongs to (stage / barrier parity run across tiles)
+    auto issue = [&](int kk, int u) {
         const UnitDev &ud = s_units[u];
         const unsigned chunkB = (unsigned)ud.Ln * ESZ;
-        const unsigned sbase = stage0 + (u % kPipeStages) * a.stageBytes;
+        const unsigned sbase = stage0 + ((kk * a.nunits + u) % kPipeStages) * a.stageBytes;
         const bool merged = (ud.flags & kUnitMerged) != 0;
         // exact column chunks (aligned units).  Whole-column units whose column size is not a multiple of 128 bytes
         // pack their slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
         const bool packed = merged && (chunkB & 127u);
         if (u < nA) {
-            unsigned long long *bar = s_mbar + (u % kPipeStages);
+            unsigned long long *bar = s_mbar + ((kk * nA + u) % kPipeStages);
             const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
-            if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)nu);   // one arrival posts the unit's bytes
+            if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)inu);   // one arrival posts the unit's bytes
             if (packed) {
                 if (brun > 0) bulk_g2s(sbase + bslot * chunkB, g, chunkB * (unsigned)brun, bar);
             } else if (bcol >= 0) {
@@ -310,7 +309,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
         if (MODE == 0) return;
         // phase B: the barrier counts one arrival per warp (lane 0 posts the bytes of the warp's copies)
-        unsigned long long *bar = s_mbar + 3 + ((u - nA) % kPipeStages);
+        unsigned long long *bar = s_mbar + 3 + ((kk * nB + (u - nA)) % kPipeStages);
         unsigned nb = 0, sdst = 0;
         uintptr_t ga = 0;
         if (!UNAL || (ud.flags & kUnitAligned)) {
@@ -324,7 +323,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             // a 16-byte-aligned address chosen so that windows never overlap, and the math reads it where it lies.
             // (absolute addresses: the source base itself need only be element-aligned; device allocations are
             // 256-byte aligned, so the window's first 16-byte chunk always lies inside the caller's allocation)
-            const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
+            const int ncol = merged ? brun : 1, r = merged ? brunIdx : bslot;
             const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
             const uintptr_t aend = (uintptr_t)ud.src + ud.srcBytes;
             ga = a0 & ~(uintptr_t)15;
@@ -346,13 +345,42 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         if (nb) bulk_g2s(sdst, (const void *)ga, nb, bar);
     };
 
+    // ---- math state: the tile being REDUCED ---------------------------------------------------------------------
+    const unsigned char *s_rec = s_rec0;
+    const int32_t *s_uniq = nullptr;
+    const unsigned char *s_runFirst = nullptr;
+    const unsigned short *s_rowoff = nullptr, *s_off = nullptr;
+    const TACC *s_w = nullptr;
+    int64_t t0 = 0;
+    bool live = false, fast = true, all3 = false;
+    unsigned row0 = 0;
+    auto math_state = [&](int buf, int t) {
+        s_rec = s_rec0 + buf * a.lay.stride;
+        s_uniq = (const int32_t *)(s_rec + a.lay.offUniq);
+        s_runFirst = s_rec + a.lay.offRunFirst;
+        s_rowoff = (const unsigned short *)(s_rec + a.lay.offRowoff);   // (generic routes only)
+        s_off = (const unsigned short *)(s_rec + a.lay.offEoff);
+        s_w = (const TACC *)(s_rec + a.lay.offEw);
+        const int row = t / a.tilesPerRow;
+        t0 = (int64_t)row * a.ni + (int64_t)(t - row * a.tilesPerRow) * kPipeTile;
+        const int ntile = ((const unsigned short *)s_rec)[3];
+        const unsigned rflags = ((const unsigned *)s_rec)[2];
+        live = lane < ntile;
+        fast = (rflags & kRecFast) != 0;   // every row of the tile has <= 3 entries
+        // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
+        all3 = (rflags & kRecAll3) != 0;
+        // this lane's row (3 weights, slots, runs, length): re-read every unit with one or two 16-byte shared loads
+        // instead of living in 6-8 registers across the copy issue and the barrier
+        row0 = (unsigned)__cvta_generic_to_shared(s_rec + 16 + lane * 8 * (int)sizeof(TACC));
+    };
+
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
 
     // the reduction of one unit; UN / RT: compile-time content of the phase the unit belongs to
-    auto math = [&](int u, auto UN_c, auto RT_c) {
+    auto math = [&](int kk, int u, auto UN_c, auto RT_c) {
         constexpr bool UN = decltype(UN_c)::value, RT = decltype(RT_c)::value;
         const UnitDev &ud = s_units[u];
-        const unsigned st = stage0 + (u % kPipeStages) * a.stageBytes;  // shared-window address of unit u's staging
+        const unsigned st = stage0 + ((kk * a.nunits + u) % kPipeStages) * a.stageBytes;  // shared-window address of unit u's staging
         const int Ln = ud.Ln;
         const int eop = ud.flags & 0xff;
         const TACC earg = (TACC)ud.epi_arg;
@@ -478,21 +506,38 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
     };
 
-    issue(0);
-    for (int u = 0; u < nA; ++u) {
-        if (u > 0) __syncthreads();     // every warp has finished reading unit u - 1: its buffer may be refilled
-        issue(u + 1);
-        mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
-        if (live) math(u, std::false_type{}, std::false_type{});
-    }
-    if (MODE != 0) {
-        for (int u = nA; u < a.nunits; ++u) {
-            if (u > 0) __syncthreads();
-            issue(u + 1);
-            const int k = u - nA;
-            mbar_wait(s_mbar + 3 + (k % kPipeStages), (unsigned)((k / kPipeStages) & 1));
-            if (live) math(u, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
+    // ---- the sweep: tiles x units, copies one unit ahead of the math, across tile boundaries too ------------------
+    mbar_wait(s_mbar + 5, 0);    // the first record has landed
+    issue_state(0);
+    issue(0, 0);
+    for (int kk = 0;; ++kk) {
+        const int buf = kk & 1;
+        const bool hasNext = tile + G < a.nTiles;
+        math_state(buf, tile);
+        for (int u = 0; u < a.nunits; ++u) {
+            if (kk > 0 || u > 0) __syncthreads();   // every warp has finished reading the previous unit: its buffer may be refilled
+            if (u == 0 && kk > 0 && tid == 0 && hasNext)
+                fetch_rec(tile + G, buf ^ 1, false);   // (the other record buffer belonged to the previous tile: free now)
+            if (u + 1 < a.nunits) {
+                issue(kk, u + 1);
+            } else if (hasNext) {
+                // the next tile's record arrived long ago (fetched a tile ahead): start ITS first unit now
+                mbar_wait(s_mbar + 5 + (buf ^ 1), (unsigned)(((kk + 1) >> 1) & 1));
+                issue_state(buf ^ 1);
+                issue(kk + 1, 0);
+            }
+            if (u < nA) {
+                const int c = kk * nA + u;
+                mbar_wait(s_mbar + (c % kPipeStages), (unsigned)((c / kPipeStages) & 1));  // unit u's bytes have landed
+                if (live) math(kk, u, std::false_type{}, std::false_type{});
+            } else if (MODE != 0) {
+                const int c = kk * nB + (u - nA);
+                mbar_wait(s_mbar + 3 + (c % kPipeStages), (unsigned)((c / kPipeStages) & 1));
+                if (live) math(kk, u, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
+            }
         }
+        if (!hasNext) break;
+        tile += G;
     }
 }
 

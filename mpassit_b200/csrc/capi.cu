@@ -116,6 +116,7 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
     c->device = device; c->rank = rank; c->nranks = nranks;
     try {
         MPRG_CUDA(cudaSetDevice(device));
+        MPRG_CUDA(cudaDeviceGetAttribute(&c->numSM, cudaDevAttrMultiProcessorCount, device));
         // engine temporaries come from the stream-ordered pool and stay cached in it (common.cuh: DevBuf)
         cudaMemPool_t pool;
         MPRG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));

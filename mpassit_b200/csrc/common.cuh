@@ -183,6 +183,7 @@ struct mprg_tuning {
 
 struct mprg_ctx {
     int device = 0, rank = 0, nranks = 1;
+    int numSM = mprg::kNumSM;             // multiprocessors of the device (persistent grids)
     mprg_tuning tune;
     int gridKind = MPRG_GRID_NOPERI;      // mprg_set_grid_kind: topology of the target grid as a regrid source
     std::string cacheDir;                 // mprg_set_weight_cache: directory of the cross-run weight cache ("" = off)
