@@ -425,11 +425,7 @@ template <typename KERN, typename TACC>
 static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes,
                           unsigned tiles) {
     MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    // persistent grid: as many CTAs as are resident at once; each walks the tiles with stride gridDim.x
-    int perSM = 1;
-    MPRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kPipeThreads, smemBytes));
-    const unsigned grid = std::min<unsigned>(tiles, (unsigned)std::max(1, perSM) * (unsigned)ctx->numSM);
-    kern<<<grid, kPipeThreads, smemBytes, ctx->stream>>>(pa, up);
+    kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa, up);   // `tiles` = strips: one CTA each
     ctx->launches++;
 }
 
@@ -502,7 +498,8 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         const int64_t off = 4 * ctx->target[r->dst_stagger].slabOffset();
         pa.rotc = sizeof(TR) == 4 ? (const void *)(ctx->rotc32.p + off) : (const void *)(ctx->rotc.p + off);
     }
-    const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
+    const unsigned gridRows = (unsigned)((r->nDst + r->dstNi - 1) / r->dstNi);
+    const unsigned tiles = ((gridRows + kStripRows - 1) / kStripRows) * (unsigned)pa.tilesPerRow;   // strips
     struct Launch { size_t g, u0, nu, smem; int mode, minb, nPlain; int32_t stageOff, stageBytes, holdOff; };
     std::vector<Launch> plan;
     for (size_t g = 0; g < groups.size(); ++g) {
@@ -521,7 +518,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
                                                               (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
             }
             stage = (stage + 15) & ~(size_t)15;
-            const size_t fixed = ((size_t)kPipeSmemHead + 2 * (size_t)lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
+            const size_t fixed = ((size_t)kPipeSmemHead + (size_t)kStripRows * lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
             const size_t hold = (mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
             const size_t smemBytes = fixed + kPipeStages * stage + hold;
             if (smemBytes + 1024 > (size_t)227 * 1024) return false;

@@ -38,6 +38,7 @@ constexpr int kPipeTile = 32;
 constexpr int kPipeCap = 256;      // CSR entries per tile accepted (== threads: one entry per thread in the prologue)
 constexpr int kPipeLev = 64;       // levels per unit
 constexpr int kPipeMaxUnits = 64;  // units (field x 64-level chunk) per launch; the host splits longer stacks
+constexpr int kStripRows = 4;       // vertically adjacent tiles swept together by one CTA
 constexpr int kPipeStages = 2;     // resident CTAs beat pipeline depth (profiles/r01: 2 x 5 CTAs > 3 x 4 > 4 x 3)
 constexpr int kRunPad = 40;        // unaligned units: slack per run so that 16-byte-aligned windows never overlap
 // launch content the kernel is compiled for
@@ -73,19 +74,21 @@ constexpr int kUnitMerged = 0x800;                   // the chunk is the whole c
 //                   run0 | run1 << 8 | run2 << 16   (rows of <= 3 entries; longer rows: len only)
 //   uniq     int32 [nuCap]   distinct source columns of the tile, ascending
 //   urun     uint8 [nuCap]   run (maximal sequence of consecutive ids) each of them belongs to
+//   runLen   uint8 [nuCap]   at the first slot of a run: its length in columns; 0 elsewhere
 //   runFirst uint8 [runCap]  first slot of every run
 //   (routes with rows of more than 3 entries only -- conservative:)
 //   rowoff   uint16 [34]     entry offset of every target's row
 //   eoff     uint16 [entCap] per entry: slot | run << 8
 //   ew       weight [entCap] per entry
 struct RecLayout {
-    int32_t stride, offUniq, offUrun, offRunFirst, offRowoff, offEoff, offEw;
+    int32_t stride, offUniq, offUrun, offRunLen, offRunFirst, offRowoff, offEoff, offEw;
 };
 __host__ __device__ inline RecLayout rec_layout(int wsize, int nuMax, int runsMax, int entMax, bool generic) {
     RecLayout L;
     int o = 16 + kPipeTile * 8 * wsize;
     L.offUniq = o; o += ((nuMax + 3) & ~3) * 4;
     L.offUrun = o; o += (nuMax + 15) & ~15;
+    L.offRunLen = o; o += (nuMax + 15) & ~15;
     L.offRunFirst = o; o += (runsMax + 15) & ~15;
     L.offRowoff = L.offEoff = L.offEw = 0;
     if (generic) {
@@ -110,7 +113,7 @@ struct PipeArgs {
     int64_t dstLev, dstOff;
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
-    int32_t nTiles;     // tiles of the route; the grid is persistent (a few CTAs per SM), CTA b takes tiles b, b + grid, ...
+    int32_t nTiles;     // tiles of the route (tilesPerRow x grid rows); one CTA per strip of kStripRows rows
     int32_t nunits;
     int32_t nPlain;     // the first nPlain units are plain aligned fields (phase A of the kernel)
     int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the record and the unit descriptors)
@@ -226,36 +229,35 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     using TR = typename RotMath<TOUT, TACC>::type;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    // [0..1] phase A stages, [3..4] phase B stages, [5..6] the two tile-record buffers
+    // [0..1] phase A stages, [2] the strip's tile records, [3..4] phase B stages
     unsigned long long *s_mbar = (unsigned long long *)smem;
-    unsigned char *s_rec0 = smem + kPipeSmemHead;                   // two tile records (RecLayout), double buffered
-    UnitDev *s_units = (UnitDev *)(s_rec0 + 2 * a.lay.stride);
+    unsigned char *s_rec0 = smem + kPipeSmemHead;                   // the strip's tile records (RecLayout), one per row
+    UnitDev *s_units = (UnitDev *)(s_rec0 + kStripRows * a.lay.stride);
     unsigned char *s_stage = smem + a.stageOff;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = (int)gridDim.x;
-    int tile = (int)blockIdx.x;          // PERSISTENT: this CTA takes tiles blockIdx.x, + gridDim.x, ...
-    if (tile >= a.nTiles) return;
+    // A CTA owns a STRIP: the tiles of kStripRows consecutive grid rows above one another, and sweeps it unit-major
+    // (unit 0 of every row, unit 1 of every row, ...).  Vertically adjacent tiles share about half of their source
+    // columns, so the second fetch of a column follows the first within a unit time (an L2 hit whatever the other CTAs
+    // do), and the strip pays the record fetch and the pipeline fill once for kStripRows tiles.
+    const int tcol = (int)blockIdx.x % a.tilesPerRow;
+    const int row0g = ((int)blockIdx.x / a.tilesPerRow) * kStripRows;
+    const int nrowsGrid = a.nTiles / a.tilesPerRow;
+    const int Rn = min(kStripRows, nrowsGrid - row0g);   // rows of this strip
 
-    // The record of a tile (schedule, per-target rows, weights) comes with ONE bulk copy, and it is fetched a whole
-    // tile ahead: no CTA ever waits for the three dependent memory latencies a CSR-driven prologue costs.
-    auto fetch_rec = [&](int t, int buf, bool first) {   // thread 0 only
-        unsigned long long *bar = s_mbar + 5 + buf;
-        (void)first;
-        mbar_arrive_tx(bar, (unsigned)a.lay.stride);
-        bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec0 + buf * a.lay.stride), a.rec + (size_t)t * a.lay.stride,
-                 (unsigned)a.lay.stride, bar);
-    };
+    // ---- prologue: one bulk copy per tile record (schedule, per-target rows, weights), all in flight together ----
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kPipeStages; ++i) {
-            mbar_init(s_mbar + i, 1);                    // phase A: one arrival per unit
-            mbar_init(s_mbar + 3 + i, kPipeWarps);       // phase B: one arrival per warp per unit
-            mbar_init(s_mbar + 5 + i, 1);                // tile records
+            mbar_init(s_mbar + i, 1);                    // phase A: one arrival per step
+            mbar_init(s_mbar + 3 + i, kPipeWarps);       // phase B: one arrival per warp per step
         }
+        mbar_init(s_mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        fetch_rec(tile, 0, true);
-        if (tile + G < a.nTiles) fetch_rec(tile + G, 1, true);
+        mbar_arrive_tx(s_mbar + 2, (unsigned)(Rn * a.lay.stride));
+        for (int r = 0; r < Rn; ++r)
+            bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec0 + r * a.lay.stride),
+                     a.rec + (size_t)((row0g + r) * a.tilesPerRow + tcol) * a.lay.stride, (unsigned)a.lay.stride, s_mbar + 2);
     }
     for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
         ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
@@ -273,31 +275,26 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     // with one bulk copy (brun = its length in columns, 0 for the other slots of the run).
     const int bslot = lane * kPipeWarps + warp;
     int inu = 0, bcol = -1, brun = 0, brunIdx = 0;
-    auto issue_state = [&](int buf) {
-        const unsigned char *rec = s_rec0 + buf * a.lay.stride;
-        const int32_t *uq = (const int32_t *)(rec + a.lay.offUniq);
-        const unsigned char *ur = rec + a.lay.offUrun;
+    auto issue_state = [&](int r) {
+        const unsigned char *rec = s_rec0 + r * a.lay.stride;
         inu = ((const unsigned short *)rec)[0];
-        bcol = bslot < inu ? uq[bslot] : -1;
-        brun = 0;
-        brunIdx = bcol >= 0 ? (int)ur[bslot] : 0;
-        if (bcol >= 0 && (bslot == 0 || ur[bslot] != ur[bslot - 1])) {
-            brun = 1;
-            while (bslot + brun < inu && ur[bslot + brun] == ur[bslot]) ++brun;
-        }
+        const bool have = bslot < inu;
+        bcol = have ? ((const int32_t *)(rec + a.lay.offUniq))[bslot] : -1;
+        brun = have ? (int)rec[a.lay.offRunLen + bslot] : 0;           // run length at the first slot of a run, else 0
+        if (UNAL) brunIdx = have ? (int)rec[a.lay.offUrun + bslot] : 0;
     };
 
-    // kk: how many tiles this CTA has taken before the one the unit belongs to (stage / barrier parity run across tiles)
-    auto issue = [&](int kk, int u) {
+    // step = u * Rn + r (unit-major over the strip's rows): stage and barrier parity run along the steps
+    auto issue = [&](int step, int u) {
         const UnitDev &ud = s_units[u];
         const unsigned chunkB = (unsigned)ud.Ln * ESZ;
-        const unsigned sbase = stage0 + ((kk * a.nunits + u) % kPipeStages) * a.stageBytes;
+        const unsigned sbase = stage0 + (step % kPipeStages) * a.stageBytes;
         const bool merged = (ud.flags & kUnitMerged) != 0;
         // exact column chunks (aligned units).  Whole-column units whose column size is not a multiple of 128 bytes
         // pack their slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
         const bool packed = merged && (chunkB & 127u);
         if (u < nA) {
-            unsigned long long *bar = s_mbar + ((kk * nA + u) % kPipeStages);
+            unsigned long long *bar = s_mbar + (step % kPipeStages);
             const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
             if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)inu);   // one arrival posts the unit's bytes
             if (packed) {
@@ -309,7 +306,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
         if (MODE == 0) return;
         // phase B: the barrier counts one arrival per warp (lane 0 posts the bytes of the warp's copies)
-        unsigned long long *bar = s_mbar + 3 + ((kk * nB + (u - nA)) % kPipeStages);
+        unsigned long long *bar = s_mbar + 3 + ((step - nA * Rn) % kPipeStages);
         unsigned nb = 0, sdst = 0;
         uintptr_t ga = 0;
         if (!UNAL || (ud.flags & kUnitAligned)) {
@@ -354,8 +351,9 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     int64_t t0 = 0;
     bool live = false, fast = true, all3 = false;
     unsigned row0 = 0;
-    auto math_state = [&](int buf, int t) {
-        s_rec = s_rec0 + buf * a.lay.stride;
+    auto math_state = [&](int r) {
+        const int t = (row0g + r) * a.tilesPerRow + tcol;
+        s_rec = s_rec0 + r * a.lay.stride;
         s_uniq = (const int32_t *)(s_rec + a.lay.offUniq);
         s_runFirst = s_rec + a.lay.offRunFirst;
         s_rowoff = (const unsigned short *)(s_rec + a.lay.offRowoff);   // (generic routes only)
@@ -377,10 +375,10 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
 
     // the reduction of one unit; UN / RT: compile-time content of the phase the unit belongs to
-    auto math = [&](int kk, int u, auto UN_c, auto RT_c) {
+    auto math = [&](int step, int u, int /*r*/, auto UN_c, auto RT_c) {
         constexpr bool UN = decltype(UN_c)::value, RT = decltype(RT_c)::value;
         const UnitDev &ud = s_units[u];
-        const unsigned st = stage0 + ((kk * a.nunits + u) % kPipeStages) * a.stageBytes;  // shared-window address of unit u's staging
+        const unsigned st = stage0 + (step % kPipeStages) * a.stageBytes;  // shared-window address of this step's staging
         const int Ln = ud.Ln;
         const int eop = ud.flags & 0xff;
         const TACC earg = (TACC)ud.epi_arg;
@@ -506,38 +504,44 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
     };
 
-    // ---- the sweep: tiles x units, copies one unit ahead of the math, across tile boundaries too ------------------
-    mbar_wait(s_mbar + 5, 0);    // the first record has landed
-    issue_state(0);
-    issue(0, 0);
-    for (int kk = 0;; ++kk) {
-        const int buf = kk & 1;
-        const bool hasNext = tile + G < a.nTiles;
-        math_state(buf, tile);
-        for (int u = 0; u < a.nunits; ++u) {
-            if (kk > 0 || u > 0) __syncthreads();   // every warp has finished reading the previous unit: its buffer may be refilled
-            if (u == 0 && kk > 0 && tid == 0 && hasNext)
-                fetch_rec(tile + G, buf ^ 1, false);   // (the other record buffer belonged to the previous tile: free now)
-            if (u + 1 < a.nunits) {
-                issue(kk, u + 1);
-            } else if (hasNext) {
-                // the next tile's record arrived long ago (fetched a tile ahead): start ITS first unit now
-                mbar_wait(s_mbar + 5 + (buf ^ 1), (unsigned)(((kk + 1) >> 1) & 1));
-                issue_state(buf ^ 1);
-                issue(kk + 1, 0);
-            }
-            if (u < nA) {
-                const int c = kk * nA + u;
-                mbar_wait(s_mbar + (c % kPipeStages), (unsigned)((c / kPipeStages) & 1));  // unit u's bytes have landed
-                if (live) math(kk, u, std::false_type{}, std::false_type{});
-            } else if (MODE != 0) {
-                const int c = kk * nB + (u - nA);
-                mbar_wait(s_mbar + 3 + (c % kPipeStages), (unsigned)((c / kPipeStages) & 1));
-                if (live) math(kk, u, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
+    // ---- the sweep: units x rows of the strip, copies one step ahead of the math --------------------------------
+    mbar_wait(s_mbar + 2, 0);    // the strip's records have landed
+    const int nsteps = a.nunits * Rn, stepsA = nA * Rn;
+    // step -> (unit, strip row): unit-major, except that the two units of a wind pair alternate row by row (zonal r,
+    // meridional r, zonal r + 1, ...) so that the zonal results wait in the hold buffer for one step only
+    auto step_of = [&](int st, int &uu, int &rr) {
+        uu = st / Rn;
+        rr = st - uu * Rn;
+        if (ROT && st >= stepsA) {
+            const int fl = s_units[uu].flags;
+            if (fl & (kUnitRotU | kUnitRotV)) {
+                const int uU = (fl & kUnitRotU) ? uu : uu - 1;
+                const int q = st - uU * Rn;
+                rr = q >> 1;
+                uu = uU + (q & 1);
             }
         }
-        if (!hasNext) break;
-        tile += G;
+    };
+    issue_state(0);
+    issue(0, 0);
+    for (int step = 0; step < nsteps; ++step) {
+        if (step > 0) __syncthreads();   // every warp has finished reading the previous step: its buffer may be refilled
+        int u, r, un, rn;
+        step_of(step, u, r);
+        if (step + 1 < nsteps) {
+            step_of(step + 1, un, rn);
+            issue_state(rn);
+            issue(step + 1, un);
+        }
+        math_state(r);
+        if (step < stepsA) {
+            mbar_wait(s_mbar + (step % kPipeStages), (unsigned)((step / kPipeStages) & 1));  // this step's bytes have landed
+            if (live) math(step, u, r, std::false_type{}, std::false_type{});
+        } else if (MODE != 0) {
+            const int c = step - stepsA;
+            mbar_wait(s_mbar + 3 + (c % kPipeStages), (unsigned)((c / kPipeStages) & 1));
+            if (live) math(step, u, r, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
+        }
     }
 }
 
@@ -620,6 +624,10 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
     }
     if (tid < cnt) s_eoff[s_idx[tid]] = (unsigned short)((incl - 1) | ((rincl - 1) << 8));
     __syncthreads();
+    if (tid < nr) {   // (the record was written by this CTA just above: visible after the barrier)
+        const int f0 = R[lay.offRunFirst + tid], f1 = tid + 1 < nr ? (int)R[lay.offRunFirst + tid + 1] : nu;
+        R[lay.offRunLen + f0] = (unsigned char)(f1 - f0);
+    }
     // per-target rows
     const bool shortRow = rowMax <= 3;
     const unsigned allShort = __ballot_sync(0xffffffffu, tid >= ntile || shortRow);
