@@ -425,7 +425,7 @@ template <typename KERN, typename TACC>
 static void launch_pipe_k(mprg_ctx *ctx, KERN kern, const PipeArgs<TACC> &pa, const UnitPack &up, size_t smemBytes,
                           unsigned tiles) {
     MPRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa, up);   // `tiles` = strips: one CTA each
+    kern<<<tiles, kPipeThreads, smemBytes, ctx->stream>>>(pa, up);
     ctx->launches++;
 }
 
@@ -491,15 +491,13 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     pa.dstLev = dl.lev; pa.dstOff = dl.off;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
-    pa.nTiles = (int32_t)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
     pa.rotc = nullptr;
     if (rot) {  // checked by apply_device: rotation registered, destination on CENTER / CENTER_HALO rows
         using TR = typename RotMath<TOUT, TACC>::type;
         const int64_t off = 4 * ctx->target[r->dst_stagger].slabOffset();
         pa.rotc = sizeof(TR) == 4 ? (const void *)(ctx->rotc32.p + off) : (const void *)(ctx->rotc.p + off);
     }
-    const unsigned gridRows = (unsigned)((r->nDst + r->dstNi - 1) / r->dstNi);
-    const unsigned tiles = ((gridRows + kStripRows - 1) / kStripRows) * (unsigned)pa.tilesPerRow;   // strips
+    const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
     struct Launch { size_t g, u0, nu, smem; int mode, minb, nPlain; int32_t stageOff, stageBytes, holdOff; };
     std::vector<Launch> plan;
     for (size_t g = 0; g < groups.size(); ++g) {
@@ -518,7 +516,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
                                                               (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
             }
             stage = (stage + 15) & ~(size_t)15;
-            const size_t fixed = ((size_t)kPipeSmemHead + (size_t)kStripRows * lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
+            const size_t fixed = ((size_t)kPipeSmemHead + lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
             const size_t hold = (mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
             const size_t smemBytes = fixed + kPipeStages * stage + hold;
             if (smemBytes + 1024 > (size_t)227 * 1024) return false;

@@ -38,7 +38,6 @@ constexpr int kPipeTile = 32;
 constexpr int kPipeCap = 256;      // CSR entries per tile accepted (== threads: one entry per thread in the prologue)
 constexpr int kPipeLev = 64;       // levels per unit
 constexpr int kPipeMaxUnits = 64;  // units (field x 64-level chunk) per launch; the host splits longer stacks
-constexpr int kStripRows = 4;       // vertically adjacent tiles swept together by one CTA
 constexpr int kPipeStages = 2;     // resident CTAs beat pipeline depth (profiles/r01: 2 x 5 CTAs > 3 x 4 > 4 x 3)
 constexpr int kRunPad = 40;        // unaligned units: slack per run so that 16-byte-aligned windows never overlap
 // launch content the kernel is compiled for
@@ -113,7 +112,6 @@ struct PipeArgs {
     int64_t dstLev, dstOff;
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
-    int32_t nTiles;     // tiles of the route (tilesPerRow x grid rows); one CTA per strip of kStripRows rows
     int32_t nunits;
     int32_t nPlain;     // the first nPlain units are plain aligned fields (phase A of the kernel)
     int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the record and the unit descriptors)
@@ -141,7 +139,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned smemDst, const void *gmem, uns
                  "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-// dynamic shared memory: [mbarriers 64 B][2 tile records][unit descriptors][stages][hold buffer (kModeRot)]
+// dynamic shared memory: [mbarriers 64 B][tile record][unit descriptors][stages][hold buffer (kModeRot)]
 constexpr int kPipeSmemHead = 64;
 // bytes of one stage that a unit needs for a tile of nu columns in nruns runs.  Aligned units: slots packed at the
 // column size so that a run is contiguous in shared memory too -- unless that size is a multiple of 128 bytes (every
@@ -229,74 +227,81 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     using TR = typename RotMath<TOUT, TACC>::type;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    // [0..1] phase A stages, [2] the strip's tile records, [3..4] phase B stages
-    unsigned long long *s_mbar = (unsigned long long *)smem;
-    unsigned char *s_rec0 = smem + kPipeSmemHead;                   // the strip's tile records (RecLayout), one per row
-    UnitDev *s_units = (UnitDev *)(s_rec0 + kStripRows * a.lay.stride);
+    unsigned long long *s_mbar = (unsigned long long *)smem;        // [0..1] phase A stages, [2] the tile record, [3..4] phase B stages
+    unsigned char *s_rec = smem + kPipeSmemHead;                    // the tile record (RecLayout)
+    UnitDev *s_units = (UnitDev *)(s_rec + a.lay.stride);
     unsigned char *s_stage = smem + a.stageOff;
+    const int32_t *s_uniq = (const int32_t *)(s_rec + a.lay.offUniq);
+    const unsigned char *s_urun = s_rec + a.lay.offUrun;
+    const unsigned char *s_runFirst = s_rec + a.lay.offRunFirst;
+    const unsigned short *s_rowoff = (const unsigned short *)(s_rec + a.lay.offRowoff);   // (generic routes only)
+    const unsigned short *s_off = (const unsigned short *)(s_rec + a.lay.offEoff);
+    const TACC *s_w = (const TACC *)(s_rec + a.lay.offEw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // A CTA owns a STRIP: the tiles of kStripRows consecutive grid rows above one another, and sweeps it unit-major
-    // (unit 0 of every row, unit 1 of every row, ...).  Vertically adjacent tiles share about half of their source
-    // columns, so the second fetch of a column follows the first within a unit time (an L2 hit whatever the other CTAs
-    // do), and the strip pays the record fetch and the pipeline fill once for kStripRows tiles.
-    const int tcol = (int)blockIdx.x % a.tilesPerRow;
-    const int row0g = ((int)blockIdx.x / a.tilesPerRow) * kStripRows;
-    const int nrowsGrid = a.nTiles / a.tilesPerRow;
-    const int Rn = min(kStripRows, nrowsGrid - row0g);   // rows of this strip
+    const int row = blockIdx.x / a.tilesPerRow;
+    const int i0 = (blockIdx.x - row * a.tilesPerRow) * kPipeTile;
+    const int64_t t0 = (int64_t)row * a.ni + i0;
 
-    // ---- prologue: one bulk copy per tile record (schedule, per-target rows, weights), all in flight together ----
+    // ---- prologue: ONE bulk copy brings the tile's record (schedule, per-target rows, weights) ---------------
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kPipeStages; ++i) {
-            mbar_init(s_mbar + i, 1);                    // phase A: one arrival per step
-            mbar_init(s_mbar + 3 + i, kPipeWarps);       // phase B: one arrival per warp per step
+            mbar_init(s_mbar + i, 1);                    // phase A: one arrival per unit
+            mbar_init(s_mbar + 3 + i, kPipeWarps);       // phase B: one arrival per warp per unit
         }
         mbar_init(s_mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        mbar_arrive_tx(s_mbar + 2, (unsigned)(Rn * a.lay.stride));
-        for (int r = 0; r < Rn; ++r)
-            bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec0 + r * a.lay.stride),
-                     a.rec + (size_t)((row0g + r) * a.tilesPerRow + tcol) * a.lay.stride, (unsigned)a.lay.stride, s_mbar + 2);
+        mbar_arrive_tx(s_mbar + 2, (unsigned)a.lay.stride);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec), a.rec + (size_t)blockIdx.x * a.lay.stride, (unsigned)a.lay.stride, s_mbar + 2);
     }
     for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
         ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
     __syncthreads();             // barriers initialised, unit descriptors in place
+    mbar_wait(s_mbar + 2, 0);    // the record has landed
+    const int nu = ((const unsigned short *)s_rec)[0];
+    const int ntile = ((const unsigned short *)s_rec)[3];
+    const unsigned rflags = ((const unsigned *)s_rec)[2];
+    const bool live = lane < ntile;
+    const bool fast = (rflags & kRecFast) != 0;   // every row of the tile has <= 3 entries
+    // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
+    const bool all3 = (rflags & kRecAll3) != 0;
+    // this lane's row (3 weights, slots, runs, length): re-read every unit with one or two 16-byte shared loads
+    // instead of living in 6-8 registers across the copy issue and the barrier
+    const unsigned row0 = (unsigned)__cvta_generic_to_shared(s_rec + 16 + lane * 8 * (int)sizeof(TACC));
 
     const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
     const unsigned hold0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.holdOff;
-    const int nA = a.nPlain, nB = a.nunits - a.nPlain;
 
-    // ---- copy-issue state: the tile whose units are being FETCHED (one unit ahead of the math, so it moves on to
-    //      the next tile while the last unit of the current one is reduced) ---------------------------------------
     // slot s = lane * warps + warp is copied by that lane, so the (warp-serialised) bulk-copy issue is spread
     // evenly over all warps instead of queuing behind the first two.  The list is in ascending id order and columns
     // of consecutive ids are contiguous in memory, so the owner of the first slot of a run fetches the whole run
     // with one bulk copy (brun = its length in columns, 0 for the other slots of the run).
+    // (column id and run length are re-read from the record at every issue -- two shared loads -- rather than held in
+    // registers across the whole sweep)
     const int bslot = lane * kPipeWarps + warp;
-    int inu = 0, bcol = -1, brun = 0, brunIdx = 0;
-    auto issue_state = [&](int r) {
-        const unsigned char *rec = s_rec0 + r * a.lay.stride;
-        inu = ((const unsigned short *)rec)[0];
-        const bool have = bslot < inu;
-        bcol = have ? ((const int32_t *)(rec + a.lay.offUniq))[bslot] : -1;
-        brun = have ? (int)rec[a.lay.offRunLen + bslot] : 0;           // run length at the first slot of a run, else 0
-        if (UNAL) brunIdx = have ? (int)rec[a.lay.offUrun + bslot] : 0;
-    };
+    const unsigned char *s_runLen = s_rec + a.lay.offRunLen;
 
-    // step = u * Rn + r (unit-major over the strip's rows): stage and barrier parity run along the steps
-    auto issue = [&](int step, int u) {
+    // Two phases in one launch.  Phase A: the first a.nPlain units are plain aligned fields -- the bulk of every
+    // pass -- and run the leanest code (one barrier arrival per unit, 16-byte loads only).  Phase B: wind pairs and
+    // unaligned columns (per-warp arrivals, in-place element loads, rotation).  One launch pays the tile prologue
+    // once; the lean loop is not slowed by the code and registers the general one needs.
+    const int nA = a.nPlain;
+    auto issue = [&](int u) {
+        if (u >= a.nunits) return;
         const UnitDev &ud = s_units[u];
         const unsigned chunkB = (unsigned)ud.Ln * ESZ;
-        const unsigned sbase = stage0 + (step % kPipeStages) * a.stageBytes;
+        const unsigned sbase = stage0 + (u % kPipeStages) * a.stageBytes;
         const bool merged = (ud.flags & kUnitMerged) != 0;
+        const int bcol = bslot < nu ? s_uniq[bslot] : -1;
+        const int brun = bslot < nu ? (int)s_runLen[bslot] : 0;   // run length at the first slot of a run, else 0
         // exact column chunks (aligned units).  Whole-column units whose column size is not a multiple of 128 bytes
         // pack their slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
         const bool packed = merged && (chunkB & 127u);
         if (u < nA) {
-            unsigned long long *bar = s_mbar + (step % kPipeStages);
+            unsigned long long *bar = s_mbar + (u % kPipeStages);
             const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
-            if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)inu);   // one arrival posts the unit's bytes
+            if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)nu);   // one arrival posts the unit's bytes
             if (packed) {
                 if (brun > 0) bulk_g2s(sbase + bslot * chunkB, g, chunkB * (unsigned)brun, bar);
             } else if (bcol >= 0) {
@@ -306,7 +311,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
         if (MODE == 0) return;
         // phase B: the barrier counts one arrival per warp (lane 0 posts the bytes of the warp's copies)
-        unsigned long long *bar = s_mbar + 3 + ((step - nA * Rn) % kPipeStages);
+        unsigned long long *bar = s_mbar + 3 + ((u - nA) % kPipeStages);
         unsigned nb = 0, sdst = 0;
         uintptr_t ga = 0;
         if (!UNAL || (ud.flags & kUnitAligned)) {
@@ -320,7 +325,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             // a 16-byte-aligned address chosen so that windows never overlap, and the math reads it where it lies.
             // (absolute addresses: the source base itself need only be element-aligned; device allocations are
             // 256-byte aligned, so the window's first 16-byte chunk always lies inside the caller's allocation)
-            const int ncol = merged ? brun : 1, r = merged ? brunIdx : bslot;
+            const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
             const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
             const uintptr_t aend = (uintptr_t)ud.src + ud.srcBytes;
             ga = a0 & ~(uintptr_t)15;
@@ -342,43 +347,13 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         if (nb) bulk_g2s(sdst, (const void *)ga, nb, bar);
     };
 
-    // ---- math state: the tile being REDUCED ---------------------------------------------------------------------
-    const unsigned char *s_rec = s_rec0;
-    const int32_t *s_uniq = nullptr;
-    const unsigned char *s_runFirst = nullptr;
-    const unsigned short *s_rowoff = nullptr, *s_off = nullptr;
-    const TACC *s_w = nullptr;
-    int64_t t0 = 0;
-    bool live = false, fast = true, all3 = false;
-    unsigned row0 = 0;
-    auto math_state = [&](int r) {
-        const int t = (row0g + r) * a.tilesPerRow + tcol;
-        s_rec = s_rec0 + r * a.lay.stride;
-        s_uniq = (const int32_t *)(s_rec + a.lay.offUniq);
-        s_runFirst = s_rec + a.lay.offRunFirst;
-        s_rowoff = (const unsigned short *)(s_rec + a.lay.offRowoff);   // (generic routes only)
-        s_off = (const unsigned short *)(s_rec + a.lay.offEoff);
-        s_w = (const TACC *)(s_rec + a.lay.offEw);
-        const int row = t / a.tilesPerRow;
-        t0 = (int64_t)row * a.ni + (int64_t)(t - row * a.tilesPerRow) * kPipeTile;
-        const int ntile = ((const unsigned short *)s_rec)[3];
-        const unsigned rflags = ((const unsigned *)s_rec)[2];
-        live = lane < ntile;
-        fast = (rflags & kRecFast) != 0;   // every row of the tile has <= 3 entries
-        // whole tile made of 3-entry rows (bilinear, fully mapped, full tile): no per-entry predicates at all
-        all3 = (rflags & kRecAll3) != 0;
-        // this lane's row (3 weights, slots, runs, length): re-read every unit with one or two 16-byte shared loads
-        // instead of living in 6-8 registers across the copy issue and the barrier
-        row0 = (unsigned)__cvta_generic_to_shared(s_rec + 16 + lane * 8 * (int)sizeof(TACC));
-    };
-
     const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
 
     // the reduction of one unit; UN / RT: compile-time content of the phase the unit belongs to
-    auto math = [&](int step, int u, int /*r*/, auto UN_c, auto RT_c) {
+    auto math = [&](int u, auto UN_c, auto RT_c) {
         constexpr bool UN = decltype(UN_c)::value, RT = decltype(RT_c)::value;
         const UnitDev &ud = s_units[u];
-        const unsigned st = stage0 + (step % kPipeStages) * a.stageBytes;  // shared-window address of this step's staging
+        const unsigned st = stage0 + (u % kPipeStages) * a.stageBytes;  // shared-window address of unit u's staging
         const int Ln = ud.Ln;
         const int eop = ud.flags & 0xff;
         const TACC earg = (TACC)ud.epi_arg;
@@ -504,43 +479,20 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
     };
 
-    // ---- the sweep: units x rows of the strip, copies one step ahead of the math --------------------------------
-    mbar_wait(s_mbar + 2, 0);    // the strip's records have landed
-    const int nsteps = a.nunits * Rn, stepsA = nA * Rn;
-    // step -> (unit, strip row): unit-major, except that the two units of a wind pair alternate row by row (zonal r,
-    // meridional r, zonal r + 1, ...) so that the zonal results wait in the hold buffer for one step only
-    auto step_of = [&](int st, int &uu, int &rr) {
-        uu = st / Rn;
-        rr = st - uu * Rn;
-        if (ROT && st >= stepsA) {
-            const int fl = s_units[uu].flags;
-            if (fl & (kUnitRotU | kUnitRotV)) {
-                const int uU = (fl & kUnitRotU) ? uu : uu - 1;
-                const int q = st - uU * Rn;
-                rr = q >> 1;
-                uu = uU + (q & 1);
-            }
-        }
-    };
-    issue_state(0);
-    issue(0, 0);
-    for (int step = 0; step < nsteps; ++step) {
-        if (step > 0) __syncthreads();   // every warp has finished reading the previous step: its buffer may be refilled
-        int u, r, un, rn;
-        step_of(step, u, r);
-        if (step + 1 < nsteps) {
-            step_of(step + 1, un, rn);
-            issue_state(rn);
-            issue(step + 1, un);
-        }
-        math_state(r);
-        if (step < stepsA) {
-            mbar_wait(s_mbar + (step % kPipeStages), (unsigned)((step / kPipeStages) & 1));  // this step's bytes have landed
-            if (live) math(step, u, r, std::false_type{}, std::false_type{});
-        } else if (MODE != 0) {
-            const int c = step - stepsA;
-            mbar_wait(s_mbar + 3 + (c % kPipeStages), (unsigned)((c / kPipeStages) & 1));
-            if (live) math(step, u, r, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
+    issue(0);
+    for (int u = 0; u < nA; ++u) {
+        if (u > 0) __syncthreads();     // every warp has finished reading unit u - 1: its buffer may be refilled
+        issue(u + 1);
+        mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
+        if (live) math(u, std::false_type{}, std::false_type{});
+    }
+    if (MODE != 0) {
+        for (int u = nA; u < a.nunits; ++u) {
+            if (u > 0) __syncthreads();
+            issue(u + 1);
+            const int k = u - nA;
+            mbar_wait(s_mbar + 3 + (k % kPipeStages), (unsigned)((k / kPipeStages) & 1));
+            if (live) math(u, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
         }
     }
 }

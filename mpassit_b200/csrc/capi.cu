@@ -86,8 +86,6 @@ static bool set_option(mprg_ctx *c, const char *key, const char *val) {
         t.pipeSplit = v.empty() || atoi(v.c_str()) != 0;
     } else if (k == "pipe_minb") {
         t.pipeMinb = atoi(v.c_str());
-    } else if (k == "stagger_ns") {
-        t.staggerNs = atoi(v.c_str());
     } else if (k == "cols_minb") {
         t.colsMinb = v.empty() ? 3 : atoi(v.c_str());
     } else if (k == "upload_threads") {

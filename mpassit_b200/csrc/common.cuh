@@ -177,7 +177,6 @@ struct mprg_tuning {
     bool pipeOff = false;      // MPASSIT_GPU_APPLY=direct | option "apply": register-gather kernels only
     int pipeMinb = 0;          // MPASSIT_GPU_PIPE_MINB | option "pipe_minb": 4 / 5 resident CTAs per SM (0 = by shared memory)
     bool pipeSplit = false;    // MPASSIT_GPU_PIPE_SPLIT=0|1 | option "pipe_split": plain aligned units and the rest in separate launches
-    int staggerNs = 400;       // option "stagger_ns": start-up delay between the resident CTAs of an SM (persistent column kernel)
     int colsMinb = 3;          // MPASSIT_GPU_MINB | option "cols_minb": register cap of the fallback kernel
     int uploadThreads = 0;     // MPASSIT_UPLOAD_THREADS | option "upload_threads" (0 = 3/4 of the cores / ranks)
 };

@@ -67,9 +67,6 @@ def main():
     for var in args.variants.split(","):
         # accumulate : launch grouping [b4|b5]   e.g. f32:split  f32:one  f64:split  f32:splitb4  f32:direct
         acc, mode = var.split(":")
-        if "@" in mode:      # f32:one@600 -> stagger_ns = 600
-            mode, stg = mode.split("@")
-            rg.set_option("stagger_ns", stg)
         rg.set_option("accumulate", acc)
         mb = ""
         if len(mode) > 2 and mode[-2] == "b" and mode[-1].isdigit():
