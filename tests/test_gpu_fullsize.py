@@ -78,7 +78,7 @@ def test_c2_device_generated_target_keeps_the_matrix_structure(c2):
               (l.BILINEAR, l.SRC_GRID_CENTER, l.EDGE2)]
     res = compare_target_generation(wl, routes)
     print("c2", res)
-    assert res["ulp_lon"] <= 8 and res["ulp_lat"] <= 8 and res["structure_diffs"] == 0, res
+    assert res["ulp_lon"] <= 8 and res["ulp_lat"] <= 8 and res["structure_diffs"] <= 1e-5 * res["rows"], res
 
 
 def test_bilinear_weights_partition_of_unity_and_constant_field(c2):
