@@ -73,21 +73,19 @@ constexpr int kUnitMerged = 0x800;                   // the chunk is the whole c
 //                   run0 | run1 << 8 | run2 << 16   (rows of <= 3 entries; longer rows: len only)
 //   uniq     int32 [nuCap]   distinct source columns of the tile, ascending
 //   urun     uint8 [nuCap]   run (maximal sequence of consecutive ids) each of them belongs to
-//   runLen   uint8 [nuCap]   at the first slot of a run: its length in columns; 0 elsewhere
 //   runFirst uint8 [runCap]  first slot of every run
 //   (routes with rows of more than 3 entries only -- conservative:)
 //   rowoff   uint16 [34]     entry offset of every target's row
 //   eoff     uint16 [entCap] per entry: slot | run << 8
 //   ew       weight [entCap] per entry
 struct RecLayout {
-    int32_t stride, offUniq, offUrun, offRunLen, offRunFirst, offRowoff, offEoff, offEw;
+    int32_t stride, offUniq, offUrun, offRunFirst, offRowoff, offEoff, offEw;
 };
 __host__ __device__ inline RecLayout rec_layout(int wsize, int nuMax, int runsMax, int entMax, bool generic) {
     RecLayout L;
     int o = 16 + kPipeTile * 8 * wsize;
     L.offUniq = o; o += ((nuMax + 3) & ~3) * 4;
     L.offUrun = o; o += (nuMax + 15) & ~15;
-    L.offRunLen = o; o += (nuMax + 15) & ~15;
     L.offRunFirst = o; o += (runsMax + 15) & ~15;
     L.offRowoff = L.offEoff = L.offEw = 0;
     if (generic) {
@@ -277,10 +275,13 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     // evenly over all warps instead of queuing behind the first two.  The list is in ascending id order and columns
     // of consecutive ids are contiguous in memory, so the owner of the first slot of a run fetches the whole run
     // with one bulk copy (brun = its length in columns, 0 for the other slots of the run).
-    // (column id and run length are re-read from the record at every issue -- two shared loads -- rather than held in
-    // registers across the whole sweep)
     const int bslot = lane * kPipeWarps + warp;
-    const unsigned char *s_runLen = s_rec + a.lay.offRunLen;
+    const int bcol = bslot < nu ? s_uniq[bslot] : -1;
+    int brun = 0;
+    if (bcol >= 0 && (bslot == 0 || s_urun[bslot] != s_urun[bslot - 1])) {
+        brun = 1;
+        while (bslot + brun < nu && s_urun[bslot + brun] == s_urun[bslot]) ++brun;
+    }
 
     // Two phases in one launch.  Phase A: the first a.nPlain units are plain aligned fields -- the bulk of every
     // pass -- and run the leanest code (one barrier arrival per unit, 16-byte loads only).  Phase B: wind pairs and
@@ -293,8 +294,6 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         const unsigned chunkB = (unsigned)ud.Ln * ESZ;
         const unsigned sbase = stage0 + (u % kPipeStages) * a.stageBytes;
         const bool merged = (ud.flags & kUnitMerged) != 0;
-        const int bcol = bslot < nu ? s_uniq[bslot] : -1;
-        const int brun = bslot < nu ? (int)s_runLen[bslot] : 0;   // run length at the first slot of a run, else 0
         // exact column chunks (aligned units).  Whole-column units whose column size is not a multiple of 128 bytes
         // pack their slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
         const bool packed = merged && (chunkB & 127u);
@@ -576,10 +575,6 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
     }
     if (tid < cnt) s_eoff[s_idx[tid]] = (unsigned short)((incl - 1) | ((rincl - 1) << 8));
     __syncthreads();
-    if (tid < nr) {   // (the record was written by this CTA just above: visible after the barrier)
-        const int f0 = R[lay.offRunFirst + tid], f1 = tid + 1 < nr ? (int)R[lay.offRunFirst + tid + 1] : nu;
-        R[lay.offRunLen + f0] = (unsigned char)(f1 - f0);
-    }
     // per-target rows
     const bool shortRow = rowMax <= 3;
     const unsigned allShort = __ballot_sync(0xffffffffu, tid >= ntile || shortRow);
