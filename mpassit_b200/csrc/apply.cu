@@ -339,12 +339,12 @@ k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
         c[k] = h ? __ldg(a.col + b + k) : 0;   // absent entries: weight 0 on a valid address (index 0)
         w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
     }
+    if (e - b > kLongRow) return;  // pole rows of a periodic source grid: k_apply_planes_long
     const FieldDev fd = fp.f[blockIdx.y];
     const TIN *__restrict__ src = (const TIN *)fd.src;
     TOUT *__restrict__ dst = (TOUT *)fd.dst;
-    const bool shortrow = e - b <= kFlatRow;
     int lev = 0;
-    if (shortrow && e > b) {
+    if (e > b) {
         // rows of <= 4 entries (the stagger matrices): kPlaneBatch levels x 4 gathers in flight per thread
         for (; lev + kPlaneBatch <= fd.nlev; lev += kPlaneBatch) {
             TIN x[kPlaneBatch][kFlatRow];
@@ -370,9 +370,31 @@ k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
 #pragma unroll
         for (int k = 0; k < kFlatRow; ++k)
             if (b + k < e) acc += w[k] * (TACC)__ldg(pl + c[k]);
-        for (int k = b + kFlatRow; k < e; ++k) acc += __ldg(a.w + k) * (TACC)__ldg(pl + __ldg(a.col + k));
         st_stream(dst + (size_t)lev * a.dstLev + a.dstOff + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
     }
+}
+
+// Long rows of a grid-source route (a pole-row point of a periodic grid averages the whole end row: ni + 2 entries,
+// consecutive source columns).  One warp per (row, level): lanes stride over the entries (coalesced), fp64 partial
+// sums, fixed shuffle tree -- deterministic, and spread over the whole GPU instead of 2 x ni threads.
+template <typename TIN, typename TOUT, typename TACC>
+__global__ void __launch_bounds__(256)
+k_apply_planes_long(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, const int32_t *__restrict__ longRows,
+                    int64_t nLong) {
+    const FieldDev fd = fp.f[blockIdx.y];
+    const int64_t id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (id >= nLong * fd.nlev) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t t = __ldg(longRows + id / fd.nlev);
+    const int lev = (int)(id % fd.nlev);
+    const int b = __ldg(a.rowptr + t), e = __ldg(a.rowptr + t + 1);
+    const TIN *__restrict__ pl = (const TIN *)fd.src + (size_t)lev * a.srcPlane;
+    double acc = 0.0;
+    for (int k = b + lane; k < e; k += 32) acc += (double)__ldg(a.w + k) * (double)__ldg(pl + __ldg(a.col + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0)
+        st_stream((TOUT *)fd.dst + (size_t)lev * a.dstLev + a.dstOff + t, (TOUT)epilogue((TACC)acc, fd.epi_op, fd.epi_arg));
 }
 
 // ---------------------------------------------------------------------------
@@ -675,6 +697,13 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         packs(planes, [&](const FieldPack &fp, size_t n) {
             dim3 g((unsigned)((r->nDst + 255) / 256), (unsigned)n);
             k_apply_planes<TIN, TOUT, TACC><<<g, 256, 0, ctx->stream>>>(a, fp);
+            if (r->nLong > 0) {
+                int maxLev = 0;
+                for (size_t i = 0; i < n; ++i) maxLev = std::max(maxLev, (int)fp.f[i].nlev);
+                dim3 gl((unsigned)((r->nLong * maxLev + 7) / 8), (unsigned)n);
+                k_apply_planes_long<TIN, TOUT, TACC><<<gl, 256, 0, ctx->stream>>>(a, fp, r->longRows.p, r->nLong);
+                ctx->launches++;
+            }
         });
     }
     MPRG_CUDA(cudaGetLastError());

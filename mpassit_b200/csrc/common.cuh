@@ -139,6 +139,8 @@ struct Target {
 }  // namespace mprg
 
 // Route handle: CSR weights of this rank's destination slab.
+namespace mprg { constexpr int kLongRow = 4; }
+
 struct mprg_route {
     int method = 0, src_loc = 0, dst_stagger = 0;
     int64_t nDst = 0, nnz = 0, nUnmapped = 0, nSrc = 0;
@@ -163,6 +165,10 @@ struct mprg_route {
     // source is a structured grid (MPRG_SRC_GRID_CENTER): level-slowest source layout
     bool srcLevelSlowest = false;
     int64_t srcPlane = 0;      // points per source level plane
+    // rows of a grid-source route longer than kLongRow entries (the pole rows of a periodic grid: ni + 2 entries):
+    // applied by one warp per (row, level) instead of one thread per row
+    mprg::DevBuf<int32_t> longRows;
+    int64_t nLong = 0;
 };
 
 struct mprg_graph {

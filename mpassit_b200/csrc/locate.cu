@@ -181,6 +181,15 @@ __global__ void k_w32(int64_t nnz, const double *__restrict__ w, float *__restri
     if (i < nnz) w32[i] = (float)w[i];
 }
 
+// rows longer than kLongRow: counted (out == nullptr) or listed
+__global__ void k_long_rows(int64_t nDst, const int32_t *__restrict__ rowptr, int32_t *__restrict__ out,
+                            unsigned long long *count) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDst || rowptr[t + 1] - rowptr[t] <= kLongRow) return;
+    const unsigned long long i = atomicAdd(count, 1ULL);
+    if (out) out[i] = (int32_t)t;
+}
+
 void route_finish(mprg_ctx *ctx, mprg_route *r) {
     DevBuf<unsigned long long> un(1);
     DevBuf<int32_t> mm(2);
@@ -221,6 +230,18 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
     if (!r->srcLevelSlowest) route_tile_stats(ctx, r);
     r->maxRow = hmm[0];
     r->uniform = (r->nnz > 0 && hmm[0] == hmm[1]);
+    r->nLong = 0;
+    if (r->srcLevelSlowest && r->maxRow > kLongRow) {
+        const unsigned g = (unsigned)((r->nDst + 255) / 256);
+        MPRG_CUDA(cudaMemsetAsync(un.p, 0, sizeof(unsigned long long), ctx->stream));
+        k_long_rows<<<g, 256, 0, ctx->stream>>>(r->nDst, r->rowptr.p, nullptr, un.p);
+        peek(ctx, &hun, un.p, sizeof hun);
+        r->longRows.alloc(hun);
+        MPRG_CUDA(cudaMemsetAsync(un.p, 0, sizeof(unsigned long long), ctx->stream));
+        k_long_rows<<<g, 256, 0, ctx->stream>>>(r->nDst, r->rowptr.p, r->longRows.p, un.p);
+        ctx->launches += 2;
+        r->nLong = (int64_t)hun;
+    }
 }
 
 }  // namespace mprg

@@ -41,9 +41,11 @@ def main(path):
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| {n} | {c} | {t:.3f} | {100 * t / tot:.1f} % |")
     if len(pipes) >= 4:
-        # a step starts at its first k_apply_pipe launch minus the launches before it in the pass
-        per = pipes[-2] - pipes[-4]           # two pipe launches per step
-        first = pipes[-2] - (pipes[-2] - pipes[-3] > per // 2 and 0 or 0)
+        # the pass starts with the column launch of the bilinear apply (the one with the largest duration);
+        # its period = distance between the last two such launches
+        big = max(seq[i][1] for i in pipes)
+        heads = [i for i in pipes if seq[i][1] > 0.5 * big]
+        per = heads[-1] - heads[-2]
         start = len(seq) - per
         step = seq[start:]
         st = sum(ms for _, ms, _ in step)
