@@ -325,12 +325,17 @@ k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
 // ---------------------------------------------------------------------------
 constexpr int kPlaneBatch = 8;  // levels whose gathers are all issued before the first FMA (memory-level parallelism)
 
+}  // namespace mprg
+#include "apply_planes.cuh"
+namespace mprg {
+
 template <typename TIN, typename TOUT, typename TACC>
 __global__ void __launch_bounds__(256)
 k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nDst) return;
     const int b = __ldg(a.rowptr + t), e = __ldg(a.rowptr + t + 1);
+    if (e - b > kLongRow) return;  // pole rows of a periodic source grid: k_apply_planes_long
     int c[kFlatRow];
     TACC w[kFlatRow];
 #pragma unroll
@@ -339,39 +344,7 @@ k_apply_planes(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
         c[k] = h ? __ldg(a.col + b + k) : 0;   // absent entries: weight 0 on a valid address (index 0)
         w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
     }
-    if (e - b > kLongRow) return;  // pole rows of a periodic source grid: k_apply_planes_long
-    const FieldDev fd = fp.f[blockIdx.y];
-    const TIN *__restrict__ src = (const TIN *)fd.src;
-    TOUT *__restrict__ dst = (TOUT *)fd.dst;
-    int lev = 0;
-    if (e > b) {
-        // rows of <= 4 entries (the stagger matrices): kPlaneBatch levels x 4 gathers in flight per thread
-        for (; lev + kPlaneBatch <= fd.nlev; lev += kPlaneBatch) {
-            TIN x[kPlaneBatch][kFlatRow];
-#pragma unroll
-            for (int q = 0; q < kPlaneBatch; ++q) {
-                const TIN *pl = src + (size_t)(lev + q) * a.srcPlane;
-#pragma unroll
-                for (int k = 0; k < kFlatRow; ++k) x[q][k] = (b + k < e) ? __ldg(pl + c[k]) : (TIN)0;
-            }
-#pragma unroll
-            for (int q = 0; q < kPlaneBatch; ++q) {
-                TACC acc = 0;
-#pragma unroll
-                for (int k = 0; k < kFlatRow; ++k)
-                    if (b + k < e) acc += w[k] * (TACC)x[q][k];
-                st_stream(dst + (size_t)(lev + q) * a.dstLev + a.dstOff + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
-            }
-        }
-    }
-    for (; lev < fd.nlev; ++lev) {
-        const TIN *pl = src + (size_t)lev * a.srcPlane;
-        TACC acc = 0;
-#pragma unroll
-        for (int k = 0; k < kFlatRow; ++k)
-            if (b + k < e) acc += w[k] * (TACC)__ldg(pl + c[k]);
-        st_stream(dst + (size_t)lev * a.dstLev + a.dstOff + t, (TOUT)epilogue(acc, fd.epi_op, fd.epi_arg));
-    }
+    planes_direct<TIN, TOUT, TACC>(a, fp.f[blockIdx.y], t, e - b, c, w);
 }
 
 // Long rows of a grid-source route (a pole-row point of a periodic grid averages the whole end row: ni + 2 entries,
@@ -629,6 +602,32 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
     r->schedTiles = tiles; r->schedCols = (int64_t)ht[0]; r->schedRuns = (int64_t)ht[1];
 }
 
+// tile geometry of the TMA-staged planes kernel for a grid-source route
+static PlaneGeom plane_geom(const mprg_route *r) {
+    PlaneGeom pg;
+    pg.tilesPerRow = (r->dstNi + kPlTile - 1) / kPlTile;
+    pg.tw = (r->dstNi + pg.tilesPerRow - 1) / pg.tilesPerRow;
+    pg.dstNi = r->dstNi; pg.srcNi = r->srcNi;
+    pg.nWin = r->planeWin;
+    return pg;
+}
+
+// route_finish: how many source rows the tiles of a grid-source route reference (0: the route cannot be staged)
+void route_plane_stats(mprg_ctx *ctx, mprg_route *r) {
+    r->planeWin = 0;
+    if (!r->srcLevelSlowest || r->srcNi <= 0 || r->dstNi <= 0 || r->nDst <= 0 || r->nDst % r->dstNi != 0 || r->nnz <= 0) return;
+    PlaneGeom pg = plane_geom(r);
+    DevBuf<int32_t> st(2);
+    MPRG_CUDA(cudaMemsetAsync(st.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    const unsigned tiles = (unsigned)((r->nDst / r->dstNi) * pg.tilesPerRow);
+    k_plane_stats<<<tiles, kPlTile, 0, ctx->stream>>>(r->rowptr.p, r->col.p, pg, st.p);
+    ctx->launches++;
+    int32_t h[2] = {0, 0};
+    peek(ctx, h, st.p, sizeof h);
+    // staged when most tiles fit (the rest -- the seam tiles of a periodic grid -- take the gather path inside the kernel)
+    if (h[0] > 0 && (int64_t)h[1] * 4 <= (int64_t)tiles) r->planeWin = h[0];
+}
+
 // cols: every 3-D field of the apply (wind pairs adjacent, ROT_U then ROT_V); flat: 2-D fields and short columns;
 // planes: grid-source fields.  Returns false when wind pairs (fused rotation) are present but the pipelined
 // kernel could not take the route.
@@ -694,9 +693,34 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     }
     if (!planes.empty()) {
         ProfScope ps(ctx, 3, alg_bytes(r, ksum(planes), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(planes) * r->nDst);
+        // TMA-staged kernel when the slab is whole destination rows of a known source grid whose tiles' windows fit
+        // (route_finish: planeWin); "apply" = "direct" keeps the register-gather kernel
+        const bool staged = !ctx->tune.pipeOff && r->planeWin > 0 && ((size_t)r->srcPlane * sizeof(TIN)) % 16 == 0;   // windows keep their 16-byte phase from level to level
         packs(planes, [&](const FieldPack &fp, size_t n) {
-            dim3 g((unsigned)((r->nDst + 255) / 256), (unsigned)n);
-            k_apply_planes<TIN, TOUT, TACC><<<g, 256, 0, ctx->stream>>>(a, fp);
+            if (staged) {
+                PlaneGeom pg = plane_geom(r);
+                const unsigned tiles = (unsigned)((r->nDst / r->dstNi) * pg.tilesPerRow);
+                auto go = [&](auto lev_c, auto st_c) {
+                    constexpr int LEV = decltype(lev_c)::value, ST = decltype(st_c)::value;
+                    const unsigned smem = (unsigned)ST * pg.nWin * LEV * pl_win_bytes<TIN>();
+                    static unsigned attr = 0;
+                    if (smem > attr) {
+                        MPRG_CUDA(cudaFuncSetAttribute(k_apply_planes_pipe<TIN, TOUT, TACC, LEV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        attr = smem;
+                    }
+                    k_apply_planes_pipe<TIN, TOUT, TACC, LEV, ST><<<tiles, kPlThreads, smem, ctx->stream>>>(a, fp, pg);
+                };
+                using std::integral_constant;
+                switch (ctx->tune.planesShape) {
+                // measured on the 3-km case (profiles/r02/README.md): 4 levels x 4 stages 0.44 ms per pass, 4 x 6 0.55,
+                // 8 x 3 0.50, 8 x 4 0.53 -- deeper pipelines are slower, as for the column kernel
+                case 83: go(integral_constant<int, 8>{}, integral_constant<int, 3>{}); break;
+                default: go(integral_constant<int, 4>{}, integral_constant<int, 4>{}); break;
+                }
+            } else {
+                dim3 g((unsigned)((r->nDst + 255) / 256), (unsigned)n);
+                k_apply_planes<TIN, TOUT, TACC><<<g, 256, 0, ctx->stream>>>(a, fp);
+            }
             if (r->nLong > 0) {
                 int maxLev = 0;
                 for (size_t i = 0; i < n; ++i) maxLev = std::max(maxLev, (int)fp.f[i].nlev);

@@ -86,6 +86,8 @@ static bool set_option(mprg_ctx *c, const char *key, const char *val) {
         t.pipeSplit = v.empty() || atoi(v.c_str()) != 0;
     } else if (k == "pipe_minb") {
         t.pipeMinb = atoi(v.c_str());
+    } else if (k == "planes_shape") {
+        t.planesShape = atoi(v.c_str());
     } else if (k == "cols_minb") {
         t.colsMinb = v.empty() ? 3 : atoi(v.c_str());
     } else if (k == "upload_threads") {
@@ -136,7 +138,7 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
         // tuning knobs: the environment is read here, once; mprg_set_option changes them afterwards
         for (const char *const *kv = (const char *const[]){"MPASSIT_GPU_ACC", "accumulate", "MPASSIT_GPU_APPLY", "apply",
                                                            "MPASSIT_GPU_PIPE_MINB", "pipe_minb", "MPASSIT_GPU_PIPE_SPLIT", "pipe_split",
-                                                           "MPASSIT_GPU_MINB", "cols_minb", "MPASSIT_UPLOAD_THREADS",
+                                                           "MPASSIT_GPU_MINB", "cols_minb", "MPASSIT_GPU_PLANES", "planes_shape", "MPASSIT_UPLOAD_THREADS",
                                                            "upload_threads", nullptr};
              *kv; kv += 2)
             if (const char *e = getenv(kv[0])) set_option(c, kv[1], e);
@@ -331,6 +333,7 @@ int mprg_get_option(const mprg_ctx *ctx, const char *key, char *value, size_t le
     else if (k == "apply") v = t.pipeOff ? "direct" : "pipe";
     else if (k == "pipe_split") v = t.pipeSplit ? "1" : "0";
     else if (k == "pipe_minb") v = std::to_string(t.pipeMinb);
+    else if (k == "planes_shape") v = std::to_string(t.planesShape);
     else if (k == "cols_minb") v = std::to_string(t.colsMinb);
     else if (k == "upload_threads") v = std::to_string(t.uploadThreads);
     else return 59;
@@ -510,6 +513,7 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
         else store_bilinear_grid(ctx, r.get());
     }
     r->dstNi = ctx->target[dst_stagger].ni;
+    if (r->srcLevelSlowest) r->srcNi = ctx->target[MPRG_CENTER_HALO].ni;
     route_finish(ctx, r.get());
     if (!cached && !ctx->cacheDir.empty()) wcache_save(ctx, r.get(), ckey);
     MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));

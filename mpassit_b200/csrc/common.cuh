@@ -165,6 +165,8 @@ struct mprg_route {
     // source is a structured grid (MPRG_SRC_GRID_CENTER): level-slowest source layout
     bool srcLevelSlowest = false;
     int64_t srcPlane = 0;      // points per source level plane
+    int32_t srcNi = 0;         // row length of the source grid
+    int32_t planeWin = 0;      // source rows per 256-target tile (apply_planes.cuh); 0: register-gather kernel only
     // rows of a grid-source route longer than kLongRow entries (the pole rows of a periodic grid: ni + 2 entries):
     // applied by one warp per (row, level) instead of one thread per row
     mprg::DevBuf<int32_t> longRows;
@@ -183,6 +185,7 @@ struct mprg_tuning {
     bool pipeOff = false;      // MPASSIT_GPU_APPLY=direct | option "apply": register-gather kernels only
     int pipeMinb = 0;          // MPASSIT_GPU_PIPE_MINB | option "pipe_minb": 4 / 5 resident CTAs per SM (0 = by shared memory)
     bool pipeSplit = false;    // MPASSIT_GPU_PIPE_SPLIT=0|1 | option "pipe_split": plain aligned units and the rest in separate launches
+    int planesShape = 0;       // option "planes_shape": levels per stage * 10 + stages of the staged grid-source kernel (0 = default)
     int colsMinb = 3;          // MPASSIT_GPU_MINB | option "cols_minb": register cap of the fallback kernel
     int uploadThreads = 0;     // MPASSIT_UPLOAD_THREADS | option "upload_threads" (0 = 3/4 of the cores / ranks)
 };
@@ -296,6 +299,7 @@ void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r);
 void store_bilinear_node(mprg_ctx *ctx, mprg_route *r);
 void route_finish(mprg_ctx *ctx, mprg_route *r);  // stats + fp32 weight copy
 void route_tile_stats(mprg_ctx *ctx, mprg_route *r);  // apply.cu
+void route_plane_stats(mprg_ctx *ctx, mprg_route *r); // apply.cu
 
 // apply.cu
 struct ApplyField {

@@ -230,6 +230,7 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
     if (!r->srcLevelSlowest) route_tile_stats(ctx, r);
     r->maxRow = hmm[0];
     r->uniform = (r->nnz > 0 && hmm[0] == hmm[1]);
+    route_plane_stats(ctx, r);
     r->nLong = 0;
     if (r->srcLevelSlowest && r->maxRow > kLongRow) {
         const unsigned g = (unsigned)((r->nDst + 255) / 256);
