@@ -41,6 +41,7 @@ module mpassit_rg_mod
   public :: mprg_set_mesh, mprg_set_target, mprg_set_grid_kind, mprg_set_option, mprg_set_weight_cache, mprg_get_slab
   public :: mprg_store, mprg_release, mprg_clear_routes, mprg_route_info
   public :: mprg_apply, mprg_apply_ex, mprg_set_rotation, mprg_rotate_winds, mprg_rotate_winds_on
+  public :: mprg_store_wind, mprg_apply_wind
   public :: mprg_comm_id, mprg_comm_init, mprg_gather, mprg_gather_v
   public :: mprg_set_async, mprg_get_async, mprg_download, mprg_io_bytes
   public :: mprg_post_midlevels, mprg_post_ptop, mprg_route_schedule_info
@@ -234,6 +235,24 @@ module mpassit_rg_mod
        integer(c_int), value :: stagger
        integer(c_int32_t), value :: nlev
        integer(c_int), value :: dtype, mem
+     end function
+
+     !> the wind chain of interp_hist_data (interp.F90:256-328: regrid to mass points, rotate_winds_cgrid, regrid to
+     !! EDGE1 / EDGE2) composed into ONE matrix per staggered grid; rh = c_null_ptr with rc 0: not composable
+     !! (global / periodic grid, no rotation), keep the three steps
+     integer(c_int) function mprg_store_wind(ctx, dst_stagger, rh) bind(C, name="mprg_store_wind")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: dst_stagger
+       type(c_ptr), intent(out) :: rh
+     end function
+     !> dst = A u_src + B v_src: cell-centre winds (device, file order) -> this rank's slab of rotated U / V
+     integer(c_int) function mprg_apply_wind(ctx, rh, u_src, v_src, nlev, src_dtype, dst, dst_dtype, into_full) &
+         bind(C, name="mprg_apply_wind")
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: ctx, rh, u_src, v_src, dst
+       integer(c_int32_t), value :: nlev
+       integer(c_int), value :: src_dtype, dst_dtype, into_full
      end function
 
      !> NCCL bootstrap: rank 0 calls mprg_comm_id, the 128 bytes are MPI_Bcast'ed by the host

@@ -38,7 +38,9 @@ enum { MPRG_BILINEAR = 0, MPRG_CONSERVE = 1, MPRG_NEAREST_STOD = 2 };
 /* where the source field lives: ESMF_MESHLOC_ELEMENT (input_data.F90:970-1132),
  * ESMF_MESHLOC_NODE (vorticity bundle, interp.F90:353), or the target grid's
  * CENTER stagger (u/v_target_grid_nostag, interp.F90:298,316) */
-enum { MPRG_SRC_MESH_ELEMENT = 0, MPRG_SRC_MESH_NODE = 1, MPRG_SRC_GRID_CENTER = 2 };
+enum { MPRG_SRC_MESH_ELEMENT = 0, MPRG_SRC_MESH_NODE = 1, MPRG_SRC_GRID_CENTER = 2,
+       /* the (u, v) pair on mesh cells: source of a composed wind route (mprg_store_wind) */
+       MPRG_SRC_MESH_WIND = 3 };
 /* ESMF_STAGGERLOC_* of the destination, interp.F90:477-520, model_grid.F90:707-728 */
 enum { MPRG_CENTER = 0, MPRG_EDGE1 = 1, MPRG_EDGE2 = 2, MPRG_CORNER = 3,
        /* CENTER rows of this rank widened by one halo row on each side (clipped to the grid): the
@@ -85,6 +87,9 @@ int mprg_set_async(mprg_ctx *ctx, int on);
  *   "apply"       "pipe" (default) | "direct": register-gather kernels only                    [MPASSIT_GPU_APPLY]
  *   "pipe_minb"   0 (default: by shared memory) | 4 | 5 resident CTAs per SM               [MPASSIT_GPU_PIPE_MINB]
  *   "cols_minb"   2 | 3 (default) | 4: register cap of the register-gather kernel               [MPASSIT_GPU_MINB]
+ *   "wind"        "chain" (default) | "composed": with chain, mprg_store_wind always declines and hosts run the
+ *                 reference's three regrid / rotate steps one after the other; composed lets it build the
+ *                 one-matrix route (measured slower than the chain on a mesh as fine as the grid)   [MPASSIT_GPU_WIND]
  *   "upload_threads"  host threads of the unpinned-source bounce ring (0 = 3/4 of the cores) [MPASSIT_UPLOAD_THREADS] */
 int mprg_set_option(mprg_ctx *ctx, const char *key, const char *value);
 int mprg_get_option(const mprg_ctx *ctx, const char *key, char *value, size_t len);
@@ -196,6 +201,8 @@ int mprg_route_info(const mprg_route *rh, int64_t *nDst, int64_t *nnz, int64_t *
 /* test / weight-cache hooks: CSR of this rank's slab, 0-based, host buffers
  * rowptr[nDst+1], col[nnz], w[nnz] */
 int mprg_route_export_csr(mprg_ctx *ctx, const mprg_route *rh, int32_t *rowptr, int32_t *col, double *w);
+/* composed wind routes (mprg_store_wind): the entries' second weights (meridional source), w2[nnz] */
+int mprg_route_export_w2(mprg_ctx *ctx, const mprg_route *rh, double *w2);
 int mprg_route_import_csr(mprg_ctx *ctx, int64_t nSrc, int64_t nDst, const int32_t *rowptr,
                           const int32_t *col, const double *w, mprg_route **rh);
 
@@ -248,6 +255,25 @@ int mprg_has_rotation(const mprg_ctx *ctx); /* 1 once mprg_set_rotation succeede
 int mprg_rotate_winds(mprg_ctx *ctx, void *u, void *v, int32_t nlev, int dtype, int mem);
 /* same on the rows of `stagger` = MPRG_CENTER or MPRG_CENTER_HALO (u, v: [nlev][rows][ni]) */
 int mprg_rotate_winds_on(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype, int mem);
+
+/* ---- the wind chain as ONE matrix per staggered grid.  interp_hist_data regrids the cell-centre
+ *      winds to the mass points (interp.F90:256-289), rotates them there (rotate_winds_cgrid, :291-293) and regrids
+ *      the rotated mass-point fields to the EDGE1 / EDGE2 points (:295-328).  All three steps are linear in (u, v), so
+ *          U = S_U R_u W (u, v)      V = S_V R_v W (u, v)
+ *      is one sparse matrix per staggered grid whose entries carry two weights (one for the zonal, one for the
+ *      meridional source column).  mprg_store_wind composes it from the memoised bilinear (mesh -> CENTER_HALO) and
+ *      stagger (CENTER -> EDGE) routes and the angles of mprg_set_rotation; mprg_apply_wind applies it to the pair of
+ *      cell-centre sources (device buffers, file order [nCells][nlev], 16-byte aligned columns) and writes this rank's
+ *      slab of the staggered field [nlev][nj_slab][ni] (into_full != 0: its rows of the full field, as
+ *      mprg_apply_into).  The mass-point fields UMASS / VMASS are never materialised: one write and one read of two
+ *      3-D fields and the grid-source launches disappear from the pass.  Results differ from the three-step chain by
+ *      rounding only (the chain rounds the mass-point values to the output type).
+ *      *rh == NULL with rc 0 means "not composable here" -- a periodic / global target grid, no rotation registered,
+ *      a destination point that draws on more than 12 mesh cells, or option "wind" = "chain" -- and the caller keeps
+ *      the chain.  Released with mprg_release; mprg_set_rotation drops the memoised composed routes. */
+int mprg_store_wind(mprg_ctx *ctx, int dst_stagger /* MPRG_EDGE1 | MPRG_EDGE2 */, mprg_route **rh);
+int mprg_apply_wind(mprg_ctx *ctx, mprg_route *rh, const void *u_src, const void *v_src, int32_t nlev, int src_dtype,
+                    void *dst, int dst_dtype, int into_full);
 
 /* ---- file byte order.  NetCDF classic / CDF-5 data is big-endian; the reference lets the NetCDF library
  *      swap on the host inside nf90_get_var / nf90_put_var (input_data.F90:186,205,437..., write_data.F90:1010...).

@@ -28,6 +28,7 @@ UNITS = [
     ("locate.cu", ["-fmad=false"], []),
     ("conserve.cu", ["-fmad=false"], ["MPRG_HAVE_CONSERVE"]),
     ("stagger.cu", ["-fmad=false"], ["MPRG_HAVE_STAGGER", "MPRG_HAVE_NODE"]),
+    ("compose.cu", ["-fmad=false"], []),
     ("apply.cu", [], []),
     ("wcache.cu", [], []),
     ("target_gen.cu", ["-fmad=false"], []),

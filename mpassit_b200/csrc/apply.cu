@@ -248,8 +248,10 @@ constexpr int kFlatRow = 4;  // row entries held in registers; longer rows strea
 
 constexpr int kShortLev = 8;  // fields with at most this many levels (2-D fields, soil) take the flat kernel
 
+// (latency-bound: 6 resident CTAs per SM instead of the 4 that 64 registers allowed -- ncu: 72-77 % of the stall samples
+// were long-scoreboard at 46 % occupancy)
 template <typename TIN, typename TOUT, typename TACC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(TACC) == 4 ? 6 : 4)
 k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nDst) return;
@@ -512,8 +514,10 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             }
             stage = (stage + 15) & ~(size_t)15;
             const size_t fixed = ((size_t)kPipeSmemHead + lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
+            using TRot = typename RotMath<TOUT, TACC>::type;
             const size_t hold = (mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0;
-            const size_t smemBytes = fixed + kPipeStages * stage + hold;
+            const size_t rotc = (mode & kModeRot) ? (size_t)kPipeTile * 4 * sizeof(TRot) : 0;   // the tile's rotation constants
+            const size_t smemBytes = fixed + kPipeStages * stage + hold + rotc;
             if (smemBytes + 1024 > (size_t)227 * 1024) return false;
             // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
             int minb = (smemBytes + 1024) * 5 <= (size_t)228 * 1024 ? 5 : 4;
@@ -529,6 +533,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         pa.nunits = (int)l.nu;
         pa.nPlain = l.nPlain;
         pa.stageOff = l.stageOff; pa.stageBytes = l.stageBytes; pa.holdOff = l.holdOff;
+        pa.rotOff = (int32_t)(l.holdOff + ((l.mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0));
         const size_t smemBytes = l.smem;
         const int minb = l.minb;
 #define MPRG_PIPE_LAUNCH(M)                                                                                        \
@@ -549,18 +554,22 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
 void scan_counts(mprg_ctx *ctx, const int32_t *cnt, int32_t *rowptr, int64_t nPlus1);  // locate.cu
 
 static RecLayout route_rec_layout(const mprg_route *r, int wsize) {
-    return rec_layout(wsize, r->tileUniqMax, r->tileRunsMax, r->tileEntriesMax, r->tileRowMax > 3);
+    return rec_layout(wsize, r->tileUniqMax, r->tileRunsMax, r->tileEntriesMax, r->tileRowMax > 3, r->composite);
 }
 
 template <typename TW>
-static void route_build_records(mprg_ctx *ctx, mprg_route *r, const TW *w, DevBuf<unsigned char> &out) {
+static void route_build_records(mprg_ctx *ctx, mprg_route *r, const TW *w, const TW *w2, DevBuf<unsigned char> &out) {
     const int tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * tilesPerRow);
     const RecLayout lay = route_rec_layout(r, (int)sizeof(TW));
     out.alloc((size_t)tiles * lay.stride);
     MPRG_CUDA(cudaMemsetAsync(out.p, 0, (size_t)tiles * lay.stride, ctx->stream));
-    k_tile_schedule<true, TW><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, w, r->nDst, r->dstNi, tilesPerRow,
-                                                                       nullptr, nullptr, out.p, lay);
+    if (r->composite)
+        k_tile_schedule<true, TW, 2 * kPipeCap><<<tiles, 2 * kPipeCap, 0, ctx->stream>>>(r->rowptr.p, r->col.p, w, w2, r->nDst, r->dstNi,
+                                                                                         tilesPerRow, nullptr, nullptr, out.p, lay);
+    else
+        k_tile_schedule<true, TW, kPipeCap><<<tiles, kPipeCap, 0, ctx->stream>>>(r->rowptr.p, r->col.p, w, w2, r->nDst, r->dstNi, tilesPerRow,
+                                                                                 nullptr, nullptr, out.p, lay);
     ctx->launches++;
     MPRG_CUDA(cudaGetLastError());
 }
@@ -569,7 +578,7 @@ static void route_build_records(mprg_ctx *ctx, mprg_route *r, const TW *w, DevBu
 static const unsigned char *route_rec64(mprg_ctx *ctx, mprg_route *r) {
     if (!r->rec64.p) {
         if (ctx->capturing) fail(46, "mprg_apply: this route's fp64 schedule is not built yet; run the pass once before mprg_capture_begin");
-        route_build_records<double>(ctx, r, r->w.p, r->rec64);
+        route_build_records<double>(ctx, r, r->w.p, r->composite ? r->w2.p : nullptr, r->rec64);
     }
     return r->rec64.p;
 }
@@ -585,8 +594,12 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
     DevBuf<unsigned long long> tot(2);
     MPRG_CUDA(cudaMemsetAsync(mm.p, 0, 4 * sizeof(int32_t), ctx->stream));
     MPRG_CUDA(cudaMemsetAsync(tot.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    k_tile_schedule<false, float><<<tiles, kPipeThreads, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->w32.p, r->nDst, r->dstNi,
-                                                                          tilesPerRow, mm.p, tot.p, nullptr, RecLayout{});
+    if (r->composite)
+        k_tile_schedule<false, float, 2 * kPipeCap><<<tiles, 2 * kPipeCap, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->w32.p, nullptr, r->nDst,
+                                                                                             r->dstNi, tilesPerRow, mm.p, tot.p, nullptr, RecLayout{});
+    else
+        k_tile_schedule<false, float, kPipeCap><<<tiles, kPipeCap, 0, ctx->stream>>>(r->rowptr.p, r->col.p, r->w32.p, nullptr, r->nDst, r->dstNi,
+                                                                                     tilesPerRow, mm.p, tot.p, nullptr, RecLayout{});
     ctx->launches++;
     int32_t h[4] = {0, 0, 0, 0};
     unsigned long long ht[2] = {0, 0};
@@ -596,8 +609,8 @@ void route_tile_stats(mprg_ctx *ctx, mprg_route *r) {
     r->tileUniqMax = h[1];
     r->tileRunsMax = h[2];
     r->tileRowMax = h[3];
-    if (h[0] > kPipeCap) return;  // no schedule: register-gather kernels only
-    route_build_records<float>(ctx, r, r->w32.p, r->rec32);
+    if (h[0] > (r->composite ? 2 * kPipeCap : kPipeCap) || h[1] > 255 || h[2] > 255) return;  // no schedule: register-gather kernels only
+    route_build_records<float>(ctx, r, r->w32.p, r->composite ? r->w2_32.p : nullptr, r->rec32);
     r->rec64 = DevBuf<unsigned char>();
     r->schedTiles = tiles; r->schedCols = (int64_t)ht[0]; r->schedRuns = (int64_t)ht[1];
 }
@@ -609,6 +622,7 @@ static PlaneGeom plane_geom(const mprg_route *r) {
     pg.tw = (r->dstNi + pg.tilesPerRow - 1) / pg.tilesPerRow;
     pg.dstNi = r->dstNi; pg.srcNi = r->srcNi;
     pg.nWin = r->planeWin;
+    pg.tiles = r->planeTiles.p;
     return pg;
 }
 
@@ -620,7 +634,8 @@ void route_plane_stats(mprg_ctx *ctx, mprg_route *r) {
     DevBuf<int32_t> st(2);
     MPRG_CUDA(cudaMemsetAsync(st.p, 0, 2 * sizeof(int32_t), ctx->stream));
     const unsigned tiles = (unsigned)((r->nDst / r->dstNi) * pg.tilesPerRow);
-    k_plane_stats<<<tiles, kPlTile, 0, ctx->stream>>>(r->rowptr.p, r->col.p, pg, st.p);
+    r->planeTiles.alloc((size_t)tiles * 8);
+    k_plane_stats<<<tiles, kPlTile, 0, ctx->stream>>>(r->rowptr.p, r->col.p, pg, st.p, r->planeTiles.p);
     ctx->launches++;
     int32_t h[2] = {0, 0};
     peek(ctx, h, st.p, sizeof h);
@@ -736,6 +751,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
 
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
                   int dst_dtype, bool into_full) {
+    if (r->composite) fail(47, "mprg_apply: a composed wind route takes mprg_apply_wind");
     // destination layout: this rank's slab buffer, or (into_full) its rows inside a full-grid field
     DstLayout dl{r->nDst, 0};
     if (into_full) {
@@ -815,6 +831,85 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
         for (size_t p = 0; p < pairs.size(); ++p)
             if (all_late || pair_nlev[p] <= kShortLev)
                 rotate_device(ctx, r->dst_stagger, pairs[p].first, pairs[p].second, pair_nlev[p], dst_dtype);
+}
+
+// ---------------------------------------------------------------------------
+// composed wind route (compose.cu): dst = A u_src + B v_src in one launch of the column kernel
+// ---------------------------------------------------------------------------
+template <typename TIN, typename TOUT, typename TACC>
+static void launch_wind(mprg_ctx *ctx, const mprg_route *r, const void *u, const void *v, int32_t nlev, void *dst, DstLayout dl) {
+    if (r->tileEntriesMax <= 0 || r->tileEntriesMax > 2 * kPipeCap || !r->rec32.p)
+        fail(47, "mprg_apply_wind: the composed route has no tile schedule");
+    if (((size_t)nlev * sizeof(TIN)) % 16 || (uintptr_t)u % 16 || (uintptr_t)v % 16)
+        fail(48, "mprg_apply_wind: source columns must be 16-byte aligned (level count x element size a multiple of 16)");
+    const RecLayout lay = route_rec_layout(r, (int)sizeof(TACC));
+    const unsigned char *rec = sizeof(TACC) == 8 ? route_rec64(ctx, const_cast<mprg_route *>(r)) : r->rec32.p;
+    UnitPack up;
+    int nu = 0;
+    size_t stage = 0;
+    for (int L0 = 0; L0 < nlev; L0 += kPipeLev) {
+        for (int s = 0; s < 2; ++s) {
+            if (nu >= kPipeMaxUnits) fail(49, "mprg_apply_wind: too many levels");
+            UnitDev &d = up.u[nu++];
+            d.src = s ? v : u; d.dst = dst; d.srcBytes = (size_t)r->nSrc * nlev * sizeof(TIN);
+            d.nlev = nlev; d.L0 = L0; d.Ln = std::min(kPipeLev, nlev - L0);
+            const bool aligned = ((size_t)L0 * sizeof(TIN)) % 16 == 0 && ((size_t)d.Ln * sizeof(TIN)) % 16 == 0;
+            if (!aligned) fail(48, "mprg_apply_wind: level chunk not 16-byte aligned");
+            d.flags = kUnitAligned | (d.Ln == nlev ? kUnitMerged : 0) | (s ? kUnitCmpB : kUnitCmpA);
+            d.epi_arg = 0.0;
+            stage = std::max(stage, pipe_unit_stage_bytes(true, (d.flags & kUnitMerged) != 0, (unsigned)(d.Ln * sizeof(TIN)),
+                                                          r->tileUniqMax, r->tileRunsMax));
+        }
+    }
+    stage = (stage + 15) & ~(size_t)15;
+    PipeArgs<TACC> pa;
+    pa.rec = rec; pa.lay = lay; pa.nDst = r->nDst;
+    pa.dstLev = dl.lev; pa.dstOff = dl.off;
+    pa.ni = r->dstNi;
+    pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
+    pa.rotc = nullptr;
+    pa.nunits = nu; pa.nPlain = 0; pa.rotOff = 0;
+    const size_t fixed = ((size_t)kPipeSmemHead + lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
+    const size_t hold = (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TACC);
+    const size_t smemBytes = fixed + kPipeStages * stage + hold;
+    if (smemBytes + 1024 > (size_t)227 * 1024) fail(47, "mprg_apply_wind: tile too large for shared memory");
+    pa.stageOff = (int32_t)fixed; pa.stageBytes = (int32_t)stage; pa.holdOff = (int32_t)(fixed + kPipeStages * stage);
+    const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
+    const int minb = (smemBytes + 1024) * 5 <= (size_t)228 * 1024 ? 5 : 4;
+    const double K = nlev;
+    ProfScope ps(ctx, 4,
+                 2.0 * K * (double)r->nSrcRef * sizeof(TIN) + K * (double)r->nDst * sizeof(TOUT) +
+                     (double)r->nnz * (4.0 + 2.0 * sizeof(TACC)) + ((double)r->nDst + 1.0) * 4.0,
+                 K * (double)r->nDst);
+    if (minb >= 5) launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, kModeCmp, 5>, pa, up, smemBytes, tiles);
+    else launch_pipe_k(ctx, k_apply_pipe<TIN, TOUT, TACC, kModeCmp, 4>, pa, up, smemBytes, tiles);
+    MPRG_CUDA(cudaGetLastError());
+}
+
+void apply_wind_device(mprg_ctx *ctx, const mprg_route *r, const void *u, const void *v, int32_t nlev, int src_dtype,
+                       void *dst, int dst_dtype, bool into_full) {
+    if (!r->composite) fail(47, "mprg_apply_wind: not a composed wind route (mprg_store_wind)");
+    if (nlev <= 0) fail(31, "mprg_apply_wind: nlev %d", nlev);
+    if (!u || !v || !dst) fail(32, "mprg_apply_wind: null buffer");
+    if (r->nDst == 0) return;
+    DstLayout dl{r->nDst, 0};
+    if (into_full) {
+        const Target &tg = ctx->target[r->dst_stagger];
+        dl.lev = (int64_t)tg.ni * tg.nj;
+        dl.off = tg.slabOffset();
+    }
+    if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F32) {
+        if (acc_fp32_requested(ctx)) launch_wind<float, float, float>(ctx, r, u, v, nlev, dst, dl);
+        else launch_wind<float, float, double>(ctx, r, u, v, nlev, dst, dl);
+    } else if (src_dtype == MPRG_F32 && dst_dtype == MPRG_F64) {
+        launch_wind<float, double, double>(ctx, r, u, v, nlev, dst, dl);
+    } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F32) {
+        launch_wind<double, float, double>(ctx, r, u, v, nlev, dst, dl);
+    } else if (src_dtype == MPRG_F64 && dst_dtype == MPRG_F64) {
+        launch_wind<double, double, double>(ctx, r, u, v, nlev, dst, dl);
+    } else {
+        fail(33, "mprg_apply_wind: bad dtype %d/%d", src_dtype, dst_dtype);
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -43,6 +43,7 @@ constexpr int kRunPad = 40;        // unaligned units: slack per run so that 16-
 // launch content the kernel is compiled for
 constexpr int kModeUnal = 1;       // some unit's column chunks are not 16-byte aligned
 constexpr int kModeRot = 2;        // some units are wind pairs (fused rotation)
+constexpr int kModeCmp = 4;        // composed wind route: every two units are the (zonal, meridional) sources of one output
 
 struct UnitDev {
     const void *src;
@@ -61,6 +62,9 @@ struct UnitPack {
 constexpr int kUnitAligned = 0x100;                  // column chunks start 16-byte aligned and are a multiple of 16 bytes long
 constexpr int kUnitRotU = 0x200, kUnitRotV = 0x400;  // wind pair: this unit is the zonal / meridional chunk
 constexpr int kUnitMerged = 0x800;                   // the chunk is the whole column: runs of consecutive ids are contiguous in memory
+// composed wind route: A = the zonal source (partial sums parked in shared memory), B = the meridional source (adds its
+// terms with the entries' second weights and stores)
+constexpr int kUnitCmpA = 0x1000, kUnitCmpB = 0x2000;
 
 // Tile record: everything the kernel needs to know about one tile, precomputed when the route is built
 // (k_tile_schedule) and laid out so that ONE bulk copy brings it into shared memory -- the prologue of a tile is a
@@ -73,20 +77,25 @@ constexpr int kUnitMerged = 0x800;                   // the chunk is the whole c
 //                   run0 | run1 << 8 | run2 << 16   (rows of <= 3 entries; longer rows: len only)
 //   uniq     int32 [nuCap]   distinct source columns of the tile, ascending
 //   urun     uint8 [nuCap]   run (maximal sequence of consecutive ids) each of them belongs to
-//   runFirst uint8 [runCap]  first slot of every run
+//   runFirst uint8 [runCap + 1]  first slot of every run; runFirst[nruns] = nu (low byte), so a run's length is a difference
 //   (routes with rows of more than 3 entries only -- conservative:)
 //   rowoff   uint16 [34]     entry offset of every target's row
 //   eoff     uint16 [entCap] per entry: slot | run << 8
 //   ew       weight [entCap] per entry
+// Composed wind routes (compose.cu) replace the rows section by 32 x cmpStride bytes: per target
+//   a[12] b[12] (weight type) | uint32 slots 0-3 | slots 4-7 | slots 8-11 | uint32 len
 struct RecLayout {
     int32_t stride, offUniq, offUrun, offRunFirst, offRowoff, offEoff, offEw;
+    int32_t cmpStride;   // bytes of one composed row; 0: ordinary route
 };
-__host__ __device__ inline RecLayout rec_layout(int wsize, int nuMax, int runsMax, int entMax, bool generic) {
+__host__ __device__ inline RecLayout rec_layout(int wsize, int nuMax, int runsMax, int entMax, bool generic, bool composite = false) {
     RecLayout L;
-    int o = 16 + kPipeTile * 8 * wsize;
+    L.cmpStride = composite ? 2 * kCmpRow * wsize + 16 : 0;
+    int o = 16 + kPipeTile * (composite ? L.cmpStride : 8 * wsize);
+    if (composite) generic = false;
     L.offUniq = o; o += ((nuMax + 3) & ~3) * 4;
     L.offUrun = o; o += (nuMax + 15) & ~15;
-    L.offRunFirst = o; o += (runsMax + 15) & ~15;
+    L.offRunFirst = o; o += (runsMax + 1 + 15) & ~15;   // + the sentinel runFirst[nruns] = nu
     L.offRowoff = L.offEoff = L.offEw = 0;
     if (generic) {
         L.offRowoff = o; o += 80;
@@ -115,6 +124,7 @@ struct PipeArgs {
     int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the record and the unit descriptors)
     int32_t stageBytes; // bytes of one stage (host: the largest unit's need at the route's tile maxima)
     int32_t holdOff;    // byte offset of the wind-pair hold buffer (kModeRot launches)
+    int32_t rotOff;     // byte offset of the tile's rotation constants (kModeRot launches): fetched with the record
     // kModeRot launches only: per-point rotation constants of this rank's destination rows, in the arithmetic type
     // of the rotation (RotMath): [nDst][4] = sina, tana, 1/cosa, 1/(cosa + sina tana)
     const void *rotc;
@@ -219,7 +229,7 @@ __device__ __forceinline__ void lds4(unsigned saddr, T (&v)[4]) {
 template <typename TIN, typename TOUT, typename TACC, int MODE, int MINB>
 __global__ void __launch_bounds__(kPipeThreads, MINB)
 k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
-    constexpr bool UNAL = (MODE & kModeUnal) != 0, ROT = (MODE & kModeRot) != 0;
+    constexpr bool UNAL = (MODE & kModeUnal) != 0, ROT = (MODE & kModeRot) != 0, CMP = (MODE & kModeCmp) != 0;
     constexpr int ESZ = (int)sizeof(TIN);
     constexpr int GB = 4 * ESZ;                           // bytes of one 4-level group in a staged column
     using TR = typename RotMath<TOUT, TACC>::type;
@@ -250,8 +260,13 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
         mbar_init(s_mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        mbar_arrive_tx(s_mbar + 2, (unsigned)a.lay.stride);
+        // kModeRot: the tile's rotation constants ride the same barrier (one latency, instead of a global load in the
+        // middle of every meridional unit: 0.13 ms of a 0.6-ms pair launch, profiles/r02)
+        unsigned rotB = 0;
+        if (ROT) rotB = (unsigned)min((int64_t)min(kPipeTile, a.ni - i0), a.nDst - t0) * 4u * (unsigned)sizeof(TR);
+        mbar_arrive_tx(s_mbar + 2, (unsigned)a.lay.stride + rotB);
         bulk_g2s((unsigned)__cvta_generic_to_shared(s_rec), a.rec + (size_t)blockIdx.x * a.lay.stride, (unsigned)a.lay.stride, s_mbar + 2);
+        if (ROT && rotB) bulk_g2s((unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.rotOff, (const TR *)a.rotc + 4 * t0, rotB, s_mbar + 2);
     }
     for (int i = tid; i < a.nunits * (int)(sizeof(UnitDev) / 4); i += kPipeThreads)
         ((int32_t *)s_units)[i] = ((const int32_t *)&up)[i];
@@ -266,10 +281,11 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     const bool all3 = (rflags & kRecAll3) != 0;
     // this lane's row (3 weights, slots, runs, length): re-read every unit with one or two 16-byte shared loads
     // instead of living in 6-8 registers across the copy issue and the barrier
-    const unsigned row0 = (unsigned)__cvta_generic_to_shared(s_rec + 16 + lane * 8 * (int)sizeof(TACC));
+    const unsigned row0 = (unsigned)__cvta_generic_to_shared(s_rec + 16 + lane * (CMP ? a.lay.cmpStride : 8 * (int)sizeof(TACC)));
 
     const unsigned stage0 = (unsigned)__cvta_generic_to_shared(s_stage);
     const unsigned hold0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.holdOff;
+    const unsigned rot0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)a.rotOff;
 
     // slot s = lane * warps + warp is copied by that lane, so the (warp-serialised) bulk-copy issue is spread
     // evenly over all warps instead of queuing behind the first two.  The list is in ascending id order and columns
@@ -278,9 +294,9 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     const int bslot = lane * kPipeWarps + warp;
     const int bcol = bslot < nu ? s_uniq[bslot] : -1;
     int brun = 0;
-    if (bcol >= 0 && (bslot == 0 || s_urun[bslot] != s_urun[bslot - 1])) {
-        brun = 1;
-        while (bslot + brun < nu && s_urun[bslot + brun] == s_urun[bslot]) ++brun;
+    if (bcol >= 0) {
+        const int r = s_urun[bslot];
+        if ((int)s_runFirst[r] == bslot) brun = (((int)s_runFirst[r + 1] - bslot - 1) & 0xff) + 1;   // (1..256: the sentinel is nu mod 256)
     }
 
     // Two phases in one launch.  Phase A: the first a.nPlain units are plain aligned fields -- the bulk of every
@@ -357,6 +373,43 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         const int eop = ud.flags & 0xff;
         const TACC earg = (TACC)ud.epi_arg;
         const int ngroups = (Ln + 3) >> 2;
+        if constexpr (CMP) {
+            // composed wind route: this lane's <= 8 entries; the A unit (zonal source) parks its partial sums, the B unit
+            // (meridional source, the entries' second weights) starts from them and stores
+            const bool isB = (ud.flags & kUnitCmpB) != 0;
+            const unsigned wrow = row0 + (isB ? (unsigned)(kCmpRow * sizeof(TACC)) : 0u);
+            TACC cw0[4], cw1[4], cw2[4];
+            lds4<TACC>(wrow, cw0);
+            lds4<TACC>(wrow + 4 * (unsigned)sizeof(TACC), cw1);
+            lds4<TACC>(wrow + 8 * (unsigned)sizeof(TACC), cw2);
+            unsigned sl[4];   // slots 0-3, 4-7, 8-11, len
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(sl[0]), "=r"(sl[1]), "=r"(sl[2]), "=r"(sl[3])
+                         : "r"(row0 + (unsigned)(2 * kCmpRow * sizeof(TACC))));
+            const int clen = (int)sl[3];
+            const unsigned cstride = ((ud.flags & kUnitMerged) && (((unsigned)Ln * ESZ) & 127u)) ? (unsigned)Ln * ESZ : (unsigned)Ln * ESZ + 16u;
+            TOUT *d = (TOUT *)ud.dst + ((size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane);
+#pragma unroll
+            for (int gi = 0; gi < kPipeLev / 4 / kPipeWarps; ++gi, d += grp8) {
+                const int g = warp + gi * kPipeWarps;
+                if (g >= ngroups) break;
+                const unsigned hp = hold0 + (unsigned)((gi * kPipeThreads + tid) * 4 * (int)sizeof(TACC));
+                TACC acc[4] = {0, 0, 0, 0};
+                if (isB) lds4<TACC>(hp, acc);
+                const unsigned lp = st + g * GB;
+#pragma unroll
+                for (int j = 0; j < kCmpRow; ++j)   // absent entries never touch staging
+                    if (j < clen) fma4<TIN, TACC>(acc, j < 4 ? cw0[j & 3] : (j < 8 ? cw1[j & 3] : cw2[j & 3]), lp + ((sl[j >> 2] >> (8 * (j & 3))) & 0xffu) * cstride);
+                if (!isB) { sts4<TACC>(hp, acc); continue; }
+                if (eop != MPRG_EPI_NONE) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[k] = pipe_epi(acc[k], eop, earg);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (4 * g + k < Ln) __stcs(d + (size_t)k * a.dstLev, (TOUT)acc[k]);
+            }
+            return;
+        }
         // this lane's row (weights, slots, runs): one or two 16-byte shared loads per unit
         TACC rw[3];
         unsigned pk, pr = 0;
@@ -438,14 +491,8 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                 // the two divisors are per-point constants, applied as reciprocals (same in k_rotate)
                 TOUT h[4];
                 lds4<TOUT>(hold0 + (unsigned)((gi * kPipeThreads + tid) * 4 * (int)sizeof(TOUT)), h);
-                TR c[4];   // sina, tana, 1/cosa, 1/(cosa + sina tana) of this lane's target
-                if (sizeof(TR) == 4) {
-                    const float4 q = __ldg((const float4 *)a.rotc + (t0 + lane));
-                    c[0] = (TR)q.x; c[1] = (TR)q.y; c[2] = (TR)q.z; c[3] = (TR)q.w;
-                } else {
-                    const double2 q0 = __ldg((const double2 *)a.rotc + 2 * (t0 + lane)), q1 = __ldg((const double2 *)a.rotc + 2 * (t0 + lane) + 1);
-                    c[0] = (TR)q0.x; c[1] = (TR)q0.y; c[2] = (TR)q1.x; c[3] = (TR)q1.y;
-                }
+                TR c[4];   // sina, tana, 1/cosa, 1/(cosa + sina tana) of this lane's target (staged with the record)
+                lds4<TR>(rot0 + (unsigned)(lane * 4 * (int)sizeof(TR)), c);
                 TOUT *du = (TOUT *)s_units[u - 1].dst + dcol + (size_t)gi * grp8;   // where the held zonal values go
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -502,15 +549,17 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
 // columns of consecutively numbered cells neighbours in the list; they are also neighbours in memory (file order),
 // so the apply kernel fetches each such run with ONE bulk copy.
 // FILL == false: per-tile maxima (entries, distinct columns, runs, longest row) and totals;  FILL == true: the records.
-template <bool FILL, typename TW>
-__global__ void __launch_bounds__(kPipeThreads)
-k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const TW *__restrict__ w, int64_t nDst,
+template <bool FILL, typename TW, int CAP>
+__global__ void __launch_bounds__(CAP)
+k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const TW *__restrict__ w,
+                const TW *__restrict__ w2 /* composed routes: the entries' second weights */, int64_t nDst,
                 int32_t ni, int32_t tilesPerRow, int32_t *maxima /* entries, uniq, runs, row */,
                 unsigned long long *totals /* columns, runs */, unsigned char *__restrict__ rec, RecLayout lay) {
-    __shared__ int32_t s_col[kPipeCap];   // sort keys (column ids; INT_MAX padding)
-    __shared__ int32_t s_idx[kPipeCap];   // entry index within the tile that the key came from
-    __shared__ int32_t s_cnt[kPipeWarps], s_rcnt[kPipeWarps];
-    __shared__ unsigned short s_eoff[kPipeCap];   // per entry (original order): slot | run << 8
+    // CAP = threads = CSR entries a tile may hold: kPipeCap for ordinary routes, 2 kPipeCap for composed wind routes
+    __shared__ int32_t s_col[CAP];   // sort keys (column ids; INT_MAX padding)
+    __shared__ int32_t s_idx[CAP];   // entry index within the tile that the key came from
+    __shared__ int32_t s_cnt[CAP / 32], s_rcnt[CAP / 32];
+    __shared__ unsigned short s_eoff[CAP];   // per entry (original order): slot | run << 8
     __shared__ int32_t s_rp[kPipeTile + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = blockIdx.x / tilesPerRow;
@@ -522,15 +571,15 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
     if (t0 < nDst) { base = rowptr[t0]; cnt = rowptr[t1] - base; }
     if (tid <= kPipeTile) s_rp[tid] = (t0 < nDst ? rowptr[min(t0 + min(tid, ntile), nDst)] : 0) - base;
     if (!FILL && tid == 0) atomicMax(maxima, cnt);
-    if (cnt > kPipeCap) {  // tile too fat for the pipelined kernel: the route falls back to register gathers
+    if (cnt > CAP) {  // tile too fat for the pipelined kernel: the route falls back to register gathers
         if (!FILL && tid == 0) atomicMax(maxima + 1, cnt);
         return;
     }
     s_col[tid] = tid < cnt ? col[base + tid] : 0x7fffffff;
     s_idx[tid] = tid;
     __syncthreads();
-    // bitonic sort of the kPipeCap (key, index) pairs
-    for (int k = 2; k <= kPipeCap; k <<= 1)
+    // bitonic sort of the CAP (key, index) pairs
+    for (int k = 2; k <= CAP; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             const int p = tid ^ j;
             if (p > tid) {
@@ -552,7 +601,7 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
     int incl = __popc(bal & ((2u << lane) - 1u)), nu = 0;   // unique keys up to and including this position
     int rincl = __popc(rb & ((2u << lane) - 1u)), nr = 0;   // run starts up to and including this position
 #pragma unroll
-    for (int wq = 0; wq < kPipeWarps; ++wq) {
+    for (int wq = 0; wq < CAP / 32; ++wq) {
         const int v = s_cnt[wq], rv = s_rcnt[wq];
         if (wq < warp) { incl += v; rincl += rv; }
         nu += v; nr += rv;
@@ -573,13 +622,29 @@ k_tile_schedule(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
         R[lay.offUrun + incl - 1] = (unsigned char)(rincl - 1);
         if (runStart) R[lay.offRunFirst + rincl - 1] = (unsigned char)(incl - 1);
     }
+    if (tid == 0) R[lay.offRunFirst + nr] = (unsigned char)nu;   // sentinel
     if (tid < cnt) s_eoff[s_idx[tid]] = (unsigned short)((incl - 1) | ((rincl - 1) << 8));
     __syncthreads();
     // per-target rows
     const bool shortRow = rowMax <= 3;
     const unsigned allShort = __ballot_sync(0xffffffffu, tid >= ntile || shortRow);
     const unsigned allThree = __ballot_sync(0xffffffffu, tid < ntile && rowMax == 3);
-    if (tid < kPipeTile) {
+    if (lay.cmpStride) {
+        if (tid < kPipeTile) {   // composed wind route: <= kCmpRow entries, two weights each
+            TW *wa = (TW *)(R + 16 + tid * lay.cmpStride), *wb = wa + kCmpRow;
+            unsigned *sl = (unsigned *)(wb + kCmpRow);
+            const int len = tid < ntile ? min(rowMax, kCmpRow) : 0;
+            unsigned s[3] = {0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < kCmpRow; ++j) {
+                const bool h = j < len;
+                wa[j] = h ? w[base + s_rp[tid] + j] : (TW)0;
+                wb[j] = h ? w2[base + s_rp[tid] + j] : (TW)0;
+                s[j >> 2] |= (h ? (unsigned)(s_eoff[s_rp[tid] + j] & 0xffu) : 0u) << (8 * (j & 3));
+            }
+            sl[0] = s[0]; sl[1] = s[1]; sl[2] = s[2]; sl[3] = (unsigned)len;
+        }
+    } else if (tid < kPipeTile) {
         TW *rw = (TW *)(R + 16 + tid * 8 * (int)sizeof(TW));
         unsigned pk = (unsigned)min(rowMax, 255) << 24, pr = 0;
 #pragma unroll

@@ -62,12 +62,17 @@ struct PlaneGeom {
     int32_t tilesPerRow, tw;   // tiles per destination row, targets per tile
     int32_t dstNi, srcNi;
     int32_t nWin;              // source rows per tile the stages have room for (tiles needing more take the gather path)
+    // per-tile headers written by k_plane_stats when the route is built: first source row, window extents per source
+    // row and whether the windows fit -- [tile][8] = y0, xmin[3], xmax[3], fits.  The producer warp starts streaming
+    // one memory latency after the CTA starts instead of after the consumers' three dependent CSR loads.
+    const int32_t *tiles;
 };
 
 // Route statistics for the launch: the largest number of source rows any tile references whose windows fit
 // (out[0]), and how many tiles do not fit at all (out[1]).
 __global__ void __launch_bounds__(kPlTile)
-k_plane_stats(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, PlaneGeom g, int32_t *__restrict__ out) {
+k_plane_stats(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, PlaneGeom g, int32_t *__restrict__ out,
+              int32_t *__restrict__ tiles) {
     __shared__ int s_y0, s_xmin[kPlWin + 1], s_xmax[kPlWin + 1], s_bad;
     const int tid = threadIdx.x;
     const int j = blockIdx.x / g.tilesPerRow, tx = blockIdx.x - j * g.tilesPerRow;
@@ -90,15 +95,21 @@ k_plane_stats(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
         else { atomicMin(&s_xmin[q], x); atomicMax(&s_xmax[q], x); }
     }
     __syncthreads();
-    if (tid == 0 && y0 != 0x7fffffff) {
-        bool bad = s_bad != 0;
+    if (tid == 0) {
+        bool bad = s_bad != 0 || y0 == 0x7fffffff;
         int nw = 0;
         for (int q = 0; q < kPlWin; ++q) {
             if (s_xmax[q] >= 0) nw = q + 1;
             if (s_xmax[q] - s_xmin[q] + 1 > kPlTile + 4) bad = true;
         }
-        if (bad) atomicAdd(out + 1, 1);
-        else atomicMax(out, nw);
+        if (y0 != 0x7fffffff) {
+            if (bad) atomicAdd(out + 1, 1);
+            else atomicMax(out, nw);
+        }
+        int32_t *h = tiles + 8 * (size_t)blockIdx.x;
+        h[0] = y0;
+        for (int q = 0; q < kPlWin; ++q) { h[1 + q] = s_xmin[q]; h[4 + q] = s_xmax[q]; }
+        h[7] = bad ? 0 : 1;     // (a tile with nothing mapped does not "fit": it only writes zeros)
     }
 }
 
@@ -114,7 +125,6 @@ __global__ void __launch_bounds__(kPlThreads, sizeof(TIN) == 4 ? 4 : 2)
 k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, PlaneGeom g) {
     extern __shared__ __align__(128) unsigned char pl_smem[];
     __shared__ unsigned long long s_full[kPlStages], s_empty[kPlStages];
-    __shared__ int s_y0, s_xmin[kPlWin], s_xmax[kPlWin], s_bad;
     constexpr unsigned ESZ = sizeof(TIN), WCB = pl_win_bytes<TIN>();
     const unsigned STB = (unsigned)g.nWin * kPlLev * WCB;
 
@@ -125,76 +135,36 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
     const int64_t t = (int64_t)j * g.dstNi + i0 + tid;
     const bool live = tid < cnt;      // (producer lanes: tid >= kPlTile >= cnt)
 
-    int ne = 0, b = 0;
-    if (live) {
-        b = __ldg(a.rowptr + t);
-        ne = __ldg(a.rowptr + t + 1) - b;
-    }
-    const bool store = live && ne <= kLongRow;   // longer rows: k_apply_planes_long
-    if (!store) ne = 0;
-    int c[kFlatRow];
-    TACC w[kFlatRow];
-#pragma unroll
-    for (int k = 0; k < kFlatRow; ++k) {
-        const bool h = k < ne;
-        c[k] = h ? __ldg(a.col + b + k) : 0;
-        w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
-    }
+    // the tile's header (k_plane_stats): every thread reads the same 32 bytes
+    const int4 h0 = __ldg((const int4 *)(g.tiles + 8 * (size_t)blockIdx.x)), h1 = __ldg((const int4 *)(g.tiles + 8 * (size_t)blockIdx.x) + 1);
     if (tid == 0) {
-        s_y0 = 0x7fffffff; s_bad = 0;
-#pragma unroll
-        for (int q = 0; q < kPlWin; ++q) { s_xmin[q] = 0x7fffffff; s_xmax[q] = -1; }
 #pragma unroll
         for (int q = 0; q < kPlStages; ++q) { mbar_init(s_full + q, 1); mbar_init(s_empty + q, kPlTile / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    // source row / column of every entry; the tile's first source row
-    int yk[kFlatRow], xk[kFlatRow];
-    int ymin = 0x7fffffff;
-#pragma unroll
-    for (int k = 0; k < kFlatRow; ++k) {
-        yk[k] = c[k] / g.srcNi;
-        xk[k] = c[k] - yk[k] * g.srcNi;
-        if (k < ne) ymin = min(ymin, yk[k]);
-    }
-    ymin = __reduce_min_sync(0xffffffffu, ymin);
     __syncthreads();
-    if (lane == 0 && ymin != 0x7fffffff) atomicMin(&s_y0, ymin);
-    __syncthreads();
-    const int y0 = s_y0;
-    {
-        int lo[kPlWin], hi[kPlWin], bad = 0;
-#pragma unroll
-        for (int q = 0; q < kPlWin; ++q) { lo[q] = 0x7fffffff; hi[q] = -1; }
+    const int y0 = h0.x;
+    const int s_xmin[kPlWin] = {h0.y, h0.z, h0.w}, s_xmax[kPlWin] = {h1.x, h1.y, h1.z};
+    const bool fits = h1.w != 0;
+
+    int ne = 0, b = 0;
+    int c[kFlatRow] = {};
+    TACC w[kFlatRow] = {};
+    bool store = false;
+    if (!producer || !fits) {     // (the producer warp of a staged tile needs nothing from the CSR)
+        if (live) {
+            b = __ldg(a.rowptr + t);
+            ne = __ldg(a.rowptr + t + 1) - b;
+        }
+        store = live && ne <= kLongRow;   // longer rows: k_apply_planes_long
+        if (!store) ne = 0;
 #pragma unroll
         for (int k = 0; k < kFlatRow; ++k) {
-            if (k < ne) {
-                const int q = yk[k] - y0;
-                if (q >= g.nWin) bad = 1;
-#pragma unroll
-                for (int p = 0; p < kPlWin; ++p)
-                    if (q == p) { lo[p] = min(lo[p], xk[k]); hi[p] = max(hi[p], xk[k]); }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < kPlWin; ++q) {
-            lo[q] = __reduce_min_sync(0xffffffffu, lo[q]);
-            hi[q] = __reduce_max_sync(0xffffffffu, hi[q]);
-        }
-        bad = __reduce_max_sync(0xffffffffu, bad);
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < kPlWin; ++q) {
-                if (hi[q] >= 0) { atomicMin(&s_xmin[q], lo[q]); atomicMax(&s_xmax[q], hi[q]); }
-            }
-            if (bad) s_bad = 1;
+            const bool h = k < ne;
+            c[k] = h ? __ldg(a.col + b + k) : 0;
+            w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
         }
     }
-    __syncthreads();
-    bool fits = s_bad == 0 && y0 != 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < kPlWin; ++q)
-        if (s_xmax[q] - s_xmin[q] + 1 > kPlTile + 4) fits = false;
     if (!fits) {
         // windows too wide / too many source rows (or nothing mapped: zeros): register-gather code, whole CTA
         if (store)
@@ -208,9 +178,10 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
         const int l = lane / g.nWin, q = lane - l * g.nWin;
         int wd = 0, xm = 0;
         if (l < kPlLev) {
-            wd = s_xmax[q] - s_xmin[q] + 1;
-            xm = s_xmin[q];
-            if (wd <= 0) wd = 0;            // no entry in this source row
+            const int hi = q == 0 ? s_xmax[0] : (q == 1 ? s_xmax[1] : s_xmax[2]);
+            xm = q == 0 ? s_xmin[0] : (q == 1 ? s_xmin[1] : s_xmin[2]);
+            wd = hi - xm + 1;
+            if (hi < 0 || wd <= 0) wd = 0;  // no entry in this source row
         }
         const unsigned sdst0 = (unsigned)__cvta_generic_to_shared(pl_smem) + (unsigned)(q * kPlLev + l) * WCB;
         int n = 0;
@@ -244,6 +215,12 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
     }
 
     // ---- consumers ----
+    int yk[kFlatRow], xk[kFlatRow];
+#pragma unroll
+    for (int k = 0; k < kFlatRow; ++k) {
+        yk[k] = c[k] / g.srcNi;
+        xk[k] = c[k] - yk[k] * g.srcNi;
+    }
     // byte offset of each entry inside a level's slot of a stage, without the window's alignment shift.
     // Absent entries (k >= ne) carry weight 0 and re-read the lane's first entry (always staged: finite x 0 adds
     // nothing); a lane with no entry at all reads the start of the stage and its result is replaced by 0.

@@ -90,6 +90,10 @@ static bool set_option(mprg_ctx *c, const char *key, const char *val) {
         t.planesShape = atoi(v.c_str());
     } else if (k == "cols_minb") {
         t.colsMinb = v.empty() ? 3 : atoi(v.c_str());
+    } else if (k == "wind") {
+        if (v == "chain") t.windChain = true;
+        else if (v == "composed" || v.empty()) t.windChain = false;
+        else return false;
     } else if (k == "upload_threads") {
         t.uploadThreads = std::max(0, atoi(v.c_str()));
     } else {
@@ -138,7 +142,7 @@ int mprg_init(int device, int rank, int nranks, mprg_ctx **out) {
         // tuning knobs: the environment is read here, once; mprg_set_option changes them afterwards
         for (const char *const *kv = (const char *const[]){"MPASSIT_GPU_ACC", "accumulate", "MPASSIT_GPU_APPLY", "apply",
                                                            "MPASSIT_GPU_PIPE_MINB", "pipe_minb", "MPASSIT_GPU_PIPE_SPLIT", "pipe_split",
-                                                           "MPASSIT_GPU_MINB", "cols_minb", "MPASSIT_GPU_PLANES", "planes_shape", "MPASSIT_UPLOAD_THREADS",
+                                                           "MPASSIT_GPU_MINB", "cols_minb", "MPASSIT_GPU_PLANES", "planes_shape", "MPASSIT_GPU_WIND", "wind", "MPASSIT_UPLOAD_THREADS",
                                                            "upload_threads", nullptr};
              *kv; kv += 2)
             if (const char *e = getenv(kv[0])) set_option(c, kv[1], e);
@@ -335,6 +339,7 @@ int mprg_get_option(const mprg_ctx *ctx, const char *key, char *value, size_t le
     else if (k == "pipe_minb") v = std::to_string(t.pipeMinb);
     else if (k == "planes_shape") v = std::to_string(t.planesShape);
     else if (k == "cols_minb") v = std::to_string(t.colsMinb);
+    else if (k == "wind") v = t.windChain ? "chain" : "composed";
     else if (k == "upload_threads") v = std::to_string(t.uploadThreads);
     else return 59;
     snprintf(value, len, "%s", v.c_str());
@@ -451,7 +456,7 @@ int mprg_set_grid_kind(mprg_ctx *ctx, int kind) {
         if (ctx->capturing) fail(45, "mprg_set_grid_kind: not while capturing a graph");
         MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
         for (auto it = ctx->routes.begin(); it != ctx->routes.end();) {  // grid-source routes depend on the topology
-            if (std::get<1>(it->first) == MPRG_SRC_GRID_CENTER) {
+            if (std::get<1>(it->first) == MPRG_SRC_GRID_CENTER || std::get<1>(it->first) == MPRG_SRC_MESH_WIND) {
                 it->second->memoised = false;
                 if (it->second->refcount <= 0) delete it->second;
                 else ctx->imported.push_back(it->second);
@@ -461,6 +466,7 @@ int mprg_set_grid_kind(mprg_ctx *ctx, int kind) {
             }
         }
         ctx->gridKind = kind;
+        for (bool &d : ctx->windDeclined) d = false;
     }
     MPRG_LEAVE(ctx)
 }
@@ -528,6 +534,91 @@ int mprg_store(mprg_ctx *ctx, int method, int src_loc, int dst_stagger, mprg_rou
     MPRG_LEAVE(ctx)
 }
 
+// drop the memoised composed wind routes (they embed the rotation angles)
+static void drop_wind_routes(mprg_ctx *ctx) {
+    for (bool &d : ctx->windDeclined) d = false;
+    for (auto it = ctx->routes.begin(); it != ctx->routes.end();) {
+        if (std::get<1>(it->first) == MPRG_SRC_MESH_WIND) {
+            it->second->memoised = false;
+            if (it->second->refcount <= 0) delete it->second;
+            else ctx->imported.push_back(it->second);
+            it = ctx->routes.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
+int mprg_store_wind(mprg_ctx *ctx, int dst_stagger, mprg_route **rh) {
+    Trace tr("store_wind", dst_stagger);
+    if (!ctx) return 1;
+    if (!rh) { ctx->err = "mprg_store_wind: null route pointer"; return 1; }
+    *rh = nullptr;
+    if (dst_stagger != MPRG_EDGE1 && dst_stagger != MPRG_EDGE2) { ctx->err = "mprg_store_wind: destination must be MPRG_EDGE1 or MPRG_EDGE2"; return 51; }
+    auto key = std::make_tuple((int)MPRG_BILINEAR, (int)MPRG_SRC_MESH_WIND, dst_stagger);
+    auto it = ctx->routes.find(key);
+    if (it != ctx->routes.end()) {
+        it->second->refcount++;
+        *rh = it->second;
+        ctx->last_ms = 0.0;
+        return 0;
+    }
+    if (ctx->tune.windChain || !ctx->haveRot || ctx->gridKind != MPRG_GRID_NOPERI || ctx->windDeclined[dst_stagger]) return 0;   // not composable: *rh stays NULL
+    // the two matrices of the chain (memoised like any other route)
+    mprg_route *bil = nullptr, *stag = nullptr;
+    int rc = mprg_store(ctx, MPRG_BILINEAR, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER_HALO, &bil);
+    if (rc) return rc;
+    rc = mprg_store(ctx, MPRG_BILINEAR, MPRG_SRC_GRID_CENTER, dst_stagger, &stag);
+    if (rc) { mprg_release(ctx, bil); return rc; }
+    int out = 0;
+    {
+        struct Guard { mprg_ctx *c; mprg_route *a, *b; ~Guard() { mprg_release(c, a); mprg_release(c, b); } } guard{ctx, bil, stag};
+        MPRG_ENTER(ctx)
+        if (ctx->capturing) fail(46, "mprg_store_wind: this route is not memoised yet; build it before mprg_capture_begin");
+        struct StreamSwap {
+            mprg_ctx *c; cudaStream_t saved;
+            StreamSwap(mprg_ctx *c_) : c(c_), saved(c_->stream) { c->stream = c->store_stream; mprg::tl_stream = c->stream; }
+            ~StreamSwap() { c->stream = saved; mprg::tl_stream = saved; }
+        } swap(ctx);
+        std::unique_ptr<mprg_route> r(new mprg_route());
+        r->method = MPRG_BILINEAR; r->src_loc = MPRG_SRC_MESH_WIND; r->dst_stagger = dst_stagger;
+        MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (!store_wind_composed(ctx, r.get(), stag, bil)) {
+            MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+            ctx->windDeclined[dst_stagger] = true;
+            return 0;   // not composable on this grid / mesh: the caller keeps the three-step chain
+        }
+        r->dstNi = ctx->target[dst_stagger].ni;
+        route_finish(ctx, r.get());
+        MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        MPRG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms = ms;
+        if (r->tileEntriesMax <= 0 || r->tileEntriesMax > 512 || !r->rec32.p) {   // no tile schedule: chain
+            ctx->windDeclined[dst_stagger] = true;
+            return 0;
+        }
+        r->refcount = 1;
+        r->memoised = true;
+        *rh = r.get();
+        ctx->routes[key] = r.release();
+        MPRG_LEAVE(ctx)
+    }
+    return out;
+}
+
+int mprg_apply_wind(mprg_ctx *ctx, mprg_route *rh, const void *u_src, const void *v_src, int32_t nlev, int src_dtype,
+                    void *dst, int dst_dtype, int into_full) {
+    Trace tr("apply_wind", nlev, into_full);
+    MPRG_ENTER(ctx)
+    if (!rh) fail(1, "mprg_apply_wind: null route");
+    if (!ctx->capturing) MPRG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    apply_wind_device(ctx, rh, u_src, v_src, nlev, src_dtype, dst, dst_dtype, into_full != 0);
+    if (!ctx->capturing) MPRG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MPRG_LEAVE(ctx)
+}
+
 int mprg_release(mprg_ctx *ctx, mprg_route *rh) {
     MPRG_ENTER(ctx)
     if (!rh) fail(1, "mprg_release: null route");
@@ -551,6 +642,7 @@ int mprg_clear_routes(mprg_ctx *ctx) {
         else ctx->imported.push_back(kv.second);  // still held by a caller: freed on its release
     }
     ctx->routes.clear();
+    for (bool &d : ctx->windDeclined) d = false;
     MPRG_LEAVE(ctx)
 }
 
@@ -570,6 +662,15 @@ int mprg_route_export_csr(mprg_ctx *ctx, const mprg_route *rh, int32_t *rowptr, 
     if (rowptr) MPRG_CUDA(cudaMemcpy(rowptr, rh->rowptr.p, (rh->nDst + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (col && rh->nnz) MPRG_CUDA(cudaMemcpy(col, rh->col.p, rh->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (w && rh->nnz) MPRG_CUDA(cudaMemcpy(w, rh->w.p, rh->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    MPRG_LEAVE(ctx)
+}
+
+int mprg_route_export_w2(mprg_ctx *ctx, const mprg_route *rh, double *w2) {
+    MPRG_ENTER(ctx)
+    if (!rh || !w2) fail(1, "mprg_route_export_w2: null argument");
+    if (!rh->composite) fail(47, "mprg_route_export_w2: not a composed wind route");
+    MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (rh->nnz) MPRG_CUDA(cudaMemcpy(w2, rh->w2.p, rh->nnz * sizeof(double), cudaMemcpyDeviceToHost));
     MPRG_LEAVE(ctx)
 }
 
@@ -899,6 +1000,7 @@ int mprg_set_rotation(mprg_ctx *ctx, const double *cosa, const double *sina) {
     rotation_constants(ctx, n);
     MPRG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->haveRot = true;
+    drop_wind_routes(ctx);   // composed wind routes embed the previous angles
     MPRG_LEAVE(ctx)
 }
 

@@ -139,7 +139,7 @@ struct Target {
 }  // namespace mprg
 
 // Route handle: CSR weights of this rank's destination slab.
-namespace mprg { constexpr int kLongRow = 4; }
+namespace mprg { constexpr int kLongRow = 4; constexpr int kCmpRow = 12; }
 
 struct mprg_route {
     int method = 0, src_loc = 0, dst_stagger = 0;
@@ -167,10 +167,16 @@ struct mprg_route {
     int64_t srcPlane = 0;      // points per source level plane
     int32_t srcNi = 0;         // row length of the source grid
     int32_t planeWin = 0;      // source rows per 256-target tile (apply_planes.cuh); 0: register-gather kernel only
+    mprg::DevBuf<int32_t> planeTiles;  // [tiles][8] per-tile headers of the staged grid-source kernel (k_plane_stats)
     // rows of a grid-source route longer than kLongRow entries (the pole rows of a periodic grid: ni + 2 entries):
     // applied by one warp per (row, level) instead of one thread per row
     mprg::DevBuf<int32_t> longRows;
     int64_t nLong = 0;
+    // composed wind route (mprg_store_wind, compose.cu): every entry carries TWO weights -- w multiplies the zonal
+    // source column, w2 the meridional one -- and rows have at most kCmpRow entries
+    bool composite = false;
+    mprg::DevBuf<double> w2;
+    mprg::DevBuf<float> w2_32;
 };
 
 struct mprg_graph {
@@ -187,6 +193,7 @@ struct mprg_tuning {
     bool pipeSplit = false;    // MPASSIT_GPU_PIPE_SPLIT=0|1 | option "pipe_split": plain aligned units and the rest in separate launches
     int planesShape = 0;       // option "planes_shape": levels per stage * 10 + stages of the staged grid-source kernel (0 = default)
     int colsMinb = 3;          // MPASSIT_GPU_MINB | option "cols_minb": register cap of the fallback kernel
+    bool windChain = true;     // MPASSIT_GPU_WIND=composed|chain | option "wind": chain = mprg_store_wind declines, hosts keep the three-step wind chain
     int uploadThreads = 0;     // MPASSIT_UPLOAD_THREADS | option "upload_threads" (0 = 3/4 of the cores / ranks)
 };
 
@@ -213,6 +220,7 @@ struct mprg_ctx {
     mprg::DevBuf<double> rotc;        // [n][4] per-point rotation constants (sina, tana, 1/cosa, 1/(cosa + sina tana))
     mprg::DevBuf<float> rotc32;       // the same rounded to fp32 (all-fp32 applies rotate in fp32)
     bool haveRot = false;
+    bool windDeclined[4] = {};        // mprg_store_wind found this stagger not composable (reset with the routes)
     int64_t launches = 0;
     double last_ms = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -297,6 +305,8 @@ void store_bilinear_element(mprg_ctx *ctx, mprg_route *r);
 void store_conserve(mprg_ctx *ctx, mprg_route *r);
 void store_bilinear_grid(mprg_ctx *ctx, mprg_route *r);
 void store_bilinear_node(mprg_ctx *ctx, mprg_route *r);
+// compose.cu: stagger x rotation x bilinear in one matrix; false = not composable (the caller keeps the chain)
+bool store_wind_composed(mprg_ctx *ctx, mprg_route *r, const mprg_route *stag, const mprg_route *bil);
 void route_finish(mprg_ctx *ctx, mprg_route *r);  // stats + fp32 weight copy
 void route_tile_stats(mprg_ctx *ctx, mprg_route *r);  // apply.cu
 void route_plane_stats(mprg_ctx *ctx, mprg_route *r); // apply.cu
@@ -311,6 +321,8 @@ struct ApplyField {
 };
 void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, int nfields, int src_dtype,
                   int dst_dtype, bool into_full = false);
+void apply_wind_device(mprg_ctx *ctx, const mprg_route *r, const void *u, const void *v, int32_t nlev, int src_dtype,
+                       void *dst, int dst_dtype, bool into_full);
 void rotate_device(mprg_ctx *ctx, int stagger, void *u, void *v, int32_t nlev, int dtype);
 void rotation_constants(mprg_ctx *ctx, int64_t n);  // fills ctx->rotc from ctx->cosa / ctx->sina
 

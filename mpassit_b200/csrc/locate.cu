@@ -206,6 +206,13 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
         k_w32<<<(unsigned)((r->nnz + 255) / 256), 256, 0, ctx->stream>>>(r->nnz, r->w.p, r->w32.p);
         ctx->launches++;
     }
+    if (r->composite) {
+        r->w2_32.alloc(r->nnz > 0 ? r->nnz : 1);
+        if (r->nnz > 0) {
+            k_w32<<<(unsigned)((r->nnz + 255) / 256), 256, 0, ctx->stream>>>(r->nnz, r->w2.p, r->w2_32.p);
+            ctx->launches++;
+        }
+    }
     DevBuf<unsigned long long> nref(3);
     const unsigned long long nref0[3] = {0ULL, ~0ULL, 0ULL};
     poke(ctx, nref.p, nref0, sizeof nref0);

@@ -167,6 +167,7 @@ void mesh_set(mprg_ctx *ctx, int32_t nCells, int32_t nVertices, int32_t maxEdges
     // geometry changed: every memoised route is stale
     for (auto &kv : ctx->routes) { kv.second->memoised = false; if (kv.second->refcount <= 0) delete kv.second; }
     ctx->routes.clear();
+    for (bool &d : ctx->windDeclined) d = false;
 }
 
 void mesh_need_cell_bvh(mprg_ctx *ctx) {
@@ -216,9 +217,10 @@ void target_register(mprg_ctx *ctx, int stagger, int32_t ni, int32_t nj) {
         ctx->haveRot = false;  // angles belong to the previous grid
     }
     // routes into this stagger (or out of CENTER) are stale
+    for (bool &d : ctx->windDeclined) d = false;
     for (auto it = ctx->routes.begin(); it != ctx->routes.end();) {
         int dst = std::get<2>(it->first), srcloc = std::get<1>(it->first);
-        if (dst == stagger || (stagger == MPRG_CENTER && (srcloc == MPRG_SRC_GRID_CENTER || dst == MPRG_CENTER_HALO))) {
+        if (dst == stagger || (stagger == MPRG_CENTER && (srcloc == MPRG_SRC_GRID_CENTER || srcloc == MPRG_SRC_MESH_WIND || dst == MPRG_CENTER_HALO))) {
             it->second->memoised = false;
             if (it->second->refcount <= 0) delete it->second;
             it = ctx->routes.erase(it);

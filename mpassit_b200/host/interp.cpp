@@ -11,6 +11,7 @@
 // What differs by design: fields that share a route are stacked into ONE batched
 // apply, and each distinct weight matrix is generated once (mprg_store memoises),
 // instead of the reference's 12 RegridStore calls.
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -209,8 +210,23 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             // Mass-point winds live on MPRG_CENTER_HALO rows: this rank's CENTER slab plus the one row
             // either side that its EDGE1 / EDGE2 points interpolate from (the reference gets those rows
             // through ESMF's halo exchange; recomputing them from the replicated mesh needs no exchange).
+            // The whole wind chain as one matrix per staggered grid (mprg_store_wind): cell-centre (u, v) -> rotated U on
+            // EDGE1 / V on EDGE2 directly, no mass-point intermediates.  Taken when the sources are device buffers with
+            // 16-byte-aligned columns, the grid is composable (regional, rotation set) and both staggered outputs are
+            // wanted; otherwise the reference's three steps run one after the other below.
+            mprg_route *cmp_u = nullptr, *cmp_v = nullptr;
+            if (fu && fv && rotate && fu->nlev == fv->nlev && io->u_stag && io->v_stag && mem == MPRG_DEVICE && dmem == MPRG_DEVICE &&
+                ((size_t)fu->nlev * (sdt == MPRG_F64 ? 8 : 4)) % 16 == 0 && (uintptr_t)fu->src % 16 == 0 && (uintptr_t)fv->src % 16 == 0) {
+                ck(ctx, mprg_store_wind(ctx, MPRG_EDGE1, &cmp_u), "FieldRegridStore");
+                if (cmp_u) {
+                    held.push_back(cmp_u);
+                    ck(ctx, mprg_store_wind(ctx, MPRG_EDGE2, &cmp_v), "FieldRegridStore");
+                    if (cmp_v) held.push_back(cmp_v);
+                }
+            }
+            const bool composed = cmp_u && cmp_v;
             bool halo_is_center = true;
-            if (fu || fv) {
+            if ((fu || fv) && !composed) {
                 int32_t j0 = 0, j1 = 0, c0 = 0, c1 = 0, ni = 0, nj = 0;
                 mpassit_target_dims(cfg, MPRG_CENTER, &ni, &nj);
                 ck(ctx, mprg_get_slab(ctx, MPRG_CENTER_HALO, &j0, &j1), "get_slab");
@@ -224,7 +240,7 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             // rotate_winds_cgrid (interp.F90:291-293) is fused into the store of the (u, v) pair
             const bool fuse_rot = fu && fv && rotate && fu->nlev == fv->nlev;
             const int op_u = fuse_rot ? MPRG_EPI_ROT_U : MPRG_EPI_NONE, op_v = fuse_rot ? MPRG_EPI_ROT_V : MPRG_EPI_NONE;
-            const bool winds_in_batch = (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR && halo_is_center && !into;
+            const bool winds_in_batch = !composed && (fu || fv) && mem == MPRG_DEVICE && chain_dt == ddt && m_bil == MPRG_BILINEAR && halo_is_center && !into;
 
             // one stacked apply for everything on the bilinear element->CENTER route:
             // 2d_patch (:207-221), hgt (:226-238), 3d_nz (:240-254), 3d_nzp1 (:331-347)
@@ -255,7 +271,10 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
             }
 
             // winds, interp.F90:256-328
-            if (do_u || do_v) {
+            if (composed) {
+                ck(ctx, mprg_apply_wind(ctx, cmp_u, fu->src, fv->src, fu->nlev, sdt, io->u_stag, ddt, into ? 1 : 0), "FieldRegrid");
+                ck(ctx, mprg_apply_wind(ctx, cmp_v, fu->src, fv->src, fu->nlev, sdt, io->v_stag, ddt, into ? 1 : 0), "FieldRegrid");
+            } else if (do_u || do_v) {
                 if (!winds_in_batch) {
                     mprg_route *rh = store(m_bil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER_HALO, "FieldRegridStore");
                     Batch b;
@@ -298,16 +317,20 @@ int mpassit_interp_data(mprg_ctx *ctx, const mpassit_config *cfg, mpassit_interp
                 run(ctx, rh, b, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
             }
             // 2d_nstd bundle, interp.F90:418-434
+            bool soil_done = false;
             if (n2n > 0) {
                 method = MPRG_NEAREST_STOD;
                 mprg_route *rh = store(method, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
                 Batch b;
                 for (int i = 0; i < io->n_hist_2d; ++i)
                     if (io->hist_2d[i].klass == MPASSIT_CLASS_2D_NSTD) b.add(io->hist_2d[i].src, io->hist_2d[i].dst, 1);
+                // the soil bundle inherits this `method` (:436-443): same matrix, so its fields ride the same apply
+                for (int i = 0; i < io->n_soil; ++i) b.add(io->soil[i].src, io->soil[i].dst, io->soil[i].nlev);
+                soil_done = true;
                 run(ctx, rh, b, sdt, mem, ddt, dmem, "FieldBundleRegrid", into);
             }
             // soil bundle: whatever `method` holds now, interp.F90:436-447
-            if (io->n_soil > 0) {
+            if (io->n_soil > 0 && !soil_done) {
                 const int m_soil = method == kUnset ? MPRG_BILINEAR : method;
                 mprg_route *rh = store(m_soil, MPRG_SRC_MESH_ELEMENT, MPRG_CENTER, "FieldBundleRegridStore");
                 Batch b;

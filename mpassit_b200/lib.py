@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpassit_rg.so")
 
 BILINEAR, CONSERVE, NEAREST_STOD = 0, 1, 2
-SRC_MESH_ELEMENT, SRC_MESH_NODE, SRC_GRID_CENTER = 0, 1, 2
+SRC_MESH_ELEMENT, SRC_MESH_NODE, SRC_GRID_CENTER, SRC_MESH_WIND = 0, 1, 2, 3
 CENTER, EDGE1, EDGE2, CORNER, CENTER_HALO = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
@@ -31,6 +31,7 @@ EXPORTS = [
     "mprg_apply", "mprg_apply_ex", "mprg_apply_into", "mprg_put_slab", "mprg_ipc_export", "mprg_ipc_open", "mprg_ipc_close_all", "mprg_set_rotation", "mprg_rotate_winds", "mprg_rotate_winds_on", "mprg_comm_id", "mprg_comm_init",
     "mprg_post_midlevels", "mprg_post_ptop", "mprg_gather", "mprg_gather_v", "mprg_kernel_launches", "mprg_io_bytes", "mprg_capture_begin", "mprg_capture_end", "mprg_graph_launch", "mprg_graph_release", "mprg_last_ms", "mprg_profile_enable", "mprg_profile_read",
     "mprg_profile_reset", "mprg_route_src_referenced", "mprg_route_schedule_info", "mprg_set_source_byte_order", "mprg_bswap", "mprg_post_affine",
+    "mprg_store_wind", "mprg_apply_wind", "mprg_route_export_w2",
 ]
 
 
@@ -88,9 +89,12 @@ def load() -> C.CDLL:
     L.mprg_get_slab.argtypes = [vp, C.c_int, C.POINTER(i32), C.POINTER(i32)]
     L.mprg_store.argtypes = [vp, C.c_int, C.c_int, C.c_int, pp]
     L.mprg_release.argtypes = [vp, vp]
+    L.mprg_store_wind.argtypes = [vp, C.c_int, pp]
+    L.mprg_apply_wind.argtypes = [vp, vp, vp, vp, i32, C.c_int, vp, C.c_int, C.c_int]
     L.mprg_clear_routes.argtypes = [vp]
     L.mprg_route_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.mprg_route_export_csr.argtypes = [vp, vp, vp, vp, vp]
+    L.mprg_route_export_w2.argtypes = [vp, vp, vp]
     L.mprg_route_import_csr.argtypes = [vp, i64, i64, vp, vp, vp, pp]
     L.mprg_apply.argtypes = [vp, vp, i32, pp, C.POINTER(i32), C.c_int, C.c_int, pp, C.c_int, C.c_int]
     L.mprg_apply_ex.argtypes = [vp, vp, i32, pp, C.POINTER(i32), C.c_int, C.c_int, pp, C.c_int, C.c_int,

@@ -83,6 +83,12 @@ class Route:
         _l.check(self.owner.ctx, rc)
         return rowptr, col[: i["nnz"]], w[: i["nnz"]]
 
+    def export_w2(self):
+        """Second weights (meridional source) of a composed wind route."""
+        w2 = np.empty(max(self.info()["nnz"], 1), np.float64)
+        _l.check(self.owner.ctx, _l.load().mprg_route_export_w2(self.owner.ctx, self.handle, w2.ctypes.data))
+        return w2[: self.info()["nnz"]]
+
     def release(self) -> None:
         if self.handle:
             _l.check(self.owner.ctx, _l.load().mprg_release(self.owner.ctx, self.handle))
@@ -370,6 +376,20 @@ class Regridder:
         ca = np.ascontiguousarray(cosa, np.float64)
         sa = np.ascontiguousarray(sina, np.float64)
         self._ck(self.L.mprg_set_rotation(self.ctx, ca.ctypes.data, sa.ctypes.data))
+
+    def store_wind(self, dst_stagger: int) -> Route | None:
+        """Composed wind route (stagger x rotate_winds_cgrid x bilinear, interp.F90:256-328) or None when the grid /
+        mesh is not composable and the three-step chain must be used."""
+        h = C.c_void_p()
+        self._ck(self.L.mprg_store_wind(self.ctx, int(dst_stagger), C.byref(h)))
+        return Route(self, h.value, BILINEAR, _l.SRC_MESH_WIND, dst_stagger) if h.value else None
+
+    def apply_wind(self, route: Route, u_src, v_src, dst, nlev: int, into_full: bool = False) -> None:
+        """dst = A u_src + B v_src: cell-centre winds (torch CUDA tensors, [nCells][nlev]) -> this rank's slab of the
+        rotated, staggered wind [nlev][nj_slab][ni]."""
+        self.order_after_torch(u_src, v_src, dst)
+        self._ck(self.L.mprg_apply_wind(self.ctx, route.handle, _ptr(u_src), _ptr(v_src), int(nlev), _dtype_code(u_src),
+                                        _ptr(dst), _dtype_code(dst), 1 if into_full else 0))
 
     def rotate_winds(self, u, v, nlev: int, stagger: int = CENTER) -> None:
         self.order_after_torch(u, v)

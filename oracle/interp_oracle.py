@@ -175,3 +175,25 @@ def interp_data(mesh, grids, fields, cosa=None, sina=None, wrf_mod_vars=True, lc
 def wl_rows(arr, halo, own, ni):
     """Output values of a mass-point wind field that belong to the block's own rows."""
     return arr.shape[0] * (own[1] - own[0]) * ni
+
+
+def wind_chain(mesh, grids, u, v, cosa, sina):
+    """The reference's wind chain alone, in R8 (interp.F90:256-328): cell-centre (u, v) [nCells][nlev] -> mass points
+    (bilinear), rotate_winds_cgrid there, -> EDGE1 / EDGE2 (grid-to-grid bilinear).  Returns {"U", "V"} fp64
+    [nlev][points]: what the composed wind routes of the engine must reproduce."""
+    cxyz, vxyz, tri = geometry(mesh)
+    lat, lon = grids["M"]
+    nj, ni = lat.shape
+    dxyz = orc.sph_deg_to_cart(lon, lat)
+    e, c, w = orc.bilinear(cxyz, tri, mesh.verticesOnCell, dxyz)
+    bil = orc.ell_to_csr(e >= 0, c, w)
+    um = orc.apply(*bil, np.ascontiguousarray(u, np.float64), np.float64)
+    vm = orc.apply(*bil, np.ascontiguousarray(v, np.float64), np.float64)
+    orc.rotate_winds(um, vm, np.asarray(cosa, np.float64).reshape(-1), np.asarray(sina, np.float64).reshape(-1))
+    sx = dxyz.reshape(nj, ni, 3)
+    out = {}
+    for key, src in (("U", um), ("V", vm)):
+        slat, slon = grids[key]
+        es, cs, ws = orc.bilinear_quadgrid(sx, orc.sph_deg_to_cart(slon, slat), topo=0)
+        out[key] = np.asarray(orc.apply_planes(*orc.quadgrid_csr(ni, nj, es, cs, ws, 0), src), np.float64)
+    return out

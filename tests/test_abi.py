@@ -66,7 +66,7 @@ def test_fortran_module_binds_every_reference_facing_entry():
     declared = _declared()
     # instrumentation that only the bench / tuning scripts use
     tooling = {"mprg_profile_enable", "mprg_profile_read", "mprg_profile_reset", "mprg_set_stream", "mprg_version",
-               "mprg_route_export_csr", "mprg_route_import_csr", "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc",
+               "mprg_route_export_csr", "mprg_route_export_w2", "mprg_route_import_csr", "mprg_host_alloc", "mprg_host_free", "mprg_device_alloc",
                "mprg_device_free", "mprg_kernel_launches", "mprg_last_ms", "mprg_route_src_referenced", "mprg_clear_routes",
                "mprg_route_info", "mprg_scratch", "mprg_has_rotation", "mprg_synchronize", "mprg_get_slab", "mprg_get_option", "mprg_weight_cache_stats", "mprg_get_target_lonlat"}
     assert not [b for b in bound if b not in declared], "Fortran binds a name the header does not declare"
