@@ -250,7 +250,9 @@ constexpr int kShortLev = 8;  // fields with at most this many levels (2-D field
 
 // (latency-bound: 6 resident CTAs per SM instead of the 4 that 64 registers allowed -- ncu: 72-77 % of the stall samples
 // were long-scoreboard at 46 % occupancy)
-template <typename TIN, typename TOUT, typename TACC>
+// ROW: row entries held in registers (3 when no row of the route is longer: bilinear, nearest; else kFlatRow);
+// BATCH: 2-D fields whose gathers are all issued before the first FMA (ROW x BATCH loads in flight per thread)
+template <typename TIN, typename TOUT, typename TACC, int ROW, int BATCH>
 __global__ void __launch_bounds__(256, sizeof(TACC) == 4 ? 6 : 4)
 k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,30 +262,36 @@ k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     TACC w[kFlatRow];
 #pragma unroll
     for (int k = 0; k < kFlatRow; ++k) {
-        const bool h = b + k < e;
+        const bool h = k < ROW && b + k < e;
         c[k] = h ? __ldg(a.col + b + k) : 0;
         w[k] = h ? __ldg(a.w + b + k) : (TACC)0;
     }
     int f = 0;
-    if (e - b <= kFlatRow) {
-        // 2-D fields, rows of <= 4 entries (bilinear, nearest): four fields' gathers in flight per thread
-        for (; f + 4 <= a.nfields; f += 4) {
-            if (fp.f[f].nlev != 1 || fp.f[f + 1].nlev != 1 || fp.f[f + 2].nlev != 1 || fp.f[f + 3].nlev != 1) break;
-            TIN x[4][kFlatRow];
+    if (e - b <= ROW) {
+        // 2-D fields, short rows (bilinear, nearest): BATCH fields' gathers in flight per thread
+        while (f < a.nfields) {
+            const int nb = min(BATCH, a.nfields - f);     // (the last batch may be partial)
+            bool flat2d = true;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const TIN *__restrict__ src = (const TIN *)fp.f[f + q].src;
+            for (int q = 0; q < BATCH; ++q) flat2d = flat2d && (q >= nb || fp.f[f + q].nlev == 1);
+            if (!flat2d) break;
+            TIN x[BATCH][ROW];
 #pragma unroll
-                for (int k = 0; k < kFlatRow; ++k) x[q][k] = (b + k < e) ? __ldg(src + c[k]) : (TIN)0;
+            for (int q = 0; q < BATCH; ++q) {
+                const TIN *__restrict__ src = (const TIN *)fp.f[q < nb ? f + q : f].src;
+#pragma unroll
+                for (int k = 0; k < ROW; ++k) x[q][k] = (q < nb && b + k < e) ? __ldg(src + c[k]) : (TIN)0;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < BATCH; ++q) {
+                if (q >= nb) break;
                 TACC acc = 0;
 #pragma unroll
-                for (int k = 0; k < kFlatRow; ++k)
+                for (int k = 0; k < ROW; ++k)
                     if (b + k < e) acc += w[k] * (TACC)x[q][k];
                 st_stream((TOUT *)fp.f[f + q].dst + a.dstOff + t, (TOUT)epilogue(acc, fp.f[f + q].epi_op, fp.f[f + q].epi_arg));
             }
+            f += nb;
         }
     }
     for (; f < a.nfields; ++f) {
@@ -468,9 +476,22 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     }
     // One launch, two phases: the plain aligned units first (the kernel's lean phase A), then wind pairs and
     // unaligned columns (phase B).  pipe_split = 1 puts the two groups into separate launches instead.
-    std::vector<UnitDev> plain, rest;
-    for (const UnitDev &u : units)
-        (((u.flags & kUnitAligned) && !(u.flags & (kUnitRotU | kUnitRotV))) ? plain : rest).push_back(u);
+    // (aligned wind pairs come right after the plain units: they keep phase A's copy protocol)
+    std::vector<UnitDev> plain, rotal, rest;
+    for (size_t k = 0; k < units.size(); ++k) {
+        const UnitDev &u = units[k];
+        const bool isrot = (u.flags & (kUnitRotU | kUnitRotV)) != 0;
+        // a pair is aligned when both of its chunks are (same level count; the two sources may differ in alignment)
+        bool pairAligned = false;
+        if (isrot) {
+            const size_t k0 = (u.flags & kUnitRotU) ? k : k - 1;
+            pairAligned = (units[k0].flags & kUnitAligned) && (units[k0 + 1].flags & kUnitAligned);
+        }
+        if (!isrot && (u.flags & kUnitAligned)) plain.push_back(u);
+        else if (isrot && pairAligned) rotal.push_back(u);
+        else rest.push_back(u);
+    }
+    rest.insert(rest.begin(), rotal.begin(), rotal.end());
     std::vector<std::vector<UnitDev>> groups;
     std::vector<size_t> groupPlain;
     if (ctx->tune.pipeSplit) {
@@ -495,7 +516,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         pa.rotc = sizeof(TR) == 4 ? (const void *)(ctx->rotc32.p + off) : (const void *)(ctx->rotc.p + off);
     }
     const unsigned tiles = (unsigned)(((r->nDst + r->dstNi - 1) / r->dstNi) * pa.tilesPerRow);
-    struct Launch { size_t g, u0, nu, smem; int mode, minb, nPlain; int32_t stageOff, stageBytes, holdOff; };
+    struct Launch { size_t g, u0, nu, smem; int mode, minb, nPlain, nRotA; int32_t stageOff, stageBytes, holdOff; };
     std::vector<Launch> plan;
     for (size_t g = 0; g < groups.size(); ++g) {
         const std::vector<UnitDev> &us = groups[g];
@@ -505,9 +526,16 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             int mode = 0;
             size_t stage = 0;   // one stage holds the largest unit of the launch at the route's tile maxima
             const int nPlain = (int)std::min<size_t>(nu, groupPlain[g] > u0 ? groupPlain[g] - u0 : 0);
+            int nRotA = 0;   // aligned wind-pair units directly after the plain ones
+            for (size_t k = (size_t)nPlain; k < nu; ++k) {
+                const UnitDev &u = us[u0 + k];
+                if (!(u.flags & (kUnitRotU | kUnitRotV)) || !(u.flags & kUnitAligned)) break;
+                ++nRotA;
+            }
+            nRotA &= ~1;
             for (size_t k = 0; k < nu; ++k) {
                 const UnitDev &u = us[u0 + k];
-                if ((int)k >= nPlain && !(u.flags & kUnitAligned)) mode |= kModeUnal;
+                if ((int)k >= nPlain + nRotA && !(u.flags & kUnitAligned)) mode |= kModeUnal;
                 if ((int)k >= nPlain && (u.flags & (kUnitRotU | kUnitRotV))) mode |= kModeRot;
                 stage = std::max(stage, pipe_unit_stage_bytes((u.flags & kUnitAligned) != 0, (u.flags & kUnitMerged) != 0,
                                                               (unsigned)(u.Ln * sizeof(TIN)), r->tileUniqMax, r->tileRunsMax));
@@ -522,7 +550,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
             // 5 resident CTAs per SM (48 registers) when their shared memory fits, else 4 (64 registers)
             int minb = (smemBytes + 1024) * 5 <= (size_t)228 * 1024 ? 5 : 4;
             if (ctx->tune.pipeMinb) minb = ctx->tune.pipeMinb >= 5 ? 5 : 4;
-            plan.push_back(Launch{g, u0, nu, smemBytes, mode, minb, nPlain, (int32_t)fixed, (int32_t)stage,
+            plan.push_back(Launch{g, u0, nu, smemBytes, mode, minb, nPlain, nRotA, (int32_t)fixed, (int32_t)stage,
                                   (int32_t)(fixed + kPipeStages * stage)});
             u0 += nu;
         }
@@ -531,7 +559,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
         UnitPack up;
         memcpy(up.u, groups[l.g].data() + l.u0, l.nu * sizeof(UnitDev));
         pa.nunits = (int)l.nu;
-        pa.nPlain = l.nPlain;
+        pa.nPlain = l.nPlain; pa.nRotA = l.nRotA;
         pa.stageOff = l.stageOff; pa.stageBytes = l.stageBytes; pa.holdOff = l.holdOff;
         pa.rotOff = (int32_t)(l.holdOff + ((l.mode & kModeRot) ? (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TOUT) : 0));
         const size_t smemBytes = l.smem;
@@ -703,7 +731,9 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     if (!flat.empty()) {
         ProfScope ps(ctx, 2, alg_bytes(r, ksum(flat), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(flat) * r->nDst);
         packs(flat, [&](const FieldPack &fp, size_t) {
-            k_apply_flat<TIN, TOUT, TACC><<<(unsigned)((r->nDst + 255) / 256), 256, 0, ctx->stream>>>(a, fp);
+            const unsigned g = (unsigned)((r->nDst + 255) / 256);
+            if (r->maxRow <= 3) k_apply_flat<TIN, TOUT, TACC, 3, (sizeof(TACC) == 4 ? 6 : 4)><<<g, 256, 0, ctx->stream>>>(a, fp);
+            else k_apply_flat<TIN, TOUT, TACC, kFlatRow, 4><<<g, 256, 0, ctx->stream>>>(a, fp);
         });
     }
     if (!planes.empty()) {
@@ -868,7 +898,7 @@ static void launch_wind(mprg_ctx *ctx, const mprg_route *r, const void *u, const
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
     pa.rotc = nullptr;
-    pa.nunits = nu; pa.nPlain = 0; pa.rotOff = 0;
+    pa.nunits = nu; pa.nPlain = 0; pa.nRotA = 0; pa.rotOff = 0;
     const size_t fixed = ((size_t)kPipeSmemHead + lay.stride + nu * sizeof(UnitDev) + 15) & ~(size_t)15;
     const size_t hold = (size_t)(kPipeLev / 4 / kPipeWarps) * kPipeThreads * 4 * sizeof(TACC);
     const size_t smemBytes = fixed + kPipeStages * stage + hold;

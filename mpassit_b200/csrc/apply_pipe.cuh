@@ -121,6 +121,7 @@ struct PipeArgs {
     int32_t tilesPerRow;
     int32_t nunits;
     int32_t nPlain;     // the first nPlain units are plain aligned fields (phase A of the kernel)
+    int32_t nRotA;      // the next nRotA units are aligned wind pairs: phase A's copy protocol, rotation in the math
     int32_t stageOff;   // byte offset of the first stage in dynamic shared memory (after the record and the unit descriptors)
     int32_t stageBytes; // bytes of one stage (host: the largest unit's need at the route's tile maxima)
     int32_t holdOff;    // byte offset of the wind-pair hold buffer (kModeRot launches)
@@ -303,7 +304,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     // pass -- and run the leanest code (one barrier arrival per unit, 16-byte loads only).  Phase B: wind pairs and
     // unaligned columns (per-warp arrivals, in-place element loads, rotation).  One launch pays the tile prologue
     // once; the lean loop is not slowed by the code and registers the general one needs.
-    const int nA = a.nPlain;
+    const int nA = a.nPlain, nA2 = a.nPlain + (ROT ? a.nRotA : 0);
     auto issue = [&](int u) {
         if (u >= a.nunits) return;
         const UnitDev &ud = s_units[u];
@@ -313,7 +314,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         // exact column chunks (aligned units).  Whole-column units whose column size is not a multiple of 128 bytes
         // pack their slots at the column size, so a run is contiguous in shared memory too and its owner fetches it whole
         const bool packed = merged && (chunkB & 127u);
-        if (u < nA) {
+        if (u < nA2) {
             unsigned long long *bar = s_mbar + (u % kPipeStages);
             const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
             if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)nu);   // one arrival posts the unit's bytes
@@ -326,7 +327,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         }
         if (MODE == 0) return;
         // phase B: the barrier counts one arrival per warp (lane 0 posts the bytes of the warp's copies)
-        unsigned long long *bar = s_mbar + 3 + ((u - nA) % kPipeStages);
+        unsigned long long *bar = s_mbar + 3 + ((u - nA2) % kPipeStages);
         unsigned nb = 0, sdst = 0;
         uintptr_t ga = 0;
         if (!UNAL || (ud.flags & kUnitAligned)) {
@@ -532,11 +533,19 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));  // unit u's bytes have landed
         if (live) math(u, std::false_type{}, std::false_type{});
     }
-    if (MODE != 0) {
-        for (int u = nA; u < a.nunits; ++u) {
+    if (ROT) {     // aligned wind pairs: the same single-arrival copy protocol, rotation fused into the math
+        for (int u = nA; u < nA2; ++u) {
             if (u > 0) __syncthreads();
             issue(u + 1);
-            const int k = u - nA;
+            mbar_wait(s_mbar + (u % kPipeStages), (unsigned)((u / kPipeStages) & 1));
+            if (live) math(u, std::false_type{}, std::true_type{});
+        }
+    }
+    if (MODE != 0) {
+        for (int u = nA2; u < a.nunits; ++u) {
+            if (u > 0) __syncthreads();
+            issue(u + 1);
+            const int k = u - nA2;
             mbar_wait(s_mbar + 3 + (k % kPipeStages), (unsigned)((k / kPipeStages) & 1));
             if (live) math(u, std::integral_constant<bool, UNAL>{}, std::integral_constant<bool, ROT>{});
         }

@@ -849,12 +849,22 @@ static void apply_impl(mprg_ctx *ctx, mprg_route *rh, int32_t nfields, const voi
                     // keep the 16-byte phase of the original layout so aligned fields stay aligned
                     unsigned char *data = ctx->stageIn[slot].p + io + kPad + (skip & 15);
                     const unsigned char *from = (const unsigned char *)src[k] + skip;
-                    if (in_bytes(k) >= ((size_t)16 << 20) && !is_pinned_host(from))
-                        upload_unpinned(ctx, data, from, in_bytes(k));
-                    else
-                        MPRG_CUDA(cudaMemcpyAsync(data, from, in_bytes(k), cudaMemcpyHostToDevice, ctx->h2d_stream));
-                    ctx->h2dBytes += in_bytes(k);
-                    staged.emplace_back(data, in_bytes(k) / isz);
+                    // only the id ranges the weights reference cross PCIe (one range when the mesh is numbered along
+                    // the slab; a short list otherwise); the staged field keeps the layout of [lo, hi)
+                    std::pair<int64_t, int64_t> whole(lo, hi);
+                    const std::pair<int64_t, int64_t> *rb = &whole, *re = rb + 1;
+                    if (range && !rh->srcRanges.empty()) { rb = rh->srcRanges.data(); re = rb + rh->srcRanges.size(); }
+                    const bool pinned = is_pinned_host(from);
+                    for (const std::pair<int64_t, int64_t> *rg = rb; rg != re; ++rg) {
+                        const size_t off = (size_t)(rg->first - lo) * col, nb = (size_t)(rg->second - rg->first) * col;
+                        if (nb == 0) continue;
+                        if (nb >= ((size_t)16 << 20) && !pinned)
+                            upload_unpinned(ctx, data + off, from + off, nb);
+                        else
+                            MPRG_CUDA(cudaMemcpyAsync(data + off, from + off, nb, cudaMemcpyHostToDevice, ctx->h2d_stream));
+                        ctx->h2dBytes += nb;
+                        staged.emplace_back(data + off, nb / isz);
+                    }
                     s = data - skip;
                 }
                 if (dst_mem == MPRG_HOST) d = ctx->stageOut[slot].p + oo;

@@ -146,6 +146,10 @@ struct mprg_route {
     int64_t nDst = 0, nnz = 0, nUnmapped = 0, nSrc = 0;
     int64_t nSrcRef = 0;       // distinct source entities referenced by the weights
     int64_t srcLo = 0, srcHi = 0;  // [srcLo, srcHi): smallest id range containing all of them
+    // the referenced ids as a short list of ranges inside [srcLo, srcHi) (256-cell granularity, small gaps merged):
+    // what a host-buffer apply uploads.  One range on a mesh numbered along the slab; a few dozen on a Z-order or
+    // generator-ordered mesh, where [srcLo, srcHi) alone would be most of the field on every rank.
+    std::vector<std::pair<int64_t, int64_t>> srcRanges;
     int32_t tileEntriesMax = 0, tileUniqMax = 0;  // per 32-target tile: CSR entries / distinct columns
     int32_t tileRunsMax = 0;                      // per tile: runs of consecutive column ids
     int32_t dstNi = 0;         // destination row length (tiles of the apply kernel never straddle rows)
@@ -241,6 +245,7 @@ struct mprg_ctx {
     cudaEvent_t evDl = nullptr;           // mprg_download ordering
     mprg::DevBuf<unsigned char> userScratch[8];  // mprg_scratch slots
     void *peekBuf = nullptr;              // pinned, device-visible: scalar readbacks without a copy engine (peek)
+    mprg::PinnedBuf blockMarks;           // pinned, device-visible: per-256-cell "referenced" flags of a route (route_finish)
     std::map<std::string, void *> ipcOpen;  // peer allocations mapped with mprg_ipc_open (handle bytes -> base)
     void *nccl = nullptr;                 // ncclComm_t
     void *ncclLib = nullptr;

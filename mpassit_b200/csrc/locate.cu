@@ -176,6 +176,15 @@ __global__ void k_count_marks(int64_t n, const unsigned char *__restrict__ mark,
     }
 }
 
+// one flag per kMarkBlock source ids: any of them referenced?  Written straight into pinned host memory.
+constexpr int kMarkBlock = 256;
+__global__ void __launch_bounds__(kMarkBlock)
+k_block_marks(int64_t n, const unsigned char *__restrict__ mark, unsigned char *host_visible) {
+    const int64_t i = (int64_t)blockIdx.x * kMarkBlock + threadIdx.x;
+    const int any = __syncthreads_or(i < n && mark[i]);
+    if (threadIdx.x == 0) host_visible[blockIdx.x] = any ? 1 : 0;
+}
+
 __global__ void k_w32(int64_t nnz, const double *__restrict__ w, float *__restrict__ w32) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) w32[i] = (float)w[i];
@@ -217,12 +226,19 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
     const unsigned long long nref0[3] = {0ULL, ~0ULL, 0ULL};
     poke(ctx, nref.p, nref0, sizeof nref0);
     DevBuf<unsigned char> mark;
+    int64_t nblk = 0;
     if (r->nnz > 0 && r->nSrc > 0) {
         mark.alloc(r->nSrc);
         MPRG_CUDA(cudaMemsetAsync(mark.p, 0, r->nSrc, ctx->stream));
         k_mark_cols<<<(unsigned)((r->nnz + 255) / 256), 256, 0, ctx->stream>>>(r->nnz, r->col.p, mark.p);
         k_count_marks<<<(unsigned)((r->nSrc + 255) / 256), 256, 0, ctx->stream>>>(r->nSrc, mark.p, nref.p);
         ctx->launches += 2;
+        if (!r->srcLevelSlowest) {
+            nblk = (r->nSrc + kMarkBlock - 1) / kMarkBlock;
+            ctx->blockMarks.ensure((size_t)nblk);
+            k_block_marks<<<(unsigned)nblk, kMarkBlock, 0, ctx->stream>>>(r->nSrc, mark.p, (unsigned char *)ctx->blockMarks.p);
+            ctx->launches++;
+        }
     }
     unsigned long long hun = 0, href[3] = {0, 0, 0};
     int32_t hmm[2] = {0, 0};
@@ -234,6 +250,26 @@ void route_finish(mprg_ctx *ctx, mprg_route *r) {
     // contiguous id range that holds every referenced source: host-buffer applies upload only this range
     r->srcLo = href[0] ? (int64_t)href[1] : 0;
     r->srcHi = href[0] ? (int64_t)href[2] + 1 : 0;
+    // (the peeks above synchronised the stream: the block flags are in host memory)
+    r->srcRanges.clear();
+    if (nblk > 0 && href[0]) {
+        const unsigned char *bm = (const unsigned char *)ctx->blockMarks.p;
+        for (int64_t gap = 4;; gap *= 2) {   // merge gaps of up to `gap` blocks; widen until the list is short
+            r->srcRanges.clear();
+            int64_t b = 0;
+            while (b < nblk) {
+                if (!bm[b]) { ++b; continue; }
+                int64_t e = b + 1, last = b;   // last marked block of the range
+                while (e < nblk && e - last <= gap) {
+                    if (bm[e]) last = e;
+                    ++e;
+                }
+                r->srcRanges.emplace_back(std::max(b * kMarkBlock, r->srcLo), std::min((last + 1) * kMarkBlock, r->srcHi));
+                b = last + 1;
+            }
+            if (r->srcRanges.size() <= 256) break;
+        }
+    }
     if (!r->srcLevelSlowest) route_tile_stats(ctx, r);
     r->maxRow = hmm[0];
     r->uniform = (r->nnz > 0 && hmm[0] == hmm[1]);

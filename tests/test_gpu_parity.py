@@ -397,3 +397,47 @@ def test_results_do_not_depend_on_the_cell_numbering(engine_lib, orc, order):
     np.testing.assert_allclose(outs[1], outs[0], rtol=3e-7, atol=0)
     assert infos[0]["tile_columns"] == infos[1]["tile_columns"]
     assert infos[0]["tile_runs"] < infos[1]["tile_runs"] <= infos[1]["tile_columns"]  # row-major numbering has the longest runs
+
+
+@pytest.mark.parametrize("order", ["rowmajor", "morton", "random"])
+def test_host_sources_upload_only_the_referenced_id_ranges(engine_lib, order):
+    """Host-buffer applies move only the id ranges a rank's weights reference (route.srcRanges): on a row slab of a
+    mesh numbered along a Z-order curve that is a short list of ranges -- a fraction of the field -- where the single
+    enclosing range [srcLo, srcHi) would be most of it.  Results equal the device-buffer apply bit for bit, gaps
+    between the ranges (never uploaded) included in the addressing."""
+    import torch
+
+    from mpassit_b200 import lib as l
+    from mpassit_b200.regrid import Regridder
+
+    mesh = H.synth.regional_hex_mesh(spacing_m=12000.0, extent_x_m=2400e3, extent_y_m=1600e3, seed=5)
+    if order != "rowmajor":
+        mesh = H.synth.renumber_cells(mesh, order, seed=2)
+    lon, lat = H.latlon_grid(192, 128, lon0=-108.0, lon1=-87.0, lat0=32.0, lat1=45.0)
+    rng = np.random.default_rng(3)
+    srcs = [rng.standard_normal((mesh.nCells, nl)).astype(np.float32) for nl in (60, 61, 1)]
+    moved = {}
+    for nranks, rank in ((1, 0), (4, 1)):
+        rg = Regridder(device=0, rank=rank, nranks=nranks)
+        rg.set_mesh(mesh.lonCell, mesh.latCell, mesh.lonVertex, mesh.latVertex, mesh.verticesOnCell)
+        rg.set_target(l.CENTER, lon, lat)
+        r = rg.store(l.BILINEAR, l.SRC_MESH_ELEMENT, l.CENTER)
+        n = r.info()["nDst"]
+        host_out = [np.full((s.shape[1], n), np.nan, np.float32) for s in srcs]
+        b0 = rg.io_bytes()[0]
+        rg.apply(r, srcs, host_out, nlev=[s.shape[1] for s in srcs])
+        moved[nranks] = rg.io_bytes()[0] - b0
+        dev_src = [torch.from_numpy(s).cuda() for s in srcs]
+        dev_out = [torch.full((s.shape[1], n), float("nan"), device="cuda") for s in srcs]
+        rg.apply(r, dev_src, dev_out, nlev=[s.shape[1] for s in srcs])
+        rg.synchronize()
+        for h, d in zip(host_out, dev_out):
+            assert np.array_equal(h, d.cpu().numpy())
+        r.release()
+        rg.close()
+    full = sum(s.nbytes for s in srcs)
+    assert moved[1] <= full
+    if order in ("rowmajor", "morton"):       # a quarter of the rows needs about a quarter of the cells (+ halo, + merged gaps)
+        assert moved[4] < 0.45 * full, (moved, full)
+    else:                                      # a random numbering references cells all over the id space
+        assert moved[4] <= full
