@@ -740,7 +740,8 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
         ProfScope ps(ctx, 3, alg_bytes(r, ksum(planes), sizeof(TIN), sizeof(TOUT), sizeof(TACC)), ksum(planes) * r->nDst);
         // TMA-staged kernel when the slab is whole destination rows of a known source grid whose tiles' windows fit
         // (route_finish: planeWin); "apply" = "direct" keeps the register-gather kernel
-        const bool staged = !ctx->tune.pipeOff && r->planeWin > 0 && ((size_t)r->srcPlane * sizeof(TIN)) % 16 == 0;   // windows keep their 16-byte phase from level to level
+        bool staged = !ctx->tune.pipeOff && r->planeWin > 0 && ((size_t)r->srcPlane * sizeof(TIN)) % 16 == 0;   // windows keep their 16-byte phase from level to level
+        for (const FieldDev &f : planes) staged = staged && ((uintptr_t)f.src % 16) == 0;                          // ... and from field to field
         packs(planes, [&](const FieldPack &fp, size_t n) {
             if (staged) {
                 PlaneGeom pg = plane_geom(r);

@@ -81,6 +81,7 @@ k_plane_stats(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
     int b = 0, ne = 0;
     if (tid < cnt) { b = rowptr[t]; ne = rowptr[t + 1] - b; }
     if (ne > kLongRow) ne = 0;
+    const int nMapped = __syncthreads_count(tid < cnt && ne > 0);
     if (tid == 0) {
         s_y0 = 0x7fffffff; s_bad = 0;
         for (int q = 0; q <= kPlWin; ++q) { s_xmin[q] = 0x7fffffff; s_xmax[q] = -1; }
@@ -109,7 +110,8 @@ k_plane_stats(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
         int32_t *h = tiles + 8 * (size_t)blockIdx.x;
         h[0] = y0;
         for (int q = 0; q < kPlWin; ++q) { h[1 + q] = s_xmin[q]; h[4 + q] = s_xmax[q]; }
-        h[7] = bad ? 0 : 1;     // (a tile with nothing mapped does not "fit": it only writes zeros)
+        // bit 0: the windows fit (a tile with nothing mapped does not: it only writes zeros); bit 1: every target mapped
+        h[7] = bad ? 0 : (1 | (nMapped == cnt ? 2 : 0));
     }
 }
 
@@ -145,7 +147,8 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
     __syncthreads();
     const int y0 = h0.x;
     const int s_xmin[kPlWin] = {h0.y, h0.z, h0.w}, s_xmax[kPlWin] = {h1.x, h1.y, h1.z};
-    const bool fits = h1.w != 0;
+    const bool fits = (h1.w & 1) != 0;
+    const bool fullTile = (h1.w & 2) != 0;     // every target of the tile is mapped: no per-level zero selects
 
     int ne = 0, b = 0;
     int c[kFlatRow] = {};
@@ -240,17 +243,20 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
         off[k] = (unsigned)q * (kPlLev * WCB) + (unsigned)(mapped ? xx - xm : 0) * ESZ;
         gx[k] = (size_t)(y0 + q) * g.srcNi + (mapped ? xm : s_xmin[0]);
     }
+    // + the window's alignment shift: the same at every level and for every field (planes are a multiple of 16 bytes
+    // apart and the launch takes this kernel only when every source base is 16-byte aligned)
+    unsigned ad0[kFlatRow];
+#pragma unroll
+    for (int k = 0; k < kFlatRow; ++k) ad0[k] = off[k] + ((unsigned)(gx[k] * ESZ) & 15u);
     int slot = 0;
     unsigned par = 0, so = 0;
+    const size_t dl = (size_t)a.dstLev;
     for (int f = 0; f < a.nfields; ++f) {
         const FieldDev &fd = fp.f[f];
         TOUT *__restrict__ d = (TOUT *)fd.dst + a.dstOff + t;
         const int eop = fd.epi_op;
         const TACC earg = (TACC)fd.epi_arg;
-        // + the window's alignment shift (the same at every level: planes are a multiple of 16 bytes apart)
-        unsigned ad0[kFlatRow];
-#pragma unroll
-        for (int k = 0; k < kFlatRow; ++k) ad0[k] = off[k] + ((unsigned)((uintptr_t)fd.src + gx[k] * ESZ) & 15u);
+        const bool lean = fullTile && eop == 0;
         for (int l0 = 0; l0 < fd.nlev; l0 += kPlLev) {
             const int nl = fd.nlev - l0;
             mbar_wait(s_full + slot, par);
@@ -264,7 +270,21 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + slot);   // this warp holds the stage in registers: refill it
             if (++slot == kPlStages) { slot = 0; so = 0; par ^= 1u; } else so += STB;
-            if (store) {
+            if (lean && nl >= kPlLev) {
+                // the common case, straight line: every lane of the tile mapped, a full stage, no epilogue
+                TACC acc[kPlLev];
+#pragma unroll
+                for (int l = 0; l < kPlLev; ++l) {
+                    acc[l] = 0;
+#pragma unroll
+                    for (int k = 0; k < kFlatRow; ++k) acc[l] += w[k] * (TACC)x[l][k];
+                }
+                if (store) {
+#pragma unroll
+                    for (int l = 0; l < kPlLev; ++l) st_stream(d + l * dl, (TOUT)acc[l]);
+                }
+                d += kPlLev * dl;
+            } else if (store) {
                 TACC acc[kPlLev];
 #pragma unroll
                 for (int l = 0; l < kPlLev; ++l) {

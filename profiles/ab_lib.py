@@ -51,13 +51,18 @@ def main():
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--only", default="")
     ap.add_argument("--rounds", type=int, default=2)
+    ap.add_argument("--planes", action="store_true", help="A/B the grid-source (centre -> EDGE1) apply instead of the column apply")
     args = ap.parse_args()
     wl = workload.make("c2", cell_order=args.order)
     m = wl.mesh
     levs = [int(a.split("x")[0]) for a in args.stack.split(",") for _ in range(int(a.split("x")[1]))]
     n = m.nCells
-    srcs = [torch.randn((n, L_), device="cuda") for L_ in levs]
-    dsts = [torch.empty((L_, wl.n_mass), device="cuda") for L_ in levs]
+    if args.planes:
+        srcs = [torch.randn((L_, wl.n_mass), device="cuda") for L_ in levs]
+        dsts = [torch.empty((L_, wl.grids["U"][0].size), device="cuda") for L_ in levs]
+    else:
+        srcs = [torch.randn((n, L_), device="cuda") for L_ in levs]
+        dsts = [torch.empty((L_, wl.n_mass), device="cuda") for L_ in levs]
     torch.cuda.synchronize()
     peak = 6450.0
     try:
@@ -86,7 +91,13 @@ def main():
         ca, sa = np.ascontiguousarray(wl.cosa), np.ascontiguousarray(wl.sina)
         ck(L.mprg_set_rotation(ctx, ca.ctypes.data, sa.ctypes.data))
         rh = C.c_void_p()
-        ck(L.mprg_store(ctx, 0, 0, 0, C.byref(rh)))
+        if args.planes:
+            ulat, ulon = wl.grids["U"]
+            ulon, ulat = np.ascontiguousarray(ulon), np.ascontiguousarray(ulat)
+            ck(L.mprg_set_target(ctx, 1, ulon.shape[1], ulon.shape[0], ulon.ctypes.data, ulat.ctypes.data))
+            ck(L.mprg_store(ctx, 0, 2, 1, C.byref(rh)))      # BILINEAR, SRC_GRID_CENTER, EDGE1
+        else:
+            ck(L.mprg_store(ctx, 0, 0, 0, C.byref(rh)))
         ctxs[name] = (L, ctx, rh, ck)
     k = len(levs)
     sp = (C.c_void_p * k)(*[t.data_ptr() for t in srcs])
