@@ -292,20 +292,13 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
     // evenly over all warps instead of queuing behind the first two.  The list is in ascending id order and columns
     // of consecutive ids are contiguous in memory, so the owner of the first slot of a run fetches the whole run
     // with one bulk copy (brun = its length in columns, 0 for the other slots of the run).
-    // (the column id itself is re-read from the record by the few lanes that issue a copy: it is not worth a register
-    // -- at the 48-register cap it was spilled and reloaded by every lane in every unit)
     const int bslot = lane * kPipeWarps + warp;
-    const bool bhas = bslot < nu;
+    const int bcol = bslot < nu ? s_uniq[bslot] : -1;
     int brun = 0;
-    if (bhas) {
+    if (bcol >= 0) {
         const int r = s_urun[bslot];
         if ((int)s_runFirst[r] == bslot) brun = (((int)s_runFirst[r + 1] - bslot - 1) & 0xff) + 1;   // (1..256: the sentinel is nu mod 256)
     }
-    auto col_of_slot = [&]() -> size_t {
-        int c;
-        asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(c) : "r"((unsigned)__cvta_generic_to_shared(s_uniq + bslot)));
-        return (size_t)c;
-    };
 
     // Two phases in one launch.  Phase A: the first a.nPlain units are plain aligned fields -- the bulk of every
     // pass -- and run the leanest code (one barrier arrival per unit, 16-byte loads only).  Phase B: wind pairs and
@@ -323,11 +316,12 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         const bool packed = merged && (chunkB & 127u);
         if (u < nA2) {
             unsigned long long *bar = s_mbar + (u % kPipeStages);
+            const char *g = (const char *)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
             if (tid == 0) mbar_arrive_tx(bar, chunkB * (unsigned)nu);   // one arrival posts the unit's bytes
-            if (packed ? brun > 0 : bhas) {
-                const char *g = (const char *)ud.src + (col_of_slot() * ud.nlev + ud.L0) * ESZ;
-                if (packed) bulk_g2s(sbase + bslot * chunkB, g, chunkB * (unsigned)brun, bar);
-                else bulk_g2s(sbase + bslot * (chunkB + 16u), g, chunkB, bar);
+            if (packed) {
+                if (brun > 0) bulk_g2s(sbase + bslot * chunkB, g, chunkB * (unsigned)brun, bar);
+            } else if (bcol >= 0) {
+                bulk_g2s(sbase + bslot * (chunkB + 16u), g, chunkB, bar);
             }
             return;
         }
@@ -337,18 +331,18 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         unsigned nb = 0, sdst = 0;
         uintptr_t ga = 0;
         if (!UNAL || (ud.flags & kUnitAligned)) {
-            if (packed ? brun > 0 : bhas) {
+            if (packed ? brun > 0 : bcol >= 0) {
                 nb = packed ? chunkB * (unsigned)brun : chunkB;
                 sdst = sbase + bslot * (packed ? chunkB : chunkB + 16u);
-                ga = (uintptr_t)ud.src + (col_of_slot() * ud.nlev + ud.L0) * ESZ;
+                ga = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
             }
-        } else if (merged ? brun > 0 : bhas) {
+        } else if (merged ? brun > 0 : bcol >= 0) {
             // unaligned columns: the 16-byte-aligned window around the run (or the single column chunk); it lands at
             // a 16-byte-aligned address chosen so that windows never overlap, and the math reads it where it lies.
             // (absolute addresses: the source base itself need only be element-aligned; device allocations are
             // 256-byte aligned, so the window's first 16-byte chunk always lies inside the caller's allocation)
             const int ncol = merged ? brun : 1, r = merged ? (int)s_urun[bslot] : bslot;
-            const uintptr_t a0 = (uintptr_t)ud.src + (col_of_slot() * ud.nlev + ud.L0) * ESZ;
+            const uintptr_t a0 = (uintptr_t)ud.src + ((size_t)bcol * ud.nlev + ud.L0) * ESZ;
             const uintptr_t aend = (uintptr_t)ud.src + ud.srcBytes;
             ga = a0 & ~(uintptr_t)15;
             size_t n = ((a0 + (size_t)(ncol - 1) * ud.nlev * ESZ + chunkB + 15) & ~(uintptr_t)15) - ga;
