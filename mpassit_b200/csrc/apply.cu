@@ -507,6 +507,7 @@ static bool launch_pipe(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fi
     pa.lay = lay;
     pa.nDst = r->nDst;
     pa.dstLev = dl.lev; pa.dstOff = dl.off;
+    pa.dstLev32 = (uint32_t)dl.lev;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
     pa.rotc = nullptr;
@@ -896,6 +897,7 @@ static void launch_wind(mprg_ctx *ctx, const mprg_route *r, const void *u, const
     PipeArgs<TACC> pa;
     pa.rec = rec; pa.lay = lay; pa.nDst = r->nDst;
     pa.dstLev = dl.lev; pa.dstOff = dl.off;
+    pa.dstLev32 = (uint32_t)dl.lev;
     pa.ni = r->dstNi;
     pa.tilesPerRow = (r->dstNi + kPipeTile - 1) / kPipeTile;
     pa.rotc = nullptr;

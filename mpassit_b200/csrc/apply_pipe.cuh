@@ -117,6 +117,7 @@ struct PipeArgs {
     // rank's own, or the writing rank's mapped over NVLink: the gather fused into the store) has
     // dstLev = ni * nj, dstOff = first owned point.
     int64_t dstLev, dstOff;
+    uint32_t dstLev32;  // = dstLev (always < 2^31: rows are indexed with int32): level offsets are one 32 x 32 -> 64 multiply
     int32_t ni;         // destination row length (tiles never straddle rows)
     int32_t tilesPerRow;
     int32_t nunits;
@@ -363,7 +364,8 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
         if (nb) bulk_g2s(sdst, (const void *)ga, nb, bar);
     };
 
-    const size_t grp8 = (size_t)(4 * kPipeWarps) * (size_t)a.dstLev;  // elements between a warp's consecutive level groups
+    const size_t dlev = a.dstLev32;                              // elements between consecutive levels of a destination field
+    const size_t grp8 = (size_t)(4 * kPipeWarps) * dlev;          // elements between a warp's consecutive level groups
 
     // the reduction of one unit; UN / RT: compile-time content of the phase the unit belongs to
     auto math = [&](int u, auto UN_c, auto RT_c) {
@@ -388,7 +390,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                          : "r"(row0 + (unsigned)(2 * kCmpRow * sizeof(TACC))));
             const int clen = (int)sl[3];
             const unsigned cstride = ((ud.flags & kUnitMerged) && (((unsigned)Ln * ESZ) & 127u)) ? (unsigned)Ln * ESZ : (unsigned)Ln * ESZ + 16u;
-            TOUT *d = (TOUT *)ud.dst + ((size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane);
+            TOUT *d = (TOUT *)ud.dst + ((size_t)(unsigned)(ud.L0 + 4 * warp) * dlev + a.dstOff + t0 + lane);
 #pragma unroll
             for (int gi = 0; gi < kPipeLev / 4 / kPipeWarps; ++gi, d += grp8) {
                 const int g = warp + gi * kPipeWarps;
@@ -407,7 +409,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (4 * g + k < Ln) __stcs(d + (size_t)k * a.dstLev, (TOUT)acc[k]);
+                    if (4 * g + k < Ln) __stcs(d + (size_t)k * dlev, (TOUT)acc[k]);
             }
             return;
         }
@@ -447,7 +449,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             }
         }
         // this lane's output column: level L0 + 4 * warp of target t0 + lane; groups are 8 * 4 levels apart
-        const size_t dcol = (size_t)(ud.L0 + 4 * warp) * a.dstLev + a.dstOff + t0 + lane;
+        const size_t dcol = (size_t)(unsigned)(ud.L0 + 4 * warp) * dlev + a.dstOff + t0 + lane;
         TOUT *d = (TOUT *)ud.dst + dcol;
         const bool rotU = RT && (ud.flags & kUnitRotU), rotV = RT && (ud.flags & kUnitRotV);
 #pragma unroll
@@ -501,8 +503,8 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
                     uu = (uu + vv * c[1]) * c[3];
                     vv = (vv - uu * c[0]) * c[2];
                     if (4 * g + k < Ln) {
-                        __stcs(du + (size_t)k * a.dstLev, (TOUT)uu);
-                        __stcs(d + (size_t)k * a.dstLev, (TOUT)vv);
+                        __stcs(du + (size_t)k * dlev, (TOUT)uu);
+                        __stcs(d + (size_t)k * dlev, (TOUT)vv);
                     }
                 }
                 continue;
@@ -513,7 +515,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             }
             // one coalesced 128-byte (fp32) streaming store per level
             if (4 * g + 3 < Ln) {
-                TOUT *d1 = d + a.dstLev, *d2 = d1 + a.dstLev, *d3 = d2 + a.dstLev;
+                TOUT *d1 = d + dlev, *d2 = d1 + dlev, *d3 = d2 + dlev;
                 __stcs(d, (TOUT)acc[0]);
                 __stcs(d1, (TOUT)acc[1]);
                 __stcs(d2, (TOUT)acc[2]);
@@ -521,7 +523,7 @@ k_apply_pipe(PipeArgs<TACC> a, const __grid_constant__ UnitPack up) {
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (4 * g + k < Ln) __stcs(d + (size_t)k * a.dstLev, (TOUT)acc[k]);
+                    if (4 * g + k < Ln) __stcs(d + (size_t)k * dlev, (TOUT)acc[k]);
             }
         }
     };
