@@ -44,6 +44,7 @@ struct ApplyArgs {
     const TW *w;
     int64_t nDst;
     int64_t dstLev, dstOff;  // dst[l * dstLev + dstOff + t]: slab buffer (nDst, 0) or full-grid field (see PipeArgs)
+    uint32_t dstLev32;       // = dstLev (< 2^31): level offsets are one 32 x 32 -> 64 multiply
     int32_t nfields;
     int64_t srcPlane;  // k_apply_planes only
 };
@@ -698,6 +699,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     if (sizeof(TACC) == 8) a.w = (const TACC *)r->w.p; else a.w = (const TACC *)r->w32.p;
     a.nDst = r->nDst;
     a.dstLev = dl.lev; a.dstOff = dl.off;
+    a.dstLev32 = (uint32_t)dl.lev;
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
     // field-descriptor kernels take their fields kPackFields at a time, as a kernel parameter

@@ -250,7 +250,7 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
     for (int k = 0; k < kFlatRow; ++k) ad0[k] = off[k] + ((unsigned)(gx[k] * ESZ) & 15u);
     int slot = 0;
     unsigned par = 0, so = 0;
-    const size_t dl = (size_t)a.dstLev;
+    const size_t dl = a.dstLev32;
     for (int f = 0; f < a.nfields; ++f) {
         const FieldDev &fd = fp.f[f];
         TOUT *__restrict__ d = (TOUT *)fd.dst + a.dstOff + t;
@@ -300,10 +300,10 @@ k_apply_planes_pipe(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp, Pla
 #pragma unroll
                 for (int l = 0; l < kPlLev; ++l) {
                     if (l < nl) st_stream(d, (TOUT)acc[l]);
-                    d += a.dstLev;
+                    d += dl;
                 }
             } else {
-                d += (size_t)kPlLev * a.dstLev;
+                d += (size_t)kPlLev * dl;
             }
         }
     }
