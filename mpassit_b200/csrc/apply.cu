@@ -45,6 +45,7 @@ struct ApplyArgs {
     int64_t nDst;
     int64_t dstLev, dstOff;  // dst[l * dstLev + dstOff + t]: slab buffer (nDst, 0) or full-grid field (see PipeArgs)
     uint32_t dstLev32;       // = dstLev (< 2^31): level offsets are one 32 x 32 -> 64 multiply
+    int32_t uniformRow;      // > 0: every row has exactly this many entries (row t starts at t * uniformRow): no row-pointer load
     int32_t nfields;
     int64_t srcPlane;  // k_apply_planes only
 };
@@ -258,7 +259,10 @@ __global__ void __launch_bounds__(256, sizeof(TACC) == 4 ? 6 : 4)
 k_apply_flat(ApplyArgs<TACC> a, const __grid_constant__ FieldPack fp) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nDst) return;
-    const int b = __ldg(a.rowptr + t), e = __ldg(a.rowptr + t + 1);
+    // (a fully mapped bilinear / nearest route: the row pointer is t * row length -- one dependent load less in a
+    // latency-bound kernel)
+    const int b = a.uniformRow ? (int)t * a.uniformRow : __ldg(a.rowptr + t);
+    const int e = a.uniformRow ? b + a.uniformRow : __ldg(a.rowptr + t + 1);
     int c[kFlatRow];
     TACC w[kFlatRow];
 #pragma unroll
@@ -700,6 +704,7 @@ static bool launch_all(mprg_ctx *ctx, const mprg_route *r, const std::vector<Fie
     a.nDst = r->nDst;
     a.dstLev = dl.lev; a.dstOff = dl.off;
     a.dstLev32 = (uint32_t)dl.lev;
+    a.uniformRow = (r->uniform && r->nUnmapped == 0 && r->maxRow > 0 && r->nnz == r->nDst * r->maxRow) ? r->maxRow : 0;
     a.srcPlane = r->srcPlane;
     const unsigned tiles = (unsigned)((r->nDst + kTile - 1) / kTile);
     // field-descriptor kernels take their fields kPackFields at a time, as a kernel parameter
