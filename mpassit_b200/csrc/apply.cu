@@ -799,6 +799,7 @@ void apply_device(mprg_ctx *ctx, const mprg_route *r, const ApplyField *fields, 
         dl.lev = (int64_t)tg.ni * tg.nj;
         dl.off = tg.slabOffset();
     }
+    if (dl.lev >= ((int64_t)1 << 32)) fail(40, "mprg_apply: destination level stride %lld does not fit 32 bits", (long long)dl.lev);
     std::vector<FieldDev> cols, rots, flat, planes;   // cols: plain 3-D fields; rots: wind pairs (appended to cols)
     std::vector<std::pair<void *, void *>> pairs;  // every (u, v) destination pair with fused rotation requested
     std::vector<int32_t> pair_nlev;
