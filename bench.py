@@ -88,7 +88,10 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
         names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 # the remaining NVML reason bits, so that a clock below max is never reported without its cause
+                 ("hw_power_brake_slowdown", 0x80), ("sync_boost", 0x10), ("applications_clocks_setting", 0x2),
+                 ("display_clock_setting", 0x100))
         # samples inside the timed region; a region shorter than a few NVML calls falls back to the
         # samples of the warm-up passes right before it (same kernels, same load)
         inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= self.t1]
@@ -100,7 +103,7 @@ class ClockSampler:
         thr = 0.5 * (min(pw) + max(pw))     # under load = samples in the upper half of the power range seen
         load = [c for _, c, p, _ in use if p >= thr] or [c for _, c, _, _ in use]
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": self.max_mhz,
-                "reasons": [n for n, bit in names if mask & bit], "samples": len(use),
+                "reasons": [n for n, bit in names if mask & bit], "reasons_mask": hex(mask & ~0x1), "samples": len(use),
                 "samples_in_timed_region": len(inside), "power_w_max": max(pw)}
 
 
